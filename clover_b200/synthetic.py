@@ -1,0 +1,86 @@
+"""Deterministic synthetic weights and batches (numpy PCG64 streams keyed by tensor name).
+
+The reference has no datasets or checkpoints reachable offline, so every test, golden vector and
+bench run uses random-init weights and synthetic clips/captions of the shapes in SURVEY.md 8(d).
+numpy's default_rng stream is stable across platforms and versions, so the same (name, seed) gives
+bit-identical tensors in the build container and on the GPU box.
+"""
+import zlib
+
+import numpy as np
+import torch
+
+CLS, SEP, MASK, PAD = 101, 102, 103, 0
+
+
+def _rng(name, seed):
+    return np.random.default_rng([zlib.crc32(name.encode()), seed])
+
+
+def named_tensor(name, shape, seed=0, dtype=torch.float32):
+    """LayerNorm-like weights ~ 1 + 0.1 N(0,1); biases / tables ~ 0.02 N(0,1); matrices ~ N(0, 1/fan_in) (capped)."""
+    shape = tuple(shape)
+    r = _rng(name, seed)
+    leaf = name.rsplit(".", 1)[-1]
+    x = r.standard_normal(shape, dtype=np.float32)
+    is_norm = any(t in name for t in ("norm", "LayerNorm", "_bn", "img_projector.1.", "img_projector.4.",
+                                      "vqa_classifier.2.", "mc_vqa_classifier.2."))
+    if is_norm and leaf == "weight" and len(shape) == 1:
+        x = 1.0 + 0.1 * x
+    elif len(shape) >= 2 and leaf == "weight" and "embeddings" not in name:
+        fan_in = int(np.prod(shape[1:]))
+        x = x * min(0.08, 1.0 / np.sqrt(fan_in)) * 1.5
+    elif "relative_position_bias_table" in name:
+        x = x * 0.5
+    else:
+        x = x * 0.05
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dtype)
+
+
+def synth_state_dict(shapes, seed=0):
+    """shapes: mapping name -> shape (or a module's state_dict()).  Integer buffers are left out."""
+    out = {}
+    for k, v in shapes.items():
+        if hasattr(v, "shape"):
+            if not torch.is_floating_point(v):
+                continue
+            v = v.shape
+        out[k] = named_tensor(k, v, seed)
+    return out
+
+
+def make_batch(B, frames=8, L=32, seed=1, size=224, vocab=30522, mask_cells=10, grid=7):
+    """Synthetic pre-training batch with the reference's input contract:
+    imgs (B,1,3,F,size,size) ~ N(0,1); token_ids/input_mask/segment_ids/mlm_label (B,1,L) int64;
+    v_token_mask (B,1,grid,grid) int64 with a block of ~mask_cells ones."""
+    r = np.random.default_rng([seed, 77])
+    imgs = r.standard_normal((B, 1, 3, frames, size, size), dtype=np.float32)
+    tok = np.zeros((B, 1, L), dtype=np.int64)
+    lab = np.full((B, 1, L), -100, dtype=np.int64)
+    lo = min(1000, vocab // 2)
+    for b in range(B):
+        n = int(r.integers(min(8, L - 2), L - 1))
+        ids = r.integers(lo, vocab - 1, size=n)
+        tok[b, 0, 0] = CLS if vocab > CLS else 1
+        tok[b, 0, 1:1 + n] = ids
+        tok[b, 0, 1 + n] = SEP if vocab > SEP else 2
+        k = max(1, int(round(0.3 * n)))
+        pos = r.permutation(n)[:k] + 1
+        lab[b, 0, pos] = tok[b, 0, pos]
+        tok[b, 0, pos] = MASK if vocab > MASK else 3
+    vm = np.zeros((B, 1, grid, grid), dtype=np.int64)
+    for b in range(B):
+        h = 2
+        w = max(1, mask_cells // h)
+        y0 = int(r.integers(0, grid - h + 1))
+        x0 = int(r.integers(0, grid - w + 1))
+        vm[b, 0, y0:y0 + h, x0:x0 + w] = 1
+    return {
+        "imgs": torch.from_numpy(imgs),
+        "label": torch.zeros(B),
+        "token_ids": torch.from_numpy(tok),
+        "input_mask": torch.from_numpy((tok != 0).astype(np.int64)),
+        "segment_ids": torch.zeros(B, 1, L, dtype=torch.long),
+        "mlm_label": torch.from_numpy(lab),
+        "v_token_mask": torch.from_numpy(vm),
+    }
