@@ -1,0 +1,230 @@
+// Shared device helpers for the clover_b200 kernels (sm_100a only).
+// PTX wrappers for mbarrier / TMA / tcgen05, warp reductions, bf16 packing and the closed-form
+// window index maps of the Video Swin backbone (reference
+// mmaction/models/backbones/swin_transformer_3d.py:271-299,460,474).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CLV_DEVICE __device__ __forceinline__
+
+namespace clv {
+
+// ------------------------------------------------------------------------------------------
+// error slot (thread-local, read through clv_last_error())
+// ------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+// call right after every kernel launch: counts it (clv_launch_count) and reports launch errors
+int after_launch(const char* what);
+
+#define CLV_CHECK_CUDA(expr)                                   \
+  do {                                                         \
+    int _e = ::clv::check_cuda((expr), #expr);                 \
+    if (_e) return _e;                                         \
+  } while (0)
+
+#define CLV_REQUIRE(cond, ...)                                 \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      ::clv::set_error(__VA_ARGS__);                           \
+      return 1;                                                \
+    }                                                          \
+  } while (0)
+
+int num_sms();
+
+// ------------------------------------------------------------------------------------------
+// small math
+// ------------------------------------------------------------------------------------------
+CLV_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+CLV_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+CLV_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx [0.5 x (1+erf(x/sqrt2))] = 0.5(1+erf(x/sqrt2)) + x * exp(-x^2/2)/sqrt(2pi)
+CLV_DEVICE float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+CLV_DEVICE uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+CLV_DEVICE float2 unpack_bf16(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// window geometry: fused cyclic roll + window_partition and its inverse, with zero padding.
+// Frame (Dp,Hp,Wp) is the padded extent; (D,H,W) the real one.
+// ------------------------------------------------------------------------------------------
+struct WindowGeom {
+  int B, D, H, W;        // real extent
+  int Dp, Hp, Wp;        // padded to window multiples
+  int wd, wh, ww;        // clamped window
+  int sd, sh, sw;        // clamped shift
+  int nD, nH, nW;        // windows per axis
+  int N;                 // tokens per window
+  int nWin;              // windows per clip
+};
+
+// window-order row r -> source spatial row (or -1 when the token lies in the zero padding).
+CLV_DEVICE long long window_row_to_src(const WindowGeom& g, long long r) {
+  int n = (int)(r % g.N);
+  long long gi = r / g.N;
+  int win = (int)(gi % g.nWin);
+  int b = (int)(gi / g.nWin);
+  int bw = win % g.nW, bh = (win / g.nW) % g.nH, bd = win / (g.nW * g.nH);
+  int lw = n % g.ww, lh = (n / g.ww) % g.wh, ld = n / (g.ww * g.wh);
+  int d = bd * g.wd + ld + g.sd; if (d >= g.Dp) d -= g.Dp;
+  int h = bh * g.wh + lh + g.sh; if (h >= g.Hp) h -= g.Hp;
+  int w = bw * g.ww + lw + g.sw; if (w >= g.Wp) w -= g.Wp;
+  if (d >= g.D || h >= g.H || w >= g.W) return -1;
+  return (((long long)b * g.D + d) * g.H + h) * g.W + w;
+}
+
+// source spatial row s -> window-order row (always valid: every real token lives in one window).
+CLV_DEVICE long long src_row_to_window(const WindowGeom& g, long long s) {
+  int w = (int)(s % g.W); long long t = s / g.W;
+  int h = (int)(t % g.H); t /= g.H;
+  int d = (int)(t % g.D); int b = (int)(t / g.D);
+  int d2 = d - g.sd; if (d2 < 0) d2 += g.Dp;
+  int h2 = h - g.sh; if (h2 < 0) h2 += g.Hp;
+  int w2 = w - g.sw; if (w2 < 0) w2 += g.Wp;
+  int bd = d2 / g.wd, ld = d2 % g.wd;
+  int bh = h2 / g.wh, lh = h2 % g.wh;
+  int bw = w2 / g.ww, lw = w2 % g.ww;
+  long long win = ((long long)b * g.nD + bd) * g.nH * g.nW + (long long)bh * g.nW + bw;
+  return win * g.N + (ld * g.wh + lh) * g.ww + lw;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / TMA / tcgen05 PTX wrappers
+// ------------------------------------------------------------------------------------------
+CLV_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+CLV_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+CLV_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+CLV_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+CLV_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+CLV_DEVICE void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+CLV_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (sticky launch error) instead of hanging the GPU.
+CLV_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 0xFFF) == 0 && clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+
+CLV_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2D tiled TMA load global -> shared, completion on mbarrier (bytes).
+CLV_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+CLV_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+CLV_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Warp-collective.  Writes the TMEM base address to *smem_slot.
+CLV_DEVICE void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+CLV_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; single thread issues.
+CLV_DEVICE void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed.
+CLV_DEVICE void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread = lane/row).
+CLV_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+CLV_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B).
+CLV_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation
+// (cute::UMMA::InstrDescriptor): c_format[4,6)=1, a_format[7,10)=1, b_format[10,13)=1,
+// a_major bit15, b_major bit16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+CLV_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+}  // namespace clv

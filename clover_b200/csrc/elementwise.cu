@@ -1,0 +1,220 @@
+// HBM-bound helper kernels of the Clover hot path: casts, im2col-free patchify for PatchEmbed3D,
+// grouped column sums (bias / positional-embedding gradients, average pooling), row copies with an
+// affine term (fusion concat), broadcast adds and embedding-gradient scatter.
+#include <algorithm>
+
+#include "common.cuh"
+#include "clover_b200.h"
+
+namespace clv {
+
+CLV_DEVICE float4 ldv4(const void* base, int is_bf16, long long off) {
+  if (is_bf16) {
+    uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+}
+CLV_DEVICE void stv4(void* base, int is_bf16, long long off, float4 v) {
+  if (is_bf16)
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  else
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_kernel(const void* src, int src_bf16, void* dst, int dst_bf16, long long n4, float scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = ldv4(src, src_bf16, i * 4);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    stv4(dst, dst_bf16, i * 4, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PatchEmbed3D as a GEMM (swin_transformer_3d.py:665,671-681): Conv3d with kernel == stride is a
+// [tokens, Cin*pd*ph*pw] x [Cin*pd*ph*pw, C] product.  One CTA stages the Cin*pd*ph input rows of
+// one token row (b, d, hp) through shared memory (coalesced reads) and writes the patch matrix
+// rows (column order (c, kd, kh, kw) = the conv weight's flattening) with coalesced bf16 stores.
+// Out-of-range input (the F.pad of :675-680) reads as zero.
+__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Cin, int F,
+                                int H, int W, int pd, int ph, int pw, int D, int Hp, int Wp) {
+  extern __shared__ float tile[];            // [Cin*pd*ph][Wp*pw]
+  const int hp = blockIdx.x % Hp, d = (blockIdx.x / Hp) % D, b = blockIdx.x / (Hp * D);
+  const int nrow = Cin * pd * ph, roww = Wp * pw;
+  for (int i = threadIdx.x; i < nrow * roww; i += blockDim.x) {
+    const int r = i / roww, col = i % roww;
+    const int kh = r % ph, kd = (r / ph) % pd, c = r / (ph * pd);
+    const int f = d * pd + kd, h = hp * ph + kh;
+    float v = 0.f;
+    if (f < F && h < H && col < W) v = x[(((long long)b * Cin + c) * F + f) * H * W + (long long)h * W + col];
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int K = nrow * pw;
+  const long long row0 = ((long long)(b * D + d) * Hp + hp) * Wp;
+  for (int i = threadIdx.x; i < Wp * K / 2; i += blockDim.x) {
+    const int e = i * 2;
+    const int wp = e / K, k = e % K;          // k even; pw even => both elements share (c,kd,kh)
+    const int r = k / pw, kw = k % pw;
+    const float v0 = tile[r * roww + wp * pw + kw];
+    const int k1 = k + 1, r1 = k1 / pw, kw1 = k1 % pw;
+    const float v1 = tile[r1 * roww + wp * pw + kw1];
+    *reinterpret_cast<uint32_t*>(out + (row0 + wp) * K + k) = pack_bf16(v0, v1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[g, c] (+)= scale * sum over rows r with (r / div) % mod == g of x[r, c].
+// grid = (col tiles of 128, row chunks, mod).  Used for nn.Linear bias gradients (mod = 1),
+// AdaptiveAvgPool3d of ssl_head.py:105 (groups = clips), and the gradients of vis_space_pos /
+// vis_tempor_pos / BERT position embeddings.
+__global__ void grouped_colsum_kernel(const void* x, int x_bf16, long long ld, long long rows, int C, int div, int mod,
+                                      float scale, float* out) {
+  const int g = blockIdx.z;
+  const int c4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+  const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // rows of group g: r = (q*mod + g)*div + t
+  const long long full = rows / ((long long)div * mod);                 // complete periods
+  const long long rem = rows - full * div * mod;
+  long long in_group = full * div;
+  {
+    const long long start = (long long)g * div;
+    if (rem > start) in_group += min((long long)div, rem - start);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < C) {
+    for (long long k = (long long)blockIdx.y * nw + wib; k < in_group; k += (long long)gridDim.y * nw) {
+      const long long r = ((k / div) * mod + g) * div + (k % div);
+      const float4 v = ldv4(x, x_bf16, r * ld + c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  __shared__ float4 red[8][32];
+  red[wib][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (wib == 0 && c4 < C) {
+    for (int w = 1; w < nw; ++w) {
+      const float4 v = red[w][threadIdx.x];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* o = out + (long long)g * C + c4;
+    atomicAdd(o + 0, acc.x * scale); atomicAdd(o + 1, acc.y * scale);
+    atomicAdd(o + 2, acc.z * scale); atomicAdd(o + 3, acc.w * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y[orow(r), :] = x[irow(r), :] + add0 + bvec[(r / bdiv), :] * bscale
+// with grouped row maps  row(r) = (r / group_rows) * group_stride + r % group_rows + offset.
+struct RowsAffineArgs {
+  const void* x; int x_bf16; long long ld_x; long long in_group_rows, in_group_stride, in_offset;
+  void* y; int y_bf16; long long ld_y; long long out_group_rows, out_group_stride, out_offset;
+  const float* add0; const float* bvec; long long bdiv; float bscale;
+  long long rows; int C;
+};
+__global__ void rows_affine_kernel(RowsAffineArgs a) {
+  const int nvec = a.C / 4;
+  const long long total = a.rows * nvec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / nvec; const int c = (int)(i % nvec) * 4;
+    const long long ir = a.in_group_rows > 0 ? (r / a.in_group_rows) * a.in_group_stride + r % a.in_group_rows + a.in_offset : r;
+    const long long orow = a.out_group_rows > 0 ? (r / a.out_group_rows) * a.out_group_stride + r % a.out_group_rows + a.out_offset : r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.x) v = ldv4(a.x, a.x_bf16, ir * a.ld_x + c);
+    if (a.add0) { const float4 t = *reinterpret_cast<const float4*>(a.add0 + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    if (a.bvec) {
+      const float4 t = *reinterpret_cast<const float4*>(a.bvec + (r / a.bdiv) * a.C + c);
+      v.x += t.x * a.bscale; v.y += t.y * a.bscale; v.z += t.z * a.bscale; v.w += t.w * a.bscale;
+    }
+    stv4(a.y, a.y_bf16, orow * a.ld_y + c, v);
+  }
+}
+
+// dst[index[r], :] += src[r, :]   (word-embedding gradient; duplicates allowed -> atomics)
+__global__ void scatter_add_rows_kernel(const float* src, const long long* index, float* dst, long long rows, int C) {
+  const long long total = rows * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / C; const int c = (int)(i % C);
+    atomicAdd(dst + index[r] * C + c, src[i]);
+  }
+}
+
+static int grid_for(long long work, int block) {
+  long long g = (work + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" int clv_cast(const void* src, int src_is_bf16, void* dst, int dst_is_bf16, long long n, float scale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(src && dst && n >= 0 && n % 4 == 0, "clv_cast: n must be a multiple of 4 (got %lld)", n);
+  if (n == 0) return 0;
+  cast_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(src, src_is_bf16, dst, dst_is_bf16, n / 4, scale);
+  return after_launch("cast_kernel");
+}
+
+extern "C" int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int F, int H, int W, int pd, int ph, int pw,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(x && out_bf16 && B > 0 && pw % 2 == 0, "clv_patchify: bad arguments");
+  const int D = (F + pd - 1) / pd, Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
+  const size_t smem = (size_t)Cin * pd * ph * Wp * pw * sizeof(float);
+  CLV_REQUIRE(smem <= 200 * 1024, "clv_patchify: row tile too large (%zu bytes)", smem);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  patchify_kernel<<<B * D * Hp, 256, smem, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, F, H, W, pd, ph,
+                                                    pw, D, Hp, Wp);
+  return after_launch("patchify_kernel");
+}
+
+extern "C" int clv_grouped_colsum(const void* x, int x_is_bf16, long long ld, long long rows, int C, int div, int mod,
+                                  float scale, float* out, int accumulate, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(x && out && C > 0 && C % 4 == 0 && div > 0 && mod > 0, "clv_grouped_colsum: bad arguments");
+  if (!accumulate) CLV_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)mod * C * sizeof(float), stream));
+  if (rows == 0) return 0;
+  const int col_tiles = (C + 127) / 128;
+  const long long per_group = (rows + mod - 1) / mod;
+  long long chunks = (per_group + 63) / 64;
+  const long long cap = std::max<long long>(1, (long long)num_sms() * 8 / ((long long)col_tiles * mod));
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(col_tiles, (unsigned)chunks, mod);
+  grouped_colsum_kernel<<<grid, 256, 0, stream>>>(x, x_is_bf16, ld, rows, C, div, mod, scale, out);
+  return after_launch("grouped_colsum_kernel");
+}
+
+extern "C" int clv_rows_affine(const clv_rows_affine_t* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(d && d->y && d->C > 0 && d->C % 4 == 0, "clv_rows_affine: bad arguments");
+  if (d->rows == 0) return 0;
+  RowsAffineArgs a{};
+  a.x = d->x; a.x_bf16 = d->x_is_bf16; a.ld_x = d->ld_x;
+  a.in_group_rows = d->in_group_rows; a.in_group_stride = d->in_group_stride; a.in_offset = d->in_offset;
+  a.y = d->y; a.y_bf16 = d->y_is_bf16; a.ld_y = d->ld_y;
+  a.out_group_rows = d->out_group_rows; a.out_group_stride = d->out_group_stride; a.out_offset = d->out_offset;
+  a.add0 = d->add0; a.bvec = d->bvec; a.bdiv = d->bdiv > 0 ? d->bdiv : 1; a.bscale = d->bscale;
+  a.rows = d->rows; a.C = d->C;
+  rows_affine_kernel<<<grid_for(a.rows * (a.C / 4), 256), 256, 0, stream>>>(a);
+  return after_launch("rows_affine_kernel");
+}
+
+extern "C" int clv_scatter_add_rows(const float* src, const long long* index, float* dst, long long rows, int C, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(src && index && dst && C > 0, "clv_scatter_add_rows: bad arguments");
+  if (rows == 0) return 0;
+  scatter_add_rows_kernel<<<grid_for(rows * C, 256), 256, 0, stream>>>(src, index, dst, rows, C);
+  return after_launch("scatter_add_rows_kernel");
+}

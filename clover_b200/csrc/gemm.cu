@@ -1,0 +1,374 @@
+// Persistent warp-specialised bf16 GEMM on tcgen05 / TMEM / TMA (sm_100a).
+//
+//   D[M,N] = epilogue( sum_k A[m,k] * B[n,k] )         fp32 accumulation in tensor memory
+//
+// Both operands may be K-major (row-major [rows, K]) or MN-major (stored transposed, [K, rows]),
+// which covers forward (X W^T), dgrad (dY W) and wgrad (dY^T X) of every nn.Linear on the Clover
+// hot path (reference: swin_transformer_3d.py:376,398,263,266,542; HF BertSelfAttention /
+// BertSelfOutput / BertIntermediate / BertOutput denses; heads/ssl_head.py projections) without
+// materialising a transposed copy.  Fused epilogues: bias, q-scale on a column prefix, erf-GELU
+// (optionally also storing the pre-activation), multiply by GELU'(pre) (fc2 dgrad), residual add
+// (fp32 or bf16), window-reverse row scatter (window_reverse + roll back, :471-474), bf16 or fp32
+// output, and split-K with fp32 atomic accumulation for weight gradients.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 =
+// epilogue (TMEM -> registers -> global).  Two TMEM accumulator stages let the epilogue of tile i
+// overlap the mainloop of tile i+1.  Tile 128x128x64, 6 smem stages (192 KB).
+#include <algorithm>
+
+#include "common.cuh"
+#include "clover_b200.h"
+
+namespace clv {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 256;  // 2 accumulator stages x 128 fp32 columns
+
+struct GemmEpi {
+  const float* bias;
+  const void* residual;
+  void* out;
+  __nv_bfloat16* out_pre;
+  const __nv_bfloat16* gelu_pre;
+  long long ld_res, ld_out, ld_pre, ld_gpre;
+  int residual_bf16, out_bf16, act, atomic_out;
+  int scale_cols;
+  float scale;
+  int use_row_map;
+  WindowGeom geom;
+};
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 int M, int N, int K, int k_splits, GemmEpi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_kb = (K + BK - 1) / BK;
+  const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
+  const long long num_tiles = (long long)num_m * num_n * k_splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = (int)(t % k_splits);
+        const long long mn = t / k_splits;
+        const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(num_kb, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (A_MN) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], m_idx * BM, kb * BK);
+            tma_load_2d(sa + A_BYTES / 2, &tma_a, &full_bar[stage], m_idx * BM + 64, kb * BK);
+          } else {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_idx * BM);
+          }
+          if (B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], n_idx * BN, kb * BK);
+            tma_load_2d(sb + B_BYTES / 2, &tma_b, &full_bar[stage], n_idx * BN + 64, kb * BK);
+          } else {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_idx * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int split = (int)(t % k_splits);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(num_kb, kb0 + kb_per_split);
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
+            // MN-major: 16 k-rows = 2 groups of 8 rows x 128 B = 2048 B; 64-element MN chunks BK*128 B apart.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: TMEM lanes (warp % 4) * 32 ... +31 ----------------
+    const int quarter = warp & 3;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const long long mn = t / k_splits;
+      const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m_idx * BM + quarter * 32 + lane;
+      long long drow = row;
+      if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
+      const bool row_ok = row < M && drow >= 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const int n0 = n_idx * BN + c * 32;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (!row_ok || n0 >= N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int ncols = min(32, N - n0);  // multiple of 8 (N % 8 == 0)
+        if (ep.atomic_out) {
+          float* o = reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) atomicAdd(o + j, v[j]);
+          continue;
+        }
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] += __ldg(ep.bias + n0 + j);
+        }
+        if (ep.scale_cols > n0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
+        }
+        if (ep.act == 1) {
+          if (ep.out_pre) {
+            uint4* p = reinterpret_cast<uint4*>(ep.out_pre + row * ep.ld_pre + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q * 8 < ncols)
+                p[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                  pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (ep.gelu_pre) {
+          const uint4* p = reinterpret_cast<const uint4*>(ep.gelu_pre + row * ep.ld_gpre + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q * 8 < ncols) {
+              uint4 u = __ldg(p + q);
+              float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+              v[q * 8 + 0] *= gelu_erf_grad(f0.x); v[q * 8 + 1] *= gelu_erf_grad(f0.y);
+              v[q * 8 + 2] *= gelu_erf_grad(f1.x); v[q * 8 + 3] *= gelu_erf_grad(f1.y);
+              v[q * 8 + 4] *= gelu_erf_grad(f2.x); v[q * 8 + 5] *= gelu_erf_grad(f2.y);
+              v[q * 8 + 6] *= gelu_erf_grad(f3.x); v[q * 8 + 7] *= gelu_erf_grad(f3.y);
+            }
+        }
+        if (ep.residual) {
+          if (ep.residual_bf16) {
+            const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) +
+                                                            drow * ep.ld_res + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q * 8 < ncols) {
+                uint4 u = __ldg(p + q);
+                float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+              }
+          } else {
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) +
+                                                              drow * ep.ld_res + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q * 4 < ncols) {
+                float4 f = __ldg(p + q);
+                v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+              }
+          }
+        }
+        if (ep.out_bf16) {
+          uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q * 8 < ncols)
+              p[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+        } else {
+          float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q * 4 < ncols) p[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dimension `inner` (contiguous), outer `outer`, row pitch ld elements.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
+                      int box_inner, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  CLV_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  CLV_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
+              "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p ld=%lld)", ptr, ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CLV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r, inner,
+              outer, ld);
+  return 0;
+}
+
+template <int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int k_splits,
+                       const GemmEpi& ep, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN>;
+  if (!attr_set) {
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
+  const int grid = (int)std::min<long long>(tiles, num_sms());
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(ta, tb, M, N, K, k_splits, ep);
+  return after_launch("gemm_bf16_kernel launch");
+}
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                             int b_mn_major, int M, int N, int K, const clv_gemm_epilogue_t* e, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(A && B && e && e->out, "clv_gemm_bf16: null pointer");
+  CLV_REQUIRE(M > 0 && N > 0 && K > 0, "clv_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  CLV_REQUIRE(N % 8 == 0, "clv_gemm_bf16: N must be a multiple of 8 (got %d)", N);
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn_major) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BK);
+  else rc = make_tmap_bf16_2d(&ta, A, K, M, lda, BK, BM);
+  if (rc) return rc;
+  if (b_mn_major) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, BK);
+  else rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, BK, BN);
+  if (rc) return rc;
+
+  GemmEpi ep{};
+  ep.bias = e->bias;
+  ep.residual = e->residual;
+  ep.out = e->out;
+  ep.out_pre = reinterpret_cast<__nv_bfloat16*>(e->out_pre);
+  ep.gelu_pre = reinterpret_cast<const __nv_bfloat16*>(e->gelu_pre);
+  ep.ld_res = e->ld_residual; ep.ld_out = e->ld_out; ep.ld_pre = e->ld_pre; ep.ld_gpre = e->ld_gelu_pre;
+  ep.residual_bf16 = e->residual_is_bf16; ep.out_bf16 = e->out_is_bf16; ep.act = e->act;
+  ep.scale_cols = e->scale_cols; ep.scale = e->scale;
+  ep.use_row_map = e->window != nullptr;
+  int k_splits = e->k_splits > 0 ? e->k_splits : 1;
+  const int num_kb = (K + BK - 1) / BK;
+  if (k_splits > num_kb) k_splits = num_kb;
+  {  // every split must own at least one k-block (the kernel's barrier protocol assumes it)
+    const int per = (num_kb + k_splits - 1) / k_splits;
+    k_splits = (num_kb + per - 1) / per;
+  }
+  ep.atomic_out = k_splits > 1 || e->accumulate;
+  if (ep.atomic_out) {
+    CLV_REQUIRE(!e->out_is_bf16 && !e->bias && !e->residual && !e->act && !e->gelu_pre && !e->window,
+                "clv_gemm_bf16: split-K / accumulate supports plain fp32 output only");
+    if (!e->accumulate)
+      CLV_CHECK_CUDA(cudaMemset2DAsync(e->out, e->ld_out * 4, 0, (size_t)N * 4, M, stream));
+  }
+  if (e->window) {
+    const clv_window_geom_t* w = e->window;
+    WindowGeom& g = ep.geom;
+    g.B = w->B; g.D = w->D; g.H = w->H; g.W = w->W; g.wd = w->wd; g.wh = w->wh; g.ww = w->ww;
+    g.sd = w->sd; g.sh = w->sh; g.sw = w->sw;
+    g.Dp = (w->D + w->wd - 1) / w->wd * w->wd; g.Hp = (w->H + w->wh - 1) / w->wh * w->wh;
+    g.Wp = (w->W + w->ww - 1) / w->ww * w->ww;
+    g.nD = g.Dp / g.wd; g.nH = g.Hp / g.wh; g.nW = g.Wp / g.ww; g.N = g.wd * g.wh * g.ww; g.nWin = g.nD * g.nH * g.nW;
+    CLV_REQUIRE((long long)g.B * g.nWin * g.N == M, "clv_gemm_bf16: window geometry does not match M=%d", M);
+  }
+  if (a_mn_major && b_mn_major) return launch_gemm<1, 1>(ta, tb, M, N, K, k_splits, ep, stream);
+  if (a_mn_major) return launch_gemm<1, 0>(ta, tb, M, N, K, k_splits, ep, stream);
+  if (b_mn_major) return launch_gemm<0, 1>(ta, tb, M, N, K, k_splits, ep, stream);
+  return launch_gemm<0, 0>(ta, tb, M, N, K, k_splits, ep, stream);
+}

@@ -1,0 +1,358 @@
+// LayerNorm family (HBM-bound, fp32 statistics), one warp per row, vectorised 128-bit accesses.
+//
+// Forward variants fold the layout work that the reference does with separate full-tensor copies
+// into the load/store of the normalisation itself:
+//   * window gather  : LN(norm1) + F.pad + torch.roll + window_partition
+//                      (swin_transformer_3d.py:450-466, 271-283)  -> bf16 windows (B_,N,C)
+//   * merge gather   : PatchMerging 2x2 strided slices + cat + LN(4C)   (:521-541)
+//   * additive terms : fusion encoder's  + vis_space_pos + vis_tempor_pos + token_type  then LN,
+//                      written straight into the concatenated [video ; text] buffer
+//                      (cross_transformer.py:84-108)
+//   * mask-token blend after the patch-embed LN  (:222-230)
+// Backward mirrors them (scatter instead of gather) and can add the residual-stream gradient and
+// emit a bf16 copy (optionally in window order) for the next GEMM's operand.
+#include "common.cuh"
+#include "clover_b200.h"
+
+namespace clv {
+
+struct LnArgs {
+  const void* x; int x_bf16; long long ld_x;
+  const float* gamma; const float* beta; float eps;
+  void* y; int y_bf16; long long ld_y;
+  float* mean; float* rstd;
+  long long rows; int C;                  // rows = number of OUTPUT rows, C = normalised width
+  int mode;                               // 0 plain, 1 window gather, 2 merge gather
+  WindowGeom geom;                        // mode 1
+  int mB, mD, mH, mW, mC;                 // mode 2: input (B,D,H,W,mC), C == 4*mC
+  const float* add0;                      // [C] broadcast
+  const float* add1; int div1, mod1;      // [mod1, C] indexed (row / div1) % mod1
+  const float* add2; int div2, mod2;
+  long long group_rows, group_stride, row_offset;   // output row = (r / group_rows)*group_stride + r % group_rows + row_offset
+  const long long* blend_mask; const float* blend_token; int bH, bW, mh, mw, bD;   // mask (B,mh,mw) int64
+  const long long* row_index;             // mode 0: source row = row_index[r] (embedding lookup)
+};
+
+CLV_DEVICE float4 ld4(const void* base, int is_bf16, long long elem_off) {
+  if (is_bf16) {
+    uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+}
+CLV_DEVICE void st4(void* base, int is_bf16, long long elem_off, float4 v) {
+  if (is_bf16) {
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) =
+        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off) = v;
+  }
+}
+
+// Source (row, column) of vector `i` (4 elements) of output row r; false for zero padding.
+CLV_DEVICE bool ln_src(const LnArgs& a, long long r, long long src_row, int i, long long& srow, int& col) {
+  if (a.mode == 2) {
+    const int e = i * 4;
+    const int part = e / a.mC;
+    col = e % a.mC;
+    const int W2 = (a.mW + 1) / 2, H2 = (a.mH + 1) / 2;
+    int w2 = (int)(r % W2); long long t = r / W2;
+    int h2 = (int)(t % H2); t /= H2;
+    int d = (int)(t % a.mD); int b = (int)(t / a.mD);
+    // PatchMerging channel blocks: [(even h, even w), (odd h, even w), (even h, odd w), (odd h, odd w)]
+    const int h = 2 * h2 + (part & 1), w = 2 * w2 + (part >> 1);
+    if (h >= a.mH || w >= a.mW) return false;
+    srow = (((long long)b * a.mD + d) * a.mH + h) * a.mW + w;
+    return true;
+  }
+  col = i * 4;
+  srow = src_row;
+  return src_row >= 0;
+}
+
+CLV_DEVICE long long ln_out_row(const LnArgs& a, long long r) {
+  if (a.group_rows > 0) return (r / a.group_rows) * a.group_stride + (r % a.group_rows) + a.row_offset;
+  return r;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = a.C >> 2;
+  const float inv_c = 1.0f / (float)a.C;
+  for (long long r = warp_global; r < a.rows; r += nwarps) {
+    long long src_row = a.row_index ? a.row_index[r] : r;
+    if (a.mode == 1) src_row = window_row_to_src(a.geom, r);
+    const long long orow = ln_out_row(a, r);
+    if (a.mode == 1 && src_row < 0) {  // zero padding is applied AFTER norm1 in the reference
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) st4(a.y, a.y_bf16, orow * a.ld_y + (long long)i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      if (lane == 0 && a.mean) { a.mean[r] = 0.f; a.rstd[r] = 0.f; }
+      continue;
+    }
+    float4 v[VPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = lane + 32 * j;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < nvec) {
+        long long srow; int col;
+        if (ln_src(a, r, src_row, i, srow, col)) v[j] = ld4(a.x, a.x_bf16, srow * a.ld_x + col);
+        if (a.add0) { float4 t = *reinterpret_cast<const float4*>(a.add0 + i * 4); v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w; }
+        if (a.add1) { float4 t = *reinterpret_cast<const float4*>(a.add1 + ((r / a.div1) % a.mod1) * a.C + i * 4); v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w; }
+        if (a.add2) { float4 t = *reinterpret_cast<const float4*>(a.add2 + ((r / a.div2) % a.mod2) * a.C + i * 4); v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w; }
+        sum += v[j].x + v[j].y + v[j].z + v[j].w;
+      }
+    }
+    const float mu = warp_sum(sum) * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float dx = v[j].x - mu, dy = v[j].y - mu, dz = v[j].z - mu, dw = v[j].w - mu;
+        sq += dx * dx + dy * dy + dz * dz + dw * dw;
+      }
+    }
+    const float rs = rsqrtf(warp_sum(sq) * inv_c + a.eps);
+    float bw = 0.f;
+    if (a.blend_mask) {
+      // row r = (b, d, h, w) of the (B, bD, bH, bW) token grid; mask (B, mh, mw)
+      int w_ = (int)(r % a.bW); long long t = r / a.bW;
+      int h_ = (int)(t % a.bH); t /= a.bH;
+      int b_ = (int)(t / a.bD);
+      bw = (float)a.blend_mask[((long long)b_ * a.mh + h_ / (a.bH / a.mh)) * a.mw + w_ / (a.bW / a.mw)];
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(a.gamma + i * 4);
+        const float4 b = *reinterpret_cast<const float4*>(a.beta + i * 4);
+        float4 o;
+        o.x = (v[j].x - mu) * rs * g.x + b.x; o.y = (v[j].y - mu) * rs * g.y + b.y;
+        o.z = (v[j].z - mu) * rs * g.z + b.z; o.w = (v[j].w - mu) * rs * g.w + b.w;
+        if (a.blend_mask) {
+          const float4 tk = *reinterpret_cast<const float4*>(a.blend_token + i * 4);
+          o.x = o.x * (1.f - bw) + tk.x * bw; o.y = o.y * (1.f - bw) + tk.y * bw;
+          o.z = o.z * (1.f - bw) + tk.z * bw; o.w = o.w * (1.f - bw) + tk.w * bw;
+        }
+        st4(a.y, a.y_bf16, orow * a.ld_y + (long long)i * 4, o);
+      }
+    }
+    if (lane == 0 && a.mean) { a.mean[r] = mu; a.rstd[r] = rs; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+struct LnBwdArgs {
+  LnArgs f;                                // forward description (x, gamma, mean, rstd, geometry, adds, blend)
+  const void* dy; int dy_bf16; long long ld_dy;     // indexed by ln_out_row(r)
+  float* dx; long long ld_dx;              // fp32, at the SOURCE rows
+  const float* dres; long long ld_dres;    // optional residual-stream gradient added to dx (source rows)
+  void* dx_copy; int dx_copy_bf16; long long ld_copy;  // optional copy of the final dx
+  int copy_window_map; WindowGeom copy_geom;           // copy row = src_row_to_window(copy_geom, s)
+  float* dgamma; float* dbeta;             // [C] fp32, atomically accumulated (caller zero-fills)
+  float* dtoken;                           // [C] d(mask_token), blend only
+  int dx_dense;                            // write dx (and copy) at row r instead of the source row
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(128) ln_bwd_kernel(LnBwdArgs a) {
+  const LnArgs& f = a.f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = f.C >> 2;
+  const float inv_c = 1.0f / (float)f.C;
+  float4 dg[VPL], db[VPL], dt[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) dg[j] = db[j] = dt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (long long r = warp_global; r < f.rows; r += nwarps) {
+    long long src_row = f.row_index ? f.row_index[r] : r;
+    if (f.mode == 1) {
+      src_row = window_row_to_src(f.geom, r);
+      if (src_row < 0) continue;           // padding rows carry no gradient
+    }
+    const long long orow = ln_out_row(f, r);
+    const float mu = f.mean[r], rs = f.rstd[r];
+    float bw = 0.f;
+    if (f.blend_mask) {
+      int w_ = (int)(r % f.bW); long long t = r / f.bW;
+      int h_ = (int)(t % f.bH); t /= f.bH;
+      int b_ = (int)(t / f.bD);
+      bw = (float)f.blend_mask[((long long)b_ * f.mh + h_ / (f.bH / f.mh)) * f.mw + w_ / (f.bW / f.mw)];
+    }
+    float4 xh[VPL], gy[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = lane + 32 * j;
+      xh[j] = gy[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < nvec) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        long long srow; int col;
+        if (ln_src(f, r, src_row, i, srow, col)) v = ld4(f.x, f.x_bf16, srow * f.ld_x + col);
+        if (f.add0) { float4 t = *reinterpret_cast<const float4*>(f.add0 + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        if (f.add1) { float4 t = *reinterpret_cast<const float4*>(f.add1 + ((r / f.div1) % f.mod1) * f.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        if (f.add2) { float4 t = *reinterpret_cast<const float4*>(f.add2 + ((r / f.div2) % f.mod2) * f.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        xh[j] = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+        float4 d = ld4(a.dy, a.dy_bf16, orow * a.ld_dy + (long long)i * 4);
+        if (f.blend_mask) {
+          dt[j].x += d.x * bw; dt[j].y += d.y * bw; dt[j].z += d.z * bw; dt[j].w += d.w * bw;
+          d.x *= (1.f - bw); d.y *= (1.f - bw); d.z *= (1.f - bw); d.w *= (1.f - bw);
+        }
+        dg[j].x += d.x * xh[j].x; dg[j].y += d.y * xh[j].y; dg[j].z += d.z * xh[j].z; dg[j].w += d.w * xh[j].w;
+        db[j].x += d.x; db[j].y += d.y; db[j].z += d.z; db[j].w += d.w;
+        const float4 g = *reinterpret_cast<const float4*>(f.gamma + i * 4);
+        gy[j] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        s1 += gy[j].x * xh[j].x + gy[j].y * xh[j].y + gy[j].z * xh[j].z + gy[j].w * xh[j].w;
+        s2 += gy[j].x + gy[j].y + gy[j].z + gy[j].w;
+      }
+    }
+    s1 = warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
+    if (!a.dx) continue;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        float4 o;
+        o.x = rs * (gy[j].x - s2 - xh[j].x * s1); o.y = rs * (gy[j].y - s2 - xh[j].y * s1);
+        o.z = rs * (gy[j].z - s2 - xh[j].z * s1); o.w = rs * (gy[j].w - s2 - xh[j].w * s1);
+        long long srow; int col;
+        if (!ln_src(f, r, src_row, i, srow, col)) continue;
+        if (a.dx_dense) srow = r;
+        if (a.dres) {
+          const float4 rr = *reinterpret_cast<const float4*>(a.dres + srow * a.ld_dres + col);
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(a.dx + srow * a.ld_dx + col) = o;
+        if (a.dx_copy) {
+          long long crow = srow;
+          if (a.copy_window_map) crow = src_row_to_window(a.copy_geom, srow);
+          st4(a.dx_copy, a.dx_copy_bf16, crow * a.ld_copy + col, o);
+        }
+      }
+    }
+  }
+
+  // reduce dgamma / dbeta (/ dtoken) across the CTA's warps, then one atomic per column per CTA
+  extern __shared__ float red[];   // [nwarps_in_block][C]
+  const int nw = blockDim.x >> 5;
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? a.dgamma : (pass == 1 ? a.dbeta : a.dtoken);
+    if (!dst) continue;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) *reinterpret_cast<float4*>(red + wib * f.C + i * 4) = pass == 0 ? dg[j] : (pass == 1 ? db[j] : dt[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < f.C; c += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nw; ++w) s += red[w * f.C + c];
+      atomicAdd(dst + c, s);
+    }
+    __syncthreads();
+  }
+}
+
+static void fill_geom(WindowGeom& g, const clv_window_geom_t* w) {
+  g.B = w->B; g.D = w->D; g.H = w->H; g.W = w->W; g.wd = w->wd; g.wh = w->wh; g.ww = w->ww;
+  g.sd = w->sd; g.sh = w->sh; g.sw = w->sw;
+  g.Dp = (w->D + w->wd - 1) / w->wd * w->wd; g.Hp = (w->H + w->wh - 1) / w->wh * w->wh;
+  g.Wp = (w->W + w->ww - 1) / w->ww * w->ww;
+  g.nD = g.Dp / g.wd; g.nH = g.Hp / g.wh; g.nW = g.Wp / g.ww; g.N = g.wd * g.wh * g.ww; g.nWin = g.nD * g.nH * g.nW;
+}
+
+static int build_ln_args(LnArgs& a, const clv_ln_desc_t* d) {
+  CLV_REQUIRE(d && d->x && d->gamma && d->beta, "layernorm: null pointer");
+  CLV_REQUIRE(d->C > 0 && d->C % 4 == 0 && d->C <= 4096, "layernorm: C must be a multiple of 4 and <= 4096 (got %d)", d->C);
+  a = LnArgs{};
+  a.x = d->x; a.x_bf16 = d->x_is_bf16; a.ld_x = d->ld_x;
+  a.gamma = d->gamma; a.beta = d->beta; a.eps = d->eps;
+  a.mean = d->mean; a.rstd = d->rstd; a.rows = d->rows; a.C = d->C;
+  a.mode = 0;
+  if (d->window) { a.mode = 1; fill_geom(a.geom, d->window);
+    CLV_REQUIRE((long long)a.geom.B * a.geom.nWin * a.geom.N == d->rows, "layernorm: window geometry/rows mismatch"); }
+  if (d->merge_C > 0) {
+    CLV_REQUIRE(!d->window, "layernorm: window and merge gathers are exclusive");
+    a.mode = 2; a.mB = d->merge_B; a.mD = d->merge_D; a.mH = d->merge_H; a.mW = d->merge_W; a.mC = d->merge_C;
+    CLV_REQUIRE(d->C == 4 * d->merge_C && d->merge_C % 4 == 0, "layernorm: merge gather needs C == 4*merge_C");
+    CLV_REQUIRE((long long)a.mB * a.mD * ((a.mH + 1) / 2) * ((a.mW + 1) / 2) == d->rows, "layernorm: merge rows mismatch");
+  }
+  a.add0 = d->add0; a.add1 = d->add1; a.div1 = d->div1 > 0 ? d->div1 : 1; a.mod1 = d->mod1 > 0 ? d->mod1 : 1;
+  a.add2 = d->add2; a.div2 = d->div2 > 0 ? d->div2 : 1; a.mod2 = d->mod2 > 0 ? d->mod2 : 1;
+  a.group_rows = d->group_rows; a.group_stride = d->group_stride; a.row_offset = d->row_offset;
+  a.row_index = d->row_index;
+  CLV_REQUIRE(!a.row_index || a.mode == 0, "layernorm: row_index only with the plain mode");
+  a.blend_mask = d->blend_mask; a.blend_token = d->blend_token;
+  a.bD = d->blend_D; a.bH = d->blend_H; a.bW = d->blend_W; a.mh = d->blend_mh; a.mw = d->blend_mw;
+  if (a.blend_mask) CLV_REQUIRE(a.blend_token && a.bH > 0 && a.mh > 0 && a.bH % a.mh == 0 && a.bW % a.mw == 0,
+                                "layernorm: bad mask-token blend geometry");
+  return 0;
+}
+
+#define LN_DISPATCH(KERNEL, nvec_per_lane, ...)                    \
+  switch (nvec_per_lane) {                                         \
+    case 1: KERNEL<1> __VA_ARGS__; break;                          \
+    case 2: KERNEL<2> __VA_ARGS__; break;                          \
+    case 3: case 4: KERNEL<4> __VA_ARGS__; break;                  \
+    case 5: case 6: case 7: case 8: KERNEL<8> __VA_ARGS__; break;  \
+    case 9: case 10: case 11: case 12: case 13: case 14: case 15: case 16: KERNEL<16> __VA_ARGS__; break; \
+    default: KERNEL<32> __VA_ARGS__; break;                        \
+  }
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" int clv_layernorm_fwd(const clv_ln_desc_t* d, void* y, int y_is_bf16, long long ld_y, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LnArgs a;
+  if (int rc = build_ln_args(a, d)) return rc;
+  CLV_REQUIRE(y != nullptr, "layernorm_fwd: null output");
+  a.y = y; a.y_bf16 = y_is_bf16; a.ld_y = ld_y;
+  if (a.rows == 0) return 0;
+  const int vpl = (a.C / 4 + 31) / 32;
+  const int warps_per_block = 8;
+  long long blocks = (a.rows + warps_per_block - 1) / warps_per_block;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  LN_DISPATCH(ln_fwd_kernel, vpl, <<<(int)blocks, warps_per_block * 32, 0, stream>>>(a));
+  return after_launch("ln_fwd_kernel launch");
+}
+
+extern "C" int clv_layernorm_bwd(const clv_ln_desc_t* d, const clv_ln_bwd_t* b, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LnBwdArgs a{};
+  if (int rc = build_ln_args(a.f, d)) return rc;
+  CLV_REQUIRE(b && b->dy && d->mean && d->rstd, "layernorm_bwd: null pointer");
+  a.dy = b->dy; a.dy_bf16 = b->dy_is_bf16; a.ld_dy = b->ld_dy;
+  a.dx = b->dx; a.ld_dx = b->ld_dx; a.dres = b->dres; a.ld_dres = b->ld_dres;
+  a.dx_copy = b->dx_copy; a.dx_copy_bf16 = b->dx_copy_is_bf16; a.ld_copy = b->ld_copy;
+  a.copy_window_map = b->copy_window != nullptr;
+  if (b->copy_window) fill_geom(a.copy_geom, b->copy_window);
+  a.dgamma = b->dgamma; a.dbeta = b->dbeta; a.dtoken = b->dtoken; a.dx_dense = b->dx_dense;
+  CLV_REQUIRE(a.f.C <= 2048, "layernorm_bwd: C must be <= 2048 (got %d)", a.f.C);
+  if (a.f.rows == 0) return 0;
+  const int vpl = (a.f.C / 4 + 31) / 32;
+  const int warps_per_block = 4;
+  long long blocks = (a.f.rows + warps_per_block - 1) / warps_per_block;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)warps_per_block * a.f.C * sizeof(float);
+  LN_DISPATCH(ln_bwd_kernel, vpl, <<<(int)blocks, warps_per_block * 32, smem, stream>>>(a));
+  return after_launch("ln_bwd_kernel launch");
+}

@@ -1,0 +1,325 @@
+"""Tensor-level wrappers over the C ABI (one Python function per kernel family).
+
+PyTorch is used for device memory and streams only: every function checks shapes / dtypes /
+contiguity, takes ``tensor.data_ptr()`` and calls into libclover_b200.so on the current CUDA stream.
+CUDA tensors are mandatory -- there is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, GemmEpilogue, LnBwd, LnDesc, RowsAffine, WindowGeom
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("clover_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def _is_bf16(t):
+    if t.dtype == BF16:
+        return 1
+    if t.dtype == F32:
+        return 0
+    raise TypeError(f"expected bf16 or fp32 tensor, got {t.dtype}")
+
+
+def _rowmajor2d(t, name):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+class Window:
+    """Clamped window geometry of one Swin block call (get_window_size, swin_transformer_3d.py:302-315)."""
+
+    def __init__(self, B, D, H, W, window, shift):
+        self.B, self.D, self.H, self.W = B, D, H, W
+        self.window, self.shift = tuple(window), tuple(shift)
+        self.c = WindowGeom(B, D, H, W, *self.window, *self.shift)
+        self.Dp = -(-D // window[0]) * window[0]
+        self.Hp = -(-H // window[1]) * window[1]
+        self.Wp = -(-W // window[2]) * window[2]
+        self.N = window[0] * window[1] * window[2]
+        self.nwin = (self.Dp // window[0]) * (self.Hp // window[1]) * (self.Wp // window[2])
+        self.rows = B * self.nwin * self.N            # window-order rows (incl. zero padding)
+        self.tokens = B * D * H * W
+        self.padded = (self.Dp, self.Hp, self.Wp) != (D, H, W)
+        self.shifted = any(s > 0 for s in self.shift)
+
+    def ref(self):
+        return C.pointer(self.c)
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None, out_pre=None, gelu_pre=None,
+         scale_cols=0, scale=1.0, window=None, k_splits=1, accumulate=False):
+    """out = epilogue(A @ B^T).  a: [M,K] (or [K,M] if a_t), b: [N,K] (or [K,N] if b_t), bf16.
+    See clv_gemm_bf16 in include/clover_b200.h."""
+    _need_cuda(a, b, out)
+    if a.dtype != BF16 or b.dtype != BF16:
+        raise TypeError("gemm operands must be bf16")
+    lda, ldb = _rowmajor2d(a, "A"), _rowmajor2d(b, "B")
+    M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError(f"gemm: K mismatch {K} vs {Kb}")
+    ldo = _rowmajor2d(out, "out")
+    if out.shape[1] != N or (window is None and out.shape[0] != M):
+        raise ValueError(f"gemm: out shape {tuple(out.shape)} does not match M={M} N={N}")
+    e = GemmEpilogue()
+    e.bias = _ptr(bias)
+    if bias is not None and (bias.dtype != F32 or bias.numel() != N):
+        raise ValueError("gemm: bias must be fp32 [N]")
+    if residual is not None:
+        e.residual = _ptr(residual)
+        e.residual_is_bf16 = _is_bf16(residual)
+        e.ld_residual = _rowmajor2d(residual, "residual")
+    e.out, e.out_is_bf16, e.ld_out = _ptr(out), _is_bf16(out), ldo
+    if out_pre is not None:
+        e.out_pre, e.ld_pre = _ptr(out_pre), _rowmajor2d(out_pre, "out_pre")
+    if gelu_pre is not None:
+        e.gelu_pre, e.ld_gelu_pre = _ptr(gelu_pre), _rowmajor2d(gelu_pre, "gelu_pre")
+    e.act = 1 if act == "gelu" else 0
+    e.scale_cols, e.scale = int(scale_cols), float(scale)
+    if window is not None:
+        e.window = window.ref()
+    e.k_splits, e.accumulate = int(k_splits), int(bool(accumulate))
+    lib = _lib.load()
+    _lib.check(lib.clv_gemm_bf16(_ptr(a), lda, int(a_t), _ptr(b), ldb, int(b_t), M, N, K, C.byref(e), _stream()), "clv_gemm_bf16")
+    return out
+
+
+def wgrad_splits(M, N, K):
+    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K)."""
+    tiles = -(-M // 128) * -(-N // 128)
+    kb = -(-K // 64)
+    want = max(1, (148 * 2) // tiles)
+    return max(1, min(want, kb // 4 if kb >= 8 else 1))
+
+
+# ------------------------------------------------------------------------------------------------
+def _ln_desc(x, gamma, beta, eps, rows, Cn, mean, rstd, *, window=None, merge=None, add0=None, add1=None, add2=None,
+             group=None, blend=None, row_index=None):
+    d = LnDesc()
+    d.x, d.x_is_bf16 = _ptr(x), _is_bf16(x)
+    d.ld_x = x.stride(-2) if x.dim() >= 2 else Cn
+    d.gamma, d.beta, d.eps = _ptr(gamma), _ptr(beta), float(eps)
+    d.mean, d.rstd = _ptr(mean), _ptr(rstd)
+    d.rows, d.C = int(rows), int(Cn)
+    if window is not None:
+        d.window = window.ref()
+    if merge is not None:
+        d.merge_B, d.merge_D, d.merge_H, d.merge_W, d.merge_C = merge
+    if add0 is not None:
+        d.add0 = _ptr(add0)
+    if add1 is not None:
+        d.add1, d.div1, d.mod1 = _ptr(add1[0]), int(add1[1]), int(add1[2])
+    if add2 is not None:
+        d.add2, d.div2, d.mod2 = _ptr(add2[0]), int(add2[1]), int(add2[2])
+    if group is not None:
+        d.group_rows, d.group_stride, d.row_offset = group
+    if blend is not None:
+        mask, token, (bD, bH, bW) = blend
+        d.blend_mask, d.blend_token = _ptr(mask), _ptr(token)
+        d.blend_D, d.blend_H, d.blend_W = bD, bH, bW
+        d.blend_mh, d.blend_mw = mask.shape[-2], mask.shape[-1]
+    if row_index is not None:
+        d.row_index = _ptr(row_index)
+    return d
+
+
+def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **kw):
+    """y = LN(gather(x) + adds) (* blend).  x: [..., C] fp32/bf16 2-D; y: 2-D bf16/fp32."""
+    _need_cuda(x, gamma, beta, y)
+    Cn = gamma.numel()
+    rows = y.shape[0] if rows is None else rows
+    d = _ln_desc(x, gamma, beta, eps, rows, Cn, mean, rstd, **kw)
+    _lib.check(_lib.load().clv_layernorm_fwd(C.byref(d), _ptr(y), _is_bf16(y), y.stride(0), _stream()), "clv_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=None, dx_copy=None, copy_window=None,
+                  dgamma=None, dbeta=None, dtoken=None, dx_dense=False, **kw):
+    _need_cuda(x, gamma, dy)
+    Cn = gamma.numel()
+    d = _ln_desc(x, gamma, beta, eps, rows, Cn, mean, rstd, **kw)
+    b = LnBwd()
+    b.dy, b.dy_is_bf16, b.ld_dy = _ptr(dy), _is_bf16(dy), dy.stride(0)
+    if dx is not None:
+        if dx.dtype != F32:
+            raise TypeError("layernorm_bwd: dx must be fp32")
+        b.dx, b.ld_dx = _ptr(dx), dx.stride(0)
+    if dres is not None:
+        b.dres, b.ld_dres = _ptr(dres), dres.stride(0)
+    if dx_copy is not None:
+        b.dx_copy, b.dx_copy_is_bf16, b.ld_copy = _ptr(dx_copy), _is_bf16(dx_copy), dx_copy.stride(0)
+    if copy_window is not None:
+        b.copy_window = copy_window.ref()
+    b.dgamma, b.dbeta, b.dtoken = _ptr(dgamma), _ptr(dbeta), _ptr(dtoken)
+    b.dx_dense = int(dx_dense)
+    _lib.check(_lib.load().clv_layernorm_bwd(C.byref(d), C.byref(b), _stream()), "clv_layernorm_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+def _attn_desc(batch, seq, heads, hd, bias_table=None, rel_code=None, code_off=0, region=None, key_mask=None):
+    d = AttnDesc()
+    d.batch, d.seq, d.heads, d.head_dim = batch, seq, heads, hd
+    if bias_table is not None:
+        d.bias_table, d.table_len = _ptr(bias_table), bias_table.shape[0]
+        d.rel_code, d.code_off = _ptr(rel_code), int(code_off)
+    if region is not None:
+        d.region, d.nwin = _ptr(region), region.shape[0]
+    if key_mask is not None:
+        d.key_mask = _ptr(key_mask)
+    return d
+
+
+def attention_fwd(qkv, batch, seq, heads, hd, out, lse, **bias):
+    _need_cuda(qkv, out, lse)
+    if qkv.dtype != BF16 or not qkv.is_contiguous() or qkv.shape != (batch * seq, 3 * heads * hd):
+        raise ValueError(f"attention_fwd: qkv must be contiguous bf16 [{batch * seq}, {3 * heads * hd}], got {tuple(qkv.shape)} {qkv.dtype}")
+    d = _attn_desc(batch, seq, heads, hd, **bias)
+    _lib.check(_lib.load().clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
+    return out
+
+
+def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbias_table=None, **bias):
+    _need_cuda(qkv, out, dout, lse, dqkv)
+    for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
+        if t.dtype != BF16 or not t.is_contiguous():
+            raise ValueError(f"attention_bwd: {n} must be contiguous bf16")
+    d = _attn_desc(batch, seq, heads, hd, **bias)
+    ws = torch.empty(batch * heads * seq, dtype=F32, device=qkv.device)
+    _lib.check(_lib.load().clv_attention_bwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                            float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------------
+def cast(src, dst, scale=1.0):
+    _need_cuda(src, dst)
+    if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
+        raise ValueError("cast: contiguous tensors of equal size required")
+    n = src.numel()
+    if n % 4:
+        raise ValueError("cast: numel must be a multiple of 4")
+    _lib.check(_lib.load().clv_cast(_ptr(src), _is_bf16(src), _ptr(dst), _is_bf16(dst), n, float(scale), _stream()), "clv_cast")
+    return dst
+
+
+def to_bf16(src):
+    return cast(src, torch.empty(src.shape, dtype=BF16, device=src.device))
+
+
+def patchify(x, patch):
+    """x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw] and (D,Hp,Wp)."""
+    _need_cuda(x)
+    if x.dtype != F32 or not x.is_contiguous():
+        raise ValueError("patchify: contiguous fp32 input required")
+    B, Cin, Fr, H, W = x.shape
+    pd, ph, pw = patch
+    D, Hp, Wp = -(-Fr // pd), -(-H // ph), -(-W // pw)
+    out = torch.empty(B * D * Hp * Wp, Cin * pd * ph * pw, dtype=BF16, device=x.device)
+    _lib.check(_lib.load().clv_patchify(_ptr(x), _ptr(out), B, Cin, Fr, H, W, pd, ph, pw, _stream()), "clv_patchify")
+    return out, (D, Hp, Wp)
+
+
+def grouped_colsum(x, out, div=1, mod=1, scale=1.0, accumulate=False, rows=None):
+    _need_cuda(x, out)
+    if out.dtype != F32 or not out.is_contiguous():
+        raise ValueError("grouped_colsum: out must be contiguous fp32")
+    Cn = x.shape[-1]
+    rows = x.shape[0] if rows is None else rows
+    _lib.check(_lib.load().clv_grouped_colsum(_ptr(x), _is_bf16(x), x.stride(0), rows, Cn, div, mod, float(scale), _ptr(out),
+                                             int(accumulate), _stream()), "clv_grouped_colsum")
+    return out
+
+
+def rows_affine(y, rows, Cn, x=None, in_group=None, out_group=None, add0=None, bvec=None, bdiv=1, bscale=1.0):
+    _need_cuda(y)
+    d = RowsAffine()
+    if x is not None:
+        d.x, d.x_is_bf16, d.ld_x = _ptr(x), _is_bf16(x), x.stride(0)
+    if in_group is not None:
+        d.in_group_rows, d.in_group_stride, d.in_offset = in_group
+    d.y, d.y_is_bf16, d.ld_y = _ptr(y), _is_bf16(y), y.stride(0)
+    if out_group is not None:
+        d.out_group_rows, d.out_group_stride, d.out_offset = out_group
+    d.add0 = _ptr(add0)
+    if bvec is not None:
+        d.bvec, d.bdiv, d.bscale = _ptr(bvec), int(bdiv), float(bscale)
+    d.rows, d.C = int(rows), int(Cn)
+    _lib.check(_lib.load().clv_rows_affine(C.byref(d), _stream()), "clv_rows_affine")
+    return y
+
+
+def scatter_add_rows(src, index, dst):
+    _need_cuda(src, index, dst)
+    if src.dtype != F32 or dst.dtype != F32 or index.dtype != torch.int64:
+        raise TypeError("scatter_add_rows: fp32 src/dst and int64 index required")
+    _lib.check(_lib.load().clv_scatter_add_rows(_ptr(src), _ptr(index), _ptr(dst), src.shape[0], src.shape[1], _stream()),
+               "clv_scatter_add_rows")
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------
+def nce_rank_fwd(embs, temperature, margin, use_rank, eps=1e-8):
+    """embs: list of (nblk+1) contiguous fp32 [Bg, D] (query side first).  Returns (losses[2], workspace)."""
+    _need_cuda(*embs)
+    nblk = len(embs) - 1
+    Bg, D = embs[0].shape
+    for e in embs:
+        if e.dtype != F32 or not e.is_contiguous() or e.shape != (Bg, D):
+            raise ValueError("nce_rank_fwd: contiguous fp32 [Bg, D] embeddings required")
+    lib = _lib.load()
+    ws = torch.empty(lib.clv_nce_workspace_floats(nblk, Bg, D), dtype=F32, device=embs[0].device)
+    out = torch.empty(2, dtype=F32, device=embs[0].device)
+    arr = (C.c_void_p * (nblk + 1))(*[e.data_ptr() for e in embs])
+    _lib.check(lib.clv_nce_rank_fwd(arr, nblk, Bg, D, float(temperature), float(margin), int(use_rank), float(eps),
+                                    _ptr(ws), _ptr(out), _stream()), "clv_nce_rank_fwd")
+    return out, ws
+
+
+def nce_rank_bwd(ws, nblk, Bg, D, temperature, use_rank, g_nce, g_rank):
+    grads = [torch.empty(Bg, D, dtype=F32, device=ws.device) for _ in range(nblk + 1)]
+    arr = (C.c_void_p * (nblk + 1))(*[g.data_ptr() for g in grads])
+    _lib.check(_lib.load().clv_nce_rank_bwd(nblk, Bg, D, float(temperature), int(use_rank), _ptr(ws), _ptr(g_nce),
+                                           _ptr(g_rank), arr, _stream()), "clv_nce_rank_bwd")
+    return grads
+
+
+def softmax_focal_fwd(logits, target, V, gamma, ignore_index=-100):
+    """logits fp32 [rows, >=V]; returns (loss[1], stats, sums)."""
+    _need_cuda(logits, target)
+    if logits.dtype != F32 or target.dtype != torch.int64:
+        raise TypeError("softmax_focal_fwd: fp32 logits and int64 targets required")
+    rows = logits.shape[0]
+    stats = torch.empty(rows, 3, dtype=F32, device=logits.device)
+    sums = torch.empty(2, dtype=F32, device=logits.device)
+    loss = torch.empty(1, dtype=F32, device=logits.device)
+    _lib.check(_lib.load().clv_softmax_focal_fwd(_ptr(logits), logits.stride(0), rows, V, _ptr(target), ignore_index,
+                                                float(gamma), _ptr(stats), _ptr(sums), _ptr(loss), _stream()),
+               "clv_softmax_focal_fwd")
+    return loss, stats, sums
+
+
+def softmax_focal_bwd(logits, target, V, gamma, stats, sums, g_loss, dlogits):
+    Vpad = dlogits.shape[1]
+    _lib.check(_lib.load().clv_softmax_focal_bwd(_ptr(logits), logits.stride(0), logits.shape[0], V, Vpad, _ptr(target),
+                                                float(gamma), _ptr(stats), _ptr(sums), _ptr(g_loss), _ptr(dlogits),
+                                                _is_bf16(dlogits), dlogits.stride(0), _stream()), "clv_softmax_focal_bwd")
+    return dlogits

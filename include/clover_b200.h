@@ -1,0 +1,195 @@
+/* clover_b200 -- C ABI of the B200-native (sm_100a) Clover hot-path kernels.
+ *
+ * This is the drop-in boundary of the project: the reference (LeeYN-43/Clover, an mmaction2 fork)
+ * is pure Python/PyTorch and has NO FFI of its own, so each entry point below
+ * names the reference Python code whose arithmetic it replaces (file:line under the reference
+ * tree).  The Python host side (clover_b200/ops.py) binds these with ctypes; INTEGRATION.md shows
+ * the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + explicit sizes/pitches (in ELEMENTS) + a cudaStream_t passed as void*;
+ *   - every function is stream-ordered, re-entrant, allocates nothing persistent, never
+ *     synchronises the device and frees nothing: the caller owns all memory;
+ *   - return 0 on success; otherwise non-zero and clv_last_error() (thread-local) describes it;
+ *   - "bf16" buffers hold __nv_bfloat16, "f32" buffers float; *_is_bf16 flags select per operand;
+ *   - no CPU fallback exists: without a CUDA device every compute call fails.
+ */
+#ifndef CLOVER_B200_H_
+#define CLOVER_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* clv_last_error(void);
+int clv_version(void);
+/* Number of kernel launches issued by this library in the calling process (gpu_launches claim). */
+long long clv_launch_count(void);
+
+/* Window geometry of one Swin stage call: real extent (B,D,H,W), clamped window and shift as
+ * returned by get_window_size (swin_transformer_3d.py:302-315).  Padding to window multiples
+ * (:452-456) is derived inside.  Encodes fused roll(-shift)+window_partition (:460,:271-283)
+ * and its inverse window_reverse+roll(+shift) (:471-474) in closed form. */
+typedef struct {
+  int B, D, H, W;
+  int wd, wh, ww;
+  int sd, sh, sw;
+} clv_window_geom_t;
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM (tcgen05 / TMEM / TMA).  D[M,N] = epilogue(sum_k A[m,k] B[n,k]).
+ *   A: K-major  -> row-major [M, K] with pitch lda;  MN-major -> stored [K, M] with pitch lda.
+ *   B: K-major  -> row-major [N, K] (an nn.Linear weight);  MN-major -> stored [K, N].
+ * Replaces every nn.Linear forward/backward on the path: qkv/proj (swin_transformer_3d.py:376,398),
+ * Mlp fc1/fc2 (:263-266), PatchMerging.reduction (:542), PatchEmbed3D conv-as-GEMM (:681), HF BERT
+ * dense layers (call sites bert_from_hugface.py:30, cross_transformer.py:67,110), head projections
+ * (heads/ssl_head.py:50-69,181-185,257-260; mlm_itm_head.py:38-41; qa_head.py:59-65).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* bias;          /* [N] or NULL */
+  const void* residual;       /* [M(out rows), N] or NULL, added last */
+  int residual_is_bf16;
+  long long ld_residual;
+  void* out;                  /* required */
+  int out_is_bf16;
+  long long ld_out;
+  void* out_pre;              /* bf16 pre-activation copy (act == 1) or NULL */
+  long long ld_pre;
+  const void* gelu_pre;       /* bf16 [M,N]: multiply result by GELU'(gelu_pre) (fc2 dgrad) or NULL */
+  long long ld_gelu_pre;
+  int act;                    /* 0 none, 1 exact erf GELU */
+  int scale_cols;             /* columns [0,scale_cols) are multiplied by `scale` after the bias (q * hd^-0.5, :379) */
+  float scale;
+  const clv_window_geom_t* window;  /* non-NULL: GEMM row (window order) -> spatial output/residual row (:471-479) */
+  int k_splits;               /* >1: split K across CTAs, fp32 atomic accumulation (weight gradients) */
+  int accumulate;             /* 1: add into `out` (fp32) instead of overwriting */
+} clv_gemm_epilogue_t;
+
+int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                  int M, int N, int K, const clv_gemm_epilogue_t* epilogue, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm family.  Replaces nn.LayerNorm at swin_transformer_3d.py:450,483,541,685,238 (eps 1e-5),
+ * cross_transformer.py:98 (eps 1e-5), HF BERT LayerNorms (eps 1e-12), head LNs, together with the
+ * layout copies around them (pad/roll/window_partition :456-466; PatchMerging slices+cat :535-539;
+ * mask-token blend :222-230; fusion positional adds + concat cross_transformer.py:84-108).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x; int x_is_bf16; long long ld_x;
+  const float* gamma; const float* beta; float eps;
+  float* mean; float* rstd;          /* [rows] fp32; written by fwd, read by bwd (may be NULL in fwd) */
+  long long rows; int C;             /* OUTPUT rows, normalised width */
+  const clv_window_geom_t* window;   /* gather: output row r (window order) <- spatial row; padding -> 0 */
+  int merge_B, merge_D, merge_H, merge_W, merge_C;   /* merge_C > 0: 2x2 patch-merging gather, C == 4*merge_C */
+  const float* add0;                 /* [C] added before normalising */
+  const float* add1; int div1, mod1; /* [mod1, C] row (r / div1) % mod1 */
+  const float* add2; int div2, mod2;
+  long long group_rows, group_stride, row_offset;    /* group_rows > 0: out row = (r/group_rows)*group_stride + r%group_rows + row_offset */
+  const long long* blend_mask;       /* (B, mh, mw) int64 0/1: y = y*(1-w) + token*w after the LN */
+  const float* blend_token;          /* [C] */
+  int blend_D, blend_H, blend_W, blend_mh, blend_mw;
+  const long long* row_index;        /* plain mode: source row = row_index[r] (HF BertEmbeddings word lookup) */
+} clv_ln_desc_t;
+
+int clv_layernorm_fwd(const clv_ln_desc_t* desc, void* y, int y_is_bf16, long long ld_y, void* stream);
+
+typedef struct {
+  const void* dy; int dy_is_bf16; long long ld_dy;
+  float* dx; long long ld_dx;                  /* fp32 at the source rows (NULL: parameter grads only) */
+  const float* dres; long long ld_dres;        /* optional residual-stream gradient added into dx */
+  void* dx_copy; int dx_copy_is_bf16; long long ld_copy;   /* optional copy of the final dx */
+  const clv_window_geom_t* copy_window;        /* copy written in window order of this geometry */
+  float* dgamma; float* dbeta;                 /* [C] fp32, ACCUMULATED (caller zero-fills) */
+  float* dtoken;                               /* [C] d(mask_token), blend only */
+  int dx_dense;                                /* write dx at row r, not at the (gathered) source row */
+} clv_ln_bwd_t;
+
+int clv_layernorm_bwd(const clv_ln_desc_t* desc, const clv_ln_bwd_t* bwd, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention core on packed qkv rows.  qkv: bf16 [batch*seq, 3*heads*hd] laid out [3][heads][hd]
+ * per row (the reshape of swin_transformer_3d.py:376 and of a fused BERT q|k|v dense), q already
+ * scaled.  out: bf16 [batch*seq, heads*hd]; lse: fp32 [batch, heads, seq] (saved for backward).
+ *   bias_table (+ rel_code)  : relative-position bias table[(code_i - code_j + code_off), head]
+ *                              (:341-359, :382-385), table fp32 [table_len, heads]
+ *   region (+ nwin)          : shift mask, 0 if region[win][i] == region[win][j] else -100
+ *                              (:388-390, compute_mask :548-562); win = batch % nwin
+ *   key_mask                 : fp32 additive per key [batch, seq] ((1-m)*-10000, HF BERT 4.6.1)
+ * Replaces WindowAttention3D.forward :379-397 and HF BertSelfAttention's softmax(QK^T/8+M)V.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int batch, seq, heads, head_dim;       /* head_dim 32 or 64; seq <= 512 */
+  const float* bias_table; int table_len;
+  const int* rel_code; int code_off;     /* [seq] */
+  const int* region; int nwin;           /* [nwin, seq] or NULL */
+  const float* key_mask;                 /* [batch, seq] or NULL */
+} clv_attn_desc_t;
+
+int clv_attention_fwd(const clv_attn_desc_t* desc, const void* qkv, void* out, float* lse, void* stream);
+/* dqkv: bf16 same layout as qkv (dq already multiplied by q_scale so it is d/d(unscaled q));
+ * dbias_table: fp32 [table_len, heads] ACCUMULATED (may be NULL). */
+int clv_attention_bwd(const clv_attn_desc_t* desc, const void* qkv, const void* out, const void* dout,
+                      const float* lse, void* dqkv, float q_scale, float* dbias_table,
+                      float* dsum_workspace /* fp32 [batch*heads*seq] */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HBM-bound helpers.
+ * ------------------------------------------------------------------------------------------- */
+/* dst[i] = scale * src[i] with dtype conversion (fp32 master weights -> bf16 operand caches, the
+ * model.half() of core/hooks/fp16_utils.py:215-239; gradient-stream casts).  n % 4 == 0. */
+int clv_cast(const void* src, int src_is_bf16, void* dst, int dst_is_bf16, long long n, float scale, void* stream);
+
+/* PatchEmbed3D's Conv3d(kernel == stride) as a patch matrix (swin_transformer_3d.py:665,671-681):
+ * x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw], column order (c,kd,kh,kw); zero padding. */
+int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int F, int H, int W, int pd, int ph, int pw, void* stream);
+
+/* out[g,c] (+)= scale * sum_{r : (r/div)%mod == g} x[r,c]; out fp32 [mod, C].  nn.Linear bias grads,
+ * AdaptiveAvgPool3d (ssl_head.py:105-106), d vis_space_pos / vis_tempor_pos / position embeddings. */
+int clv_grouped_colsum(const void* x, int x_is_bf16, long long ld, long long rows, int C, int div, int mod, float scale,
+                       float* out, int accumulate, void* stream);
+
+/* y[orow(r),:] = x[irow(r),:] + add0 + bscale * bvec[r / bdiv,:], row(r) = (r/group_rows)*group_stride + r%group_rows + offset
+ * (group_rows == 0: identity).  Text half of the fusion concat (cross_transformer.py:84-86,108), its
+ * backward slice, and the broadcast of the pooled-feature gradient. */
+typedef struct {
+  const void* x; int x_is_bf16; long long ld_x;
+  long long in_group_rows, in_group_stride, in_offset;
+  void* y; int y_is_bf16; long long ld_y;
+  long long out_group_rows, out_group_stride, out_offset;
+  const float* add0;            /* [C] or NULL */
+  const float* bvec; long long bdiv; float bscale;   /* [rows/bdiv, C] or NULL */
+  long long rows; int C;
+} clv_rows_affine_t;
+int clv_rows_affine(const clv_rows_affine_t* desc, void* stream);
+
+/* dst[index[r],:] += src[r,:]  (fp32 atomics; word-embedding gradient of HF BertEmbeddings). */
+int clv_scatter_add_rows(const float* src, const long long* index, float* dst, long long rows, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses (fp32, @force_fp32 in the reference).
+ * clv_nce_rank_*: ExclusiveNCEwithRankingLoss.forward (losses/contrastive_loss.py:103-161) for nblk == 3
+ * (emb = {video, text, text_mask, text_recon}) and NormSoftmaxLoss.forward (:40-68) for nblk == 1
+ * (emb = {video, text}); all matrices [Bg, D] fp32, already all-gathered.  out_losses[0] = nce
+ * (loss_v + loss_t), out_losses[1] = pair-wise ranking hinge on the /t-scaled diagonals (:155-159).
+ * The workspace (clv_nce_workspace_floats) carries the saved statistics from fwd to bwd.
+ * ------------------------------------------------------------------------------------------- */
+long long clv_nce_workspace_floats(int nblk, int Bg, int D);
+int clv_nce_rank_fwd(const float* const* emb, int nblk, int Bg, int D, float temperature, float margin, int use_rank,
+                     float eps, float* workspace, float* out_losses, void* stream);
+int clv_nce_rank_bwd(int nblk, int Bg, int D, float temperature, int use_rank, float* workspace, const float* g_nce,
+                     const float* g_rank, float* const* grads, void* stream);
+
+/* SoftmaxFocalLossMultiClass.forward (losses/focal_loss.py:61-72; gamma == 0 gives the mean cross-entropy
+ * of CrossEntropyLoss._forward, cross_entropy_loss.py:74-81).  Rows whose target == ignore_index are
+ * skipped (the row selection of multimodal_transformer_pretrain.py:137-139).  stats fp32 [rows,3],
+ * sums fp32 [2] carry state to the backward, which writes d logits (bf16 or fp32, [rows, Vpad]). */
+int clv_softmax_focal_fwd(const float* logits, long long ld, long long rows, int V, const long long* target,
+                          long long ignore_index, float gamma, float* stats, float* sums, float* loss, void* stream);
+int clv_softmax_focal_bwd(const float* logits, long long ld, long long rows, int V, int Vpad, const long long* target,
+                          float gamma, const float* stats, const float* sums, const float* g_loss, void* dlogits,
+                          int dlogits_is_bf16, long long ld_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOVER_B200_H_ */

@@ -1,0 +1,60 @@
+"""CPU-only host-logic tests: product-side integer tables are bit-exact against the reference's
+golden tables; the C-ABI library loads and exports every symbol include/clover_b200.h declares."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from clover_b200 import tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_product_tables_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tables.npz"))
+    assert np.array_equal(tables.relative_position_index((8, 7, 7)), g["rel_index_877"].astype(np.int64))
+    assert np.array_equal(tables.relative_position_index((2, 7, 7)), g["rel_index_277"].astype(np.int64))
+    for N in (196, 392, 98):
+        code, off = tables.rel_code(N, (8, 7, 7))
+        idx = code.astype(np.int64)[:, None] - code.astype(np.int64)[None, :] + off
+        assert np.array_equal(idx, g["rel_index_877"].astype(np.int64)[:N, :N])
+    meta = json.loads(str(g["meta"]))
+    for i, m in enumerate(meta):
+        win, sh = tables.get_window_size(tuple(m["dims"]), tuple(m["window_cfg"]), tuple(m["shift_cfg"]))
+        assert list(win) == m["window"] and list(sh) == m["shift"]
+        D, H, W = m["dims"]
+        rid = tables.region_ids(D, H, W, win, sh)
+        mask = tables.attn_mask_from_regions(rid)
+        shape = tuple(g[f"mask_shape_{i}"])
+        ref = np.unpackbits(g[f"mask_bits_{i}"])[: int(np.prod(shape))].reshape(shape).astype(bool)
+        assert np.array_equal(mask != 0, ref)
+        assert np.array_equal(tables.window_gather_index(2, D, H, W, win, sh), g[f"gather_{i}"].astype(np.int64))
+
+
+def test_library_exports_every_declared_symbol():
+    from clover_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "clover_b200.h")).read()
+    declared = set(re.findall(r"\b(clv_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.fail(f"{_lib.LIB_PATH} has not been built (run __graft_entry__.build())")
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.clv_version() >= 100
+    assert lib.clv_launch_count() == 0
+    assert lib.clv_nce_workspace_floats(3, 4, 8) > 0
+
+
+def test_ops_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from clover_b200 import ops
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, a, torch.zeros(128, 128))

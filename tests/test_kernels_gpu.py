@@ -1,0 +1,397 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against the CPU oracle / plain fp32 torch
+formulas on the same seeded inputs.  bf16 tensor-core kernels: <= 2e-2 relative (north-star);
+fp32 kernels (LayerNorm, losses, reductions): <= 1e-4 relative; index work: bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clover_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from clover_b200 import ops as _ops
+    return _ops
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=F32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 136, 96), (64, 768, 1024), (1000, 384, 64), (128, 128, 1000)])
+def test_gemm_layouts(ops, a_t, b_t, M, N, K):
+    if (a_t and M % 8) or (b_t and N % 8) or (not a_t and K % 8) or (not b_t and K % 8):
+        pytest.skip("TMA needs 16-byte row pitch")
+    A = rnd(M, K, seed=1, dtype=BF16)
+    B = rnd(N, K, seed=2, dtype=BF16)
+    a = A.t().contiguous() if a_t else A
+    b = B.t().contiguous() if b_t else B
+    out = torch.empty(M, N, dtype=F32, device="cuda")
+    ops.gemm(a, b, out, a_t=a_t, b_t=b_t)
+    ref = A.float() @ B.float().t()
+    assert rel(out, ref) < 2e-3
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 392, 256, 192
+    A, B = rnd(M, K, seed=3, dtype=BF16), rnd(N, K, seed=4, scale=0.1, dtype=BF16)
+    bias = rnd(N, seed=5)
+    base = A.float() @ B.float().t() + bias
+    # bias + q-scale prefix, bf16 out
+    out = torch.empty(M, N, dtype=BF16, device="cuda")
+    ops.gemm(A, B, out, bias=bias, scale_cols=96, scale=0.25)
+    ref = base.clone(); ref[:, :96] *= 0.25
+    assert rel(out, ref) < 1e-2
+    # GELU with pre-activation copy
+    pre = torch.empty(M, N, dtype=BF16, device="cuda")
+    ops.gemm(A, B, out, bias=bias, act="gelu", out_pre=pre)
+    assert rel(pre, base) < 1e-2
+    assert rel(out, O.gelu(base.cpu())) < 1e-2
+    # multiply by GELU'(pre) (fc2 dgrad)
+    out32 = torch.empty(M, N, dtype=F32, device="cuda")
+    ops.gemm(A, B, out32, gelu_pre=pre)
+    p = pre.float().cpu().requires_grad_(True)
+    O.gelu(p).sum().backward()
+    assert rel(out32, (A.float() @ B.float().t()).cpu() * p.grad) < 2e-3
+    # residual fp32 -> fp32, residual bf16 -> bf16
+    res = rnd(M, N, seed=6)
+    ops.gemm(A, B, out32, bias=bias, residual=res)
+    assert rel(out32, base + res) < 2e-3
+    resb = res.to(BF16)
+    ops.gemm(A, B, out, bias=bias, residual=resb)
+    assert rel(out, base + resb.float()) < 1e-2
+
+
+def test_gemm_window_scatter(ops):
+    # proj GEMM + window_reverse + roll back + residual, with spatial padding
+    B_, D, H, W, Cc = 2, 4, 10, 9, 64
+    win, sh = O.get_window_size((D, H, W), (8, 7, 7), (4, 3, 3))
+    wg = ops.Window(B_, D, H, W, win, sh)
+    A = rnd(wg.rows, 64, seed=7, dtype=BF16)
+    Wt = rnd(Cc, 64, seed=8, scale=0.1, dtype=BF16)
+    x = rnd(wg.tokens, Cc, seed=9)
+    out = torch.empty(wg.tokens, Cc, dtype=F32, device="cuda")
+    ops.gemm(A, Wt, out, residual=x, window=wg)
+    gi = torch.from_numpy(O.window_gather_index(B_, wg.Dp, wg.Hp, wg.Wp, win, sh))
+    y = (A.float() @ Wt.float().t()).cpu()
+    back = torch.zeros(B_ * wg.Dp * wg.Hp * wg.Wp, Cc).index_copy(0, gi.reshape(-1), y)
+    back = back.view(B_, wg.Dp, wg.Hp, wg.Wp, Cc)[:, :D, :H, :W].reshape(-1, Cc)
+    assert rel(out, back + x.cpu()) < 2e-3
+
+
+@pytest.mark.parametrize("splits", [2, 7, 64])
+def test_gemm_splitk_wgrad(ops, splits):
+    T, Nout, Nin = 5000, 384, 128
+    dY, X = rnd(T, Nout, seed=10, dtype=BF16), rnd(T, Nin, seed=11, dtype=BF16)
+    dW = torch.empty(Nout, Nin, dtype=F32, device="cuda")
+    ops.gemm(dY, X, dW, a_t=True, b_t=True, k_splits=splits)
+    ref = dY.float().t() @ X.float()
+    assert rel(dW, ref) < 2e-3
+    ops.gemm(dY, X, dW, a_t=True, b_t=True, k_splits=splits, accumulate=True)
+    assert rel(dW, 2 * ref) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+def _ln_ref(x, g, b, eps):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+
+@pytest.mark.parametrize("C", [96, 128, 768, 1536, 2048])
+def test_layernorm_plain(ops, C):
+    rows = 333
+    x, g, b = rnd(rows, C, seed=1, scale=3), 1 + 0.1 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    y = torch.empty(rows, C, dtype=F32, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd)
+    xr = x.cpu().requires_grad_(True); gr = g.cpu().requires_grad_(True); br = b.cpu().requires_grad_(True)
+    yr = _ln_ref(xr, gr, br, 1e-5)
+    assert rel(y, yr.detach()) < 1e-5
+    yb = torch.empty(rows, C, dtype=BF16, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, yb)
+    assert rel(yb, yr.detach()) < 1e-2
+    dy = rnd(rows, C, seed=4)
+    dres = rnd(rows, C, seed=5)
+    (yr * dy.cpu()).sum().backward()
+    dx = torch.empty(rows, C, dtype=F32, device="cuda")
+    dxc = torch.empty(rows, C, dtype=BF16, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.layernorm_bwd(x, g, b, 1e-5, mean, rstd, dy, rows=rows, dx=dx, dres=dres, dx_copy=dxc, dgamma=dg, dbeta=db)
+    assert rel(dx, xr.grad + dres.cpu()) < 1e-4
+    assert rel(dxc, xr.grad + dres.cpu()) < 1e-2
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dims,Bc", [((4, 14, 14), 2), ((16, 14, 7), 1), ((3, 10, 9), 2)])
+def test_layernorm_window_gather(ops, dims, Bc):
+    D, H, W = dims
+    C = 64
+    win, sh = O.get_window_size(dims, (8, 7, 7), (4, 3, 3))
+    wg = ops.Window(Bc, D, H, W, win, sh)
+    x, g, b = rnd(wg.tokens, C, seed=1, scale=2), 1 + 0.1 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    y = torch.empty(wg.rows, C, dtype=F32, device="cuda")
+    mean, rstd = torch.empty(wg.rows, device="cuda"), torch.empty(wg.rows, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd, window=wg)
+    xr = x.cpu().requires_grad_(True)
+    h = _ln_ref(xr, g.cpu(), b.cpu(), 1e-5).view(Bc, D, H, W, C)
+    h = torch.nn.functional.pad(h, (0, 0, 0, wg.Wp - W, 0, wg.Hp - H, 0, wg.Dp - D))
+    gi = torch.from_numpy(O.window_gather_index(Bc, wg.Dp, wg.Hp, wg.Wp, win, sh)).reshape(-1)
+    yr = h.reshape(-1, C)[gi]
+    assert rel(y, yr.detach()) < 1e-5
+    # backward: scatter + residual gradient + window-ordered bf16 copy of the result
+    dy, dres = rnd(wg.rows, C, seed=4), rnd(wg.tokens, C, seed=5)
+    (yr * dy.cpu()).sum().backward()
+    dx = torch.empty(wg.tokens, C, dtype=F32, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.layernorm_bwd(x, g, b, 1e-5, mean, rstd, dy, rows=wg.rows, dx=dx, dres=dres, dgamma=dg, dbeta=db, window=wg)
+    assert rel(dx, xr.grad + dres.cpu()) < 1e-4
+    # plain LN backward whose dx copy is emitted in window order (LN2 -> proj operand)
+    y2 = torch.empty(wg.tokens, C, dtype=F32, device="cuda")
+    m2, r2 = torch.empty(wg.tokens, device="cuda"), torch.empty(wg.tokens, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, y2, mean=m2, rstd=r2)
+    dy2 = rnd(wg.tokens, C, seed=6)
+    copy = torch.zeros(wg.rows, C, dtype=F32, device="cuda")
+    dx2 = torch.empty(wg.tokens, C, dtype=F32, device="cuda")
+    ops.layernorm_bwd(x, g, b, 1e-5, m2, r2, dy2, rows=wg.tokens, dx=dx2, dx_copy=copy, copy_window=wg)
+    padded = torch.nn.functional.pad(dx2.cpu().view(Bc, D, H, W, C), (0, 0, 0, wg.Wp - W, 0, wg.Hp - H, 0, wg.Dp - D))
+    assert torch.equal(copy.cpu(), padded.reshape(-1, C)[gi])
+
+
+@pytest.mark.parametrize("H,W", [(8, 6), (7, 5)])
+def test_layernorm_merge(ops, H, W):
+    Bc, D, C = 2, 3, 32
+    x = rnd(Bc * D * H * W, C, seed=1, scale=2)
+    g, b = 1 + 0.1 * rnd(4 * C, seed=2), 0.1 * rnd(4 * C, seed=3)
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    rows = Bc * D * H2 * W2
+    y = torch.empty(rows, 4 * C, dtype=F32, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd, merge=(Bc, D, H, W, C))
+    xr = x.cpu().requires_grad_(True)
+    xx = torch.nn.functional.pad(xr.view(Bc, D, H, W, C), (0, 0, 0, W % 2, 0, H % 2))
+    cat = torch.cat([xx[:, :, i::2, j::2] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))], -1).reshape(rows, 4 * C)
+    yr = _ln_ref(cat, g.cpu(), b.cpu(), 1e-5)
+    assert rel(y, yr.detach()) < 1e-5
+    dy = rnd(rows, 4 * C, seed=4)
+    (yr * dy.cpu()).sum().backward()
+    dx = torch.zeros(Bc * D * H * W, C, dtype=F32, device="cuda")
+    dg, db = torch.zeros(4 * C, device="cuda"), torch.zeros(4 * C, device="cuda")
+    ops.layernorm_bwd(x, g, b, 1e-5, mean, rstd, dy, rows=rows, dx=dx, dgamma=dg, dbeta=db, merge=(Bc, D, H, W, C))
+    assert rel(dx, xr.grad) < 1e-4
+
+
+def test_layernorm_fusion_adds_and_blend_and_lookup(ops):
+    # fusion: LN(v + space[s] + tempor[t] + type0) written into rows of the concat buffer
+    Bc, T, S, C, L = 3, 2, 49, 128, 16
+    v = rnd(Bc * T * S, C, seed=1, dtype=BF16)
+    space, tempor, type0 = rnd(S, C, seed=2), rnd(T, C, seed=3), rnd(C, seed=4)
+    g, b = 1 + 0.1 * rnd(C, seed=5), 0.1 * rnd(C, seed=6)
+    tot = T * S + L
+    z = torch.zeros(Bc * tot, C, dtype=F32, device="cuda")
+    ops.layernorm_fwd(v, g, b, 1e-5, z, rows=Bc * T * S, add0=type0, add1=(space, 1, S), add2=(tempor, S, T),
+                      group=(T * S, tot, 0))
+    ref = v.float().cpu().view(Bc, T, S, C) + space.cpu()[None, None] + tempor.cpu()[None, :, None] + type0.cpu()
+    ref = _ln_ref(ref.view(Bc, T * S, C), g.cpu(), b.cpu(), 1e-5)
+    assert rel(z.view(Bc, tot, C)[:, :T * S], ref) < 1e-5
+    assert float(z.view(Bc, tot, C)[:, T * S:].abs().max()) == 0.0
+    # mask-token blend (patch-embed LN epilogue)
+    Bc, D, H, W, C = 2, 2, 14, 14, 32
+    x = rnd(Bc * D * H * W, C, seed=7)
+    g, b, tok = 1 + 0.1 * rnd(C, seed=8), 0.1 * rnd(C, seed=9), rnd(C, seed=10)
+    mask = (torch.rand(Bc, 7, 7, generator=torch.Generator().manual_seed(3)) < 0.3).long().cuda()
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(x.shape[0], device="cuda"), torch.empty(x.shape[0], device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd, blend=(mask, tok, (D, H, W)))
+    st = {"mask_token": tok.cpu().view(1, C, 1, 1, 1)}
+    yr, _ = O.mask_token_blend(st, _ln_ref(x.cpu(), g.cpu(), b.cpu(), 1e-5).view(Bc, D, H, W, C), mask.cpu()[:, None])
+    assert rel(y, yr.reshape(-1, C)) < 1e-5
+    # embedding lookup + position add (HF BertEmbeddings)
+    V, H_, Lq, Bq = 50, 64, 8, 4
+    table, pos, typ = rnd(V, H_, seed=11), rnd(Lq, H_, seed=12), rnd(H_, seed=13)
+    ids = torch.randint(0, V, (Bq * Lq,), generator=torch.Generator().manual_seed(5)).cuda()
+    g, b = 1 + 0.1 * rnd(H_, seed=14), 0.1 * rnd(H_, seed=15)
+    y = torch.empty(Bq * Lq, H_, dtype=F32, device="cuda")
+    ops.layernorm_fwd(table, g, b, 1e-12, y, rows=Bq * Lq, row_index=ids, add0=typ, add1=(pos, 1, Lq))
+    ref = table.cpu()[ids.cpu()].view(Bq, Lq, H_) + pos.cpu()[None] + typ.cpu()
+    assert rel(y, _ln_ref(ref, g.cpu(), b.cpu(), 1e-12).view(-1, H_)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_inputs(batch, seq, heads, hd, seed):
+    qkv = rnd(batch * seq, 3 * heads * hd, seed=seed, scale=0.7, dtype=BF16)
+    dout = rnd(batch * seq, heads * hd, seed=seed + 1, dtype=BF16)
+    return qkv, dout
+
+
+def _attn_ref(qkv, dout, batch, seq, heads, hd, bias=None):
+    """fp32 reference on CPU with autograd.  bias: (batch|1, heads|1, seq, seq) additive or None."""
+    x = qkv.float().cpu().requires_grad_(True)
+    q, k, v = x.view(batch, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2)
+    if bias is not None:
+        s = s + bias
+    p = torch.softmax(s, -1)
+    o = (p @ v).transpose(1, 2).reshape(batch * seq, heads * hd)
+    lse = torch.logsumexp(s, -1)
+    return x, o, lse
+
+
+@pytest.mark.parametrize("dims,shifted", [((4, 14, 14), False), ((4, 14, 14), True), ((8, 14, 7), True), ((16, 7, 7), True)])
+def test_window_attention_core(ops, dims, shifted):
+    heads, hd, Bc = 3, 32, 2
+    win, sh = O.get_window_size(dims, (8, 7, 7), (4, 3, 3) if shifted else (0, 0, 0))
+    N = win[0] * win[1] * win[2]
+    nwin = (dims[0] // win[0]) * (dims[1] // win[1]) * (dims[2] // win[2])
+    batch = Bc * nwin
+    qkv, dout = _attn_inputs(batch, N, heads, hd, 20)
+    table = rnd(2535, heads, seed=22, scale=0.5)
+    from clover_b200.tables import rel_code, region_ids
+    code, off = rel_code(N, (8, 7, 7))
+    code = torch.from_numpy(code).cuda()
+    region = torch.from_numpy(region_ids(*dims, win, sh)).cuda() if shifted else None
+    out = torch.empty(batch * N, heads * hd, dtype=BF16, device="cuda")
+    lse = torch.empty(batch, heads, N, dtype=F32, device="cuda")
+    kw = dict(bias_table=table, rel_code=code, code_off=off, region=region)
+    ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)
+    idx = torch.from_numpy(O.relative_position_index((8, 7, 7))[:N, :N].reshape(-1))
+    tb = table.cpu().requires_grad_(True)
+    bias = tb[idx].view(N, N, heads).permute(2, 0, 1)[None]
+    if shifted:
+        m = torch.from_numpy(O.compute_mask(*dims, win, sh))            # (nwin, N, N)
+        bias = bias + m.repeat(Bc, 1, 1)[:, None]
+    x, o_ref, lse_ref = _attn_ref(qkv, dout, batch, N, heads, hd, bias)
+    assert rel(out, o_ref.detach()) < 1e-2
+    assert rel(lse, lse_ref.detach()) < 1e-4
+    (o_ref * dout.float().cpu()).sum().backward()
+    dqkv = torch.empty_like(qkv)
+    dtab = torch.zeros(2535, heads, dtype=F32, device="cuda")
+    ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dqkv, 1.0, dbias_table=dtab, **kw)
+    assert rel(dqkv, x.grad) < 2e-2
+    assert rel(dtab, tb.grad) < 2e-2
+
+
+@pytest.mark.parametrize("seq", [32, 228, 432])
+def test_bert_attention_core(ops, seq):
+    heads, hd, batch = 2, 64, 3
+    qkv, dout = _attn_inputs(batch, seq, heads, hd, 30)
+    lens = [seq, seq - 5, max(3, seq // 2)]
+    keep = torch.zeros(batch, seq)
+    for i, n in enumerate(lens):
+        keep[i, :n] = 1
+    km = ((1 - keep) * -10000.0).cuda()
+    out = torch.empty(batch * seq, heads * hd, dtype=BF16, device="cuda")
+    lse = torch.empty(batch, heads, seq, dtype=F32, device="cuda")
+    ops.attention_fwd(qkv, batch, seq, heads, hd, out, lse, key_mask=km)
+    x, o_ref, lse_ref = _attn_ref(qkv, dout, batch, seq, heads, hd, km.cpu()[:, None, None, :])
+    assert rel(out, o_ref.detach()) < 1e-2
+    (o_ref * dout.float().cpu()).sum().backward()
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, 0.125, key_mask=km)
+    g = x.grad.clone().view(batch * seq, 3, heads * hd)
+    g[:, 0] *= 0.125
+    assert rel(dqkv, g.view(batch * seq, -1)) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def test_cast_patchify_colsum_affine_scatter(ops):
+    x = rnd(4096, seed=1)
+    assert torch.equal(ops.to_bf16(x), x.to(BF16))
+    imgs = rnd(2, 3, 6, 30, 28, seed=2)
+    cols, (D, Hp, Wp) = ops.patchify(imgs, (2, 4, 4))
+    xp = torch.nn.functional.pad(imgs.cpu(), (0, 0, 0, 2))
+    ref = xp.view(2, 3, D, 2, Hp, 4, Wp, 4).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(-1, 96)
+    assert torch.equal(cols.cpu(), ref.to(BF16))
+    y = rnd(1000, 256, seed=3)
+    out = torch.empty(1, 256, device="cuda")
+    ops.grouped_colsum(y, out)
+    assert rel(out[0], y.sum(0)) < 1e-5
+    out = torch.empty(7, 256, device="cuda")
+    ops.grouped_colsum(y, out, div=3, mod=7, scale=0.5)
+    grp = (torch.arange(1000) // 3) % 7
+    ref = torch.stack([y.cpu()[grp == g].sum(0) * 0.5 for g in range(7)])
+    assert rel(out, ref) < 1e-5
+    yb = y.to(BF16)
+    ops.grouped_colsum(yb, out, div=1, mod=7)
+    ref = torch.stack([yb.float().cpu()[torch.arange(1000) % 7 == g].sum(0) for g in range(7)])
+    assert rel(out, ref) < 1e-5
+    # text half of the fusion concat: z[b, off + l] = t[b, l] + type1
+    Bc, L, tot, off, C = 3, 5, 12, 7, 64
+    t, ty = rnd(Bc * L, C, seed=4, dtype=BF16), rnd(C, seed=5)
+    z = torch.zeros(Bc * tot, C, dtype=BF16, device="cuda")
+    ops.rows_affine(z, Bc * L, C, x=t, out_group=(L, tot, off), add0=ty)
+    ref = (t.float() + ty).to(BF16).view(Bc, L, C)
+    assert torch.equal(z.view(Bc, tot, C)[:, off:], ref)
+    # broadcast add of a pooled gradient
+    a, bv = rnd(Bc * L, C, seed=6), rnd(Bc, C, seed=7)
+    o = torch.empty(Bc * L, C, device="cuda")
+    ops.rows_affine(o, Bc * L, C, x=a, bvec=bv, bdiv=L, bscale=0.2)
+    assert rel(o, a + 0.2 * bv.repeat_interleave(L, 0)) < 1e-6
+    src = rnd(40, 64, seed=8)
+    idx = torch.randint(0, 9, (40,), generator=torch.Generator().manual_seed(1)).cuda()
+    dst = torch.zeros(9, 64, device="cuda")
+    ops.scatter_add_rows(src, idx, dst)
+    assert rel(dst, torch.zeros(9, 64).index_add_(0, idx.cpu(), src.cpu())) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ losses
+@pytest.mark.parametrize("Bg,D", [(6, 24), (130, 768)])
+def test_exclusive_nce_ranking(ops, Bg, D):
+    embs = [rnd(Bg, D, seed=40 + i) for i in range(4)]
+    embs[1] = embs[0] * 0.5 + embs[1] * 0.5           # make positives non-trivial (hinge partly active)
+    losses, ws = ops.nce_rank_fwd(embs, 0.05, 5.0, True)
+    cpu = [e.cpu().requires_grad_(True) for e in embs]
+    d = O.exclusive_nce_ranking(*cpu, t=0.05, margin=5.0)
+    assert abs(float(losses[0]) - float(d["nce_loss"])) < 1e-4 * abs(float(d["nce_loss"]))
+    assert abs(float(losses[1]) - float(d["rank_t_tm_loss"])) < 1e-4 * max(1.0, abs(float(d["rank_t_tm_loss"])))
+    (0.7 * d["nce_loss"] + 1.3 * d["rank_t_tm_loss"]).backward()
+    g = ops.nce_rank_bwd(ws, 3, Bg, D, 0.05, True, torch.tensor([0.7], device="cuda"), torch.tensor([1.3], device="cuda"))
+    for i in range(4):
+        assert rel(g[i], cpu[i].grad) < 1e-3, i
+
+
+def test_norm_softmax_loss(ops):
+    Bg, D = 65, 768
+    embs = [rnd(Bg, D, seed=50 + i) for i in range(2)]
+    losses, ws = ops.nce_rank_fwd(embs, 0.05, 0.0, False)
+    cpu = [e.cpu().requires_grad_(True) for e in embs]
+    v = O.norm_softmax_loss(*cpu, 0.05, True)
+    assert abs(float(losses[0]) - float(v)) < 1e-4 * abs(float(v))
+    v.backward()
+    g = ops.nce_rank_bwd(ws, 1, Bg, D, 0.05, False, torch.ones(1, device="cuda"), None)
+    for i in range(2):
+        assert rel(g[i], cpu[i].grad) < 1e-3
+
+
+@pytest.mark.parametrize("gamma,V", [(2.0, 30522), (0.0, 1500)])
+def test_softmax_focal(ops, gamma, V):
+    rows, Vpad = 37, (V + 7) // 8 * 8
+    logits = rnd(rows, Vpad, seed=60, scale=3)
+    logits[:, V:] = -1e30
+    tgt = torch.randint(0, V, (rows,), generator=torch.Generator().manual_seed(2))
+    tgt[::5] = -100
+    tgt = tgt.cuda()
+    loss, stats, sums = ops.softmax_focal_fwd(logits, tgt, V, gamma)
+    lr = logits[:, :V].cpu().requires_grad_(True)
+    keep = tgt.cpu() != -100
+    ref = O.softmax_focal_multiclass(lr[keep], tgt.cpu()[keep], gamma) if gamma else O.cross_entropy(lr[keep], tgt.cpu()[keep])
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    (ref * 1.7).backward()
+    dl = torch.empty(rows, Vpad, dtype=F32, device="cuda")
+    ops.softmax_focal_bwd(logits, tgt, V, gamma, stats, sums, torch.tensor([1.7], device="cuda"), dl)
+    assert rel(dl[:, :V], lr.grad) < 1e-4
+    assert float(dl[:, V:].abs().max()) == 0.0 if Vpad > V else True
