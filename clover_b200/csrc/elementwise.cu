@@ -33,6 +33,22 @@ __global__ void cast_kernel(const void* src, int src_bf16, void* dst, int dst_bf
   }
 }
 
+// y = GELU(x)  (mode 0)   or   y = dy * GELU'(x)  (mode 1); exact erf form (nn.GELU default)
+__global__ void gelu_kernel(const void* x, int x_bf16, const void* dy, int dy_bf16, void* y, int y_bf16, long long n4, int mode) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ldv4(x, x_bf16, i * 4);
+    float4 o;
+    if (mode == 0) {
+      o = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+    } else {
+      const float4 d = ldv4(dy, dy_bf16, i * 4);
+      o = make_float4(d.x * gelu_erf_grad(v.x), d.y * gelu_erf_grad(v.y), d.z * gelu_erf_grad(v.z), d.w * gelu_erf_grad(v.w));
+    }
+    stv4(y, y_bf16, i * 4, o);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // PatchEmbed3D as a GEMM (swin_transformer_3d.py:665,671-681): Conv3d with kernel == stride is a
 // [tokens, Cin*pd*ph*pw] x [Cin*pd*ph*pw, C] product.  One CTA stages the Cin*pd*ph input rows of
@@ -160,6 +176,15 @@ extern "C" int clv_cast(const void* src, int src_is_bf16, void* dst, int dst_is_
   if (n == 0) return 0;
   cast_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(src, src_is_bf16, dst, dst_is_bf16, n / 4, scale);
   return after_launch("cast_kernel");
+}
+
+extern "C" int clv_gelu(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, void* y, int y_is_bf16, long long n,
+                        void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(x && y && n >= 0 && n % 4 == 0, "clv_gelu: n must be a multiple of 4 (got %lld)", n);
+  if (n == 0) return 0;
+  gelu_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(x, x_is_bf16, dy, dy_is_bf16, y, y_is_bf16, n / 4, dy ? 1 : 0);
+  return after_launch("gelu_kernel");
 }
 
 extern "C" int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int F, int H, int W, int pd, int ph, int pw,

@@ -1,0 +1,736 @@
+"""Autograd glue: torch.autograd.Function wrappers that chain the C-ABI kernels.
+
+Precision policy: bf16 tensor-core operands with fp32 accumulation, fp32 residual
+stream inside the Swin backbone, fp32 LayerNorm statistics, fp32 parameter gradients, fp32 losses.
+Each Function saves exactly the tensors its hand-written backward needs; nothing here falls back
+to a PyTorch implementation of the math.
+"""
+import torch
+
+from . import ops
+from .ops import BF16, F32
+
+# ------------------------------------------------------------------------------------------------
+# bf16 operand cache for fp32 master weights (derived data, refreshed when the parameter changes)
+# ------------------------------------------------------------------------------------------------
+_W16 = {}
+
+
+def w16(p):
+    """bf16 copy of an fp32 parameter (2-D view of the weight), re-cast when the parameter is updated."""
+    key = id(p)
+    ent = _W16.get(key)
+    ver = p._version
+    if ent is not None and ent[0] == ver and ent[1].device == p.device and ent[2] is p:
+        return ent[1]
+    src = p.detach()
+    flat = src.reshape(src.shape[0], -1)
+    if not flat.is_contiguous():
+        flat = flat.contiguous()
+    t = ops.to_bf16(flat)
+    _W16[key] = (ver, t, p)
+    return t
+
+
+def w16_cat(params, key_obj):
+    """bf16 [sum(out_i), in] concatenation of several nn.Linear weights (fused BERT q|k|v)."""
+    key = ("cat", id(key_obj))
+    vers = tuple(p._version for p in params)
+    ent = _W16.get(key)
+    if ent is not None and ent[0] == vers and ent[1].device == params[0].device:
+        return ent[1]
+    t = ops.to_bf16(torch.cat([p.detach() for p in params], 0).contiguous())
+    _W16[key] = (vers, t, key_obj)
+    return t
+
+
+def clear_weight_cache():
+    _W16.clear()
+
+
+def _zeros(n, device):
+    return torch.zeros(n, dtype=F32, device=device)
+
+
+def _wgrad(dy16, x16, out_features, in_features):
+    """dW[out,in] = dY^T X with split-K (dY [T,out], X [T,in], both bf16 row-major)."""
+    T = dy16.shape[0]
+    dW = torch.empty(out_features, in_features, dtype=F32, device=dy16.device)
+    ops.gemm(dy16, x16, dW, a_t=True, b_t=True, k_splits=ops.wgrad_splits(out_features, in_features, T))
+    return dW
+
+
+def _colsum(x, n):
+    out = torch.empty(1, n, dtype=F32, device=x.device)
+    ops.grouped_colsum(x, out)
+    return out.view(n)
+
+
+# ------------------------------------------------------------------------------------------------
+# generic linear (+bias, +GELU, +residual) on 2-D bf16 activations
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) (+ residual).  x bf16 [M,K]; W fp32 param [N,K]; out bf16 or fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, act, out_fp32, w_override):
+        M, K = x.shape
+        N = weight.shape[0]
+        wb = w_override if w_override is not None else w16(weight)
+        out = torch.empty(M, N, dtype=F32 if out_fp32 else BF16, device=x.device)
+        pre = torch.empty(M, N, dtype=BF16, device=x.device) if act == "gelu" else None
+        ops.gemm(x, wb, out, bias=bias, act=act, out_pre=pre, residual=residual)
+        ctx.save_for_backward(x, weight, pre)
+        ctx.has_bias, ctx.has_res, ctx.act, ctx.wb = bias is not None, residual is not None, act, wb
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, pre = ctx.saved_tensors
+        wb = ctx.wb
+        M, K = x.shape
+        N = weight.shape[0]
+        dy = dy.contiguous()
+        dy16 = dy if dy.dtype == BF16 else ops.to_bf16(dy)
+        dres = None
+        if ctx.has_res:
+            dres = dy16 if ctx.res_dtype == BF16 else (dy if dy.dtype == F32 else ops.cast(dy, torch.empty(dy.shape, dtype=F32, device=dy.device)))
+        if ctx.act == "gelu":
+            dpre = torch.empty_like(dy16)
+            _gelu_bwd(dy16, pre, dpre)
+            dy16 = dpre
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=BF16, device=x.device)
+            ops.gemm(dy16, wb, dx, b_t=True)
+        dW = _wgrad(dy16, x, N, K).view_as(weight) if ctx.needs_input_grad[1] else None
+        db = _colsum(dy16, N) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dW, db, dres, None, None, None
+
+
+def _gelu_bwd(dy16, pre16, out16):
+    ops.gelu(pre16, out16, dy=dy16)
+
+
+class GeluFn(torch.autograd.Function):
+    """Standalone exact GELU (after a LayerNorm in the projection heads)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.gelu(x, torch.empty_like(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.gelu(x, torch.empty_like(x), dy=dy.contiguous())
+
+
+def gelu(x):
+    return GeluFn.apply(x)
+
+
+def linear(x, weight, bias=None, residual=None, act=None, out_fp32=False, w_override=None):
+    return LinearFn.apply(x, weight, bias, residual, act, out_fp32, w_override)
+
+
+class MlpFn(torch.autograd.Function):
+    """y = fc2(GELU(fc1(x))) + residual with the GELU derivative fused into fc2's dgrad epilogue.
+    x bf16 [M,C]; residual (bf16 or fp32) [M,C_out]; out dtype = residual dtype (or bf16)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, out_fp32):
+        M = x.shape[0]
+        Hd, Co = w1.shape[0], w2.shape[0]
+        w1b, w2b = w16(w1), w16(w2)
+        pre = torch.empty(M, Hd, dtype=BF16, device=x.device)
+        act = torch.empty(M, Hd, dtype=BF16, device=x.device)
+        ops.gemm(x, w1b, act, bias=b1, act="gelu", out_pre=pre)
+        out = torch.empty(M, Co, dtype=F32 if out_fp32 else BF16, device=x.device)
+        ops.gemm(act, w2b, out, bias=b2, residual=residual)
+        ctx.save_for_backward(x, w1, w2, pre, act)
+        ctx.wb = (w1b, w2b)
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, pre, act = ctx.saved_tensors
+        w1b, w2b = ctx.wb
+        dy = dy.contiguous()
+        dy16 = dy if dy.dtype == BF16 else ops.to_bf16(dy)
+        dres = None
+        if ctx.res_dtype is not None:
+            dres = dy16 if ctx.res_dtype == BF16 else (dy if dy.dtype == F32 else ops.cast(dy, torch.empty(dy.shape, dtype=F32, device=dy.device)))
+        M, Hd = pre.shape
+        dpre = torch.empty(M, Hd, dtype=BF16, device=x.device)
+        ops.gemm(dy16, w2b, dpre, b_t=True, gelu_pre=pre)
+        dW2 = _wgrad(dy16, act, w2.shape[0], Hd)
+        db2 = _colsum(dy16, w2.shape[0])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.gemm(dpre, w1b, dx, b_t=True)
+        dW1 = _wgrad(dpre, x, Hd, x.shape[1])
+        db1 = _colsum(dpre, Hd)
+        return dx, dW1, db1, dW2, db2, dres, None
+
+
+def mlp(x, w1, b1, w2, b2, residual=None, out_fp32=False):
+    return MlpFn.apply(x, w1, b1, w2, b2, residual, out_fp32)
+
+
+# ------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """y = LN(x) for 2-D x (fp32 or bf16); y bf16 or fp32."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_fp32):
+        rows, C = x.shape
+        y = torch.empty(rows, C, dtype=F32 if out_fp32 else BF16, device=x.device)
+        mean = torch.empty(rows, dtype=F32, device=x.device)
+        rstd = torch.empty(rows, dtype=F32, device=x.device)
+        ops.layernorm_fwd(x, gamma, beta, eps, y, mean=mean, rstd=rstd)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        rows, C = x.shape
+        dy = dy.contiguous()
+        dx32 = torch.empty(rows, C, dtype=F32, device=x.device)
+        small = _zeros(2 * C, x.device)
+        copy = torch.empty(rows, C, dtype=BF16, device=x.device) if x.dtype == BF16 else None
+        ops.layernorm_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, rows=rows, dx=dx32, dx_copy=copy,
+                          dgamma=small[:C], dbeta=small[C:])
+        return (copy if copy is not None else dx32), small[:C], small[C:], None, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, out_fp32=False):
+    return LayerNormFn.apply(x, gamma, beta, eps, out_fp32)
+
+
+# ------------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    """softmax(q k^T + key_mask) v on packed bf16 qkv rows (q pre-scaled by the qkv GEMM epilogue)."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_mask, batch, seq, heads, hd, q_scale):
+        out = torch.empty(batch * seq, heads * hd, dtype=BF16, device=qkv.device)
+        lse = torch.empty(batch, heads, seq, dtype=F32, device=qkv.device)
+        ops.attention_fwd(qkv, batch, seq, heads, hd, out, lse, key_mask=key_mask)
+        ctx.save_for_backward(qkv, out, lse, key_mask)
+        ctx.dims = (batch, seq, heads, hd, q_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, key_mask = ctx.saved_tensors
+        batch, seq, heads, hd, q_scale = ctx.dims
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv, out, dout.contiguous(), lse, batch, seq, heads, hd, dqkv, q_scale, key_mask=key_mask)
+        return dqkv, None, None, None, None, None, None
+
+
+class QkvLinearFn(torch.autograd.Function):
+    """Fused q|k|v projection of a BERT layer: one GEMM against the concatenated weight, q columns
+    scaled by head_dim^-0.5 in the epilogue.  Gradients are split back to the three nn.Linear params."""
+
+    @staticmethod
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, scale, cache_key):
+        Hd = wq.shape[0]
+        wcat = w16_cat([wq, wk, wv], cache_key)
+        bcat = torch.cat([bq.detach(), bk.detach(), bv.detach()]).contiguous()
+        out = torch.empty(x.shape[0], 3 * Hd, dtype=BF16, device=x.device)
+        ops.gemm(x, wcat, out, bias=bcat, scale_cols=Hd, scale=scale)
+        ctx.save_for_backward(x)
+        ctx.wcat, ctx.Hd = wcat, Hd
+        return out
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        (x,) = ctx.saved_tensors
+        Hd, wcat = ctx.Hd, ctx.wcat
+        dqkv = dqkv.contiguous()
+        dx = torch.empty_like(x)
+        ops.gemm(dqkv, wcat, dx, b_t=True)
+        dW = _wgrad(dqkv, x, 3 * Hd, x.shape[1])
+        db = _colsum(dqkv, 3 * Hd)
+        return (dx, dW[:Hd], db[:Hd], dW[Hd:2 * Hd], db[Hd:2 * Hd], dW[2 * Hd:], db[2 * Hd:], None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# Video Swin
+# ------------------------------------------------------------------------------------------------
+class SwinBlockFn(torch.autograd.Function):
+    """One SwinTransformerBlock3D (swin_transformer_3d.py:485-505) on the fp32 channels-last residual
+    stream x [B*D*H*W, C].  7 launches forward; the window partition / roll / reverse copies of the
+    reference are folded into the LN gather and the proj-GEMM scatter epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, wg, heads, code, code_off, region,
+                n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b):
+        T, C = x.shape
+        hd = C // heads
+        dev = x.device
+        rows = wg.rows
+        wq, wp, w1, w2 = w16(qkv_w), w16(proj_w), w16(fc1_w), w16(fc2_w)
+        stats = torch.empty(2 * rows + 2 * T, dtype=F32, device=dev)
+        mean1, rstd1, mean2, rstd2 = stats[:rows], stats[rows:2 * rows], stats[2 * rows:2 * rows + T], stats[2 * rows + T:]
+        xw = torch.empty(rows, C, dtype=BF16, device=dev)
+        ops.layernorm_fwd(x, n1w, n1b, 1e-5, xw, mean=mean1, rstd=rstd1, window=wg)
+        qkv = torch.empty(rows, 3 * C, dtype=BF16, device=dev)
+        scale = hd ** -0.5
+        ops.gemm(xw, wq, qkv, bias=qkv_b, scale_cols=C, scale=scale)
+        ao = torch.empty(rows, C, dtype=BF16, device=dev)
+        batch = wg.B * wg.nwin
+        lse = torch.empty(batch, heads, wg.N, dtype=F32, device=dev)
+        ops.attention_fwd(qkv, batch, wg.N, heads, hd, ao, lse, bias_table=table, rel_code=code, code_off=code_off,
+                          region=region)
+        x_mid = torch.empty(T, C, dtype=F32, device=dev)
+        ops.gemm(ao, wp, x_mid, bias=proj_b, residual=x, window=wg)
+        h2 = torch.empty(T, C, dtype=BF16, device=dev)
+        ops.layernorm_fwd(x_mid, n2w, n2b, 1e-5, h2, mean=mean2, rstd=rstd2)
+        pre = torch.empty(T, fc1_w.shape[0], dtype=BF16, device=dev)
+        act = torch.empty(T, fc1_w.shape[0], dtype=BF16, device=dev)
+        ops.gemm(h2, w1, act, bias=fc1_b, act="gelu", out_pre=pre)
+        out = torch.empty(T, C, dtype=F32, device=dev)
+        ops.gemm(act, w2, out, bias=fc2_b, residual=x_mid)
+        ctx.save_for_backward(x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region,
+                              n1w, n1b, n2w, n2b, table)
+        ctx.w = (wq, wp, w1, w2)
+        ctx.meta = (wg, heads, hd, code_off, scale, fc1_w.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region, n1w, n1b, n2w, n2b, table) = ctx.saved_tensors
+        wq, wp, w1, w2 = ctx.w
+        wg, heads, hd, code_off, scale, Hd = ctx.meta
+        T, C = x.shape
+        rows = wg.rows
+        dev = x.device
+        mean1, rstd1, mean2, rstd2 = stats[:rows], stats[rows:2 * rows], stats[2 * rows:2 * rows + T], stats[2 * rows + T:]
+        dout = dout.contiguous()
+        small = _zeros(4 * C + table.numel(), dev)
+        dg1, db1, dg2, db2 = small[:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
+        dtable = small[4 * C:].view_as(table)
+        # ---- MLP branch
+        dy16 = ops.to_bf16(dout)
+        dpre = torch.empty(T, Hd, dtype=BF16, device=dev)
+        ops.gemm(dy16, w2, dpre, b_t=True, gelu_pre=pre)
+        dW2 = _wgrad(dy16, act, C, Hd)
+        dB2 = _colsum(dy16, C)
+        dh2 = dy16                                            # reuse the buffer: [T, C] bf16
+        ops.gemm(dpre, w1, dh2, b_t=True)
+        dW1 = _wgrad(dpre, h2, Hd, C)
+        dB1 = _colsum(dpre, Hd)
+        del dpre
+        # ---- LN2 backward: d x_mid = dout + LN2'(dh2); bf16 copy emitted in window order for proj
+        dmid = torch.empty(T, C, dtype=F32, device=dev)
+        dmid_w = (torch.zeros if wg.padded else torch.empty)(rows, C, dtype=BF16, device=dev)
+        ops.layernorm_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, rows=T, dx=dmid, dres=dout, dx_copy=dmid_w,
+                          copy_window=wg, dgamma=dg2, dbeta=db2)
+        # ---- attention branch
+        dao = torch.empty(rows, C, dtype=BF16, device=dev)
+        ops.gemm(dmid_w, wp, dao, b_t=True)
+        dWp = _wgrad(dmid_w, ao, C, C)
+        dBp = _colsum(dmid_w, C)
+        dqkv = torch.empty(rows, 3 * C, dtype=BF16, device=dev)
+        ops.attention_bwd(qkv, ao, dao, lse, wg.B * wg.nwin, wg.N, heads, hd, dqkv, scale, dbias_table=dtable,
+                          bias_table=table, rel_code=code, code_off=code_off, region=region)
+        dxw = dao                                             # reuse: [rows, C] bf16
+        ops.gemm(dqkv, wq, dxw, b_t=True)
+        dWq = _wgrad(dqkv, xw, 3 * C, C)
+        dBq = _colsum(dqkv, 3 * C)
+        # ---- LN1 backward through the window gather, accumulated onto d x_mid in place
+        ops.layernorm_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, rows=rows, dx=dmid, dres=dmid, dgamma=dg1, dbeta=db1,
+                          window=wg)
+        return (dmid, None, None, None, None, None,
+                dg1, db1, dWq, dBq, dtable, dWp, dBp, dg2, db2, dW1, dB1, dW2, dB2)
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """PatchEmbed3D (:671-688) + SimMIM mask-token blend (:222-230): patchify -> GEMM -> LN(+blend)."""
+
+    @staticmethod
+    def forward(ctx, imgs, weight, bias, nw, nb, mask, token, patch):
+        B = imgs.shape[0]
+        cols, (D, Hp, Wp) = ops.patchify(imgs.contiguous(), patch)
+        C = weight.shape[0]
+        T = cols.shape[0]
+        wb = w16(weight)
+        y = torch.empty(T, C, dtype=F32, device=imgs.device)
+        ops.gemm(cols, wb, y, bias=bias)
+        ctx.dims = (B, D, Hp, Wp, C)
+        if nw is None:
+            ctx.save_for_backward(cols)
+            ctx.norm = False
+            return y
+        out = torch.empty(T, C, dtype=F32, device=imgs.device)
+        stats = torch.empty(2 * T, dtype=F32, device=imgs.device)
+        blend = None
+        if mask is not None:
+            blend = (mask.reshape(B, mask.shape[-2], mask.shape[-1]).contiguous(), token.detach().reshape(-1).contiguous(),
+                     (D, Hp, Wp))
+        ops.layernorm_fwd(y, nw, nb, 1e-5, out, mean=stats[:T], rstd=stats[T:], blend=blend)
+        ctx.save_for_backward(cols, y, nw, nb, stats, blend[0] if blend else None, blend[1] if blend else None)
+        ctx.norm = True
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, D, Hp, Wp, C = ctx.dims
+        dout = dout.contiguous()
+        T = dout.shape[0]
+        dev = dout.device
+        dgn = dbn = dtok = None
+        if ctx.norm:
+            cols, y, nw, nb, stats, mask, token = ctx.saved_tensors
+            small = _zeros(3 * C, dev)
+            dgn, dbn = small[:C], small[C:2 * C]
+            dy = torch.empty(T, C, dtype=F32, device=dev)
+            dy16 = torch.empty(T, C, dtype=BF16, device=dev)
+            blend = (mask, token, (D, Hp, Wp)) if mask is not None else None
+            ops.layernorm_bwd(y, nw, nb, 1e-5, stats[:T], stats[T:], dout, rows=T, dx=dy, dx_copy=dy16, dgamma=dgn,
+                              dbeta=dbn, dtoken=small[2 * C:] if blend else None, blend=blend)
+            if blend:
+                dtok = small[2 * C:].view(1, C, 1, 1, 1)
+        else:
+            (cols,) = ctx.saved_tensors
+            dy16 = ops.to_bf16(dout)
+        dW = _wgrad(dy16, cols, C, cols.shape[1])
+        dB = _colsum(dy16, C)
+        return None, dW, dB, dgn, dbn, None, dtok, None
+
+
+class PatchMergeFn(torch.autograd.Function):
+    """PatchMerging (:521-544): 2x2 gather + LN(4C) in one kernel, then the bias-free reduction GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, dims, nw, nb, red_w):
+        B, D, H, W = dims
+        C = x.shape[1]
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        rows = B * D * H2 * W2
+        h = torch.empty(rows, 4 * C, dtype=BF16, device=x.device)
+        stats = torch.empty(2 * rows, dtype=F32, device=x.device)
+        ops.layernorm_fwd(x, nw, nb, 1e-5, h, mean=stats[:rows], rstd=stats[rows:], merge=(B, D, H, W, C))
+        wb = w16(red_w)
+        out = torch.empty(rows, red_w.shape[0], dtype=F32, device=x.device)
+        ops.gemm(h, wb, out)
+        ctx.save_for_backward(x, h, stats, nw, nb)
+        ctx.meta = (dims, wb, red_w.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, h, stats, nw, nb = ctx.saved_tensors
+        (B, D, H, W), wb, Co = ctx.meta
+        C = x.shape[1]
+        rows = h.shape[0]
+        dy16 = ops.to_bf16(dout.contiguous())
+        dh = torch.empty(rows, 4 * C, dtype=BF16, device=x.device)
+        ops.gemm(dy16, wb, dh, b_t=True)
+        dW = _wgrad(dy16, h, Co, 4 * C)
+        small = _zeros(8 * C, x.device)
+        dx = torch.empty_like(x)
+        ops.layernorm_bwd(x, nw, nb, 1e-5, stats[:rows], stats[rows:], dh, rows=rows, dx=dx, dgamma=small[:4 * C],
+                          dbeta=small[4 * C:], merge=(B, D, H, W, C))
+        return dx, None, small[:4 * C], small[4 * C:], dW
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling / embeddings / fusion input
+# ------------------------------------------------------------------------------------------------
+class MeanTokensFn(torch.autograd.Function):
+    """mean over the S tokens of each sample: x fp32 [B*S, C] -> fp32 [B, C]
+    (AdaptiveAvgPool3d((1,1,1)) of ssl_head.py:105-106 on channels-last tokens)."""
+
+    @staticmethod
+    def forward(ctx, x, B, S):
+        out = torch.empty(B, x.shape[1], dtype=F32, device=x.device)
+        ops.grouped_colsum(x, out, div=S, mod=B, scale=1.0 / S)
+        ctx.dims = (B, S, x.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, S, C = ctx.dims
+        dx = torch.empty(B * S, C, dtype=F32, device=dy.device)
+        ops.rows_affine(dx, B * S, C, bvec=dy.contiguous(), bdiv=S, bscale=1.0 / S)
+        return dx, None, None
+
+
+class BertEmbedFn(torch.autograd.Function):
+    """HF BertEmbeddings: LN(word[ids] + pos[l] + type[0]) -> bf16 [B*L, H]."""
+
+    @staticmethod
+    def forward(ctx, ids, word, pos, typ, gamma, beta, eps):
+        B, L = ids.shape
+        Hd = word.shape[1]
+        flat = ids.reshape(-1).contiguous()
+        out = torch.empty(B * L, Hd, dtype=BF16, device=word.device)
+        stats = torch.empty(2 * B * L, dtype=F32, device=word.device)
+        type0 = typ.detach()[0].contiguous()
+        posd = pos.detach()
+        ops.layernorm_fwd(word.detach(), gamma, beta, eps, out, rows=B * L, mean=stats[:B * L], rstd=stats[B * L:],
+                          row_index=flat, add0=type0, add1=(posd, 1, L))
+        ctx.save_for_backward(flat, word, pos, typ, gamma, beta, stats)
+        ctx.meta = (B, L, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        flat, word, pos, typ, gamma, beta, stats = ctx.saved_tensors
+        B, L, eps = ctx.meta
+        Hd = word.shape[1]
+        rows = B * L
+        dev = word.device
+        dx = torch.empty(rows, Hd, dtype=F32, device=dev)
+        small = _zeros(2 * Hd, dev)
+        ops.layernorm_bwd(word.detach(), gamma, beta, eps, stats[:rows], stats[rows:], dy.contiguous(), rows=rows, dx=dx,
+                          dgamma=small[:Hd], dbeta=small[Hd:], dx_dense=True, row_index=flat,
+                          add0=typ.detach()[0].contiguous(), add1=(pos.detach(), 1, L))
+        dword = torch.zeros_like(word)
+        ops.scatter_add_rows(dx, flat, dword)
+        dpos = torch.zeros_like(pos)
+        ops.grouped_colsum(dx, dpos[:L], div=1, mod=L)
+        dtyp = torch.zeros_like(typ)
+        ops.grouped_colsum(dx, dtyp[:1])
+        return None, dword, dpos, dtyp, small[:Hd], small[Hd:], None
+
+
+class FusionInputFn(torch.autograd.Function):
+    """cross_transformer.py:84-108: z = cat(LN(v + space + tempor + type0), t + type1) written
+    directly into one bf16 [B, T*S + L, H] buffer.  v bf16 [B*T*S, H] (fc_in output), t bf16 [B*L, H]."""
+
+    @staticmethod
+    def forward(ctx, v, t, space, tempor, type_emb, gamma, beta, B, T, S, L):
+        Hd = v.shape[1]
+        tot = T * S + L
+        z = torch.empty(B * tot, Hd, dtype=BF16, device=v.device)
+        stats = torch.empty(2 * B * T * S, dtype=F32, device=v.device)
+        ty = type_emb.detach()
+        sp = space.detach().reshape(-1, Hd)[:S].contiguous()
+        tp = tempor.detach().reshape(-1, Hd)[:T].contiguous()
+        ops.layernorm_fwd(v, gamma, beta, 1e-5, z, rows=B * T * S, mean=stats[:B * T * S], rstd=stats[B * T * S:],
+                          add0=ty[0].contiguous(), add1=(sp, 1, S), add2=(tp, S, T), group=(T * S, tot, 0))
+        ops.rows_affine(z, B * L, Hd, x=t, out_group=(L, tot, T * S), add0=ty[1].contiguous())
+        ctx.save_for_backward(v, space, tempor, type_emb, gamma, beta, stats, sp, tp)
+        ctx.meta = (B, T, S, L)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        v, space, tempor, type_emb, gamma, beta, stats, sp, tp = ctx.saved_tensors
+        B, T, S, L = ctx.meta
+        Hd = v.shape[1]
+        tot = T * S + L
+        rows = B * T * S
+        dev = v.device
+        dz = dz.contiguous()
+        dv32 = torch.empty(rows, Hd, dtype=F32, device=dev)
+        dv16 = torch.empty(rows, Hd, dtype=BF16, device=dev)
+        small = _zeros(2 * Hd, dev)
+        ty = type_emb.detach()
+        ops.layernorm_bwd(v, gamma, beta, 1e-5, stats[:rows], stats[rows:], dz, rows=rows, dx=dv32, dx_copy=dv16,
+                          dgamma=small[:Hd], dbeta=small[Hd:], add0=ty[0].contiguous(), add1=(sp, 1, S), add2=(tp, S, T),
+                          group=(T * S, tot, 0))
+        dt = torch.empty(B * L, Hd, dtype=BF16, device=dev)
+        ops.rows_affine(dt, B * L, Hd, x=dz, in_group=(L, tot, T * S))
+        dspace = torch.zeros_like(space)
+        ops.grouped_colsum(dv32, dspace.view(-1, Hd)[:S], div=1, mod=S)
+        dtempor = torch.zeros_like(tempor)
+        ops.grouped_colsum(dv32, dtempor.view(-1, Hd)[:T], div=S, mod=T)
+        dtype_emb = torch.zeros_like(type_emb)
+        ops.grouped_colsum(dv32, dtype_emb[:1])
+        ops.grouped_colsum(dt, dtype_emb[1:2])
+        return dv16, dt, dspace, dtempor, dtype_emb, small[:Hd], small[Hd:], None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+class NceRankFn(torch.autograd.Function):
+    """Returns (nce_loss, rank_loss) for already-gathered fp32 embeddings (query side first)."""
+
+    @staticmethod
+    def forward(ctx, temperature, margin, use_rank, eps, *embs):
+        embs = [e.contiguous().float() for e in embs]
+        losses, ws = ops.nce_rank_fwd(embs, temperature, margin, use_rank, eps)
+        ctx.ws = ws
+        ctx.meta = (len(embs) - 1, embs[0].shape[0], embs[0].shape[1], temperature, use_rank)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_nce, g_rank):
+        nblk, Bg, D, temperature, use_rank = ctx.meta
+        g_nce = g_nce.reshape(1).float().contiguous()
+        g_rank = g_rank.reshape(1).float().contiguous() if g_rank is not None else None
+        grads = ops.nce_rank_bwd(ctx.ws, nblk, Bg, D, temperature, use_rank, g_nce, g_rank)
+        return (None, None, None, None, *grads)
+
+
+class VocabFocalFn(torch.autograd.Function):
+    """decoder GEMM (hidden -> vocab) + softmax focal / CE over rows whose label != ignore_index.
+    h bf16 [rows, H]; decoder weight fp32 [V, H] (padded to a multiple of 8 rows in the bf16 cache)."""
+
+    @staticmethod
+    def forward(ctx, h, dec_w, dec_b, target, gamma, ignore_index):
+        rows, Hd = h.shape
+        V = dec_w.shape[0]
+        Vpad = (V + 7) // 8 * 8
+        key = ("vocab", id(dec_w))
+        ent = _W16.get(key)
+        ver = (dec_w._version, dec_b._version)
+        if ent is None or ent[0] != ver:
+            wpad = torch.zeros(Vpad, Hd, dtype=F32, device=h.device)
+            wpad[:V] = dec_w.detach()
+            bpad = torch.full((Vpad,), -1e30, dtype=F32, device=h.device)
+            bpad[:V] = dec_b.detach()
+            ent = (ver, (ops.to_bf16(wpad), bpad), dec_w)
+            _W16[key] = ent
+        wb, bpad = ent[1]
+        logits = torch.empty(rows, Vpad, dtype=F32, device=h.device)
+        ops.gemm(h, wb, logits, bias=bpad)
+        tgt = target.reshape(-1).contiguous()
+        loss, stats, sums = ops.softmax_focal_fwd(logits, tgt, V, gamma, ignore_index)
+        ctx.save_for_backward(h, logits, tgt, stats, sums)
+        ctx.meta = (V, Vpad, gamma, wb)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        h, logits, tgt, stats, sums = ctx.saved_tensors
+        V, Vpad, gamma, wb = ctx.meta
+        rows, Hd = h.shape
+        dl = torch.empty(rows, Vpad, dtype=BF16, device=h.device)
+        ops.softmax_focal_bwd(logits, tgt, V, gamma, stats, sums, g.reshape(1).float().contiguous(), dl)
+        dh = torch.empty_like(h)
+        ops.gemm(dl, wb, dh, b_t=True)
+        dW = _wgrad(dl, h, Vpad, Hd)[:V]
+        db = _colsum(dl, Vpad)[:V]
+        return dh, dW, db, None, None, None
+
+
+class LogitsFocalFn(torch.autograd.Function):
+    """softmax focal / CE on given logits (fp32 or bf16 [rows, V]) -- the losses' public forward."""
+
+    @staticmethod
+    def forward(ctx, logits, target, gamma, ignore_index):
+        lg = logits.float().contiguous()
+        tgt = target.reshape(-1).contiguous()
+        loss, stats, sums = ops.softmax_focal_fwd(lg, tgt, lg.shape[1], gamma, ignore_index)
+        ctx.save_for_backward(lg, tgt, stats, sums)
+        ctx.meta = (gamma, logits.dtype)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, tgt, stats, sums = ctx.saved_tensors
+        gamma, dt = ctx.meta
+        dl = torch.empty(lg.shape, dtype=dt if dt in (BF16, F32) else F32, device=lg.device)
+        ops.softmax_focal_bwd(lg, tgt, lg.shape[1], gamma, stats, sums, g.reshape(1).float().contiguous(), dl)
+        return dl, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+class CastFn(torch.autograd.Function):
+    """dtype conversion (fp32 <-> bf16) with the transposed conversion in backward."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        return ops.cast(x.contiguous(), torch.empty(x.shape, dtype=dtype, device=x.device))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.cast(dy.contiguous(), torch.empty(dy.shape, dtype=ctx.src, device=dy.device)), None
+
+
+def to_dtype(x, dtype):
+    return x if x.dtype == dtype else CastFn.apply(x, dtype)
+
+
+class WindowAttnFn(torch.autograd.Function):
+    """WindowAttention3D.forward (swin_transformer_3d.py:369-400) on windows: qkv GEMM (q-scale in
+    the epilogue) -> fused attention core -> proj GEMM.  x bf16 [B_*N, C] -> fp32 [B_*N, C]."""
+
+    @staticmethod
+    def forward(ctx, x, B_, N, heads, code, code_off, region, scale, qkv_w, qkv_b, table, proj_w, proj_b):
+        rows, C = x.shape
+        hd = C // heads
+        wq, wp = w16(qkv_w), w16(proj_w)
+        qkv = torch.empty(rows, 3 * C, dtype=BF16, device=x.device)
+        ops.gemm(x, wq, qkv, bias=qkv_b, scale_cols=C, scale=scale)
+        ao = torch.empty(rows, C, dtype=BF16, device=x.device)
+        lse = torch.empty(B_, heads, N, dtype=F32, device=x.device)
+        ops.attention_fwd(qkv, B_, N, heads, hd, ao, lse, bias_table=table, rel_code=code, code_off=code_off, region=region)
+        y = torch.empty(rows, C, dtype=F32, device=x.device)
+        ops.gemm(ao, wp, y, bias=proj_b)
+        ctx.save_for_backward(x, qkv, ao, lse, code, region, table)
+        ctx.meta = (B_, N, heads, hd, code_off, scale, wq, wp, qkv_b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, qkv, ao, lse, code, region, table = ctx.saved_tensors
+        B_, N, heads, hd, code_off, scale, wq, wp, has_qb = ctx.meta
+        rows, C = x.shape
+        dy16 = ops.to_bf16(dy.contiguous())
+        dao = torch.empty(rows, C, dtype=BF16, device=x.device)
+        ops.gemm(dy16, wp, dao, b_t=True)
+        dWp = _wgrad(dy16, ao, C, C)
+        dBp = _colsum(dy16, C)
+        dqkv = torch.empty(rows, 3 * C, dtype=BF16, device=x.device)
+        dtable = torch.zeros_like(table)
+        ops.attention_bwd(qkv, ao, dao, lse, B_, N, heads, hd, dqkv, scale, dbias_table=dtable, bias_table=table,
+                          rel_code=code, code_off=code_off, region=region)
+        dx = torch.empty_like(x)
+        ops.gemm(dqkv, wq, dx, b_t=True)
+        dWq = _wgrad(dqkv, x, 3 * C, C)
+        dBq = _colsum(dqkv, 3 * C) if has_qb else None
+        return dx, None, None, None, None, None, None, None, dWq, dBq, dtable, dWp, dBp
+
+
+class PaddedLinearFn(torch.autograd.Function):
+    """nn.Linear whose out_features is not a multiple of 8 (QA answer logits, 1-logit MC head): the
+    bf16 weight cache is zero-padded to the next multiple of 8 rows; x bf16 [M,K] -> fp32 [M,N]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        N, K = weight.shape
+        Np = (N + 7) // 8 * 8
+        key = ("padlin", id(weight))
+        ver = (weight._version, bias._version)
+        ent = _W16.get(key)
+        if ent is None or ent[0] != ver:
+            wp = torch.zeros(Np, K, dtype=F32, device=x.device)
+            wp[:N] = weight.detach()
+            bp = torch.zeros(Np, dtype=F32, device=x.device)
+            bp[:N] = bias.detach()
+            ent = (ver, (ops.to_bf16(wp), bp), weight)
+            _W16[key] = ent
+        wb, bp = ent[1]
+        out = torch.empty(x.shape[0], Np, dtype=F32, device=x.device)
+        ops.gemm(x, wb, out, bias=bp)
+        ctx.save_for_backward(x)
+        ctx.meta = (N, Np, wb)
+        return out[:, :N]
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, Np, wb = ctx.meta
+        dyp = torch.zeros(x.shape[0], Np, dtype=BF16, device=x.device)
+        dyp[:, :N] = dy
+        dx = torch.empty_like(x)
+        ops.gemm(dyp, wb, dx, b_t=True)
+        dW = _wgrad(dyp, x, Np, x.shape[1])[:N]
+        db = _colsum(dyp, Np)[:N]
+        return dx, dW, db

@@ -225,6 +225,17 @@ def to_bf16(src):
     return cast(src, torch.empty(src.shape, dtype=BF16, device=src.device))
 
 
+def gelu(x, y, dy=None):
+    """y = GELU(x), or y = dy * GELU'(x) when dy is given (contiguous tensors of equal size)."""
+    _need_cuda(x, y, dy)
+    n = x.numel()
+    if n % 4 or y.numel() != n or not (x.is_contiguous() and y.is_contiguous()) or (dy is not None and not dy.is_contiguous()):
+        raise ValueError("gelu: contiguous tensors with numel % 4 == 0 required")
+    _lib.check(_lib.load().clv_gelu(_ptr(x), _is_bf16(x), _ptr(dy), _is_bf16(dy) if dy is not None else 0, _ptr(y),
+                                   _is_bf16(y), n, _stream()), "clv_gelu")
+    return y
+
+
 def patchify(x, patch):
     """x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw] and (D,Hp,Wp)."""
     _need_cuda(x)

@@ -139,6 +139,10 @@ int clv_attention_bwd(const clv_attn_desc_t* desc, const void* qkv, const void* 
  * model.half() of core/hooks/fp16_utils.py:215-239; gradient-stream casts).  n % 4 == 0. */
 int clv_cast(const void* src, int src_is_bf16, void* dst, int dst_is_bf16, long long n, float scale, void* stream);
 
+/* Exact erf GELU (nn.GELU() in heads/ssl_head.py:53,67,183,259 and qa_head.py:14,63).  dy == NULL: y = GELU(x);
+ * otherwise y = dy * GELU'(x).  n % 4 == 0. */
+int clv_gelu(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, void* y, int y_is_bf16, long long n, void* stream);
+
 /* PatchEmbed3D's Conv3d(kernel == stride) as a patch matrix (swin_transformer_3d.py:665,671-681):
  * x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw], column order (c,kd,kh,kw); zero padding. */
 int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int F, int H, int W, int pd, int ph, int pw, void* stream);

@@ -1,0 +1,84 @@
+"""CPU-only: drop-in boundary -- registry selection by the reference's class names, constructor
+signatures of the shipped configs, and state-dict key/shape/dtype parity with the reference."""
+import json
+import os
+
+import pytest
+import torch
+
+from clover_b200 import registry
+
+
+def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024, hidden=768, vocab=30522,
+                 text_layers=12, fusion_layers=3, frames_half=4, **bert):
+    """The model dict of configs/exp_local/pretrain_webvid_cc3m.py:22-104 (+ swin3d_base_stride.py)."""
+    aux = ["token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask"]
+    return dict(
+        type="CloverPretrain", freeze_stage=None, separate_test=True, use_Cmask=True,
+        backbone=dict(type="SwinTransformer3D", stride=(2, 4, 4), mask_token=True, pretrained2d=False, pretrained=None,
+                      embed_dim=embed, depths=list(depths), num_heads=list(heads), patch_size=(2, 4, 4),
+                      window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True),
+        freeze_text_backbone=None, text_vocab_size=vocab,
+        mm_backbone=dict(type="CrossModalTransformerFromPretrained", use_text_cls=True, use_prompt=False,
+                         pretrained_model="bert-base-uncased", num_hidden_layers=fusion_layers, img_in_size=img_in,
+                         hidden_size=hidden, num_frames=frames_half, spacial_tokens=49, token_types=2,
+                         layer_norm_eps=1e-12, word_pos_start=False, **bert),
+        text_backbone=dict(type="BertFromPretrained", num_hidden_layers=text_layers,
+                           **(dict(bert, hidden_size=hidden) if bert else {})),
+        cls_head=None,
+        ssl_head=dict(type="NCEHeadForMM", visual_in_channels=img_in, text_in_channels=hidden, img_hidden_dim=hidden * 2,
+                      vts_embed_dim=hidden, ln=True, spatial_type="avg", text_agg_type="cls", dropout_ratio=0),
+        mlm_head=dict(type="MLMHead", hidden_size=hidden, vocab_size=vocab),
+        mlm_ssl_head=dict(V=dict(type="NCEHeadForVision", visual_in_channels=hidden, cross_in_channels=hidden,
+                                 hidden_dim=hidden, ln=True, vts_embed_dim=hidden, dropout_ratio=0),
+                          T=dict(type="NCEHeadForText", cross_in_channels=hidden, vts_embed_dim=hidden, text_bn=False,
+                                 dropout_ratio=0.0)),
+        mlm_loss=dict(type="SoftmaxFocalLossMultiClass", gamma=2.0), loss_type=dict(type="CrossEntropyLoss"),
+        ssl_loss=dict(type="ExclusiveNCEwithRankingLoss", temperature=0.05, use_rank=True, use_rank_ttm=True,
+                      use_rank_trtm=False, margin_ttm=5.0, margin_trtm=10.0),
+        symmetry_rank=True, train_cfg=dict(aux_info=aux))
+
+
+def test_registry_has_reference_names():
+    reg = registry.register_all()
+    for name in ("SwinTransformer3D", "BertFromPretrained", "CrossModalTransformerFromPretrained", "NCEHeadForMM",
+                 "NCEHeadForVision", "NCEHeadForText", "MLMHead", "QA_OE_Head", "QA_MC_head",
+                 "ExclusiveNCEwithRankingLoss", "NormSoftmaxLoss", "SoftmaxFocalLossMultiClass", "CrossEntropyLoss",
+                 "CloverPretrain", "CloverFinetune"):
+        assert name in reg
+    # same-name re-registration must need force=True, like mmcv's Registry
+    with pytest.raises(KeyError):
+        registry.MODELS.register_module(name="SwinTransformer3D", module=registry.MODELS.get("SwinTransformer3D"))
+
+
+def test_state_dict_matches_reference_swinb(golden_dir):
+    registry.register_all()
+    ref = json.load(open(os.path.join(golden_dir, "state_keys_pretrain_swinb.json")))
+    model = registry.build_model(pretrain_cfg())
+    sd = model.state_dict()
+    ours = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd.items()}
+    assert set(ours) == set(ref), (sorted(set(ours) ^ set(ref))[:20])
+    for k in ref:
+        assert ours[k] == ref[k], (k, ours[k], ref[k])
+    assert sum(p.numel() for p in model.parameters()) == 274604674       # 274.6 M
+    # reference-format checkpoints round-trip with strict=True; 4.6.1's persistent position_ids is tolerated
+    extra = dict(sd)
+    extra["text_backbone.bert.embeddings.position_ids"] = torch.arange(512)[None]
+    model.load_state_dict(extra, strict=True)
+
+
+def test_finetune_configs_build():
+    registry.register_all()
+    base = pretrain_cfg(embed=32, depths=(2, 2), heads=(1, 2), img_in=64, hidden=128, vocab=1000, text_layers=1,
+                        fusion_layers=1, frames_half=2, num_attention_heads=2, intermediate_size=256,
+                        max_position_embeddings=64, vocab_size=1000)
+    common = {k: base[k] for k in ("backbone", "mm_backbone", "text_backbone")}
+    r = registry.build_model(dict(type="CloverFinetune", task="retrieval", separate_test=True, ssl_head=base["ssl_head"],
+                                  loss_type=dict(type="NormSoftmaxLoss", temperature=0.05, cos_sim=True), **common))
+    assert hasattr(r, "ssl_head") and r.loss_func.use_cos_similarity
+    q = registry.build_model(dict(type="CloverFinetune", task="video_qa", answer_cls=True,
+                                  qa_head=dict(type="QA_OE_Head", hidden_dim=128, dropout_ratio=0.0, num_labels=1500),
+                                  loss_type=dict(type="CrossEntropyLoss"), **common))
+    assert q.qa_head.num_labels == 1500
+    with pytest.raises(NotImplementedError):
+        registry.build_model(dict(type="CloverFinetune", task="nope", **common))
