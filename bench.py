@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Headline benchmark: Clover pre-training clips/sec (BASELINE.json metric, config c3).
+
+    python bench.py --gpus N --steps K --warmup W            # clover_b200 arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU restatement of the reference
+                                                               (oracle/, the reference is pure Python and cannot
+                                                               travel to the GPU box) on the host cores
+
+A step = one pass of the hot path over one synthetic batch: CloverPretrain forward (2x Video Swin-B,
+2x BERT-base, 2x 3-layer fusion, heads, MLM focal + tri-modal NCE/ranking losses) + backward +
+data-parallel gradient all-reduce (N > 1) + AdamW update of the fp32 master weights.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clover_pretrain_clips_per_sec"
+UNIT = "clips/s"
+SWIN_B = dict(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024)
+FLOP_PER_CLIP_FWD_BWD = 885e9          # ~295 GFLOP fwd, x3 for fwd+bwd
+
+
+def model_cfg():
+    from clover_b200.configs import pretrain_cfg
+    return pretrain_cfg(SWIN_B["embed"], SWIN_B["depths"], SWIN_B["heads"], SWIN_B["img_in"], 768, 30522, 12, 3, 4)
+
+
+def workload_config(clips, n_gpus):
+    return {
+        "workload": "c3: CloverPretrain step, Video Swin-B + BERT-base text + 3-layer fusion, tri-modal NCE/ranking + MLM focal, "
+                    "fwd+bwd+grad-allreduce+AdamW",
+        "clips_per_gpu": clips, "frames": 8, "resolution": 224, "caption_tokens": 32, "global_batch": clips * n_gpus,
+        "parallelism": f"dp{n_gpus}", "dropout": 0.0, "drop_path": 0.0,
+        "optimizer": "torch.optim.AdamW(fused) on fp32 master weights, inside the timed region",
+        "l2_policy": "per-step inputs (308 MB of clips) and activations (tens of GB) far exceed the 126 MB L2",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1381.1), d.get("bf16_tflops", 1639.5), d.get("hbm_gbs", 6545.0), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, clips=2, seed=1000):
+    """The reference's algorithm (oracle port, fp32, plain PyTorch CPU ops) on the host cores: fwd + bwd of the same
+    pre-train step on a bounded sample of `clips` clips per step.  Returns (clips_per_sec, ms_per_step, cores)."""
+    import torch
+    from clover_b200.synthetic import make_batch, synth_state_dict
+    from oracle import clover_oracle as O
+    from oracle.state_shapes import pretrain_shapes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    shapes = pretrain_shapes(SWIN_B["embed"], list(SWIN_B["depths"]), list(SWIN_B["heads"]), SWIN_B["img_in"], 768, 3072,
+                             30522, 512, 12, 3, 4)
+    state = {k: v.requires_grad_(True) for k, v in synth_state_dict(shapes, 7).items()}
+    cfg = dict(depths=list(SWIN_B["depths"]), num_heads=list(SWIN_B["heads"]), text_layers=12, fusion_layers=3, bert_heads=12,
+               vocab=30522)
+    times = []
+    for it in range(warmup + steps):
+        batch = make_batch(clips, frames=8, L=32, seed=seed + it)
+        t0 = time.perf_counter()
+        losses, _ = O.pretrain_forward(state, batch, cfg)
+        O.total_loss(losses).backward()
+        for v in state.values():
+            v.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return clips / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    clips = 2
+    value, ms, cores = cpu_reference_run(args.steps, args.warmup, clips)
+    sample = f"{clips} clips/step of the c3 step (Swin-B + BERT-base + fusion, 8x224x224, L=32), fp32, fwd+bwd, no optimizer"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(64, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from clover_b200 import _lib, ops, registry
+    from clover_b200.synthetic import make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    registry.register_all()
+    torch.manual_seed(0)
+    model = registry.build_model(model_cfg()).to(dev)
+    model.train()
+    # parameters the reference never gives a gradient (text pooler, fusion's unused bert_embedding): keep DDP static
+    for n, p in model.named_parameters():
+        if ".pooler." in n or ".bert_embedding." in n:
+            p.requires_grad_(False)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
+                                                        gradient_as_bucket_view=True, bucket_cap_mb=100)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-7, betas=(0.9, 0.98), eps=1e-8,
+                            weight_decay=0.005, fused=True)
+    clips = args.clips
+    keys = ("imgs", "label", "token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")
+    host = {k: v.pin_memory() for k, v in make_batch(clips, frames=8, L=32, seed=1000 + rank).items()}
+    devb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+
+    def step(batch):
+        kw = {k: batch[k] for k in keys[2:]}
+        losses = net(batch["imgs"], batch["label"], return_loss=True, **kw)
+        loss = sum(v for k, v in losses.items() if "loss" in k)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(devb)
+    sync()
+    # ---- timed region 1: inputs resident in HBM ----------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ops.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(devb)
+    e1.record()
+    sync()
+    ms_total = e0.elapsed_time(e1)
+    prof = ops.profile_end()
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    value = world * clips / (ms_step / 1e3)
+    # ---- timed region 2: end to end through the public API with host buffers ----------------------
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss = step(b)
+        loss_host = loss.detach().float().cpu()            # device -> host read of the step's result
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * clips / (float(t) / args.steps / 1e3)
+
+    if rank == 0:
+        sus, burst, hbm, src = measured_peaks()
+        fam = {}
+        for f, fl, by, ms in prof:
+            a = fam.setdefault(f, [0.0, 0.0, 0.0, 0])
+            a[0] += fl; a[1] += by; a[2] += ms; a[3] += 1
+        g = fam.get("gemm", [0.0, 0.0, 1e-9, 1])
+        gemm_tflops = g[0] / (g[2] * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": gemm_tflops, "peak": sus,
+                    "unit": "TFLOP/s", "frac": gemm_tflops / sus, "traffic": traffic, "peak_source": f"{src} bf16_tflops_sustained",
+                    "launches_timed": g[3], "avg_launch_ms": g[2] / max(1, g[3]),
+                    "share_of_step": g[2] / (ms_step * args.steps),
+                    "families_ms_per_step": {k: v[2] / args.steps for k, v in fam.items()},
+                    "attn_core_tflops": (fam.get("attn_fwd", [0, 0, 1e-9])[0] + fam.get("attn_bwd", [0, 0, 1e-9])[0]) /
+                                        ((fam.get("attn_fwd", [0, 0, 1e-9])[2] + fam.get("attn_bwd", [0, 0, 1e-9])[2]) * 1e-3) / 1e12,
+                    "step_model_tflops": FLOP_PER_CLIP_FWD_BWD * clips / (ms_step * 1e-3) / 1e12}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_reference_run(1, 1, 2)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "2 clips of the same c3 step (fp32 oracle port, fwd+bwd), 1 warm-up + 1 timed step"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(clips, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(loss_host.numel() * 4)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "loss": float(loss_host), "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU (BASELINE config c3: 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

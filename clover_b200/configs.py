@@ -1,0 +1,32 @@
+"""Model dicts of the reference's shipped configs, as Python (configs/exp_local/*.py are mmcv config files;
+these helpers reproduce their ``model = dict(...)`` so tests, smoke() and bench.py build exactly that model)."""
+
+
+def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024, hidden=768, vocab=30522,
+                 text_layers=12, fusion_layers=3, frames_half=4, **bert):
+    """The model dict of configs/exp_local/pretrain_webvid_cc3m.py:22-104 (+ swin3d_base_stride.py)."""
+    aux = ["token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask"]
+    return dict(
+        type="CloverPretrain", freeze_stage=None, separate_test=True, use_Cmask=True,
+        backbone=dict(type="SwinTransformer3D", stride=(2, 4, 4), mask_token=True, pretrained2d=False, pretrained=None,
+                      embed_dim=embed, depths=list(depths), num_heads=list(heads), patch_size=(2, 4, 4),
+                      window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True),
+        freeze_text_backbone=None, text_vocab_size=vocab,
+        mm_backbone=dict(type="CrossModalTransformerFromPretrained", use_text_cls=True, use_prompt=False,
+                         pretrained_model="bert-base-uncased", num_hidden_layers=fusion_layers, img_in_size=img_in,
+                         hidden_size=hidden, num_frames=frames_half, spacial_tokens=49, token_types=2,
+                         layer_norm_eps=1e-12, word_pos_start=False, **bert),
+        text_backbone=dict(type="BertFromPretrained", num_hidden_layers=text_layers,
+                           **(dict(bert, hidden_size=hidden) if bert else {})),
+        cls_head=None,
+        ssl_head=dict(type="NCEHeadForMM", visual_in_channels=img_in, text_in_channels=hidden, img_hidden_dim=hidden * 2,
+                      vts_embed_dim=hidden, ln=True, spatial_type="avg", text_agg_type="cls", dropout_ratio=0),
+        mlm_head=dict(type="MLMHead", hidden_size=hidden, vocab_size=vocab),
+        mlm_ssl_head=dict(V=dict(type="NCEHeadForVision", visual_in_channels=hidden, cross_in_channels=hidden,
+                                 hidden_dim=hidden, ln=True, vts_embed_dim=hidden, dropout_ratio=0),
+                          T=dict(type="NCEHeadForText", cross_in_channels=hidden, vts_embed_dim=hidden, text_bn=False,
+                                 dropout_ratio=0.0)),
+        mlm_loss=dict(type="SoftmaxFocalLossMultiClass", gamma=2.0), loss_type=dict(type="CrossEntropyLoss"),
+        ssl_loss=dict(type="ExclusiveNCEwithRankingLoss", temperature=0.05, use_rank=True, use_rank_ttm=True,
+                      use_rank_trtm=False, margin_ttm=5.0, margin_trtm=10.0),
+        symmetry_rank=True, train_cfg=dict(aux_info=aux))

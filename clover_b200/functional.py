@@ -367,6 +367,7 @@ class PatchEmbedFn(torch.autograd.Function):
         y = torch.empty(T, C, dtype=F32, device=imgs.device)
         ops.gemm(cols, wb, y, bias=bias)
         ctx.dims = (B, D, Hp, Wp, C)
+        ctx.wshape = weight.shape
         if nw is None:
             ctx.save_for_backward(cols)
             ctx.norm = False
@@ -403,7 +404,7 @@ class PatchEmbedFn(torch.autograd.Function):
         else:
             (cols,) = ctx.saved_tensors
             dy16 = ops.to_bf16(dout)
-        dW = _wgrad(dy16, cols, C, cols.shape[1])
+        dW = _wgrad(dy16, cols, C, cols.shape[1]).view(ctx.wshape)
         dB = _colsum(dy16, C)
         return None, dW, dB, dgn, dbn, None, dtok, None
 

@@ -43,6 +43,40 @@ def _rowmajor2d(t, name):
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
+# ------------------------------------------------------------------------------------------------
+# optional per-launch CUDA-event timing (bench.py's roofline leg); off by default
+# ------------------------------------------------------------------------------------------------
+_PROF = None
+
+
+def profile_begin():
+    global _PROF
+    _PROF = []
+
+
+def profile_end():
+    """Returns [(family, algorithmic_flops, algorithmic_bytes, milliseconds)] after synchronising."""
+    global _PROF
+    rec, _PROF = _PROF or [], None
+    torch.cuda.synchronize()
+    return [(fam, fl, by, e0.elapsed_time(e1)) for fam, fl, by, e0, e1 in rec]
+
+
+def _prof_open():
+    if _PROF is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_close(e0, family, flops, nbytes):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _PROF.append((family, flops, nbytes, e0, e1))
+
+
 class Window:
     """Clamped window geometry of one Swin block call (get_window_size, swin_transformer_3d.py:302-315)."""
 
@@ -99,7 +133,9 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None,
         e.window = window.ref()
     e.k_splits, e.accumulate = int(k_splits), int(bool(accumulate))
     lib = _lib.load()
+    ev = _prof_open()
     _lib.check(lib.clv_gemm_bf16(_ptr(a), lda, int(a_t), _ptr(b), ldb, int(b_t), M, N, K, C.byref(e), _stream()), "clv_gemm_bf16")
+    _prof_close(ev, "gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * N)
     return out
 
 
@@ -193,7 +229,9 @@ def attention_fwd(qkv, batch, seq, heads, hd, out, lse, **bias):
     if qkv.dtype != BF16 or not qkv.is_contiguous() or qkv.shape != (batch * seq, 3 * heads * hd):
         raise ValueError(f"attention_fwd: qkv must be contiguous bf16 [{batch * seq}, {3 * heads * hd}], got {tuple(qkv.shape)} {qkv.dtype}")
     d = _attn_desc(batch, seq, heads, hd, **bias)
+    ev = _prof_open()
     _lib.check(_lib.load().clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
+    _prof_close(ev, "attn_fwd", 4.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 4)
     return out
 
 
@@ -204,8 +242,10 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
             raise ValueError(f"attention_bwd: {n} must be contiguous bf16")
     d = _attn_desc(batch, seq, heads, hd, **bias)
     ws = torch.empty(batch * heads * seq, dtype=F32, device=qkv.device)
+    ev = _prof_open()
     _lib.check(_lib.load().clv_attention_bwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
                                             float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd")
+    _prof_close(ev, "attn_bwd", 8.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 8)
     return dqkv
 
 

@@ -176,7 +176,7 @@ def test_loss_modules_vs_reference_golden(cb, golden_dir):
 
 
 def _pretrain_model(cb, embed, depths, heads, img_in, hidden, vocab, text_layers, fusion_layers, frames_half, bert):
-    from tests.test_modules_cpu import pretrain_cfg
+    from clover_b200.configs import pretrain_cfg
     cfg = pretrain_cfg(embed, depths, heads, img_in, hidden, vocab, text_layers, fusion_layers, frames_half, **bert)
     return cb.build_model(cfg).cuda()
 
