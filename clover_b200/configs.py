@@ -3,9 +3,11 @@ these helpers reproduce their ``model = dict(...)`` so tests, smoke() and bench.
 
 
 def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024, hidden=768, vocab=30522,
-                 text_layers=12, fusion_layers=3, frames_half=4, **bert):
+                 text_layers=12, fusion_layers=3, frames_half=4, bert_dropout=0.0, **bert):
     """The model dict of configs/exp_local/pretrain_webvid_cc3m.py:22-104 (+ swin3d_base_stride.py)."""
     aux = ["token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask"]
+    # HF BERT's dropout rates; the reference classes swallow unknown kwargs (bert_from_hugface.py:9, cross_transformer.py:15)
+    drop = dict(hidden_dropout_prob=bert_dropout, attention_probs_dropout_prob=bert_dropout)
     return dict(
         type="CloverPretrain", freeze_stage=None, separate_test=True, use_Cmask=True,
         backbone=dict(type="SwinTransformer3D", stride=(2, 4, 4), mask_token=True, pretrained2d=False, pretrained=None,
@@ -15,9 +17,9 @@ def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1
         mm_backbone=dict(type="CrossModalTransformerFromPretrained", use_text_cls=True, use_prompt=False,
                          pretrained_model="bert-base-uncased", num_hidden_layers=fusion_layers, img_in_size=img_in,
                          hidden_size=hidden, num_frames=frames_half, spacial_tokens=49, token_types=2,
-                         layer_norm_eps=1e-12, word_pos_start=False, **bert),
+                         layer_norm_eps=1e-12, word_pos_start=False, **drop, **bert),
         text_backbone=dict(type="BertFromPretrained", num_hidden_layers=text_layers,
-                           **(dict(bert, hidden_size=hidden) if bert else {})),
+                           **drop, **(dict(bert, hidden_size=hidden) if bert else {})),
         cls_head=None,
         ssl_head=dict(type="NCEHeadForMM", visual_in_channels=img_in, text_in_channels=hidden, img_hidden_dim=hidden * 2,
                       vts_embed_dim=hidden, ln=True, spatial_type="avg", text_agg_type="cls", dropout_ratio=0),
