@@ -82,6 +82,7 @@ SIGNATURES = {
     "clv_layernorm_fwd": (C.c_int, [C.POINTER(LnDesc), c_vp, C.c_int, c_ll, c_vp]),
     "clv_layernorm_bwd": (C.c_int, [C.POINTER(LnDesc), C.POINTER(LnBwd), c_vp]),
     "clv_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
+    "clv_attention_fwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, c_vp]),
     "clv_gelu": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, c_vp]),

@@ -1,0 +1,301 @@
+// Window-attention core on tcgen05 / TMEM / TMA (sm_100a), head_dim 32 -- forward.
+//
+// Work unit = (window b, head h, query tile t of <= 128 rows).  Per unit:
+//   TMA   : Q tile [128 x 32], K [NK x 32], V [NK x 32] of head h straight out of the packed qkv rows
+//           (64-byte rows, SWIZZLE_64B) -- the reference's reshape/permute of
+//           swin_transformer_3d.py:376-377 is just the TMA coordinate;
+//   UMMA  : S = Q K^T  (M=128, N=NK<=2x208, K=32) into tensor memory;
+//   warps : one thread per query row (= TMEM lane): + relative-position bias (table[code_i - code_j + off],
+//           :382-385) + shift mask (region ids, :388-390), row max, exp2, row sum -- no shuffles, the
+//           row lives in one thread; P is written back in place as packed bf16;
+//   UMMA  : O = P V  with P as the TMEM A-operand and V as an MN-major smem operand (K = NK);
+//   warps : O / rowsum -> bf16 -> global, log-sum-exp saved for the backward.
+// Roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue.
+// Two CTAs per SM (256 TMEM columns each) hide each other's MMA / TMA latency; a CTA double-buffers
+// the next unit's Q/K/V in shared memory.
+#include <algorithm>
+
+#include "common.cuh"
+#include "clover_b200.h"
+
+namespace clv {
+
+constexpr int TC_HD = 32;
+constexpr int TC_ROWB = TC_HD * 2;           // bytes per Q/K/V row (64)
+constexpr int TC_THREADS = 192;
+constexpr float TC_LOG2E = 1.4426950408889634f;
+
+struct AttnTcArgs {
+  int batch, seq, heads;
+  int nk;                       // keys padded to a multiple of 32
+  int n_qt, rows_per_tile;
+  int kv_boxes, kv_box_rows;    // TMA boxes per K / V load
+  int kb_bytes;                 // bytes reserved per K (or V) buffer, multiple of 1024
+  int tmem_cols;
+  long long units;
+  __nv_bfloat16* out;
+  float* lse;
+  const float* bias_table; int table_len; const int* rel_code; int code_off;
+  const int* region; int nwin;
+};
+
+CLV_DEVICE float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = 8192 + 2 * a.kb_bytes;
+  float* sTable = reinterpret_cast<float*>(smem + 2 * stage_bytes);
+  int* sCode = reinterpret_cast<int*>(sTable + ((a.table_len + 3) & ~3));
+  int* sReg = sCode + a.nk;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sReg + a.nk) + 7) & ~uintptr_t(7));
+  uint64_t* full_bar = bars;          // [2]
+  uint64_t* empty_bar = bars + 2;     // [2]
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_ready = bars + 5;
+  uint64_t* o_full = bars + 6;
+  uint64_t* s_free = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.heads * TC_HD;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(s_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (warp >= 2) {
+    for (int j = threadIdx.x - 64; j < a.nk; j += 128) sCode[j] = (a.rel_code && j < a.seq) ? a.rel_code[j] : 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int t = (int)(u % a.n_qt);
+        const long long bh = u / a.n_qt;
+        const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+        const int stage = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sQ = smem + stage * stage_bytes;
+        uint8_t* sK = sQ + 8192;
+        uint8_t* sV = sK + a.kb_bytes;
+        mbar_expect_tx(&full_bar[stage], 8192 + 2 * a.nk * TC_ROWB);
+        const int row0 = b * a.seq;
+        tma_load_2d(sQ, &tm_q, &full_bar[stage], h * TC_HD, row0 + t * a.rows_per_tile);
+        for (int i = 0; i < a.kv_boxes; ++i) {
+          tma_load_2d(sK + i * a.kv_box_rows * TC_ROWB, &tm_kv, &full_bar[stage], C + h * TC_HD, row0 + i * a.kv_box_rows);
+          tma_load_2d(sV + i * a.kv_box_rows * TC_ROWB, &tm_kv, &full_bar[stage], 2 * C + h * TC_HD, row0 + i * a.kv_box_rows);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_pv = make_idesc_bf16(128, TC_HD, 0, 1);
+      // S-MMA column chunks (N <= 256, multiple of 16)
+      const int n0 = a.nk <= 256 ? a.nk : ((a.nk / 2 + 15) & ~15);
+      const int n1 = a.nk - n0;
+      uint32_t it = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(s_free, (it & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
+        const uint32_t k_addr = q_addr + 8192;
+        const uint32_t v_addr = k_addr + a.kb_bytes;
+#pragma unroll
+        for (int k = 0; k < TC_HD / 16; ++k) {
+          const uint64_t da = make_smem_desc(q_addr + k * 32, 16, 512, 4);
+          umma_bf16_ss(tmem_base, da, make_smem_desc(k_addr + k * 32, 16, 512, 4), make_idesc_bf16(128, n0, 0, 0), k > 0);
+        }
+        if (n1 > 0) {
+#pragma unroll
+          for (int k = 0; k < TC_HD / 16; ++k) {
+            const uint64_t da = make_smem_desc(q_addr + k * 32, 16, 512, 4);
+            umma_bf16_ss(tmem_base + n0, da, make_smem_desc(k_addr + n0 * TC_ROWB + k * 32, 16, 512, 4),
+                         make_idesc_bf16(128, n1, 0, 0), k > 0);
+          }
+        }
+        umma_commit(s_full);
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        const uint32_t tmem_o = tmem_base + (a.nk - TC_HD);
+        for (int kk = 0; kk < a.nk / 16; ++kk)
+          umma_bf16_ts(tmem_o, tmem_base + kk * 8, make_smem_desc(v_addr + kk * 1024, 16, 512, 4), idesc_pv, kk > 0);
+        umma_commit(o_full);
+        umma_commit(&empty_bar[stage]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool use_region = a.region != nullptr;
+    int cur_h = -1;
+    uint32_t it = 0;
+    for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      const int t = (int)(u % a.n_qt);
+      const long long bh = u / a.n_qt;
+      const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+      const int i = t * a.rows_per_tile + r;
+      const bool valid = r < a.rows_per_tile && i < a.seq;
+      const bool warp_active = (quarter * 32) < a.rows_per_tile && (t * a.rows_per_tile + quarter * 32) < a.seq;
+      // ---- per-unit tables
+      named_bar_sync(1, 128);
+      if (h != cur_h) {
+        if (a.bias_table)
+          for (int x = tid; x < a.table_len; x += 128) sTable[x] = a.bias_table[(long long)x * a.heads + h];
+        cur_h = h;
+      }
+      if (use_region) {
+        const int* rg = a.region + (long long)(b % a.nwin) * a.seq;
+        for (int j = tid; j < a.nk; j += 128) sReg[j] = j < a.seq ? rg[j] : 0;
+      }
+      named_bar_sync(1, 128);
+      const int ci = (valid ? sCode[i] : 0) + a.code_off;
+      const int ri = (valid && use_region) ? sReg[i] : 0;
+
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float m = -1.0e30f, l = 0.f;
+      if (warp_active) {
+        // ---- pass 1: s += bias (+ mask); row max; biased scores written back to TMEM
+#pragma unroll 1
+        for (int c0 = 0; c0 < a.nk; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+          if (a.bias_table) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + sTable[ci - sCode[c0 + j]]);
+          }
+          if (use_region) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (sReg[c0 + j] != ri) v[j] = __float_as_uint(__uint_as_float(v[j]) - 100.0f);
+          }
+          if (c0 + 32 > a.seq) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j >= a.seq) v[j] = __float_as_uint(-1.0e30f);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          uint32_t lo[16], hi[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { lo[j] = v[j]; hi[j] = v[16 + j]; }
+          tmem_st_32x16(taddr + c0, lo);
+          tmem_st_32x16(taddr + c0 + 16, hi);
+        }
+        tmem_st_wait();
+        // ---- pass 2: p = exp(s - m), row sum, packed bf16 P written in place (columns [0, nk/2))
+        const float mL = m * TC_LOG2E;
+#pragma unroll 1
+        for (int c0 = 0; c0 < a.nk; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), TC_LOG2E, -mL));
+            const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), TC_LOG2E, -mL));
+            l += p0 + p1;
+            pk[j] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x16(taddr + (c0 >> 1), pk);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+
+      // ---- epilogue: O / l -> bf16 -> global; lse
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      if (warp_active) {
+        uint32_t o[32];
+        tmem_ld_32x32(taddr + (a.nk - TC_HD), o);
+        tmem_ld_wait();
+        if (valid) {
+          const float inv = 1.0f / l;
+          uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)b * a.seq + i) * C + h * TC_HD);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8]) * inv, __uint_as_float(o[q * 8 + 1]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv));
+          a.lse[((long long)b * a.heads + h) * a.seq + i] = m + logf(l);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+}  // namespace clv
+
+using namespace clv;
+
+// head_dim 32 forward on tensor memory; same contract as clv_attention_fwd (key_mask unsupported).
+extern "C" int clv_attention_fwd_tc(const clv_attn_desc_t* d, const void* qkv, void* out, float* lse, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(d && qkv && out && lse, "attention_fwd_tc: null pointer");
+  CLV_REQUIRE(d->head_dim == 32 && !d->key_mask, "attention_fwd_tc: head_dim 32 without key mask only");
+  CLV_REQUIRE(d->seq >= 33 && d->seq <= 416, "attention_fwd_tc: seq must be in [33, 416] (got %d)", d->seq);
+  CLV_REQUIRE(!d->bias_table || (d->rel_code && d->table_len > 0), "attention_fwd_tc: bias_table needs rel_code");
+  AttnTcArgs a{};
+  a.batch = d->batch; a.seq = d->seq; a.heads = d->heads;
+  a.nk = (d->seq + 31) / 32 * 32;
+  a.n_qt = (d->seq + 127) / 128;
+  a.rows_per_tile = (d->seq + a.n_qt - 1) / a.n_qt;
+  a.kv_boxes = a.nk <= 256 ? 1 : 2;
+  a.kv_box_rows = a.nk / a.kv_boxes;
+  a.kb_bytes = (a.nk * TC_ROWB + 1023) / 1024 * 1024;
+  a.tmem_cols = a.nk <= 256 ? 256 : 512;
+  a.units = (long long)d->batch * d->heads * a.n_qt;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse;
+  a.bias_table = d->bias_table; a.table_len = d->bias_table ? d->table_len : 0; a.rel_code = d->rel_code; a.code_off = d->code_off;
+  a.region = d->region; a.nwin = d->nwin > 0 ? d->nwin : 1;
+  const long long rows = (long long)d->batch * d->seq;
+  const long long ld = 3LL * d->heads * TC_HD;
+  CUtensorMap tq, tkv;
+  if (int rc = make_tmap_bf16_2d(&tq, qkv, ld, rows, ld, TC_HD, 128, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tkv, qkv, ld, rows, ld, TC_HD, a.kv_box_rows, 64)) return rc;
+  const size_t smem = 1024 + 2 * (size_t)(8192 + 2 * a.kb_bytes) + (size_t)((a.table_len + 3) & ~3) * 4 + (size_t)a.nk * 8 + 8 + 128;
+  CLV_REQUIRE(smem <= 227 * 1024, "attention_fwd_tc: %zu bytes of shared memory needed", smem);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int per_sm = (a.tmem_cols == 256 && smem <= 110 * 1024) ? 2 : 1;
+  const int grid = (int)std::min<long long>(a.units, (long long)num_sms() * per_sm);
+  attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tq, tkv, a);
+  return after_launch("attn_fwd_tc_kernel");
+}

@@ -282,7 +282,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 tensor map: inner dimension `inner` (contiguous), outer `outer`, row pitch ld elements.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
-                      int box_inner, int box_outer) {
+                      int box_inner, int box_outer, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   CLV_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
   CLV_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
@@ -292,7 +292,10 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long l
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CLV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r, inner,
               outer, ld);

@@ -5,6 +5,7 @@ contiguity, takes ``tensor.data_ptr()`` and calls into libclover_b200.so on the 
 CUDA tensors are mandatory -- there is no CPU path.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -47,6 +48,8 @@ def _rowmajor2d(t, name):
 # optional per-launch CUDA-event timing (bench.py's roofline leg); off by default
 # ------------------------------------------------------------------------------------------------
 _PROF = None
+# head_dim-32 window attention runs on the tcgen05 kernel; the mma.sync kernel serves head_dim 64 (BERT / fusion)
+USE_TC_ATTENTION = os.environ.get("CLOVER_B200_TC_ATTENTION", "1") != "0"
 
 
 def profile_begin():
@@ -230,7 +233,11 @@ def attention_fwd(qkv, batch, seq, heads, hd, out, lse, **bias):
         raise ValueError(f"attention_fwd: qkv must be contiguous bf16 [{batch * seq}, {3 * heads * hd}], got {tuple(qkv.shape)} {qkv.dtype}")
     d = _attn_desc(batch, seq, heads, hd, **bias)
     ev = _prof_open()
-    _lib.check(_lib.load().clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
+    lib = _lib.load()
+    if hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 416 and USE_TC_ATTENTION:
+        _lib.check(lib.clv_attention_fwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd_tc")
+    else:
+        _lib.check(lib.clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
     _prof_close(ev, "attn_fwd", 4.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 4)
     return out
 

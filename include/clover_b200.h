@@ -126,6 +126,8 @@ typedef struct {
 } clv_attn_desc_t;
 
 int clv_attention_fwd(const clv_attn_desc_t* desc, const void* qkv, void* out, float* lse, void* stream);
+/* Same contract on tcgen05 / TMEM / TMA: head_dim 32, 33 <= seq <= 416, no key_mask (the Video Swin windows). */
+int clv_attention_fwd_tc(const clv_attn_desc_t* desc, const void* qkv, void* out, float* lse, void* stream);
 /* dqkv: bf16 same layout as qkv (dq already multiplied by q_scale so it is d/d(unscaled q));
  * dbias_table: fp32 [table_len, heads] ACCUMULATED (may be NULL). */
 int clv_attention_bwd(const clv_attn_desc_t* desc, const void* qkv, const void* out, const void* dout,
