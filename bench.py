@@ -235,8 +235,8 @@ def run_ours(args):
                     "launches_timed": g[3], "avg_launch_ms": g[2] / max(1, g[3]),
                     "share_of_step": g[2] / (ms_step * args.steps),
                     "families_ms_per_step": {k: v[2] / args.steps for k, v in fam.items()},
-                    "attn_core_tflops": (fam.get("attn_fwd", [0, 0, 1e-9])[0] + fam.get("attn_bwd", [0, 0, 1e-9])[0]) /
-                                        ((fam.get("attn_fwd", [0, 0, 1e-9])[2] + fam.get("attn_bwd", [0, 0, 1e-9])[2]) * 1e-3) / 1e12,
+                    "window_attn_core_tflops": (fam.get("attn_fwd_hd32", [0, 0, 1e-9])[0] + fam.get("attn_bwd_hd32", [0, 0, 1e-9])[0]) /
+                                               ((fam.get("attn_fwd_hd32", [0, 0, 1e-9])[2] + fam.get("attn_bwd_hd32", [0, 0, 1e-9])[2]) * 1e-3) / 1e12,
                     "step_model_tflops": FLOP_PER_CLIP_FWD_BWD * clips / (ms_step * 1e-3) / 1e12}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -84,6 +84,8 @@ SIGNATURES = {
     "clv_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_fwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
+    "clv_attention_bwd_tc_workspace_bytes": (c_ll, [C.POINTER(AttnDesc), C.c_int]),
+    "clv_attention_bwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, c_vp]),
     "clv_gelu": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, c_vp]),
     "clv_patchify": (C.c_int, [c_vp, c_vp] + [C.c_int] * 8 + [c_vp]),

@@ -495,6 +495,14 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(AttnArgs a) {
   }
 }
 
+int launch_attn_bwd_prep(const void* out, const void* dout, float* dsum, long long rows, int heads, int hd, int seq,
+                         cudaStream_t stream) {
+  const long long n = rows * heads;
+  attn_bwd_prep_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                                 reinterpret_cast<const __nv_bfloat16*>(dout), dsum, rows, heads, hd, seq);
+  return after_launch("attn_bwd_prep_kernel");
+}
+
 static int attn_common_checks(const clv_attn_desc_t* d) {
   CLV_REQUIRE(d != nullptr, "attention: null descriptor");
   CLV_REQUIRE(d->head_dim == 32 || d->head_dim == 64, "attention: head_dim must be 32 or 64 (got %d)", d->head_dim);

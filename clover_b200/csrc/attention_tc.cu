@@ -299,3 +299,384 @@ extern "C" int clv_attention_fwd_tc(const clv_attn_desc_t* d, const void* qkv, v
   attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tq, tkv, a);
   return after_launch("attn_fwd_tc_kernel");
 }
+
+// =================================================================================================
+// Backward (head_dim 32, seq <= 224).  Unit = (window b, head h); inner loop over key tiles t.
+//   UMMA 1 : S^T = K_t Q^T  and  dP^T = V_t dO^T   (M = 128 keys, N = NQ queries, K = 32)   -> TMEM
+//   warps  : one thread per key row j: p = exp(s + bias - lse_i), ds = p (dp - D_i); P^T and dS^T are
+//            written back in place as packed bf16 (TMEM A-operands); dS^T also goes to shared memory
+//            (MN-major, SWIZZLE_128B) for the dQ product and to global (bf16) for the bias-table gradient
+//   UMMA 2 : dV_t = P^T dO, dK_t = dS^T Q  (A from TMEM), dQ += dS K_t (A from smem, accumulated in TMEM
+//            across the key tiles of the unit)
+//   warps  : dK_t / dV_t (and at the end of the unit dQ * q_scale) -> bf16 -> packed dqkv rows.
+// The reference's autograd reduces d(bias) over all windows with index_put_(accumulate) on an fp16 dS
+// tensor; here dS^T is stored once in bf16 and reduced by dbias_reduce_kernel into the (2535, nH) table.
+// =================================================================================================
+struct AttnTcBwdArgs {
+  int batch, seq, heads;
+  int nq;                       // queries padded to a multiple of 32 (<= 224)
+  int n_kt, rows_per_tile;      // key tiling
+  int n_mq;                     // 128-row query tiles of the dQ accumulator
+  int qb_bytes;                 // bytes per Q (or dO) buffer, multiple of 1024
+  int tmem_cols;
+  long long units;
+  const float* lse; const float* dsum;
+  __nv_bfloat16* dqkv; float q_scale;
+  __nv_bfloat16* ds_out;        // [batch, heads, seq, nq] bf16 or nullptr
+  const float* bias_table; int table_len; const int* rel_code; int code_off;
+  const int* region; int nwin;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_tile,
+                   const __grid_constant__ CUtensorMap tm_do_full, AttnTcBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // layout: [Q0 dO0 Q1 dO1] [K0 V0 K1 V1] [dS^T tile] tables barriers
+  uint8_t* sQdO = smem;
+  uint8_t* sKV = sQdO + 4 * a.qb_bytes;
+  uint8_t* sDS = sKV + 4 * 8192;
+  const int ds_bytes = a.n_mq * 2 * 16384;
+  float* sTable = reinterpret_cast<float*>(sDS + ds_bytes);
+  float* sLse = sTable + ((a.table_len + 3) & ~3);
+  float* sD = sLse + a.nq;
+  int* sCode = reinterpret_cast<int*>(sD + a.nq);
+  int* sReg = sCode + a.nq;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sReg + a.nq) + 7) & ~uintptr_t(7));
+  uint64_t* qdo_full = bars;        // [2]
+  uint64_t* qdo_empty = bars + 2;   // [2]
+  uint64_t* kv_full = bars + 4;     // [2]
+  uint64_t* kv_empty = bars + 6;    // [2]
+  uint64_t* st_full = bars + 8;
+  uint64_t* p_ready = bars + 9;
+  uint64_t* mma2_done = bars + 10;
+  uint64_t* acc_free = bars + 11;
+  uint64_t* dq_free = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.heads * TC_HD;
+  const int NQ = a.nq;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv_full); tma_prefetch_desc(&tm_qkv_tile); tma_prefetch_desc(&tm_do_full);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(st_full, 1); mbar_init(p_ready, 4); mbar_init(mma2_done, 1); mbar_init(acc_free, 4); mbar_init(dq_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (warp >= 2) {
+    const int tid = threadIdx.x - 64;
+    for (int j = tid; j < NQ; j += 128) sCode[j] = (a.rel_code && j < a.seq) ? a.rel_code[j] : 0;
+    for (int x = tid; x < ds_bytes / 16; x += 128) reinterpret_cast<uint4*>(sDS)[x] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t col_dv = NQ - TC_HD, col_dp = NQ, col_dk = 2 * NQ - TC_HD, col_dq = 2 * NQ;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, tt = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+        const int us = it & 1;
+        mbar_wait(&qdo_empty[us], ((it >> 1) & 1) ^ 1);
+        uint8_t* sQ = sQdO + us * 2 * a.qb_bytes;
+        uint8_t* sDO = sQ + a.qb_bytes;
+        mbar_expect_tx(&qdo_full[us], 2 * NQ * TC_ROWB);
+        const int row0 = b * a.seq;
+        tma_load_2d(sQ, &tm_qkv_full, &qdo_full[us], h * TC_HD, row0);
+        tma_load_2d(sDO, &tm_do_full, &qdo_full[us], h * TC_HD, row0);
+        for (int t = 0; t < a.n_kt; ++t, ++tt) {
+          const int ts = tt & 1;
+          mbar_wait(&kv_empty[ts], ((tt >> 1) & 1) ^ 1);
+          uint8_t* sK = sKV + ts * 2 * 8192;
+          mbar_expect_tx(&kv_full[ts], 2 * 8192);
+          tma_load_2d(sK, &tm_qkv_tile, &kv_full[ts], C + h * TC_HD, row0 + t * a.rows_per_tile);
+          tma_load_2d(sK + 8192, &tm_qkv_tile, &kv_full[ts], 2 * C + h * TC_HD, row0 + t * a.rows_per_tile);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_st = make_idesc_bf16(128, NQ, 0, 0);
+      const uint32_t idesc_ts = make_idesc_bf16(128, TC_HD, 0, 1);
+      const uint32_t idesc_dq = make_idesc_bf16(128, TC_HD, 1, 1);
+      uint32_t it = 0, tt = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int us = it & 1;
+        mbar_wait(&qdo_full[us], (it >> 1) & 1);
+        mbar_wait(dq_free, (it & 1) ^ 1);
+        const uint32_t q_addr = smem_u32(sQdO + us * 2 * a.qb_bytes);
+        const uint32_t do_addr = q_addr + a.qb_bytes;
+        for (int t = 0; t < a.n_kt; ++t, ++tt) {
+          const int ts = tt & 1;
+          mbar_wait(&kv_full[ts], (tt >> 1) & 1);
+          mbar_wait(acc_free, (tt & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sKV + ts * 2 * 8192);
+          const uint32_t v_addr = k_addr + 8192;
+#pragma unroll
+          for (int k = 0; k < TC_HD / 16; ++k)
+            umma_bf16_ss(tmem_base, make_smem_desc(k_addr + k * 32, 16, 512, 4), make_smem_desc(q_addr + k * 32, 16, 512, 4),
+                         idesc_st, k > 0);
+#pragma unroll
+          for (int k = 0; k < TC_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + col_dp, make_smem_desc(v_addr + k * 32, 16, 512, 4),
+                         make_smem_desc(do_addr + k * 32, 16, 512, 4), idesc_st, k > 0);
+          umma_commit(st_full);
+          mbar_wait(p_ready, tt & 1);
+          tc_fence_after();
+          for (int kk = 0; kk < NQ / 16; ++kk) {   // dV_t = P^T dO ; dK_t = dS^T Q   (K = queries)
+            umma_bf16_ts(tmem_base + col_dv, tmem_base + kk * 8, make_smem_desc(do_addr + kk * 1024, 16, 512, 4), idesc_ts, kk > 0);
+            umma_bf16_ts(tmem_base + col_dk, tmem_base + col_dp + kk * 8, make_smem_desc(q_addr + kk * 1024, 16, 512, 4), idesc_ts,
+                         kk > 0);
+          }
+          const uint32_t ds_addr = smem_u32(sDS);
+          for (int mq = 0; mq < a.n_mq; ++mq)      // dQ[mq] += dS K_t   (K = 128 keys of this tile)
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_ss(tmem_base + col_dq + mq * TC_HD, make_smem_desc(ds_addr + mq * 2 * 16384 + ks * 2048, 16384, 1024, 2),
+                           make_smem_desc(k_addr + ks * 1024, 16, 512, 4), idesc_dq, (t > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(mma2_done);
+          umma_commit(&kv_empty[ts]);
+          if (t == a.n_kt - 1) umma_commit(&qdo_empty[us]);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool use_region = a.region != nullptr;
+    int cur_h = -1;
+    uint32_t it = 0, tt = 0;
+    for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+      named_bar_sync(1, 128);
+      if (h != cur_h) {
+        if (a.bias_table)
+          for (int x = tid; x < a.table_len; x += 128) sTable[x] = a.bias_table[(long long)x * a.heads + h];
+        cur_h = h;
+      }
+      {
+        const float* lp = a.lse + ((long long)b * a.heads + h) * a.seq;
+        const float* dp = a.dsum + ((long long)b * a.heads + h) * a.seq;
+        const int* rg = use_region ? a.region + (long long)(b % a.nwin) * a.seq : nullptr;
+        for (int j = tid; j < NQ; j += 128) {
+          sLse[j] = j < a.seq ? lp[j] * TC_LOG2E : 1.0e30f;      // queries outside the window get p = 0
+          sD[j] = j < a.seq ? dp[j] : 0.f;
+          sReg[j] = (rg && j < a.seq) ? rg[j] : 0;
+        }
+      }
+      named_bar_sync(1, 128);
+      for (int t = 0; t < a.n_kt; ++t, ++tt) {
+        const int j = t * a.rows_per_tile + r;
+        const bool valid = r < a.rows_per_tile && j < a.seq;
+        const bool warp_active = (quarter * 32) < a.rows_per_tile && (t * a.rows_per_tile + quarter * 32) < a.seq;
+        const int cj = a.code_off - (valid ? sCode[j] : 0);
+        const int rj = valid ? sReg[j] : 0;
+        uint8_t* ds_row = sDS + (r >> 3) * 1024 + (r & 7) * 128;
+        __nv_bfloat16* ds_g = a.ds_out ? a.ds_out + (((long long)b * a.heads + h) * a.seq + (valid ? j : 0)) * NQ : nullptr;
+        mbar_wait(st_full, tt & 1);
+        tc_fence_after();
+        if (warp_active) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < NQ; c0 += 32) {
+            uint32_t v[32], w[32];
+            tmem_ld_32x32(taddr + c0, v);
+            tmem_ld_32x32(taddr + col_dp + c0, w);
+            tmem_ld_wait();
+            uint32_t pk[16], dk[16];
+#pragma unroll
+            for (int x = 0; x < 32; x += 2) {
+              float p[2], ds[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = c0 + x + e;
+                float s = __uint_as_float(v[x + e]);
+                if (a.bias_table) s += sTable[sCode[i] + cj];
+                if (use_region && sReg[i] != rj) s -= 100.0f;
+                p[e] = ex2(fmaf(s, TC_LOG2E, -sLse[i]));
+                ds[e] = p[e] * (__uint_as_float(w[x + e]) - sD[i]);
+              }
+              pk[x >> 1] = pack_bf16(p[0], p[1]);
+              dk[x >> 1] = valid ? pack_bf16(ds[0], ds[1]) : 0u;
+            }
+            tmem_st_32x16(taddr + (c0 >> 1), pk);
+            tmem_st_32x16(taddr + col_dp + (c0 >> 1), dk);
+            // dS^T row -> shared memory (MN-major A operand of the dQ product, 64-query chunks, 128B swizzle)
+            uint8_t* chunk = ds_row + (c0 >> 6) * 16384;
+            const int half = (c0 >> 5) & 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int unit = (half * 4 + q) ^ (r & 7);
+              *reinterpret_cast<uint4*>(chunk + unit * 16) = make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]);
+            }
+            if (ds_g && valid) {
+              uint4* g = reinterpret_cast<uint4*>(ds_g + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) g[q] = make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]);
+            }
+          }
+          tmem_st_wait();
+        } else {
+          for (int c0 = 0; c0 < NQ; c0 += 32) {
+            uint8_t* chunk = ds_row + (c0 >> 6) * 16384;
+            const int half = (c0 >> 5) & 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(chunk + ((half * 4 + q) ^ (r & 7)) * 16) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+
+        mbar_wait(mma2_done, tt & 1);
+        tc_fence_after();
+        if (warp_active) {
+          uint32_t ov[32], ok[32];
+          tmem_ld_32x32(taddr + col_dv, ov);
+          tmem_ld_32x32(taddr + col_dk, ok);
+          tmem_ld_wait();
+          if (valid) {
+            __nv_bfloat16* rowp = a.dqkv + ((long long)b * a.seq + j) * (3 * C) + h * TC_HD;
+            uint4* gk = reinterpret_cast<uint4*>(rowp + C);
+            uint4* gv = reinterpret_cast<uint4*>(rowp + 2 * C);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              gk[q] = make_uint4(pack_bf16(__uint_as_float(ok[q * 8]), __uint_as_float(ok[q * 8 + 1])),
+                                 pack_bf16(__uint_as_float(ok[q * 8 + 2]), __uint_as_float(ok[q * 8 + 3])),
+                                 pack_bf16(__uint_as_float(ok[q * 8 + 4]), __uint_as_float(ok[q * 8 + 5])),
+                                 pack_bf16(__uint_as_float(ok[q * 8 + 6]), __uint_as_float(ok[q * 8 + 7])));
+              gv[q] = make_uint4(pack_bf16(__uint_as_float(ov[q * 8]), __uint_as_float(ov[q * 8 + 1])),
+                                 pack_bf16(__uint_as_float(ov[q * 8 + 2]), __uint_as_float(ov[q * 8 + 3])),
+                                 pack_bf16(__uint_as_float(ov[q * 8 + 4]), __uint_as_float(ov[q * 8 + 5])),
+                                 pack_bf16(__uint_as_float(ov[q * 8 + 6]), __uint_as_float(ov[q * 8 + 7])));
+            }
+          }
+        }
+        if (t == a.n_kt - 1) {
+          // dQ of the whole unit (all key tiles accumulated); query row i = mq*128 + r
+          for (int mq = 0; mq < a.n_mq; ++mq) {
+            const int i = mq * 128 + r;
+            if (mq * 128 + quarter * 32 < a.seq) {
+              uint32_t oq[32];
+              tmem_ld_32x32(taddr + col_dq + mq * TC_HD, oq);
+              tmem_ld_wait();
+              if (i < a.seq) {
+                uint4* gq = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * a.seq + i) * (3 * C) + h * TC_HD);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  gq[q] = make_uint4(pack_bf16(__uint_as_float(oq[q * 8]) * a.q_scale, __uint_as_float(oq[q * 8 + 1]) * a.q_scale),
+                                     pack_bf16(__uint_as_float(oq[q * 8 + 2]) * a.q_scale, __uint_as_float(oq[q * 8 + 3]) * a.q_scale),
+                                     pack_bf16(__uint_as_float(oq[q * 8 + 4]) * a.q_scale, __uint_as_float(oq[q * 8 + 5]) * a.q_scale),
+                                     pack_bf16(__uint_as_float(oq[q * 8 + 6]) * a.q_scale, __uint_as_float(oq[q * 8 + 7]) * a.q_scale));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(acc_free);
+          if (t == a.n_kt - 1) mbar_arrive(dq_free);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// dTable[(code_i - code_j + off), h] += sum_b dS^T[b, h, j, i]   (bf16 dS^T, fp32 accumulation)
+// grid = (seq rows j, heads, batch splits); block = nq/4 threads (4 queries each).
+__global__ void dbias_reduce_kernel(const __nv_bfloat16* ds, int batch, int heads, int seq, int nq, const int* rel_code,
+                                    int code_off, float* dtable) {
+  const int j = blockIdx.x, h = blockIdx.y;
+  const int i0 = threadIdx.x * 4;
+  if (i0 >= nq) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)heads * seq * nq;
+  const __nv_bfloat16* p = ds + ((long long)h * seq + j) * nq + i0;
+  const int per = (batch + gridDim.z - 1) / gridDim.z;
+  const int b0 = blockIdx.z * per, b1 = min(batch, b0 + per);
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p + b * stride);
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+    acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+  }
+  const int cj = rel_code[j];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (i0 + e < seq) atomicAdd(dtable + (long long)(rel_code[i0 + e] - cj + code_off) * heads + h, acc[e]);
+}
+
+extern "C" long long clv_attention_bwd_tc_workspace_bytes(const clv_attn_desc_t* d, int with_dbias) {
+  if (!d) return 0;
+  const long long nq = (d->seq + 31) / 32 * 32;
+  long long bytes = (long long)d->batch * d->heads * d->seq * 4;                       // D = rowsum(dO * O)
+  if (with_dbias) bytes += (long long)d->batch * d->heads * d->seq * nq * 2 + 256;     // bf16 dS^T
+  return bytes;
+}
+
+extern "C" int clv_attention_bwd_tc(const clv_attn_desc_t* d, const void* qkv, const void* out, const void* dout,
+                                    const float* lse, void* dqkv, float q_scale, float* dbias_table, void* workspace,
+                                    void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(d && qkv && out && dout && lse && dqkv && workspace, "attention_bwd_tc: null pointer");
+  CLV_REQUIRE(d->head_dim == 32 && !d->key_mask, "attention_bwd_tc: head_dim 32 without key mask only");
+  CLV_REQUIRE(d->seq >= 33 && d->seq <= 224, "attention_bwd_tc: seq must be in [33, 224] (got %d)", d->seq);
+  CLV_REQUIRE(!dbias_table || d->bias_table, "attention_bwd_tc: dbias_table without bias_table");
+  AttnTcBwdArgs a{};
+  a.batch = d->batch; a.seq = d->seq; a.heads = d->heads;
+  a.nq = (d->seq + 31) / 32 * 32;
+  a.n_kt = (d->seq + 127) / 128;
+  a.rows_per_tile = (d->seq + a.n_kt - 1) / a.n_kt;
+  a.n_mq = (a.nq + 127) / 128;
+  a.qb_bytes = (a.nq * TC_ROWB + 1023) / 1024 * 1024;
+  const int need_cols = 2 * a.nq + a.n_mq * TC_HD;
+  a.tmem_cols = need_cols <= 256 ? 256 : 512;
+  a.units = (long long)d->batch * d->heads;
+  float* dsum = reinterpret_cast<float*>(workspace);
+  a.lse = lse; a.dsum = dsum;
+  a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.q_scale = q_scale;
+  const long long dsum_bytes = ((long long)d->batch * d->heads * d->seq * 4 + 255) / 256 * 256;
+  a.ds_out = dbias_table ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + dsum_bytes) : nullptr;
+  a.bias_table = d->bias_table; a.table_len = d->bias_table ? d->table_len : 0; a.rel_code = d->rel_code; a.code_off = d->code_off;
+  a.region = d->region; a.nwin = d->nwin > 0 ? d->nwin : 1;
+  const long long rows = (long long)d->batch * d->seq;
+  if (int rc = launch_attn_bwd_prep(out, dout, dsum, rows, d->heads, TC_HD, d->seq, stream)) return rc;
+  const long long ld = 3LL * d->heads * TC_HD, ldo = (long long)d->heads * TC_HD;
+  CUtensorMap tfull, ttile, tdo;
+  if (int rc = make_tmap_bf16_2d(&tfull, qkv, ld, rows, ld, TC_HD, a.nq, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&ttile, qkv, ld, rows, ld, TC_HD, 128, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tdo, dout, ldo, rows, ldo, TC_HD, a.nq, 64)) return rc;
+  const size_t smem = 1024 + 4 * (size_t)a.qb_bytes + 4 * 8192 + (size_t)a.n_mq * 2 * 16384 + (size_t)((a.table_len + 3) & ~3) * 4 +
+                      (size_t)a.nq * 16 + 8 + 14 * 8 + 16;
+  CLV_REQUIRE(smem <= 227 * 1024, "attention_bwd_tc: %zu bytes of shared memory needed", smem);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
+  attn_bwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tfull, ttile, tdo, a);
+  if (int rc = after_launch("attn_bwd_tc_kernel")) return rc;
+  if (dbias_table) {
+    const int zsplit = std::max(1, std::min(32, d->batch / 32));
+    dim3 g(d->seq, d->heads, zsplit);
+    dbias_reduce_kernel<<<g, a.nq / 4, 0, stream>>>(a.ds_out, d->batch, d->heads, d->seq, a.nq, d->rel_code, d->code_off, dbias_table);
+    if (int rc = after_launch("dbias_reduce_kernel")) return rc;
+  }
+  return 0;
+}

@@ -35,6 +35,9 @@ int after_launch(const char* what);
   } while (0)
 
 int num_sms();
+// D[b,h,i] = <dO_i, O_i> (attention backward preparation), defined in attention.cu
+int launch_attn_bwd_prep(const void* out, const void* dout, float* dsum, long long rows, int heads, int hd, int seq,
+                         cudaStream_t stream);
 // 2-D bf16 tensor map (inner contiguous dimension first).  swizzle_bytes: 128, 64, 32 or 0.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
                       int box_outer, int swizzle_bytes = 128);

@@ -238,7 +238,7 @@ def attention_fwd(qkv, batch, seq, heads, hd, out, lse, **bias):
         _lib.check(lib.clv_attention_fwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd_tc")
     else:
         _lib.check(lib.clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
-    _prof_close(ev, "attn_fwd", 4.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 4)
+    _prof_close(ev, "attn_fwd_hd%d" % hd, 4.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 4)
     return out
 
 
@@ -248,11 +248,18 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
         if t.dtype != BF16 or not t.is_contiguous():
             raise ValueError(f"attention_bwd: {n} must be contiguous bf16")
     d = _attn_desc(batch, seq, heads, hd, **bias)
-    ws = torch.empty(batch * heads * seq, dtype=F32, device=qkv.device)
+    lib = _lib.load()
     ev = _prof_open()
-    _lib.check(_lib.load().clv_attention_bwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
-                                            float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd")
-    _prof_close(ev, "attn_bwd", 8.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 8)
+    if hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 224 and USE_TC_ATTENTION:
+        nbytes = lib.clv_attention_bwd_tc_workspace_bytes(C.byref(d), int(dbias_table is not None))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
+        _lib.check(lib.clv_attention_bwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                            float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd_tc")
+    else:
+        ws = torch.empty(batch * heads * seq, dtype=F32, device=qkv.device)
+        _lib.check(lib.clv_attention_bwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                         float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd")
+    _prof_close(ev, "attn_bwd_hd%d" % hd, 8.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 8)
     return dqkv
 
 

@@ -195,6 +195,12 @@ int clv_softmax_focal_bwd(const float* logits, long long ld, long long rows, int
                           float gamma, const float* stats, const float* sums, const float* g_loss, void* dlogits,
                           int dlogits_is_bf16, long long ld_d, void* stream);
 
+/* Backward of the head_dim-32 window attention on tcgen05 / TMEM (33 <= seq <= 224, no key_mask); same outputs as
+ * clv_attention_bwd.  workspace: clv_attention_bwd_tc_workspace_bytes(desc, dbias_table != NULL) bytes. */
+long long clv_attention_bwd_tc_workspace_bytes(const clv_attn_desc_t* desc, int with_dbias);
+int clv_attention_bwd_tc(const clv_attn_desc_t* desc, const void* qkv, const void* out, const void* dout, const float* lse,
+                         void* dqkv, float q_scale, float* dbias_table, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
