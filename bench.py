@@ -224,7 +224,17 @@ def run_ours(args):
         for f, fl, by, ms in prof:
             a = fam.setdefault(f, [0.0, 0.0, 0.0, 0])
             a[0] += fl; a[1] += by; a[2] += ms; a[3] += 1
-        g = fam.get("gemm", [0.0, 0.0, 1e-9, 1])
+        if os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1":
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            rows = sorted(((k, v[3] // args.steps, v[2] / args.steps, v[0] / max(v[2], 1e-9) / 1e9, v[1] / max(v[2], 1e-9) / 1e6)
+                           for k, v in fam.items()), key=lambda r: -r[2])
+            with open(os.path.join(ROOT, "gpurun_out", "family_times.txt"), "w") as f:
+                f.write("family | launches/step | ms/step | TFLOP/s | GB/s\n")
+                for r in rows:
+                    f.write(f"{r[0]} | {r[1]} | {r[2]:.3f} | {r[3]:.1f} | {r[4]:.0f}\n")
+            g = [sum(v[i] for k, v in fam.items() if k.startswith("gemm")) for i in range(4)]
+        else:
+            g = fam.get("gemm", [0.0, 0.0, 1e-9, 1])
         gemm_tflops = g[0] / (g[2] * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")

@@ -48,6 +48,7 @@ def _rowmajor2d(t, name):
 # optional per-launch CUDA-event timing (bench.py's roofline leg); off by default
 # ------------------------------------------------------------------------------------------------
 _PROF = None
+PROFILE_SHAPES = os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1"
 # head_dim-32 window attention runs on the tcgen05 kernel; the mma.sync kernel serves head_dim 64 (BERT / fusion)
 USE_TC_ATTENTION = os.environ.get("CLOVER_B200_TC_ATTENTION", "1") != "0"
 
@@ -138,7 +139,10 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None,
     lib = _lib.load()
     ev = _prof_open()
     _lib.check(lib.clv_gemm_bf16(_ptr(a), lda, int(a_t), _ptr(b), ldb, int(b_t), M, N, K, C.byref(e), _stream()), "clv_gemm_bf16")
-    _prof_close(ev, "gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * N)
+    _prof_close(ev, "gemm" if not PROFILE_SHAPES else f"gemm M={M} N={N} K={K} at={int(a_t)} bt={int(b_t)} ks={int(k_splits)} "
+                f"ep={'b' if bias is not None else ''}{'g' if act else ''}{'r' if residual is not None else ''}"
+                f"{'w' if window is not None else ''}{'p' if gelu_pre is not None else ''}{'o16' if out.dtype == BF16 else 'o32'}",
+                2.0 * M * N * K, 2.0 * (M * K + N * K) + out.element_size() * M * N)
     return out
 
 
