@@ -55,10 +55,32 @@ CLV_DEVICE float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-CLV_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Branch-free erf (Abramowitz & Stegun 7.1.26, |abs err| < 5e-7 incl. the MUFU approximations) that also
+// returns exp(-u^2): exact-erf GELU (nn.GELU default / HF "gelu") and its derivative need both, and the epilogues
+// that evaluate them are instruction-bound, so erff()'s range branches are avoided.
+CLV_DEVICE void erf_exp(float u, float& erf_u, float& exp_mu2) {
+  const float au = fabsf(u);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, au, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-au * au * 1.4426950408889634f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  erf_u = copysignf(fmaf(-p, e, 1.0f), u);
+  exp_mu2 = e;
+}
+CLV_DEVICE float gelu_erf(float x) {
+  float er, e;
+  erf_exp(x * 0.70710678118654752440f, er, e);
+  return 0.5f * x * (1.0f + er);
+}
 // d/dx [0.5 x (1+erf(x/sqrt2))] = 0.5(1+erf(x/sqrt2)) + x * exp(-x^2/2)/sqrt(2pi)
 CLV_DEVICE float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+  float er, e;
+  erf_exp(x * 0.70710678118654752440f, er, e);
+  return fmaf(x * 0.39894228040143267794f, e, 0.5f * (1.0f + er));
 }
 CLV_DEVICE uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

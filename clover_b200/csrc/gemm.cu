@@ -11,9 +11,10 @@
 // (fp32 or bf16), window-reverse row scatter (window_reverse + roll back, :471-474), bf16 or fp32
 // output, and split-K with fp32 atomic accumulation for weight gradients.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 =
-// epilogue (TMEM -> registers -> global).  Two TMEM accumulator stages let the epilogue of tile i
-// overlap the mainloop of tile i+1.  Tile 128x128x64, 6 smem stages (192 KB).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-9 =
+// epilogue (TMEM -> registers -> 256-bit global stores; bias staged in shared memory).  Two TMEM
+// accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+// Tiles 128x256x64 (4 smem stages) when N is a multiple of 256 and the grid still fills, else 128x128x64 (6 stages).
 #include <algorithm>
 
 #include "common.cuh"
@@ -21,13 +22,16 @@
 
 namespace clv {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 6;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int GEMM_THREADS = 192;
-constexpr int TMEM_COLS = 256;  // 2 accumulator stages x 128 fp32 columns
+constexpr int BM = 128, BK = 64;
+constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two column halves x four lane quarters)
+
+template <int BN> struct GemmCfg {
+  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages
+};
 
 struct GemmEpi {
   const float* bias;
@@ -40,16 +44,106 @@ struct GemmEpi {
   int scale_cols;
   float scale;
   int use_row_map;
+  int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
   WindowGeom geom;
 };
 
-template <int A_MN, int B_MN>
+CLV_DEVICE void ld256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+CLV_DEVICE void st256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// 32 bf16 (64 B) or 32 fp32 (128 B) of one row <-> registers; `wide` selects the 256-bit path
+CLV_DEVICE void load_row32(const void* base, int is_bf16, bool wide, int ncols, float (&f)[32]) {
+  if (is_bf16) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base);
+    if (wide) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[8];
+        ld256(p + h * 16, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float2 t = unpack_bf16(r[j]); f[h * 16 + 2 * j] = t.x; f[h * 16 + 2 * j + 1] = t.y; }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q * 8 < ncols) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + q);
+          const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+          f[q * 8] = a.x; f[q * 8 + 1] = a.y; f[q * 8 + 2] = b.x; f[q * 8 + 3] = b.y;
+          f[q * 8 + 4] = c.x; f[q * 8 + 5] = c.y; f[q * 8 + 6] = d.x; f[q * 8 + 7] = d.y;
+        }
+    }
+  } else {
+    const float* p = reinterpret_cast<const float*>(base);
+    if (wide) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t r[8];
+        ld256(p + h * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[h * 8 + j] = __uint_as_float(r[j]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q * 4 < ncols) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+          f[q * 4] = t.x; f[q * 4 + 1] = t.y; f[q * 4 + 2] = t.z; f[q * 4 + 3] = t.w;
+        }
+    }
+  }
+}
+CLV_DEVICE void store_row32(void* base, int is_bf16, bool wide, int ncols, const float (&v)[32]) {
+  if (is_bf16) {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base);
+    if (wide) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = pack_bf16(v[h * 16 + 2 * j], v[h * 16 + 2 * j + 1]);
+        st256(p + h * 16, r);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q * 8 < ncols)
+          reinterpret_cast<uint4*>(p)[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                                      pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+    }
+  } else {
+    float* p = reinterpret_cast<float*>(base);
+    if (wide) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[h * 8 + j]);
+        st256(p + h * 8, r);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q * 4 < ncols) reinterpret_cast<float4*>(p)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    }
+  }
+}
+
+template <int A_MN, int B_MN, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  int M, int N, int K, int k_splits, GemmEpi ep) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* sBias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -70,11 +164,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -102,10 +196,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_idx * BM);
           }
           if (B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], n_idx * BN, kb * BK);
-            tma_load_2d(sb + B_BYTES / 2, &tma_b, &full_bar[stage], n_idx * BN + 64, kb * BK);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (BK * 128), &tma_b, &full_bar[stage], n_idx * BN + c * 64, kb * BK);
           } else {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_idx * BN);
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c)
+              tma_load_2d(sb + c * (128 * BK * 2), &tma_b, &full_bar[stage], kb * BK, n_idx * BN + c * 128);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -132,8 +229,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
-            // MN-major: 16 k-rows = 2 groups of 8 rows x 128 B = 2048 B; 64-element MN chunks BK*128 B apart.
+            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart (a 256-row B tile is
+            // two stacked 128-row boxes, still 1024 B per group).  MN-major: 16 k-rows = 2 groups of 8 rows x 128 B
+            // = 2048 B; 64-element MN chunks BK*128 B apart.
             const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, BK * 128, 1024)
                                      : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024)
@@ -147,13 +245,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ---------------- epilogue warps: TMEM lanes (warp % 4) * 32 ... +31 ----------------
+    // ---------------- epilogue: 8 warps; TMEM lanes (warp % 4) * 32 ... +31, column half (warp - 2) / 4 ----------------
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    constexpr int CHUNKS = BN / 64;          // 32-column chunks per warp
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const long long mn = t / k_splits;
       const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const float* sb = sBias + acc * BN;
+      if (ep.bias) {
+        for (int x = et; x < BN; x += 256) sBias[acc * BN + x] = (n_idx * BN + x < N) ? __ldg(ep.bias + n_idx * BN + x) : 0.f;
+        named_bar_sync(1, 256);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const long long row = (long long)m_idx * BM + quarter * 32 + lane;
@@ -161,16 +267,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
       const bool row_ok = row < M && drow >= 0;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
-        const int n0 = n_idx * BN + c * 32;
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, r);
+        const int cb = chalf * (BN / 2) + c * 32;        // column offset inside the tile
+        const int n0 = n_idx * BN + cb;
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb, r);
         tmem_ld_wait();
         if (!row_ok || n0 >= N) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const int ncols = min(32, N - n0);  // multiple of 8 (N % 8 == 0)
+        const bool wide = ep.vec32 != 0;    // implies ncols == 32
         if (ep.atomic_out) {
           float* o = reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0;
 #pragma unroll
@@ -180,8 +288,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         if (ep.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) v[j] += __ldg(ep.bias + n0 + j);
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + cb + q * 4);
+            v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+          }
         }
         if (ep.scale_cols > n0) {
 #pragma unroll
@@ -189,66 +299,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
         }
         if (ep.act == 1) {
-          if (ep.out_pre) {
-            uint4* p = reinterpret_cast<uint4*>(ep.out_pre + row * ep.ld_pre + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (q * 8 < ncols)
-                p[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                  pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-          }
+          if (ep.out_pre) store_row32(ep.out_pre + row * ep.ld_pre + n0, 1, wide, ncols, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
         if (ep.gelu_pre) {
-          const uint4* p = reinterpret_cast<const uint4*>(ep.gelu_pre + row * ep.ld_gpre + n0);
+          float g[32];
+          load_row32(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q * 8 < ncols) {
-              uint4 u = __ldg(p + q);
-              float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-              v[q * 8 + 0] *= gelu_erf_grad(f0.x); v[q * 8 + 1] *= gelu_erf_grad(f0.y);
-              v[q * 8 + 2] *= gelu_erf_grad(f1.x); v[q * 8 + 3] *= gelu_erf_grad(f1.y);
-              v[q * 8 + 4] *= gelu_erf_grad(f2.x); v[q * 8 + 5] *= gelu_erf_grad(f2.y);
-              v[q * 8 + 6] *= gelu_erf_grad(f3.x); v[q * 8 + 7] *= gelu_erf_grad(f3.y);
-            }
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(g[j]);
         }
         if (ep.residual) {
-          if (ep.residual_bf16) {
-            const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) +
-                                                            drow * ep.ld_res + n0);
+          float g[32];
+          if (ep.residual_bf16)
+            load_row32(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + drow * ep.ld_res + n0, 1, wide, ncols, g);
+          else
+            load_row32(reinterpret_cast<const float*>(ep.residual) + drow * ep.ld_res + n0, 0, wide, ncols, g);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (q * 8 < ncols) {
-                uint4 u = __ldg(p + q);
-                float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-                v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
-                v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
-              }
-          } else {
-            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) +
-                                                              drow * ep.ld_res + n0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q * 4 < ncols) {
-                float4 f = __ldg(p + q);
-                v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
-              }
-          }
+          for (int j = 0; j < 32; ++j) v[j] += g[j];
         }
-        if (ep.out_bf16) {
-          uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q * 8 < ncols)
-              p[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-        } else {
-          float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q * 4 < ncols) p[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-        }
+        if (ep.out_bf16)
+          store_row32(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0, 1, wide, ncols, v);
+        else
+          store_row32(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0, 0, wide, ncols, v);
       }
       tc_fence_before();
       __syncwarp();
@@ -258,7 +331,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -302,19 +375,29 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long l
   return 0;
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int k_splits,
                        const GemmEpi& ep, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN>;
+  constexpr int SMEM = GemmCfg<BN>::SMEM;
   if (!attr_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
   const int grid = (int)std::min<long long>(tiles, num_sms());
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(ta, tb, M, N, K, k_splits, ep);
+  kern<<<grid, GEMM_THREADS, SMEM, stream>>>(ta, tb, M, N, K, k_splits, ep);
   return after_launch("gemm_bf16_kernel launch");
+}
+
+template <int BN>
+static int dispatch_gemm(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int k_splits,
+                         const GemmEpi& ep, cudaStream_t stream) {
+  if (a_mn && b_mn) return launch_gemm<1, 1, BN>(ta, tb, M, N, K, k_splits, ep, stream);
+  if (a_mn) return launch_gemm<1, 0, BN>(ta, tb, M, N, K, k_splits, ep, stream);
+  if (b_mn) return launch_gemm<0, 1, BN>(ta, tb, M, N, K, k_splits, ep, stream);
+  return launch_gemm<0, 0, BN>(ta, tb, M, N, K, k_splits, ep, stream);
 }
 
 }  // namespace clv
@@ -327,13 +410,16 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   CLV_REQUIRE(A && B && e && e->out, "clv_gemm_bf16: null pointer");
   CLV_REQUIRE(M > 0 && N > 0 && K > 0, "clv_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   CLV_REQUIRE(N % 8 == 0, "clv_gemm_bf16: N must be a multiple of 8 (got %d)", N);
+  // 128x256 tiles when N fills them (less smem traffic per MAC); 128x128 otherwise
+  const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
+  const bool bn256 = (N % 256 == 0) && tiles256 * (e->k_splits > 0 ? e->k_splits : 1) >= 2LL * num_sms();
   CUtensorMap ta, tb;
   int rc;
   if (a_mn_major) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BK);
   else rc = make_tmap_bf16_2d(&ta, A, K, M, lda, BK, BM);
   if (rc) return rc;
   if (b_mn_major) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, BK);
-  else rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, BK, BN);
+  else rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, BK, 128);
   if (rc) return rc;
 
   GemmEpi ep{};
@@ -370,8 +456,14 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     g.nD = g.Dp / g.wd; g.nH = g.Hp / g.wh; g.nW = g.Wp / g.ww; g.N = g.wd * g.wh * g.ww; g.nWin = g.nD * g.nH * g.nW;
     CLV_REQUIRE((long long)g.B * g.nWin * g.N == M, "clv_gemm_bf16: window geometry does not match M=%d", M);
   }
-  if (a_mn_major && b_mn_major) return launch_gemm<1, 1>(ta, tb, M, N, K, k_splits, ep, stream);
-  if (a_mn_major) return launch_gemm<1, 0>(ta, tb, M, N, K, k_splits, ep, stream);
-  if (b_mn_major) return launch_gemm<0, 1>(ta, tb, M, N, K, k_splits, ep, stream);
-  return launch_gemm<0, 0>(ta, tb, M, N, K, k_splits, ep, stream);
+  {
+    auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    bool ok = (N % 32 == 0) && al32(e->out) && (e->ld_out * (e->out_is_bf16 ? 2 : 4)) % 32 == 0;
+    if (e->residual) ok = ok && al32(e->residual) && (e->ld_residual * (e->residual_is_bf16 ? 2 : 4)) % 32 == 0;
+    if (e->out_pre) ok = ok && al32(e->out_pre) && (e->ld_pre * 2) % 32 == 0;
+    if (e->gelu_pre) ok = ok && al32(e->gelu_pre) && (e->ld_gelu_pre * 2) % 32 == 0;
+    ep.vec32 = ok ? 1 : 0;
+  }
+  if (bn256) return dispatch_gemm<256>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
+  return dispatch_gemm<128>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
 }

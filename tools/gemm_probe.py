@@ -1,0 +1,58 @@
+"""Micro-benchmark of the tcgen05 GEMM on the shapes that dominate the Clover pre-train step (c3, 64 clips/GPU).
+   python tools/gemm_probe.py [reps]      -> TFLOP/s and GB/s per shape (CUDA events, L2 flushed between reps)"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from clover_b200 import ops  # noqa: E402
+
+BF16, F32 = torch.bfloat16, torch.float32
+# (M, N, K, a_t, b_t, epilogue)  epilogue: b=bias g=gelu(+pre) r=residual fp32 p=gelu' multiply, o16/o32 output, ks = split-K
+SHAPES = [
+    (50176, 2048, 512, 0, 0, "bg", "o16", 1), (50176, 2048, 512, 0, 1, "p", "o16", 1), (50176, 1536, 512, 0, 0, "b", "o16", 1),
+    (50176, 512, 2048, 0, 0, "br", "o32", 1), (50176, 512, 2048, 0, 1, "", "o16", 1), (50176, 512, 512, 0, 0, "br", "o32", 1),
+    (802816, 512, 128, 0, 0, "bg", "o16", 1), (802816, 512, 128, 0, 1, "p", "o16", 1), (802816, 384, 128, 0, 0, "b", "o16", 1),
+    (802816, 128, 512, 0, 0, "br", "o32", 1), (200704, 1024, 256, 0, 0, "bg", "o16", 1),
+    (512, 2048, 50176, 1, 1, "", "o32", 4), (2048, 512, 50176, 1, 1, "", "o32", 4), (512, 512, 50176, 1, 1, "", "o32", 18),
+    (128, 512, 802816, 1, 1, "", "o32", 74), (8192, 8192, 8192, 0, 0, "", "o16", 1),
+]
+
+
+def main():
+    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+    only = sys.argv[2] if len(sys.argv) > 2 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for (M, N, K, at, bt, ep, od, ks) in SHAPES:
+        tag = f"M={M} N={N} K={K} at={at} bt={bt} ep={ep}{od} ks={ks}"
+        if only and only not in tag:
+            continue
+        a = torch.randn((K, M) if at else (M, K), device="cuda").to(BF16)
+        b = torch.randn((K, N) if bt else (N, K), device="cuda").to(BF16)
+        out = torch.empty(M, N, dtype=BF16 if od == "o16" else F32, device="cuda")
+        kw = {}
+        if "b" in ep:
+            kw["bias"] = torch.randn(N, device="cuda")
+        if "g" in ep:
+            kw["act"] = "gelu"
+            kw["out_pre"] = torch.empty(M, N, dtype=BF16, device="cuda")
+        if "p" in ep:
+            kw["gelu_pre"] = torch.randn(M, N, device="cuda").to(BF16)
+        if "r" in ep:
+            kw["residual"] = torch.randn(M, N, device="cuda")
+        ms = []
+        for _ in range(reps + 1):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.gemm(a, b, out, a_t=bool(at), b_t=bool(bt), k_splits=ks, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = sorted(ms[1:])[len(ms[1:]) // 2]
+        nbytes = 2 * (M * K + N * K) + out.element_size() * M * N * (2 if "g" in ep else 1) + (2 * M * N if "p" in ep else 0) + (4 * M * N if "r" in ep else 0)
+        print(f"{tag:70s} {t:8.3f} ms  {2 * M * N * K / t / 1e9:8.1f} TFLOP/s  {nbytes / t / 1e6:8.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
