@@ -319,6 +319,7 @@ struct AttnTcBwdArgs {
   int n_mq;                     // 128-row query tiles of the dQ accumulator
   int qb_bytes;                 // bytes per Q (or dO) buffer, multiple of 1024
   int tmem_cols;
+  int col_split;                // queries [0, col_split) are handled by softmax warps 2-5, the rest by warps 6-9
   long long units;
   const float* lse; const float* dsum;
   __nv_bfloat16* dqkv; float q_scale;
@@ -327,7 +328,9 @@ struct AttnTcBwdArgs {
   const int* region; int nwin;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+constexpr int TC_BWD_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two column halves x four lane quarters)
+
+__global__ void __launch_bounds__(TC_BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_tile,
                    const __grid_constant__ CUtensorMap tm_do_full, AttnTcBwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -363,14 +366,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     for (int s = 0; s < 2; ++s) {
       mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(st_full, 1); mbar_init(p_ready, 4); mbar_init(mma2_done, 1); mbar_init(acc_free, 4); mbar_init(dq_free, 4);
+    mbar_init(st_full, 1); mbar_init(p_ready, 8); mbar_init(mma2_done, 1); mbar_init(acc_free, 8); mbar_init(dq_free, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
   if (warp >= 2) {
     const int tid = threadIdx.x - 64;
-    for (int j = tid; j < NQ; j += 128) sCode[j] = (a.rel_code && j < a.seq) ? a.rel_code[j] : 0;
-    for (int x = tid; x < ds_bytes / 16; x += 128) reinterpret_cast<uint4*>(sDS)[x] = make_uint4(0, 0, 0, 0);
+    for (int j = tid; j < NQ; j += 256) sCode[j] = (a.rel_code && j < a.seq) ? a.rel_code[j] : 0;
+    for (int x = tid; x < ds_bytes / 16; x += 256) reinterpret_cast<uint4*>(sDS)[x] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -433,8 +436,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
           mbar_wait(p_ready, tt & 1);
           tc_fence_after();
           for (int kk = 0; kk < NQ / 16; ++kk) {   // dV_t = P^T dO ; dK_t = dS^T Q   (K = queries)
-            umma_bf16_ts(tmem_base + col_dv, tmem_base + kk * 8, make_smem_desc(do_addr + kk * 1024, 16, 512, 4), idesc_ts, kk > 0);
-            umma_bf16_ts(tmem_base + col_dk, tmem_base + col_dp + kk * 8, make_smem_desc(q_addr + kk * 1024, 16, 512, 4), idesc_ts,
+            // packed bf16 operands live in two column segments (one per softmax warp group)
+            const uint32_t pc = kk * 16 < a.col_split ? kk * 8 : a.col_split + ((kk * 16 - a.col_split) >> 1);
+            umma_bf16_ts(tmem_base + col_dv, tmem_base + pc, make_smem_desc(do_addr + kk * 1024, 16, 512, 4), idesc_ts, kk > 0);
+            umma_bf16_ts(tmem_base + col_dk, tmem_base + col_dp + pc, make_smem_desc(q_addr + kk * 1024, 16, 512, 4), idesc_ts,
                          kk > 0);
           }
           const uint32_t ds_addr = smem_u32(sDS);
@@ -450,31 +455,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     }
   } else {
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const int tid = threadIdx.x - 64;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const bool use_region = a.region != nullptr;
+    const int c_begin = chalf ? a.col_split : 0, c_end = chalf ? NQ : a.col_split;
     int cur_h = -1;
     uint32_t it = 0, tt = 0;
     for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
       const int b = (int)(u % a.batch), h = (int)(u / a.batch);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (h != cur_h) {
         if (a.bias_table)
-          for (int x = tid; x < a.table_len; x += 128) sTable[x] = a.bias_table[(long long)x * a.heads + h];
+          for (int x = tid; x < a.table_len; x += 256) sTable[x] = a.bias_table[(long long)x * a.heads + h];
         cur_h = h;
       }
       {
         const float* lp = a.lse + ((long long)b * a.heads + h) * a.seq;
         const float* dp = a.dsum + ((long long)b * a.heads + h) * a.seq;
         const int* rg = use_region ? a.region + (long long)(b % a.nwin) * a.seq : nullptr;
-        for (int j = tid; j < NQ; j += 128) {
+        for (int j = tid; j < NQ; j += 256) {
           sLse[j] = j < a.seq ? lp[j] * TC_LOG2E : 1.0e30f;      // queries outside the window get p = 0
           sD[j] = j < a.seq ? dp[j] : 0.f;
           sReg[j] = (rg && j < a.seq) ? rg[j] : 0;
         }
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       for (int t = 0; t < a.n_kt; ++t, ++tt) {
         const int j = t * a.rows_per_tile + r;
         const bool valid = r < a.rows_per_tile && j < a.seq;
@@ -487,7 +494,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         tc_fence_after();
         if (warp_active) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < NQ; c0 += 32) {
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            const uint32_t pc = c_begin + ((c0 - c_begin) >> 1);      // packed columns of this warp group's segment
             uint32_t v[32], w[32];
             tmem_ld_32x32(taddr + c0, v);
             tmem_ld_32x32(taddr + col_dp + c0, w);
@@ -508,8 +516,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
               pk[x >> 1] = pack_bf16(p[0], p[1]);
               dk[x >> 1] = valid ? pack_bf16(ds[0], ds[1]) : 0u;
             }
-            tmem_st_32x16(taddr + (c0 >> 1), pk);
-            tmem_st_32x16(taddr + col_dp + (c0 >> 1), dk);
+            tmem_st_32x16(taddr + pc, pk);
+            tmem_st_32x16(taddr + col_dp + pc, dk);
             // dS^T row -> shared memory (MN-major A operand of the dQ product, 64-query chunks, 128B swizzle)
             uint8_t* chunk = ds_row + (c0 >> 6) * 16384;
             const int half = (c0 >> 5) & 1;
@@ -526,7 +534,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
           }
           tmem_st_wait();
         } else {
-          for (int c0 = 0; c0 < NQ; c0 += 32) {
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             uint8_t* chunk = ds_row + (c0 >> 6) * 16384;
             const int half = (c0 >> 5) & 1;
 #pragma unroll
@@ -541,30 +549,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         mbar_wait(mma2_done, tt & 1);
         tc_fence_after();
         if (warp_active) {
-          uint32_t ov[32], ok[32];
-          tmem_ld_32x32(taddr + col_dv, ov);
-          tmem_ld_32x32(taddr + col_dk, ok);
+          // dV rows by warp group 0, dK rows by warp group 1
+          uint32_t o[32];
+          tmem_ld_32x32(taddr + (chalf ? col_dk : col_dv), o);
           tmem_ld_wait();
           if (valid) {
-            __nv_bfloat16* rowp = a.dqkv + ((long long)b * a.seq + j) * (3 * C) + h * TC_HD;
-            uint4* gk = reinterpret_cast<uint4*>(rowp + C);
-            uint4* gv = reinterpret_cast<uint4*>(rowp + 2 * C);
+            uint4* g = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * a.seq + j) * (3 * C) + (chalf ? 1 : 2) * C + h * TC_HD);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              gk[q] = make_uint4(pack_bf16(__uint_as_float(ok[q * 8]), __uint_as_float(ok[q * 8 + 1])),
-                                 pack_bf16(__uint_as_float(ok[q * 8 + 2]), __uint_as_float(ok[q * 8 + 3])),
-                                 pack_bf16(__uint_as_float(ok[q * 8 + 4]), __uint_as_float(ok[q * 8 + 5])),
-                                 pack_bf16(__uint_as_float(ok[q * 8 + 6]), __uint_as_float(ok[q * 8 + 7])));
-              gv[q] = make_uint4(pack_bf16(__uint_as_float(ov[q * 8]), __uint_as_float(ov[q * 8 + 1])),
-                                 pack_bf16(__uint_as_float(ov[q * 8 + 2]), __uint_as_float(ov[q * 8 + 3])),
-                                 pack_bf16(__uint_as_float(ov[q * 8 + 4]), __uint_as_float(ov[q * 8 + 5])),
-                                 pack_bf16(__uint_as_float(ov[q * 8 + 6]), __uint_as_float(ov[q * 8 + 7])));
-            }
+            for (int q = 0; q < 4; ++q)
+              g[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8]), __uint_as_float(o[q * 8 + 1])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7])));
           }
         }
         if (t == a.n_kt - 1) {
-          // dQ of the whole unit (all key tiles accumulated); query row i = mq*128 + r
-          for (int mq = 0; mq < a.n_mq; ++mq) {
+          // dQ of the whole unit (all key tiles accumulated); query row i = mq*128 + r; tiles alternate between warp groups
+          for (int mq = chalf; mq < a.n_mq; mq += 2) {
             const int i = mq * 128 + r;
             if (mq * 128 + quarter * 32 < a.seq) {
               uint32_t oq[32];
@@ -647,6 +648,9 @@ extern "C" int clv_attention_bwd_tc(const clv_attn_desc_t* d, const void* qkv, c
   const int need_cols = 2 * a.nq + a.n_mq * TC_HD;
   a.tmem_cols = need_cols <= 256 ? 256 : 512;
   a.units = (long long)d->batch * d->heads;
+  // second warp group needs its own in-place packing segment that stays clear of the accumulator columns [nq-32, nq)
+  a.col_split = a.nq >= 128 ? std::min(128, (a.nq - 64) / 32 * 32) : a.nq;
+  if (a.col_split <= 0) a.col_split = a.nq;
   float* dsum = reinterpret_cast<float*>(workspace);
   a.lse = lse; a.dsum = dsum;
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.q_scale = q_scale;
@@ -670,7 +674,7 @@ extern "C" int clv_attention_bwd_tc(const clv_attn_desc_t* d, const void* qkv, c
     smem_set = smem;
   }
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
-  attn_bwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tfull, ttile, tdo, a);
+  attn_bwd_tc_kernel<<<grid, TC_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, a);
   if (int rc = after_launch("attn_bwd_tc_kernel")) return rc;
   if (dbias_table) {
     const int zsplit = std::max(1, std::min(32, d->batch / 32));

@@ -87,10 +87,43 @@ __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __re
 // grid = (col tiles of 128, row chunks, mod).  Used for nn.Linear bias gradients (mod = 1),
 // AdaptiveAvgPool3d of ssl_head.py:105 (groups = clips), and the gradients of vis_space_pos /
 // vis_tempor_pos / BERT position embeddings.
-__global__ void grouped_colsum_kernel(const void* x, int x_bf16, long long ld, long long rows, int C, int div, int mod,
-                                      float scale, float* out) {
+// bf16 input whose width / pitch is only a multiple of 4: 8-byte loads
+__global__ void __launch_bounds__(256) grouped_colsum_bf16x4_kernel(const void* x, long long ld, long long rows, int C, int div,
+                                                                     int mod, float scale, float* out) {
   const int g = blockIdx.z;
-  const int c4 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+  const int lane = threadIdx.x & 31;
+  const int c0 = (blockIdx.x * 32 + lane) * 4;
+  const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long full = rows / ((long long)div * mod);
+  const long long rem = rows - full * div * mod;
+  long long in_group = full * div;
+  {
+    const long long start = (long long)g * div;
+    if (rem > start) in_group += min((long long)div, rem - start);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c0 < C)
+    for (long long k = (long long)blockIdx.y * nw + wib; k < in_group; k += (long long)gridDim.y * nw) {
+      const long long r = ((k / div) * mod + g) * div + (k % div);
+      const float4 v = ldv4(x, 1, r * ld + c0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  __shared__ float4 red[8][32];
+  red[wib][lane] = acc;
+  __syncthreads();
+  if (wib == 0 && c0 < C) {
+    for (int w = 1; w < nw; ++w) { const float4 v = red[w][lane]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    float* o = out + (long long)g * C + c0;
+    atomicAdd(o + 0, acc.x * scale); atomicAdd(o + 1, acc.y * scale); atomicAdd(o + 2, acc.z * scale); atomicAdd(o + 3, acc.w * scale);
+  }
+}
+
+template <int VEC>   // VEC columns per lane: 8 for bf16 input (16-byte loads), 4 for fp32
+__global__ void __launch_bounds__(256) grouped_colsum_kernel(const void* x, long long ld, long long rows, int C, int div, int mod,
+                                                              float scale, float* out) {
+  const int g = blockIdx.z;
+  const int lane = threadIdx.x & 31;
+  const int c0 = (blockIdx.x * 32 + lane) * VEC;
   const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // rows of group g: r = (q*mod + g)*div + t
   const long long full = rows / ((long long)div * mod);                 // complete periods
@@ -100,25 +133,36 @@ __global__ void grouped_colsum_kernel(const void* x, int x_bf16, long long ld, l
     const long long start = (long long)g * div;
     if (rem > start) in_group += min((long long)div, rem - start);
   }
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c4 < C) {
-    for (long long k = (long long)blockIdx.y * nw + wib; k < in_group; k += (long long)gridDim.y * nw) {
-      const long long r = ((k / div) * mod + g) * div + (k % div);
-      const float4 v = ldv4(x, x_bf16, r * ld + c4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  if (c0 < C) {
+    const long long step = (long long)gridDim.y * nw;
+#pragma unroll 4
+    for (long long k = (long long)blockIdx.y * nw + wib; k < in_group; k += step) {
+      const long long r = (mod == 1) ? k : ((k / div) * mod + g) * div + (k % div);
+      if (VEC == 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + r * ld + c0);
+        const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+        acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+        acc[4 % VEC] += f2.x; acc[5 % VEC] += f2.y; acc[6 % VEC] += f3.x; acc[7 % VEC] += f3.y;
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + r * ld + c0);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      }
     }
   }
-  __shared__ float4 red[8][32];
-  red[wib][threadIdx.x & 31] = acc;
+  __shared__ float red[8][32 * VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) red[wib][lane * VEC + e] = acc[e];
   __syncthreads();
-  if (wib == 0 && c4 < C) {
-    for (int w = 1; w < nw; ++w) {
-      const float4 v = red[w][threadIdx.x];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  for (int i = threadIdx.x; i < 32 * VEC; i += blockDim.x) {
+    const int c = blockIdx.x * 32 * VEC + i;
+    if (c < C) {
+      float s = 0.f;
+      for (int w = 0; w < nw; ++w) s += red[w][i];
+      atomicAdd(out + (long long)g * C + c, s * scale);
     }
-    float* o = out + (long long)g * C + c4;
-    atomicAdd(o + 0, acc.x * scale); atomicAdd(o + 1, acc.y * scale);
-    atomicAdd(o + 2, acc.z * scale); atomicAdd(o + 3, acc.w * scale);
   }
 }
 
@@ -210,14 +254,22 @@ extern "C" int clv_grouped_colsum(const void* x, int x_is_bf16, long long ld, lo
   CLV_REQUIRE(x && out && C > 0 && C % 4 == 0 && div > 0 && mod > 0, "clv_grouped_colsum: bad arguments");
   if (!accumulate) CLV_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)mod * C * sizeof(float), stream));
   if (rows == 0) return 0;
-  const int col_tiles = (C + 127) / 128;
+  const bool wide = x_is_bf16 && C % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int vec = wide ? 8 : 4;
+  const int col_tiles = (C + 32 * vec - 1) / (32 * vec);
   const long long per_group = (rows + mod - 1) / mod;
   long long chunks = (per_group + 63) / 64;
   const long long cap = std::max<long long>(1, (long long)num_sms() * 8 / ((long long)col_tiles * mod));
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   dim3 grid(col_tiles, (unsigned)chunks, mod);
-  grouped_colsum_kernel<<<grid, 256, 0, stream>>>(x, x_is_bf16, ld, rows, C, div, mod, scale, out);
+  if (wide) {
+    grouped_colsum_kernel<8><<<grid, 256, 0, stream>>>(x, ld, rows, C, div, mod, scale, out);
+  } else if (!x_is_bf16) {
+    grouped_colsum_kernel<4><<<grid, 256, 0, stream>>>(x, ld, rows, C, div, mod, scale, out);
+  } else {
+    grouped_colsum_bf16x4_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, C, div, mod, scale, out);
+  }
   return after_launch("grouped_colsum_kernel");
 }
 
