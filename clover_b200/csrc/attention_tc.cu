@@ -48,12 +48,13 @@ CLV_DEVICE float ex2(float x) {
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = 8192 + 2 * a.kb_bytes;
   float* sTable = reinterpret_cast<float*>(smem + 2 * stage_bytes);
   int* sCode = reinterpret_cast<int*>(sTable + ((a.table_len + 3) & ~3));
   int* sReg = sCode + a.nk;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sReg + a.nk) + 7) & ~uintptr_t(7));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sReg + a.nk);   // 16-byte aligned by construction
   uint64_t* full_bar = bars;          // [2]
   uint64_t* empty_bar = bars + 2;     // [2]
   uint64_t* s_full = bars + 4;
@@ -334,7 +335,8 @@ __global__ void __launch_bounds__(TC_BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_tile,
                    const __grid_constant__ CUtensorMap tm_do_full, AttnTcBwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // layout: [Q0 dO0 Q1 dO1] [K0 V0 K1 V1] [dS^T tile] tables barriers
   uint8_t* sQdO = smem;
   uint8_t* sKV = sQdO + 4 * a.qb_bytes;
@@ -345,7 +347,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   float* sD = sLse + a.nq;
   int* sCode = reinterpret_cast<int*>(sD + a.nq);
   int* sReg = sCode + a.nq;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sReg + a.nq) + 7) & ~uintptr_t(7));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sReg + a.nq);   // 16-byte aligned by construction
   uint64_t* qdo_full = bars;        // [2]
   uint64_t* qdo_empty = bars + 2;   // [2]
   uint64_t* kv_full = bars + 4;     // [2]

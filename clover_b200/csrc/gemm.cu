@@ -141,7 +141,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sBias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
