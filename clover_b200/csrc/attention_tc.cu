@@ -185,12 +185,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           tmem_ld_wait();
           if (a.bias_table) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + sTable[ci - sCode[c0 + j]]);
+            for (int j = 0; j < 32; j += 4) {
+              const int4 c4 = *reinterpret_cast<const int4*>(sCode + c0 + j);      // broadcast 128-bit load
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + sTable[ci - c4.x]);
+              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + sTable[ci - c4.y]);
+              v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + sTable[ci - c4.z]);
+              v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + sTable[ci - c4.w]);
+            }
           }
           if (use_region) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (sReg[c0 + j] != ri) v[j] = __float_as_uint(__uint_as_float(v[j]) - 100.0f);
+            for (int j = 0; j < 32; j += 4) {
+              const int4 r4 = *reinterpret_cast<const int4*>(sReg + c0 + j);
+              if (r4.x != ri) v[j] = __float_as_uint(__uint_as_float(v[j]) - 100.0f);
+              if (r4.y != ri) v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) - 100.0f);
+              if (r4.z != ri) v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) - 100.0f);
+              if (r4.w != ri) v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) - 100.0f);
+            }
           }
           if (c0 + 32 > a.seq) {
 #pragma unroll
@@ -504,19 +515,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
             tmem_ld_wait();
             uint32_t pk[16], dk[16];
 #pragma unroll
-            for (int x = 0; x < 32; x += 2) {
-              float p[2], ds[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int i = c0 + x + e;
-                float s = __uint_as_float(v[x + e]);
-                if (a.bias_table) s += sTable[sCode[i] + cj];
-                if (use_region && sReg[i] != rj) s -= 100.0f;
-                p[e] = ex2(fmaf(s, TC_LOG2E, -sLse[i]));
-                ds[e] = p[e] * (__uint_as_float(w[x + e]) - sD[i]);
+            for (int x = 0; x < 32; x += 4) {
+              const int i = c0 + x;
+              const int4 c4 = *reinterpret_cast<const int4*>(sCode + i);           // broadcast 128-bit loads
+              const float4 l4 = *reinterpret_cast<const float4*>(sLse + i);
+              const float4 d4 = *reinterpret_cast<const float4*>(sD + i);
+              float s[4] = {__uint_as_float(v[x]), __uint_as_float(v[x + 1]), __uint_as_float(v[x + 2]), __uint_as_float(v[x + 3])};
+              if (a.bias_table) {
+                s[0] += sTable[c4.x + cj]; s[1] += sTable[c4.y + cj]; s[2] += sTable[c4.z + cj]; s[3] += sTable[c4.w + cj];
               }
-              pk[x >> 1] = pack_bf16(p[0], p[1]);
-              dk[x >> 1] = valid ? pack_bf16(ds[0], ds[1]) : 0u;
+              if (use_region) {
+                const int4 r4 = *reinterpret_cast<const int4*>(sReg + i);
+                if (r4.x != rj) s[0] -= 100.0f;
+                if (r4.y != rj) s[1] -= 100.0f;
+                if (r4.z != rj) s[2] -= 100.0f;
+                if (r4.w != rj) s[3] -= 100.0f;
+              }
+              const float p0 = ex2(fmaf(s[0], TC_LOG2E, -l4.x)), p1 = ex2(fmaf(s[1], TC_LOG2E, -l4.y));
+              const float p2 = ex2(fmaf(s[2], TC_LOG2E, -l4.z)), p3 = ex2(fmaf(s[3], TC_LOG2E, -l4.w));
+              const float g0 = p0 * (__uint_as_float(w[x]) - d4.x), g1 = p1 * (__uint_as_float(w[x + 1]) - d4.y);
+              const float g2 = p2 * (__uint_as_float(w[x + 2]) - d4.z), g3 = p3 * (__uint_as_float(w[x + 3]) - d4.w);
+              pk[x >> 1] = pack_bf16(p0, p1);
+              pk[(x >> 1) + 1] = pack_bf16(p2, p3);
+              dk[x >> 1] = valid ? pack_bf16(g0, g1) : 0u;
+              dk[(x >> 1) + 1] = valid ? pack_bf16(g2, g3) : 0u;
             }
             tmem_st_32x16(taddr + pc, pk);
             tmem_st_32x16(taddr + col_dp + pc, dk);
@@ -601,26 +623,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
 }
 
 // dTable[(code_i - code_j + off), h] += sum_b dS^T[b, h, j, i]   (bf16 dS^T, fp32 accumulation)
-// grid = (seq rows j, heads, batch splits); block = nq/4 threads (4 queries each).
+// grid = (seq rows j, heads, batch splits); block = nq/8 threads (8 queries = one 16-byte load each).
 __global__ void dbias_reduce_kernel(const __nv_bfloat16* ds, int batch, int heads, int seq, int nq, const int* rel_code,
                                     int code_off, float* dtable) {
   const int j = blockIdx.x, h = blockIdx.y;
-  const int i0 = threadIdx.x * 4;
+  const int i0 = threadIdx.x * 8;
   if (i0 >= nq) return;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const long long stride = (long long)heads * seq * nq;
   const __nv_bfloat16* p = ds + ((long long)h * seq + j) * nq + i0;
   const int per = (batch + gridDim.z - 1) / gridDim.z;
   const int b0 = blockIdx.z * per, b1 = min(batch, b0 + per);
 #pragma unroll 4
   for (int b = b0; b < b1; ++b) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p + b * stride);
-    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + b * stride));
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
     acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+    acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
   }
   const int cj = rel_code[j];
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
+  for (int e = 0; e < 8; ++e)
     if (i0 + e < seq) atomicAdd(dtable + (long long)(rel_code[i0 + e] - cj + code_off) * heads + h, acc[e]);
 }
 
@@ -681,7 +704,7 @@ extern "C" int clv_attention_bwd_tc(const clv_attn_desc_t* d, const void* qkv, c
   if (dbias_table) {
     const int zsplit = std::max(1, std::min(32, d->batch / 32));
     dim3 g(d->seq, d->heads, zsplit);
-    dbias_reduce_kernel<<<g, a.nq / 4, 0, stream>>>(a.ds_out, d->batch, d->heads, d->seq, a.nq, d->rel_code, d->code_off, dbias_table);
+    dbias_reduce_kernel<<<g, a.nq / 8, 0, stream>>>(a.ds_out, d->batch, d->heads, d->seq, a.nq, d->rel_code, d->code_off, dbias_table);
     if (int rc = after_launch("dbias_reduce_kernel")) return rc;
   }
   return 0;

@@ -76,78 +76,105 @@ CLV_DEVICE long long ln_out_row(const LnArgs& a, long long r) {
   return r;
 }
 
-template <int VPL>
+CLV_DEVICE float ln_blend_weight(const LnArgs& a, long long r) {
+  // row r = (b, d, h, w) of the (B, bD, bH, bW) token grid; mask (B, mh, mw)
+  int w_ = (int)(r % a.bW); long long t = r / a.bW;
+  int h_ = (int)(t % a.bH); t /= a.bH;
+  int b_ = (int)(t / a.bD);
+  return (float)a.blend_mask[((long long)b_ * a.mh + h_ / (a.bH / a.mh)) * a.mw + w_ / (a.bW / a.mw)];
+}
+
+CLV_DEVICE float4 ln_load_x(const LnArgs& a, long long r, long long src_row, int i) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long srow; int col;
+  if (ln_src(a, r, src_row, i, srow, col)) v = ld4(a.x, a.x_bf16, srow * a.ld_x + col);
+  if (a.add0) { float4 t = *reinterpret_cast<const float4*>(a.add0 + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  if (a.add1) { float4 t = *reinterpret_cast<const float4*>(a.add1 + ((r / a.div1) % a.mod1) * a.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  if (a.add2) { float4 t = *reinterpret_cast<const float4*>(a.add2 + ((r / a.div2) % a.mod2) * a.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  return v;
+}
+
+// One warp normalises RPW rows per iteration (RPW > 1 for narrow rows keeps enough bytes in flight per warp).
+template <int VPL, int RPW>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = a.C >> 2;
   const float inv_c = 1.0f / (float)a.C;
-  for (long long r = warp_global; r < a.rows; r += nwarps) {
-    long long src_row = a.row_index ? a.row_index[r] : r;
-    if (a.mode == 1) src_row = window_row_to_src(a.geom, r);
-    const long long orow = ln_out_row(a, r);
-    if (a.mode == 1 && src_row < 0) {  // zero padding is applied AFTER norm1 in the reference
+  for (long long r0 = warp_global * RPW; r0 < a.rows; r0 += nwarps * RPW) {
+    float4 v[RPW][VPL];
+    long long src_row[RPW];
+    bool live[RPW], pad[RPW];
+    float sum[RPW];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+      const long long r = r0 + q;
+      live[q] = r < a.rows;
+      src_row[q] = live[q] ? (a.row_index ? a.row_index[r] : r) : 0;
+      if (a.mode == 1 && live[q]) src_row[q] = window_row_to_src(a.geom, r);
+      pad[q] = a.mode == 1 && src_row[q] < 0;      // zero padding is applied AFTER norm1 in the reference
+      sum[q] = 0.f;
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         const int i = lane + 32 * j;
-        if (i < nvec) st4(a.y, a.y_bf16, orow * a.ld_y + (long long)i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-      }
-      if (lane == 0 && a.mean) { a.mean[r] = 0.f; a.rstd[r] = 0.f; }
-      continue;
-    }
-    float4 v[VPL];
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = lane + 32 * j;
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < nvec) {
-        long long srow; int col;
-        if (ln_src(a, r, src_row, i, srow, col)) v[j] = ld4(a.x, a.x_bf16, srow * a.ld_x + col);
-        if (a.add0) { float4 t = *reinterpret_cast<const float4*>(a.add0 + i * 4); v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w; }
-        if (a.add1) { float4 t = *reinterpret_cast<const float4*>(a.add1 + ((r / a.div1) % a.mod1) * a.C + i * 4); v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w; }
-        if (a.add2) { float4 t = *reinterpret_cast<const float4*>(a.add2 + ((r / a.div2) % a.mod2) * a.C + i * 4); v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w; }
-        sum += v[j].x + v[j].y + v[j].z + v[j].w;
-      }
-    }
-    const float mu = warp_sum(sum) * inv_c;
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = lane + 32 * j;
-      if (i < nvec) {
-        const float dx = v[j].x - mu, dy = v[j].y - mu, dz = v[j].z - mu, dw = v[j].w - mu;
-        sq += dx * dx + dy * dy + dz * dz + dw * dw;
-      }
-    }
-    const float rs = rsqrtf(warp_sum(sq) * inv_c + a.eps);
-    float bw = 0.f;
-    if (a.blend_mask) {
-      // row r = (b, d, h, w) of the (B, bD, bH, bW) token grid; mask (B, mh, mw)
-      int w_ = (int)(r % a.bW); long long t = r / a.bW;
-      int h_ = (int)(t % a.bH); t /= a.bH;
-      int b_ = (int)(t / a.bD);
-      bw = (float)a.blend_mask[((long long)b_ * a.mh + h_ / (a.bH / a.mh)) * a.mw + w_ / (a.bW / a.mw)];
-    }
-#pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = lane + 32 * j;
-      if (i < nvec) {
-        const float4 g = *reinterpret_cast<const float4*>(a.gamma + i * 4);
-        const float4 b = *reinterpret_cast<const float4*>(a.beta + i * 4);
-        float4 o;
-        o.x = (v[j].x - mu) * rs * g.x + b.x; o.y = (v[j].y - mu) * rs * g.y + b.y;
-        o.z = (v[j].z - mu) * rs * g.z + b.z; o.w = (v[j].w - mu) * rs * g.w + b.w;
-        if (a.blend_mask) {
-          const float4 tk = *reinterpret_cast<const float4*>(a.blend_token + i * 4);
-          o.x = o.x * (1.f - bw) + tk.x * bw; o.y = o.y * (1.f - bw) + tk.y * bw;
-          o.z = o.z * (1.f - bw) + tk.z * bw; o.w = o.w * (1.f - bw) + tk.w * bw;
+        v[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live[q] && !pad[q] && i < nvec) {
+          v[q][j] = ln_load_x(a, r, src_row[q], i);
+          sum[q] += v[q][j].x + v[q][j].y + v[q][j].z + v[q][j].w;
         }
-        st4(a.y, a.y_bf16, orow * a.ld_y + (long long)i * 4, o);
       }
     }
-    if (lane == 0 && a.mean) { a.mean[r] = mu; a.rstd[r] = rs; }
+    float mu[RPW], rs[RPW];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) mu[q] = warp_sum(sum[q]) * inv_c;
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) {
+          const float dx = v[q][j].x - mu[q], dy = v[q][j].y - mu[q], dz = v[q][j].z - mu[q], dw = v[q][j].w - mu[q];
+          sq += dx * dx + dy * dy + dz * dz + dw * dw;
+        }
+      }
+      rs[q] = rsqrtf(warp_sum(sq) * inv_c + a.eps);
+    }
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+      const long long r = r0 + q;
+      if (!live[q]) continue;
+      const long long orow = ln_out_row(a, r);
+      if (pad[q]) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int i = lane + 32 * j;
+          if (i < nvec) st4(a.y, a.y_bf16, orow * a.ld_y + (long long)i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        if (lane == 0 && a.mean) { a.mean[r] = 0.f; a.rstd[r] = 0.f; }
+        continue;
+      }
+      const float bw = a.blend_mask ? ln_blend_weight(a, r) : 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) {
+          const float4 g = *reinterpret_cast<const float4*>(a.gamma + i * 4);
+          const float4 b = *reinterpret_cast<const float4*>(a.beta + i * 4);
+          float4 o;
+          o.x = (v[q][j].x - mu[q]) * rs[q] * g.x + b.x; o.y = (v[q][j].y - mu[q]) * rs[q] * g.y + b.y;
+          o.z = (v[q][j].z - mu[q]) * rs[q] * g.z + b.z; o.w = (v[q][j].w - mu[q]) * rs[q] * g.w + b.w;
+          if (a.blend_mask) {
+            const float4 tk = *reinterpret_cast<const float4*>(a.blend_token + i * 4);
+            o.x = o.x * (1.f - bw) + tk.x * bw; o.y = o.y * (1.f - bw) + tk.y * bw;
+            o.z = o.z * (1.f - bw) + tk.z * bw; o.w = o.w * (1.f - bw) + tk.w * bw;
+          }
+          st4(a.y, a.y_bf16, orow * a.ld_y + (long long)i * 4, o);
+        }
+      }
+      if (lane == 0 && a.mean) { a.mean[r] = mu[q]; a.rstd[r] = rs[q]; }
+    }
   }
 }
 
@@ -166,7 +193,7 @@ struct LnBwdArgs {
   int dx_dense;                            // write dx (and copy) at row r instead of the source row
 };
 
-template <int VPL>
+template <int VPL, int RPW>
 __global__ void __launch_bounds__(128) ln_bwd_kernel(LnBwdArgs a) {
   const LnArgs& f = a.f;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -178,70 +205,77 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(LnBwdArgs a) {
 #pragma unroll
   for (int j = 0; j < VPL; ++j) dg[j] = db[j] = dt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (long long r = warp_global; r < f.rows; r += nwarps) {
-    long long src_row = f.row_index ? f.row_index[r] : r;
-    if (f.mode == 1) {
-      src_row = window_row_to_src(f.geom, r);
-      if (src_row < 0) continue;           // padding rows carry no gradient
-    }
-    const long long orow = ln_out_row(f, r);
-    const float mu = f.mean[r], rs = f.rstd[r];
-    float bw = 0.f;
-    if (f.blend_mask) {
-      int w_ = (int)(r % f.bW); long long t = r / f.bW;
-      int h_ = (int)(t % f.bH); t /= f.bH;
-      int b_ = (int)(t / f.bD);
-      bw = (float)f.blend_mask[((long long)b_ * f.mh + h_ / (f.bH / f.mh)) * f.mw + w_ / (f.bW / f.mw)];
-    }
-    float4 xh[VPL], gy[VPL];
-    float s1 = 0.f, s2 = 0.f;
+  for (long long r0 = warp_global * RPW; r0 < f.rows; r0 += nwarps * RPW) {
+    float4 xh[RPW][VPL], gy[RPW][VPL];
+    long long src_row[RPW];
+    bool live[RPW];
+    float s1[RPW], s2[RPW], rsv[RPW];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = lane + 32 * j;
-      xh[j] = gy[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < nvec) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        long long srow; int col;
-        if (ln_src(f, r, src_row, i, srow, col)) v = ld4(f.x, f.x_bf16, srow * f.ld_x + col);
-        if (f.add0) { float4 t = *reinterpret_cast<const float4*>(f.add0 + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        if (f.add1) { float4 t = *reinterpret_cast<const float4*>(f.add1 + ((r / f.div1) % f.mod1) * f.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        if (f.add2) { float4 t = *reinterpret_cast<const float4*>(f.add2 + ((r / f.div2) % f.mod2) * f.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-        xh[j] = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
-        float4 d = ld4(a.dy, a.dy_bf16, orow * a.ld_dy + (long long)i * 4);
-        if (f.blend_mask) {
-          dt[j].x += d.x * bw; dt[j].y += d.y * bw; dt[j].z += d.z * bw; dt[j].w += d.w * bw;
-          d.x *= (1.f - bw); d.y *= (1.f - bw); d.z *= (1.f - bw); d.w *= (1.f - bw);
+    for (int q = 0; q < RPW; ++q) {
+      const long long r = r0 + q;
+      live[q] = r < f.rows;
+      src_row[q] = live[q] ? (f.row_index ? f.row_index[r] : r) : 0;
+      if (f.mode == 1 && live[q]) {
+        src_row[q] = window_row_to_src(f.geom, r);
+        if (src_row[q] < 0) live[q] = false;       // padding rows carry no gradient
+      }
+      s1[q] = s2[q] = 0.f;
+      rsv[q] = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) xh[q][j] = gy[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!live[q]) continue;
+      const long long orow = ln_out_row(f, r);
+      const float mu = f.mean[r], rs = f.rstd[r];
+      rsv[q] = rs;
+      const float bw = f.blend_mask ? ln_blend_weight(f, r) : 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) {
+          const float4 v = ln_load_x(f, r, src_row[q], i);
+          xh[q][j] = make_float4((v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs);
+          float4 d = ld4(a.dy, a.dy_bf16, orow * a.ld_dy + (long long)i * 4);
+          if (f.blend_mask) {
+            dt[j].x += d.x * bw; dt[j].y += d.y * bw; dt[j].z += d.z * bw; dt[j].w += d.w * bw;
+            d.x *= (1.f - bw); d.y *= (1.f - bw); d.z *= (1.f - bw); d.w *= (1.f - bw);
+          }
+          dg[j].x += d.x * xh[q][j].x; dg[j].y += d.y * xh[q][j].y; dg[j].z += d.z * xh[q][j].z; dg[j].w += d.w * xh[q][j].w;
+          db[j].x += d.x; db[j].y += d.y; db[j].z += d.z; db[j].w += d.w;
+          const float4 g = *reinterpret_cast<const float4*>(f.gamma + i * 4);
+          gy[q][j] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+          s1[q] += gy[q][j].x * xh[q][j].x + gy[q][j].y * xh[q][j].y + gy[q][j].z * xh[q][j].z + gy[q][j].w * xh[q][j].w;
+          s2[q] += gy[q][j].x + gy[q][j].y + gy[q][j].z + gy[q][j].w;
         }
-        dg[j].x += d.x * xh[j].x; dg[j].y += d.y * xh[j].y; dg[j].z += d.z * xh[j].z; dg[j].w += d.w * xh[j].w;
-        db[j].x += d.x; db[j].y += d.y; db[j].z += d.z; db[j].w += d.w;
-        const float4 g = *reinterpret_cast<const float4*>(f.gamma + i * 4);
-        gy[j] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-        s1 += gy[j].x * xh[j].x + gy[j].y * xh[j].y + gy[j].z * xh[j].z + gy[j].w * xh[j].w;
-        s2 += gy[j].x + gy[j].y + gy[j].z + gy[j].w;
       }
     }
-    s1 = warp_sum(s1) * inv_c;
-    s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) { s1[q] = warp_sum(s1[q]) * inv_c; s2[q] = warp_sum(s2[q]) * inv_c; }
     if (!a.dx) continue;
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int i = lane + 32 * j;
-      if (i < nvec) {
-        float4 o;
-        o.x = rs * (gy[j].x - s2 - xh[j].x * s1); o.y = rs * (gy[j].y - s2 - xh[j].y * s1);
-        o.z = rs * (gy[j].z - s2 - xh[j].z * s1); o.w = rs * (gy[j].w - s2 - xh[j].w * s1);
-        long long srow; int col;
-        if (!ln_src(f, r, src_row, i, srow, col)) continue;
-        if (a.dx_dense) srow = r;
-        if (a.dres) {
-          const float4 rr = *reinterpret_cast<const float4*>(a.dres + srow * a.ld_dres + col);
-          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-        }
-        *reinterpret_cast<float4*>(a.dx + srow * a.ld_dx + col) = o;
-        if (a.dx_copy) {
-          long long crow = srow;
-          if (a.copy_window_map) crow = src_row_to_window(a.copy_geom, srow);
-          st4(a.dx_copy, a.dx_copy_bf16, crow * a.ld_copy + col, o);
+    for (int q = 0; q < RPW; ++q) {
+      if (!live[q]) continue;
+      const long long r = r0 + q;
+      const float rs = rsv[q];
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nvec) {
+          float4 o;
+          o.x = rs * (gy[q][j].x - s2[q] - xh[q][j].x * s1[q]); o.y = rs * (gy[q][j].y - s2[q] - xh[q][j].y * s1[q]);
+          o.z = rs * (gy[q][j].z - s2[q] - xh[q][j].z * s1[q]); o.w = rs * (gy[q][j].w - s2[q] - xh[q][j].w * s1[q]);
+          long long srow; int col;
+          if (!ln_src(f, r, src_row[q], i, srow, col)) continue;
+          if (a.dx_dense) srow = r;
+          if (a.dres) {
+            const float4 rr = *reinterpret_cast<const float4*>(a.dres + srow * a.ld_dres + col);
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
+          *reinterpret_cast<float4*>(a.dx + srow * a.ld_dx + col) = o;
+          if (a.dx_copy) {
+            long long crow = srow;
+            if (a.copy_window_map) crow = src_row_to_window(a.copy_geom, srow);
+            st4(a.dx_copy, a.dx_copy_bf16, crow * a.ld_copy + col, o);
+          }
         }
       }
     }
@@ -304,15 +338,18 @@ static int build_ln_args(LnArgs& a, const clv_ln_desc_t* d) {
   return 0;
 }
 
+// rows per warp iteration: 4 for C <= 128, 2 for C <= 256 (narrow rows are latency-bound otherwise)
 #define LN_DISPATCH(KERNEL, nvec_per_lane, ...)                    \
   switch (nvec_per_lane) {                                         \
-    case 1: KERNEL<1> __VA_ARGS__; break;                          \
-    case 2: KERNEL<2> __VA_ARGS__; break;                          \
-    case 3: case 4: KERNEL<4> __VA_ARGS__; break;                  \
-    case 5: case 6: case 7: case 8: KERNEL<8> __VA_ARGS__; break;  \
-    case 9: case 10: case 11: case 12: case 13: case 14: case 15: case 16: KERNEL<16> __VA_ARGS__; break; \
-    default: KERNEL<32> __VA_ARGS__; break;                        \
+    case 1: KERNEL<1, 4> __VA_ARGS__; break;                       \
+    case 2: KERNEL<2, 2> __VA_ARGS__; break;                       \
+    case 3: case 4: KERNEL<4, 1> __VA_ARGS__; break;               \
+    case 5: case 6: case 7: case 8: KERNEL<8, 1> __VA_ARGS__; break;  \
+    case 9: case 10: case 11: case 12: case 13: case 14: case 15: case 16: KERNEL<16, 1> __VA_ARGS__; break; \
+    default: KERNEL<32, 1> __VA_ARGS__; break;                     \
   }
+
+static int ln_rows_per_warp(int vpl) { return vpl == 1 ? 4 : (vpl == 2 ? 2 : 1); }
 
 }  // namespace clv
 
@@ -327,7 +364,8 @@ extern "C" int clv_layernorm_fwd(const clv_ln_desc_t* d, void* y, int y_is_bf16,
   if (a.rows == 0) return 0;
   const int vpl = (a.C / 4 + 31) / 32;
   const int warps_per_block = 8;
-  long long blocks = (a.rows + warps_per_block - 1) / warps_per_block;
+  const long long rows_per_block = (long long)warps_per_block * ln_rows_per_warp(vpl);
+  long long blocks = (a.rows + rows_per_block - 1) / rows_per_block;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   LN_DISPATCH(ln_fwd_kernel, vpl, <<<(int)blocks, warps_per_block * 32, 0, stream>>>(a));
@@ -349,7 +387,8 @@ extern "C" int clv_layernorm_bwd(const clv_ln_desc_t* d, const clv_ln_bwd_t* b, 
   if (a.f.rows == 0) return 0;
   const int vpl = (a.f.C / 4 + 31) / 32;
   const int warps_per_block = 4;
-  long long blocks = (a.f.rows + warps_per_block - 1) / warps_per_block;
+  const long long rows_per_block = (long long)warps_per_block * ln_rows_per_warp(vpl);
+  long long blocks = (a.f.rows + rows_per_block - 1) / rows_per_block;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)warps_per_block * a.f.C * sizeof(float);
