@@ -224,6 +224,7 @@ def run_ours(args):
         for f, fl, by, ms in prof:
             a = fam.setdefault(f, [0.0, 0.0, 0.0, 0])
             a[0] += fl; a[1] += by; a[2] += ms; a[3] += 1
+        fam_total = sum(v[2] for v in fam.values()) / args.steps
         if os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1":
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             rows = sorted(((k, v[3] // args.steps, v[2] / args.steps, v[0] / max(v[2], 1e-9) / 1e9, v[1] / max(v[2], 1e-9) / 1e6)
@@ -244,7 +245,8 @@ def run_ours(args):
                     "unit": "TFLOP/s", "frac": gemm_tflops / sus, "traffic": traffic, "peak_source": f"{src} bf16_tflops_sustained",
                     "launches_timed": g[3], "avg_launch_ms": g[2] / max(1, g[3]),
                     "share_of_step": g[2] / (ms_step * args.steps),
-                    "families_ms_per_step": {k: v[2] / args.steps for k, v in fam.items()},
+                    "families_ms_per_step": {k: round(v[2] / args.steps, 3) for k, v in fam.items() if not k.startswith("gemm ")},
+                    "untracked_ms_per_step": round(ms_step - fam_total, 3),
                     "window_attn_core_tflops": (fam.get("attn_fwd_hd32", [0, 0, 1e-9])[0] + fam.get("attn_bwd_hd32", [0, 0, 1e-9])[0]) /
                                                ((fam.get("attn_fwd_hd32", [0, 0, 1e-9])[2] + fam.get("attn_bwd_hd32", [0, 0, 1e-9])[2]) * 1e-3) / 1e12,
                     "step_model_tflops": FLOP_PER_CLIP_FWD_BWD * clips / (ms_step * 1e-3) / 1e12}

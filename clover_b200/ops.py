@@ -81,6 +81,21 @@ def _prof_close(e0, family, flops, nbytes):
         _PROF.append((family, flops, nbytes, e0, e1))
 
 
+def _profiled(family):
+    def deco(fn):
+        def wrapped(*a, **k):
+            if _PROF is None:
+                return fn(*a, **k)
+            e0 = _prof_open()
+            out = fn(*a, **k)
+            _prof_close(e0, family, 0.0, 0.0)
+            return out
+        wrapped.__name__ = fn.__name__
+        wrapped.__doc__ = fn.__doc__
+        return wrapped
+    return deco
+
+
 class Window:
     """Clamped window geometry of one Swin block call (get_window_size, swin_transformer_3d.py:302-315)."""
 
@@ -185,6 +200,7 @@ def _ln_desc(x, gamma, beta, eps, rows, Cn, mean, rstd, *, window=None, merge=No
     return d
 
 
+@_profiled("ln_fwd")
 def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **kw):
     """y = LN(gather(x) + adds) (* blend).  x: [..., C] fp32/bf16 2-D; y: 2-D bf16/fp32."""
     _need_cuda(x, gamma, beta, y)
@@ -195,6 +211,7 @@ def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **
     return y
 
 
+@_profiled("ln_bwd")
 def layernorm_bwd(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=None, dx_copy=None, copy_window=None,
                   dgamma=None, dbeta=None, dtoken=None, dx_dense=False, **kw):
     _need_cuda(x, gamma, dy)
@@ -268,6 +285,7 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
 
 
 # ------------------------------------------------------------------------------------------------
+@_profiled("cast")
 def cast(src, dst, scale=1.0):
     _need_cuda(src, dst)
     if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
@@ -283,6 +301,7 @@ def to_bf16(src):
     return cast(src, torch.empty(src.shape, dtype=BF16, device=src.device))
 
 
+@_profiled("gelu")
 def gelu(x, y, dy=None):
     """y = GELU(x), or y = dy * GELU'(x) when dy is given (contiguous tensors of equal size)."""
     _need_cuda(x, y, dy)
@@ -294,6 +313,7 @@ def gelu(x, y, dy=None):
     return y
 
 
+@_profiled("patchify")
 def patchify(x, patch):
     """x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw] and (D,Hp,Wp)."""
     _need_cuda(x)
@@ -307,6 +327,7 @@ def patchify(x, patch):
     return out, (D, Hp, Wp)
 
 
+@_profiled("colsum")
 def grouped_colsum(x, out, div=1, mod=1, scale=1.0, accumulate=False, rows=None):
     _need_cuda(x, out)
     if out.dtype != F32 or not out.is_contiguous():
@@ -318,6 +339,7 @@ def grouped_colsum(x, out, div=1, mod=1, scale=1.0, accumulate=False, rows=None)
     return out
 
 
+@_profiled("rows_affine")
 def rows_affine(y, rows, Cn, x=None, in_group=None, out_group=None, add0=None, bvec=None, bdiv=1, bscale=1.0):
     _need_cuda(y)
     d = RowsAffine()
@@ -336,6 +358,7 @@ def rows_affine(y, rows, Cn, x=None, in_group=None, out_group=None, add0=None, b
     return y
 
 
+@_profiled("scatter_add")
 def scatter_add_rows(src, index, dst):
     _need_cuda(src, index, dst)
     if src.dtype != F32 or dst.dtype != F32 or index.dtype != torch.int64:
@@ -346,6 +369,7 @@ def scatter_add_rows(src, index, dst):
 
 
 # ------------------------------------------------------------------------------------------------
+@_profiled("nce_fwd")
 def nce_rank_fwd(embs, temperature, margin, use_rank, eps=1e-8):
     """embs: list of (nblk+1) contiguous fp32 [Bg, D] (query side first).  Returns (losses[2], workspace)."""
     _need_cuda(*embs)
@@ -363,6 +387,7 @@ def nce_rank_fwd(embs, temperature, margin, use_rank, eps=1e-8):
     return out, ws
 
 
+@_profiled("nce_bwd")
 def nce_rank_bwd(ws, nblk, Bg, D, temperature, use_rank, g_nce, g_rank):
     grads = [torch.empty(Bg, D, dtype=F32, device=ws.device) for _ in range(nblk + 1)]
     arr = (C.c_void_p * (nblk + 1))(*[g.data_ptr() for g in grads])
@@ -371,6 +396,7 @@ def nce_rank_bwd(ws, nblk, Bg, D, temperature, use_rank, g_nce, g_rank):
     return grads
 
 
+@_profiled("focal_fwd")
 def softmax_focal_fwd(logits, target, V, gamma, ignore_index=-100):
     """logits fp32 [rows, >=V]; returns (loss[1], stats, sums)."""
     _need_cuda(logits, target)
@@ -386,6 +412,7 @@ def softmax_focal_fwd(logits, target, V, gamma, ignore_index=-100):
     return loss, stats, sums
 
 
+@_profiled("focal_bwd")
 def softmax_focal_bwd(logits, target, V, gamma, stats, sums, g_loss, dlogits):
     Vpad = dlogits.shape[1]
     _lib.check(_lib.load().clv_softmax_focal_bwd(_ptr(logits), logits.stride(0), logits.shape[0], V, Vpad, _ptr(target),
