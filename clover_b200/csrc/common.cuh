@@ -106,33 +106,34 @@ struct WindowGeom {
 };
 
 // window-order row r -> source spatial row (or -1 when the token lies in the zero padding).
-CLV_DEVICE long long window_row_to_src(const WindowGeom& g, long long r) {
-  int n = (int)(r % g.N);
-  long long gi = r / g.N;
-  int win = (int)(gi % g.nWin);
-  int b = (int)(gi / g.nWin);
-  int bw = win % g.nW, bh = (win / g.nW) % g.nH, bd = win / (g.nW * g.nH);
-  int lw = n % g.ww, lh = (n / g.ww) % g.wh, ld = n / (g.ww * g.wh);
+// Row counts fit 32 bits (checked on the host): 64-bit div/mod would cost more than the rest of a row.
+CLV_DEVICE long long window_row_to_src(const WindowGeom& g, long long r64) {
+  const unsigned r = (unsigned)r64;
+  const unsigned n = r % (unsigned)g.N, gi = r / (unsigned)g.N;
+  const unsigned win = gi % (unsigned)g.nWin, b = gi / (unsigned)g.nWin;
+  const int bw = win % g.nW, bh = (win / g.nW) % g.nH, bd = win / (g.nW * g.nH);
+  const int lw = n % g.ww, lh = (n / g.ww) % g.wh, ld = n / (g.ww * g.wh);
   int d = bd * g.wd + ld + g.sd; if (d >= g.Dp) d -= g.Dp;
   int h = bh * g.wh + lh + g.sh; if (h >= g.Hp) h -= g.Hp;
   int w = bw * g.ww + lw + g.sw; if (w >= g.Wp) w -= g.Wp;
   if (d >= g.D || h >= g.H || w >= g.W) return -1;
-  return (((long long)b * g.D + d) * g.H + h) * g.W + w;
+  return (long long)(((b * (unsigned)g.D + d) * (unsigned)g.H + h) * (unsigned)g.W + w);
 }
 
 // source spatial row s -> window-order row (always valid: every real token lives in one window).
-CLV_DEVICE long long src_row_to_window(const WindowGeom& g, long long s) {
-  int w = (int)(s % g.W); long long t = s / g.W;
-  int h = (int)(t % g.H); t /= g.H;
-  int d = (int)(t % g.D); int b = (int)(t / g.D);
+CLV_DEVICE long long src_row_to_window(const WindowGeom& g, long long s64) {
+  const unsigned s = (unsigned)s64;
+  const int w = s % (unsigned)g.W; unsigned t = s / (unsigned)g.W;
+  const int h = t % (unsigned)g.H; t /= (unsigned)g.H;
+  const int d = t % (unsigned)g.D; const unsigned b = t / (unsigned)g.D;
   int d2 = d - g.sd; if (d2 < 0) d2 += g.Dp;
   int h2 = h - g.sh; if (h2 < 0) h2 += g.Hp;
   int w2 = w - g.sw; if (w2 < 0) w2 += g.Wp;
-  int bd = d2 / g.wd, ld = d2 % g.wd;
-  int bh = h2 / g.wh, lh = h2 % g.wh;
-  int bw = w2 / g.ww, lw = w2 % g.ww;
-  long long win = ((long long)b * g.nD + bd) * g.nH * g.nW + (long long)bh * g.nW + bw;
-  return win * g.N + (ld * g.wh + lh) * g.ww + lw;
+  const int bd = d2 / g.wd, ld = d2 % g.wd;
+  const int bh = h2 / g.wh, lh = h2 % g.wh;
+  const int bw = w2 / g.ww, lw = w2 % g.ww;
+  const unsigned win = ((b * g.nD + bd) * g.nH + bh) * g.nW + bw;
+  return (long long)(win * (unsigned)g.N + (ld * g.wh + lh) * g.ww + lw);
 }
 
 // ------------------------------------------------------------------------------------------

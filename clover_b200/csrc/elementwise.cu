@@ -180,9 +180,9 @@ __global__ void rows_affine_kernel(RowsAffineArgs a) {
   const long long total = a.rows * nvec;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long r = i / nvec; const int c = (int)(i % nvec) * 4;
-    const long long ir = a.in_group_rows > 0 ? (r / a.in_group_rows) * a.in_group_stride + r % a.in_group_rows + a.in_offset : r;
-    const long long orow = a.out_group_rows > 0 ? (r / a.out_group_rows) * a.out_group_stride + r % a.out_group_rows + a.out_offset : r;
+    const unsigned r32 = (unsigned)(i / nvec); const long long r = r32; const int c = (int)(i % nvec) * 4;
+    const long long ir = a.in_group_rows > 0 ? (long long)(r32 / (unsigned)a.in_group_rows) * a.in_group_stride + r32 % (unsigned)a.in_group_rows + a.in_offset : r;
+    const long long orow = a.out_group_rows > 0 ? (long long)(r32 / (unsigned)a.out_group_rows) * a.out_group_stride + r32 % (unsigned)a.out_group_rows + a.out_offset : r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.x) v = ldv4(a.x, a.x_bf16, ir * a.ld_x + c);
     if (a.add0) { const float4 t = *reinterpret_cast<const float4*>(a.add0 + c); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }

@@ -56,10 +56,11 @@ CLV_DEVICE bool ln_src(const LnArgs& a, long long r, long long src_row, int i, l
     const int e = i * 4;
     const int part = e / a.mC;
     col = e % a.mC;
-    const int W2 = (a.mW + 1) / 2, H2 = (a.mH + 1) / 2;
-    int w2 = (int)(r % W2); long long t = r / W2;
+    const unsigned W2 = (a.mW + 1) / 2, H2 = (a.mH + 1) / 2;
+    const unsigned r32 = (unsigned)r;
+    int w2 = (int)(r32 % W2); unsigned t = r32 / W2;
     int h2 = (int)(t % H2); t /= H2;
-    int d = (int)(t % a.mD); int b = (int)(t / a.mD);
+    int d = (int)(t % (unsigned)a.mD); int b = (int)(t / (unsigned)a.mD);
     // PatchMerging channel blocks: [(even h, even w), (odd h, even w), (even h, odd w), (odd h, odd w)]
     const int h = 2 * h2 + (part & 1), w = 2 * w2 + (part >> 1);
     if (h >= a.mH || w >= a.mW) return false;
@@ -72,15 +73,19 @@ CLV_DEVICE bool ln_src(const LnArgs& a, long long r, long long src_row, int i, l
 }
 
 CLV_DEVICE long long ln_out_row(const LnArgs& a, long long r) {
-  if (a.group_rows > 0) return (r / a.group_rows) * a.group_stride + (r % a.group_rows) + a.row_offset;
+  if (a.group_rows > 0) {
+    const unsigned r32 = (unsigned)r, gr = (unsigned)a.group_rows;
+    return (long long)(r32 / gr) * a.group_stride + (r32 % gr) + a.row_offset;
+  }
   return r;
 }
 
 CLV_DEVICE float ln_blend_weight(const LnArgs& a, long long r) {
   // row r = (b, d, h, w) of the (B, bD, bH, bW) token grid; mask (B, mh, mw)
-  int w_ = (int)(r % a.bW); long long t = r / a.bW;
-  int h_ = (int)(t % a.bH); t /= a.bH;
-  int b_ = (int)(t / a.bD);
+  const unsigned r32 = (unsigned)r;
+  int w_ = (int)(r32 % (unsigned)a.bW); unsigned t = r32 / (unsigned)a.bW;
+  int h_ = (int)(t % (unsigned)a.bH); t /= (unsigned)a.bH;
+  int b_ = (int)(t / (unsigned)a.bD);
   return (float)a.blend_mask[((long long)b_ * a.mh + h_ / (a.bH / a.mh)) * a.mw + w_ / (a.bW / a.mw)];
 }
 
@@ -89,8 +94,8 @@ CLV_DEVICE float4 ln_load_x(const LnArgs& a, long long r, long long src_row, int
   long long srow; int col;
   if (ln_src(a, r, src_row, i, srow, col)) v = ld4(a.x, a.x_bf16, srow * a.ld_x + col);
   if (a.add0) { float4 t = *reinterpret_cast<const float4*>(a.add0 + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-  if (a.add1) { float4 t = *reinterpret_cast<const float4*>(a.add1 + ((r / a.div1) % a.mod1) * a.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
-  if (a.add2) { float4 t = *reinterpret_cast<const float4*>(a.add2 + ((r / a.div2) % a.mod2) * a.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  if (a.add1) { float4 t = *reinterpret_cast<const float4*>(a.add1 + (((unsigned)r / (unsigned)a.div1) % (unsigned)a.mod1) * a.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  if (a.add2) { float4 t = *reinterpret_cast<const float4*>(a.add2 + (((unsigned)r / (unsigned)a.div2) % (unsigned)a.mod2) * a.C + i * 4); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
   return v;
 }
 
@@ -256,6 +261,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(LnBwdArgs a) {
       if (!live[q]) continue;
       const long long r = r0 + q;
       const float rs = rsv[q];
+      long long crow_w = 0;
+      if (a.dx_copy && a.copy_window_map && f.mode != 2) crow_w = src_row_to_window(a.copy_geom, a.dx_dense ? r : src_row[q]);
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         const int i = lane + 32 * j;
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(LnBwdArgs a) {
           *reinterpret_cast<float4*>(a.dx + srow * a.ld_dx + col) = o;
           if (a.dx_copy) {
             long long crow = srow;
-            if (a.copy_window_map) crow = src_row_to_window(a.copy_geom, srow);
+            if (a.copy_window_map) crow = (f.mode != 2) ? crow_w : src_row_to_window(a.copy_geom, srow);
             st4(a.dx_copy, a.dx_copy_bf16, crow * a.ld_copy + col, o);
           }
         }
@@ -329,6 +336,7 @@ static int build_ln_args(LnArgs& a, const clv_ln_desc_t* d) {
   a.add0 = d->add0; a.add1 = d->add1; a.div1 = d->div1 > 0 ? d->div1 : 1; a.mod1 = d->mod1 > 0 ? d->mod1 : 1;
   a.add2 = d->add2; a.div2 = d->div2 > 0 ? d->div2 : 1; a.mod2 = d->mod2 > 0 ? d->mod2 : 1;
   a.group_rows = d->group_rows; a.group_stride = d->group_stride; a.row_offset = d->row_offset;
+  CLV_REQUIRE(d->rows < 2000000000LL, "layernorm: more than 2^31 rows");
   a.row_index = d->row_index;
   CLV_REQUIRE(!a.row_index || a.mode == 0, "layernorm: row_index only with the plain mode");
   a.blend_mask = d->blend_mask; a.blend_token = d->blend_token;
