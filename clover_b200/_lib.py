@@ -53,6 +53,20 @@ class LnBwd(C.Structure):
     ]
 
 
+class LnrDesc(C.Structure):
+    _fields_ = [
+        ("x", c_vp), ("x_is_bf16", C.c_int), ("gamma", c_vp), ("beta", c_vp), ("eps", C.c_float),
+        ("mean", c_vp), ("rstd", c_vp), ("rows", c_ll), ("C", C.c_int), ("row_map", c_vp), ("map_period", C.c_int),
+    ]
+
+
+class LnrBwd(C.Structure):
+    _fields_ = [
+        ("dy", c_vp), ("dy_is_bf16", C.c_int), ("dy_mapped", C.c_int), ("dres", c_vp), ("dx", c_vp),
+        ("dx_bf16", c_vp), ("dx_bf16_mapped", C.c_int), ("dgamma", c_vp), ("dbeta", c_vp),
+    ]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [
         ("batch", C.c_int), ("seq", C.c_int), ("heads", C.c_int), ("head_dim", C.c_int),
@@ -81,6 +95,9 @@ SIGNATURES = {
                                 C.POINTER(GemmEpilogue), c_vp]),
     "clv_layernorm_fwd": (C.c_int, [C.POINTER(LnDesc), c_vp, C.c_int, c_ll, c_vp]),
     "clv_layernorm_bwd": (C.c_int, [C.POINTER(LnDesc), C.POINTER(LnBwd), c_vp]),
+    "clv_lnr_supported": (C.c_int, [C.c_int]),
+    "clv_lnr_fwd": (C.c_int, [C.POINTER(LnrDesc), c_vp, C.c_int, C.c_int, c_vp]),
+    "clv_lnr_bwd": (C.c_int, [C.POINTER(LnrDesc), C.POINTER(LnrBwd), c_vp]),
     "clv_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_fwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),

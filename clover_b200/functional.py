@@ -60,6 +60,28 @@ def _wgrad(dy16, x16, out_features, in_features):
     return dW
 
 
+# bf16 copy of the most recent fp32 residual-stream gradient: norm1's backward writes it next to d x so that the
+# consumer (the previous block's / PatchMerging's backward) does not need a separate cast pass over the tensor.
+_GRAD16 = [None]
+
+
+def _publish_grad16(t32, t16):
+    _GRAD16[0] = (t32, t32._version, t16)
+
+
+def _grad_bf16(t):
+    """bf16 copy of gradient t (fp32 [T, C]); reuses the copy published by the producing kernel when there is one."""
+    if t.dtype == BF16:
+        return t
+    ent, _GRAD16[0] = _GRAD16[0], None
+    if ent is not None:
+        t32, ver, t16 = ent
+        if (t32.data_ptr() == t.data_ptr() and t32.numel() == t.numel() and t.is_contiguous() and t._version == ver
+                and t32._version == ver):
+            return t16.view(t.shape)
+    return ops.to_bf16(t)
+
+
 def _colsum(x, n):
     out = torch.empty(1, n, dtype=F32, device=x.device)
     ops.grouped_colsum(x, out)
@@ -192,7 +214,10 @@ class LayerNormFn(torch.autograd.Function):
         y = torch.empty(rows, C, dtype=F32 if out_fp32 else BF16, device=x.device)
         mean = torch.empty(rows, dtype=F32, device=x.device)
         rstd = torch.empty(rows, dtype=F32, device=x.device)
-        ops.layernorm_fwd(x, gamma, beta, eps, y, mean=mean, rstd=rstd)
+        if x.is_contiguous() and ops.lnr_supported(C):
+            ops.lnr_fwd(x, gamma, beta, eps, y, mean=mean, rstd=rstd)
+        else:
+            ops.layernorm_fwd(x, gamma, beta, eps, y, mean=mean, rstd=rstd)
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.eps = eps
         return y
@@ -202,11 +227,18 @@ class LayerNormFn(torch.autograd.Function):
         x, gamma, beta, mean, rstd = ctx.saved_tensors
         rows, C = x.shape
         dy = dy.contiguous()
-        dx32 = torch.empty(rows, C, dtype=F32, device=x.device)
         small = _zeros(2 * C, x.device)
         copy = torch.empty(rows, C, dtype=BF16, device=x.device) if x.dtype == BF16 else None
-        ops.layernorm_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, rows=rows, dx=dx32, dx_copy=copy,
-                          dgamma=small[:C], dbeta=small[C:])
+        fast = x.is_contiguous() and ops.lnr_supported(C)
+        dx32 = torch.empty(rows, C, dtype=F32, device=x.device) if (copy is None or not fast) else None
+        if fast:
+            if copy is not None:                  # bf16 activations (BERT): only the bf16 gradient is consumed
+                ops.lnr_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, dx_bf16=copy, dgamma=small[:C], dbeta=small[C:])
+            else:
+                ops.lnr_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, dx=dx32, dgamma=small[:C], dbeta=small[C:])
+        else:
+            ops.layernorm_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, rows=rows, dx=dx32, dx_copy=copy,
+                              dgamma=small[:C], dbeta=small[C:])
         return (copy if copy is not None else dx32), small[:C], small[C:], None, None
 
 
@@ -282,7 +314,12 @@ class SwinBlockFn(torch.autograd.Function):
         stats = torch.empty(2 * rows + 2 * T, dtype=F32, device=dev)
         mean1, rstd1, mean2, rstd2 = stats[:rows], stats[rows:2 * rows], stats[2 * rows:2 * rows + T], stats[2 * rows + T:]
         xw = torch.empty(rows, C, dtype=BF16, device=dev)
-        ops.layernorm_fwd(x, n1w, n1b, 1e-5, xw, mean=mean1, rstd=rstd1, window=wg)
+        fast_ln = (not wg.padded) and x.is_contiguous() and ops.lnr_supported(C)
+        rmap = wg.row_map(dev) if fast_ln else None
+        if fast_ln:
+            ops.lnr_fwd(x, n1w, n1b, 1e-5, xw, mean=mean1, rstd=rstd1, row_map=rmap, y_mapped=True)
+        else:
+            ops.layernorm_fwd(x, n1w, n1b, 1e-5, xw, mean=mean1, rstd=rstd1, window=wg)
         qkv = torch.empty(rows, 3 * C, dtype=BF16, device=dev)
         scale = hd ** -0.5
         ops.gemm(xw, wq, qkv, bias=qkv_b, scale_cols=C, scale=scale)
@@ -294,7 +331,10 @@ class SwinBlockFn(torch.autograd.Function):
         x_mid = torch.empty(T, C, dtype=F32, device=dev)
         ops.gemm(ao, wp, x_mid, bias=proj_b, residual=x, window=wg)
         h2 = torch.empty(T, C, dtype=BF16, device=dev)
-        ops.layernorm_fwd(x_mid, n2w, n2b, 1e-5, h2, mean=mean2, rstd=rstd2)
+        if fast_ln:
+            ops.lnr_fwd(x_mid, n2w, n2b, 1e-5, h2, mean=mean2, rstd=rstd2)
+        else:
+            ops.layernorm_fwd(x_mid, n2w, n2b, 1e-5, h2, mean=mean2, rstd=rstd2)
         pre = torch.empty(T, fc1_w.shape[0], dtype=BF16, device=dev)
         act = torch.empty(T, fc1_w.shape[0], dtype=BF16, device=dev)
         ops.gemm(h2, w1, act, bias=fc1_b, act="gelu", out_pre=pre)
@@ -303,14 +343,14 @@ class SwinBlockFn(torch.autograd.Function):
         ctx.save_for_backward(x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region,
                               n1w, n1b, n2w, n2b, table)
         ctx.w = (wq, wp, w1, w2)
-        ctx.meta = (wg, heads, hd, code_off, scale, fc1_w.shape[0])
+        ctx.meta = (wg, heads, hd, code_off, scale, fc1_w.shape[0], rmap)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region, n1w, n1b, n2w, n2b, table) = ctx.saved_tensors
         wq, wp, w1, w2 = ctx.w
-        wg, heads, hd, code_off, scale, Hd = ctx.meta
+        wg, heads, hd, code_off, scale, Hd, rmap = ctx.meta
         T, C = x.shape
         rows = wg.rows
         dev = x.device
@@ -320,7 +360,7 @@ class SwinBlockFn(torch.autograd.Function):
         dg1, db1, dg2, db2 = small[:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
         dtable = small[4 * C:].view_as(table)
         # ---- MLP branch
-        dy16 = ops.to_bf16(dout)
+        dy16 = _grad_bf16(dout)
         dpre = torch.empty(T, Hd, dtype=BF16, device=dev)
         ops.gemm(dy16, w2, dpre, b_t=True, gelu_pre=pre)
         dW2 = _wgrad(dy16, act, C, Hd)
@@ -333,8 +373,12 @@ class SwinBlockFn(torch.autograd.Function):
         # ---- LN2 backward: d x_mid = dout + LN2'(dh2); bf16 copy emitted in window order for proj
         dmid = torch.empty(T, C, dtype=F32, device=dev)
         dmid_w = (torch.zeros if wg.padded else torch.empty)(rows, C, dtype=BF16, device=dev)
-        ops.layernorm_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, rows=T, dx=dmid, dres=dout, dx_copy=dmid_w,
-                          copy_window=wg, dgamma=dg2, dbeta=db2)
+        if rmap is not None:
+            ops.lnr_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, dx=dmid, dres=dout, dx_bf16=dmid_w, row_map=rmap,
+                        dx_bf16_mapped=True, dgamma=dg2, dbeta=db2)
+        else:
+            ops.layernorm_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, rows=T, dx=dmid, dres=dout, dx_copy=dmid_w,
+                              copy_window=wg, dgamma=dg2, dbeta=db2)
         # ---- attention branch
         dao = torch.empty(rows, C, dtype=BF16, device=dev)
         ops.gemm(dmid_w, wp, dao, b_t=True)
@@ -348,8 +392,14 @@ class SwinBlockFn(torch.autograd.Function):
         dWq = _wgrad(dqkv, xw, 3 * C, C)
         dBq = _colsum(dqkv, 3 * C)
         # ---- LN1 backward through the window gather, accumulated onto d x_mid in place
-        ops.layernorm_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, rows=rows, dx=dmid, dres=dmid, dgamma=dg1, dbeta=db1,
-                          window=wg)
+        if rmap is not None:
+            dmid16 = dmid_w                                   # reuse: [T, C] bf16 (rows == T when unpadded)
+            ops.lnr_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, dx=dmid, dres=dmid, dx_bf16=dmid16, row_map=rmap,
+                        dy_mapped=True, dgamma=dg1, dbeta=db1)
+            _publish_grad16(dmid, dmid16)
+        else:
+            ops.layernorm_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, rows=rows, dx=dmid, dres=dmid, dgamma=dg1, dbeta=db1,
+                              window=wg)
         return (dmid, None, None, None, None, None,
                 dg1, db1, dWq, dBq, dtable, dWp, dBp, dg2, db2, dW1, dB1, dW2, dB2)
 
@@ -434,7 +484,7 @@ class PatchMergeFn(torch.autograd.Function):
         (B, D, H, W), wb, Co = ctx.meta
         C = x.shape[1]
         rows = h.shape[0]
-        dy16 = ops.to_bf16(dout.contiguous())
+        dy16 = _grad_bf16(dout.contiguous())
         dh = torch.empty(rows, 4 * C, dtype=BF16, device=x.device)
         ops.gemm(dy16, wb, dh, b_t=True)
         dW = _wgrad(dy16, h, Co, 4 * C)

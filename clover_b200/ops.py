@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, GemmEpilogue, LnBwd, LnDesc, RowsAffine, WindowGeom
+from ._lib import AttnDesc, GemmEpilogue, LnBwd, LnDesc, LnrBwd, LnrDesc, RowsAffine, WindowGeom
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -115,6 +115,21 @@ class Window:
 
     def ref(self):
         return C.pointer(self.c)
+
+    def row_map(self, device):
+        """int32 [D*H*W] device tensor: window-order row (within a clip) of every spatial token (unpadded frames)."""
+        if self.padded:
+            raise ValueError("row_map: the frame is padded to window multiples; use the closed-form kernels")
+        key = (self.D, self.H, self.W, self.window, self.shift, str(device))
+        t = _ROW_MAPS.get(key)
+        if t is None:
+            from . import tables
+            t = torch.from_numpy(tables.window_row_map(self.D, self.H, self.W, self.window, self.shift)).to(device)
+            _ROW_MAPS[key] = t
+        return t
+
+
+_ROW_MAPS = {}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,6 +247,53 @@ def layernorm_bwd(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=No
     b.dgamma, b.dbeta, b.dtoken = _ptr(dgamma), _ptr(dbeta), _ptr(dtoken)
     b.dx_dense = int(dx_dense)
     _lib.check(_lib.load().clv_layernorm_bwd(C.byref(d), C.byref(b), _stream()), "clv_layernorm_bwd")
+
+
+def lnr_supported(Cn):
+    return bool(_lib.load().clv_lnr_supported(int(Cn)))
+
+
+def _lnr_desc(x, gamma, beta, eps, mean, rstd, row_map):
+    if x.dim() != 2 or not x.is_contiguous():
+        raise ValueError("lnr: x must be a contiguous 2-D tensor")
+    d = LnrDesc()
+    d.x, d.x_is_bf16 = _ptr(x), _is_bf16(x)
+    d.gamma, d.beta, d.eps = _ptr(gamma), _ptr(beta), float(eps)
+    d.mean, d.rstd = _ptr(mean), _ptr(rstd)
+    d.rows, d.C = x.shape[0], x.shape[1]
+    if row_map is not None:
+        if row_map.dtype != torch.int32 or not row_map.is_contiguous():
+            raise TypeError("lnr: row_map must be contiguous int32")
+        d.row_map, d.map_period = _ptr(row_map), row_map.numel()
+    return d
+
+
+@_profiled("ln_fwd")
+def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_mapped=False):
+    """y[m(s)] = LN(x[s]) on dense rows (clv_lnr_fwd); m = identity unless y_mapped."""
+    _need_cuda(x, gamma, beta, y)
+    if y.shape != x.shape or not y.is_contiguous():
+        raise ValueError("lnr_fwd: y must be contiguous with x's shape")
+    d = _lnr_desc(x, gamma, beta, eps, mean, rstd, row_map)
+    _lib.check(_lib.load().clv_lnr_fwd(C.byref(d), _ptr(y), _is_bf16(y), int(y_mapped), _stream()), "clv_lnr_fwd")
+    return y
+
+
+@_profiled("ln_bwd")
+def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, row_map=None, dy_mapped=False,
+            dx_bf16_mapped=False, dgamma=None, dbeta=None):
+    _need_cuda(x, gamma, dy)
+    for t, n in ((dy, "dy"), (dx, "dx"), (dres, "dres"), (dx_bf16, "dx_bf16")):
+        if t is not None and (t.shape != x.shape or not t.is_contiguous()):
+            raise ValueError(f"lnr_bwd: {n} must be contiguous with x's shape")
+    if (dx is not None and dx.dtype != F32) or (dres is not None and dres.dtype != F32) or (dx_bf16 is not None and dx_bf16.dtype != BF16):
+        raise TypeError("lnr_bwd: dx / dres fp32 and dx_bf16 bf16 required")
+    d = _lnr_desc(x, gamma, beta, eps, mean, rstd, row_map)
+    b = LnrBwd()
+    b.dy, b.dy_is_bf16, b.dy_mapped = _ptr(dy), _is_bf16(dy), int(dy_mapped)
+    b.dres, b.dx, b.dx_bf16, b.dx_bf16_mapped = _ptr(dres), _ptr(dx), _ptr(dx_bf16), int(dx_bf16_mapped)
+    b.dgamma, b.dbeta = _ptr(dgamma), _ptr(dbeta)
+    _lib.check(_lib.load().clv_lnr_bwd(C.byref(d), C.byref(b), _stream()), "clv_lnr_bwd")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -82,3 +82,14 @@ def window_gather_index(B, D, H, W, window, shift):
     w = ((g % nW) * ww + n % ww + shift[2]) % W
     src = (d * H + h) * W + w
     return (np.arange(B, dtype=np.int64)[:, None, None] * (D * H * W) + src[None]).reshape(B * src.shape[0], -1)
+
+
+@lru_cache(maxsize=None)
+def window_row_map(D, H, W, window, shift):
+    """int32 (D*H*W,): window-order row (within one clip) of every spatial token s of an UNPADDED frame --
+    the inverse permutation of :func:`window_gather_index`, i.e. where roll(-shift) + window_partition
+    (swin_transformer_3d.py:456-466) puts token s; window_reverse + roll(+shift) (:471-479) reads it back."""
+    src = window_gather_index(1, D, H, W, tuple(window), tuple(shift)).reshape(-1)
+    inv = np.empty(D * H * W, dtype=np.int32)
+    inv[src] = np.arange(D * H * W, dtype=np.int32)
+    return inv

@@ -106,8 +106,36 @@ typedef struct {
 
 int clv_layernorm_bwd(const clv_ln_desc_t* desc, const clv_ln_bwd_t* bwd, void* stream);
 
+/* Row-mapped LayerNorm on dense contiguous rows [rows, C] (pitch == C): the lean hot path of
+ * SwinTransformerBlock3D's norm1 / norm2 (swin_transformer_3d.py:450,483) and of every plain nn.LayerNorm.
+ * Statistics are indexed by the SOURCE row s.  row_map (int32 [map_period], one clip's permutation) sends
+ * source row s to m(s) = (s / map_period) * map_period + row_map[s % map_period]: the fused
+ * roll(-shift) + window_partition of :456-466 (its inverse is window_reverse + roll back, :471-479), built on
+ * the host from the closed forms.  Unpadded geometries only; clv_lnr_supported(C) tells whether the width
+ * has a specialisation (otherwise use clv_layernorm_*). */
+typedef struct {
+  const void* x; int x_is_bf16;
+  const float* gamma; const float* beta; float eps;
+  float* mean; float* rstd;          /* [rows] fp32 by source row; written by fwd (may be NULL), read by bwd */
+  long long rows; int C;
+  const int* row_map; int map_period;
+} clv_lnr_desc_t;
+
+typedef struct {
+  const void* dy; int dy_is_bf16;
+  int dy_mapped;                     /* dy of source row s lives at row m(s) (norm1: gradient in window order) */
+  const float* dres;                 /* fp32 [rows, C] residual-stream gradient added to dx, or NULL (may alias dx) */
+  float* dx;                         /* fp32 [rows, C] or NULL */
+  void* dx_bf16; int dx_bf16_mapped; /* optional bf16 copy of dx, at row m(s) when mapped (norm2: proj operand) */
+  float* dgamma; float* dbeta;       /* [C] fp32, ACCUMULATED (caller zero-fills); both or neither */
+} clv_lnr_bwd_t;
+
+int clv_lnr_supported(int C);
+int clv_lnr_fwd(const clv_lnr_desc_t* desc, void* y, int y_is_bf16, int y_mapped, void* stream);
+int clv_lnr_bwd(const clv_lnr_desc_t* desc, const clv_lnr_bwd_t* bwd, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
- * Attention core on packed qkv rows.  qkv: bf16 [batch*seq, 3*heads*hd] laid out [3][heads][hd]
+ * Attention core on packed qkv rows. qkv: bf16 [batch*seq, 3*heads*hd] laid out [3][heads][hd]
  * per row (the reshape of swin_transformer_3d.py:376 and of a fused BERT q|k|v dense), q already
  * scaled.  out: bf16 [batch*seq, heads*hd]; lse: fp32 [batch, heads, seq] (saved for backward).
  *   bias_table (+ rel_code)  : relative-position bias table[(code_i - code_j + code_off), head]

@@ -31,7 +31,13 @@ def test_product_tables_bit_exact(golden_dir):
         shape = tuple(g[f"mask_shape_{i}"])
         ref = np.unpackbits(g[f"mask_bits_{i}"])[: int(np.prod(shape))].reshape(shape).astype(bool)
         assert np.array_equal(mask != 0, ref)
-        assert np.array_equal(tables.window_gather_index(2, D, H, W, win, sh), g[f"gather_{i}"].astype(np.int64))
+        gather = g[f"gather_{i}"].astype(np.int64)
+        assert np.array_equal(tables.window_gather_index(2, D, H, W, win, sh), gather)
+        if D % win[0] == 0 and H % win[1] == 0 and W % win[2] == 0:
+            # the row map of the LN kernels is the inverse of the reference's roll + window_partition permutation
+            rmap = tables.window_row_map(D, H, W, win, sh)
+            clip0 = gather.reshape(-1)[: D * H * W]
+            assert np.array_equal(rmap[clip0], np.arange(D * H * W))
 
 
 def test_library_exports_every_declared_symbol():

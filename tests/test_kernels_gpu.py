@@ -137,6 +137,83 @@ def test_layernorm_plain(ops, C):
     assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("C", [96, 128, 192, 256, 384, 512, 768, 1024])
+@pytest.mark.parametrize("xdt", [F32, BF16])
+def test_lnr_plain(ops, C, xdt):
+    """Row-mapped LayerNorm without a map == nn.LayerNorm on dense rows (fp32 / bf16 activations)."""
+    assert ops.lnr_supported(C)
+    rows = 1003
+    x32, g, b = rnd(rows, C, seed=1, scale=3), 1 + 0.1 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    x = x32.to(xdt)
+    y = torch.empty(rows, C, dtype=F32, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.lnr_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd)
+    xr = x.float().cpu().requires_grad_(True); gr = g.cpu().requires_grad_(True); br = b.cpu().requires_grad_(True)
+    yr = _ln_ref(xr, gr, br, 1e-5)
+    assert rel(y, yr.detach()) < 1e-5
+    yb = torch.empty(rows, C, dtype=BF16, device="cuda")
+    ops.lnr_fwd(x, g, b, 1e-5, yb)
+    assert rel(yb, yr.detach()) < 1e-2
+    dy, dres = rnd(rows, C, seed=4), rnd(rows, C, seed=5)
+    (yr * dy.cpu()).sum().backward()
+    dx = torch.empty(rows, C, dtype=F32, device="cuda")
+    dxc = torch.empty(rows, C, dtype=BF16, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.lnr_bwd(x, g, b, 1e-5, mean, rstd, dy, dx=dx, dres=dres, dx_bf16=dxc, dgamma=dg, dbeta=db)
+    assert rel(dx, xr.grad + dres.cpu()) < 1e-4
+    assert rel(dxc, xr.grad + dres.cpu()) < 1e-2
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    # bf16 dy, in-place residual accumulation (dres aliases dx), no parameter gradients
+    dyb = dy.to(BF16)
+    acc = dres.clone()
+    ops.lnr_bwd(x, g, b, 1e-5, mean, rstd, dyb, dx=acc, dres=acc)
+    xr.grad = None
+    (_ln_ref(xr, g.cpu(), b.cpu(), 1e-5) * dyb.float().cpu()).sum().backward()
+    assert rel(acc, xr.grad + dres.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("dims,Bc,C,shifted", [((4, 14, 14), 3, 128, True), ((8, 14, 7), 2, 256, True),
+                                               ((4, 7, 7), 5, 512, False), ((2, 14, 14), 2, 96, True)])
+def test_lnr_window_map(ops, dims, Bc, C, shifted):
+    """norm1 / norm2 of a Swin block through the int32 row map: forward writes window order, backward reads dy in
+    window order (norm1) or emits the window-ordered bf16 copy of dx (norm2); bit-exact placement."""
+    D, H, W = dims
+    win, sh = O.get_window_size(dims, (8, 7, 7), (4, 3, 3) if shifted else (0, 0, 0))
+    wg = ops.Window(Bc, D, H, W, win, sh)
+    assert not wg.padded
+    rmap = wg.row_map("cuda")
+    gi = torch.from_numpy(O.window_gather_index(Bc, D, H, W, win, sh)).reshape(-1)      # window row -> source row
+    T = wg.tokens
+    x, g, b = rnd(T, C, seed=1, scale=2), 1 + 0.1 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    y = torch.empty(T, C, dtype=F32, device="cuda")
+    mean, rstd = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    ops.lnr_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd, row_map=rmap, y_mapped=True)
+    xr = x.cpu().requires_grad_(True)
+    h = _ln_ref(xr, g.cpu(), b.cpu(), 1e-5)
+    yr = h[gi]
+    assert rel(y, yr.detach()) < 1e-5
+    # the permutation itself is index work: bit-exact against an unmapped run
+    y0 = torch.empty(T, C, dtype=F32, device="cuda")
+    ops.lnr_fwd(x, g, b, 1e-5, y0)
+    assert torch.equal(y.cpu(), y0.cpu()[gi])
+    # norm1 backward: dy in window order, accumulated onto the residual gradient in place
+    dy, dres = rnd(T, C, seed=4), rnd(T, C, seed=5)
+    (yr * dy.cpu()).sum().backward()
+    acc = dres.clone()
+    c16 = torch.empty(T, C, dtype=BF16, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.lnr_bwd(x, g, b, 1e-5, mean, rstd, dy, dx=acc, dres=acc, dx_bf16=c16, row_map=rmap, dy_mapped=True, dgamma=dg, dbeta=db)
+    want = xr.grad + dres.cpu()
+    assert rel(acc, want) < 1e-4
+    assert torch.equal(c16.cpu(), acc.cpu().to(BF16))
+    # norm2 backward: dense dy, bf16 copy of dx emitted in window order
+    dx = torch.empty(T, C, dtype=F32, device="cuda")
+    cw = torch.empty(T, C, dtype=BF16, device="cuda")
+    ops.lnr_bwd(x, g, b, 1e-5, mean, rstd, dy, dx=dx, dres=dres, dx_bf16=cw, row_map=rmap, dx_bf16_mapped=True,
+                dgamma=torch.zeros(C, device="cuda"), dbeta=torch.zeros(C, device="cuda"))
+    assert torch.equal(cw.cpu(), dx.cpu().to(BF16)[gi])
+
+
 @pytest.mark.parametrize("dims,Bc", [((4, 14, 14), 2), ((16, 14, 7), 1), ((3, 10, 9), 2)])
 def test_layernorm_window_gather(ops, dims, Bc):
     D, H, W = dims
