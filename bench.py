@@ -225,6 +225,9 @@ def run_ours(args):
             a = fam.setdefault(f, [0.0, 0.0, 0.0, 0])
             a[0] += fl; a[1] += by; a[2] += ms; a[3] += 1
         fam_total = sum(v[2] for v in fam.values()) / args.steps
+
+        def pre(prefix, i):
+            return sum(v[i] for k, v in fam.items() if k.startswith(prefix))
         if os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1":
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             rows = sorted(((k, v[3] // args.steps, v[2] / args.steps, v[0] / max(v[2], 1e-9) / 1e9, v[1] / max(v[2], 1e-9) / 1e6)
@@ -245,10 +248,10 @@ def run_ours(args):
                     "unit": "TFLOP/s", "frac": gemm_tflops / sus, "traffic": traffic, "peak_source": f"{src} bf16_tflops_sustained",
                     "launches_timed": g[3], "avg_launch_ms": g[2] / max(1, g[3]),
                     "share_of_step": g[2] / (ms_step * args.steps),
-                    "families_ms_per_step": {k: round(v[2] / args.steps, 3) for k, v in fam.items() if not k.startswith("gemm ")},
+                    "families_ms_per_step": {k: round(pre(k, 2) / args.steps, 3) for k in sorted({n.split(" ")[0] for n in fam})},
                     "untracked_ms_per_step": round(ms_step - fam_total, 3),
-                    "window_attn_core_tflops": (fam.get("attn_fwd_hd32", [0, 0, 1e-9])[0] + fam.get("attn_bwd_hd32", [0, 0, 1e-9])[0]) /
-                                               ((fam.get("attn_fwd_hd32", [0, 0, 1e-9])[2] + fam.get("attn_bwd_hd32", [0, 0, 1e-9])[2]) * 1e-3) / 1e12,
+                    "window_attn_core_tflops": (pre("attn_fwd_hd32", 0) + pre("attn_bwd_hd32", 0)) /
+                                               max(1e-9, (pre("attn_fwd_hd32", 2) + pre("attn_bwd_hd32", 2)) * 1e-3) / 1e12,
                     "step_model_tflops": FLOP_PER_CLIP_FWD_BWD * clips / (ms_step * 1e-3) / 1e12}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -75,6 +75,14 @@ class AttnDesc(C.Structure):
     ]
 
 
+class AttnW7Desc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("heads", C.c_int), ("wd", C.c_int),
+        ("bias_table", c_vp), ("table_len", C.c_int), ("cfg_wd", C.c_int),
+        ("q_ext", c_vp), ("k_ext", c_vp), ("nwin", C.c_int),
+    ]
+
+
 class RowsAffine(C.Structure):
     _fields_ = [
         ("x", c_vp), ("x_is_bf16", C.c_int), ("ld_x", c_ll),
@@ -103,6 +111,9 @@ SIGNATURES = {
     "clv_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_attention_bwd_tc_workspace_bytes": (c_ll, [C.POINTER(AttnDesc), C.c_int]),
     "clv_attention_bwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
+    "clv_attention_w7_fwd": (C.c_int, [C.POINTER(AttnW7Desc), c_vp, c_vp, c_vp, c_vp]),
+    "clv_attention_w7_bwd_workspace_bytes": (c_ll, [C.POINTER(AttnW7Desc), C.c_int]),
+    "clv_attention_w7_bwd": (C.c_int, [C.POINTER(AttnW7Desc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, c_vp]),
     "clv_gelu": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, c_vp]),
     "clv_patchify": (C.c_int, [c_vp, c_vp] + [C.c_int] * 8 + [c_vp]),

@@ -1,0 +1,878 @@
+// Window attention core for the Video Swin windows actually used by Clover: head_dim 32, spatial window 7x7,
+// tokens in (d, h, w) order, N = 49 * wd (wd = 2, 4, 6, 8 frames-of-tokens).  tcgen05 / TMEM / TMA, sm_100a.
+//
+// The first tcgen05 version (attention_tc.cu, kept for other window shapes) spends 15 (forward) / 26 (backward)
+// issued instructions per score element on index arithmetic, mask compares, broadcast loads and selects while the
+// tensor pipe idles at < 1 %.  The softmax exponent (MUFU, 16/clk/SM) allows 8 issue slots per element per warp,
+// so this version moves everything that is not the exponent off the CUDA cores:
+//   * relative-position bias (swin_transformer_3d.py:345-359,382-385): idx(i,j) = code_i - code_j + off with
+//     code = d*169 + h*13 + w.  The column token of every TMEM element is a compile-time constant here, so
+//     the gather is ONE shared-memory load with an immediate offset from a per-thread base (table staged per head,
+//     pre-multiplied by log2 e) and the add is folded into the log2-domain FMA;
+//   * shift mask (compute_mask :548-562, added at :388-390): 0 / -100 by region equality.  Regions factor per axis
+//     (3 x 3 x 3), so "+100 per matching axis, -300" is a rank-11 term; it rides in a 16-wide K-extension of the
+//     Q K^T product (bf16 one-hots scaled by 10; -256 and -44 against two ones columns) -- an entry that differs in
+//     1..3 axes gets -100..-300, all of which vanish from the softmax exactly like the reference's -100;
+//   * backward: -lse_i and -D_i (hi/lo bf16 pairs) ride in the same K-extension of K Q^T and V dO^T, so a thread
+//     computes p = ex2(fma(s, log2e, bias)) and ds = p * dp and nothing else; rows outside the window are never
+//     touched (their dS^T rows in shared memory stay zero from the start).
+// Layouts, barriers and roles follow attention_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, the rest one thread
+// per TMEM lane (query row forward / key row backward).
+#include <algorithm>
+
+#include "common.cuh"
+#include "clover_b200.h"
+
+namespace clv {
+
+constexpr int W7_HD = 32;
+constexpr int W7_ROWB = 64;            // bytes per Q/K/V row of one head
+constexpr int W7_XROWB = 32;           // bytes per K-extension row (16 bf16)
+constexpr int W7_TILE = 98;            // rows per tile = two 49-token slabs
+constexpr int W7_SH = 169, W7_SW = 13; // code strides of the configured (., 7, 7) window: (2*7-1)^2 and 2*7-1
+constexpr float W7_LOG2E = 1.4426950408889634f;
+constexpr float W7_LN2 = 0.6931471805599453f;
+
+// code of body column c (two slabs of 49 tokens) relative to the body's first slab
+__host__ __device__ constexpr int w7_code(int c) { return (c / 49) * W7_SH + ((c % 49) / 7) * W7_SW + (c % 7); }
+
+CLV_DEVICE float w7_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+CLV_DEVICE float w7_max3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
+// ---- TMEM access shapes not in common.cuh -------------------------------------------------------------------
+CLV_DEVICE void tmem_ld_32x2(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+CLV_DEVICE void tmem_ld_32x4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+CLV_DEVICE void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+CLV_DEVICE void tmem_st_32x2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+CLV_DEVICE void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+CLV_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// =================================================================================================================
+// Forward.  Unit = (window b, head h, query tile t of 98 rows).
+// =================================================================================================================
+struct W7FwdArgs {
+  int batch, heads, seq, n_qt;
+  int nmma;                     // S columns issued to the tensor core: seq rounded up to 16
+  int n0;                       // first N chunk of the S product (<= 256), the rest is nmma - n0
+  int kb_bytes, kx_bytes;       // bytes reserved per K (or V) buffer / per key-side extension buffer (multiples of 1024)
+  int tmem_cols, col_o;
+  long long units;
+  __nv_bfloat16* out; float* lse;
+  const float* bias_table; int table_len; int code_off;
+  int has_ext, nwin;
+};
+
+constexpr int W7_FWD_THREADS = 192;
+
+// pass 1 on CNT (<= 32) consecutive body columns starting at static column C0: x = s*log2e + bias*log2e; running max
+template <int C0, int CNT, int NREG>
+CLV_DEVICE void w7_fwd_p1(uint32_t (&v)[NREG], const float* tb, float& m) {
+#pragma unroll
+  for (int x = 0; x < CNT; ++x) v[x] = __float_as_uint(fmaf(__uint_as_float(v[x]), W7_LOG2E, tb[-w7_code(C0 + x)]));
+#pragma unroll
+  for (int x = 0; x + 1 < CNT; x += 2) m = w7_max3(m, __uint_as_float(v[x]), __uint_as_float(v[x + 1]));
+  if (CNT & 1) m = fmaxf(m, __uint_as_float(v[CNT - 1]));
+}
+// pass 2: p = 2^(x - m), partial row sums, packed bf16 pairs
+template <int CNT, int NREG>
+CLV_DEVICE void w7_fwd_p2(const uint32_t (&v)[NREG], float m, float& l0, float& l1, uint32_t* pk) {
+#pragma unroll
+  for (int x = 0; x < CNT; x += 2) {
+    const float p0 = w7_ex2(__uint_as_float(v[x]) - m), p1 = w7_ex2(__uint_as_float(v[x + 1]) - m);
+    l0 += p0; l1 += p1;
+    pk[x >> 1] = pack_bf16(p0, p1);
+  }
+}
+
+__global__ void __launch_bounds__(W7_FWD_THREADS, 2)
+attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv0,
+                   const __grid_constant__ CUtensorMap tm_kv1, const __grid_constant__ CUtensorMap tm_qx,
+                   const __grid_constant__ CUtensorMap tm_kx0, const __grid_constant__ CUtensorMap tm_kx1, W7FwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = 8192 + 2 * a.kb_bytes + (a.has_ext ? 4096 + a.kx_bytes : 0);
+  float* sTable = reinterpret_cast<float*>(smem + 2 * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTable + ((a.table_len + 3) & ~3));
+  uint64_t* full_bar = bars;          // [2]
+  uint64_t* empty_bar = bars + 2;     // [2]
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_ready = bars + 5;
+  uint64_t* o_full = bars + 6;
+  uint64_t* s_free = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.heads * W7_HD;
+  const int n1 = a.nmma - a.n0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv0);
+    if (n1 > 0) tma_prefetch_desc(&tm_kv1);
+    if (a.has_ext) { tma_prefetch_desc(&tm_qx); tma_prefetch_desc(&tm_kx0); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(s_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int t = (int)(u % a.n_qt);
+        const long long bh = u / a.n_qt;
+        const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+        const int stage = it & 1;
+        mbar_wait(&empty_bar[stage], ((it >> 1) & 1) ^ 1);
+        uint8_t* sQ = smem + stage * stage_bytes;
+        uint8_t* sK = sQ + 8192;
+        uint8_t* sV = sK + a.kb_bytes;
+        uint8_t* sQx = sV + a.kb_bytes;
+        uint8_t* sKx = sQx + 4096;
+        mbar_expect_tx(&full_bar[stage], 8192 + 2 * a.nmma * W7_ROWB + (a.has_ext ? 4096 + a.nmma * W7_XROWB : 0));
+        const int row0 = b * a.seq;
+        tma_load_2d(sQ, &tm_q, &full_bar[stage], h * W7_HD, row0 + t * W7_TILE);
+        tma_load_2d(sK, &tm_kv0, &full_bar[stage], C + h * W7_HD, row0);
+        tma_load_2d(sV, &tm_kv0, &full_bar[stage], 2 * C + h * W7_HD, row0);
+        if (n1 > 0) {
+          tma_load_2d(sK + a.n0 * W7_ROWB, &tm_kv1, &full_bar[stage], C + h * W7_HD, row0 + a.n0);
+          tma_load_2d(sV + a.n0 * W7_ROWB, &tm_kv1, &full_bar[stage], 2 * C + h * W7_HD, row0 + a.n0);
+        }
+        if (a.has_ext) {
+          const int xrow0 = (b % a.nwin) * a.seq;
+          tma_load_2d(sQx, &tm_qx, &full_bar[stage], 0, xrow0 + t * W7_TILE);
+          tma_load_2d(sKx, &tm_kx0, &full_bar[stage], 0, xrow0);
+          if (n1 > 0) tma_load_2d(sKx + a.n0 * W7_XROWB, &tm_kx1, &full_bar[stage], 0, xrow0 + a.n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_pv = make_idesc_bf16(128, W7_HD, 0, 1);
+      const uint32_t idesc_s0 = make_idesc_bf16(128, a.n0, 0, 0);
+      const uint32_t idesc_s1 = make_idesc_bf16(128, n1 > 0 ? n1 : 16, 0, 0);
+      uint32_t it = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int stage = it & 1;
+        mbar_wait(&full_bar[stage], (it >> 1) & 1);
+        mbar_wait(s_free, (it & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
+        const uint32_t k_addr = q_addr + 8192;
+        const uint32_t v_addr = k_addr + a.kb_bytes;
+        const uint32_t qx_addr = v_addr + a.kb_bytes;
+        const uint32_t kx_addr = qx_addr + 4096;
+#pragma unroll
+        for (int k = 0; k < W7_HD / 16; ++k)
+          umma_bf16_ss(tmem_base, make_smem_desc(q_addr + k * 32, 16, 512, 4), make_smem_desc(k_addr + k * 32, 16, 512, 4), idesc_s0, k > 0);
+        if (a.has_ext)
+          umma_bf16_ss(tmem_base, make_smem_desc(qx_addr, 16, 256, 6), make_smem_desc(kx_addr, 16, 256, 6), idesc_s0, 1);
+        if (n1 > 0) {
+#pragma unroll
+          for (int k = 0; k < W7_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + a.n0, make_smem_desc(q_addr + k * 32, 16, 512, 4),
+                         make_smem_desc(k_addr + a.n0 * W7_ROWB + k * 32, 16, 512, 4), idesc_s1, k > 0);
+          if (a.has_ext)
+            umma_bf16_ss(tmem_base + a.n0, make_smem_desc(qx_addr, 16, 256, 6),
+                         make_smem_desc(kx_addr + a.n0 * W7_XROWB, 16, 256, 6), idesc_s1, 1);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        const uint32_t tmem_o = tmem_base + a.col_o;
+        for (int kk = 0; kk < a.nmma / 16; ++kk)
+          umma_bf16_ts(tmem_o, tmem_base + kk * 8, make_smem_desc(v_addr + kk * 1024, 16, 512, 4), idesc_pv, kk > 0);
+        umma_commit(o_full);
+        umma_commit(&empty_bar[stage]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool valid = r < W7_TILE;
+    const bool warp_active = quarter * 32 < W7_TILE;
+    const int n_body = a.seq / W7_TILE;
+    int cur_h = -1;
+    uint32_t it = 0;
+    for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      const int t = (int)(u % a.n_qt);
+      const long long bh = u / a.n_qt;
+      const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+      const int i = t * W7_TILE + (valid ? r : 0);
+      if (h != cur_h) {                       // stage this head's bias column, pre-multiplied by log2 e
+        named_bar_sync(1, 128);
+        for (int x = tid; x < a.table_len; x += 128) sTable[x] = a.bias_table[(long long)x * a.heads + h] * W7_LOG2E;
+        cur_h = h;
+        named_bar_sync(1, 128);
+      }
+      // sTable[(code_i + off) - code_j]: per-thread base, static column offsets
+      const float* tb0 = sTable + ((i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7) + a.code_off);
+
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float m = -1.0e30f, l = 0.f;
+      if (warp_active) {
+        // ---- pass 1: x = (s + bias) * log2 e written back; row max
+        const float* tb = tb0;
+#pragma unroll 1
+        for (int body = 0; body < n_body; ++body, tb -= 2 * W7_SH) {
+          const uint32_t tc = taddr + body * W7_TILE;
+          uint32_t va[32], vb[32], vd[2];
+          tmem_ld_32x32(tc, va); tmem_ld_wait();
+          tmem_ld_32x32(tc + 32, vb);
+          w7_fwd_p1<0, 32>(va, tb, m); tmem_st_32x32(tc, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(tc + 64, va);
+          w7_fwd_p1<32, 32>(vb, tb, m); tmem_st_32x32(tc + 32, vb);
+          tmem_ld_wait();
+          tmem_ld_32x2(tc + 96, vd);
+          w7_fwd_p1<64, 32>(va, tb, m); tmem_st_32x32(tc + 64, va);
+          tmem_ld_wait();
+          w7_fwd_p1<96, 2>(vd, tb, m); tmem_st_32x2(tc + 96, vd[0], vd[1]);
+        }
+        tmem_st_wait();
+        // ---- pass 2: p = 2^(x - m); packed bf16 P written in place (columns [0, seq/2))
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+        for (int body = 0; body < n_body; ++body) {
+          const uint32_t tc = taddr + body * W7_TILE, tp = taddr + body * (W7_TILE / 2);
+          uint32_t va[32], vb[32], vd[2], pk[16];
+          tmem_ld_32x32(tc, va); tmem_ld_wait();
+          tmem_ld_32x32(tc + 32, vb);
+          w7_fwd_p2<32>(va, m, l0, l1, pk); tmem_st_32x16(tp, pk);
+          tmem_ld_wait();
+          tmem_ld_32x32(tc + 64, va);
+          w7_fwd_p2<32>(vb, m, l0, l1, pk); tmem_st_32x16(tp + 16, pk);
+          tmem_ld_wait();
+          tmem_ld_32x2(tc + 96, vd);
+          w7_fwd_p2<32>(va, m, l0, l1, pk); tmem_st_32x16(tp + 32, pk);
+          tmem_ld_wait();
+          w7_fwd_p2<2>(vd, m, l0, l1, pk); tmem_st_32x1(tp + 48, pk[0]);
+        }
+        l = l0 + l1;
+        // keys [seq, nmma) of the P V product: zero probabilities
+        const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        tmem_st_32x8(taddr + a.seq / 2, z);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+
+      // ---- epilogue: O / l -> bf16 -> global; lse (natural log)
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      if (warp_active) {
+        uint32_t o[32];
+        tmem_ld_32x32(taddr + a.col_o, o);
+        tmem_ld_wait();
+        if (valid) {
+          const float inv = 1.0f / l;
+          uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)b * a.seq + i) * C + h * W7_HD);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8]) * inv, __uint_as_float(o[q * 8 + 1]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv));
+          a.lse[((long long)b * a.heads + h) * a.seq + i] = (m + log2f(l)) * W7_LN2;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// =================================================================================================================
+// Backward (seq = 98 or 196).  Unit = (window b, head h); key tiles t of 98 rows.
+//   UMMA 1 : S^T = [K_t | kx] [Q | e]^T,  dP^T = [V_t | vx] [dO | e]^T      (M = 128 keys, N = NQ queries, K = 48)
+//            e_i  = (-lse_hi, -lse_lo, -D_hi, -D_lo, 10*onehot(region_i) x9, 1, 1, 0)      (prep kernel, per b,h,i)
+//            kx_j = (1, 1, 0, 0, 10*onehot(region_j) x9, -256, -44, 0),  vx = (0, 0, 1, 1, 0, ...)
+//            so S^T arrives as s + mask - lse and dP^T as dp - D.
+//   warps  : key row per thread; p = 2^(s' log2e + bias log2e), ds = p * dp'; P^T / dS^T packed in place (two column
+//            segments, one per warp group), dS^T also to shared memory (A of the dQ product) and to global (bf16)
+//            for the bias-table gradient.
+//   UMMA 2 : dV_t = P^T dO, dK_t = dS^T Q (A from TMEM), dQ += dS K_t (A from smem, accumulated over key tiles).
+// =================================================================================================================
+struct W7BwdArgs {
+  int batch, heads, seq, n_kt;
+  int nq;                        // MMA N / K extent over queries: seq rounded up to 16 (208 or 112)
+  int qb_bytes, eb_bytes;        // bytes per Q (or dO) buffer / per e buffer
+  int n_mq;                      // 128-row query tiles of the dQ accumulator
+  int col_dp, col_dv, col_dk, col_dq, tmem_cols;
+  long long units;
+  __nv_bfloat16* dqkv; float q_scale;
+  __nv_bfloat16* ds_out; int ds_ld;   // [batch, heads, seq, ds_ld] bf16 or nullptr
+  const float* bias_table; int table_len; int code_off;
+  int has_kx, nwin;
+};
+
+constexpr int W7_BWD_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2-9: two column groups x four lane quarters
+constexpr int W7_SPLIT = 96;           // queries [0, 96) -> warp group 0, [96, seq) -> warp group 1
+
+// D_i = <dO_i, O_i>;  e rows for the K-extension (see above).  One thread per (row, head).
+__global__ void attn_w7_prep_kernel(const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
+                                    const __nv_bfloat16* q_ext, int nwin, __nv_bfloat16* e, long long rows, int heads, int seq) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * heads) return;
+  const long long row = idx / heads; const int h = (int)(idx % heads);
+  const uint4* po = reinterpret_cast<const uint4*>(out + row * heads * W7_HD + h * W7_HD);
+  const uint4* pd = reinterpret_cast<const uint4*>(dout + row * heads * W7_HD + h * W7_HD);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < W7_HD / 8; ++c) {
+    const uint4 u = po[c], v = pd[c];
+    float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+    float2 b0 = unpack_bf16(v.x), b1 = unpack_bf16(v.y), b2 = unpack_bf16(v.z), b3 = unpack_bf16(v.w);
+    s += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+  }
+  const long long b = row / seq; const int i = (int)(row % seq);
+  const long long er = (b * heads + h) * seq + i;
+  const float nl = -lse[er], nd = -s;
+  const __nv_bfloat16 lh = __float2bfloat16_rn(nl), dh = __float2bfloat16_rn(nd);
+  const __nv_bfloat16 ll = __float2bfloat16_rn(nl - __bfloat162float(lh)), dl = __float2bfloat16_rn(nd - __bfloat162float(dh));
+  uint4 lo, hi;
+  if (q_ext) {
+    const uint4* src = reinterpret_cast<const uint4*>(q_ext + ((long long)(b % nwin) * seq + i) * 16);
+    lo = src[0]; hi = src[1];
+  } else {
+    lo = make_uint4(0, 0, 0, 0); hi = make_uint4(0, 0, 0, 0);
+  }
+  __nv_bfloat162 p0(lh, ll), p1(dh, dl);
+  lo.x = *reinterpret_cast<uint32_t*>(&p0);
+  lo.y = *reinterpret_cast<uint32_t*>(&p1);
+  uint4* dst = reinterpret_cast<uint4*>(e + er * 16);
+  dst[0] = lo; dst[1] = hi;
+}
+
+// One 32-column chunk of the backward element loop.  C0 = static query column of v[0] (also its dS^T smem position).
+template <int C0, int CNT, int NREG>
+CLV_DEVICE void w7_bwd_chunk(const uint32_t (&v)[NREG], const uint32_t (&w)[NREG], const float* tbj, uint32_t* pk, uint32_t* dk) {
+#pragma unroll
+  for (int x = 0; x < CNT; x += 2) {
+    const float p0 = w7_ex2(fmaf(__uint_as_float(v[x]), W7_LOG2E, tbj[w7_code((C0 + x) % 98) + ((C0 + x) / 98) * 2 * W7_SH]));
+    const float p1 = w7_ex2(fmaf(__uint_as_float(v[x + 1]), W7_LOG2E, tbj[w7_code((C0 + x + 1) % 98) + ((C0 + x + 1) / 98) * 2 * W7_SH]));
+    pk[x >> 1] = pack_bf16(p0, p1);
+    dk[x >> 1] = pack_bf16(p0 * __uint_as_float(w[x]), p1 * __uint_as_float(w[x + 1]));
+  }
+}
+
+template <int SEQ>
+__global__ void __launch_bounds__(W7_BWD_THREADS, 1)
+attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_constant__ CUtensorMap tm_kv_tile,
+                   const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_e,
+                   const __grid_constant__ CUtensorMap tm_kx, W7BwdArgs a) {
+  constexpr int NQ = (SEQ + 15) / 16 * 16;
+  constexpr int SPLIT = SEQ > W7_SPLIT ? W7_SPLIT : SEQ;     // SEQ == 98: group 0 takes [0, 96), group 1 the last two columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // layout: [Q0 dO0 e0 | Q1 dO1 e1] [K0 V0 kx0 | K1 V1 kx1] [vx] [dS^T tile] table barriers
+  const int unit_bytes = 2 * a.qb_bytes + a.eb_bytes;
+  constexpr int tile_bytes = 2 * 8192 + 4096;
+  uint8_t* sQdO = smem;
+  uint8_t* sKV = sQdO + 2 * unit_bytes;
+  uint8_t* sVx = sKV + 2 * tile_bytes;
+  uint8_t* sDS = sVx + 4096;
+  const int ds_bytes = a.n_mq * 2 * 16384;
+  float* sTable = reinterpret_cast<float*>(sDS + ds_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTable + ((a.table_len + 3) & ~3));
+  uint64_t* qdo_full = bars;        // [2]
+  uint64_t* qdo_empty = bars + 2;   // [2]
+  uint64_t* kv_full = bars + 4;     // [2]
+  uint64_t* kv_empty = bars + 6;    // [2]
+  uint64_t* st_full = bars + 8;
+  uint64_t* p_ready = bars + 9;
+  uint64_t* mma2_done = bars + 10;
+  uint64_t* acc_free = bars + 11;
+  uint64_t* dq_free = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.heads * W7_HD;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q_full); tma_prefetch_desc(&tm_kv_tile); tma_prefetch_desc(&tm_do_full); tma_prefetch_desc(&tm_e);
+    if (a.has_kx) tma_prefetch_desc(&tm_kx);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(st_full, 1); mbar_init(p_ready, 8); mbar_init(mma2_done, 1); mbar_init(acc_free, 8); mbar_init(dq_free, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (warp >= 2) {
+    const int tid = threadIdx.x - 64;
+    for (int x = tid; x < ds_bytes / 16; x += 256) reinterpret_cast<uint4*>(sDS)[x] = make_uint4(0, 0, 0, 0);
+    // constant key-side extensions: vx = (0,0,1,1,0...) for V dO^T; kx = (1,1,0...) when no shift-mask table is given.
+    // SWIZZLE_32B K-major rows: 16-byte chunk c of row r sits at r*32 + ((c ^ (r >> 2)) & 1) * 16.
+    const uint32_t one2 = 0x3F803F80u;
+    for (int x = tid; x < 128; x += 256) {
+      uint4* rowp = reinterpret_cast<uint4*>(sVx + x * 32);
+      const int sw = (x >> 2) & 1;
+      rowp[sw] = make_uint4(0, one2, 0, 0);
+      rowp[sw ^ 1] = make_uint4(0, 0, 0, 0);
+      if (!a.has_kx) {
+        for (int s = 0; s < 2; ++s) {
+          uint4* kp = reinterpret_cast<uint4*>(sKV + s * tile_bytes + 2 * 8192 + x * 32);
+          kp[sw] = make_uint4(one2, 0, 0, 0);
+          kp[sw ^ 1] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, tt = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+        const int us = it & 1;
+        mbar_wait(&qdo_empty[us], ((it >> 1) & 1) ^ 1);
+        uint8_t* sQ = sQdO + us * unit_bytes;
+        uint8_t* sDO = sQ + a.qb_bytes;
+        uint8_t* sE = sDO + a.qb_bytes;
+        mbar_expect_tx(&qdo_full[us], 2 * NQ * W7_ROWB + NQ * W7_XROWB);
+        const int row0 = b * SEQ;
+        tma_load_2d(sQ, &tm_q_full, &qdo_full[us], h * W7_HD, row0);
+        tma_load_2d(sDO, &tm_do_full, &qdo_full[us], h * W7_HD, row0);
+        tma_load_2d(sE, &tm_e, &qdo_full[us], 0, (int)(((long long)b * a.heads + h) * SEQ));
+        for (int t = 0; t < a.n_kt; ++t, ++tt) {
+          const int ts = tt & 1;
+          mbar_wait(&kv_empty[ts], ((tt >> 1) & 1) ^ 1);
+          uint8_t* sK = sKV + ts * tile_bytes;
+          mbar_expect_tx(&kv_full[ts], 2 * 8192 + (a.has_kx ? 4096 : 0));
+          tma_load_2d(sK, &tm_kv_tile, &kv_full[ts], C + h * W7_HD, row0 + t * W7_TILE);
+          tma_load_2d(sK + 8192, &tm_kv_tile, &kv_full[ts], 2 * C + h * W7_HD, row0 + t * W7_TILE);
+          if (a.has_kx) tma_load_2d(sK + 2 * 8192, &tm_kx, &kv_full[ts], 0, (b % a.nwin) * SEQ + t * W7_TILE);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_st = make_idesc_bf16(128, NQ, 0, 0);
+      const uint32_t idesc_ts = make_idesc_bf16(128, W7_HD, 0, 1);
+      const uint32_t idesc_dq = make_idesc_bf16(128, W7_HD, 1, 1);
+      uint32_t it = 0, tt = 0;
+      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+        const int us = it & 1;
+        mbar_wait(&qdo_full[us], (it >> 1) & 1);
+        mbar_wait(dq_free, (it & 1) ^ 1);
+        const uint32_t q_addr = smem_u32(sQdO + us * unit_bytes);
+        const uint32_t do_addr = q_addr + a.qb_bytes;
+        const uint32_t e_addr = do_addr + a.qb_bytes;
+        const uint64_t desc_e = make_smem_desc(e_addr, 16, 256, 6);
+        for (int t = 0; t < a.n_kt; ++t, ++tt) {
+          const int ts = tt & 1;
+          mbar_wait(&kv_full[ts], (tt >> 1) & 1);
+          mbar_wait(acc_free, (tt & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sKV + ts * tile_bytes);
+          const uint32_t v_addr = k_addr + 8192;
+          const uint32_t kx_addr = v_addr + 8192;
+#pragma unroll
+          for (int k = 0; k < W7_HD / 16; ++k)
+            umma_bf16_ss(tmem_base, make_smem_desc(k_addr + k * 32, 16, 512, 4), make_smem_desc(q_addr + k * 32, 16, 512, 4),
+                         idesc_st, k > 0);
+          umma_bf16_ss(tmem_base, make_smem_desc(kx_addr, 16, 256, 6), desc_e, idesc_st, 1);
+#pragma unroll
+          for (int k = 0; k < W7_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + a.col_dp, make_smem_desc(v_addr + k * 32, 16, 512, 4),
+                         make_smem_desc(do_addr + k * 32, 16, 512, 4), idesc_st, k > 0);
+          umma_bf16_ss(tmem_base + a.col_dp, make_smem_desc(smem_u32(sVx), 16, 256, 6), desc_e, idesc_st, 1);
+          umma_commit(st_full);
+          mbar_wait(p_ready, tt & 1);
+          tc_fence_after();
+          for (int kk = 0; kk < NQ / 16; ++kk) {   // dV_t = P^T dO ; dK_t = dS^T Q   (K = queries, 16 per step)
+            // packed operands: queries [0, SPLIT) at columns [0, SPLIT/2); queries [SPLIT, NQ) at SPLIT + (q - SPLIT)/2
+            const uint32_t pc = kk * 16 < SPLIT ? kk * 8 : SPLIT + ((kk * 16 - SPLIT) >> 1);
+            umma_bf16_ts(tmem_base + a.col_dv, tmem_base + pc, make_smem_desc(do_addr + kk * 1024, 16, 512, 4), idesc_ts, kk > 0);
+            umma_bf16_ts(tmem_base + a.col_dk, tmem_base + a.col_dp + pc, make_smem_desc(q_addr + kk * 1024, 16, 512, 4), idesc_ts,
+                         kk > 0);
+          }
+          const uint32_t ds_addr = smem_u32(sDS);
+          for (int mq = 0; mq < a.n_mq; ++mq)      // dQ[mq] += dS K_t   (K = 128 keys of this tile; rows >= 98 of dS^T are zero)
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_ss(tmem_base + a.col_dq + mq * W7_HD, make_smem_desc(ds_addr + mq * 2 * 16384 + ks * 2048, 16384, 1024, 2),
+                           make_smem_desc(k_addr + ks * 1024, 16, 512, 4), idesc_dq, (t > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(mma2_done);
+          umma_commit(&kv_empty[ts]);
+          if (t == a.n_kt - 1) umma_commit(&qdo_empty[us]);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool valid = r < W7_TILE;
+    const bool warp_active = quarter * 32 < W7_TILE;
+    uint8_t* ds_row = sDS + (r >> 3) * 1024 + (r & 7) * 128;
+    const int rsw = r & 7;
+    int cur_h = -1;
+    uint32_t it = 0, tt = 0;
+    for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+      if (h != cur_h) {
+        named_bar_sync(1, 256);
+        for (int x = tid; x < a.table_len; x += 256) sTable[x] = a.bias_table[(long long)x * a.heads + h] * W7_LOG2E;
+        cur_h = h;
+        named_bar_sync(1, 256);
+      }
+      for (int t = 0; t < a.n_kt; ++t, ++tt) {
+        const int j = t * W7_TILE + (valid ? r : 0);
+        // sTable[code_i + (off - code_j)]: per-thread base, static query offsets
+        const float* tbj = sTable + (a.code_off - ((j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7)));
+        __nv_bfloat16* ds_g = a.ds_out ? a.ds_out + (((long long)b * a.heads + h) * SEQ + j) * a.ds_ld : nullptr;
+        mbar_wait(st_full, tt & 1);
+        tc_fence_after();
+        if (warp_active) {
+          const uint32_t ts0 = taddr, td0 = taddr + a.col_dp;
+          if (grp == 0) {
+            // queries [0, 96): three chunks of 32, packed at [0, 48)
+            uint32_t v[32], w[32], v2[32], w2[32], pk[16], dk[16];
+            tmem_ld_32x32(ts0, v); tmem_ld_32x32(td0, w); tmem_ld_wait();
+#define W7_BWD_EMIT(C0, PV, PW)                                                                                  \
+            w7_bwd_chunk<C0, 32>(PV, PW, tbj, pk, dk);                                                           \
+            tmem_st_32x16(ts0 + (C0) / 2, pk); tmem_st_32x16(td0 + (C0) / 2, dk);                                 \
+            if (valid) {                                                                                         \
+              uint8_t* chunk = ds_row + ((C0) >> 6) * 16384;                                                     \
+              _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                      \
+                *reinterpret_cast<uint4*>(chunk + (((((C0) >> 5) & 1) * 4 + q) ^ rsw) * 16) =                    \
+                    make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]);                          \
+              if (ds_g) {                                                                                        \
+                uint4* g = reinterpret_cast<uint4*>(ds_g + (C0));                                                \
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) g[q] = make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]); \
+              }                                                                                                  \
+            }
+            tmem_ld_32x32(ts0 + 32, v2); tmem_ld_32x32(td0 + 32, w2);
+            W7_BWD_EMIT(0, v, w)
+            tmem_ld_wait();
+            tmem_ld_32x32(ts0 + 64, v); tmem_ld_32x32(td0 + 64, w);
+            W7_BWD_EMIT(32, v2, w2)
+            tmem_ld_wait();
+            W7_BWD_EMIT(64, v, w)
+          } else if (SEQ > W7_SPLIT + 2) {
+            // queries [96, 196): three chunks of 32 and a tail of 4, packed at [96, 146); zero the packed pads [146, 152)
+            uint32_t v[32], w[32], v2[32], w2[32], pk[16], dk[16];
+            tmem_ld_32x32(ts0 + 96, v); tmem_ld_32x32(td0 + 96, w); tmem_ld_wait();
+#define W7_BWD_EMIT1(C0, PV, PW)                                                                                 \
+            w7_bwd_chunk<C0, 32>(PV, PW, tbj, pk, dk);                                                           \
+            tmem_st_32x16(ts0 + 96 + ((C0) - 96) / 2, pk); tmem_st_32x16(td0 + 96 + ((C0) - 96) / 2, dk);         \
+            if (valid) {                                                                                         \
+              uint8_t* chunk = ds_row + ((C0) >> 6) * 16384;                                                     \
+              _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                      \
+                *reinterpret_cast<uint4*>(chunk + (((((C0) >> 5) & 1) * 4 + q) ^ rsw) * 16) =                    \
+                    make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]);                          \
+              if (ds_g) {                                                                                        \
+                uint4* g = reinterpret_cast<uint4*>(ds_g + (C0));                                                \
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) g[q] = make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]); \
+              }                                                                                                  \
+            }
+            tmem_ld_32x32(ts0 + 128, v2); tmem_ld_32x32(td0 + 128, w2);
+            W7_BWD_EMIT1(96, v, w)
+            tmem_ld_wait();
+            tmem_ld_32x32(ts0 + 160, v); tmem_ld_32x32(td0 + 160, w);
+            W7_BWD_EMIT1(128, v2, w2)
+            tmem_ld_wait();
+            uint32_t v4[4], w4[4];
+            tmem_ld_32x4(ts0 + 192, v4); tmem_ld_32x4(td0 + 192, w4);
+            W7_BWD_EMIT1(160, v, w)
+            tmem_ld_wait();
+            w7_bwd_chunk<192, 4>(v4, w4, tbj, pk, dk);
+            {
+              const uint32_t zp[8] = {pk[0], pk[1], 0, 0, 0, 0, 0, 0}, zd[8] = {dk[0], dk[1], 0, 0, 0, 0, 0, 0};
+              tmem_st_32x8(ts0 + 96 + 48, zp); tmem_st_32x8(td0 + 96 + 48, zd);     // packed columns [144, 152)
+            }
+            if (valid) {
+              *reinterpret_cast<uint4*>(ds_row + 3 * 16384 + ((0 ^ rsw) * 16)) = make_uint4(dk[0], dk[1], 0, 0);
+              if (ds_g) *reinterpret_cast<uint2*>(ds_g + 192) = make_uint2(dk[0], dk[1]);
+            }
+          } else {
+            // SEQ == 98: group 1 takes the last two queries; packed at [96/2 .. ) does not apply -> single segment
+            uint32_t v4[2], w4[2], pk[16], dk[16];
+            tmem_ld_32x2(ts0 + 96, v4); tmem_ld_32x2(td0 + 96, w4); tmem_ld_wait();
+            w7_bwd_chunk<96, 2>(v4, w4, tbj, pk, dk);
+            {
+              const uint32_t zp[8] = {pk[0], 0, 0, 0, 0, 0, 0, 0}, zd[8] = {dk[0], 0, 0, 0, 0, 0, 0, 0};
+              tmem_st_32x8(ts0 + 96, zp); tmem_st_32x8(td0 + 96, zd);               // packed columns [96, 104) <- queries [96, 112)
+            }
+            if (valid) {
+              *reinterpret_cast<uint4*>(ds_row + 1 * 16384 + (((4 + 0) ^ rsw) * 16)) = make_uint4(dk[0], 0, 0, 0);
+              if (ds_g) *reinterpret_cast<uint32_t*>(ds_g + 96) = dk[0];
+            }
+          }
+          tmem_st_wait();
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+
+        mbar_wait(mma2_done, tt & 1);
+        tc_fence_after();
+        if (warp_active) {
+          // dV rows by warp group 0, dK rows by warp group 1
+          uint32_t o[32];
+          tmem_ld_32x32(taddr + (grp ? a.col_dk : a.col_dv), o);
+          tmem_ld_wait();
+          if (valid) {
+            // dK picked up the log2e-free scores' gradient directly: dS^T already is d/ds
+            uint4* g = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * SEQ + j) * (3 * C) + (grp ? 1 : 2) * C + h * W7_HD);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              g[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8]), __uint_as_float(o[q * 8 + 1])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7])));
+          }
+        }
+        if (t == a.n_kt - 1) {
+          // dQ of the whole unit (all key tiles accumulated); query row i = mq*128 + r; tiles alternate between warp groups
+          for (int mq = grp; mq < a.n_mq; mq += 2) {
+            const int i = mq * 128 + r;
+            if (mq * 128 + quarter * 32 < SEQ) {
+              uint32_t oq[32];
+              tmem_ld_32x32(taddr + a.col_dq + mq * W7_HD, oq);
+              tmem_ld_wait();
+              if (i < SEQ) {
+                uint4* gq = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * SEQ + i) * (3 * C) + h * W7_HD);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  gq[q] = make_uint4(pack_bf16(__uint_as_float(oq[q * 8]) * a.q_scale, __uint_as_float(oq[q * 8 + 1]) * a.q_scale),
+                                     pack_bf16(__uint_as_float(oq[q * 8 + 2]) * a.q_scale, __uint_as_float(oq[q * 8 + 3]) * a.q_scale),
+                                     pack_bf16(__uint_as_float(oq[q * 8 + 4]) * a.q_scale, __uint_as_float(oq[q * 8 + 5]) * a.q_scale),
+                                     pack_bf16(__uint_as_float(oq[q * 8 + 6]) * a.q_scale, __uint_as_float(oq[q * 8 + 7]) * a.q_scale));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(acc_free);
+          if (t == a.n_kt - 1) mbar_arrive(dq_free);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// dTable[(code_i - code_j + off), h] += sum_b dS^T[b, h, j, i]   (bf16 dS^T, fp32 accumulation).
+// grid = (key rows j, heads, batch splits); one thread per 4 queries (8-byte loads), static 7x7 codes.
+__global__ void attn_w7_dbias_kernel(const __nv_bfloat16* ds, int batch, int heads, int seq, int ld, int code_off, float* dtable) {
+  const int j = blockIdx.x, h = blockIdx.y;
+  const int i0 = threadIdx.x * 4;
+  if (i0 >= seq) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)heads * seq * ld;
+  const __nv_bfloat16* p = ds + ((long long)h * seq + j) * ld + i0;
+  const int per = (batch + gridDim.z - 1) / gridDim.z;
+  const int b0 = blockIdx.z * per, b1 = min(batch, b0 + per);
+#pragma unroll 8
+  for (int b = b0; b < b1; ++b) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + b * stride));
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+    acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+  }
+  const int cj = (j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = i0 + e;
+    if (i < seq) {
+      const int ci = (i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7);
+      atomicAdd(dtable + (long long)(ci - cj + code_off) * heads + h, acc[e]);
+    }
+  }
+}
+
+static int w7_check(const clv_attn_w7_desc_t* d, const char* who, int max_wd) {
+  CLV_REQUIRE(d != nullptr, "%s: null descriptor", who);
+  CLV_REQUIRE(d->batch > 0 && d->heads > 0 && d->wd >= 2 && d->wd <= max_wd && d->wd % 2 == 0,
+              "%s: wd must be even in [2, %d] (got %d)", who, max_wd, d->wd);
+  CLV_REQUIRE(d->bias_table && d->cfg_wd >= d->wd && d->table_len == (2 * d->cfg_wd - 1) * W7_SH,
+              "%s: bias table must be the (2*cfg_wd-1)*169 table of a (cfg_wd,7,7) window (len %d, cfg_wd %d)", who,
+              d->table_len, d->cfg_wd);
+  CLV_REQUIRE((d->q_ext == nullptr) == (d->k_ext == nullptr) && (!d->q_ext || d->nwin > 0), "%s: q_ext/k_ext/nwin go together", who);
+  CLV_REQUIRE((long long)d->batch * d->wd * 49 < 2000000000LL, "%s: too many rows", who);
+  return 0;
+}
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv, void* out, float* lse, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = w7_check(d, "attention_w7_fwd", 8)) return rc;
+  CLV_REQUIRE(qkv && out && lse, "attention_w7_fwd: null pointer");
+  W7FwdArgs a{};
+  a.batch = d->batch; a.heads = d->heads; a.seq = 49 * d->wd; a.n_qt = d->wd / 2;
+  a.nmma = (a.seq + 15) / 16 * 16;
+  a.n0 = a.nmma <= 256 ? a.nmma : 208;
+  a.kb_bytes = (a.nmma * W7_ROWB + 1023) / 1024 * 1024;
+  a.kx_bytes = (a.nmma * W7_XROWB + 1023) / 1024 * 1024;
+  a.tmem_cols = a.nmma + W7_HD <= 256 ? 256 : 512;
+  a.col_o = a.nmma;
+  a.units = (long long)d->batch * d->heads * a.n_qt;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse;
+  a.bias_table = d->bias_table; a.table_len = d->table_len;
+  a.code_off = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;
+  a.has_ext = d->q_ext != nullptr; a.nwin = d->nwin > 0 ? d->nwin : 1;
+  const long long rows = (long long)d->batch * a.seq;
+  const long long ld = 3LL * d->heads * W7_HD;
+  const int n1 = a.nmma - a.n0;
+  CUtensorMap tq, tkv0, tkv1, tqx, tkx0, tkx1;
+  if (int rc = make_tmap_bf16_2d(&tq, qkv, ld, rows, ld, W7_HD, 128, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tkv0, qkv, ld, rows, ld, W7_HD, a.n0, 64)) return rc;
+  tkv1 = tkv0; tqx = tq; tkx0 = tq; tkx1 = tq;
+  if (n1 > 0) { if (int rc = make_tmap_bf16_2d(&tkv1, qkv, ld, rows, ld, W7_HD, n1, 64)) return rc; }
+  if (a.has_ext) {
+    const long long xrows = (long long)a.nwin * a.seq;
+    if (int rc = make_tmap_bf16_2d(&tqx, d->q_ext, 16, xrows, 16, 16, 128, 32)) return rc;
+    if (int rc = make_tmap_bf16_2d(&tkx0, d->k_ext, 16, xrows, 16, 16, a.n0, 32)) return rc;
+    tkx1 = tkx0;
+    if (n1 > 0) { if (int rc = make_tmap_bf16_2d(&tkx1, d->k_ext, 16, xrows, 16, 16, n1, 32)) return rc; }
+  }
+  const size_t stage = 8192 + 2 * (size_t)a.kb_bytes + (a.has_ext ? 4096 + (size_t)a.kx_bytes : 0);
+  const size_t smem = 1024 + 2 * stage + (size_t)((a.table_len + 3) & ~3) * 4 + 9 * 8 + 16;
+  CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_fwd: %zu bytes of shared memory needed", smem);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(attn_w7_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int per_sm = (a.tmem_cols == 256 && smem <= 113 * 1024) ? 2 : 1;
+  const int grid = (int)std::min<long long>(a.units, (long long)num_sms() * per_sm);
+  attn_w7_fwd_kernel<<<grid, W7_FWD_THREADS, smem, stream>>>(tq, tkv0, tkv1, tqx, tkx0, tkx1, a);
+  return after_launch("attn_w7_fwd_kernel");
+}
+
+extern "C" long long clv_attention_w7_bwd_workspace_bytes(const clv_attn_w7_desc_t* d, int with_dbias) {
+  if (!d) return 0;
+  const long long seq = 49LL * d->wd;
+  const long long nq = (seq + 15) / 16 * 16;
+  long long bytes = ((long long)d->batch * d->heads * seq * 32 + 255) / 256 * 256 + 1024;      // e rows (16 bf16)
+  if (with_dbias) bytes += (long long)d->batch * d->heads * seq * nq * 2 + 256;                 // bf16 dS^T
+  return bytes;
+}
+
+extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv, const void* out, const void* dout,
+                                    const float* lse, void* dqkv, float q_scale, float* dbias_table, void* workspace,
+                                    void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = w7_check(d, "attention_w7_bwd", 4)) return rc;
+  CLV_REQUIRE(qkv && out && dout && lse && dqkv && workspace, "attention_w7_bwd: null pointer");
+  CLV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "attention_w7_bwd: workspace must be 256-byte aligned");
+  W7BwdArgs a{};
+  a.batch = d->batch; a.heads = d->heads; a.seq = 49 * d->wd; a.n_kt = d->wd / 2;
+  a.nq = (a.seq + 15) / 16 * 16;
+  a.qb_bytes = (a.nq * W7_ROWB + 1023) / 1024 * 1024;
+  a.eb_bytes = (a.nq * W7_XROWB + 1023) / 1024 * 1024;
+  a.n_mq = (a.nq + 127) / 128;
+  a.col_dp = a.nq;
+  a.col_dv = a.nq - W7_HD - 16;          // dead S^T columns clear of both packed segments ([0,48) and [96,152))
+  a.col_dk = a.col_dp + a.col_dv;
+  a.col_dq = 2 * a.nq;
+  const int need_cols = 2 * a.nq + a.n_mq * W7_HD;
+  a.tmem_cols = need_cols <= 256 ? 256 : 512;
+  CLV_REQUIRE(need_cols <= 512, "attention_w7_bwd: %d TMEM columns needed", need_cols);
+  if (a.seq == 98) a.col_dv = 56;        // single 98-query segment packed at [0,48) + [96,104): columns [56, 88) are dead
+  a.col_dk = a.col_dp + a.col_dv;
+  a.units = (long long)d->batch * d->heads;
+  a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.q_scale = q_scale;
+  a.bias_table = d->bias_table; a.table_len = d->table_len;
+  a.code_off = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;
+  a.has_kx = d->k_ext != nullptr; a.nwin = d->nwin > 0 ? d->nwin : 1;
+  const long long rows = (long long)d->batch * a.seq;
+  __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(workspace);
+  const long long e_bytes = ((long long)d->batch * d->heads * a.seq * 32 + 255) / 256 * 256 + 1024;
+  a.ds_ld = a.nq;
+  a.ds_out = dbias_table ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + e_bytes) : nullptr;
+  {
+    const long long n = rows * d->heads;
+    attn_w7_prep_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+        reinterpret_cast<const __nv_bfloat16*>(d->q_ext), a.nwin, e, rows, d->heads, a.seq);
+    if (int rc = after_launch("attn_w7_prep_kernel")) return rc;
+  }
+  const long long ld = 3LL * d->heads * W7_HD, ldo = (long long)d->heads * W7_HD;
+  CUtensorMap tfull, ttile, tdo, te, tkx;
+  if (int rc = make_tmap_bf16_2d(&tfull, qkv, ld, rows, ld, W7_HD, a.nq, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&ttile, qkv, ld, rows, ld, W7_HD, 128, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tdo, dout, ldo, rows, ldo, W7_HD, a.nq, 64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&te, e, 16, rows * d->heads, 16, 16, a.nq, 32)) return rc;
+  tkx = te;
+  if (a.has_kx) { if (int rc = make_tmap_bf16_2d(&tkx, d->k_ext, 16, (long long)a.nwin * a.seq, 16, 16, 128, 32)) return rc; }
+  const size_t smem = 1024 + 2 * (2 * (size_t)a.qb_bytes + a.eb_bytes) + 2 * (2 * 8192 + 4096) + 4096 + (size_t)a.n_mq * 2 * 16384 +
+                      (size_t)((a.table_len + 3) & ~3) * 4 + 14 * 8 + 16;
+  CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_bwd: %zu bytes of shared memory needed", smem);
+  auto kern = a.seq == 196 ? attn_w7_bwd_kernel<196> : attn_w7_bwd_kernel<98>;
+  static size_t smem_set[2] = {0, 0};
+  if (smem > smem_set[a.seq == 196]) {
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[a.seq == 196] = smem;
+  }
+  const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
+  kern<<<grid, W7_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, te, tkx, a);
+  if (int rc = after_launch("attn_w7_bwd_kernel")) return rc;
+  if (dbias_table) {
+    const int zsplit = std::max(1, std::min(32, d->batch / 32));
+    dim3 g(a.seq, d->heads, zsplit);
+    attn_w7_dbias_kernel<<<g, (a.seq + 3) / 4, 0, stream>>>(a.ds_out, d->batch, d->heads, a.seq, a.ds_ld, a.code_off, dbias_table);
+    if (int rc = after_launch("attn_w7_dbias_kernel")) return rc;
+  }
+  return 0;
+}

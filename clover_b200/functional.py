@@ -326,7 +326,7 @@ class SwinBlockFn(torch.autograd.Function):
         ao = torch.empty(rows, C, dtype=BF16, device=dev)
         batch = wg.B * wg.nwin
         lse = torch.empty(batch, heads, wg.N, dtype=F32, device=dev)
-        ops.attention_fwd(qkv, batch, wg.N, heads, hd, ao, lse, bias_table=table, rel_code=code, code_off=code_off,
+        ops.attention_fwd(qkv, batch, wg.N, heads, hd, ao, lse, w7=wg.w7, bias_table=table, rel_code=code, code_off=code_off,
                           region=region)
         x_mid = torch.empty(T, C, dtype=F32, device=dev)
         ops.gemm(ao, wp, x_mid, bias=proj_b, residual=x, window=wg)
@@ -385,7 +385,7 @@ class SwinBlockFn(torch.autograd.Function):
         dWp = _wgrad(dmid_w, ao, C, C)
         dBp = _colsum(dmid_w, C)
         dqkv = torch.empty(rows, 3 * C, dtype=BF16, device=dev)
-        ops.attention_bwd(qkv, ao, dao, lse, wg.B * wg.nwin, wg.N, heads, hd, dqkv, scale, dbias_table=dtable,
+        ops.attention_bwd(qkv, ao, dao, lse, wg.B * wg.nwin, wg.N, heads, hd, dqkv, scale, dbias_table=dtable, w7=wg.w7,
                           bias_table=table, rel_code=code, code_off=code_off, region=region)
         dxw = dao                                             # reuse: [rows, C] bf16
         ops.gemm(dqkv, wq, dxw, b_t=True)

@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, GemmEpilogue, LnBwd, LnDesc, LnrBwd, LnrDesc, RowsAffine, WindowGeom
+from ._lib import AttnDesc, AttnW7Desc, GemmEpilogue, LnBwd, LnDesc, LnrBwd, LnrDesc, RowsAffine, WindowGeom
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -51,6 +51,8 @@ _PROF = None
 PROFILE_SHAPES = os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1"
 # head_dim-32 window attention runs on the tcgen05 kernel; the mma.sync kernel serves head_dim 64 (BERT / fusion)
 USE_TC_ATTENTION = os.environ.get("CLOVER_B200_TC_ATTENTION", "1") != "0"
+# (., 7, 7) windows with tokens in (d, h, w) order run on the specialised kernels of attention_w7.cu
+USE_W7_ATTENTION = os.environ.get("CLOVER_B200_W7_ATTENTION", "1") != "0"
 
 
 def profile_begin():
@@ -81,14 +83,17 @@ def _prof_close(e0, family, flops, nbytes):
         _PROF.append((family, flops, nbytes, e0, e1))
 
 
-def _profiled(family):
+def _profiled(family, tag=None):
     def deco(fn):
         def wrapped(*a, **k):
             if _PROF is None:
                 return fn(*a, **k)
             e0 = _prof_open()
             out = fn(*a, **k)
-            _prof_close(e0, family, 0.0, 0.0)
+            name = family
+            if PROFILE_SHAPES and tag is not None:
+                name = family + " " + tag(*a, **k)
+            _prof_close(e0, name, 0.0, 0.0)
             return out
         wrapped.__name__ = fn.__name__
         wrapped.__doc__ = fn.__doc__
@@ -112,6 +117,7 @@ class Window:
         self.tokens = B * D * H * W
         self.padded = (self.Dp, self.Hp, self.Wp) != (D, H, W)
         self.shifted = any(s > 0 for s in self.shift)
+        self.w7 = None                                # ops.W7Spec when the specialised (., 7, 7) attention kernels apply
 
     def ref(self):
         return C.pointer(self.c)
@@ -215,7 +221,12 @@ def _ln_desc(x, gamma, beta, eps, rows, Cn, mean, rstd, *, window=None, merge=No
     return d
 
 
-@_profiled("ln_fwd")
+def _ln_tag(x, gamma, *a, **k):
+    kinds = [n for n in ("window", "merge", "blend", "row_index", "add1", "group", "dres", "dx_copy", "dx_bf16", "row_map") if k.get(n) is not None]
+    return f"generic rows={k.get('rows') or x.shape[0]} C={gamma.numel()} x={str(x.dtype)[-4:]} {'+'.join(kinds)}"
+
+
+@_profiled("ln_fwd", _ln_tag)
 def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **kw):
     """y = LN(gather(x) + adds) (* blend).  x: [..., C] fp32/bf16 2-D; y: 2-D bf16/fp32."""
     _need_cuda(x, gamma, beta, y)
@@ -226,7 +237,7 @@ def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **
     return y
 
 
-@_profiled("ln_bwd")
+@_profiled("ln_bwd", _ln_tag)
 def layernorm_bwd(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=None, dx_copy=None, copy_window=None,
                   dgamma=None, dbeta=None, dtoken=None, dx_dense=False, **kw):
     _need_cuda(x, gamma, dy)
@@ -268,7 +279,12 @@ def _lnr_desc(x, gamma, beta, eps, mean, rstd, row_map):
     return d
 
 
-@_profiled("ln_fwd")
+def _lnr_tag(x, gamma, *a, **k):
+    kinds = [n for n in ("dres", "dx", "dx_bf16", "row_map") if k.get(n) is not None]
+    return f"rows={x.shape[0]} C={x.shape[1]} x={str(x.dtype)[-4:]} {'+'.join(kinds)}"
+
+
+@_profiled("ln_fwd", _lnr_tag)
 def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_mapped=False):
     """y[m(s)] = LN(x[s]) on dense rows (clv_lnr_fwd); m = identity unless y_mapped."""
     _need_cuda(x, gamma, beta, y)
@@ -279,7 +295,7 @@ def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_map
     return y
 
 
-@_profiled("ln_bwd")
+@_profiled("ln_bwd", _lnr_tag)
 def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, row_map=None, dy_mapped=False,
             dx_bf16_mapped=False, dgamma=None, dbeta=None):
     _need_cuda(x, gamma, dy)
@@ -310,22 +326,50 @@ def _attn_desc(batch, seq, heads, hd, bias_table=None, rel_code=None, code_off=0
     return d
 
 
-def attention_fwd(qkv, batch, seq, heads, hd, out, lse, **bias):
+class W7Spec:
+    """Static description of a (wd, 7, 7) window-attention call for the specialised kernels: temporal extent of the
+    clamped window, the configured temporal window (bias-table size) and the bf16 K-extension tables that encode the
+    shift mask (None for unshifted blocks)."""
+
+    def __init__(self, wd, cfg_wd, q_ext=None, k_ext=None):
+        self.wd, self.cfg_wd, self.q_ext, self.k_ext = int(wd), int(cfg_wd), q_ext, k_ext
+        self.nwin = q_ext.shape[0] if q_ext is not None else 0
+
+    def desc(self, batch, heads, bias_table):
+        d = AttnW7Desc()
+        d.batch, d.heads, d.wd = batch, heads, self.wd
+        d.bias_table, d.table_len, d.cfg_wd = _ptr(bias_table), bias_table.shape[0], self.cfg_wd
+        d.q_ext, d.k_ext, d.nwin = _ptr(self.q_ext), _ptr(self.k_ext), self.nwin
+        return d
+
+    def fwd_ok(self):
+        return USE_W7_ATTENTION and self.wd % 2 == 0 and 2 <= self.wd <= 8
+
+    def bwd_ok(self):
+        return USE_W7_ATTENTION and self.wd in (2, 4)
+
+
+def attention_fwd(qkv, batch, seq, heads, hd, out, lse, w7=None, **bias):
     _need_cuda(qkv, out, lse)
     if qkv.dtype != BF16 or not qkv.is_contiguous() or qkv.shape != (batch * seq, 3 * heads * hd):
         raise ValueError(f"attention_fwd: qkv must be contiguous bf16 [{batch * seq}, {3 * heads * hd}], got {tuple(qkv.shape)} {qkv.dtype}")
     d = _attn_desc(batch, seq, heads, hd, **bias)
     ev = _prof_open()
     lib = _lib.load()
-    if hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 416 and USE_TC_ATTENTION:
+    if w7 is not None and hd == 32 and w7.fwd_ok() and seq == 49 * w7.wd and bias.get("bias_table") is not None:
+        if bias["bias_table"].dtype != F32 or not bias["bias_table"].is_contiguous():
+            raise TypeError("attention_fwd: bias_table must be contiguous fp32")
+        dw = w7.desc(batch, heads, bias["bias_table"])
+        _lib.check(lib.clv_attention_w7_fwd(C.byref(dw), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_w7_fwd")
+    elif hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 416 and USE_TC_ATTENTION:
         _lib.check(lib.clv_attention_fwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd_tc")
     else:
         _lib.check(lib.clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
-    _prof_close(ev, "attn_fwd_hd%d" % hd, 4.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 4)
+    _prof_close(ev, ("attn_fwd_hd%d" % hd) + (f" b={batch} n={seq} h={heads}" if PROFILE_SHAPES else ""), 4.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 4)
     return out
 
 
-def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbias_table=None, **bias):
+def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbias_table=None, w7=None, **bias):
     _need_cuda(qkv, out, dout, lse, dqkv)
     for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
         if t.dtype != BF16 or not t.is_contiguous():
@@ -333,7 +377,13 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
     d = _attn_desc(batch, seq, heads, hd, **bias)
     lib = _lib.load()
     ev = _prof_open()
-    if hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 224 and USE_TC_ATTENTION:
+    if w7 is not None and hd == 32 and w7.bwd_ok() and seq == 49 * w7.wd and bias.get("bias_table") is not None:
+        dw = w7.desc(batch, heads, bias["bias_table"])
+        nbytes = lib.clv_attention_w7_bwd_workspace_bytes(C.byref(dw), int(dbias_table is not None))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
+        _lib.check(lib.clv_attention_w7_bwd(C.byref(dw), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                            float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_w7_bwd")
+    elif hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 224 and USE_TC_ATTENTION:
         nbytes = lib.clv_attention_bwd_tc_workspace_bytes(C.byref(d), int(dbias_table is not None))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
         _lib.check(lib.clv_attention_bwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
@@ -342,12 +392,12 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
         ws = torch.empty(batch * heads * seq, dtype=F32, device=qkv.device)
         _lib.check(lib.clv_attention_bwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
                                          float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd")
-    _prof_close(ev, "attn_bwd_hd%d" % hd, 8.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 8)
+    _prof_close(ev, ("attn_bwd_hd%d" % hd) + (f" b={batch} n={seq} h={heads}" if PROFILE_SHAPES else ""), 8.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 8)
     return dqkv
 
 
 # ------------------------------------------------------------------------------------------------
-@_profiled("cast")
+@_profiled("cast", lambda src, dst, *a, **k: f"n={src.numel()} {str(src.dtype)[-4:]}->{str(dst.dtype)[-4:]}")
 def cast(src, dst, scale=1.0):
     _need_cuda(src, dst)
     if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
@@ -389,7 +439,7 @@ def patchify(x, patch):
     return out, (D, Hp, Wp)
 
 
-@_profiled("colsum")
+@_profiled("colsum", lambda x, out, *a, **k: f"rows={k.get('rows') or x.shape[0]} C={x.shape[-1]} {str(x.dtype)[-4:]} mod={k.get('mod', 1)}")
 def grouped_colsum(x, out, div=1, mod=1, scale=1.0, accumulate=False, rows=None):
     _need_cuda(x, out)
     if out.dtype != F32 or not out.is_contiguous():

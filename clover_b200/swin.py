@@ -38,6 +38,27 @@ def _device_tables(dims, window, shift, window_cfg, device):
     return ent
 
 
+_W7_SPECS = {}
+
+
+def _w7_spec(dims, window, shift, window_cfg, device):
+    """ops.W7Spec for (wd, 7, 7) windows of a (Wd, 7, 7) configuration (specialised attention kernels), else None.
+    `dims` is the padded frame extent the shift-mask regions are computed on."""
+    if tuple(window[1:]) != (7, 7) or tuple(window_cfg[1:]) != (7, 7) or window[0] % 2 or not 2 <= window[0] <= 8:
+        return None
+    key = (dims, tuple(window), tuple(shift), tuple(window_cfg), str(device))
+    spec = _W7_SPECS.get(key)
+    if spec is None:
+        q_ext = k_ext = None
+        if any(s > 0 for s in shift):
+            q, k = tables.w7_ext_tables(tables.region_ids(*dims, tuple(window), tuple(shift)))
+            q_ext = torch.from_numpy(q).to(device=device, dtype=torch.bfloat16).contiguous()
+            k_ext = torch.from_numpy(k).to(device=device, dtype=torch.bfloat16).contiguous()
+        spec = ops.W7Spec(window[0], window_cfg[0], q_ext, k_ext)
+        _W7_SPECS[key] = spec
+    return spec
+
+
 class Mlp(nn.Module):
     """reference :250-268 (parameter container)."""
 
@@ -135,6 +156,7 @@ class SwinTransformerBlock3D(nn.Module):
         window, shift = get_window_size((D, H, W), self.window_size, self.shift_size)
         wg = ops.Window(B, D, H, W, window, shift)
         code, off, region = _device_tables((wg.Dp, wg.Hp, wg.Wp), window, shift, self.window_size, x.device)
+        wg.w7 = _w7_spec((wg.Dp, wg.Hp, wg.Wp), window, shift, self.window_size, x.device)
         a, m = self.attn, self.mlp
         return Fn.SwinBlockFn.apply(x, wg, self.num_heads, code, off, region,
                                     self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias,

@@ -93,3 +93,23 @@ def window_row_map(D, H, W, window, shift):
     inv = np.empty(D * H * W, dtype=np.int32)
     inv[src] = np.arange(D * H * W, dtype=np.int32)
     return inv
+
+
+def w7_ext_tables(rid):
+    """K-extension rows of the 7x7-window attention kernels (include/clover_b200.h, clv_attn_w7_desc_t) from the
+    shift-mask region ids ``rid`` (nWin, N) of :func:`region_ids` (id = 9*rd + 3*rh + rw).  Returns float32
+    (q_ext, k_ext), each (nWin, N, 16); every value is exactly representable in bf16.  <q_ext[i], k_ext[j]> is
+    100 * (#axes on which the regions of i and j agree) - 300: 0 where compute_mask (swin_transformer_3d.py:548-562)
+    gives 0, and -100, -200 or -300 where it gives -100."""
+    rid = np.asarray(rid)
+    nW, N = rid.shape
+    axes = np.stack([rid // 9, (rid // 3) % 3, rid % 3], -1)                      # (nW, N, 3)
+    onehot = (axes[..., None] == np.arange(3)).astype(np.float32).reshape(nW, N, 9) * 10.0
+    q = np.zeros((nW, N, 16), np.float32)
+    k = np.zeros((nW, N, 16), np.float32)
+    q[..., 4:13] = onehot
+    k[..., 4:13] = onehot
+    q[..., 13], q[..., 14] = 1.0, 1.0
+    k[..., 0], k[..., 1] = 1.0, 1.0
+    k[..., 13], k[..., 14] = -256.0, -44.0
+    return q, k

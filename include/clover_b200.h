@@ -229,6 +229,29 @@ long long clv_attention_bwd_tc_workspace_bytes(const clv_attn_desc_t* desc, int 
 int clv_attention_bwd_tc(const clv_attn_desc_t* desc, const void* qkv, const void* out, const void* dout, const float* lse,
                          void* dqkv, float q_scale, float* dbias_table, void* workspace, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Window attention specialised for the windows Clover actually runs (WindowAttention3D.forward,
+ * swin_transformer_3d.py:379-397): head_dim 32, spatial window 7x7, tokens in (d,h,w) order, seq = 49*wd.
+ * Same tensors as clv_attention_fwd_tc / clv_attention_bwd_tc (packed qkv, out, lse, dqkv, dbias_table).
+ * The relative-position index (:345-359) is evaluated from compile-time token codes; the shift mask
+ * (compute_mask :548-562) arrives as two bf16 tables [nwin, seq, 16] that ride in a K-extension of Q K^T:
+ *   q_ext row = (0,0,0,0, 10*onehot3(rd), 10*onehot3(rh), 10*onehot3(rw),    1,   1, 0)
+ *   k_ext row = (1,1,0,0, 10*onehot3(rd), 10*onehot3(rh), 10*onehot3(rw), -256, -44, 0)
+ * with (rd,rh,rw) the per-axis region of the token (region id = 9 rd + 3 rh + rw); tokens whose regions differ in
+ * k axes get -100 k, which leaves the softmax exactly like the reference's -100.  NULL tables = no shift mask.
+ * forward: wd even in [2, 8]; backward: wd in {2, 4}.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int batch, heads, wd;                  /* windows, heads, temporal window extent (seq = 49*wd) */
+  const float* bias_table; int table_len; int cfg_wd;   /* fp32 [(2*cfg_wd-1)*169, heads]; configured temporal window */
+  const void* q_ext; const void* k_ext; int nwin;       /* bf16 [nwin, seq, 16] each, or NULL; window type = batch % nwin */
+} clv_attn_w7_desc_t;
+
+int clv_attention_w7_fwd(const clv_attn_w7_desc_t* desc, const void* qkv, void* out, float* lse, void* stream);
+long long clv_attention_w7_bwd_workspace_bytes(const clv_attn_w7_desc_t* desc, int with_dbias);
+int clv_attention_w7_bwd(const clv_attn_w7_desc_t* desc, const void* qkv, const void* out, const void* dout, const float* lse,
+                         void* dqkv, float q_scale, float* dbias_table, void* workspace /* 256-byte aligned */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

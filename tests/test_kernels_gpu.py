@@ -362,6 +362,63 @@ def test_window_attention_core(ops, dims, shifted):
     assert rel(dtab, tb.grad) < 2e-2
 
 
+@pytest.mark.parametrize("dims,shifted,Bc", [((4, 14, 14), False, 2), ((4, 14, 14), True, 2), ((4, 14, 14), True, 40),
+                                            ((2, 14, 14), True, 3), ((8, 14, 7), True, 2), ((16, 7, 7), True, 2),
+                                            ((6, 7, 7), False, 5)])
+def test_window_attention_w7(ops, dims, shifted, Bc):
+    """Specialised (wd, 7, 7) window attention (attention_w7.cu): static bias gather, shift mask / lse / D folded
+    into the MMA K-extension.  Same oracle and tolerances as the generic kernels."""
+    heads, hd = 3, 32
+    win, sh = O.get_window_size(dims, (8, 7, 7), (4, 3, 3) if shifted else (0, 0, 0))
+    N = win[0] * win[1] * win[2]
+    nwin = (dims[0] // win[0]) * (dims[1] // win[1]) * (dims[2] // win[2])
+    batch = Bc * nwin
+    qkv, dout = _attn_inputs(batch, N, heads, hd, 30)
+    table = rnd(2535, heads, seed=32, scale=0.5)
+    from clover_b200 import swin
+    from clover_b200.tables import rel_code, region_ids, w7_ext_tables
+    code, off = rel_code(N, (8, 7, 7))
+    code = torch.from_numpy(code).cuda()
+    masked = any(s > 0 for s in sh)
+    rid = region_ids(*dims, win, sh) if masked else None
+    region = torch.from_numpy(rid).cuda() if masked else None
+    spec = swin._w7_spec(dims, win, sh, (8, 7, 7), "cuda")
+    assert spec is not None and spec.fwd_ok() and (spec.q_ext is not None) == masked
+    if masked:
+        # the K-extension reproduces compute_mask: 0 where the reference has 0, <= -100 where it has -100 (exact integers)
+        q, k = w7_ext_tables(rid)
+        ext = np.einsum("wik,wjk->wij", q, k)
+        ref_mask = O.compute_mask(*dims, win, sh)
+        assert np.array_equal(ext == 0, ref_mask == 0) and np.all(ext[ref_mask != 0] <= -100.0)
+        assert np.array_equal(spec.q_ext.float().cpu().numpy(), q) and np.array_equal(spec.k_ext.float().cpu().numpy(), k)
+    out = torch.empty(batch * N, heads * hd, dtype=BF16, device="cuda")
+    lse = torch.empty(batch, heads, N, dtype=F32, device="cuda")
+    kw = dict(bias_table=table, rel_code=code, code_off=off, region=region)
+    ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, w7=spec, **kw)
+    idx = torch.from_numpy(O.relative_position_index((8, 7, 7))[:N, :N].reshape(-1))
+    tb = table.cpu().requires_grad_(True)
+    bias = tb[idx].view(N, N, heads).permute(2, 0, 1)[None]
+    if masked:
+        m = torch.from_numpy(O.compute_mask(*dims, win, sh))            # (nwin, N, N)
+        bias = bias + m.repeat(Bc, 1, 1)[:, None]
+    x, o_ref, lse_ref = _attn_ref(qkv, dout, batch, N, heads, hd, bias)
+    assert rel(out, o_ref.detach()) < 1e-2
+    assert rel(lse, lse_ref.detach()) < 1e-4
+    # the generic tcgen05 kernel and the specialised one agree closely (same bf16 operands, same fp32 math)
+    out2 = torch.empty_like(out); lse2 = torch.empty_like(lse)
+    ops.attention_fwd(qkv, batch, N, heads, hd, out2, lse2, **kw)
+    assert rel(out, out2) < 4e-3 and rel(lse, lse2) < 1e-5
+    (o_ref * dout.float().cpu()).sum().backward()
+    dqkv = torch.empty_like(qkv)
+    dtab = torch.zeros(2535, heads, dtype=F32, device="cuda")
+    ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dqkv, 1.0, dbias_table=dtab, w7=spec, **kw)
+    assert rel(dqkv, x.grad) < 2e-2
+    assert rel(dtab, tb.grad) < 2e-2
+    dq2 = torch.empty_like(qkv)                                          # without the bias-table gradient
+    ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dq2, 1.0, w7=spec, **kw)
+    assert torch.equal(dq2, dqkv)
+
+
 @pytest.mark.parametrize("seq", [32, 228, 432])
 def test_bert_attention_core(ops, seq):
     heads, hd, batch = 2, 64, 3

@@ -1,0 +1,84 @@
+"""WindowAttention3D core microbenchmark (BASELINE.json config c2 and the c3 production shapes).
+
+    python tools/attn_microbench.py [--shapes s1,s3,c2] [--iters 10] [--which fwd,bwd] [--shifted 0|1]
+
+Times the attention core (QK^T + bias + mask + softmax + PV, and its backward incl. the bias-table gradient)
+through the C ABI with CUDA events, one launch per iteration on tensors larger than L2, and prints TFLOP/s on the
+algorithmic FLOPs of SURVEY.md 8(d) (4*T*N*C forward, 8*T*N*C backward).  Used under ncu for profiles/.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SHAPES = {                      # name: (clips, (D, H, W) tokens, heads)  -- Swin-B, head_dim 32
+    "s1": (64, (4, 56, 56), 4),       # c3 stage 1: 4096 windows x 196 tokens, C = 128
+    "s2": (64, (4, 28, 28), 8),
+    "s3": (64, (4, 14, 14), 16),      # c3 stage 3: 256 windows, C = 512 (18 of the 24 blocks)
+    "s4": (64, (4, 7, 7), 32),
+    "c2": (64, (8, 56, 56), 4),       # BASELINE c2: window 8x7x7 -> N = 392, stage-1 width
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shapes", default="s1,s3")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--which", default="fwd,bwd")
+    ap.add_argument("--shifted", type=int, default=1)
+    args = ap.parse_args()
+    from clover_b200 import ops, swin, tables
+    dev = torch.device("cuda")
+    res = []
+    for name in args.shapes.split(","):
+        clips, dims, heads = SHAPES[name]
+        hd = 32
+        win, sh = tables.get_window_size(dims, (8, 7, 7), (4, 3, 3) if args.shifted else (0, 0, 0))
+        N = win[0] * win[1] * win[2]
+        nwin = (dims[0] // win[0]) * (dims[1] // win[1]) * (dims[2] // win[2])
+        batch = clips * nwin
+        g = torch.Generator(device="cuda").manual_seed(1)
+        qkv = (torch.randn(batch * N, 3 * heads * hd, generator=g, device=dev) * 0.7).bfloat16()
+        dout = torch.randn(batch * N, heads * hd, generator=g, device=dev).bfloat16()
+        table = torch.randn(2535, heads, generator=g, device=dev) * 0.5
+        code, off = tables.rel_code(N, (8, 7, 7))
+        code = torch.from_numpy(code).to(dev)
+        masked = any(s > 0 for s in sh)
+        region = torch.from_numpy(tables.region_ids(*dims, win, sh)).to(dev) if masked else None
+        spec = swin._w7_spec(dims, win, sh, (8, 7, 7), dev)
+        out = torch.empty(batch * N, heads * hd, dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(batch, heads, N, dtype=torch.float32, device=dev)
+        dqkv = torch.empty_like(qkv)
+        dtab = torch.zeros(2535, heads, device=dev)
+        kw = dict(bias_table=table, rel_code=code, code_off=off, region=region, w7=spec)
+        flops_f = 4.0 * batch * heads * N * N * hd
+        row = {"shape": name, "windows": batch, "N": N, "heads": heads, "shifted": bool(masked)}
+        ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)
+        for which in args.which.split(","):
+            fn = ((lambda: ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)) if which == "fwd" else
+                  (lambda: ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dqkv, hd ** -0.5, dbias_table=dtab, **kw)))
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.iters
+            fl = flops_f if which == "fwd" else 2 * flops_f
+            row[which + "_ms"] = round(ms, 4)
+            row[which + "_tflops"] = round(fl / ms / 1e9, 1)
+        res.append(row)
+        print(json.dumps(row), flush=True)
+    return res
+
+
+if __name__ == "__main__":
+    main()
