@@ -111,7 +111,8 @@ SIGNATURES = {
     "clv_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_attention_bwd_tc_workspace_bytes": (c_ll, [C.POINTER(AttnDesc), C.c_int]),
     "clv_attention_bwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
-    "clv_attention_w7_fwd": (C.c_int, [C.POINTER(AttnW7Desc), c_vp, c_vp, c_vp, c_vp]),
+    "clv_attention_w7_fwd_workspace_bytes": (c_ll, [C.POINTER(AttnW7Desc)]),
+    "clv_attention_w7_fwd": (C.c_int, [C.POINTER(AttnW7Desc), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_w7_bwd_workspace_bytes": (c_ll, [C.POINTER(AttnW7Desc), C.c_int]),
     "clv_attention_w7_bwd": (C.c_int, [C.POINTER(AttnW7Desc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, c_vp]),

@@ -19,6 +19,7 @@
 // Layouts, barriers and roles follow attention_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, the rest one thread
 // per TMEM lane (query row forward / key row backward).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "clover_b200.h"
@@ -77,6 +78,15 @@ CLV_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
       : "memory");
 }
 
+// ---- TMA store (shared -> global), bulk-group completion ----------------------------------------------------------
+CLV_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+CLV_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+CLV_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+CLV_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // =================================================================================================================
 // Forward.  Unit = (window b, head h, query tile t of 98 rows).
 // =================================================================================================================
@@ -88,11 +98,28 @@ struct W7FwdArgs {
   int tmem_cols, col_o;
   long long units;
   __nv_bfloat16* out; float* lse;
-  const float* bias_table; int table_len; int code_off;
+  const float* table_t; int table_len, table_ld; int code_off;   // [heads, table_ld] fp32, pre-multiplied by log2 e
   int has_ext, nwin;
 };
 
 constexpr int W7_FWD_THREADS = 192;
+
+// bias table -> [heads][ld] (ld = len rounded up to 4), times log2 e: one coalesced 10 KB copy per head change
+__global__ void attn_w7_table_kernel(const float* table, float* table_t, int len, int ld, int heads) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ld * heads) return;
+  const int h = idx / ld, x = idx - h * ld;
+  table_t[idx] = x < len ? table[(long long)x * heads + h] * W7_LOG2E : 0.f;
+}
+
+// contiguous unit range of CTA c: consecutive units share the head (slowest index), so the staged table is reloaded
+// at most once or twice per CTA
+CLV_DEVICE void w7_unit_range(long long units, long long& u0, long long& u1) {
+  const long long base = units / gridDim.x, rem = units % gridDim.x;
+  const long long c = blockIdx.x;
+  u0 = c * base + (c < rem ? c : rem);
+  u1 = u0 + base + (c < rem ? 1 : 0);
+}
 
 // pass 1 on CNT (<= 32) consecutive body columns starting at static column C0: x = s*log2e + bias*log2e; running max
 template <int C0, int CNT, int NREG>
@@ -122,7 +149,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = 8192 + 2 * a.kb_bytes + (a.has_ext ? 4096 + a.kx_bytes : 0);
   float* sTable = reinterpret_cast<float*>(smem + 2 * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sTable + ((a.table_len + 3) & ~3));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTable + a.table_ld);
   uint64_t* full_bar = bars;          // [2]
   uint64_t* empty_bar = bars + 2;     // [2]
   uint64_t* s_full = bars + 4;
@@ -148,11 +175,13 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long u_begin, u_end;
+  w7_unit_range(a.units, u_begin, u_end);
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int t = (int)(u % a.n_qt);
         const long long bh = u / a.n_qt;
         const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
@@ -186,7 +215,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint32_t idesc_s0 = make_idesc_bf16(128, a.n0, 0, 0);
       const uint32_t idesc_s1 = make_idesc_bf16(128, n1 > 0 ? n1 : 16, 0, 0);
       uint32_t it = 0;
-      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int stage = it & 1;
         mbar_wait(&full_bar[stage], (it >> 1) & 1);
         mbar_wait(s_free, (it & 1) ^ 1);
@@ -230,14 +259,15 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int n_body = a.seq / W7_TILE;
     int cur_h = -1;
     uint32_t it = 0;
-    for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+    for (long long u = u_begin; u < u_end; ++u, ++it) {
       const int t = (int)(u % a.n_qt);
       const long long bh = u / a.n_qt;
       const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
       const int i = t * W7_TILE + (valid ? r : 0);
       if (h != cur_h) {                       // stage this head's bias column, pre-multiplied by log2 e
         named_bar_sync(1, 128);
-        for (int x = tid; x < a.table_len; x += 128) sTable[x] = a.bias_table[(long long)x * a.heads + h] * W7_LOG2E;
+        const float4* src = reinterpret_cast<const float4*>(a.table_t + (long long)h * a.table_ld);
+        for (int x = tid; x < a.table_ld / 4; x += 128) reinterpret_cast<float4*>(sTable)[x] = __ldg(src + x);
         cur_h = h;
         named_bar_sync(1, 128);
       }
@@ -344,9 +374,10 @@ struct W7BwdArgs {
   int col_dp, col_dv, col_dk, col_dq, tmem_cols;
   long long units;
   __nv_bfloat16* dqkv; float q_scale;
-  __nv_bfloat16* ds_out; int ds_ld;   // [batch, heads, seq, ds_ld] bf16 or nullptr
-  const float* bias_table; int table_len; int code_off;
+  int dump_ds;                   // write dS^T [batch, heads, seq, nq] (bf16) with TMA stores for the bias-table gradient
+  const float* table_t; int table_len, table_ld; int code_off;
   int has_kx, nwin;
+  int pipe;                      // issue dV / dK steps chunk by chunk while the softmax warps are still working
 };
 
 constexpr int W7_BWD_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2-9: two column groups x four lane quarters
@@ -403,7 +434,7 @@ template <int SEQ>
 __global__ void __launch_bounds__(W7_BWD_THREADS, 1)
 attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_constant__ CUtensorMap tm_kv_tile,
                    const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_e,
-                   const __grid_constant__ CUtensorMap tm_kx, W7BwdArgs a) {
+                   const __grid_constant__ CUtensorMap tm_kx, const __grid_constant__ CUtensorMap tm_ds, W7BwdArgs a) {
   constexpr int NQ = (SEQ + 15) / 16 * 16;
   constexpr int SPLIT = SEQ > W7_SPLIT ? W7_SPLIT : SEQ;     // SEQ == 98: group 0 takes [0, 96), group 1 the last two columns
   extern __shared__ uint8_t smem_raw[];
@@ -417,17 +448,18 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
   uint8_t* sDS = sVx + 4096;
   const int ds_bytes = a.n_mq * 2 * 16384;
   float* sTable = reinterpret_cast<float*>(sDS + ds_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sTable + ((a.table_len + 3) & ~3));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTable + a.table_ld);
   uint64_t* qdo_full = bars;        // [2]
   uint64_t* qdo_empty = bars + 2;   // [2]
   uint64_t* kv_full = bars + 4;     // [2]
   uint64_t* kv_empty = bars + 6;    // [2]
   uint64_t* st_full = bars + 8;
-  uint64_t* p_ready = bars + 9;
+  uint64_t* dvk_done = bars + 9;
   uint64_t* mma2_done = bars + 10;
   uint64_t* acc_free = bars + 11;
   uint64_t* dq_free = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* chunk_ready = bars + 13;   // [NCH] one per 32-query chunk of the packed P^T / dS^T operands
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13 + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = a.heads * W7_HD;
@@ -438,7 +470,8 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
     for (int s = 0; s < 2; ++s) {
       mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(st_full, 1); mbar_init(p_ready, 8); mbar_init(mma2_done, 1); mbar_init(acc_free, 8); mbar_init(dq_free, 8);
+    mbar_init(st_full, 1); mbar_init(dvk_done, 1); mbar_init(mma2_done, 1); mbar_init(acc_free, 8); mbar_init(dq_free, 8);
+    for (int c = 0; c < 8; ++c) mbar_init(&chunk_ready[c], 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
@@ -467,11 +500,13 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long u_begin, u_end;
+  w7_unit_range(a.units, u_begin, u_end);
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0, tt = 0;
-      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int b = (int)(u % a.batch), h = (int)(u / a.batch);
         const int us = it & 1;
         mbar_wait(&qdo_empty[us], ((it >> 1) & 1) ^ 1);
@@ -500,7 +535,7 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
       const uint32_t idesc_ts = make_idesc_bf16(128, W7_HD, 0, 1);
       const uint32_t idesc_dq = make_idesc_bf16(128, W7_HD, 1, 1);
       uint32_t it = 0, tt = 0;
-      for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int us = it & 1;
         mbar_wait(&qdo_full[us], (it >> 1) & 1);
         mbar_wait(dq_free, (it & 1) ^ 1);
@@ -526,15 +561,56 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
             umma_bf16_ss(tmem_base + a.col_dp, make_smem_desc(v_addr + k * 32, 16, 512, 4),
                          make_smem_desc(do_addr + k * 32, 16, 512, 4), idesc_st, k > 0);
           umma_bf16_ss(tmem_base + a.col_dp, make_smem_desc(smem_u32(sVx), 16, 256, 6), desc_e, idesc_st, 1);
+          if (a.dump_ds) tma_store_wait_read();      // the previous tile's dS^T stores have left shared memory
           umma_commit(st_full);
-          mbar_wait(p_ready, tt & 1);
-          tc_fence_after();
-          for (int kk = 0; kk < NQ / 16; ++kk) {   // dV_t = P^T dO ; dK_t = dS^T Q   (K = queries, 16 per step)
+          // dV_t = P^T dO ; dK_t = dS^T Q (K = queries, 16 per step), issued chunk by chunk as the softmax warps
+          // publish 32 queries of packed operands: the tensor pipe works while the rest of the tile is still being
+          // exponentiated.  Chunks alternate between the two warp groups (they run concurrently).
+          // Accumulator columns (SEQ 196): dV in the spare columns [480,512); dK aliases dP^T columns [64,96), which are
+          // dead once warp group 0 has published its last chunk (its packed operands end at column 48) -- the dK steps
+          // of earlier chunks are deferred until then.
+          // SEQ 98 (256 columns): both alias columns [56,88) of their region, dead after chunk 2.
+          constexpr int NCH = (NQ / 16 + 1) / 2;
+          constexpr bool BIG = SEQ > W7_SPLIT + 2;
+          constexpr int order196[8] = {0, 3, 1, 4, 2, 5, 6, 6};
+          constexpr int order98[4] = {2, 0, 1, 3};
+          constexpr int DK_OPEN = BIG ? 4 : 0;          // position in the order after which dK may accumulate
+          uint32_t acc_v = 0, acc_k = 0;
+          if (!a.pipe) {
+            for (int c = 0; c < NCH; ++c) mbar_wait(&chunk_ready[c], tt & 1);
+            tc_fence_after();
+          }
+#pragma unroll 1
+          for (int o = 0; o < NCH; ++o) {
+            const int c = BIG ? order196[o & 7] : order98[o & 3];
+            if (a.pipe) {
+              mbar_wait(&chunk_ready[c], tt & 1);
+              tc_fence_after();
+            }
             // packed operands: queries [0, SPLIT) at columns [0, SPLIT/2); queries [SPLIT, NQ) at SPLIT + (q - SPLIT)/2
-            const uint32_t pc = kk * 16 < SPLIT ? kk * 8 : SPLIT + ((kk * 16 - SPLIT) >> 1);
-            umma_bf16_ts(tmem_base + a.col_dv, tmem_base + pc, make_smem_desc(do_addr + kk * 1024, 16, 512, 4), idesc_ts, kk > 0);
-            umma_bf16_ts(tmem_base + a.col_dk, tmem_base + a.col_dp + pc, make_smem_desc(q_addr + kk * 1024, 16, 512, 4), idesc_ts,
-                         kk > 0);
+            for (int kk = 2 * c; kk < 2 * c + 2 && kk < NQ / 16; ++kk) {
+              const uint32_t pc = kk * 16 < SPLIT ? kk * 8 : SPLIT + ((kk * 16 - SPLIT) >> 1);
+              umma_bf16_ts(tmem_base + a.col_dv, tmem_base + pc, make_smem_desc(do_addr + kk * 1024, 16, 512, 4), idesc_ts, acc_v);
+              acc_v = 1;
+            }
+            if (o >= DK_OPEN) {
+              for (int oo = (o == DK_OPEN ? 0 : o); oo <= o; ++oo) {
+                const int cc = BIG ? order196[oo & 7] : order98[oo & 3];
+                for (int kk = 2 * cc; kk < 2 * cc + 2 && kk < NQ / 16; ++kk) {
+                  const uint32_t pc = kk * 16 < SPLIT ? kk * 8 : SPLIT + ((kk * 16 - SPLIT) >> 1);
+                  umma_bf16_ts(tmem_base + a.col_dk, tmem_base + a.col_dp + pc, make_smem_desc(q_addr + kk * 1024, 16, 512, 4), idesc_ts, acc_k);
+                  acc_k = 1;
+                }
+              }
+            }
+          }
+          umma_commit(dvk_done);
+          if (a.dump_ds) {
+            // dS^T tile (all chunks published and fenced) -> global [b, h, key row, query]: 64-query boxes of 98 rows,
+            // same 128-byte swizzle as the shared tile; columns beyond nq are clipped by the tensor map
+            const int grow = (int)((((long long)u % a.batch) * a.heads + (u / a.batch)) * SEQ) + t * W7_TILE;
+            for (int q = 0; q < 2 * a.n_mq; ++q) tma_store_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
+            tma_store_commit();
           }
           const uint32_t ds_addr = smem_u32(sDS);
           for (int mq = 0; mq < a.n_mq; ++mq)      // dQ[mq] += dS K_t   (K = 128 keys of this tile; rows >= 98 of dS^T are zero)
@@ -546,6 +622,7 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
           if (t == a.n_kt - 1) umma_commit(&qdo_empty[us]);
         }
       }
+      if (a.dump_ds) tma_store_wait_all();
     }
   } else {
     const int quarter = warp & 3;
@@ -559,11 +636,12 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
     const int rsw = r & 7;
     int cur_h = -1;
     uint32_t it = 0, tt = 0;
-    for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
+    for (long long u = u_begin; u < u_end; ++u, ++it) {
       const int b = (int)(u % a.batch), h = (int)(u / a.batch);
       if (h != cur_h) {
         named_bar_sync(1, 256);
-        for (int x = tid; x < a.table_len; x += 256) sTable[x] = a.bias_table[(long long)x * a.heads + h] * W7_LOG2E;
+        const float4* src = reinterpret_cast<const float4*>(a.table_t + (long long)h * a.table_ld);
+        for (int x = tid; x < a.table_ld / 4; x += 256) reinterpret_cast<float4*>(sTable)[x] = __ldg(src + x);
         cur_h = h;
         named_bar_sync(1, 256);
       }
@@ -571,7 +649,6 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
         const int j = t * W7_TILE + (valid ? r : 0);
         // sTable[code_i + (off - code_j)]: per-thread base, static query offsets
         const float* tbj = sTable + (a.code_off - ((j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7)));
-        __nv_bfloat16* ds_g = a.ds_out ? a.ds_out + (((long long)b * a.heads + h) * SEQ + j) * a.ds_ld : nullptr;
         mbar_wait(st_full, tt & 1);
         tc_fence_after();
         if (warp_active) {
@@ -580,6 +657,12 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
             // queries [0, 96): three chunks of 32, packed at [0, 48)
             uint32_t v[32], w[32], v2[32], w2[32], pk[16], dk[16];
             tmem_ld_32x32(ts0, v); tmem_ld_32x32(td0, w); tmem_ld_wait();
+#define W7_CHUNK_DONE(CH, LAST)                                                                                  \
+            tmem_st_wait();                                                                                      \
+            if (LAST) fence_proxy_async();                                                                       \
+            tc_fence_before();                                                                                   \
+            __syncwarp();                                                                                        \
+            if (lane == 0) mbar_arrive(&chunk_ready[CH]);
 #define W7_BWD_EMIT(C0, PV, PW)                                                                                  \
             w7_bwd_chunk<C0, 32>(PV, PW, tbj, pk, dk);                                                           \
             tmem_st_32x16(ts0 + (C0) / 2, pk); tmem_st_32x16(td0 + (C0) / 2, dk);                                 \
@@ -588,18 +671,17 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
               _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                      \
                 *reinterpret_cast<uint4*>(chunk + (((((C0) >> 5) & 1) * 4 + q) ^ rsw) * 16) =                    \
                     make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]);                          \
-              if (ds_g) {                                                                                        \
-                uint4* g = reinterpret_cast<uint4*>(ds_g + (C0));                                                \
-                _Pragma("unroll") for (int q = 0; q < 4; ++q) g[q] = make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]); \
-              }                                                                                                  \
             }
             tmem_ld_32x32(ts0 + 32, v2); tmem_ld_32x32(td0 + 32, w2);
             W7_BWD_EMIT(0, v, w)
+            W7_CHUNK_DONE(0, false)
             tmem_ld_wait();
             tmem_ld_32x32(ts0 + 64, v); tmem_ld_32x32(td0 + 64, w);
             W7_BWD_EMIT(32, v2, w2)
+            W7_CHUNK_DONE(1, false)
             tmem_ld_wait();
             W7_BWD_EMIT(64, v, w)
+            W7_CHUNK_DONE(2, true)
           } else if (SEQ > W7_SPLIT + 2) {
             // queries [96, 196): three chunks of 32 and a tail of 4, packed at [96, 146); zero the packed pads [146, 152)
             uint32_t v[32], w[32], v2[32], w2[32], pk[16], dk[16];
@@ -612,20 +694,19 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
               _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                      \
                 *reinterpret_cast<uint4*>(chunk + (((((C0) >> 5) & 1) * 4 + q) ^ rsw) * 16) =                    \
                     make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]);                          \
-              if (ds_g) {                                                                                        \
-                uint4* g = reinterpret_cast<uint4*>(ds_g + (C0));                                                \
-                _Pragma("unroll") for (int q = 0; q < 4; ++q) g[q] = make_uint4(dk[q * 4], dk[q * 4 + 1], dk[q * 4 + 2], dk[q * 4 + 3]); \
-              }                                                                                                  \
             }
             tmem_ld_32x32(ts0 + 128, v2); tmem_ld_32x32(td0 + 128, w2);
             W7_BWD_EMIT1(96, v, w)
+            W7_CHUNK_DONE(3, false)
             tmem_ld_wait();
             tmem_ld_32x32(ts0 + 160, v); tmem_ld_32x32(td0 + 160, w);
             W7_BWD_EMIT1(128, v2, w2)
+            W7_CHUNK_DONE(4, false)
             tmem_ld_wait();
             uint32_t v4[4], w4[4];
             tmem_ld_32x4(ts0 + 192, v4); tmem_ld_32x4(td0 + 192, w4);
             W7_BWD_EMIT1(160, v, w)
+            W7_CHUNK_DONE(5, false)
             tmem_ld_wait();
             w7_bwd_chunk<192, 4>(v4, w4, tbj, pk, dk);
             {
@@ -634,8 +715,8 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
             }
             if (valid) {
               *reinterpret_cast<uint4*>(ds_row + 3 * 16384 + ((0 ^ rsw) * 16)) = make_uint4(dk[0], dk[1], 0, 0);
-              if (ds_g) *reinterpret_cast<uint2*>(ds_g + 192) = make_uint2(dk[0], dk[1]);
             }
+            W7_CHUNK_DONE(6, true)
           } else {
             // SEQ == 98: group 1 takes the last two queries; packed at [96/2 .. ) does not apply -> single segment
             uint32_t v4[2], w4[2], pk[16], dk[16];
@@ -647,17 +728,12 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
             }
             if (valid) {
               *reinterpret_cast<uint4*>(ds_row + 1 * 16384 + (((4 + 0) ^ rsw) * 16)) = make_uint4(dk[0], 0, 0, 0);
-              if (ds_g) *reinterpret_cast<uint32_t*>(ds_g + 96) = dk[0];
             }
+            W7_CHUNK_DONE(3, true)
           }
-          tmem_st_wait();
         }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_ready);
 
-        mbar_wait(mma2_done, tt & 1);
+        mbar_wait(dvk_done, tt & 1);
         tc_fence_after();
         if (warp_active) {
           // dV rows by warp group 0, dK rows by warp group 1
@@ -677,6 +753,8 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
         }
         if (t == a.n_kt - 1) {
           // dQ of the whole unit (all key tiles accumulated); query row i = mq*128 + r; tiles alternate between warp groups
+          mbar_wait(mma2_done, tt & 1);
+          tc_fence_after();
           for (int mq = grp; mq < a.n_mq; mq += 2) {
             const int i = mq * 128 + r;
             if (mq * 128 + quarter * 32 < SEQ) {
@@ -711,25 +789,30 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
 }
 
 // dTable[(code_i - code_j + off), h] += sum_b dS^T[b, h, j, i]   (bf16 dS^T, fp32 accumulation).
-// grid = (key rows j, heads, batch splits); one thread per 4 queries (8-byte loads), static 7x7 codes.
-__global__ void attn_w7_dbias_kernel(const __nv_bfloat16* ds, int batch, int heads, int seq, int ld, int code_off, float* dtable) {
-  const int j = blockIdx.x, h = blockIdx.y;
-  const int i0 = threadIdx.x * 4;
-  if (i0 >= seq) return;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+// One thread per 8 consecutive queries of one key row (16-byte loads), 256-thread blocks over the flattened
+// (key row, query octet) index; grid = (position blocks, heads, batch splits); static 7x7 codes.
+__global__ void __launch_bounds__(256) attn_w7_dbias_kernel(const __nv_bfloat16* ds, int batch, int heads, int seq, int ld,
+                                                            int code_off, float* dtable) {
+  const int oct = ld >> 3;
+  const int pos = blockIdx.x * 256 + threadIdx.x;
+  if (pos >= seq * oct) return;
+  const int j = pos / oct, i0 = (pos - j * oct) * 8;
+  const int h = blockIdx.y;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const long long stride = (long long)heads * seq * ld;
   const __nv_bfloat16* p = ds + ((long long)h * seq + j) * ld + i0;
   const int per = (batch + gridDim.z - 1) / gridDim.z;
   const int b0 = blockIdx.z * per, b1 = min(batch, b0 + per);
 #pragma unroll 8
   for (int b = b0; b < b1; ++b) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + b * stride));
-    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + b * stride));
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
     acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+    acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
   }
   const int cj = (j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7);
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < 8; ++e) {
     const int i = i0 + e;
     if (i < seq) {
       const int ci = (i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7);
@@ -754,10 +837,18 @@ static int w7_check(const clv_attn_w7_desc_t* d, const char* who, int max_wd) {
 
 using namespace clv;
 
-extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv, void* out, float* lse, void* stream_) {
+static long long w7_table_bytes(const clv_attn_w7_desc_t* d) {
+  return ((long long)((d->table_len + 3) & ~3) * d->heads * 4 + 255) / 256 * 256;
+}
+
+extern "C" long long clv_attention_w7_fwd_workspace_bytes(const clv_attn_w7_desc_t* d) { return d ? w7_table_bytes(d) : 0; }
+
+extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv, void* out, float* lse, void* workspace,
+                                    void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = w7_check(d, "attention_w7_fwd", 8)) return rc;
-  CLV_REQUIRE(qkv && out && lse, "attention_w7_fwd: null pointer");
+  CLV_REQUIRE(qkv && out && lse && workspace, "attention_w7_fwd: null pointer");
+  CLV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "attention_w7_fwd: workspace must be 16-byte aligned");
   W7FwdArgs a{};
   a.batch = d->batch; a.heads = d->heads; a.seq = 49 * d->wd; a.n_qt = d->wd / 2;
   a.nmma = (a.seq + 15) / 16 * 16;
@@ -768,7 +859,14 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
   a.col_o = a.nmma;
   a.units = (long long)d->batch * d->heads * a.n_qt;
   a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse;
-  a.bias_table = d->bias_table; a.table_len = d->table_len;
+  a.table_len = d->table_len; a.table_ld = (d->table_len + 3) & ~3;
+  {
+    float* tt = reinterpret_cast<float*>(workspace);
+    const int n = a.table_ld * d->heads;
+    attn_w7_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d->bias_table, tt, a.table_len, a.table_ld, d->heads);
+    if (int rc = after_launch("attn_w7_table_kernel")) return rc;
+    a.table_t = tt;
+  }
   a.code_off = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;
   a.has_ext = d->q_ext != nullptr; a.nwin = d->nwin > 0 ? d->nwin : 1;
   const long long rows = (long long)d->batch * a.seq;
@@ -787,7 +885,7 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
     if (n1 > 0) { if (int rc = make_tmap_bf16_2d(&tkx1, d->k_ext, 16, xrows, 16, 16, n1, 32)) return rc; }
   }
   const size_t stage = 8192 + 2 * (size_t)a.kb_bytes + (a.has_ext ? 4096 + (size_t)a.kx_bytes : 0);
-  const size_t smem = 1024 + 2 * stage + (size_t)((a.table_len + 3) & ~3) * 4 + 9 * 8 + 16;
+  const size_t smem = 1024 + 2 * stage + (size_t)a.table_ld * 4 + 9 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_fwd: %zu bytes of shared memory needed", smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -804,7 +902,7 @@ extern "C" long long clv_attention_w7_bwd_workspace_bytes(const clv_attn_w7_desc
   if (!d) return 0;
   const long long seq = 49LL * d->wd;
   const long long nq = (seq + 15) / 16 * 16;
-  long long bytes = ((long long)d->batch * d->heads * seq * 32 + 255) / 256 * 256 + 1024;      // e rows (16 bf16)
+  long long bytes = w7_table_bytes(d) + ((long long)d->batch * d->heads * seq * 32 + 255) / 256 * 256 + 1024;   // table^T, e rows (16 bf16)
   if (with_dbias) bytes += (long long)d->batch * d->heads * seq * nq * 2 + 256;                 // bf16 dS^T
   return bytes;
 }
@@ -823,24 +921,38 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   a.eb_bytes = (a.nq * W7_XROWB + 1023) / 1024 * 1024;
   a.n_mq = (a.nq + 127) / 128;
   a.col_dp = a.nq;
-  a.col_dv = a.nq - W7_HD - 16;          // dead S^T columns clear of both packed segments ([0,48) and [96,152))
-  a.col_dk = a.col_dp + a.col_dv;
   a.col_dq = 2 * a.nq;
   const int need_cols = 2 * a.nq + a.n_mq * W7_HD;
   a.tmem_cols = need_cols <= 256 ? 256 : 512;
   CLV_REQUIRE(need_cols <= 512, "attention_w7_bwd: %d TMEM columns needed", need_cols);
-  if (a.seq == 98) a.col_dv = 56;        // single 98-query segment packed at [0,48) + [96,104): columns [56, 88) are dead
-  a.col_dk = a.col_dp + a.col_dv;
+  if (a.seq == 98) {                     // packed at [0,48) + [96,104): columns [56,88) of each region are dead after chunk 2
+    a.col_dv = 56; a.col_dk = a.col_dp + 56;
+  } else {                               // see the accumulation order in the kernel
+    a.col_dv = 480; a.col_dk = a.col_dp + 64;
+  }
   a.units = (long long)d->batch * d->heads;
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.q_scale = q_scale;
-  a.bias_table = d->bias_table; a.table_len = d->table_len;
+  a.table_len = d->table_len; a.table_ld = (d->table_len + 3) & ~3;
+  {
+    float* tt = reinterpret_cast<float*>(workspace);
+    const int n = a.table_ld * d->heads;
+    attn_w7_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d->bias_table, tt, a.table_len, a.table_ld, d->heads);
+    if (int rc = after_launch("attn_w7_table_kernel")) return rc;
+    a.table_t = tt;
+  }
   a.code_off = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;
   a.has_kx = d->k_ext != nullptr; a.nwin = d->nwin > 0 ? d->nwin : 1;
+  {
+    static int pipe = -1;
+    if (pipe < 0) { const char* e = getenv("CLOVER_B200_W7_PIPE"); pipe = e ? atoi(e) : 1; }
+    a.pipe = pipe;
+  }
   const long long rows = (long long)d->batch * a.seq;
-  __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(workspace);
+  const long long t_bytes = w7_table_bytes(d);
+  __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + t_bytes);
   const long long e_bytes = ((long long)d->batch * d->heads * a.seq * 32 + 255) / 256 * 256 + 1024;
-  a.ds_ld = a.nq;
-  a.ds_out = dbias_table ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + e_bytes) : nullptr;
+  __nv_bfloat16* ds_out = dbias_table ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + t_bytes + e_bytes) : nullptr;
+  a.dump_ds = ds_out != nullptr;
   {
     const long long n = rows * d->heads;
     attn_w7_prep_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
@@ -849,15 +961,16 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     if (int rc = after_launch("attn_w7_prep_kernel")) return rc;
   }
   const long long ld = 3LL * d->heads * W7_HD, ldo = (long long)d->heads * W7_HD;
-  CUtensorMap tfull, ttile, tdo, te, tkx;
+  CUtensorMap tfull, ttile, tdo, te, tkx, tds;
   if (int rc = make_tmap_bf16_2d(&tfull, qkv, ld, rows, ld, W7_HD, a.nq, 64)) return rc;
   if (int rc = make_tmap_bf16_2d(&ttile, qkv, ld, rows, ld, W7_HD, 128, 64)) return rc;
   if (int rc = make_tmap_bf16_2d(&tdo, dout, ldo, rows, ldo, W7_HD, a.nq, 64)) return rc;
   if (int rc = make_tmap_bf16_2d(&te, e, 16, rows * d->heads, 16, 16, a.nq, 32)) return rc;
-  tkx = te;
+  tkx = te; tds = te;
+  if (ds_out) { if (int rc = make_tmap_bf16_2d(&tds, ds_out, a.nq, rows * d->heads, a.nq, 64, W7_TILE, 128)) return rc; }
   if (a.has_kx) { if (int rc = make_tmap_bf16_2d(&tkx, d->k_ext, 16, (long long)a.nwin * a.seq, 16, 16, 128, 32)) return rc; }
   const size_t smem = 1024 + 2 * (2 * (size_t)a.qb_bytes + a.eb_bytes) + 2 * (2 * 8192 + 4096) + 4096 + (size_t)a.n_mq * 2 * 16384 +
-                      (size_t)((a.table_len + 3) & ~3) * 4 + 14 * 8 + 16;
+                      (size_t)a.table_ld * 4 + 22 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_bwd: %zu bytes of shared memory needed", smem);
   auto kern = a.seq == 196 ? attn_w7_bwd_kernel<196> : attn_w7_bwd_kernel<98>;
   static size_t smem_set[2] = {0, 0};
@@ -866,12 +979,13 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     smem_set[a.seq == 196] = smem;
   }
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
-  kern<<<grid, W7_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, te, tkx, a);
+  kern<<<grid, W7_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, te, tkx, tds, a);
   if (int rc = after_launch("attn_w7_bwd_kernel")) return rc;
   if (dbias_table) {
-    const int zsplit = std::max(1, std::min(32, d->batch / 32));
-    dim3 g(a.seq, d->heads, zsplit);
-    attn_w7_dbias_kernel<<<g, (a.seq + 3) / 4, 0, stream>>>(a.ds_out, d->batch, d->heads, a.seq, a.ds_ld, a.code_off, dbias_table);
+    const int pos_blocks = (a.seq * (a.nq / 8) + 255) / 256;
+    const int zsplit = std::max(1, std::min(std::min(64, d->batch / 8), (8 * num_sms()) / (pos_blocks * d->heads) + 1));
+    dim3 g(pos_blocks, d->heads, zsplit);
+    attn_w7_dbias_kernel<<<g, 256, 0, stream>>>(ds_out, d->batch, d->heads, a.seq, a.nq, a.code_off, dbias_table);
     if (int rc = after_launch("attn_w7_dbias_kernel")) return rc;
   }
   return 0;

@@ -360,7 +360,9 @@ def attention_fwd(qkv, batch, seq, heads, hd, out, lse, w7=None, **bias):
         if bias["bias_table"].dtype != F32 or not bias["bias_table"].is_contiguous():
             raise TypeError("attention_fwd: bias_table must be contiguous fp32")
         dw = w7.desc(batch, heads, bias["bias_table"])
-        _lib.check(lib.clv_attention_w7_fwd(C.byref(dw), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_w7_fwd")
+        ws = torch.empty(lib.clv_attention_w7_fwd_workspace_bytes(C.byref(dw)), dtype=torch.uint8, device=qkv.device)
+        _lib.check(lib.clv_attention_w7_fwd(C.byref(dw), _ptr(qkv), _ptr(out), _ptr(lse), _ptr(ws), _stream()),
+                   "clv_attention_w7_fwd")
     elif hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 416 and USE_TC_ATTENTION:
         _lib.check(lib.clv_attention_fwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd_tc")
     else:

@@ -247,7 +247,9 @@ typedef struct {
   const void* q_ext; const void* k_ext; int nwin;       /* bf16 [nwin, seq, 16] each, or NULL; window type = batch % nwin */
 } clv_attn_w7_desc_t;
 
-int clv_attention_w7_fwd(const clv_attn_w7_desc_t* desc, const void* qkv, void* out, float* lse, void* stream);
+long long clv_attention_w7_fwd_workspace_bytes(const clv_attn_w7_desc_t* desc);
+int clv_attention_w7_fwd(const clv_attn_w7_desc_t* desc, const void* qkv, void* out, float* lse,
+                         void* workspace /* 16-byte aligned scratch */, void* stream);
 long long clv_attention_w7_bwd_workspace_bytes(const clv_attn_w7_desc_t* desc, int with_dbias);
 int clv_attention_w7_bwd(const clv_attn_w7_desc_t* desc, const void* qkv, const void* out, const void* dout, const float* lse,
                          void* dqkv, float q_scale, float* dbias_table, void* workspace /* 256-byte aligned */, void* stream);

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--which", default="fwd,bwd")
     ap.add_argument("--shifted", type=int, default=1)
+    ap.add_argument("--dbias", type=int, default=1, help="0: backward without the bias-table gradient (no dS dump)")
     args = ap.parse_args()
     from clover_b200 import ops, swin, tables
     dev = torch.device("cuda")
@@ -61,7 +62,7 @@ def main():
         ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)
         for which in args.which.split(","):
             fn = ((lambda: ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)) if which == "fwd" else
-                  (lambda: ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dqkv, hd ** -0.5, dbias_table=dtab, **kw)))
+                  (lambda: ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dqkv, hd ** -0.5, dbias_table=dtab if args.dbias else None, **kw)))
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
