@@ -23,7 +23,8 @@
 namespace clv {
 
 constexpr int BM = 128, BK = 64;
-constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two column halves x four lane quarters)
+constexpr int GEMM_EPI_WARPS = 16;    // four column quarters x four lane quarters
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
 
 template <int BN> struct GemmCfg {
   static constexpr int STAGES = BN == 128 ? 6 : 4;
@@ -56,13 +57,14 @@ CLV_DEVICE void st256(void* p, const uint32_t (&r)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
-// 32 bf16 (64 B) or 32 fp32 (128 B) of one row <-> registers; `wide` selects the 256-bit path
-CLV_DEVICE void load_row32(const void* base, int is_bf16, bool wide, int ncols, float (&f)[32]) {
+// NE (16 or 32) bf16 / fp32 of one row <-> registers; `wide` selects the 256-bit path
+template <int NE>
+CLV_DEVICE void load_row(const void* base, int is_bf16, bool wide, int ncols, float (&f)[NE]) {
   if (is_bf16) {
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base);
     if (wide) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NE / 16; ++h) {
         uint32_t r[8];
         ld256(p + h * 16, r);
 #pragma unroll
@@ -70,7 +72,7 @@ CLV_DEVICE void load_row32(const void* base, int is_bf16, bool wide, int ncols, 
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < NE / 8; ++q)
         if (q * 8 < ncols) {
           const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + q);
           const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
@@ -82,7 +84,7 @@ CLV_DEVICE void load_row32(const void* base, int is_bf16, bool wide, int ncols, 
     const float* p = reinterpret_cast<const float*>(base);
     if (wide) {
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 0; h < NE / 8; ++h) {
         uint32_t r[8];
         ld256(p + h * 8, r);
 #pragma unroll
@@ -90,7 +92,7 @@ CLV_DEVICE void load_row32(const void* base, int is_bf16, bool wide, int ncols, 
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < NE / 4; ++q)
         if (q * 4 < ncols) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
           f[q * 4] = t.x; f[q * 4 + 1] = t.y; f[q * 4 + 2] = t.z; f[q * 4 + 3] = t.w;
@@ -98,12 +100,13 @@ CLV_DEVICE void load_row32(const void* base, int is_bf16, bool wide, int ncols, 
     }
   }
 }
-CLV_DEVICE void store_row32(void* base, int is_bf16, bool wide, int ncols, const float (&v)[32]) {
+template <int NE>
+CLV_DEVICE void store_row(void* base, int is_bf16, bool wide, int ncols, const float (&v)[NE]) {
   if (is_bf16) {
     __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base);
     if (wide) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NE / 16; ++h) {
         uint32_t r[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = pack_bf16(v[h * 16 + 2 * j], v[h * 16 + 2 * j + 1]);
@@ -111,7 +114,7 @@ CLV_DEVICE void store_row32(void* base, int is_bf16, bool wide, int ncols, const
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < NE / 8; ++q)
         if (q * 8 < ncols)
           reinterpret_cast<uint4*>(p)[q] = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                                                       pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
@@ -120,7 +123,7 @@ CLV_DEVICE void store_row32(void* base, int is_bf16, bool wide, int ncols, const
     float* p = reinterpret_cast<float*>(base);
     if (wide) {
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 0; h < NE / 8; ++h) {
         uint32_t r[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[h * 8 + j]);
@@ -128,7 +131,7 @@ CLV_DEVICE void store_row32(void* base, int is_bf16, bool wide, int ncols, const
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < NE / 4; ++q)
         if (q * 4 < ncols) reinterpret_cast<float4*>(p)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
     }
   }
@@ -165,7 +168,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -246,11 +249,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ---------------- epilogue: 8 warps; TMEM lanes (warp % 4) * 32 ... +31, column half (warp - 2) / 4 ----------------
+    // ---------------- epilogue: 16 warps; TMEM lanes (warp % 4) * 32 ... +31, column quarter (warp - 2) / 4 -------------
+    // (issue-bound for K <= 512: four warps per scheduler hide the dependent-latency stalls of the element math)
     const int quarter = warp & 3;
     const int chalf = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
-    constexpr int CHUNKS = BN / 64;          // 32-column chunks per warp
+    constexpr int CPW = BN / (GEMM_EPI_WARPS / 4);   // columns per warp
+    constexpr int EC = 16;                           // columns per epilogue step (register budget: 576 threads)
+    constexpr int CHUNKS = CPW / EC;
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const long long mn = t / k_splits;
@@ -258,8 +264,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const float* sb = sBias + acc * BN;
       if (ep.bias) {
-        for (int x = et; x < BN; x += 256) sBias[acc * BN + x] = (n_idx * BN + x < N) ? __ldg(ep.bias + n_idx * BN + x) : 0.f;
-        named_bar_sync(1, 256);
+        for (int x = et; x < BN; x += 32 * GEMM_EPI_WARPS) sBias[acc * BN + x] = (n_idx * BN + x < N) ? __ldg(ep.bias + n_idx * BN + x) : 0.f;
+        named_bar_sync(1, 32 * GEMM_EPI_WARPS);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -269,60 +275,60 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const bool row_ok = row < M && drow >= 0;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
-        uint32_t r[32];
-        const int cb = chalf * (BN / 2) + c * 32;        // column offset inside the tile
+        uint32_t r[EC];
+        const int cb = chalf * CPW + c * EC;             // column offset inside the tile
         const int n0 = n_idx * BN + cb;
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb, r);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb, r);
         tmem_ld_wait();
         if (!row_ok || n0 >= N) continue;
-        float v[32];
+        float v[EC];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int ncols = min(32, N - n0);  // multiple of 8 (N % 8 == 0)
-        const bool wide = ep.vec32 != 0;    // implies ncols == 32
+        for (int j = 0; j < EC; ++j) v[j] = __uint_as_float(r[j]);
+        const int ncols = min(EC, N - n0);  // multiple of 8 (N % 8 == 0)
+        const bool wide = ep.vec32 != 0;    // implies ncols == EC
         if (ep.atomic_out) {
           float* o = reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < EC; ++j)
             if (j < ncols) atomicAdd(o + j, v[j]);
           continue;
         }
         if (ep.bias) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < EC / 4; ++q) {
             const float4 b4 = *reinterpret_cast<const float4*>(sb + cb + q * 4);
             v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
           }
         }
         if (ep.scale_cols > n0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < EC; ++j)
             if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
         }
         if (ep.act == 1) {
-          if (ep.out_pre) store_row32(ep.out_pre + row * ep.ld_pre + n0, 1, wide, ncols, v);
+          if (ep.out_pre) store_row<EC>(ep.out_pre + row * ep.ld_pre + n0, 1, wide, ncols, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < EC; ++j) v[j] = gelu_fit(v[j]);
         }
         if (ep.gelu_pre) {
-          float g[32];
-          load_row32(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
+          float g[EC];
+          load_row<EC>(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(g[j]);
+          for (int j = 0; j < EC; ++j) v[j] *= gelu_fit_grad(g[j]);
         }
         if (ep.residual) {
-          float g[32];
+          float g[EC];
           if (ep.residual_bf16)
-            load_row32(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + drow * ep.ld_res + n0, 1, wide, ncols, g);
+            load_row<EC>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + drow * ep.ld_res + n0, 1, wide, ncols, g);
           else
-            load_row32(reinterpret_cast<const float*>(ep.residual) + drow * ep.ld_res + n0, 0, wide, ncols, g);
+            load_row<EC>(reinterpret_cast<const float*>(ep.residual) + drow * ep.ld_res + n0, 0, wide, ncols, g);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += g[j];
+          for (int j = 0; j < EC; ++j) v[j] += g[j];
         }
         if (ep.out_bf16)
-          store_row32(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0, 1, wide, ncols, v);
+          store_row<EC>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0, 1, wide, ncols, v);
         else
-          store_row32(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0, 0, wide, ncols, v);
+          store_row<EC>(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0, 0, wide, ncols, v);
       }
       tc_fence_before();
       __syncwarp();
