@@ -63,7 +63,7 @@ class LnrDesc(C.Structure):
 class LnrBwd(C.Structure):
     _fields_ = [
         ("dy", c_vp), ("dy_is_bf16", C.c_int), ("dy_mapped", C.c_int), ("dres", c_vp), ("dx", c_vp),
-        ("dx_bf16", c_vp), ("dx_bf16_mapped", C.c_int), ("dgamma", c_vp), ("dbeta", c_vp),
+        ("dx_bf16", c_vp), ("dx_bf16_mapped", C.c_int), ("dgamma", c_vp), ("dbeta", c_vp), ("dxsum", c_vp),
     ]
 
 

@@ -788,6 +788,339 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
   if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
+// =================================================================================================================
+// Backward, second generation (seq = 196): the same math as attn_w7_bwd_kernel, re-pipelined around the measured cost
+// of tcgen05.mma -- about 98 cycles per instruction for any N <= 128 (tools/probes/mma_probe.cu) -- which makes the
+// 48 MMAs of a key tile (~5.9 k cycles) the bound, not the exponentials (~1.6 k).  The first version serialises
+// "all of S^T and dP^T -> all threads -> all of dV/dK/dQ" because the two fp32 score tiles fill tensor memory; here
+// the queries are cut into chunks of 96 that cycle through two small TMEM buffers,
+//     buf b: S^T chunk at [192 b, 192 b + 96), dP^T chunk at [192 b + 96, 192 b + 192);   dV [384,416)  dK [416,448)  dQ [448,512)
+// so the tensor pipe computes the scores of chunk c+1 and the dV/dK steps of chunk c-1 while the threads
+// exponentiate chunk c, and no accumulator aliases live data.  Chunks: queries [0,96) -> buf 0, [96,192) -> buf 1,
+// [192,208) -> buf 0 (4 real queries + zero padding).  Inside a chunk warp group g owns columns [48 g, 48 g + 48)
+// and packs P^T / dS^T in place at [48 g, 48 g + 24) of the S^T / dP^T halves (3 K-steps of 16 queries each).
+// =================================================================================================================
+constexpr int W7B2_CH = 96;            // queries per chunk
+constexpr int W7B2_BUF = 192;          // TMEM columns per buffer (S^T chunk + dP^T chunk)
+constexpr int W7B2_DV = 384, W7B2_DK = 416, W7B2_DQ = 448;
+
+// dS^T of 8 consecutive queries starting at I8 (multiple of 8) -> shared tile (64-query chunks, 128-byte swizzle)
+template <int I8>
+CLV_DEVICE void w7_ds_store(uint8_t* ds_row, int rsw, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(ds_row + (I8 >> 6) * 16384 + ((((I8 >> 3) & 7) ^ rsw) * 16)) = make_uint4(a, b, c, d);
+}
+
+// 48 query columns [I0, I0 + 48) of one key row: TMEM (S^T at ts, dP^T at td, column 0 = query I0) -> packed in place
+template <int I0>
+CLV_DEVICE void w7_bwd2_body(uint32_t ts, uint32_t td, const float* tbj, uint8_t* ds_row, int rsw, bool valid) {
+  uint32_t v[32], w[32], v2[16], w2[16], pk[16], dk[16];
+  tmem_ld_32x32(ts, v); tmem_ld_32x32(td, w); tmem_ld_wait();
+  tmem_ld_32x16(ts + 32, v2); tmem_ld_32x16(td + 32, w2);
+  w7_bwd_chunk<I0, 32>(v, w, tbj, pk, dk);
+  tmem_st_32x16(ts, pk); tmem_st_32x16(td, dk);
+  if (valid) {
+    w7_ds_store<I0>(ds_row, rsw, dk[0], dk[1], dk[2], dk[3]);
+    w7_ds_store<I0 + 8>(ds_row, rsw, dk[4], dk[5], dk[6], dk[7]);
+    w7_ds_store<I0 + 16>(ds_row, rsw, dk[8], dk[9], dk[10], dk[11]);
+    w7_ds_store<I0 + 24>(ds_row, rsw, dk[12], dk[13], dk[14], dk[15]);
+  }
+  tmem_ld_wait();
+  uint32_t pk2[8], dk2[8];
+  w7_bwd_chunk<I0 + 32, 16>(v2, w2, tbj, pk2, dk2);
+  tmem_st_32x8(ts + 16, pk2); tmem_st_32x8(td + 16, dk2);
+  if (valid) {
+    w7_ds_store<I0 + 32>(ds_row, rsw, dk2[0], dk2[1], dk2[2], dk2[3]);
+    w7_ds_store<I0 + 40>(ds_row, rsw, dk2[4], dk2[5], dk2[6], dk2[7]);
+  }
+}
+
+__global__ void __launch_bounds__(W7_BWD_THREADS, 1)
+attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_constant__ CUtensorMap tm_kv_tile,
+                    const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_e,
+                    const __grid_constant__ CUtensorMap tm_kx, const __grid_constant__ CUtensorMap tm_ds, W7BwdArgs a) {
+  constexpr int SEQ = 196, NQ = 208;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // layout: [Q0 dO0 e0 | Q1 dO1 e1] [K0 V0 kx0 | K1 V1 kx1] [vx] [dS^T tile] table barriers   (as attn_w7_bwd_kernel)
+  const int unit_bytes = 2 * a.qb_bytes + a.eb_bytes;
+  constexpr int tile_bytes = 2 * 8192 + 4096;
+  uint8_t* sQdO = smem;
+  uint8_t* sKV = sQdO + 2 * unit_bytes;
+  uint8_t* sVx = sKV + 2 * tile_bytes;
+  uint8_t* sDS = sVx + 4096;
+  constexpr int ds_bytes = 4 * 16384;
+  float* sTable = reinterpret_cast<float*>(sDS + ds_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTable + a.table_ld);
+  uint64_t* qdo_full = bars;        // [2]
+  uint64_t* qdo_empty = bars + 2;   // [2]
+  uint64_t* kv_full = bars + 4;     // [2]
+  uint64_t* kv_empty = bars + 6;    // [2]
+  uint64_t* s_ready = bars + 8;     // [2] scores of the chunk in buffer b are in tensor memory
+  uint64_t* p_ready = bars + 10;    // [2] packed operands of the chunk in buffer b are published (8 warps)
+  uint64_t* dvk_done = bars + 12;
+  uint64_t* mma2_done = bars + 13;
+  uint64_t* acc_free = bars + 14;
+  uint64_t* dq_free = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.heads * W7_HD;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q_full); tma_prefetch_desc(&tm_kv_tile); tma_prefetch_desc(&tm_do_full); tma_prefetch_desc(&tm_e);
+    if (a.has_kx) tma_prefetch_desc(&tm_kx);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_ready[s], 1); mbar_init(&p_ready[s], 8);
+    }
+    mbar_init(dvk_done, 1); mbar_init(mma2_done, 1); mbar_init(acc_free, 8); mbar_init(dq_free, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp >= 2) {
+    const int tid = threadIdx.x - 64;
+    for (int x = tid; x < ds_bytes / 16; x += 256) reinterpret_cast<uint4*>(sDS)[x] = make_uint4(0, 0, 0, 0);
+    const uint32_t one2 = 0x3F803F80u;
+    for (int x = tid; x < 128; x += 256) {
+      uint4* rowp = reinterpret_cast<uint4*>(sVx + x * 32);
+      const int sw = (x >> 2) & 1;
+      rowp[sw] = make_uint4(0, one2, 0, 0);
+      rowp[sw ^ 1] = make_uint4(0, 0, 0, 0);
+      if (!a.has_kx) {
+        for (int s = 0; s < 2; ++s) {
+          uint4* kp = reinterpret_cast<uint4*>(sKV + s * tile_bytes + 2 * 8192 + x * 32);
+          kp[sw] = make_uint4(one2, 0, 0, 0);
+          kp[sw ^ 1] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long u_begin, u_end;
+  w7_unit_range(a.units, u_begin, u_end);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, tt = 0;
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+        const int us = it & 1;
+        mbar_wait(&qdo_empty[us], ((it >> 1) & 1) ^ 1);
+        uint8_t* sQ = sQdO + us * unit_bytes;
+        uint8_t* sDO = sQ + a.qb_bytes;
+        uint8_t* sE = sDO + a.qb_bytes;
+        mbar_expect_tx(&qdo_full[us], 2 * NQ * W7_ROWB + NQ * W7_XROWB);
+        const int row0 = b * SEQ;
+        tma_load_2d(sQ, &tm_q_full, &qdo_full[us], h * W7_HD, row0);
+        tma_load_2d(sDO, &tm_do_full, &qdo_full[us], h * W7_HD, row0);
+        tma_load_2d(sE, &tm_e, &qdo_full[us], 0, (int)(((long long)b * a.heads + h) * SEQ));
+        for (int t = 0; t < 2; ++t, ++tt) {
+          const int ts = tt & 1;
+          mbar_wait(&kv_empty[ts], ((tt >> 1) & 1) ^ 1);
+          uint8_t* sK = sKV + ts * tile_bytes;
+          mbar_expect_tx(&kv_full[ts], 2 * 8192 + (a.has_kx ? 4096 : 0));
+          tma_load_2d(sK, &tm_kv_tile, &kv_full[ts], C + h * W7_HD, row0 + t * W7_TILE);
+          tma_load_2d(sK + 8192, &tm_kv_tile, &kv_full[ts], 2 * C + h * W7_HD, row0 + t * W7_TILE);
+          if (a.has_kx) tma_load_2d(sK + 2 * 8192, &tm_kx, &kv_full[ts], 0, (b % a.nwin) * SEQ + t * W7_TILE);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_ts = make_idesc_bf16(128, W7_HD, 0, 1);
+      const uint32_t idesc_dq = make_idesc_bf16(128, W7_HD, 1, 1);
+      const uint32_t idesc_c96 = make_idesc_bf16(128, 96, 0, 0), idesc_c16 = make_idesc_bf16(128, 16, 0, 0);
+      const uint64_t desc_vx = make_smem_desc(smem_u32(sVx), 16, 256, 6);
+      uint32_t it = 0, tt = 0;
+      uint32_t nuse0 = 0, nuse1 = 0;          // completed uses of buffer 0 / 1 (barrier phases)
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int us = it & 1;
+        mbar_wait(&qdo_full[us], (it >> 1) & 1);
+        mbar_wait(dq_free, (it & 1) ^ 1);
+        const uint32_t q_addr = smem_u32(sQdO + us * unit_bytes);
+        const uint32_t do_addr = q_addr + a.qb_bytes;
+        const uint32_t e_addr = do_addr + a.qb_bytes;
+        for (int t = 0; t < 2; ++t, ++tt) {
+          const int ts = tt & 1;
+          mbar_wait(&kv_full[ts], (tt >> 1) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sKV + ts * tile_bytes);
+          const uint32_t v_addr = k_addr + 8192;
+          const uint64_t desc_kx = make_smem_desc(v_addr + 8192, 16, 256, 6);
+          // scores of one chunk: S^T = [K_t | kx] [Q_c | e_c]^T and dP^T = [V_t | vx] [dO_c | e_c]^T into buffer `buf`
+          auto mma1 = [&](int c, int buf) {
+            const uint32_t idesc = c < 2 ? idesc_c96 : idesc_c16;
+            const uint32_t ds_ = tmem_base + buf * W7B2_BUF, dp_ = ds_ + W7B2_CH;
+            const uint32_t qo = c * W7B2_CH * W7_ROWB, eo = c * W7B2_CH * W7_XROWB;
+            const uint64_t desc_e = make_smem_desc(e_addr + eo, 16, 256, 6);
+#pragma unroll
+            for (int k = 0; k < W7_HD / 16; ++k)
+              umma_bf16_ss(ds_, make_smem_desc(k_addr + k * 32, 16, 512, 4), make_smem_desc(q_addr + qo + k * 32, 16, 512, 4), idesc, k > 0);
+            umma_bf16_ss(ds_, desc_kx, desc_e, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < W7_HD / 16; ++k)
+              umma_bf16_ss(dp_, make_smem_desc(v_addr + k * 32, 16, 512, 4), make_smem_desc(do_addr + qo + k * 32, 16, 512, 4), idesc, k > 0);
+            umma_bf16_ss(dp_, desc_vx, desc_e, idesc, 1);
+            umma_commit(&s_ready[buf]);
+          };
+          // dV_t += P^T_c dO_c ; dK_t += dS^T_c Q_c : K-steps of 16 queries; packed operands of warp group g at [48 g, 48 g + 24)
+          auto mma_dvk = [&](int c, int buf, uint32_t& acc) {
+            const uint32_t ps = tmem_base + buf * W7B2_BUF, pd = ps + W7B2_CH;
+            const int nsteps = c < 2 ? 6 : 1;
+            for (int s = 0; s < nsteps; ++s) {
+              const uint32_t pc = (s < 3 ? 0 : 48) + (s % 3) * 8;
+              const uint32_t ro = (c * W7B2_CH + s * 16) * W7_ROWB;     // 16 query rows = 1024 bytes
+              umma_bf16_ts(tmem_base + W7B2_DV, ps + pc, make_smem_desc(do_addr + ro, 16, 512, 4), idesc_ts, acc);
+              umma_bf16_ts(tmem_base + W7B2_DK, pd + pc, make_smem_desc(q_addr + ro, 16, 512, 4), idesc_ts, acc);
+              acc = 1;
+            }
+          };
+          uint32_t acc = 0;
+          mma1(0, 0);
+          mma1(1, 1);
+          mbar_wait(&p_ready[0], nuse0 & 1); ++nuse0;
+          mbar_wait(acc_free, (tt & 1) ^ 1);            // previous tile's dV / dK have been read
+          tc_fence_after();
+          mma_dvk(0, 0, acc);
+          mma1(2, 0);                                   // executes after the dV/dK steps that read buffer 0
+          mbar_wait(&p_ready[1], nuse1 & 1); ++nuse1;
+          tc_fence_after();
+          mma_dvk(1, 1, acc);
+          mbar_wait(&p_ready[0], nuse0 & 1); ++nuse0;
+          tc_fence_after();
+          mma_dvk(2, 0, acc);
+          umma_commit(dvk_done);
+          if (a.dump_ds) {
+            const int grow = (int)((((long long)u % a.batch) * a.heads + (u / a.batch)) * SEQ) + t * W7_TILE;
+            for (int q = 0; q < 4; ++q) tma_store_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
+            tma_store_commit();
+          }
+          const uint32_t ds_addr = smem_u32(sDS);
+          for (int mq = 0; mq < 2; ++mq)           // dQ[mq] += dS K_t   (K = 128 keys of this tile; rows >= 98 of dS^T are zero)
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_ss(tmem_base + W7B2_DQ + mq * W7_HD, make_smem_desc(ds_addr + mq * 2 * 16384 + ks * 2048, 16384, 1024, 2),
+                           make_smem_desc(k_addr + ks * 1024, 16, 512, 4), idesc_dq, (t > 0 || ks > 0) ? 1u : 0u);
+          if (a.dump_ds) tma_store_wait_read();     // (the dQ products above were only issued; the stores finish reading first)
+          umma_commit(mma2_done);
+          umma_commit(&kv_empty[ts]);
+          if (t == 1) umma_commit(&qdo_empty[us]);
+        }
+      }
+      if (a.dump_ds) tma_store_wait_all();
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool valid = r < W7_TILE;
+    uint8_t* ds_row = sDS + (r >> 3) * 1024 + (r & 7) * 128;
+    const int rsw = r & 7;
+    int cur_h = -1;
+    uint32_t it = 0, tt = 0;
+    uint32_t nuse0 = 0, nuse1 = 0;
+    for (long long u = u_begin; u < u_end; ++u, ++it) {
+      const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+      if (h != cur_h) {
+        named_bar_sync(1, 256);
+        const float4* src = reinterpret_cast<const float4*>(a.table_t + (long long)h * a.table_ld);
+        for (int x = tid; x < a.table_ld / 4; x += 256) reinterpret_cast<float4*>(sTable)[x] = __ldg(src + x);
+        cur_h = h;
+        named_bar_sync(1, 256);
+      }
+      for (int t = 0; t < 2; ++t, ++tt) {
+        const int j = t * W7_TILE + (valid ? r : 0);
+        const float* tbj = sTable + (a.code_off - ((j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7)));
+#define W7B2_PUBLISH(BUF)                                                          \
+        tmem_st_wait();                                                            \
+        fence_proxy_async();                                                       \
+        tc_fence_before();                                                         \
+        __syncwarp();                                                              \
+        if (lane == 0) mbar_arrive(&p_ready[BUF]);
+        // the previous tile's dQ products (which read the shared dS^T tile) are ordered before this tile's first
+        // score MMA, so s_ready also says the tile may be overwritten
+        // ---- chunk 0: queries [0, 96) in buffer 0
+        mbar_wait(&s_ready[0], nuse0 & 1); ++nuse0;
+        tc_fence_after();
+        if (grp == 0) w7_bwd2_body<0>(taddr, taddr + W7B2_CH, tbj, ds_row, rsw, valid);
+        else w7_bwd2_body<48>(taddr + 48, taddr + W7B2_CH + 48, tbj, ds_row, rsw, valid);
+        W7B2_PUBLISH(0)
+        // ---- chunk 1: queries [96, 192) in buffer 1
+        mbar_wait(&s_ready[1], nuse1 & 1); ++nuse1;
+        tc_fence_after();
+        if (grp == 0) w7_bwd2_body<96>(taddr + W7B2_BUF, taddr + W7B2_BUF + W7B2_CH, tbj, ds_row, rsw, valid);
+        else w7_bwd2_body<144>(taddr + W7B2_BUF + 48, taddr + W7B2_BUF + W7B2_CH + 48, tbj, ds_row, rsw, valid);
+        W7B2_PUBLISH(1)
+        // ---- chunk 2: queries [192, 196) (+ zero padding up to 208) in buffer 0, warp group 0 only
+        mbar_wait(&s_ready[0], nuse0 & 1); ++nuse0;
+        tc_fence_after();
+        if (grp == 0) {
+          uint32_t v4[4], w4[4], pk[2], dk[2];
+          tmem_ld_32x4(taddr, v4); tmem_ld_32x4(taddr + W7B2_CH, w4); tmem_ld_wait();
+          w7_bwd_chunk<192, 4>(v4, w4, tbj, pk, dk);
+          const uint32_t zp[8] = {pk[0], pk[1], 0, 0, 0, 0, 0, 0}, zd[8] = {dk[0], dk[1], 0, 0, 0, 0, 0, 0};
+          tmem_st_32x8(taddr, zp); tmem_st_32x8(taddr + W7B2_CH, zd);
+          if (valid) w7_ds_store<192>(ds_row, rsw, dk[0], dk[1], 0, 0);
+        }
+        W7B2_PUBLISH(0)
+
+        mbar_wait(dvk_done, tt & 1);
+        tc_fence_after();
+        {
+          // dV rows by warp group 0, dK rows by warp group 1
+          uint32_t o[32];
+          tmem_ld_32x32(taddr + (grp ? W7B2_DK : W7B2_DV), o);
+          tmem_ld_wait();
+          if (valid) {
+            uint4* g = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * SEQ + j) * (3 * C) + (grp ? 1 : 2) * C + h * W7_HD);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              g[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8]), __uint_as_float(o[q * 8 + 1])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5])),
+                                pack_bf16(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7])));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        if (t == 1) {
+          // dQ of the whole unit (both key tiles accumulated); query row i = grp*128 + r
+          mbar_wait(mma2_done, tt & 1);
+          tc_fence_after();
+          const int i = grp * 128 + r;
+          if (grp * 128 + quarter * 32 < SEQ) {
+            uint32_t oq[32];
+            tmem_ld_32x32(taddr + W7B2_DQ + grp * W7_HD, oq);
+            tmem_ld_wait();
+            if (i < SEQ) {
+              uint4* gq = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * SEQ + i) * (3 * C) + h * W7_HD);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                gq[q] = make_uint4(pack_bf16(__uint_as_float(oq[q * 8]) * a.q_scale, __uint_as_float(oq[q * 8 + 1]) * a.q_scale),
+                                   pack_bf16(__uint_as_float(oq[q * 8 + 2]) * a.q_scale, __uint_as_float(oq[q * 8 + 3]) * a.q_scale),
+                                   pack_bf16(__uint_as_float(oq[q * 8 + 4]) * a.q_scale, __uint_as_float(oq[q * 8 + 5]) * a.q_scale),
+                                   pack_bf16(__uint_as_float(oq[q * 8 + 6]) * a.q_scale, __uint_as_float(oq[q * 8 + 7]) * a.q_scale));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // dTable[(code_i - code_j + off), h] += sum_b dS^T[b, h, j, i]   (bf16 dS^T, fp32 accumulation).
 // One thread per 8 consecutive queries of one key row (16-byte loads), 256-thread blocks over the flattened
 // (key row, query octet) index; grid = (position blocks, heads, batch splits); static 7x7 codes.
@@ -972,7 +1305,9 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   const size_t smem = 1024 + 2 * (2 * (size_t)a.qb_bytes + a.eb_bytes) + 2 * (2 * 8192 + 4096) + 4096 + (size_t)a.n_mq * 2 * 16384 +
                       (size_t)a.table_ld * 4 + 22 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_bwd: %zu bytes of shared memory needed", smem);
-  auto kern = a.seq == 196 ? attn_w7_bwd_kernel<196> : attn_w7_bwd_kernel<98>;
+  static int gen2 = -1;
+  if (gen2 < 0) { const char* ev = getenv("CLOVER_B200_W7_BWD2"); gen2 = ev ? atoi(ev) : 1; }
+  auto kern = a.seq == 196 ? (gen2 ? attn_w7_bwd2_kernel : attn_w7_bwd_kernel<196>) : attn_w7_bwd_kernel<98>;
   static size_t smem_set[2] = {0, 0};
   if (smem > smem_set[a.seq == 196]) {
     CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

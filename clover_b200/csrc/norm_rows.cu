@@ -32,6 +32,7 @@ struct LnrArgs {
   const float* dres; float* dx;
   __nv_bfloat16* dx16; int dx16_mapped;
   float* dgamma; float* dbeta;
+  float* dxsum;                  // [C] column sums of the final dx (bias gradient of the nn.Linear that produced x's input)
 };
 
 template <bool BF>
@@ -103,18 +104,20 @@ __global__ void __launch_bounds__(256) lnr_fwd_kernel(LnrArgs a) {
   }
 }
 
-template <int V, int L, bool XB, bool DYB>
+template <int V, int L, bool XB, bool DYB, bool DXS>
 __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs a) {
   constexpr int G = 32 / L;
-  extern __shared__ float red[];          // [2][C]: dgamma | dbeta partials of this CTA
+  extern __shared__ float red[];          // [3][C]: dgamma | dbeta | dx column sums of this CTA
   const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L;
   const unsigned warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
   const float inv_c = 1.0f / (float)a.C;
-  for (int c = threadIdx.x; c < 2 * a.C; c += blockDim.x) red[c] = 0.f;
-  float4 dg[V], db[V];
+  for (int c = threadIdx.x; c < 3 * a.C; c += blockDim.x) red[c] = 0.f;
+  float4 dg[V], db[V], ds[DXS ? V : 1];
 #pragma unroll
   for (int j = 0; j < V; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < (DXS ? V : 1); ++j) ds[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (unsigned r0 = warp_global * G; r0 < a.rows; r0 += nwarps * G) {
     const unsigned s = r0 + grp;
@@ -159,10 +162,11 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
       o.z = fmaf(rs, d[j].z - s2 - xh[j].z * s1, rr[j].z); o.w = fmaf(rs, d[j].w - s2 - xh[j].w * s1, rr[j].w);
       if (a.dx) *reinterpret_cast<float4*>(a.dx + (size_t)s * a.C + c) = o;
       if (a.dx16) lnr_st<true>(a.dx16, (size_t)crow * a.C + c, o);
+      if (DXS) { ds[j].x += o.x; ds[j].y += o.y; ds[j].z += o.z; ds[j].w += o.w; }
     }
   }
 
-  if (!a.dgamma) return;
+  if (!a.dgamma && !DXS) return;
   // fold the row groups of the warp, then the CTA's warps through shared memory, then one atomic per column
 #pragma unroll
   for (int j = 0; j < V; ++j) {
@@ -172,6 +176,10 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
       dg[j].z += __shfl_xor_sync(0xffffffffu, dg[j].z, o); dg[j].w += __shfl_xor_sync(0xffffffffu, dg[j].w, o);
       db[j].x += __shfl_xor_sync(0xffffffffu, db[j].x, o); db[j].y += __shfl_xor_sync(0xffffffffu, db[j].y, o);
       db[j].z += __shfl_xor_sync(0xffffffffu, db[j].z, o); db[j].w += __shfl_xor_sync(0xffffffffu, db[j].w, o);
+      if (DXS) {
+        ds[j].x += __shfl_xor_sync(0xffffffffu, ds[j].x, o); ds[j].y += __shfl_xor_sync(0xffffffffu, ds[j].y, o);
+        ds[j].z += __shfl_xor_sync(0xffffffffu, ds[j].z, o); ds[j].w += __shfl_xor_sync(0xffffffffu, ds[j].w, o);
+      }
     }
   }
   __syncthreads();
@@ -182,12 +190,19 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
       atomicAdd(red + c, dg[j].x); atomicAdd(red + c + 1, dg[j].y); atomicAdd(red + c + 2, dg[j].z); atomicAdd(red + c + 3, dg[j].w);
       atomicAdd(red + a.C + c, db[j].x); atomicAdd(red + a.C + c + 1, db[j].y);
       atomicAdd(red + a.C + c + 2, db[j].z); atomicAdd(red + a.C + c + 3, db[j].w);
+      if (DXS) {
+        atomicAdd(red + 2 * a.C + c, ds[j].x); atomicAdd(red + 2 * a.C + c + 1, ds[j].y);
+        atomicAdd(red + 2 * a.C + c + 2, ds[j].z); atomicAdd(red + 2 * a.C + c + 3, ds[j].w);
+      }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    atomicAdd(a.dgamma + c, red[c]);
-    atomicAdd(a.dbeta + c, red[a.C + c]);
+    if (a.dgamma) {
+      atomicAdd(a.dgamma + c, red[c]);
+      atomicAdd(a.dbeta + c, red[a.C + c]);
+    }
+    if (DXS) atomicAdd(a.dxsum + c, red[2 * a.C + c]);
   }
 }
 
@@ -211,6 +226,16 @@ static bool lnr_shape(int C, int& V, int& L) {
   else if (L == 32 && V == 4) KERNEL<4, 32, XB, OB> __VA_ARGS__;              \
   else if (L == 32 && V == 6) KERNEL<6, 32, XB, OB> __VA_ARGS__;              \
   else KERNEL<8, 32, XB, OB> __VA_ARGS__;
+
+#define LNR_SHAPES_B(XB, OB, S, ...)                                          \
+  if (L == 8 && V == 3) lnr_bwd_kernel<3, 8, XB, OB, S> __VA_ARGS__;          \
+  else if (L == 8 && V == 4) lnr_bwd_kernel<4, 8, XB, OB, S> __VA_ARGS__;     \
+  else if (L == 16 && V == 3) lnr_bwd_kernel<3, 16, XB, OB, S> __VA_ARGS__;   \
+  else if (L == 16 && V == 4) lnr_bwd_kernel<4, 16, XB, OB, S> __VA_ARGS__;   \
+  else if (L == 32 && V == 3) lnr_bwd_kernel<3, 32, XB, OB, S> __VA_ARGS__;   \
+  else if (L == 32 && V == 4) lnr_bwd_kernel<4, 32, XB, OB, S> __VA_ARGS__;   \
+  else if (L == 32 && V == 6) lnr_bwd_kernel<6, 32, XB, OB, S> __VA_ARGS__;   \
+  else lnr_bwd_kernel<8, 32, XB, OB, S> __VA_ARGS__;
 
 #define LNR_DISPATCH(KERNEL, xb, ob, ...)                                     \
   if (xb) { if (ob) { LNR_SHAPES(KERNEL, true, true, __VA_ARGS__) } else { LNR_SHAPES(KERNEL, true, false, __VA_ARGS__) } } \
@@ -264,8 +289,17 @@ extern "C" int clv_lnr_bwd(const clv_lnr_desc_t* d, const clv_lnr_bwd_t* b, void
   if (a.rows == 0) return 0;
   const int rows_per_block = 8 * (32 / L);
   const long long blocks = std::min<long long>(((long long)a.rows + rows_per_block - 1) / rows_per_block, (long long)num_sms() * 2);
-  const size_t smem = 2 * (size_t)a.C * sizeof(float);
+  const size_t smem = 3 * (size_t)a.C * sizeof(float);
   const bool xb = d->x_is_bf16 != 0, dyb = b->dy_is_bf16 != 0;
-  LNR_DISPATCH(lnr_bwd_kernel, xb, dyb, <<<(int)blocks, 256, smem, stream>>>(a));
+  a.dxsum = b->dxsum;
+  if (a.dxsum) {
+    // fp32 residual stream, bf16 dy: the Swin block configuration (the only producer of a fused bias gradient)
+    CLV_REQUIRE(!xb && dyb && (b->dx || b->dx_bf16), "lnr_bwd: dxsum needs fp32 x, bf16 dy and a dx output");
+    LNR_SHAPES_B(false, true, true, <<<(int)blocks, 256, smem, stream>>>(a))
+  } else if (xb) {
+    if (dyb) { LNR_SHAPES_B(true, true, false, <<<(int)blocks, 256, smem, stream>>>(a)) } else { LNR_SHAPES_B(true, false, false, <<<(int)blocks, 256, smem, stream>>>(a)) }
+  } else {
+    if (dyb) { LNR_SHAPES_B(false, true, false, <<<(int)blocks, 256, smem, stream>>>(a)) } else { LNR_SHAPES_B(false, false, false, <<<(int)blocks, 256, smem, stream>>>(a)) }
+  }
   return after_launch("lnr_bwd_kernel");
 }

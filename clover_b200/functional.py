@@ -65,21 +65,23 @@ def _wgrad(dy16, x16, out_features, in_features):
 _GRAD16 = [None]
 
 
-def _publish_grad16(t32, t16):
-    _GRAD16[0] = (t32, t32._version, t16)
+def _publish_grad16(t32, t16, colsum=None):
+    _GRAD16[0] = (t32, t32._version, t16, colsum)
 
 
-def _grad_bf16(t):
-    """bf16 copy of gradient t (fp32 [T, C]); reuses the copy published by the producing kernel when there is one."""
+def _grad_bf16(t, want_colsum=False):
+    """bf16 copy of gradient t (fp32 [T, C]); reuses the copy (and its column sums, the bias gradient of the layer
+    that produced t's forward value) published by the producing kernel when there is one."""
     if t.dtype == BF16:
-        return t
+        return (t, None) if want_colsum else t
     ent, _GRAD16[0] = _GRAD16[0], None
     if ent is not None:
-        t32, ver, t16 = ent
+        t32, ver, t16, cs = ent
         if (t32.data_ptr() == t.data_ptr() and t32.numel() == t.numel() and t.is_contiguous() and t._version == ver
                 and t32._version == ver):
-            return t16.view(t.shape)
-    return ops.to_bf16(t)
+            return (t16.view(t.shape), cs) if want_colsum else t16.view(t.shape)
+    t16 = ops.to_bf16(t)
+    return (t16, None) if want_colsum else t16
 
 
 def _colsum(x, n):
@@ -356,15 +358,16 @@ class SwinBlockFn(torch.autograd.Function):
         dev = x.device
         mean1, rstd1, mean2, rstd2 = stats[:rows], stats[rows:2 * rows], stats[2 * rows:2 * rows + T], stats[2 * rows + T:]
         dout = dout.contiguous()
-        small = _zeros(4 * C + table.numel(), dev)
+        small = _zeros(6 * C + table.numel(), dev)
         dg1, db1, dg2, db2 = small[:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
-        dtable = small[4 * C:].view_as(table)
+        dtable = small[6 * C:].view_as(table)
         # ---- MLP branch
-        dy16 = _grad_bf16(dout)
+        dy16, dB2 = _grad_bf16(dout, want_colsum=True)
         dpre = torch.empty(T, Hd, dtype=BF16, device=dev)
         ops.gemm(dy16, w2, dpre, b_t=True, gelu_pre=pre)
         dW2 = _wgrad(dy16, act, C, Hd)
-        dB2 = _colsum(dy16, C)
+        if dB2 is None:
+            dB2 = _colsum(dy16, C)
         dh2 = dy16                                            # reuse the buffer: [T, C] bf16
         ops.gemm(dpre, w1, dh2, b_t=True)
         dW1 = _wgrad(dpre, h2, Hd, C)
@@ -373,9 +376,11 @@ class SwinBlockFn(torch.autograd.Function):
         # ---- LN2 backward: d x_mid = dout + LN2'(dh2); bf16 copy emitted in window order for proj
         dmid = torch.empty(T, C, dtype=F32, device=dev)
         dmid_w = (torch.zeros if wg.padded else torch.empty)(rows, C, dtype=BF16, device=dev)
+        dBp = None
         if rmap is not None:
+            dBp = small[4 * C:5 * C]                          # proj bias gradient = column sums of d x_mid
             ops.lnr_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, dx=dmid, dres=dout, dx_bf16=dmid_w, row_map=rmap,
-                        dx_bf16_mapped=True, dgamma=dg2, dbeta=db2)
+                        dx_bf16_mapped=True, dgamma=dg2, dbeta=db2, dxsum=dBp)
         else:
             ops.layernorm_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, rows=T, dx=dmid, dres=dout, dx_copy=dmid_w,
                               copy_window=wg, dgamma=dg2, dbeta=db2)
@@ -383,7 +388,8 @@ class SwinBlockFn(torch.autograd.Function):
         dao = torch.empty(rows, C, dtype=BF16, device=dev)
         ops.gemm(dmid_w, wp, dao, b_t=True)
         dWp = _wgrad(dmid_w, ao, C, C)
-        dBp = _colsum(dmid_w, C)
+        if dBp is None:
+            dBp = _colsum(dmid_w, C)
         dqkv = torch.empty(rows, 3 * C, dtype=BF16, device=dev)
         ops.attention_bwd(qkv, ao, dao, lse, wg.B * wg.nwin, wg.N, heads, hd, dqkv, scale, dbias_table=dtable, w7=wg.w7,
                           bias_table=table, rel_code=code, code_off=code_off, region=region)
@@ -394,9 +400,10 @@ class SwinBlockFn(torch.autograd.Function):
         # ---- LN1 backward through the window gather, accumulated onto d x_mid in place
         if rmap is not None:
             dmid16 = dmid_w                                   # reuse: [T, C] bf16 (rows == T when unpadded)
+            dx_sum = small[5 * C:6 * C]                       # = fc2 bias gradient of the block that produced x
             ops.lnr_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, dx=dmid, dres=dmid, dx_bf16=dmid16, row_map=rmap,
-                        dy_mapped=True, dgamma=dg1, dbeta=db1)
-            _publish_grad16(dmid, dmid16)
+                        dy_mapped=True, dgamma=dg1, dbeta=db1, dxsum=dx_sum)
+            _publish_grad16(dmid, dmid16, dx_sum)
         else:
             ops.layernorm_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, rows=rows, dx=dmid, dres=dmid, dgamma=dg1, dbeta=db1,
                               window=wg)
@@ -437,6 +444,7 @@ class PatchEmbedFn(torch.autograd.Function):
     def backward(ctx, dout):
         B, D, Hp, Wp, C = ctx.dims
         dout = dout.contiguous()
+        _GRAD16[0] = None                 # the published bf16 copy of d(tokens) has no consumer here
         T = dout.shape[0]
         dev = dout.device
         dgn = dbn = dtok = None

@@ -297,7 +297,7 @@ def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_map
 
 @_profiled("ln_bwd", _lnr_tag)
 def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, row_map=None, dy_mapped=False,
-            dx_bf16_mapped=False, dgamma=None, dbeta=None):
+            dx_bf16_mapped=False, dgamma=None, dbeta=None, dxsum=None):
     _need_cuda(x, gamma, dy)
     for t, n in ((dy, "dy"), (dx, "dx"), (dres, "dres"), (dx_bf16, "dx_bf16")):
         if t is not None and (t.shape != x.shape or not t.is_contiguous()):
@@ -308,7 +308,7 @@ def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=
     b = LnrBwd()
     b.dy, b.dy_is_bf16, b.dy_mapped = _ptr(dy), _is_bf16(dy), int(dy_mapped)
     b.dres, b.dx, b.dx_bf16, b.dx_bf16_mapped = _ptr(dres), _ptr(dx), _ptr(dx_bf16), int(dx_bf16_mapped)
-    b.dgamma, b.dbeta = _ptr(dgamma), _ptr(dbeta)
+    b.dgamma, b.dbeta, b.dxsum = _ptr(dgamma), _ptr(dbeta), _ptr(dxsum)
     _lib.check(_lib.load().clv_lnr_bwd(C.byref(d), C.byref(b), _stream()), "clv_lnr_bwd")
 
 

@@ -146,6 +146,8 @@ class CloverPretrain(BaseRecognizer):
                                       "(ssl_head + mlm_head + mlm_ssl_head V/T, symmetry_rank, use_Cmask)")
         Bt, L = token_ids.shape
         H = self.multimodal_backbone.hidden_size
+        if self.batch_passes and v_token_mask is not None and imgs.shape[0] == Bt:
+            return self._forward_train_batched(imgs, token_ids, text_mask, mlm_label, v_token_mask, Bt, L, H)
         # ---- clean video + clean text ---------------------------------------------------- :91-102
         v_tok, (B, T, h, w) = self.backbone.forward_tokens(imgs)                    # fp32 [B*T*hw, C]
         S = h * w
@@ -169,6 +171,42 @@ class CloverPretrain(BaseRecognizer):
         tm_emb = self.ssl_head.forward_text(T_m)
         m_tmf = self.mlm_ssl_T_head(t_last[:, 0])
         vm_emb = self.ssl_head.forward_vision_tokens(vm_tok, B, T * S)
+        g_v, g_t, g_tm, g_vmf, g_vm, g_tmf = gather_stacked([v_emb, t_emb, tm_emb, m_vmf, vm_emb, m_tmf])
+        losses.update(self.ssl_loss.forward_gathered(g_v, g_t, g_tm, g_vmf))
+        l2 = self.ssl_loss.forward_gathered(g_t, g_v, g_vm, g_tmf)
+        losses["v_nce_loss"] = l2.pop("nce_loss")
+        if self.ssl_loss.use_rank:
+            losses["rank_v_vm_loss"] = l2.pop("rank_t_tm_loss")
+        return losses
+
+    # The reference runs every encoder twice per step (clean / masked video :91,:113; clean / masked text :96,:110;
+    # two fusion passes :117-121).  No layer on the path couples samples (LayerNorm only; ln=True / text_bn=False
+    # heads), so the two passes are one pass over a doubled batch: [masked ; clean] clips (an all-zero token mask
+    # leaves the patch embedding untouched, swin_transformer_3d.py:222-230), [clean ; masked] captions, and the
+    # fusion pairs (masked video, clean text) ; (clean video, masked text) line up without any reshuffle.  Same
+    # arithmetic per sample, half the launches, and every parameter gets ONE gradient instead of two accumulated.
+    batch_passes = True
+
+    def _forward_train_batched(self, imgs, token_ids, text_mask, mlm_label, v_token_mask, B, L, H):
+        imgs2 = torch.cat([imgs, imgs], 0)
+        vmask2 = torch.cat([v_token_mask, torch.zeros_like(v_token_mask)], 0)
+        tok2, (B2, T, h, w) = self.backbone.forward_tokens(imgs2, vmask2)           # [masked ; clean] fp32 [2B*T*hw, C]
+        S = h * w
+        ids_clean = torch.where(mlm_label == -100, token_ids, mlm_label)
+        ids2 = torch.cat([ids_clean, token_ids], 0)                                 # [clean ; masked]
+        tmask2 = torch.cat([text_mask, text_mask], 0)
+        T2 = self.text_backbone(ids2, tmask2)["last_hidden_state"]                  # bf16 (2B, L, H)
+        vemb2 = self.ssl_head.forward_vision_tokens(tok2, B2, T * S)                # (2B, E): [vm ; v]
+        temb2 = self.ssl_head.forward_text(T2)                                      # (2B, E): [t ; tm]
+        vm_emb, v_emb = vemb2.split(B)
+        t_emb, tm_emb = temb2.split(B)
+        f2, _ = self.multimodal_backbone.forward_tokens(tok2, B2, T, S, T2, tmask2)  # (vm, T_e) ; (v, T_m)
+        t_last = f2[B:, T * S:]                                                     # (B, L, H) of the masked-text pass
+        losses = dict()
+        gamma = getattr(self.mlm_loss_func, "gamma", 0.0) if self.mlm_loss_func is not None else 0.0
+        losses["mlm_loss"] = self.mlm_head.focal_loss(t_last.reshape(B * L, H), mlm_label.reshape(-1), gamma=gamma)
+        m_vmf = self.mlm_ssl_V_head(f2[:B, T * S])                                  # fused text-CLS slot of the masked-video pass
+        m_tmf = self.mlm_ssl_T_head(t_last[:, 0])
         g_v, g_t, g_tm, g_vmf, g_vm, g_tmf = gather_stacked([v_emb, t_emb, tm_emb, m_vmf, vm_emb, m_tmf])
         losses.update(self.ssl_loss.forward_gathered(g_v, g_t, g_tm, g_vmf))
         l2 = self.ssl_loss.forward_gathered(g_t, g_v, g_vm, g_tmf)

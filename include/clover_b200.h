@@ -128,6 +128,8 @@ typedef struct {
   float* dx;                         /* fp32 [rows, C] or NULL */
   void* dx_bf16; int dx_bf16_mapped; /* optional bf16 copy of dx, at row m(s) when mapped (norm2: proj operand) */
   float* dgamma; float* dbeta;       /* [C] fp32, ACCUMULATED (caller zero-fills); both or neither */
+  float* dxsum;                      /* [C] fp32, ACCUMULATED column sums of dx, or NULL: the bias gradient of the nn.Linear
+                                        whose output gradient this dx is (fc2 / proj of the Swin block); fp32 x + bf16 dy only */
 } clv_lnr_bwd_t;
 
 int clv_lnr_supported(int C);

@@ -198,14 +198,19 @@ def test_lnr_window_map(ops, dims, Bc, C, shifted):
     assert torch.equal(y.cpu(), y0.cpu()[gi])
     # norm1 backward: dy in window order, accumulated onto the residual gradient in place
     dy, dres = rnd(T, C, seed=4), rnd(T, C, seed=5)
-    (yr * dy.cpu()).sum().backward()
     acc = dres.clone()
     c16 = torch.empty(T, C, dtype=BF16, device="cuda")
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    ops.lnr_bwd(x, g, b, 1e-5, mean, rstd, dy, dx=acc, dres=acc, dx_bf16=c16, row_map=rmap, dy_mapped=True, dgamma=dg, dbeta=db)
+    dyb = dy.to(BF16)
+    xs = torch.zeros(C, device="cuda")
+    ops.lnr_bwd(x, g, b, 1e-5, mean, rstd, dyb, dx=acc, dres=acc, dx_bf16=c16, row_map=rmap, dy_mapped=True, dgamma=dg, dbeta=db,
+                dxsum=xs)
+    xr.grad = None
+    (yr * dyb.float().cpu()).sum().backward()
     want = xr.grad + dres.cpu()
     assert rel(acc, want) < 1e-4
     assert torch.equal(c16.cpu(), acc.cpu().to(BF16))
+    assert rel(xs, want.sum(0)) < 1e-4                      # fused column sums (bias gradient of the producing nn.Linear)
     # norm2 backward: dense dy, bf16 copy of dx emitted in window order
     dx = torch.empty(T, C, dtype=F32, device="cuda")
     cw = torch.empty(T, C, dtype=BF16, device="cuda")

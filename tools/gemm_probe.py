@@ -16,6 +16,11 @@ SHAPES = [
     (802816, 128, 512, 0, 0, "br", "o32", 1), (200704, 1024, 256, 0, 0, "bg", "o16", 1),
     (512, 2048, 50176, 1, 1, "", "o32", 4), (2048, 512, 50176, 1, 1, "", "o32", 4), (512, 512, 50176, 1, 1, "", "o32", 18),
     (128, 512, 802816, 1, 1, "", "o32", 74), (8192, 8192, 8192, 0, 0, "", "o16", 1),
+    # split-K sweep for the stage-3 weight gradients (tag: wsweep)
+    (512, 2048, 50176, 1, 1, "", "o32", 9), (512, 2048, 50176, 1, 1, "", "o32", 14), (512, 2048, 50176, 1, 1, "", "o32", 18),
+    (2048, 512, 50176, 1, 1, "", "o32", 9), (2048, 512, 50176, 1, 1, "", "o32", 18),
+    (1536, 512, 50176, 1, 1, "", "o32", 6), (1536, 512, 50176, 1, 1, "", "o32", 12), (1536, 512, 50176, 1, 1, "", "o32", 24),
+    (512, 512, 50176, 1, 1, "", "o32", 9), (512, 512, 50176, 1, 1, "", "o32", 37),
 ]
 
 
