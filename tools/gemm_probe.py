@@ -10,6 +10,9 @@ from clover_b200 import ops  # noqa: E402
 BF16, F32 = torch.bfloat16, torch.float32
 # (M, N, K, a_t, b_t, epilogue)  epilogue: b=bias g=gelu(+pre) r=residual fp32 p=gelu' multiply, o16/o32 output, ks = split-K
 SHAPES = [
+    # c3 with clean + masked passes batched (128 clip-passes per launch)
+    (100352, 2048, 512, 0, 0, "bg", "o16", 1), (100352, 2048, 512, 0, 1, "p", "o16", 1), (100352, 512, 2048, 0, 0, "br", "o32", 1),
+    (512, 2048, 100352, 1, 1, "", "o32", 4),
     (50176, 2048, 512, 0, 0, "bg", "o16", 1), (50176, 2048, 512, 0, 1, "p", "o16", 1), (50176, 1536, 512, 0, 0, "b", "o16", 1),
     (50176, 512, 2048, 0, 0, "br", "o32", 1), (50176, 512, 2048, 0, 1, "", "o16", 1), (50176, 512, 512, 0, 0, "br", "o32", 1),
     (802816, 512, 128, 0, 0, "bg", "o16", 1), (802816, 512, 128, 0, 1, "p", "o16", 1), (802816, 384, 128, 0, 0, "b", "o16", 1),
