@@ -24,6 +24,7 @@ class GemmEpilogue(C.Structure):
         ("out_pre", c_vp), ("ld_pre", c_ll), ("gelu_pre", c_vp), ("ld_gelu_pre", c_ll),
         ("act", C.c_int), ("scale_cols", C.c_int), ("scale", C.c_float),
         ("window", C.POINTER(WindowGeom)), ("k_splits", C.c_int), ("accumulate", C.c_int),
+        ("row_scale", c_vp), ("row_scale_rows", c_ll),
     ]
 
 
@@ -72,6 +73,7 @@ class AttnDesc(C.Structure):
         ("batch", C.c_int), ("seq", C.c_int), ("heads", C.c_int), ("head_dim", C.c_int),
         ("bias_table", c_vp), ("table_len", C.c_int), ("rel_code", c_vp), ("code_off", C.c_int),
         ("region", c_vp), ("nwin", C.c_int), ("key_mask", c_vp),
+        ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong), ("drop_offset", C.c_ulonglong),
     ]
 
 
@@ -109,6 +111,11 @@ SIGNATURES = {
     "clv_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_fwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
+    "clv_attention_probs_mean": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp]),
+    "clv_dropout": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, C.c_ulonglong, C.c_ulonglong, c_vp]),
+    "clv_keep_mask": (C.c_int, [c_vp, c_ll, C.c_float, C.c_ulonglong, C.c_ulonglong, c_vp]),
+    "clv_dropout_threshold": (C.c_uint, [C.c_float]),
+    "clv_rows_scale": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_int, c_vp, c_ll, c_vp]),
     "clv_attention_bwd_tc_workspace_bytes": (c_ll, [C.POINTER(AttnDesc), C.c_int]),
     "clv_attention_bwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_attention_w7_fwd_workspace_bytes": (c_ll, [C.POINTER(AttnW7Desc)]),

@@ -32,3 +32,29 @@ def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1
         ssl_loss=dict(type="ExclusiveNCEwithRankingLoss", temperature=0.05, use_rank=True, use_rank_ttm=True,
                       use_rank_trtm=False, margin_ttm=5.0, margin_trtm=10.0),
         symmetry_rank=True, train_cfg=dict(aux_info=aux))
+
+
+def finetune_cfg(task="retrieval", embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024, hidden=768, vocab=30522,
+                 text_layers=12, fusion_layers=3, frames_half=8, bert_dropout=0.0, num_labels=1500, qa_dropout=0.0, **bert):
+    """The model dicts of configs/exp_local/finetune_msrvtt_retrieval.py:22-70 (task='retrieval'),
+    finetune_msrvttQA.py:23-66 (task='video_qa', open-ended head) and finetune_msrvtt_mc.py (task='video_qa_mc',
+    multiple-choice head).  frames_half is mm_backbone.num_frames (must cover T = frames/2)."""
+    base = pretrain_cfg(embed, depths, heads, img_in, hidden, vocab, text_layers, fusion_layers, frames_half, bert_dropout, **bert)
+    cfg = dict(type="CloverFinetune", freeze_stage=None, text_vocab_size=vocab, cls_head=None, itm_head=None,
+               backbone=dict(base["backbone"], mask_token=False), mm_backbone=base["mm_backbone"],
+               text_backbone=base["text_backbone"], train_cfg=dict(aux_info=["token_ids", "segment_ids", "input_mask"]))
+    if task == "retrieval":
+        cfg.update(task="retrieval", separate_test=True, ssl_head=base["ssl_head"],
+                   loss_type=dict(type="NormSoftmaxLoss", cos_sim=True, temperature=0.05),
+                   test_cfg=dict(feature_extraction=False))
+    elif task == "video_qa":
+        cfg.update(task="video_qa", separate_test=False, ssl_head=None, answer_cls=True,
+                   qa_head=dict(type="QA_OE_Head", hidden_dim=hidden, dropout_ratio=qa_dropout, num_labels=num_labels),
+                   loss_type=dict(type="CrossEntropyLoss"))
+    elif task == "video_qa_mc":
+        cfg.update(task="video_qa", separate_test=False, ssl_head=None, answer_cls=True,
+                   qa_head=dict(type="QA_MC_head", hidden_dim=hidden, dropout_ratio=qa_dropout),
+                   loss_type=dict(type="CrossEntropyLoss"))
+    else:
+        raise ValueError(task)
+    return cfg

@@ -27,6 +27,8 @@ struct AttnArgs {
   const float* bias_table; int table_len; const int* rel_code; int code_off;
   const int* region; int nwin;
   const float* key_mask;
+  uint32_t drop_thresh; float drop_inv_keep; unsigned long long drop_seed, drop_offset;   // drop_thresh == 0: off
+  float* probs_mean;             // [batch, seq, seq] (clv_attention_probs_mean)
   // backward
   const __nv_bfloat16* dout; const float* dsum; __nv_bfloat16* dqkv; float q_scale; float* dbias;
 };
@@ -134,6 +136,12 @@ CLV_DEVICE float score_bias(const BiasCtx& c, int i, int j) {
   return b;
 }
 
+// keep / (1 - p) of attention probability (b, h, i, j): element ((b*heads + h)*seq + i)*seq + j of the stream
+CLV_DEVICE float attn_keep(const AttnArgs& a, int bh, int i, int j) {
+  const unsigned long long e = a.drop_offset + ((unsigned long long)bh * a.seq + (unsigned)i) * a.seq + (unsigned)j;
+  return keep_scale(a.drop_seed, e, a.drop_thresh, a.drop_inv_keep);
+}
+
 // shared-memory carve-up helpers ------------------------------------------------------------
 CLV_DEVICE int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -219,6 +227,14 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
       l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+      if (a.drop_thresh) {     // dropout acts on the normalised probabilities; the normaliser l keeps every term
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int j = kc + nt * 8 + q4 * 2;
+          s[nt][0] *= attn_keep(a, bh, i0, j); s[nt][1] *= attn_keep(a, bh, i0, j + 1);
+          s[nt][2] *= attn_keep(a, bh, i1, j); s[nt][3] *= attn_keep(a, bh, i1, j + 1);
+        }
+      }
       mma_p_r<HD>(o, s, sV, kc, ntv, lane);
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -347,6 +363,10 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnArgs a) {
           p2 = b2 <= NEG_BIG ? 0.f : exp2f((s[nt][2] + b2 - lse1) * LOG2E);
           p3 = b3 <= NEG_BIG ? 0.f : exp2f((s[nt][3] + b3 - lse1) * LOG2E);
         }
+        if (a.drop_thresh) {   // dP = dP_dropped * keep / (1 - p)
+          dp[nt][0] *= attn_keep(a, bh, i0, j); dp[nt][1] *= attn_keep(a, bh, i0, j + 1);
+          dp[nt][2] *= attn_keep(a, bh, i1, j); dp[nt][3] *= attn_keep(a, bh, i1, j + 1);
+        }
         s[nt][0] = p0 * (dp[nt][0] - d0); s[nt][1] = p1 * (dp[nt][1] - d0);
         s[nt][2] = p2 * (dp[nt][2] - d1); s[nt][3] = p3 * (dp[nt][3] - d1);
         if (a.dbias && nt < ntv) {
@@ -465,8 +485,14 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(AttnArgs a) {
           p1 = b1 <= NEG_BIG ? 0.f : exp2f((st[nt][1] + b1 - sLse[i + 1]) * LOG2E);
           p2 = b2 <= NEG_BIG ? 0.f : exp2f((st[nt][2] + b2 - sLse[i]) * LOG2E);
           p3 = b3 <= NEG_BIG ? 0.f : exp2f((st[nt][3] + b3 - sLse[i + 1]) * LOG2E);
-          dpt[nt][0] = p0 * (dpt[nt][0] - sD[i]); dpt[nt][1] = p1 * (dpt[nt][1] - sD[i + 1]);
-          dpt[nt][2] = p2 * (dpt[nt][2] - sD[i]); dpt[nt][3] = p3 * (dpt[nt][3] - sD[i + 1]);
+          float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
+          if (a.drop_thresh) {
+            k0 = attn_keep(a, bh, i, j0); k1 = attn_keep(a, bh, i + 1, j0);
+            k2 = attn_keep(a, bh, i, j1); k3 = attn_keep(a, bh, i + 1, j1);
+          }
+          dpt[nt][0] = p0 * (dpt[nt][0] * k0 - sD[i]); dpt[nt][1] = p1 * (dpt[nt][1] * k1 - sD[i + 1]);
+          dpt[nt][2] = p2 * (dpt[nt][2] * k2 - sD[i]); dpt[nt][3] = p3 * (dpt[nt][3] * k3 - sD[i + 1]);
+          p0 *= k0; p1 *= k1; p2 *= k2; p3 *= k3;      // dV uses the dropped probabilities
         } else {
           dpt[nt][0] = dpt[nt][1] = dpt[nt][2] = dpt[nt][3] = 0.f;
         }
@@ -495,6 +521,71 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(AttnArgs a) {
   }
 }
 
+// probs_mean[b, i, :] = mean_h softmax_j(q_i . k_j + additive terms).  One CTA per (query row, batch element); the
+// thread block walks the heads, each thread owning keys tid, tid + blockDim, ...  (evaluation only, tiny).
+template <int HD>
+__global__ void __launch_bounds__(128) attn_probs_mean_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  float* acc = reinterpret_cast<float*>(smem_attn);            // [seq]
+  float* sq = acc + a.seq;                                     // [HD]
+  __shared__ float red[4];
+  const int i = blockIdx.x, b = blockIdx.y, seq = a.seq, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ld = 3LL * a.heads * HD;
+  const __nv_bfloat16* base = a.qkv + (long long)b * seq * ld;
+  for (int j = tid; j < seq; j += blockDim.x) acc[j] = 0.f;
+  const int ci = a.rel_code ? a.rel_code[i] : 0;
+  const int ri = a.region ? a.region[(long long)(b % a.nwin) * seq + i] : 0;
+  for (int h = 0; h < a.heads; ++h) {
+    __syncthreads();
+    if (tid < HD) sq[tid] = __bfloat162float(base[(long long)i * ld + h * HD + tid]);
+    __syncthreads();
+    float sc[4];                                               // seq <= 512 = 4 * 128
+    float mx = NEG_BIG;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = tid + u * 128;
+      sc[u] = NEG_BIG;
+      if (j < seq) {
+        const uint4* kr = reinterpret_cast<const uint4*>(base + (long long)j * ld + (a.heads + h) * HD);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+          const uint4 kv = kr[c];
+          const float2 k0 = unpack_bf16(kv.x), k1 = unpack_bf16(kv.y), k2 = unpack_bf16(kv.z), k3 = unpack_bf16(kv.w);
+          const float* q = sq + c * 8;
+          s += q[0] * k0.x + q[1] * k0.y + q[2] * k1.x + q[3] * k1.y + q[4] * k2.x + q[5] * k2.y + q[6] * k3.x + q[7] * k3.y;
+        }
+        if (a.bias_table) s += a.bias_table[(long long)(ci - a.rel_code[j] + a.code_off) * a.heads + h];
+        if (a.region) s += (a.region[(long long)(b % a.nwin) * seq + j] != ri) ? -100.0f : 0.0f;
+        if (a.key_mask) s += a.key_mask[(long long)b * seq + j];
+        sc[u] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sc[u] = (tid + u * 128 < seq) ? exp2f((sc[u] - mx) * LOG2E) : 0.f;
+      sum += sc[u];
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.0f / ((red[0] + red[1] + red[2] + red[3]) * a.heads);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (tid + u * 128 < seq) acc[tid + u * 128] += sc[u] * inv;
+  }
+  __syncthreads();
+  float* o = a.probs_mean + ((long long)b * seq + i) * seq;
+  for (int j = tid; j < seq; j += blockDim.x) o[j] = acc[j];
+}
+
 int launch_attn_bwd_prep(const void* out, const void* dout, float* dsum, long long rows, int heads, int hd, int seq,
                          cudaStream_t stream) {
   const long long n = rows * heads;
@@ -510,6 +601,7 @@ static int attn_common_checks(const clv_attn_desc_t* d) {
               d->batch, d->seq, d->heads);
   CLV_REQUIRE(!d->bias_table || (d->rel_code && d->table_len > 0), "attention: bias_table needs rel_code/table_len");
   CLV_REQUIRE(!d->region || d->nwin > 0, "attention: region needs nwin");
+  CLV_REQUIRE(d->drop_p >= 0.f && d->drop_p < 1.f, "attention: drop_p must be in [0, 1) (got %f)", (double)d->drop_p);
   return 0;
 }
 
@@ -518,6 +610,10 @@ static void fill_args(AttnArgs& a, const clv_attn_desc_t* d) {
   a.batch = d->batch; a.seq = d->seq; a.heads = d->heads;
   a.bias_table = d->bias_table; a.table_len = d->table_len; a.rel_code = d->rel_code; a.code_off = d->code_off;
   a.region = d->region; a.nwin = d->nwin > 0 ? d->nwin : 1; a.key_mask = d->key_mask;
+  if (d->drop_p > 0.f) {
+    a.drop_thresh = drop_threshold(d->drop_p); a.drop_inv_keep = 1.0f / (1.0f - d->drop_p);
+    a.drop_seed = d->drop_seed; a.drop_offset = d->drop_offset;
+  }
 }
 
 template <typename K>
@@ -581,4 +677,18 @@ extern "C" int clv_attention_bwd(const clv_attn_desc_t* d, const void* qkv, cons
     if (!rc) rc = launch_attn(attn_bwd_dkv_kernel<64>, a, nw, smem_dkv, stream, "attn_bwd_dkv_kernel<64>");
   }
   return rc;
+}
+
+extern "C" int clv_attention_probs_mean(const clv_attn_desc_t* d, const void* qkv, float* probs_mean, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (int rc = attn_common_checks(d)) return rc;
+  CLV_REQUIRE(qkv && probs_mean, "attention_probs_mean: null pointer");
+  CLV_REQUIRE(d->drop_p == 0.f, "attention_probs_mean: evaluation only (drop_p must be 0)");
+  AttnArgs a; fill_args(a, d);
+  a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv); a.probs_mean = probs_mean;
+  const size_t smem = (size_t)(d->seq + d->head_dim) * sizeof(float);
+  dim3 grid(d->seq, d->batch);
+  if (d->head_dim == 32) attn_probs_mean_kernel<32><<<grid, 128, smem, stream>>>(a);
+  else attn_probs_mean_kernel<64><<<grid, 128, smem, stream>>>(a);
+  return after_launch("attn_probs_mean_kernel");
 }

@@ -279,6 +279,7 @@ extern "C" int clv_attention_fwd_tc(const clv_attn_desc_t* d, const void* qkv, v
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CLV_REQUIRE(d && qkv && out && lse, "attention_fwd_tc: null pointer");
   CLV_REQUIRE(d->head_dim == 32 && !d->key_mask, "attention_fwd_tc: head_dim 32 without key mask only");
+  CLV_REQUIRE(d->drop_p == 0.f, "attention_fwd_tc: attention dropout is not supported (attn_drop is 0 in Video Swin)");
   CLV_REQUIRE(d->seq >= 33 && d->seq <= 416, "attention_fwd_tc: seq must be in [33, 416] (got %d)", d->seq);
   CLV_REQUIRE(!d->bias_table || (d->rel_code && d->table_len > 0), "attention_fwd_tc: bias_table needs rel_code");
   AttnTcArgs a{};
@@ -661,6 +662,7 @@ extern "C" int clv_attention_bwd_tc(const clv_attn_desc_t* d, const void* qkv, c
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CLV_REQUIRE(d && qkv && out && dout && lse && dqkv && workspace, "attention_bwd_tc: null pointer");
   CLV_REQUIRE(d->head_dim == 32 && !d->key_mask, "attention_bwd_tc: head_dim 32 without key mask only");
+  CLV_REQUIRE(d->drop_p == 0.f, "attention_bwd_tc: attention dropout is not supported (attn_drop is 0 in Video Swin)");
   CLV_REQUIRE(d->seq >= 33 && d->seq <= 224, "attention_bwd_tc: seq must be in [33, 224] (got %d)", d->seq);
   CLV_REQUIRE(!dbias_table || d->bias_table, "attention_bwd_tc: dbias_table without bias_table");
   AttnTcBwdArgs a{};

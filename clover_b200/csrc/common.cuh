@@ -110,6 +110,24 @@ CLV_DEVICE float gelu_fit_grad(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xx * -0.72134752044448170368f));
   return fmaf(x * 0.39894228040143267794f, e, fmaf(0.5f, th, 0.5f));
 }
+// ------------------------------------------------------------------------------------------
+// counter-based random stream of the dropout kernels: 32 bits = high word of splitmix64(seed * phi + idx).
+// keep iff bits >= p * 2^32.  Restated in numpy by tests/rng_ref.py (bit-exact check).
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t rand_u32(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = idx + seed * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t <= 0.0 ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+}
+CLV_DEVICE float keep_scale(unsigned long long seed, unsigned long long idx, uint32_t thresh, float inv_keep) {
+  return rand_u32(seed, idx) >= thresh ? inv_keep : 0.f;
+}
 CLV_DEVICE uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

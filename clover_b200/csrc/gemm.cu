@@ -46,6 +46,8 @@ struct GemmEpi {
   float scale;
   int use_row_map;
   int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
+  const float* row_scale;   // per row-group factor on (acc + bias) before the residual (DropPath), or nullptr
+  long long row_scale_rows;
   WindowGeom geom;
 };
 
@@ -273,6 +275,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       long long drow = row;
       if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
       const bool row_ok = row < M && drow >= 0;
+      const float rscale = (ep.row_scale && row < M) ? __ldg(ep.row_scale + row / ep.row_scale_rows) : 1.0f;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[EC];
@@ -315,6 +318,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           load_row<EC>(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
 #pragma unroll
           for (int j = 0; j < EC; ++j) v[j] *= gelu_fit_grad(g[j]);
+        }
+        if (ep.row_scale) {
+#pragma unroll
+          for (int j = 0; j < EC; ++j) v[j] *= rscale;
         }
         if (ep.residual) {
           float g[EC];
@@ -439,6 +446,9 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   ep.residual_bf16 = e->residual_is_bf16; ep.out_bf16 = e->out_is_bf16; ep.act = e->act;
   ep.scale_cols = e->scale_cols; ep.scale = e->scale;
   ep.use_row_map = e->window != nullptr;
+  ep.row_scale = e->row_scale;
+  ep.row_scale_rows = e->row_scale_rows > 0 ? e->row_scale_rows : 1;
+  CLV_REQUIRE(!e->row_scale || e->row_scale_rows > 0, "clv_gemm_bf16: row_scale needs row_scale_rows > 0");
   int k_splits = e->k_splits > 0 ? e->k_splits : 1;
   const int num_kb = (K + BK - 1) / BK;
   if (k_splits > num_kb) k_splits = num_kb;
@@ -448,7 +458,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   }
   ep.atomic_out = k_splits > 1 || e->accumulate;
   if (ep.atomic_out) {
-    CLV_REQUIRE(!e->out_is_bf16 && !e->bias && !e->residual && !e->act && !e->gelu_pre && !e->window,
+    CLV_REQUIRE(!e->out_is_bf16 && !e->bias && !e->residual && !e->act && !e->gelu_pre && !e->window && !e->row_scale,
                 "clv_gemm_bf16: split-K / accumulate supports plain fp32 output only");
     if (!e->accumulate)
       CLV_CHECK_CUDA(cudaMemset2DAsync(e->out, e->ld_out * 4, 0, (size_t)N * 4, M, stream));

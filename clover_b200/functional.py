@@ -7,7 +7,7 @@ to a PyTorch implementation of the math.
 """
 import torch
 
-from . import ops
+from . import ops, rng
 from .ops import BF16, F32
 
 # ------------------------------------------------------------------------------------------------
@@ -156,6 +156,38 @@ def gelu(x):
     return GeluFn.apply(x)
 
 
+class DropoutFn(torch.autograd.Function):
+    """y = residual + dropout_p(x) (nn.Dropout semantics: kept elements scaled by 1 / (1 - p)); the mask is a range of
+    the counter-based stream (clover_b200.rng) and is regenerated in backward.  HF BertSelfOutput / BertOutput apply
+    it between the dense layer and the residual add, BertEmbeddings after its LayerNorm (transformers 4.6.1)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p, out_fp32, kind):
+        x = x.contiguous()
+        seed, off = rng.next_stream(x.numel(), kind, x.shape, p)
+        y = torch.empty(x.shape, dtype=F32 if out_fp32 else BF16, device=x.device)
+        ops.dropout(x, y, p, seed, off, residual.contiguous() if residual is not None else None)
+        ctx.meta = (p, seed, off, x.dtype, residual.dtype if residual is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, off, xdt, rdt = ctx.meta
+        dy = dy.contiguous()
+        dx = ops.dropout(dy, torch.empty(dy.shape, dtype=xdt, device=dy.device), p, seed, off) if ctx.needs_input_grad[0] else None
+        dres = None
+        if rdt is not None and ctx.needs_input_grad[1]:
+            dres = dy if dy.dtype == rdt else ops.cast(dy, torch.empty(dy.shape, dtype=rdt, device=dy.device))
+        return dx, dres, None, None, None
+
+
+def dropout(x, p, training, residual=None, out_fp32=False, kind="dropout"):
+    """residual + nn.Dropout(p)(x); identity (plus the residual add folded elsewhere) when inactive."""
+    if not training or p <= 0.0:
+        raise RuntimeError("functional.dropout is for the active case only; callers keep the fused path otherwise")
+    return DropoutFn.apply(x, residual, float(p), out_fp32, kind)
+
+
 def linear(x, weight, bias=None, residual=None, act=None, out_fp32=False, w_override=None):
     return LinearFn.apply(x, weight, bias, residual, act, out_fp32, w_override)
 
@@ -253,21 +285,24 @@ class AttentionFn(torch.autograd.Function):
     """softmax(q k^T + key_mask) v on packed bf16 qkv rows (q pre-scaled by the qkv GEMM epilogue)."""
 
     @staticmethod
-    def forward(ctx, qkv, key_mask, batch, seq, heads, hd, q_scale):
+    def forward(ctx, qkv, key_mask, batch, seq, heads, hd, q_scale, drop_p=0.0):
         out = torch.empty(batch * seq, heads * hd, dtype=BF16, device=qkv.device)
         lse = torch.empty(batch, heads, seq, dtype=F32, device=qkv.device)
-        ops.attention_fwd(qkv, batch, seq, heads, hd, out, lse, key_mask=key_mask)
+        drop = None
+        if drop_p > 0.0:        # attention-probability dropout (HF BertSelfAttention.dropout), mask index (b, h, i, j)
+            drop = (drop_p,) + rng.next_stream(batch * heads * seq * seq, "attn_probs", (batch, heads, seq, seq), drop_p)
+        ops.attention_fwd(qkv, batch, seq, heads, hd, out, lse, key_mask=key_mask, drop=drop)
         ctx.save_for_backward(qkv, out, lse, key_mask)
-        ctx.dims = (batch, seq, heads, hd, q_scale)
+        ctx.dims = (batch, seq, heads, hd, q_scale, drop)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out, lse, key_mask = ctx.saved_tensors
-        batch, seq, heads, hd, q_scale = ctx.dims
+        batch, seq, heads, hd, q_scale, drop = ctx.dims
         dqkv = torch.empty_like(qkv)
-        ops.attention_bwd(qkv, out, dout.contiguous(), lse, batch, seq, heads, hd, dqkv, q_scale, key_mask=key_mask)
-        return dqkv, None, None, None, None, None, None
+        ops.attention_bwd(qkv, out, dout.contiguous(), lse, batch, seq, heads, hd, dqkv, q_scale, key_mask=key_mask, drop=drop)
+        return dqkv, None, None, None, None, None, None, None
 
 
 class QkvLinearFn(torch.autograd.Function):
@@ -306,8 +341,10 @@ class SwinBlockFn(torch.autograd.Function):
     reference are folded into the LN gather and the proj-GEMM scatter epilogue."""
 
     @staticmethod
-    def forward(ctx, x, wg, heads, code, code_off, region,
+    def forward(ctx, x, wg, heads, code, code_off, region, dp,
                 n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b):
+        # dp: None, or fp32 [2, B] per-sample DropPath factors keep / (1 - p) of the attention and the MLP branch
+        # (timm DropPath, :499 and :503); applied as a row scale in the proj / fc2 GEMM epilogues before the residual
         T, C = x.shape
         hd = C // heads
         dev = x.device
@@ -331,7 +368,11 @@ class SwinBlockFn(torch.autograd.Function):
         ops.attention_fwd(qkv, batch, wg.N, heads, hd, ao, lse, w7=wg.w7, bias_table=table, rel_code=code, code_off=code_off,
                           region=region)
         x_mid = torch.empty(T, C, dtype=F32, device=dev)
-        ops.gemm(ao, wp, x_mid, bias=proj_b, residual=x, window=wg)
+        tok = T // wg.B                                        # tokens per clip (== window-order rows per clip, unpadded)
+        if dp is not None and wg.padded:
+            raise NotImplementedError("clover_b200: DropPath with frames padded to window multiples is not supported")
+        ops.gemm(ao, wp, x_mid, bias=proj_b, residual=x, window=wg, row_scale=dp[0] if dp is not None else None,
+                 row_scale_rows=tok)
         h2 = torch.empty(T, C, dtype=BF16, device=dev)
         if fast_ln:
             ops.lnr_fwd(x_mid, n2w, n2b, 1e-5, h2, mean=mean2, rstd=rstd2)
@@ -341,18 +382,18 @@ class SwinBlockFn(torch.autograd.Function):
         act = torch.empty(T, fc1_w.shape[0], dtype=BF16, device=dev)
         ops.gemm(h2, w1, act, bias=fc1_b, act="gelu", out_pre=pre)
         out = torch.empty(T, C, dtype=F32, device=dev)
-        ops.gemm(act, w2, out, bias=fc2_b, residual=x_mid)
+        ops.gemm(act, w2, out, bias=fc2_b, residual=x_mid, row_scale=dp[1] if dp is not None else None, row_scale_rows=tok)
         ctx.save_for_backward(x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region,
                               n1w, n1b, n2w, n2b, table)
         ctx.w = (wq, wp, w1, w2)
-        ctx.meta = (wg, heads, hd, code_off, scale, fc1_w.shape[0], rmap)
+        ctx.meta = (wg, heads, hd, code_off, scale, fc1_w.shape[0], rmap, dp, tok)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region, n1w, n1b, n2w, n2b, table) = ctx.saved_tensors
         wq, wp, w1, w2 = ctx.w
-        wg, heads, hd, code_off, scale, Hd, rmap = ctx.meta
+        wg, heads, hd, code_off, scale, Hd, rmap, dp, tok = ctx.meta
         T, C = x.shape
         rows = wg.rows
         dev = x.device
@@ -362,7 +403,12 @@ class SwinBlockFn(torch.autograd.Function):
         dg1, db1, dg2, db2 = small[:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
         dtable = small[6 * C:].view_as(table)
         # ---- MLP branch
-        dy16, dB2 = _grad_bf16(dout, want_colsum=True)
+        if dp is not None:            # d(branch) = factor[sample] * dout: every consumer below reads the scaled bf16 copy
+            _GRAD16[0] = None
+            dy16 = ops.rows_scale(dout, torch.empty(T, C, dtype=BF16, device=dev), dp[1], tok)
+            dB2 = None
+        else:
+            dy16, dB2 = _grad_bf16(dout, want_colsum=True)
         dpre = torch.empty(T, Hd, dtype=BF16, device=dev)
         ops.gemm(dy16, w2, dpre, b_t=True, gelu_pre=pre)
         dW2 = _wgrad(dy16, act, C, Hd)
@@ -378,13 +424,15 @@ class SwinBlockFn(torch.autograd.Function):
         dmid_w = (torch.zeros if wg.padded else torch.empty)(rows, C, dtype=BF16, device=dev)
         dBp = None
         if rmap is not None:
-            dBp = small[4 * C:5 * C]                          # proj bias gradient = column sums of d x_mid
+            dBp = small[4 * C:5 * C] if dp is None else None  # proj bias gradient = column sums of d x_mid
             ops.lnr_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, dx=dmid, dres=dout, dx_bf16=dmid_w, row_map=rmap,
                         dx_bf16_mapped=True, dgamma=dg2, dbeta=db2, dxsum=dBp)
         else:
             ops.layernorm_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, rows=T, dx=dmid, dres=dout, dx_copy=dmid_w,
                               copy_window=wg, dgamma=dg2, dbeta=db2)
         # ---- attention branch
+        if dp is not None:            # window-order rows of one clip are contiguous: scale the branch gradient in place
+            ops.rows_scale(dmid_w, dmid_w, dp[0], tok)
         dao = torch.empty(rows, C, dtype=BF16, device=dev)
         ops.gemm(dmid_w, wp, dao, b_t=True)
         dWp = _wgrad(dmid_w, ao, C, C)
@@ -403,11 +451,12 @@ class SwinBlockFn(torch.autograd.Function):
             dx_sum = small[5 * C:6 * C]                       # = fc2 bias gradient of the block that produced x
             ops.lnr_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, dx=dmid, dres=dmid, dx_bf16=dmid16, row_map=rmap,
                         dy_mapped=True, dgamma=dg1, dbeta=db1, dxsum=dx_sum)
-            _publish_grad16(dmid, dmid16, dx_sum)
+            if dp is None:            # (with DropPath the producer of x scales its own copy; it ignores published ones)
+                _publish_grad16(dmid, dmid16, dx_sum)
         else:
             ops.layernorm_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, rows=rows, dx=dmid, dres=dmid, dgamma=dg1, dbeta=db1,
                               window=wg)
-        return (dmid, None, None, None, None, None,
+        return (dmid, None, None, None, None, None, None,
                 dg1, db1, dWq, dBq, dtable, dWp, dBp, dg2, db2, dW1, dB1, dW2, dB2)
 
 

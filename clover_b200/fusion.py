@@ -43,7 +43,7 @@ class CrossModalTransformerFromPretrained(nn.Module):
             elif isinstance(m, nn.Embedding):
                 m.weight.data.normal_(0.0, std)
 
-    def forward_tokens(self, v_tokens, B, T, S, text_states, text_input_mask):
+    def forward_tokens(self, v_tokens, B, T, S, text_states, text_input_mask, want_last_probs=False):
         """v_tokens: [B*T*S, img_in] (fp32 or bf16); text_states: (Bt, L, H) bf16/fp32.  Returns the
         encoder output bf16 [B, T*S + L', H] (L' = L * Bt/B for multiple-choice folding, :79-82)."""
         H = self.hidden_size
@@ -59,6 +59,9 @@ class CrossModalTransformerFromPretrained(nn.Module):
         z = Fn.FusionInputFn.apply(v16, t16, self.vis_space_pos, self.vis_tempor_pos, self.token_type_embeddings.weight,
                                    self.norm.weight, self.norm.bias, B, T, S, L)
         full_mask = torch.cat([torch.ones(B, T * S, dtype=mask.dtype, device=mask.device), mask], dim=1)
+        if want_last_probs:      # (out, mask, head-mean attention probabilities of the last layer (B, S', S'))
+            out, probs = self.bert_encoder.forward_tokens(z, full_mask, B, T * S + L, want_last_probs=True)
+            return out.view(B, T * S + L, H), full_mask, probs
         out = self.bert_encoder.forward_tokens(z, full_mask, B, T * S + L)
         return out.view(B, T * S + L, H), full_mask
 

@@ -22,10 +22,11 @@ def _xavier_init(module):
             m.weight.data.fill_(1.0)
 
 
-def _no_dropout(module, p):
+def _head_dropout(module, x, p, kind):
+    """nn.Dropout(p) of the reference heads in training mode (counter-based mask, clover_b200.rng); identity otherwise."""
     if p and module.training:
-        raise NotImplementedError("clover_b200: head dropout > 0 in training mode is not implemented yet "
-                                  "(set dropout_ratio=0 or call .eval())")
+        return Fn.dropout(x, float(p), True, out_fp32=x.dtype == torch.float32, kind=kind)
+    return x
 
 
 def _tokens_channels_last(img):
@@ -68,9 +69,9 @@ class NCEHeadForMM(nn.Module):
 
     def forward_vision_tokens(self, tokens, B, S):
         """tokens fp32 [B*S, C] -> fp32 [B, vts]"""
-        _no_dropout(self, self.dropout_ratio)
         p = self.img_projector
         x = Fn.MeanTokensFn.apply(tokens, B, S)
+        x = _head_dropout(self, x, self.dropout_ratio, "head_mm_vision")           # ssl_head.py:108-109
         x = Fn.linear(Fn.to_dtype(x, BF16), p[0].weight, p[0].bias, out_fp32=True)
         x = Fn.gelu(Fn.layer_norm(x, p[1].weight, p[1].bias, p[1].eps))
         x = Fn.linear(x, p[3].weight, p[3].bias, out_fp32=True)
@@ -110,12 +111,12 @@ class NCEHeadForVision(nn.Module):
         _xavier_init(self)
 
     def forward(self, img):
-        _no_dropout(self, self.dropout_ratio)
         if img.dim() == 3:
             B, S, C = img.shape
             x = Fn.to_dtype(Fn.MeanTokensFn.apply(Fn.to_dtype(img.reshape(B * S, C).contiguous(), torch.float32), B, S), BF16)
         else:
             x = Fn.to_dtype(img.contiguous(), BF16)
+        x = _head_dropout(self, x, self.dropout_ratio, "head_vision")              # ssl_head.py:211-212
         x = Fn.linear(x, self.img_fc1.weight, self.img_fc1.bias, out_fp32=True)
         x = Fn.gelu(Fn.layer_norm(x, self.img_bn1.weight, self.img_bn1.bias, self.img_bn1.eps))
         x = Fn.linear(x, self.img_fc2.weight, self.img_fc2.bias, out_fp32=True)
@@ -142,8 +143,11 @@ class NCEHeadForText(nn.Module):
         _xavier_init(self)
 
     def forward(self, mask_word_feat):
-        _no_dropout(self, self.dropout_ratio)
         x = Fn.to_dtype(mask_word_feat.contiguous(), BF16)
+        if self.dropout_ratio and self.training:                                   # dropout sits between GELU and fc2 (:292-293)
+            h = Fn.linear(x, self.fc1.weight, self.fc1.bias, act="gelu")
+            h = _head_dropout(self, h, self.dropout_ratio, "head_text")
+            return Fn.linear(h, self.fc2.weight, self.fc2.bias, out_fp32=True)
         return Fn.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, out_fp32=True)
 
 
@@ -215,9 +219,9 @@ class QA_OE_Head(nn.Module):
         _xavier_init(self)
 
     def forward(self, cls_feature):
-        _no_dropout(self, self.dropout_ratio)
         c = self.vqa_classifier
-        x = Fn.linear(Fn.to_dtype(cls_feature.contiguous(), BF16), c[1].weight, c[1].bias, out_fp32=True)
+        x = _head_dropout(self, Fn.to_dtype(cls_feature.contiguous(), BF16), self.dropout_ratio, "head_qa_oe")   # qa_head.py:60
+        x = Fn.linear(x, c[1].weight, c[1].bias, out_fp32=True)
         x = Fn.gelu(Fn.layer_norm(x, c[2].weight, c[2].bias, c[2].eps))
         return _linear_any_n(x, c[4])
 
@@ -236,9 +240,9 @@ class QA_MC_head(nn.Module):
         _xavier_init(self)
 
     def forward(self, x):
-        _no_dropout(self, self.dropout_ratio)
         c = self.mc_vqa_classifier
-        x = Fn.linear(Fn.to_dtype(x.contiguous(), BF16), c[1].weight, c[1].bias, out_fp32=True)
+        x = _head_dropout(self, Fn.to_dtype(x.contiguous(), BF16), self.dropout_ratio, "head_qa_mc")             # qa_head.py:12
+        x = Fn.linear(x, c[1].weight, c[1].bias, out_fp32=True)
         x = Fn.gelu(Fn.layer_norm(x, c[2].weight, c[2].bias, c[2].eps))
         return _linear_any_n(x, c[4])
 

@@ -140,7 +140,7 @@ _ROW_MAPS = {}
 
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None, out_pre=None, gelu_pre=None,
-         scale_cols=0, scale=1.0, window=None, k_splits=1, accumulate=False):
+         scale_cols=0, scale=1.0, window=None, k_splits=1, accumulate=False, row_scale=None, row_scale_rows=0):
     """out = epilogue(A @ B^T).  a: [M,K] (or [K,M] if a_t), b: [N,K] (or [K,N] if b_t), bf16.
     See clv_gemm_bf16 in include/clover_b200.h."""
     _need_cuda(a, b, out)
@@ -172,6 +172,12 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None,
     if window is not None:
         e.window = window.ref()
     e.k_splits, e.accumulate = int(k_splits), int(bool(accumulate))
+    if row_scale is not None:
+        if row_scale.dtype != F32 or not row_scale.is_contiguous() or row_scale_rows <= 0 or \
+                row_scale.numel() * row_scale_rows < M:
+            raise ValueError("gemm: row_scale must be contiguous fp32 with numel * row_scale_rows >= M")
+        _need_cuda(row_scale)
+        e.row_scale, e.row_scale_rows = _ptr(row_scale), int(row_scale_rows)
     lib = _lib.load()
     ev = _prof_open()
     _lib.check(lib.clv_gemm_bf16(_ptr(a), lda, int(a_t), _ptr(b), ldb, int(b_t), M, N, K, C.byref(e), _stream()), "clv_gemm_bf16")
@@ -313,7 +319,7 @@ def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=
 
 
 # ------------------------------------------------------------------------------------------------
-def _attn_desc(batch, seq, heads, hd, bias_table=None, rel_code=None, code_off=0, region=None, key_mask=None):
+def _attn_desc(batch, seq, heads, hd, bias_table=None, rel_code=None, code_off=0, region=None, key_mask=None, drop=None):
     d = AttnDesc()
     d.batch, d.seq, d.heads, d.head_dim = batch, seq, heads, hd
     if bias_table is not None:
@@ -323,6 +329,8 @@ def _attn_desc(batch, seq, heads, hd, bias_table=None, rel_code=None, code_off=0
         d.region, d.nwin = _ptr(region), region.shape[0]
     if key_mask is not None:
         d.key_mask = _ptr(key_mask)
+    if drop is not None:                      # (p, seed, offset) of the attention-probability dropout stream
+        d.drop_p, d.drop_seed, d.drop_offset = float(drop[0]), int(drop[1]), int(drop[2])
     return d
 
 
@@ -363,7 +371,7 @@ def attention_fwd(qkv, batch, seq, heads, hd, out, lse, w7=None, **bias):
         ws = torch.empty(lib.clv_attention_w7_fwd_workspace_bytes(C.byref(dw)), dtype=torch.uint8, device=qkv.device)
         _lib.check(lib.clv_attention_w7_fwd(C.byref(dw), _ptr(qkv), _ptr(out), _ptr(lse), _ptr(ws), _stream()),
                    "clv_attention_w7_fwd")
-    elif hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 416 and USE_TC_ATTENTION:
+    elif hd == 32 and bias.get("key_mask") is None and bias.get("drop") is None and 33 <= seq <= 416 and USE_TC_ATTENTION:
         _lib.check(lib.clv_attention_fwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd_tc")
     else:
         _lib.check(lib.clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
@@ -385,7 +393,7 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
         ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
         _lib.check(lib.clv_attention_w7_bwd(C.byref(dw), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
                                             float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_w7_bwd")
-    elif hd == 32 and bias.get("key_mask") is None and 33 <= seq <= 224 and USE_TC_ATTENTION:
+    elif hd == 32 and bias.get("key_mask") is None and bias.get("drop") is None and 33 <= seq <= 224 and USE_TC_ATTENTION:
         nbytes = lib.clv_attention_bwd_tc_workspace_bytes(C.byref(d), int(dbias_table is not None))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
         _lib.check(lib.clv_attention_bwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
@@ -396,6 +404,52 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
                                          float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd")
     _prof_close(ev, ("attn_bwd_hd%d" % hd) + (f" b={batch} n={seq} h={heads}" if PROFILE_SHAPES else ""), 8.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 8)
     return dqkv
+
+
+def attention_probs_mean(qkv, batch, seq, heads, hd, **bias):
+    """fp32 [batch, seq, seq]: head-mean of the attention probabilities (evaluation; finetune.py:192)."""
+    _need_cuda(qkv)
+    if qkv.dtype != BF16 or not qkv.is_contiguous() or qkv.shape != (batch * seq, 3 * heads * hd):
+        raise ValueError("attention_probs_mean: qkv must be contiguous bf16 [batch*seq, 3*heads*hd]")
+    d = _attn_desc(batch, seq, heads, hd, **bias)
+    out = torch.empty(batch, seq, seq, dtype=F32, device=qkv.device)
+    _lib.check(_lib.load().clv_attention_probs_mean(C.byref(d), _ptr(qkv), _ptr(out), _stream()), "clv_attention_probs_mean")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+@_profiled("dropout")
+def dropout(x, y, p, seed, offset, residual=None):
+    """y = residual + x * keep / (1 - p) with keep drawn from stream (seed, offset + i); see clv_dropout."""
+    _need_cuda(x, y, residual)
+    n = x.numel()
+    if y.numel() != n or not x.is_contiguous() or not y.is_contiguous() or (residual is not None and (
+            residual.numel() != n or not residual.is_contiguous())):
+        raise ValueError("dropout: x, y (and residual) must be contiguous with the same number of elements")
+    _lib.check(_lib.load().clv_dropout(_ptr(x), _is_bf16(x), _ptr(residual), _is_bf16(residual) if residual is not None else 0,
+                                       _ptr(y), _is_bf16(y), n, float(p), int(seed), int(offset), _stream()), "clv_dropout")
+    return y
+
+
+def keep_mask(n, p, seed, offset, device):
+    """uint8 [n]: the keep decisions of stream elements offset .. offset + n - 1."""
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    _need_cuda(out)
+    _lib.check(_lib.load().clv_keep_mask(_ptr(out), n, float(p), int(seed), int(offset), _stream()), "clv_keep_mask")
+    return out
+
+
+@_profiled("rows_scale")
+def rows_scale(x, y, scale, rows_per_group):
+    """y[r, :] = x[r, :] * scale[r // rows_per_group]  (DropPath factor on a gradient)."""
+    _need_cuda(x, y, scale)
+    rows, Cn = x.shape
+    if y.shape != x.shape or not x.is_contiguous() or not y.is_contiguous() or scale.dtype != F32 or \
+            scale.numel() * rows_per_group < rows:
+        raise ValueError("rows_scale: bad arguments")
+    _lib.check(_lib.load().clv_rows_scale(_ptr(x), _is_bf16(x), _ptr(y), _is_bf16(y), rows, Cn, _ptr(scale), int(rows_per_group),
+                                          _stream()), "clv_rows_scale")
+    return y
 
 
 # ------------------------------------------------------------------------------------------------

@@ -277,16 +277,18 @@ class CloverFinetune(BaseRecognizer):
         T_e = self.text_backbone(token_ids, input_mask)["last_hidden_state"]
         return v_tok, (B, T, h * w), T_e, token_ids, input_mask
 
-    def _qa_logits(self, v_tok, B, T, S, T_e, input_mask):
+    def _qa_logits(self, v_tok, B, T, S, T_e, input_mask, want_attention=False):
         if not hasattr(self.qa_head, "num_labels"):
             n = T_e.shape[0] // B                                                   # multiple choice: repeat the clip
             v_tok = v_tok.view(B, 1, T * S, -1).expand(-1, n, -1, -1).reshape(B * n * T * S, -1).contiguous()
             Bq = B * n
         else:
             n, Bq = self.qa_head.num_labels, B
-        out, _ = self.multimodal_backbone.forward_tokens(v_tok, Bq, T, S, T_e, input_mask)
+        res = self.multimodal_backbone.forward_tokens(v_tok, Bq, T, S, T_e, input_mask, want_last_probs=want_attention)
+        out = res[0]
         cls = out[:, T * S]                                                         # t_last_hidden_state[:, 0]
-        return self.qa_head(cls).reshape(-1, n)
+        logits = self.qa_head(cls).reshape(-1, n)
+        return (logits, res[2]) if want_attention else logits
 
     def forward_train(self, imgs, label, token_ids=None, segment_ids=None, input_mask=None, ans_ids=None, ans_mask=None,
                       **kwargs):
@@ -305,8 +307,9 @@ class CloverFinetune(BaseRecognizer):
         v_tok, (B, T, S), T_e, token_ids, input_mask = self._encode(imgs, token_ids, input_mask)
         if self.task == "retrieval":
             return self.ssl_head.forward_vision_tokens(v_tok, B, T * S), self.ssl_head.forward_text(T_e)
-        logits = self._qa_logits(v_tok, B, T, S, T_e, input_mask)
-        return logits
+        # reference :188-192: {'result': fp32 logits, 'attention': last fusion layer's head-mean attention probabilities}
+        logits, attn = self._qa_logits(v_tok, B, T, S, T_e, input_mask, want_attention=True)
+        return {"result": logits.to(torch.float32), "attention": attn}
 
     def forward_gradcam(self, imgs, token_ids=None, input_mask=None):
         return self.forward_test(imgs, token_ids, input_mask)

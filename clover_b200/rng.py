@@ -1,0 +1,51 @@
+"""Host side of the counter-based random streams used by the stochastic regularisers (dropout, DropPath).
+
+The kernels draw element ``e`` of a stream as ``keep = hash32(seed, e) >= p * 2**32`` (clover_b200/csrc/common.cuh,
+rand_u32; restated in numpy by tests/rng_ref.py).  Nothing random lives on the device: this module hands every
+dropout site a disjoint ``[offset, offset + n)`` range of one 64-bit stream per process, so the backward pass (and
+the attention kernels) regenerate the identical mask from ``(seed, offset)``.
+
+``manual_seed(s)`` pins the stream (tests); otherwise the seed comes from ``torch.initial_seed()`` mixed with the
+rank, so data-parallel ranks draw different masks as they do in the reference (independent torch generators).
+``LOG`` (a list, or None) records every site in call order so that tests can hand the same masks to the oracle.
+"""
+import torch
+
+_MASK64 = (1 << 64) - 1
+_state = {"seed": None, "offset": 0}
+LOG = None
+
+
+def manual_seed(seed):
+    _state["seed"] = int(seed) & _MASK64
+    _state["offset"] = 0
+
+
+def _seed():
+    if _state["seed"] is None:
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()
+        _state["seed"] = (int(torch.initial_seed()) ^ (rank * 0x9E3779B97F4A7C15)) & _MASK64
+    return _state["seed"]
+
+
+def next_stream(n, kind="dropout", shape=None, p=0.0):
+    """Reserve n consecutive stream elements; returns (seed, offset)."""
+    seed, off = _seed(), _state["offset"]
+    _state["offset"] = (off + int(n) + 3) // 4 * 4
+    if LOG is not None:
+        LOG.append(dict(kind=kind, shape=tuple(shape) if shape is not None else (int(n),), p=float(p), seed=seed, offset=off))
+    return seed, off
+
+
+def drop_path_scales(batch, p, device):
+    """timm DropPath factors (drop.py: x.new_empty(B,1,..).bernoulli_(keep) / keep): fp32 [batch] on `device`, drawn
+    from torch's generator of that device (torch.manual_seed controls it, as in the reference)."""
+    keep = 1.0 - float(p)
+    s = torch.empty(batch, dtype=torch.float32, device=device).bernoulli_(keep)
+    if keep > 0.0:
+        s.div_(keep)
+    if LOG is not None:
+        LOG.append(dict(kind="drop_path", shape=(batch,), p=float(p), scale=s.detach().cpu().clone()))
+    return s

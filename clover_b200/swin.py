@@ -126,6 +126,28 @@ def compute_mask(D, H, W, window_size, shift_size, device, dtype=torch.float32):
     return m
 
 
+class DropPath(nn.Module):
+    """timm.models.layers.DropPath (stochastic depth per sample), the class swin_transformer_3d.py:6,443 instantiates.
+    Inside SwinTransformerBlock3D the factor keep / (1 - p) rides in the proj / fc2 GEMM epilogues; this forward is the
+    stand-alone form for callers that use the module directly."""
+
+    def __init__(self, drop_prob=0.0, scale_by_keep=True):
+        super().__init__()
+        self.drop_prob, self.scale_by_keep = float(drop_prob), scale_by_keep
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        from . import rng
+        s = rng.drop_path_scales(x.shape[0], self.drop_prob, x.device)
+        if not self.scale_by_keep:
+            s = s * (1.0 - self.drop_prob)
+        return x * s.view((-1,) + (1,) * (x.dim() - 1)).to(x.dtype)
+
+    def extra_repr(self):
+        return f"drop_prob={self.drop_prob:0.3f}"
+
+
 class SwinTransformerBlock3D(nn.Module):
     """reference :403-505."""
 
@@ -142,7 +164,7 @@ class SwinTransformerBlock3D(nn.Module):
         self.attn = WindowAttention3D(dim, window_size=self.window_size, num_heads=num_heads, qkv_bias=qkv_bias,
                                       qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
         self.drop_path_rate = float(drop_path)
-        self.drop_path = nn.Identity()
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()       # :443
         self.norm2 = norm_layer(dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
         if drop > 0 or attn_drop > 0:
@@ -150,15 +172,17 @@ class SwinTransformerBlock3D(nn.Module):
 
     def forward_tokens(self, x, B, D, H, W):
         """x fp32 [B*D*H*W, C] channels-last tokens -> same shape."""
-        if self.training and self.drop_path_rate > 0:
-            raise NotImplementedError("clover_b200: stochastic depth (drop_path > 0) in training mode is not implemented yet; "
-                                      "set drop_path_rate=0 (parity / bench configuration)")
+        dp = None
+        if self.training and self.drop_path_rate > 0:      # two independent per-sample draws: attention branch, MLP branch
+            from . import rng
+            dp = torch.stack([rng.drop_path_scales(B, self.drop_path_rate, x.device),
+                              rng.drop_path_scales(B, self.drop_path_rate, x.device)])
         window, shift = get_window_size((D, H, W), self.window_size, self.shift_size)
         wg = ops.Window(B, D, H, W, window, shift)
         code, off, region = _device_tables((wg.Dp, wg.Hp, wg.Wp), window, shift, self.window_size, x.device)
         wg.w7 = _w7_spec((wg.Dp, wg.Hp, wg.Wp), window, shift, self.window_size, x.device)
         a, m = self.attn, self.mlp
-        return Fn.SwinBlockFn.apply(x, wg, self.num_heads, code, off, region,
+        return Fn.SwinBlockFn.apply(x, wg, self.num_heads, code, off, region, dp,
                                     self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias,
                                     a.relative_position_bias_table, a.proj.weight, a.proj.bias,
                                     self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
+from . import ops
 
 BERT_BASE = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
                  intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
@@ -45,8 +46,11 @@ class BertEmbeddings(nn.Module):
         """(B, L) int64 -> bf16 [B*L, H]"""
         if input_ids.shape[1] > self.position_embeddings.weight.shape[0]:
             raise ValueError("sequence longer than max_position_embeddings")
-        return Fn.BertEmbedFn.apply(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
-                                    self.token_type_embeddings.weight, self.LayerNorm.weight, self.LayerNorm.bias, self.eps)
+        h = Fn.BertEmbedFn.apply(input_ids, self.word_embeddings.weight, self.position_embeddings.weight,
+                                 self.token_type_embeddings.weight, self.LayerNorm.weight, self.LayerNorm.bias, self.eps)
+        if self.training and self.dropout.p > 0:            # HF BertEmbeddings: dropout(LayerNorm(sum of embeddings))
+            h = Fn.dropout(h, self.dropout.p, True, kind="bert_embeddings")
+        return h
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         state_dict.pop(prefix + "position_ids", None)      # persistent buffer in transformers 4.6.1 checkpoints
@@ -109,13 +113,34 @@ class BertLayer(nn.Module):
         scale = self.head_dim ** -0.5
         qkv = Fn.QkvLinearFn.apply(h, s.query.weight, s.query.bias, s.key.weight, s.key.bias, s.value.weight, s.value.bias,
                                    scale, self)
-        ctx = Fn.AttentionFn.apply(qkv, key_mask, B, S, self.heads, self.head_dim, scale)
         o = self.attention.output
-        a = Fn.linear(ctx, o.dense.weight, o.dense.bias, residual=h, out_fp32=True)
+        p_attn = s.dropout.p if self.training else 0.0       # HF 4.6.1: dropout on the attention probabilities,
+        p_ao = o.dropout.p if self.training else 0.0         # on the two dense outputs before their residual adds
+        p_out = self.output.dropout.p if self.training else 0.0
+        ctx = Fn.AttentionFn.apply(qkv, key_mask, B, S, self.heads, self.head_dim, scale, float(p_attn))
+        if p_ao > 0:
+            a = Fn.dropout(Fn.linear(ctx, o.dense.weight, o.dense.bias), p_ao, True, residual=h, out_fp32=True,
+                           kind="bert_self_output")
+        else:
+            a = Fn.linear(ctx, o.dense.weight, o.dense.bias, residual=h, out_fp32=True)
         a = Fn.layer_norm(a, o.LayerNorm.weight, o.LayerNorm.bias, self.eps)
-        f = Fn.mlp(a, self.intermediate.dense.weight, self.intermediate.dense.bias, self.output.dense.weight,
-                   self.output.dense.bias, residual=a, out_fp32=True)
+        m = (a, self.intermediate.dense.weight, self.intermediate.dense.bias, self.output.dense.weight, self.output.dense.bias)
+        if p_out > 0:
+            f = Fn.dropout(Fn.mlp(*m), p_out, True, residual=a, out_fp32=True, kind="bert_output")
+        else:
+            f = Fn.mlp(*m, residual=a, out_fp32=True)
         return Fn.layer_norm(f, self.output.LayerNorm.weight, self.output.LayerNorm.bias, self.eps)
+
+
+def _layer_probs_mean(layer, h, key_mask, B, S):
+    """Head-mean attention probabilities (B, S, S) fp32 of one layer on input h: what HF's output_attentions=True gives
+    the reference at finetune.py:192 (`attentions[-1].mean(dim=1)`).  Evaluation only."""
+    s = layer.attention.self
+    scale = layer.head_dim ** -0.5
+    with torch.no_grad():
+        qkv = Fn.QkvLinearFn.apply(h, s.query.weight, s.query.bias, s.key.weight, s.key.bias, s.value.weight, s.value.bias,
+                                   scale, layer)
+        return ops.attention_probs_mean(qkv, B, S, layer.heads, layer.head_dim, key_mask=key_mask)
 
 
 class BertEncoder(nn.Module):
@@ -123,15 +148,16 @@ class BertEncoder(nn.Module):
         super().__init__()
         self.layer = nn.ModuleList([BertLayer(cfg) for _ in range(cfg["num_hidden_layers"])])
 
-    def forward_tokens(self, h, attention_mask, B, S):
-        """attention_mask (B, S) 1 = attend -> additive (1-m)*-10000 (transformers 4.6.1)."""
+    def forward_tokens(self, h, attention_mask, B, S, want_last_probs=False):
+        """attention_mask (B, S) 1 = attend -> additive (1-m)*-10000 (transformers 4.6.1).
+        want_last_probs: also return the last layer's head-mean attention probabilities (B, S, S)."""
         km = ((1.0 - attention_mask.to(torch.float32)) * -10000.0).contiguous()
-        if self.training and any(l.attention.self.dropout.p > 0 or l.output.dropout.p > 0 for l in self.layer):
-            raise NotImplementedError("clover_b200: BERT dropout > 0 in training mode is not implemented yet; build with "
-                                      "hidden_dropout_prob=0 / attention_probs_dropout_prob=0 or call .eval()")
-        for layer in self.layer:
+        probs = None
+        for i, layer in enumerate(self.layer):
+            if want_last_probs and i == len(self.layer) - 1:
+                probs = _layer_probs_mean(layer, h, km, B, S)
             h = layer.forward_tokens(h, km, B, S)
-        return h
+        return (h, probs) if want_last_probs else h
 
 
 class _Pooler(nn.Module):

@@ -63,6 +63,10 @@ typedef struct {
   const clv_window_geom_t* window;  /* non-NULL: GEMM row (window order) -> spatial output/residual row (:471-479) */
   int k_splits;               /* >1: split K across CTAs, fp32 atomic accumulation (weight gradients) */
   int accumulate;             /* 1: add into `out` (fp32) instead of overwriting */
+  const float* row_scale;     /* [ceil(M / row_scale_rows)] or NULL: (acc + bias) of GEMM row m is multiplied by
+                                 row_scale[m / row_scale_rows] before the residual add -- the per-sample keep/(1-p)
+                                 factor of timm DropPath (x + drop_path(branch), swin_transformer_3d.py:499,503) */
+  long long row_scale_rows;
 } clv_gemm_epilogue_t;
 
 int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
@@ -153,6 +157,11 @@ typedef struct {
   const int* rel_code; int code_off;     /* [seq] */
   const int* region; int nwin;           /* [nwin, seq] or NULL */
   const float* key_mask;                 /* [batch, seq] or NULL */
+  /* attention-probability dropout (HF BertSelfAttention.dropout, attention_probs_dropout_prob): P is multiplied by
+   * keep/(1-p) after the softmax, keep = clv_keep_mask stream element drop_offset + ((b*heads+h)*seq+i)*seq+j.
+   * drop_p == 0 disables it.  Only clv_attention_fwd / clv_attention_bwd (the BERT kernels) support it. */
+  float drop_p;
+  unsigned long long drop_seed, drop_offset;
 } clv_attn_desc_t;
 
 int clv_attention_fwd(const clv_attn_desc_t* desc, const void* qkv, void* out, float* lse, void* stream);
@@ -163,6 +172,10 @@ int clv_attention_fwd_tc(const clv_attn_desc_t* desc, const void* qkv, void* out
 int clv_attention_bwd(const clv_attn_desc_t* desc, const void* qkv, const void* out, const void* dout,
                       const float* lse, void* dqkv, float q_scale, float* dbias_table,
                       float* dsum_workspace /* fp32 [batch*heads*seq] */, void* stream);
+/* probs_mean[b, i, j] = mean over heads of softmax_j(q_i . k_j + bias/mask terms): the `attentions[-1].mean(dim=1)`
+ * that CloverFinetune.forward_test returns for video QA (multimodal_transformer_finetune.py:192; HF BertEncoder
+ * output_attentions).  Evaluation only (no dropout).  out: fp32 [batch, seq, seq]. */
+int clv_attention_probs_mean(const clv_attn_desc_t* desc, const void* qkv, float* probs_mean, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HBM-bound helpers.
@@ -197,6 +210,23 @@ typedef struct {
   long long rows; int C;
 } clv_rows_affine_t;
 int clv_rows_affine(const clv_rows_affine_t* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stochastic regularisers (training mode).  Counter-based stream: element e keeps iff
+ * hash32(seed, e) >= p * 2^32 (splitmix64 finaliser; tests/rng_ref.py restates it in numpy).
+ * ------------------------------------------------------------------------------------------- */
+/* y[i] = (residual ? residual[i] : 0) + x[i] * keep(offset + i) / (1 - p).   nn.Dropout of HF BertEmbeddings /
+ * BertSelfOutput / BertOutput (transformers 4.6.1) and of the heads (ssl_head.py:108-109,211-212,292-293;
+ * qa_head.py:12,60).  Backward: the same call on dy with residual == NULL. */
+int clv_dropout(const void* x, int x_is_bf16, const void* residual, int residual_is_bf16, void* y, int y_is_bf16,
+                long long n, float p, unsigned long long seed, unsigned long long offset, void* stream);
+/* out[i] = 1 if element offset + i is kept else 0 (inspection / tests). */
+int clv_keep_mask(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset, void* stream);
+unsigned int clv_dropout_threshold(float p);
+/* y[r,:] = x[r,:] * scale[r / rows_per_group]: per-sample DropPath factor (timm DropPath in
+ * swin_transformer_3d.py:499,503) applied to a gradient; the forward factor is clv_gemm_epilogue_t.row_scale. */
+int clv_rows_scale(const void* x, int x_is_bf16, void* y, int y_is_bf16, long long rows, int C, const float* scale,
+                   long long rows_per_group, void* stream);
 
 /* dst[index[r],:] += src[r,:]  (fp32 atomics; word-embedding gradient of HF BertEmbeddings). */
 int clv_scatter_add_rows(const float* src, const long long* index, float* dst, long long rows, int C, void* stream);

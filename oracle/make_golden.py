@@ -17,7 +17,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ref_shim  # noqa: E402
-from clover_b200.synthetic import named_tensor, synth_state_dict, make_batch  # noqa: E402
+from clover_b200.synthetic import named_tensor, synth_state_dict, make_batch, make_finetune_batch  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -303,6 +303,63 @@ def gen_pretrain(ref, tag, cfg, bert_over, B, frames, size, L, vocab, seed, full
     return m
 
 
+FT_GRAD_KEYS = ["backbone.patch_embed.proj.weight", "backbone.layers.0.blocks.1.attn.relative_position_bias_table",
+                "backbone.layers.1.blocks.0.attn.qkv.weight", "backbone.norm.bias",
+                "text_backbone.bert.embeddings.word_embeddings.weight",
+                "text_backbone.bert.encoder.layer.1.attention.self.query.weight",
+                "multimodal_backbone.fc_in.weight", "multimodal_backbone.vis_tempor_pos",
+                "multimodal_backbone.bert_encoder.layer.0.output.dense.weight",
+                "ssl_head.img_projector.3.weight", "ssl_head.text_projector.0.bias",
+                "qa_head.vqa_classifier.1.weight", "qa_head.vqa_classifier.4.bias",
+                "qa_head.mc_vqa_classifier.1.weight", "qa_head.mc_vqa_classifier.4.weight"]
+
+
+def gen_finetune(ref, tag, task, cfg, bert_over, B, frames, size, L, vocab, seed, num_labels=50):
+    """Executes the reference CloverFinetune (multimodal_transformer_finetune.py:59-197): forward_train losses +
+    gradients, then forward_test outputs in eval mode."""
+    ref_shim.ensure_gloo_group()
+    ref_shim.BERT_OVERRIDES.clear()
+    ref_shim.BERT_OVERRIDES.update(bert_over)
+    torch.manual_seed(0)
+    m = ref.builder.build_model(cfg)
+    ref_shim.BERT_OVERRIDES.clear()
+    zero_dropout(m)
+    load_synth(m, seed=seed)
+    batch = make_finetune_batch(task, B, frames, size, L, vocab, seed + 1, num_labels, choices=3)
+    kw = {k: batch[k] for k in ("token_ids", "segment_ids", "input_mask")}
+    losses = m(batch["imgs"], batch["label"], return_loss=True, **kw)
+    total, log_vars = m._parse_losses(losses)
+    total.backward()
+    out = {f"loss::{k}": np.float64(v) for k, v in log_vars.items()}
+    params = dict(m.named_parameters())
+    out["nograd_keys"] = np.array(json.dumps(sorted(k for k, p in params.items() if p.grad is None)))
+    for k in FT_GRAD_KEYS:
+        if k not in params or params[k].grad is None:
+            continue
+        g = params[k].grad
+        out[f"gradnorm::{k}"] = np.float64(g.double().norm())
+        if g.numel() <= 70000:
+            out[f"grad::{k}"] = g.numpy().copy()
+        else:
+            flat = g.reshape(-1)
+            idx = np.random.default_rng(5).integers(0, flat.numel(), size=2048)
+            out[f"gradidx::{k}"] = idx
+            out[f"gradsample::{k}"] = flat.numpy()[idx].copy()
+    m.eval()
+    with torch.no_grad():
+        res = m(batch["imgs"], None, return_loss=False, **kw)
+    if task == "retrieval":
+        out["test::visual_emb"], out["test::text_emb"] = res[0].numpy(), res[1].numpy()
+    else:
+        out["test::result"] = res["result"].numpy()
+        att = res["attention"].numpy().astype(np.float32)               # (B, S, S): head-mean of the last fusion layer
+        rows = np.array([0, att.shape[1] // 2, att.shape[1] - L, att.shape[1] - 1])
+        out["test::attention_rows"], out["test::attention_sample"] = rows, att[:, rows]
+    np.savez_compressed(os.path.join(OUT, f"finetune_{tag}.npz"), **out)
+    print(tag, {k: float(v) for k, v in log_vars.items()})
+    return m
+
+
 def gen_state_keys(ref):
     cfg = pretrain_cfg(128, [2, 2, 18, 2], [4, 8, 16, 32], 1024, 768, 30522, 12, 3, 4)
     torch.manual_seed(0)
@@ -316,7 +373,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = ref_shim.load_reference()
-    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "keys"]
+    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "ft", "keys"]
     if "tables" in which:
         gen_tables(ref)
     if "wa" in which:
@@ -334,6 +391,17 @@ def main():
         cfg = pretrain_cfg(96, [2, 2, 6, 2], [3, 6, 12, 24], 768, 768, 30522, 12, 3, 4)
         gen_pretrain(ref, "c1", cfg, dict(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
                      B=2, frames=8, size=224, L=32, vocab=30522, seed=60, full_grads=False)
+    if "ft" in which:
+        from clover_b200.configs import finetune_cfg
+        small = dict(embed=32, depths=[2, 2], heads=[1, 2], img_in=64, hidden=128, vocab=1000, text_layers=2, fusion_layers=2,
+                     frames_half=8)
+        # 16-frame clips -> T = 8 token frames -> the full (8,7,7) window, N = 392 (BASELINE c4 / c5 shapes)
+        for tag, task in (("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc")):
+            cfg = finetune_cfg(task, num_labels=50, **small)
+            for k in ("hidden_dropout_prob", "attention_probs_dropout_prob"):
+                cfg["mm_backbone"].pop(k, None), cfg["text_backbone"].pop(k, None)
+            cfg["mm_backbone"].pop("pretrained_model", None)
+            gen_finetune(ref, tag, task, cfg, SMALL_BERT, B=3, frames=16, size=56, L=20, vocab=1000, seed=70)
     if "keys" in which:
         gen_state_keys(ref)
     print("golden written to", OUT)

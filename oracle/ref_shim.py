@@ -215,6 +215,26 @@ def load_reference():
 
     BertModel._create_attention_masks = _create_attention_masks
 
+    # 4.6.1 BertEncoder.forward(..., output_attentions=True) returns every layer's attention probabilities under
+    # 'attentions' (read by finetune.py:192); 5.5's encoder drops the flag, so collect them with forward hooks.
+    from transformers.models.bert.modeling_bert import BertEncoder
+    _enc_forward = BertEncoder.forward
+
+    def _enc_forward_461(self, hidden_states, attention_mask=None, *a, output_attentions=False, **kw):
+        if not output_attentions:
+            return _enc_forward(self, hidden_states, attention_mask, *a, **kw)
+        probs = []
+        hooks = [l.attention.self.register_forward_hook(lambda m, i, o: probs.append(o[1])) for l in self.layer]
+        try:
+            out = _enc_forward(self, hidden_states, attention_mask, *a, **kw)
+        finally:
+            for h in hooks:
+                h.remove()
+        out["attentions"] = tuple(probs)
+        return out
+
+    BertEncoder.forward = _enc_forward_461
+
     ns.swin = _load("mmaction.models.backbones.swin_transformer_3d", "mmaction/models/backbones/swin_transformer_3d.py")
     ns.bert = _load("mmaction.models.backbones.bert_from_hugface", "mmaction/models/backbones/bert_from_hugface.py")
     ns.cross = _load("mmaction.models.backbones.cross_transformer", "mmaction/models/backbones/cross_transformer.py")

@@ -73,3 +73,21 @@ def pretrain_shapes(embed, depths, heads, img_in, hidden, inter, vocab, maxpos, 
     t = "mlm_ssl_T_head."
     sh.update({t + "fc1.weight": (hidden, hidden), t + "fc1.bias": (hidden,), t + "fc2.weight": (hidden, hidden), t + "fc2.bias": (hidden,)})
     return sh
+
+
+def finetune_shapes(task, embed, depths, heads, img_in, hidden, inter, vocab, maxpos, text_layers, fusion_layers, frames_half,
+                    num_labels=1500):
+    """CloverFinetune state (multimodal_transformer_finetune.py:20-57): the pre-train encoders without the mask token,
+    plus the retrieval projection head or a QA head."""
+    full = pretrain_shapes(embed, depths, heads, img_in, hidden, inter, vocab, maxpos, text_layers, fusion_layers, frames_half)
+    keep = ("backbone.", "text_backbone.", "multimodal_backbone.") + (("ssl_head.",) if task == "retrieval" else ())
+    sh = {k: v for k, v in full.items() if k.startswith(keep) and k != "backbone.mask_token"}
+    if task == "video_qa":
+        q = "qa_head.vqa_classifier."
+        sh.update({q + "1.weight": (hidden // 2, hidden), q + "1.bias": (hidden // 2,), q + "2.weight": (hidden // 2,),
+                   q + "2.bias": (hidden // 2,), q + "4.weight": (num_labels, hidden // 2), q + "4.bias": (num_labels,)})
+    elif task == "video_qa_mc":
+        q = "qa_head.mc_vqa_classifier."
+        sh.update({q + "1.weight": (256, hidden), q + "1.bias": (256,), q + "2.weight": (256,), q + "2.bias": (256,),
+                   q + "4.weight": (1, 256), q + "4.bias": (1,)})
+    return sh

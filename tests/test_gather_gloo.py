@@ -50,6 +50,9 @@ def _worker(rank, world, port, q):
         res["emb_grads"] = [e.grad.clone() for e in embs]
         res["loss"] = float(loss["nce_loss"] + loss["rank_t_tm_loss"])
         res["x"] = x.detach()
+        # tensors travel through the queue as shared-memory handles that die with this process: send them by value
+        res = {k: ([t.numpy().copy() for t in v] if isinstance(v, list) else (v.numpy().copy() if torch.is_tensor(v) else v))
+               for k, v in res.items()}
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -65,6 +68,8 @@ def test_gather_semantics_world2():
     for p in procs:
         p.start()
     out = dict(q.get(timeout=150) for _ in range(world))
+    out = {r: {k: ([torch.from_numpy(a) for a in v] if isinstance(v, list) else (torch.from_numpy(v) if hasattr(v, "dtype") else v))
+               for k, v in res.items()} for r, res in out.items()}
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0

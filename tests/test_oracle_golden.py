@@ -7,9 +7,9 @@ import numpy as np
 import pytest
 import torch
 
-from clover_b200.synthetic import make_batch, named_tensor, synth_state_dict
+from clover_b200.synthetic import make_batch, make_finetune_batch, named_tensor, synth_state_dict
 from oracle import clover_oracle as O
-from oracle.state_shapes import bert_shapes, pretrain_shapes, swin_shapes
+from oracle.state_shapes import bert_shapes, finetune_shapes, pretrain_shapes, swin_shapes
 
 torch.set_num_threads(max(1, (os.cpu_count() or 2)))
 
@@ -216,3 +216,43 @@ def test_pretrain_c1_full_size(golden_dir):
     cfg = dict(depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], text_layers=12, fusion_layers=3, bert_heads=12, vocab=30522)
     batch = make_batch(2, frames=8, L=32, seed=61, size=224, vocab=30522)
     _run_pretrain_case(golden_dir, "pretrain_c1.npz", shapes, cfg, batch, 60, 2e-4)
+
+
+FT_SMALL = dict(depths=[2, 2], num_heads=[1, 2], text_layers=2, fusion_layers=2, bert_heads=2, vocab=1000)
+
+
+@pytest.mark.parametrize("tag,task", [("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc")])
+def test_finetune(golden_dir, tag, task):
+    """CloverFinetune (BASELINE c4 / c5 shapes scaled down: 16-frame clips -> T = 8 -> the full (8,7,7) window)
+    against the executed reference: train loss + gradients, then the forward_test outputs."""
+    g = _load(golden_dir, f"finetune_{tag}.npz")
+    shapes = finetune_shapes(task, 32, [2, 2], [1, 2], 64, 128, 256, 1000, 64, 2, 2, 8, num_labels=50)
+    st = {k: v.clone().requires_grad_(True) for k, v in synth_state_dict(shapes, 70).items()}
+    batch = make_finetune_batch(task, 3, frames=16, size=56, L=20, vocab=1000, seed=71, num_labels=50, choices=3)
+    losses = O.finetune_forward(st, batch, FT_SMALL, task, train=True)
+    total = O.total_loss(losses)
+    total.backward()
+    tol = 1e-4
+    for k, v in losses.items():
+        ref = float(g[f"loss::{k}"])
+        assert abs(float(v.detach()) - ref) <= tol * max(1.0, abs(ref)), (k, float(v.detach()), ref)
+    seen = 0
+    for k in g.files:
+        name = k.split("::")[-1]
+        if k.startswith("gradnorm::"):
+            gn = float(st[name].grad.double().norm())
+            assert abs(gn - float(g[k])) <= 10 * tol * max(1e-6, float(g[k])), (name, gn, float(g[k]))
+            seen += 1
+        elif k.startswith("grad::"):
+            assert relerr(st[name].grad, g[k]) < 10 * tol, name
+        elif k.startswith("gradsample::"):
+            assert relerr(st[name].grad.reshape(-1)[g["gradidx::" + name]], g[k]) < 10 * tol, name
+    assert seen >= 8
+    with torch.no_grad():
+        res = O.finetune_forward(st, batch, FT_SMALL, task, train=False)
+    if task == "retrieval":
+        assert relerr(res[0], g["test::visual_emb"]) < tol and relerr(res[1], g["test::text_emb"]) < tol
+    else:
+        assert relerr(res["result"], g["test::result"]) < tol
+        rows = g["test::attention_rows"]
+        assert relerr(res["attention"][:, rows], g["test::attention_sample"]) < tol
