@@ -115,6 +115,7 @@ SIGNATURES = {
     "clv_dropout": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, C.c_ulonglong, C.c_ulonglong, c_vp]),
     "clv_keep_mask": (C.c_int, [c_vp, c_ll, C.c_float, C.c_ulonglong, C.c_ulonglong, c_vp]),
     "clv_dropout_threshold": (C.c_uint, [C.c_float]),
+    "clv_rand_u32": (C.c_uint, [C.c_ulonglong, C.c_ulonglong]),
     "clv_rows_scale": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_int, c_vp, c_ll, c_vp]),
     "clv_attention_bwd_tc_workspace_bytes": (c_ll, [C.POINTER(AttnDesc), C.c_int]),
     "clv_attention_bwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),

@@ -85,6 +85,7 @@ static int grid_for(long long work, int block) {
 using namespace clv;
 
 extern "C" unsigned int clv_dropout_threshold(float p) { return drop_threshold(p); }
+extern "C" unsigned int clv_rand_u32(unsigned long long seed, unsigned long long idx) { return rand_u32(seed, idx); }
 
 extern "C" int clv_dropout(const void* x, int x_is_bf16, const void* residual, int residual_is_bf16, void* y, int y_is_bf16,
                            long long n, float p, unsigned long long seed, unsigned long long offset, void* stream_) {

@@ -223,6 +223,8 @@ int clv_dropout(const void* x, int x_is_bf16, const void* residual, int residual
 /* out[i] = 1 if element offset + i is kept else 0 (inspection / tests). */
 int clv_keep_mask(unsigned char* out, long long n, float p, unsigned long long seed, unsigned long long offset, void* stream);
 unsigned int clv_dropout_threshold(float p);
+/* host evaluation of the stream (no device needed): the 32 random bits of element idx */
+unsigned int clv_rand_u32(unsigned long long seed, unsigned long long idx);
 /* y[r,:] = x[r,:] * scale[r / rows_per_group]: per-sample DropPath factor (timm DropPath in
  * swin_transformer_3d.py:499,503) applied to a gradient; the forward factor is clv_gemm_epilogue_t.row_scale. */
 int clv_rows_scale(const void* x, int x_is_bf16, void* y, int y_is_bf16, long long rows, int C, const float* scale,

@@ -64,3 +64,37 @@ def test_ops_fail_loudly_without_cuda():
     a = torch.zeros(128, 64, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):
         ops.gemm(a, a, torch.zeros(128, 128))
+
+
+def test_dropout_stream_host_matches_numpy_restatement():
+    """Integer work, bit-exact: the library's host evaluation of the dropout stream (the same inline function the kernels
+    call) against tests/rng_ref.py, incl. 64-bit wrap-around of seed * phi + idx, and the keep thresholds."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import rng_ref
+    from clover_b200 import _lib
+    lib = _lib.load()
+    for seed in (0, 1, 12345, 2 ** 63 + 7, 2 ** 64 - 1):
+        idx = np.concatenate([np.arange(64, dtype=np.uint64), np.array([2 ** 32 - 1, 2 ** 32, 2 ** 40 + 3, 2 ** 64 - 5], dtype=np.uint64)])
+        want = rng_ref.rand_u32(seed, idx)
+        got = np.array([lib.clv_rand_u32(seed, int(i)) for i in idx], dtype=np.uint32)
+        assert np.array_equal(got, want), seed
+    for p in (0.0, 0.1, 0.3, 0.5, 0.999):
+        assert lib.clv_dropout_threshold(p) == int(rng_ref.threshold(p)), p
+    # the stream is uniform enough for dropout: keep rate within 1% of 1 - p over 1e5 draws
+    for p in (0.1, 0.5):
+        assert abs(rng_ref.keep_mask(100000, p, 99, 4096).mean() - (1 - p)) < 0.01
+
+
+def test_rng_stream_offsets_are_disjoint_and_logged():
+    from clover_b200 import rng
+    rng.manual_seed(5)
+    rng.LOG = []
+    try:
+        a = rng.next_stream(10, "x", (10,), 0.1)
+        b = rng.next_stream(7, "y", (7,), 0.2)
+        c = rng.next_stream(4, "z", (4,), 0.3)
+    finally:
+        log, rng.LOG = rng.LOG, None
+    assert a == (5, 0) and b == (5, 12) and c == (5, 20)
+    assert [e["kind"] for e in log] == ["x", "y", "z"] and log[1]["offset"] == 12

@@ -534,3 +534,101 @@ def test_softmax_focal(ops, gamma, V):
     ops.softmax_focal_bwd(logits, tgt, V, gamma, stats, sums, torch.tensor([1.7], device="cuda"), dl)
     assert rel(dl[:, :V], lr.grad) < 1e-4
     assert float(dl[:, V:].abs().max()) == 0.0 if Vpad > V else True
+
+
+# ------------------------------------------------------------------------------------------------ stochastic regularisers
+def _rng_ref():
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import rng_ref
+    return rng_ref
+
+
+def test_keep_mask_bit_exact_and_dropout(ops):
+    """The device stream equals its numpy restatement bit for bit (integer work); dropout = x * keep / (1 - p) + residual
+    for every dtype combination, and the backward call regenerates the same mask."""
+    R = _rng_ref()
+    for p, seed, off, n in ((0.1, 7, 0, 4096), (0.5, 2 ** 63 + 11, 2 ** 33 + 8, 10000), (0.3, 99, 123456, 260)):
+        got = ops.keep_mask(n, p, seed, off, "cuda").cpu().numpy().astype(bool)
+        assert np.array_equal(got, R.keep_mask(n, p, seed, off)), (p, seed, off)
+    p, seed, off = 0.1, 1234, 40
+    keep = torch.from_numpy(R.keep_mask(6 * 768, p, seed, off)).view(6, 768)
+    for xdt, rdt, ydt in ((BF16, BF16, F32), (BF16, None, BF16), (F32, F32, F32), (F32, None, BF16)):
+        x = rnd(6, 768, seed=3, dtype=xdt)
+        r = rnd(6, 768, seed=4, dtype=rdt) if rdt is not None else None
+        y = ops.dropout(x, torch.empty(6, 768, dtype=ydt, device="cuda"), p, seed, off, residual=r)
+        want = x.float().cpu() * keep / (1.0 - float(np.float32(p))) + (r.float().cpu() if r is not None else 0.0)
+        assert rel(y.float(), want) < (1e-6 if ydt == F32 else 4e-3), (xdt, rdt, ydt)
+    assert abs(float(keep.float().mean()) - 0.9) < 0.02
+
+
+def test_rows_scale(ops):
+    scale = torch.tensor([0.0, 1.0 / 0.7, 1.0 / 0.7], device="cuda")
+    for xdt, ydt in ((F32, BF16), (BF16, BF16), (F32, F32)):
+        x = rnd(3 * 50, 96, seed=8, dtype=xdt)
+        y = ops.rows_scale(x, torch.empty(150, 96, dtype=ydt, device="cuda"), scale, 50)
+        want = x.float().cpu().view(3, 50, 96) * scale.cpu().view(3, 1, 1)
+        assert rel(y.float(), want.view(150, 96)) < (1e-6 if ydt == F32 else 4e-3)
+    x = rnd(150, 96, seed=9, dtype=BF16)
+    want = x.float().cpu().view(3, 50, 96) * scale.cpu().view(3, 1, 1)
+    ops.rows_scale(x, x, scale, 50)                                  # in place
+    assert rel(x.float(), want.view(150, 96)) < 4e-3
+
+
+def test_gemm_row_scale_drop_path(ops):
+    """DropPath factor in the GEMM epilogue: out = residual + factor[row / rows_per_sample] * (A W^T + b)."""
+    M, N, K, per = 4 * 196, 128, 256, 196
+    a, w = rnd(M, K, seed=1, dtype=BF16), rnd(N, K, seed=2, scale=0.1, dtype=BF16)
+    bias, res = rnd(N, seed=3), rnd(M, N, seed=4)
+    fac = torch.tensor([1 / 0.8, 0.0, 1 / 0.8, 0.0], device="cuda")
+    out = torch.empty(M, N, dtype=F32, device="cuda")
+    ops.gemm(a, w, out, bias=bias, residual=res, row_scale=fac, row_scale_rows=per)
+    want = res.cpu() + fac.cpu().repeat_interleave(per)[:, None] * (a.float().cpu() @ w.float().cpu().T + bias.cpu())
+    assert rel(out, want) < 2e-3
+    assert torch.equal(out[per:2 * per], res[per:2 * per])          # a dropped sample passes the residual through exactly
+
+
+@pytest.mark.parametrize("seq,p", [(32, 0.1), (228, 0.1), (432, 0.3)])
+def test_bert_attention_dropout(ops, seq, p):
+    """Attention-probability dropout inside the BERT attention kernels against the fp32 formula with the SAME mask
+    (stream element ((b*heads+h)*seq+i)*seq+j), forward and backward."""
+    R = _rng_ref()
+    heads, hd, batch = 2, 64, 3
+    seed, off = 4242, 1000
+    qkv, dout = _attn_inputs(batch, seq, heads, hd, 31)
+    keep = torch.zeros(batch, seq)
+    for i, n in enumerate([seq, seq - 5, max(3, seq // 2)]):
+        keep[i, :n] = 1
+    km = ((1 - keep) * -10000.0).cuda()
+    out = torch.empty(batch * seq, heads * hd, dtype=BF16, device="cuda")
+    lse = torch.empty(batch, heads, seq, dtype=F32, device="cuda")
+    ops.attention_fwd(qkv, batch, seq, heads, hd, out, lse, key_mask=km, drop=(p, seed, off))
+    mask = torch.from_numpy(R.keep_mask(batch * heads * seq * seq, p, seed, off)).view(batch, heads, seq, seq).float()
+    x = qkv.float().cpu().requires_grad_(True)
+    q, k, v = x.view(batch, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) + km.cpu()[:, None, None, :]
+    pr = torch.softmax(s, -1) * mask / (1.0 - float(np.float32(p)))
+    o_ref = (pr @ v).transpose(1, 2).reshape(batch * seq, heads * hd)
+    assert rel(out, o_ref.detach()) < 1e-2
+    assert rel(lse, torch.logsumexp(s, -1).detach()) < 1e-4        # the normaliser ignores the dropout
+    (o_ref * dout.float().cpu()).sum().backward()
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, 0.125, key_mask=km, drop=(p, seed, off))
+    g = x.grad.clone().view(batch * seq, 3, heads * hd)
+    g[:, 0] *= 0.125
+    assert rel(dqkv, g.view(batch * seq, -1)) < 2e-2
+
+
+@pytest.mark.parametrize("seq,heads,hd", [(40, 2, 64), (412, 2, 64), (196, 3, 32)])
+def test_attention_probs_mean(ops, seq, heads, hd):
+    batch = 2
+    qkv, _ = _attn_inputs(batch, seq, heads, hd, 33)
+    keep = torch.ones(batch, seq)
+    keep[1, seq - 7:] = 0
+    km = ((1 - keep) * -10000.0).cuda()
+    got = ops.attention_probs_mean(qkv, batch, seq, heads, hd, key_mask=km)
+    q, k, v = qkv.float().cpu().view(batch, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    want = torch.softmax(q @ k.transpose(-1, -2) + km.cpu()[:, None, None, :], -1).mean(1)
+    assert rel(got, want) < 1e-4
+    assert float((got.sum(-1) - 1).abs().max()) < 1e-4

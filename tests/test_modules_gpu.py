@@ -226,3 +226,171 @@ def test_pretrain_step_c1_swin_t_vs_reference_golden(cb, golden_dir):
     batch = make_batch(2, frames=8, L=32, seed=61, size=224, vocab=30522)
     worst = _check_pretrain(m, g, batch, 2e-2)
     print({k: (round(v[0], 4), round(v[1], 5)) for k, v in worst.items()})
+
+
+# ------------------------------------------------------------------------------------------------ fine-tune (a20)
+FT_SMALL = dict(embed=32, depths=(2, 2), heads=(1, 2), img_in=64, hidden=128, vocab=1000, text_layers=2, fusion_layers=2,
+                frames_half=8, num_attention_heads=2, intermediate_size=256, max_position_embeddings=64, vocab_size=1000)
+FT_ORACLE = dict(depths=[2, 2], num_heads=[1, 2], text_layers=2, fusion_layers=2, bert_heads=2, vocab=1000)
+
+
+def _finetune_model(cb, task, **over):
+    from clover_b200.configs import finetune_cfg
+    return cb.build_model(finetune_cfg(task, num_labels=50, **dict(FT_SMALL, **over))).cuda()
+
+
+@pytest.mark.parametrize("tag,task", [("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc")])
+def test_finetune_vs_reference_golden(cb, golden_dir, tag, task):
+    """CloverFinetune (multimodal_transformer_finetune.py:59-197) on 16-frame clips (T = 8 -> the full (8,7,7) window,
+    N = 392, the BASELINE c4 / c5 shape) against the executed reference: train loss, gradients, forward_test outputs."""
+    from clover_b200.synthetic import make_finetune_batch
+    g = _g(golden_dir, f"finetune_{tag}.npz")
+    m = _finetune_model(cb, task)
+    load_synth(m, 70)
+    batch = make_finetune_batch(task, 3, frames=16, size=56, L=20, vocab=1000, seed=71, num_labels=50, choices=3)
+    kw = {k: batch[k].cuda() for k in ("token_ids", "segment_ids", "input_mask")}
+    m.train()
+    losses = m(batch["imgs"].cuda(), batch["label"].cuda(), return_loss=True, **kw)
+    total, log_vars = m._parse_losses(losses)
+    total.backward()
+    key = "retrieval_nce_loss" if task == "retrieval" else "qa_loss"
+    ref = float(g[f"loss::{key}"])
+    assert abs(log_vars[key] - ref) <= 2e-2 * max(1.0, abs(ref)), (log_vars[key], ref)
+    params = dict(m.named_parameters())
+    worst = {}
+    for k in g.files:
+        name = k.split("::")[-1]
+        if k.startswith("grad::"):
+            worst[name] = cos(params[name].grad, g[k])
+        elif k.startswith("gradsample::"):
+            worst[name] = cos(params[name].grad.reshape(-1).cpu()[torch.from_numpy(g["gradidx::" + name])], g[k])
+    assert len(worst) >= 8 and min(worst.values()) > 0.99, worst
+    m.eval()
+    with torch.no_grad():
+        res = m(batch["imgs"].cuda(), None, return_loss=False, **kw)
+    if task == "retrieval":
+        assert cos(res[0], g["test::visual_emb"]) > 0.999 and cos(res[1], g["test::text_emb"]) > 0.999
+        assert rel(res[0], g["test::visual_emb"]) < TOL and rel(res[1], g["test::text_emb"]) < TOL
+    else:
+        assert rel(res["result"], g["test::result"]) < TOL and res["result"].dtype == torch.float32
+        rows = torch.from_numpy(g["test::attention_rows"])
+        assert rel(res["attention"][:, rows.cuda()], g["test::attention_sample"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ training-mode regularisers
+def _replay():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import rng_ref
+    return rng_ref
+
+
+def test_swin_drop_path_vs_oracle(cb):
+    """Stochastic depth (timm DropPath, swin_transformer_3d.py:443,499,503; shipped rate 0.3): the product's per-sample
+    draws are replayed into the oracle; outputs and gradients must agree like the deterministic path."""
+    from clover_b200 import rng, swin
+    from oracle.state_shapes import swin_shapes
+    R = _replay()
+    torch.manual_seed(3)
+    m = swin.SwinTransformer3D(pretrained=None, pretrained2d=False, patch_size=(2, 4, 4), stride=(2, 4, 4), embed_dim=32,
+                               depths=[2, 2], num_heads=[1, 2], window_size=(8, 7, 7), drop_path_rate=0.5, patch_norm=True).cuda()
+    sd = load_synth(m, 80)
+    x = named_tensor("dp_imgs", (6, 3, 8, 56, 56), 81)
+    m.train()
+    rng.LOG = []
+    try:
+        y = m(x.cuda())
+    finally:
+        log, rng.LOG = rng.LOG, None
+    w = named_tensor("dp_w", tuple(y.shape), 82)
+    (y.float() * w.cuda()).sum().backward()
+    rp = R.Replay(log)
+    pairs = rp.drop_path_pairs([blk.drop_path_rate for layer in m.layers for blk in layer.blocks])
+    assert pairs[0] is None and any(float(s.min()) == 0.0 for pr in pairs[1:] for s in pr), "no path was dropped: weak test"
+    st = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    y_ref = O.swin_forward(st, x, [2, 2], [1, 2], drop_paths=pairs)
+    (y_ref * w).sum().backward()
+    assert rel(y, y_ref.detach()) < TOL
+    params = dict(m.named_parameters())
+    for name in ("patch_embed.proj.weight", "layers.0.blocks.1.attn.qkv.weight", "layers.0.blocks.1.attn.proj.bias",
+                 "layers.0.blocks.0.mlp.fc2.bias", "layers.1.blocks.0.mlp.fc1.weight", "layers.1.blocks.1.attn.relative_position_bias_table"):
+        assert cos(params[name].grad, st[name].grad.numpy()) > 0.99, name
+    m.eval()
+    assert rel(m(x.cuda()), O.swin_forward(st, x, [2, 2], [1, 2]).detach()) < TOL      # eval: regulariser off
+
+
+def test_bert_dropout_vs_oracle(cb):
+    """HF BERT dropout sites (embeddings, attention probabilities, self-output, output; shipped rate 0.1) in training
+    mode: the counter-based masks are regenerated in numpy from the logged (seed, offset) and replayed into the oracle."""
+    from clover_b200 import rng, text
+    from oracle.state_shapes import bert_shapes
+    R = _replay()
+    torch.manual_seed(4)
+    m = text.BertFromPretrained(num_hidden_layers=2, hidden_size=128, num_attention_heads=2, intermediate_size=256,
+                                vocab_size=1000, max_position_embeddings=64, hidden_dropout_prob=0.1,
+                                attention_probs_dropout_prob=0.1).cuda()
+    sd = load_synth(m, 90)
+    b = make_batch(4, frames=2, L=24, seed=91, size=8, vocab=1000)
+    ids, mask = b["token_ids"][:, 0], b["input_mask"][:, 0]
+    m.train()
+    rng.manual_seed(777)
+    rng.LOG = []
+    try:
+        h = m(ids.cuda(), mask.cuda())["last_hidden_state"]
+    finally:
+        log, rng.LOG = rng.LOG, None
+    w = named_tensor("bd_w", tuple(h.shape), 92)
+    (h.float() * w.cuda()).sum().backward()
+    assert [e["kind"] for e in log] == ["bert_embeddings"] + ["attn_probs", "bert_self_output", "bert_output"] * 2
+    rp = R.Replay(log)
+    st = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    h_ref = O.text_encoder(st, ids, mask, 2, heads=2, drop=rp)
+    assert rp.done()
+    (h_ref * w).sum().backward()
+    assert rel(h, h_ref.detach()) < TOL
+    params = dict(m.named_parameters())
+    for name in ("bert.embeddings.word_embeddings.weight", "bert.encoder.layer.0.attention.self.query.weight",
+                 "bert.encoder.layer.0.attention.output.dense.bias", "bert.encoder.layer.1.intermediate.dense.weight",
+                 "bert.encoder.layer.1.output.dense.weight", "bert.encoder.layer.0.attention.self.value.bias"):
+        assert cos(params[name].grad, st[name].grad.numpy()) > 0.99, name
+    m.eval()
+    h_eval = m(ids.cuda(), mask.cuda())["last_hidden_state"]
+    assert rel(h_eval, O.text_encoder(st, ids, mask, 2, heads=2).detach()) < TOL
+
+
+def test_finetune_qa_step_with_shipped_regularisers(cb):
+    """Open-ended QA fine-tune step with the shipped regularisation switched on (drop_path, BERT dropout 0.1, QA-head
+    dropout): every random draw of the product is replayed into the oracle's finetune_forward."""
+    from clover_b200 import rng
+    from clover_b200.configs import finetune_cfg
+    from clover_b200.synthetic import make_finetune_batch
+    R = _replay()
+    cfg = finetune_cfg("video_qa", num_labels=50, bert_dropout=0.1, qa_dropout=0.1, **{k: v for k, v in FT_SMALL.items()})
+    cfg["backbone"]["drop_path_rate"] = 0.3
+    torch.manual_seed(5)
+    m = cb.build_model(cfg).cuda()
+    sd = load_synth(m, 70)
+    batch = make_finetune_batch("video_qa", 4, frames=16, size=56, L=20, vocab=1000, seed=95, num_labels=50)
+    kw = {k: batch[k].cuda() for k in ("token_ids", "segment_ids", "input_mask")}
+    m.train()
+    rng.manual_seed(31337)
+    rng.LOG = []
+    try:
+        losses = m(batch["imgs"].cuda(), batch["label"].cuda(), return_loss=True, **kw)
+    finally:
+        log, rng.LOG = rng.LOG, None
+    total, log_vars = m._parse_losses(losses)
+    total.backward()
+    rp = R.Replay(log)
+    st = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rates = [blk.drop_path_rate for layer in m.backbone.layers for blk in layer.blocks]
+    ref = O.finetune_forward(st, batch, FT_ORACLE, "video_qa", train=True, drop=rp, drop_paths=rp.drop_path_pairs(rates))
+    assert rp.done()
+    ref["qa_loss"].backward()
+    want = float(ref["qa_loss"])
+    assert abs(log_vars["qa_loss"] - want) <= 2e-2 * max(1.0, abs(want)), (log_vars["qa_loss"], want)
+    params = dict(m.named_parameters())
+    for name in ("qa_head.vqa_classifier.1.weight", "multimodal_backbone.fc_in.weight",
+                 "text_backbone.bert.encoder.layer.1.attention.self.query.weight", "backbone.layers.1.blocks.0.attn.qkv.weight",
+                 "backbone.patch_embed.proj.weight"):
+        assert cos(params[name].grad, st[name].grad.numpy()) > 0.98, (name, cos(params[name].grad, st[name].grad.numpy()))
