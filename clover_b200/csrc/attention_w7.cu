@@ -378,6 +378,8 @@ struct W7BwdArgs {
   const float* table_t; int table_len, table_ld; int code_off;
   int has_kx, nwin;
   int pipe;                      // issue dV / dK steps chunk by chunk while the softmax warps are still working
+  __nv_bfloat16* dkv_part;       // bwd2 with 392 keys: dK | dV partial sums of the second query half, bf16 [rows, 2 C]
+  long long ds_half_rows;        // bwd2 with 392 keys: row offset of the second query half in the dS^T dump
 };
 
 constexpr int W7_BWD_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2-9: two column groups x four lane quarters
@@ -834,11 +836,18 @@ CLV_DEVICE void w7_bwd2_body(uint32_t ts, uint32_t td, const float* tbj, uint8_t
   }
 }
 
+// KSEQ = 196: unit = (window, head).  KSEQ = 392 (the full (8,7,7) window of 16-frame clips and of BASELINE config c2):
+// unit = (window, head, query half); a unit holds 196 queries (the TMEM budget above is unchanged) and walks all four
+// key tiles.  dQ of the half is complete; dK / dV are partial sums over the half's queries: half 0 writes them to dqkv,
+// half 1 to a.dkv_part, and attn_w7_dkv_combine_kernel adds the two.  The bias gather only needs the half's code
+// offset (196 tokens = 4 slabs -> 4 * 169) added to the per-thread table base.
+template <int KSEQ>
 __global__ void __launch_bounds__(W7_BWD_THREADS, 1)
 attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_constant__ CUtensorMap tm_kv_tile,
                     const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_e,
                     const __grid_constant__ CUtensorMap tm_kx, const __grid_constant__ CUtensorMap tm_ds, W7BwdArgs a) {
   constexpr int SEQ = 196, NQ = 208;
+  constexpr int NKT = KSEQ / W7_TILE, NH = KSEQ / SEQ;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // layout: [Q0 dO0 e0 | Q1 dO1 e1] [K0 V0 kx0 | K1 V1 kx1] [vx] [dS^T tile] table barriers   (as attn_w7_bwd_kernel)
@@ -907,25 +916,27 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
     if (lane == 0) {
       uint32_t it = 0, tt = 0;
       for (long long u = u_begin; u < u_end; ++u, ++it) {
-        const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+        const int qh = (int)(u % NH);
+        const long long uu = u / NH;
+        const int b = (int)(uu % a.batch), h = (int)(uu / a.batch);
         const int us = it & 1;
         mbar_wait(&qdo_empty[us], ((it >> 1) & 1) ^ 1);
         uint8_t* sQ = sQdO + us * unit_bytes;
         uint8_t* sDO = sQ + a.qb_bytes;
         uint8_t* sE = sDO + a.qb_bytes;
         mbar_expect_tx(&qdo_full[us], 2 * NQ * W7_ROWB + NQ * W7_XROWB);
-        const int row0 = b * SEQ;
-        tma_load_2d(sQ, &tm_q_full, &qdo_full[us], h * W7_HD, row0);
-        tma_load_2d(sDO, &tm_do_full, &qdo_full[us], h * W7_HD, row0);
-        tma_load_2d(sE, &tm_e, &qdo_full[us], 0, (int)(((long long)b * a.heads + h) * SEQ));
-        for (int t = 0; t < 2; ++t, ++tt) {
+        const int row0 = b * KSEQ;
+        tma_load_2d(sQ, &tm_q_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ);
+        tma_load_2d(sDO, &tm_do_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ);
+        tma_load_2d(sE, &tm_e, &qdo_full[us], 0, (int)(((long long)b * a.heads + h) * KSEQ + qh * SEQ));
+        for (int t = 0; t < NKT; ++t, ++tt) {
           const int ts = tt & 1;
           mbar_wait(&kv_empty[ts], ((tt >> 1) & 1) ^ 1);
           uint8_t* sK = sKV + ts * tile_bytes;
           mbar_expect_tx(&kv_full[ts], 2 * 8192 + (a.has_kx ? 4096 : 0));
           tma_load_2d(sK, &tm_kv_tile, &kv_full[ts], C + h * W7_HD, row0 + t * W7_TILE);
           tma_load_2d(sK + 8192, &tm_kv_tile, &kv_full[ts], 2 * C + h * W7_HD, row0 + t * W7_TILE);
-          if (a.has_kx) tma_load_2d(sK + 2 * 8192, &tm_kx, &kv_full[ts], 0, (b % a.nwin) * SEQ + t * W7_TILE);
+          if (a.has_kx) tma_load_2d(sK + 2 * 8192, &tm_kx, &kv_full[ts], 0, (b % a.nwin) * KSEQ + t * W7_TILE);
         }
       }
     }
@@ -944,7 +955,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         const uint32_t q_addr = smem_u32(sQdO + us * unit_bytes);
         const uint32_t do_addr = q_addr + a.qb_bytes;
         const uint32_t e_addr = do_addr + a.qb_bytes;
-        for (int t = 0; t < 2; ++t, ++tt) {
+        for (int t = 0; t < NKT; ++t, ++tt) {
           const int ts = tt & 1;
           mbar_wait(&kv_full[ts], (tt >> 1) & 1);
           tc_fence_after();
@@ -995,7 +1006,8 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
           mma_dvk(2, 0, acc);
           umma_commit(dvk_done);
           if (a.dump_ds) {
-            const int grow = (int)((((long long)u % a.batch) * a.heads + (u / a.batch)) * SEQ) + t * W7_TILE;
+            const long long uu = u / NH;
+            const int grow = (int)((u % NH) * a.ds_half_rows + ((uu % a.batch) * a.heads + (uu / a.batch)) * KSEQ) + t * W7_TILE;
             for (int q = 0; q < 4; ++q) tma_store_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
             tma_store_commit();
           }
@@ -1007,7 +1019,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
           if (a.dump_ds) tma_store_wait_read();     // (the dQ products above were only issued; the stores finish reading first)
           umma_commit(mma2_done);
           umma_commit(&kv_empty[ts]);
-          if (t == 1) umma_commit(&qdo_empty[us]);
+          if (t == NKT - 1) umma_commit(&qdo_empty[us]);
         }
       }
       if (a.dump_ds) tma_store_wait_all();
@@ -1025,7 +1037,9 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
     uint32_t it = 0, tt = 0;
     uint32_t nuse0 = 0, nuse1 = 0;
     for (long long u = u_begin; u < u_end; ++u, ++it) {
-      const int b = (int)(u % a.batch), h = (int)(u / a.batch);
+      const int qh = (int)(u % NH);
+      const long long uu = u / NH;
+      const int b = (int)(uu % a.batch), h = (int)(uu / a.batch);
       if (h != cur_h) {
         named_bar_sync(1, 256);
         const float4* src = reinterpret_cast<const float4*>(a.table_t + (long long)h * a.table_ld);
@@ -1033,9 +1047,9 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         cur_h = h;
         named_bar_sync(1, 256);
       }
-      for (int t = 0; t < 2; ++t, ++tt) {
+      for (int t = 0; t < NKT; ++t, ++tt) {
         const int j = t * W7_TILE + (valid ? r : 0);
-        const float* tbj = sTable + (a.code_off - ((j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7)));
+        const float* tbj = sTable + (a.code_off + qh * 4 * W7_SH - ((j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7)));
 #define W7B2_PUBLISH(BUF)                                                          \
         tmem_st_wait();                                                            \
         fence_proxy_async();                                                       \
@@ -1077,7 +1091,9 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
           tmem_ld_32x32(taddr + (grp ? W7B2_DK : W7B2_DV), o);
           tmem_ld_wait();
           if (valid) {
-            uint4* g = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * SEQ + j) * (3 * C) + (grp ? 1 : 2) * C + h * W7_HD);
+            uint4* g = (NH > 1 && qh == 1)
+                ? reinterpret_cast<uint4*>(a.dkv_part + ((long long)b * KSEQ + j) * (2 * C) + (grp ? 0 : 1) * C + h * W7_HD)
+                : reinterpret_cast<uint4*>(a.dqkv + ((long long)b * KSEQ + j) * (3 * C) + (grp ? 1 : 2) * C + h * W7_HD);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               g[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8]), __uint_as_float(o[q * 8 + 1])),
@@ -1089,8 +1105,8 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
-        if (t == 1) {
-          // dQ of the whole unit (both key tiles accumulated); query row i = grp*128 + r
+        if (t == NKT - 1) {
+          // dQ of the whole unit (all key tiles accumulated); query row i = grp*128 + r
           mbar_wait(mma2_done, tt & 1);
           tc_fence_after();
           const int i = grp * 128 + r;
@@ -1099,7 +1115,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
             tmem_ld_32x32(taddr + W7B2_DQ + grp * W7_HD, oq);
             tmem_ld_wait();
             if (i < SEQ) {
-              uint4* gq = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * SEQ + i) * (3 * C) + h * W7_HD);
+              uint4* gq = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * KSEQ + qh * SEQ + i) * (3 * C) + h * W7_HD);
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 gq[q] = make_uint4(pack_bf16(__uint_as_float(oq[q * 8]) * a.q_scale, __uint_as_float(oq[q * 8 + 1]) * a.q_scale),
@@ -1124,8 +1140,10 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
 // dTable[(code_i - code_j + off), h] += sum_b dS^T[b, h, j, i]   (bf16 dS^T, fp32 accumulation).
 // One thread per 8 consecutive queries of one key row (16-byte loads), 256-thread blocks over the flattened
 // (key row, query octet) index; grid = (position blocks, heads, batch splits); static 7x7 codes.
+// seq = key rows per (window, head); nqv = valid query columns (== seq, or 196 per query half of a 392-token window, whose
+// code offset the caller folds into code_off).
 __global__ void __launch_bounds__(256) attn_w7_dbias_kernel(const __nv_bfloat16* ds, int batch, int heads, int seq, int ld,
-                                                            int code_off, float* dtable) {
+                                                            int nqv, int code_off, float* dtable) {
   const int oct = ld >> 3;
   const int pos = blockIdx.x * 256 + threadIdx.x;
   if (pos >= seq * oct) return;
@@ -1147,10 +1165,28 @@ __global__ void __launch_bounds__(256) attn_w7_dbias_kernel(const __nv_bfloat16*
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int i = i0 + e;
-    if (i < seq) {
+    if (i < nqv) {
       const int ci = (i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7);
       atomicAdd(dtable + (long long)(ci - cj + code_off) * heads + h, acc[e]);
     }
+  }
+}
+
+// dqkv[row, C .. 3C) += part[row, 0 .. 2C)   (dK | dV partial sums of the second query half; 8 bf16 per thread)
+__global__ void __launch_bounds__(256) attn_w7_dkv_combine_kernel(__nv_bfloat16* dqkv, const __nv_bfloat16* part, long long rows, int C) {
+  const int per_row = 2 * C / 8;
+  const long long total = rows * per_row;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+    const long long row = x / per_row; const int c = (int)(x % per_row) * 8;
+    uint4* dst = reinterpret_cast<uint4*>(dqkv + row * 3 * C + C + c);
+    const uint4 p = __ldg(reinterpret_cast<const uint4*>(part + row * 2 * C + c));
+    uint4 d = *dst;
+    const float2 a0 = unpack_bf16(d.x), a1 = unpack_bf16(d.y), a2 = unpack_bf16(d.z), a3 = unpack_bf16(d.w);
+    const float2 b0 = unpack_bf16(p.x), b1 = unpack_bf16(p.y), b2 = unpack_bf16(p.z), b3 = unpack_bf16(p.w);
+    d.x = pack_bf16(a0.x + b0.x, a0.y + b0.y); d.y = pack_bf16(a1.x + b1.x, a1.y + b1.y);
+    d.z = pack_bf16(a2.x + b2.x, a2.y + b2.y); d.w = pack_bf16(a3.x + b3.x, a3.y + b3.y);
+    *dst = d;
   }
 }
 
@@ -1236,6 +1272,11 @@ extern "C" long long clv_attention_w7_bwd_workspace_bytes(const clv_attn_w7_desc
   const long long seq = 49LL * d->wd;
   const long long nq = (seq + 15) / 16 * 16;
   long long bytes = w7_table_bytes(d) + ((long long)d->batch * d->heads * seq * 32 + 255) / 256 * 256 + 1024;   // table^T, e rows (16 bf16)
+  if (d->wd == 8) {             // query-half units: dK | dV partial of half 1 (bf16 [rows, 2C]), dS^T of both halves [2][b*h*392, 208]
+    bytes += ((long long)d->batch * seq * 2 * d->heads * W7_HD * 2 + 255) / 256 * 256;
+    if (with_dbias) bytes += 2LL * d->batch * d->heads * seq * 208 * 2 + 256;
+    return bytes;
+  }
   if (with_dbias) bytes += (long long)d->batch * d->heads * seq * nq * 2 + 256;                 // bf16 dS^T
   return bytes;
 }
@@ -1244,12 +1285,14 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
                                     const float* lse, void* dqkv, float q_scale, float* dbias_table, void* workspace,
                                     void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (int rc = w7_check(d, "attention_w7_bwd", 4)) return rc;
+  if (int rc = w7_check(d, "attention_w7_bwd", 8)) return rc;
+  CLV_REQUIRE(d->wd != 6, "attention_w7_bwd: wd must be 2, 4 or 8 (got 6)");
   CLV_REQUIRE(qkv && out && dout && lse && dqkv && workspace, "attention_w7_bwd: null pointer");
   CLV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "attention_w7_bwd: workspace must be 256-byte aligned");
+  const bool halves = d->wd == 8;        // 392 keys: units are (window, head, query half) of the 196-query kernel
   W7BwdArgs a{};
   a.batch = d->batch; a.heads = d->heads; a.seq = 49 * d->wd; a.n_kt = d->wd / 2;
-  a.nq = (a.seq + 15) / 16 * 16;
+  a.nq = halves ? 208 : (a.seq + 15) / 16 * 16;
   a.qb_bytes = (a.nq * W7_ROWB + 1023) / 1024 * 1024;
   a.eb_bytes = (a.nq * W7_XROWB + 1023) / 1024 * 1024;
   a.n_mq = (a.nq + 127) / 128;
@@ -1263,7 +1306,7 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   } else {                               // see the accumulation order in the kernel
     a.col_dv = 480; a.col_dk = a.col_dp + 64;
   }
-  a.units = (long long)d->batch * d->heads;
+  a.units = (long long)d->batch * d->heads * (halves ? 2 : 1);
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.q_scale = q_scale;
   a.table_len = d->table_len; a.table_ld = (d->table_len + 3) & ~3;
   {
@@ -1284,7 +1327,10 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   const long long t_bytes = w7_table_bytes(d);
   __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + t_bytes);
   const long long e_bytes = ((long long)d->batch * d->heads * a.seq * 32 + 255) / 256 * 256 + 1024;
-  __nv_bfloat16* ds_out = dbias_table ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + t_bytes + e_bytes) : nullptr;
+  const long long part_bytes = halves ? ((long long)rows * 2 * d->heads * W7_HD * 2 + 255) / 256 * 256 : 0;
+  a.dkv_part = halves ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + t_bytes + e_bytes) : nullptr;
+  a.ds_half_rows = rows * d->heads;
+  __nv_bfloat16* ds_out = dbias_table ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + t_bytes + e_bytes + part_bytes) : nullptr;
   a.dump_ds = ds_out != nullptr;
   {
     const long long n = rows * d->heads;
@@ -1300,28 +1346,39 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   if (int rc = make_tmap_bf16_2d(&tdo, dout, ldo, rows, ldo, W7_HD, a.nq, 64)) return rc;
   if (int rc = make_tmap_bf16_2d(&te, e, 16, rows * d->heads, 16, 16, a.nq, 32)) return rc;
   tkx = te; tds = te;
-  if (ds_out) { if (int rc = make_tmap_bf16_2d(&tds, ds_out, a.nq, rows * d->heads, a.nq, 64, W7_TILE, 128)) return rc; }
+  if (ds_out) { if (int rc = make_tmap_bf16_2d(&tds, ds_out, a.nq, rows * d->heads * (halves ? 2 : 1), a.nq, 64, W7_TILE, 128)) return rc; }
   if (a.has_kx) { if (int rc = make_tmap_bf16_2d(&tkx, d->k_ext, 16, (long long)a.nwin * a.seq, 16, 16, 128, 32)) return rc; }
   const size_t smem = 1024 + 2 * (2 * (size_t)a.qb_bytes + a.eb_bytes) + 2 * (2 * 8192 + 4096) + 4096 + (size_t)a.n_mq * 2 * 16384 +
                       (size_t)a.table_ld * 4 + 22 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_bwd: %zu bytes of shared memory needed", smem);
   static int gen2 = -1;
   if (gen2 < 0) { const char* ev = getenv("CLOVER_B200_W7_BWD2"); gen2 = ev ? atoi(ev) : 1; }
-  auto kern = a.seq == 196 ? (gen2 ? attn_w7_bwd2_kernel : attn_w7_bwd_kernel<196>) : attn_w7_bwd_kernel<98>;
-  static size_t smem_set[2] = {0, 0};
-  if (smem > smem_set[a.seq == 196]) {
+  auto kern = halves ? attn_w7_bwd2_kernel<392>
+                     : (a.seq == 196 ? (gen2 ? attn_w7_bwd2_kernel<196> : attn_w7_bwd_kernel<196>) : attn_w7_bwd_kernel<98>);
+  const int ki = halves ? 2 : (a.seq == 196 ? 1 : 0);
+  static size_t smem_set[3] = {0, 0, 0};
+  if (smem > smem_set[ki]) {
     CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[a.seq == 196] = smem;
+    smem_set[ki] = smem;
   }
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
   kern<<<grid, W7_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, te, tkx, tds, a);
   if (int rc = after_launch("attn_w7_bwd_kernel")) return rc;
+  if (halves) {
+    const long long work = rows * (2 * d->heads * W7_HD / 8);
+    const int g = (int)std::min<long long>((work + 255) / 256, (long long)num_sms() * 16);
+    attn_w7_dkv_combine_kernel<<<g, 256, 0, stream>>>(a.dqkv, a.dkv_part, rows, d->heads * W7_HD);
+    if (int rc = after_launch("attn_w7_dkv_combine_kernel")) return rc;
+  }
   if (dbias_table) {
     const int pos_blocks = (a.seq * (a.nq / 8) + 255) / 256;
     const int zsplit = std::max(1, std::min(std::min(64, d->batch / 8), (8 * num_sms()) / (pos_blocks * d->heads) + 1));
     dim3 g(pos_blocks, d->heads, zsplit);
-    attn_w7_dbias_kernel<<<g, 256, 0, stream>>>(ds_out, d->batch, d->heads, a.seq, a.nq, a.code_off, dbias_table);
-    if (int rc = after_launch("attn_w7_dbias_kernel")) return rc;
+    for (int qh = 0; qh < (halves ? 2 : 1); ++qh) {
+      attn_w7_dbias_kernel<<<g, 256, 0, stream>>>(ds_out + (long long)qh * a.ds_half_rows * a.nq, d->batch, d->heads, a.seq, a.nq,
+                                                 halves ? 196 : a.seq, a.code_off + qh * 4 * W7_SH, dbias_table);
+      if (int rc = after_launch("attn_w7_dbias_kernel")) return rc;
+    }
   }
   return 0;
 }

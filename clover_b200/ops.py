@@ -354,7 +354,7 @@ class W7Spec:
         return USE_W7_ATTENTION and self.wd % 2 == 0 and 2 <= self.wd <= 8
 
     def bwd_ok(self):
-        return USE_W7_ATTENTION and self.wd in (2, 4)
+        return USE_W7_ATTENTION and self.wd in (2, 4, 8)
 
 
 def attention_fwd(qkv, batch, seq, heads, hd, out, lse, w7=None, **bias):

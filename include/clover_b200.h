@@ -230,6 +230,26 @@ unsigned int clv_rand_u32(unsigned long long seed, unsigned long long idx);
 int clv_rows_scale(const void* x, int x_is_bf16, void* y, int y_is_bf16, long long rows, int C, const float* scale,
                    long long rows_per_group, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step.  One multi-tensor AdamW pass over the fp32 master weights that also unscales / clips the
+ * gradients by their global norm, skips the step on a non-finite norm and refreshes the bf16 operand copies.  Replaces
+ * core/hooks/mmcv_Fp16OptimizerHook.py:96-149 + torch.optim.AdamW with paramwise lr / weight decay
+ * (configs/exp_local/pretrain_webvid_cc3m.py:129-137).  All tables live in DEVICE memory (the caller uploads them):
+ *   tensors_dev[n]               one entry per parameter (param_bf16 may be NULL)
+ *   chunk_tensor_dev[n_chunks]   tensor index of every chunk;  chunk_offset_dev[n_chunks] first element of the chunk
+ *   status_dev fp32[3]           out: [0] gradient norm (after grad_scale), [1] 1 if the step was skipped, [2] scratch
+ * g' = g * grad_scale * min(1, max_grad_norm / (norm + 1e-6)) (max_grad_norm <= 0: no clipping).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  void* param_bf16;            /* bf16 copy refreshed in the same pass, or NULL */
+  long long numel;
+  float lr, weight_decay;
+} clv_adamw_tensor_t;
+int clv_adamw_step(const clv_adamw_tensor_t* tensors_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
+                   int n_chunks, int chunk_elems, float beta1, float beta2, float eps, int step, float grad_scale,
+                   float max_grad_norm, int check_finite, float* status_dev, void* stream);
+
 /* dst[index[r],:] += src[r,:]  (fp32 atomics; word-embedding gradient of HF BertEmbeddings). */
 int clv_scatter_add_rows(const float* src, const long long* index, float* dst, long long rows, int C, void* stream);
 
@@ -273,7 +293,8 @@ int clv_attention_bwd_tc(const clv_attn_desc_t* desc, const void* qkv, const voi
  *   k_ext row = (1,1,0,0, 10*onehot3(rd), 10*onehot3(rh), 10*onehot3(rw), -256, -44, 0)
  * with (rd,rh,rw) the per-axis region of the token (region id = 9 rd + 3 rh + rw); tokens whose regions differ in
  * k axes get -100 k, which leaves the softmax exactly like the reference's -100.  NULL tables = no shift mask.
- * forward: wd even in [2, 8]; backward: wd in {2, 4}.
+ * forward: wd even in [2, 8]; backward: wd in {2, 4, 8} (wd == 8, the full (8,7,7) window of 16-frame clips and of
+ * BASELINE config c2, runs the 196-query kernel on (window, head, query half) units and adds the two dK | dV partials).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int batch, heads, wd;                  /* windows, heads, temporal window extent (seq = 49*wd) */

@@ -369,7 +369,7 @@ def test_window_attention_core(ops, dims, shifted):
 
 @pytest.mark.parametrize("dims,shifted,Bc", [((4, 14, 14), False, 2), ((4, 14, 14), True, 2), ((4, 14, 14), True, 40),
                                             ((2, 14, 14), True, 3), ((8, 14, 7), True, 2), ((16, 7, 7), True, 2),
-                                            ((6, 7, 7), False, 5)])
+                                            ((6, 7, 7), False, 5), ((8, 14, 14), False, 20), ((8, 14, 14), True, 9)])
 def test_window_attention_w7(ops, dims, shifted, Bc):
     """Specialised (wd, 7, 7) window attention (attention_w7.cu): static bias gather, shift mask / lse / D folded
     into the MMA K-extension.  Same oracle and tolerances as the generic kernels."""
