@@ -39,7 +39,8 @@ def workload_config(clips, n_gpus):
                     "fwd+bwd+grad-allreduce+AdamW",
         "clips_per_gpu": clips, "frames": 8, "resolution": 224, "caption_tokens": 32, "global_batch": clips * n_gpus,
         "parallelism": f"dp{n_gpus}", "dropout": 0.0, "drop_path": 0.0,
-        "optimizer": "torch.optim.AdamW(fused) on fp32 master weights, inside the timed region",
+        "optimizer": "clover_b200.optim.FusedAdamW (one multi-tensor kernel: AdamW on fp32 masters + grad-norm clip 15 + finite check "
+                     "+ bf16 weight refresh), paramwise weight decay of pretrain_webvid_cc3m.py:129-137, inside the timed region",
         "l2_policy": "per-step inputs (308 MB of clips) and activations (tens of GB) far exceed the 126 MB L2",
     }
 
@@ -132,6 +133,52 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def window_attention_c2(iters=5):
+    """BASELINE config c2: WindowAttention3D core, Swin-B stage-1 width (C = 128, 4 heads x 32), window (8,7,7) -> N = 392,
+    64 clip-equivalents of 8x56x56 tokens (4096 windows), shifted and unshifted, bf16 forward + backward (incl. the
+    bias-table gradient).  Algorithmic FLOPs of SURVEY.md 8(d): 4 T N C forward, 8 T N C backward."""
+    import torch
+    from clover_b200 import ops, swin, tables
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dims, heads, hd, clips = (8, 56, 56), 4, 32, 64
+    out_rows = {}
+    for shifted in (0, 1):
+        win, sh = tables.get_window_size(dims, (8, 7, 7), (4, 3, 3) if shifted else (0, 0, 0))
+        N = win[0] * win[1] * win[2]
+        nwin = (dims[0] // win[0]) * (dims[1] // win[1]) * (dims[2] // win[2])
+        batch = clips * nwin
+        g = torch.Generator(device=dev).manual_seed(1)
+        qkv = (torch.randn(batch * N, 3 * heads * hd, generator=g, device=dev) * 0.7).bfloat16()
+        dout = torch.randn(batch * N, heads * hd, generator=g, device=dev).bfloat16()
+        table = torch.randn(2535, heads, generator=g, device=dev) * 0.5
+        code, off = tables.rel_code(N, (8, 7, 7))
+        code = torch.from_numpy(code).to(dev)
+        masked = any(x > 0 for x in sh)
+        region = torch.from_numpy(tables.region_ids(*dims, win, sh)).to(dev) if masked else None
+        kw = dict(bias_table=table, rel_code=code, code_off=off, region=region, w7=swin._w7_spec(dims, win, sh, (8, 7, 7), dev))
+        out = torch.empty(batch * N, heads * hd, dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(batch, heads, N, dtype=torch.float32, device=dev)
+        dqkv = torch.empty_like(qkv)
+        dtab = torch.zeros(2535, heads, device=dev)
+
+        def both():
+            ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)
+            ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dqkv, hd ** -0.5, dbias_table=dtab, **kw)
+        for _ in range(3):
+            both()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            both()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out_rows["shifted" if shifted else "unshifted"] = {"ms_fwd_bwd": round(ms, 4),
+                                                          "tflops": round(12.0 * batch * heads * N * N * hd / ms / 1e9, 1)}
+    return out_rows
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -157,8 +204,10 @@ def run_ours(args):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
                                                         gradient_as_bucket_view=True, bucket_cap_mb=100)
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-7, betas=(0.9, 0.98), eps=1e-8,
-                            weight_decay=0.005, fused=True)
+    from clover_b200.optim import FusedAdamW, param_groups_from_cfg
+    paramwise = dict(norm_decay_mult=0.0, bias_decay_mult=0.0, custom_keys={"absolute_pos_embed": dict(decay_mult=0.0),
+                                                                             "relative_position_bias_table": dict(decay_mult=0.0)})
+    opt = FusedAdamW(param_groups_from_cfg(model, 1e-7, 0.005, paramwise), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=15.0)
     clips = args.clips
     keys = ("imgs", "label", "token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")
     host = {k: v.pin_memory() for k, v in make_batch(clips, frames=8, L=32, seed=1000 + rank).items()}
@@ -258,6 +307,9 @@ def run_ours(args):
             v, ms, cores = cpu_reference_run(1, 1, 2)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "2 clips of the same c3 step (fp32 oracle port, fwd+bwd), 1 warm-up + 1 timed step"}
+        c2 = window_attention_c2()
+        roofline["window_attn_c2_fwd_bwd"] = dict(c2, workload="c2: N=392 window (8,7,7), C=128, 4096 windows, qkv (1.6M x 384 bf16) > L2",
+                                                  frac_of_peak={k: round(v["tflops"] / sus, 4) for k, v in c2.items()})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -40,12 +40,47 @@ def w16_cat(params, key_obj):
     if ent is not None and ent[0] == vers and ent[1].device == params[0].device:
         return ent[1]
     t = ops.to_bf16(torch.cat([p.detach() for p in params], 0).contiguous())
-    _W16[key] = (vers, t, key_obj)
+    _W16[key] = (vers, t, key_obj, tuple(params))
+    row = 0
+    for p in params:                      # where each parameter lives inside the concatenation (optimizer refresh)
+        _W16_CAT_OF[id(p)] = (key, row * t.shape[1], p)
+        row += p.shape[0]
     return t
+
+
+_W16_CAT_OF = {}
+
+
+def bf16_destination(p):
+    """(device address, kind, key) of the cached bf16 operand copy of parameter p, or None: the optimizer kernel rewrites
+    the copy in the same pass that updates p (clover_b200.optim.FusedAdamW)."""
+    ent = _W16.get(id(p))
+    if ent is not None and ent[2] is p and ent[1].device == p.device and ent[1].numel() == p.numel():
+        return (ent[1].data_ptr(), "plain", id(p))
+    c = _W16_CAT_OF.get(id(p))
+    if c is not None and c[2] is p:
+        ent = _W16.get(c[0])
+        if ent is not None and ent[1].device == p.device:
+            return (ent[1].data_ptr() + 2 * c[1], "cat", c[0])
+    return None
+
+
+def bf16_restamp(p, dest):
+    """After the optimizer refreshed the copy in place: record p's new version so w16 / w16_cat keep using it."""
+    _, kind, key = dest
+    ent = _W16.get(key)
+    if ent is None:
+        return
+    if kind == "plain":
+        _W16[key] = (p._version, ent[1], p)
+    else:
+        params = ent[3]
+        _W16[key] = (tuple(q._version for q in params), ent[1], ent[2], params)
 
 
 def clear_weight_cache():
     _W16.clear()
+    _W16_CAT_OF.clear()
 
 
 def _zeros(n, device):

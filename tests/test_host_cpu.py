@@ -98,3 +98,26 @@ def test_rng_stream_offsets_are_disjoint_and_logged():
         log, rng.LOG = rng.LOG, None
     assert a == (5, 0) and b == (5, 12) and c == (5, 20)
     assert [e["kind"] for e in log] == ["x", "y", "z"] and log[1]["offset"] == 12
+
+
+def test_param_groups_follow_the_shipped_paramwise_cfg():
+    """mmcv DefaultOptimizerConstructor semantics for configs/exp_local/pretrain_webvid_cc3m.py:129-134 and
+    finetune_msrvttQA.py:90-97: no decay on norms / biases / bias tables, qa_head lr x10."""
+    import torch
+    from clover_b200 import registry
+    from clover_b200.configs import finetune_cfg
+    from clover_b200.optim import param_groups_from_cfg
+    registry.register_all()
+    m = registry.build_model(finetune_cfg("video_qa", embed=32, depths=(2, 2), heads=(1, 2), img_in=64, hidden=128, vocab=1000,
+                                          text_layers=1, fusion_layers=1, frames_half=8, num_labels=50, num_attention_heads=2,
+                                          intermediate_size=256, max_position_embeddings=64, vocab_size=1000))
+    cfg = dict(norm_decay_mult=0.0, bias_decay_mult=0.0,
+               custom_keys={"relative_position_bias_table": dict(decay_mult=0.0), "qa_head": dict(lr_mult=10)})
+    g = {x["name"]: x for x in param_groups_from_cfg(m, 1e-4, 0.05, cfg)}
+    assert g["backbone.layers.0.blocks.0.attn.relative_position_bias_table"]["weight_decay"] == 0.0
+    assert g["backbone.layers.0.blocks.0.norm1.weight"]["weight_decay"] == 0.0
+    assert g["backbone.layers.0.blocks.0.attn.qkv.bias"]["weight_decay"] == 0.0
+    assert g["backbone.layers.0.blocks.0.attn.qkv.weight"]["weight_decay"] == 0.05
+    assert abs(g["qa_head.vqa_classifier.1.weight"]["lr"] - 1e-3) < 1e-12 and g["qa_head.vqa_classifier.1.weight"]["weight_decay"] == 0.05
+    assert g["text_backbone.bert.embeddings.LayerNorm.weight"]["weight_decay"] == 0.0
+    assert len(g) == sum(1 for p in m.parameters() if p.requires_grad)

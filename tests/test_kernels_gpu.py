@@ -632,3 +632,46 @@ def test_attention_probs_mean(ops, seq, heads, hd):
     want = torch.softmax(q @ k.transpose(-1, -2) + km.cpu()[:, None, None, :], -1).mean(1)
     assert rel(got, want) < 1e-4
     assert float((got.sum(-1) - 1).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+def test_fused_adamw_vs_torch(ops):
+    """clv_adamw_step against torch.optim.AdamW + clip_grad_norm_ (the reference's optimizer + grad_clip) over several
+    steps: odd sizes (scalar tail path, unaligned views), per-group lr / weight decay, clipping active, bf16 refresh,
+    and the device-side skip of a step with a non-finite gradient."""
+    from clover_b200 import functional as Fn
+    from clover_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    shapes = [(512, 96), (30522,), (2535, 4), (7,), (3 * 16384 + 5,)]
+    base = torch.randn(sum(int(np.prod(s)) for s in shapes) + 1, device="cuda")
+    ours, ref, off = [], [], 1
+    for k, s in enumerate(shapes):
+        n = int(np.prod(s))
+        src = base[off:off + n].view(s)
+        # odd k: the parameter is a view at a 4-byte-aligned (not 16-byte-aligned) address -> the kernel's scalar path
+        ours.append(torch.nn.Parameter(src.detach().clone() if k % 2 == 0 else src.detach()))
+        ref.append(torch.nn.Parameter(src.detach().clone()))
+        off += n
+    groups = lambda ps: [dict(params=[ps[0], ps[2]], lr=1e-2, weight_decay=0.05), dict(params=ps[1:2] + ps[3:], lr=3e-3, weight_decay=0.0)]
+    o1 = FusedAdamW(groups(ours), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=2.0)
+    o2 = torch.optim.AdamW(groups(ref), betas=(0.9, 0.98), eps=1e-8)
+    w16 = Fn.w16(ours[0])                                     # a cached bf16 operand copy that the optimizer must refresh
+    for it in range(4):
+        for a, b in zip(ours, ref):
+            g = torch.randn(a.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(100 + it)) * (3.0 if it % 2 else 0.2)
+            a.grad, b.grad = g.clone(), g.clone()
+        o1.step()
+        total = torch.nn.utils.clip_grad_norm_(ref, 2.0)
+        o2.step()
+        nrm, skipped = o1.grad_norm()
+        assert not skipped and abs(nrm - float(total)) < 1e-3 * float(total)
+        for a, b in zip(ours, ref):
+            assert rel(a.detach(), b.detach()) < 2e-6, (it, tuple(a.shape))
+        assert Fn.w16(ours[0]) is w16 and torch.equal(w16, ours[0].detach().to(BF16))
+    before = [p.detach().clone() for p in ours]
+    for a in ours:
+        a.grad = torch.randn_like(a)
+    ours[1].grad[17] = float("inf")
+    o1.step()
+    nrm, skipped = o1.grad_norm()
+    assert skipped and all(torch.equal(a.detach(), b) for a, b in zip(ours, before))
