@@ -28,17 +28,23 @@ SWIN_B = dict(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024
 FLOP_PER_CLIP_FWD_BWD = 885e9          # ~295 GFLOP fwd, x3 for fwd+bwd
 
 
-def model_cfg():
-    from clover_b200.configs import pretrain_cfg
-    return pretrain_cfg(SWIN_B["embed"], SWIN_B["depths"], SWIN_B["heads"], SWIN_B["img_in"], 768, 30522, 12, 3, 4)
+def model_cfg(regularisers=True):
+    from clover_b200.configs import SHIPPED_REGULARISERS, pretrain_cfg
+    reg = SHIPPED_REGULARISERS if regularisers else {}
+    return pretrain_cfg(SWIN_B["embed"], SWIN_B["depths"], SWIN_B["heads"], SWIN_B["img_in"], 768, 30522, 12, 3, 4, **reg)
 
 
-def workload_config(clips, n_gpus):
+def workload_config(clips, n_gpus, regularisers=True):
+    from clover_b200.configs import SHIPPED_REGULARISERS
+    reg = SHIPPED_REGULARISERS if regularisers else dict(bert_dropout=0.0, drop_path_rate=0.0, t_head_dropout=0.0)
     return {
         "workload": "c3: CloverPretrain step, Video Swin-B + BERT-base text + 3-layer fusion, tri-modal NCE/ranking + MLM focal, "
                     "fwd+bwd+grad-allreduce+AdamW",
         "clips_per_gpu": clips, "frames": 8, "resolution": 224, "caption_tokens": 32, "global_batch": clips * n_gpus,
-        "parallelism": f"dp{n_gpus}", "dropout": 0.0, "drop_path": 0.0,
+        "parallelism": f"dp{n_gpus}", "dropout": reg["bert_dropout"], "drop_path": reg["drop_path_rate"],
+        "text_head_dropout": reg["t_head_dropout"],
+        "regularisers": "shipped rates of configs/exp_local/pretrain_webvid_cc3m.py (training mode)" if regularisers else
+                        "all zero (the parity configuration; --parity-config)",
         "optimizer": "clover_b200.optim.FusedAdamW (one multi-tensor kernel: AdamW on fp32 masters + grad-norm clip 15 + finite check "
                      "+ bf16 weight refresh), paramwise weight decay of pretrain_webvid_cc3m.py:129-137, inside the timed region",
         "l2_policy": "per-step inputs (308 MB of clips) and activations (tens of GB) far exceed the 126 MB L2",
@@ -86,7 +92,7 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, clips=2, seed=1000):
+def cpu_reference_run(steps, warmup, clips=2, seed=1000, regularisers=True):
     """The reference's algorithm (oracle port, fp32, plain PyTorch CPU ops) on the host cores: fwd + bwd of the same
     pre-train step on a bounded sample of `clips` clips per step.  Returns (clips_per_sec, ms_per_step, cores)."""
     import torch
@@ -104,7 +110,8 @@ def cpu_reference_run(steps, warmup, clips=2, seed=1000):
     for it in range(warmup + steps):
         batch = make_batch(clips, frames=8, L=32, seed=seed + it)
         t0 = time.perf_counter()
-        losses, _ = O.pretrain_forward(state, batch, cfg)
+        drop, dps = O.random_regularisers(cfg["depths"], clips, 0.3, 0.1, seed + it) if regularisers else (None, None)
+        losses, _ = O.pretrain_forward(state, batch, cfg, drop=drop, drop_paths=dps)
         O.total_loss(losses).backward()
         for v in state.values():
             v.grad = None
@@ -119,12 +126,12 @@ def run_reference(args):
     if rank != 0:
         return
     clips = 2
-    value, ms, cores = cpu_reference_run(args.steps, args.warmup, clips)
+    value, ms, cores = cpu_reference_run(args.steps, args.warmup, clips, regularisers=not args.parity_config)
     sample = f"{clips} clips/step of the c3 step (Swin-B + BERT-base + fusion, 8x224x224, L=32), fp32, fwd+bwd, no optimizer"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(64, args.gpus),
+        "dtype": "f32", "data": "synthetic", "config": workload_config(64, args.gpus, not args.parity_config),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,7 +201,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     registry.register_all()
     torch.manual_seed(0)
-    model = registry.build_model(model_cfg()).to(dev)
+    model = registry.build_model(model_cfg(not args.parity_config)).to(dev)
     model.train()
     # parameters the reference never gives a gradient (text pooler, fusion's unused bert_embedding): keep DDP static
     for n, p in model.named_parameters():
@@ -304,7 +311,7 @@ def run_ours(args):
                     "step_model_tflops": FLOP_PER_CLIP_FWD_BWD * clips / (ms_step * 1e-3) / 1e12}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores = cpu_reference_run(1, 1, 2)
+            v, ms, cores = cpu_reference_run(1, 1, 2, regularisers=not args.parity_config)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "2 clips of the same c3 step (fp32 oracle port, fwd+bwd), 1 warm-up + 1 timed step"}
         c2 = window_attention_c2()
@@ -313,7 +320,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": workload_config(clips, world),
+            "data": "synthetic", "config": workload_config(clips, world, not args.parity_config),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(loss_host.numel() * 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "loss": float(loss_host), "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
@@ -331,6 +338,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU (BASELINE config c3: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-config", action="store_true",
+                    help="zero dropout / drop-path (the configuration of the parity tests) instead of the shipped training rates")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

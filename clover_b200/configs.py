@@ -3,8 +3,10 @@ these helpers reproduce their ``model = dict(...)`` so tests, smoke() and bench.
 
 
 def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024, hidden=768, vocab=30522,
-                 text_layers=12, fusion_layers=3, frames_half=4, bert_dropout=0.0, **bert):
-    """The model dict of configs/exp_local/pretrain_webvid_cc3m.py:22-104 (+ swin3d_base_stride.py)."""
+                 text_layers=12, fusion_layers=3, frames_half=4, bert_dropout=0.0, drop_path_rate=0.0, t_head_dropout=0.0, **bert):
+    """The model dict of configs/exp_local/pretrain_webvid_cc3m.py:22-104 (+ swin3d_base_stride.py).  The stochastic
+    regularisers default to 0 (parity runs); the shipped values are bert_dropout=0.1 (HF BertConfig defaults),
+    drop_path_rate=0.3 (swin3d_base_stride.py:7) and t_head_dropout=0.1 (pretrain_webvid_cc3m.py:86): SHIPPED_REGULARISERS."""
     aux = ["token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask"]
     # HF BERT's dropout rates; the reference classes swallow unknown kwargs (bert_from_hugface.py:9, cross_transformer.py:15)
     drop = dict(hidden_dropout_prob=bert_dropout, attention_probs_dropout_prob=bert_dropout)
@@ -12,7 +14,7 @@ def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1
         type="CloverPretrain", freeze_stage=None, separate_test=True, use_Cmask=True,
         backbone=dict(type="SwinTransformer3D", stride=(2, 4, 4), mask_token=True, pretrained2d=False, pretrained=None,
                       embed_dim=embed, depths=list(depths), num_heads=list(heads), patch_size=(2, 4, 4),
-                      window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True),
+                      window_size=(8, 7, 7), drop_path_rate=drop_path_rate, patch_norm=True),
         freeze_text_backbone=None, text_vocab_size=vocab,
         mm_backbone=dict(type="CrossModalTransformerFromPretrained", use_text_cls=True, use_prompt=False,
                          pretrained_model="bert-base-uncased", num_hidden_layers=fusion_layers, img_in_size=img_in,
@@ -27,11 +29,14 @@ def pretrain_cfg(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1
         mlm_ssl_head=dict(V=dict(type="NCEHeadForVision", visual_in_channels=hidden, cross_in_channels=hidden,
                                  hidden_dim=hidden, ln=True, vts_embed_dim=hidden, dropout_ratio=0),
                           T=dict(type="NCEHeadForText", cross_in_channels=hidden, vts_embed_dim=hidden, text_bn=False,
-                                 dropout_ratio=0.0)),
+                                 dropout_ratio=t_head_dropout)),
         mlm_loss=dict(type="SoftmaxFocalLossMultiClass", gamma=2.0), loss_type=dict(type="CrossEntropyLoss"),
         ssl_loss=dict(type="ExclusiveNCEwithRankingLoss", temperature=0.05, use_rank=True, use_rank_ttm=True,
                       use_rank_trtm=False, margin_ttm=5.0, margin_trtm=10.0),
         symmetry_rank=True, train_cfg=dict(aux_info=aux))
+
+
+SHIPPED_REGULARISERS = dict(bert_dropout=0.1, drop_path_rate=0.3, t_head_dropout=0.1)
 
 
 def finetune_cfg(task="retrieval", embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024, hidden=768, vocab=30522,
@@ -39,7 +44,8 @@ def finetune_cfg(task="retrieval", embed=128, depths=(2, 2, 18, 2), heads=(4, 8,
     """The model dicts of configs/exp_local/finetune_msrvtt_retrieval.py:22-70 (task='retrieval'),
     finetune_msrvttQA.py:23-66 (task='video_qa', open-ended head) and finetune_msrvtt_mc.py (task='video_qa_mc',
     multiple-choice head).  frames_half is mm_backbone.num_frames (must cover T = frames/2)."""
-    base = pretrain_cfg(embed, depths, heads, img_in, hidden, vocab, text_layers, fusion_layers, frames_half, bert_dropout, **bert)
+    base = pretrain_cfg(embed, depths, heads, img_in, hidden, vocab, text_layers, fusion_layers, frames_half, bert_dropout,
+                        **bert)
     cfg = dict(type="CloverFinetune", freeze_stage=None, text_vocab_size=vocab, cls_head=None, itm_head=None,
                backbone=dict(base["backbone"], mask_token=False), mm_backbone=base["mm_backbone"],
                text_backbone=base["text_backbone"], train_cfg=dict(aux_info=["token_ids", "segment_ids", "input_mask"]))

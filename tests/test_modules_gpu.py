@@ -394,3 +394,36 @@ def test_finetune_qa_step_with_shipped_regularisers(cb):
                  "text_backbone.bert.encoder.layer.1.attention.self.query.weight", "backbone.layers.1.blocks.0.attn.qkv.weight",
                  "backbone.patch_embed.proj.weight"):
         assert cos(params[name].grad, st[name].grad.numpy()) > 0.98, (name, cos(params[name].grad, st[name].grad.numpy()))
+
+
+def test_pretrain_step_with_shipped_regularisers_reproducible(cb, golden_dir):
+    """The full pre-train step with the shipped training rates (drop_path 0.3, BERT dropout 0.1, text-head dropout 0.1):
+    the counter-based streams make it reproducible bit for bit from (torch seed, rng seed); all gradients are finite;
+    eval mode switches every regulariser off and reproduces the deterministic golden losses."""
+    from clover_b200 import rng
+    from clover_b200.configs import SHIPPED_REGULARISERS, pretrain_cfg
+    bert = dict(num_attention_heads=2, intermediate_size=256, max_position_embeddings=64, vocab_size=1000)
+    m = cb.build_model(pretrain_cfg(32, (2, 2), (1, 2), 64, 128, 1000, 2, 2, 2, **SHIPPED_REGULARISERS, **bert)).cuda()
+    load_synth(m, 50)
+    batch = make_batch(3, frames=4, L=16, seed=51, size=56, vocab=1000)
+    kw = {k: batch[k].cuda() for k in ("token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")}
+
+    def run(train):
+        m.train(train)
+        m.zero_grad(set_to_none=True)
+        torch.manual_seed(11)
+        rng.manual_seed(12)
+        losses = m(batch["imgs"].cuda(), batch["label"].cuda(), return_loss=True, **kw)
+        total, log_vars = m._parse_losses(losses)
+        total.backward()
+        return log_vars, {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    a, ga = run(True)
+    b, gb = run(True)
+    assert a == b and all(torch.equal(ga[n], gb[n]) for n in ga)
+    assert all(bool(torch.isfinite(g).all()) for g in ga.values())
+    g = _g(golden_dir, "pretrain_tiny.npz")
+    assert abs(a["loss"] - float(g["loss::loss"])) > 1e-3                      # the regularisers did act
+    e, _ = run(False)
+    for k in ("mlm_loss", "nce_loss", "rank_t_tm_loss", "v_nce_loss", "rank_v_vm_loss"):
+        ref = float(g[f"loss::{k}"])
+        assert abs(e[k] - ref) <= 2e-2 * max(1.0, abs(ref)), (k, e[k], ref)
