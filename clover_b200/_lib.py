@@ -126,6 +126,7 @@ SIGNATURES = {
     "clv_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, c_vp]),
     "clv_gelu": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, c_vp]),
     "clv_patchify": (C.c_int, [c_vp, c_vp] + [C.c_int] * 8 + [c_vp]),
+    "clv_patchify_u8": (C.c_int, [c_vp, c_vp, c_vp, c_vp] + [C.c_int] * 8 + [c_vp]),
     "clv_grouped_colsum": (C.c_int, [c_vp, C.c_int, c_ll, c_ll, C.c_int, C.c_int, C.c_int, C.c_float, c_vp, C.c_int, c_vp]),
     "clv_rows_affine": (C.c_int, [C.POINTER(RowsAffine), c_vp]),
     "clv_cosine_scores": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp]),

@@ -55,8 +55,13 @@ __global__ void gelu_kernel(const void* x, int x_bf16, const void* dy, int dy_bf
 // one token row (b, d, hp) through shared memory (coalesced reads) and writes the patch matrix
 // rows (column order (c, kd, kh, kw) = the conv weight's flattening) with coalesced bf16 stores.
 // Out-of-range input (the F.pad of :675-680) reads as zero.
-__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Cin, int F,
-                                int H, int W, int pd, int ph, int pw, int D, int Hp, int Wp) {
+// TIN = float: clips normalised by the CPU pipeline (the shipped configs).  TIN = unsigned char: raw frames, normalised here
+// as (v - mean[c]) * inv_std[c] -- the GPUNormalize module hook of utils/module_hooks.py:35-87 folded into the load, so the
+// host->device copy carries 1 byte per sample instead of 4 and no separate normalisation pass runs.
+template <typename TIN>
+__global__ void patchify_kernel(const TIN* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Cin, int F,
+                                int H, int W, int pd, int ph, int pw, int D, int Hp, int Wp, const float* __restrict__ mean,
+                                const float* __restrict__ inv_std) {
   extern __shared__ float tile[];            // [Cin*pd*ph][Wp*pw]
   const int hp = blockIdx.x % Hp, d = (blockIdx.x / Hp) % D, b = blockIdx.x / (Hp * D);
   const int nrow = Cin * pd * ph, roww = Wp * pw;
@@ -65,7 +70,10 @@ __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __re
     const int kh = r % ph, kd = (r / ph) % pd, c = r / (ph * pd);
     const int f = d * pd + kd, h = hp * ph + kh;
     float v = 0.f;
-    if (f < F && h < H && col < W) v = x[(((long long)b * Cin + c) * F + f) * H * W + (long long)h * W + col];
+    if (f < F && h < H && col < W) {
+      v = (float)x[(((long long)b * Cin + c) * F + f) * H * W + (long long)h * W + col];
+      if (mean) v = (v - __ldg(mean + c)) * __ldg(inv_std + c);
+    }
     tile[i] = v;
   }
   __syncthreads();
@@ -240,12 +248,29 @@ extern "C" int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int 
   CLV_REQUIRE(smem <= 200 * 1024, "clv_patchify: row tile too large (%zu bytes)", smem);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  patchify_kernel<<<B * D * Hp, 256, smem, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, F, H, W, pd, ph,
-                                                    pw, D, Hp, Wp);
+  patchify_kernel<float><<<B * D * Hp, 256, smem, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, F, H, W, pd,
+                                                           ph, pw, D, Hp, Wp, nullptr, nullptr);
   return after_launch("patchify_kernel");
+}
+
+extern "C" int clv_patchify_u8(const unsigned char* x, const float* mean, const float* inv_std, void* out_bf16, int B, int Cin,
+                               int F, int H, int W, int pd, int ph, int pw, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(x && mean && inv_std && out_bf16 && B > 0 && pw % 2 == 0, "clv_patchify_u8: bad arguments");
+  const int D = (F + pd - 1) / pd, Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
+  const size_t smem = (size_t)Cin * pd * ph * Wp * pw * sizeof(float);
+  CLV_REQUIRE(smem <= 200 * 1024, "clv_patchify_u8: row tile too large (%zu bytes)", smem);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    CLV_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  patchify_kernel<unsigned char><<<B * D * Hp, 256, smem, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, F, H, W,
+                                                                   pd, ph, pw, D, Hp, Wp, mean, inv_std);
+  return after_launch("patchify_kernel<u8>");
 }
 
 extern "C" int clv_grouped_colsum(const void* x, int x_is_bf16, long long ld, long long rows, int C, int div, int mod,

@@ -499,9 +499,9 @@ class PatchEmbedFn(torch.autograd.Function):
     """PatchEmbed3D (:671-688) + SimMIM mask-token blend (:222-230): patchify -> GEMM -> LN(+blend)."""
 
     @staticmethod
-    def forward(ctx, imgs, weight, bias, nw, nb, mask, token, patch):
+    def forward(ctx, imgs, weight, bias, nw, nb, mask, token, patch, in_norm=None):
         B = imgs.shape[0]
-        cols, (D, Hp, Wp) = ops.patchify(imgs.contiguous(), patch)
+        cols, (D, Hp, Wp) = ops.patchify(imgs.contiguous(), patch, norm=in_norm)
         C = weight.shape[0]
         T = cols.shape[0]
         wb = w16(weight)
@@ -548,7 +548,7 @@ class PatchEmbedFn(torch.autograd.Function):
             dy16 = ops.to_bf16(dout)
         dW = _wgrad(dy16, cols, C, cols.shape[1]).view(ctx.wshape)
         dB = _colsum(dy16, C)
-        return None, dW, dB, dgn, dbn, None, dtok, None
+        return None, dW, dB, dgn, dbn, None, dtok, None, None
 
 
 class PatchMergeFn(torch.autograd.Function):

@@ -482,16 +482,24 @@ def gelu(x, y, dy=None):
 
 
 @_profiled("patchify")
-def patchify(x, patch):
-    """x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw] and (D,Hp,Wp)."""
+def patchify(x, patch, norm=None):
+    """x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw] and (D,Hp,Wp).
+    x uint8 + norm=(mean, inv_std) fp32 [Cin] device tensors: raw frames normalised in the load (GPUNormalize)."""
     _need_cuda(x)
-    if x.dtype != F32 or not x.is_contiguous():
-        raise ValueError("patchify: contiguous fp32 input required")
+    if x.dtype not in (F32, torch.uint8) or not x.is_contiguous():
+        raise ValueError("patchify: contiguous fp32 (or uint8 + norm) input required")
     B, Cin, Fr, H, W = x.shape
     pd, ph, pw = patch
     D, Hp, Wp = -(-Fr // pd), -(-H // ph), -(-W // pw)
     out = torch.empty(B * D * Hp * Wp, Cin * pd * ph * pw, dtype=BF16, device=x.device)
-    _lib.check(_lib.load().clv_patchify(_ptr(x), _ptr(out), B, Cin, Fr, H, W, pd, ph, pw, _stream()), "clv_patchify")
+    if x.dtype == torch.uint8:
+        if norm is None or norm[0].numel() != Cin or norm[1].numel() != Cin or norm[0].dtype != F32 or norm[1].dtype != F32:
+            raise ValueError("patchify: uint8 frames need norm=(mean, inv_std) fp32 [Cin] (set_input_normalization)")
+        _need_cuda(*norm)
+        _lib.check(_lib.load().clv_patchify_u8(_ptr(x), _ptr(norm[0]), _ptr(norm[1]), _ptr(out), B, Cin, Fr, H, W, pd, ph, pw,
+                                               _stream()), "clv_patchify_u8")
+    else:
+        _lib.check(_lib.load().clv_patchify(_ptr(x), _ptr(out), B, Cin, Fr, H, W, pd, ph, pw, _stream()), "clv_patchify")
     return out, (D, Hp, Wp)
 
 

@@ -60,6 +60,7 @@ class Registry:
 
 MODELS = Registry("models")
 BACKBONES = HEADS = LOSSES = RECOGNIZERS = MODELS
+MODULE_HOOKS = Registry("module_hooks")
 
 
 def build_backbone(cfg):
@@ -113,4 +114,12 @@ def register_all(target=None, force=True):
     if target is not MODELS:
         for name, cls in plugin_classes().items():
             MODELS.register_module(name=name, force=True, module=cls)
+    # the GPUNormalize module hook lives in its own registry (mmaction/utils/module_hooks.py:4,35)
+    from .swin import GPUNormalize
+    try:
+        from mmaction.utils.module_hooks import MODULE_HOOKS as hooks
+        hooks.register_module(name="GPUNormalize", force=force, module=GPUNormalize)
+    except Exception:
+        pass
+    MODULE_HOOKS.register_module(name="GPUNormalize", force=True, module=GPUNormalize)
     return target

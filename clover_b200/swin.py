@@ -256,16 +256,39 @@ class PatchEmbed3D(nn.Module):
             raise NotImplementedError("clover_b200: PatchEmbed3D needs stride == patch_size (true for every Clover config)")
         self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=patch_size, stride=stride)
         self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+        self.input_norm = None            # (mean, 1/std) fp32 [Cin]: raw uint8 frames are normalised inside the patch gather
+
+    def set_input_normalization(self, mean, std):
+        """Accept raw uint8 clips and normalise them as (v - mean[c]) / std[c] inside the patch-gather kernel -- the
+        reference's GPUNormalize module hook (utils/module_hooks.py:35-87) without its extra pass over the clip.
+        mean / std: per-channel sequences (img_norm_cfg of configs/_base_/datasets_local/*.py); None switches it off."""
+        if mean is None:
+            self.input_norm = None
+            return
+        m = torch.as_tensor(mean, dtype=torch.float32).reshape(-1)
+        s = torch.as_tensor(std, dtype=torch.float32).reshape(-1)
+        if m.numel() != self.in_chans or s.numel() != self.in_chans:
+            raise ValueError(f"set_input_normalization: need {self.in_chans} means and stds")
+        self.input_norm = (m, 1.0 / s)
 
     def forward_tokens(self, x, mask=None, mask_token=None):
-        """x fp32 (B, Cin, F, H, W) -> (tokens fp32 [B*D*Hp*Wp, C], (B, D, Hp, Wp))."""
+        """x fp32 (or uint8 after set_input_normalization) (B, Cin, F, H, W) -> (tokens fp32 [B*D*Hp*Wp, C], (B, D, Hp, Wp))."""
         if mask is not None and self.norm is None:
             raise NotImplementedError("clover_b200: mask-token blend requires patch_norm=True")
         B, _, Fr, H, W = x.shape
         pd, ph, pw = self.patch_size
         D, Hp, Wp = -(-Fr // pd), -(-H // ph), -(-W // pw)
         nw, nb = (self.norm.weight, self.norm.bias) if self.norm is not None else (None, None)
-        y = Fn.PatchEmbedFn.apply(x.float(), self.proj.weight, self.proj.bias, nw, nb, mask, mask_token, self.patch_size)
+        norm = None
+        if x.dtype == torch.uint8:
+            if self.input_norm is None:
+                raise TypeError("PatchEmbed3D: uint8 clips need set_input_normalization(mean, std) (GPUNormalize)")
+            if self.input_norm[0].device != x.device:
+                self.input_norm = tuple(t.to(x.device) for t in self.input_norm)
+            norm = self.input_norm
+        else:
+            x = x.float()
+        y = Fn.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, nw, nb, mask, mask_token, self.patch_size, norm)
         return y, (B, D, Hp, Wp)
 
     def forward(self, x):
@@ -305,6 +328,10 @@ class SwinTransformer3D(nn.Module):
             self.mask_token = nn.Parameter(torch.zeros(1, self.embed_dim, 1, 1, 1))
             trunc_normal_(self.mask_token, mean=0.0, std=0.02)
         self._freeze_stages()
+
+    def set_input_normalization(self, mean, std):
+        """Raw uint8 clips in, normalisation folded into the patch gather (see PatchEmbed3D.set_input_normalization)."""
+        self.patch_embed.set_input_normalization(mean, std)
 
     def _freeze_stages(self):
         if self.frozen_stages >= 0:
@@ -402,3 +429,25 @@ class SwinTransformer3D(nn.Module):
         super().train(mode)
         self._freeze_stages()
         return self
+
+
+class GPUNormalize:
+    """Drop-in for the reference's module hook of the same name (mmaction/utils/module_hooks.py:35-87;
+    ``module_hooks=[dict(type='GPUNormalize', hooked_module='backbone', hook_pos='forward_pre', input_format='NCTHW',
+    mean=[...], std=[...])]``).  The reference hook converts the uint8 clip to float and normalises it in a separate pass;
+    this one hands mean / std to the backbone's patch gather and lets the uint8 clip through untouched."""
+
+    def __init__(self, input_format, mean, std):
+        if input_format != "NCTHW":
+            raise ValueError(f"clover_b200.GPUNormalize supports input_format='NCTHW' (video clips), got {input_format}")
+        self.input_format, self.mean, self.std = input_format, list(mean), list(std)
+
+    def hook_func(self):
+        def normalize_hook(module, inputs):
+            x = inputs[0]
+            assert x.dtype == torch.uint8, f"The previous augmentation should use uint8 data type, but get {x.dtype}"
+            if not hasattr(module, "set_input_normalization"):
+                raise TypeError("GPUNormalize: the hooked module must be a clover_b200 SwinTransformer3D / PatchEmbed3D")
+            module.set_input_normalization(self.mean, self.std)
+            return inputs
+        return normalize_hook

@@ -191,6 +191,11 @@ int clv_gelu(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, void*
 /* PatchEmbed3D's Conv3d(kernel == stride) as a patch matrix (swin_transformer_3d.py:665,671-681):
  * x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw], column order (c,kd,kh,kw); zero padding. */
 int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int F, int H, int W, int pd, int ph, int pw, void* stream);
+/* Same patch matrix from RAW uint8 frames [B, Cin, F, H, W], normalised on the fly as (v - mean[c]) * inv_std[c]: the
+ * GPUNormalize module hook (utils/module_hooks.py:35-87; mean / std of configs/_base_/datasets_local/*.py img_norm_cfg)
+ * folded into the load -- 1 byte per sample crosses PCIe instead of 4 and no normalisation pass runs. */
+int clv_patchify_u8(const unsigned char* x, const float* mean, const float* inv_std, void* out_bf16, int B, int Cin, int F,
+                    int H, int W, int pd, int ph, int pw, void* stream);
 
 /* out[g,c] (+)= scale * sum_{r : (r/div)%mod == g} x[r,c]; out fp32 [mod, C].  nn.Linear bias grads,
  * AdaptiveAvgPool3d (ssl_head.py:105-106), d vis_space_pos / vis_tempor_pos / position embeddings. */

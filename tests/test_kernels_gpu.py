@@ -675,3 +675,20 @@ def test_fused_adamw_vs_torch(ops):
     o1.step()
     nrm, skipped = o1.grad_norm()
     assert skipped and all(torch.equal(a.detach(), b) for a, b in zip(ours, before))
+
+
+# ------------------------------------------------------------------------------------------------ input staging
+def test_patchify_uint8_fused_normalise(ops):
+    """Raw uint8 frames normalised inside the patch gather == GPUNormalize (x.float().sub_(mean).div_(std),
+    utils/module_hooks.py:80-83) followed by the fp32 patch gather; odd sizes exercise the zero padding."""
+    mean = torch.tensor([123.675, 116.28, 103.53], device="cuda")
+    std = torch.tensor([58.395, 57.12, 57.375], device="cuda")
+    for shape in ((2, 3, 8, 56, 56), (1, 3, 5, 30, 26)):
+        x8 = torch.randint(0, 256, shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(7)).cuda()
+        xf = (x8.float() - mean.view(1, 3, 1, 1, 1)) / std.view(1, 3, 1, 1, 1)
+        want, dims = ops.patchify(xf.contiguous(), (2, 4, 4))
+        got, dims2 = ops.patchify(x8, (2, 4, 4), norm=(mean, 1.0 / std))
+        assert dims == dims2 and got.shape == want.shape
+        assert rel(got.float(), want.float()) < 4e-3              # (v - m) * (1/s) vs (v - m) / s before the bf16 rounding
+    with pytest.raises(ValueError):
+        ops.patchify(x8, (2, 4, 4))

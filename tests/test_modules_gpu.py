@@ -467,3 +467,25 @@ def test_retrieval_evaluation_vs_reference_golden(cb, golden_dir):
         txt[i * 5 + l] = vid[i] * 3
     want = float(np.mean(np.argmax((vid @ txt.T).reshape(7, 7, 5)[np.arange(7), np.arange(7)], -1) == lab))
     assert abs(E.acc_for_msrvtt_mc(vid, txt, lab)["acc"] - want) < 1e-9 and want >= 5 / 7
+
+
+def test_swin_uint8_clips_gpu_normalize_hook(cb):
+    """GPUNormalize module hook (utils/module_hooks.py:35-87) on the drop-in backbone: uint8 clips through the hook ==
+    the CPU-normalised fp32 clip through the plain backbone."""
+    from clover_b200 import swin
+    torch.manual_seed(6)
+    m = swin.SwinTransformer3D(pretrained=None, pretrained2d=False, patch_size=(2, 4, 4), stride=(2, 4, 4), embed_dim=32,
+                               depths=[2, 2], num_heads=[1, 2], window_size=(8, 7, 7), drop_path_rate=0.0, patch_norm=True).cuda().eval()
+    load_synth(m, 80)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    x8 = torch.randint(0, 256, (2, 3, 8, 56, 56), dtype=torch.uint8, generator=torch.Generator().manual_seed(9)).cuda()
+    xf = (x8.float() - torch.tensor(mean, device="cuda").view(1, 3, 1, 1, 1)) / torch.tensor(std, device="cuda").view(1, 3, 1, 1, 1)
+    with torch.no_grad():
+        want = m(xf)
+        h = m.register_forward_pre_hook(swin.GPUNormalize("NCTHW", mean, std).hook_func())
+        got = m(x8)
+        h.remove()
+    assert rel(got, want) < 5e-3
+    m.set_input_normalization(None, None)
+    with pytest.raises(TypeError):
+        m(x8)
