@@ -102,3 +102,42 @@ def make_finetune_batch(task, B, frames=16, size=224, L=40, vocab=30522, seed=1,
     hi = num_labels if task == "video_qa" else 1
     batch["label"] = torch.from_numpy(np.random.default_rng([seed, 5]).integers(0, hi, size=(B, 1)))
     return batch
+
+
+def _swin_shapes(embed, depths, heads):
+    sh = {"patch_embed.proj.weight": (embed, 3, 2, 4, 4), "patch_embed.proj.bias": (embed,),
+          "patch_embed.norm.weight": (embed,), "patch_embed.norm.bias": (embed,)}
+    for s, (d, nh) in enumerate(zip(depths, heads)):
+        C = embed * 2 ** s
+        for j in range(d):
+            p = f"layers.{s}.blocks.{j}."
+            sh.update({p + "norm1.weight": (C,), p + "norm1.bias": (C,), p + "attn.relative_position_bias_table": (2535, nh),
+                       p + "attn.qkv.weight": (3 * C, C), p + "attn.qkv.bias": (3 * C,), p + "attn.proj.weight": (C, C),
+                       p + "attn.proj.bias": (C,), p + "norm2.weight": (C,), p + "norm2.bias": (C,),
+                       p + "mlp.fc1.weight": (4 * C, C), p + "mlp.fc1.bias": (4 * C,), p + "mlp.fc2.weight": (C, 4 * C),
+                       p + "mlp.fc2.bias": (C,)})
+        if s < len(depths) - 1:
+            p = f"layers.{s}.downsample."
+            sh.update({p + "reduction.weight": (2 * C, 4 * C), p + "norm.weight": (4 * C,), p + "norm.bias": (4 * C,)})
+    Cf = embed * 2 ** (len(depths) - 1)
+    sh.update({"norm.weight": (Cf,), "norm.bias": (Cf,)})
+    return sh
+
+
+def synth_swin2d_checkpoint(path, embed=32, depths=(2, 2), heads=(1, 2), window2d=6, seed=90):
+    """A synthetic 2-D Swin checkpoint (the layout of the ImageNet files inflate_weights expects): 2-D patch-embed kernel,
+    (2*window2d-1)^2 bias tables (window 6 -> 11x11, so the 13x13 target needs the bicubic resize), stale index buffers."""
+    sh = _swin_shapes(embed, list(depths), list(heads))
+    sd = {}
+    for k, shape in sh.items():
+        if k == "patch_embed.proj.weight":
+            shape = (embed, 3, 4, 4)
+        elif k.endswith("relative_position_bias_table"):
+            shape = ((2 * window2d - 1) ** 2, shape[1])
+        sd[k] = named_tensor("ck2d." + k, shape, seed)
+    sd["layers.0.blocks.0.attn.relative_position_index"] = torch.zeros(36, 36, dtype=torch.long)
+    sd["layers.0.blocks.1.attn_mask"] = torch.zeros(4, 36, 36)
+    torch.save({"state_dict": sd}, path)
+    return sd
+
+

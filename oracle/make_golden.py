@@ -17,7 +17,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ref_shim  # noqa: E402
-from clover_b200.synthetic import named_tensor, synth_state_dict, make_batch, make_finetune_batch  # noqa: E402
+from clover_b200.synthetic import named_tensor, synth_state_dict, make_batch, make_finetune_batch, synth_swin2d_checkpoint  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -378,6 +378,25 @@ def gen_eval(ref):
     print({k: float(v) for k, v in out.items()})
 
 
+def gen_inflate(ref):
+    """Executes SwinTransformer3D.inflate_weights (swin_transformer_3d.py:130-181) on the synthetic 2-D checkpoint."""
+    import logging
+    import tempfile
+    path = os.path.join(tempfile.mkdtemp(), "swin2d.pth")
+    synth_swin2d_checkpoint(path)
+    torch.manual_seed(0)
+    m = ref.swin.SwinTransformer3D(pretrained=path, pretrained2d=True, patch_size=(2, 4, 4), embed_dim=32, depths=[2, 2],
+                                   num_heads=[1, 2], window_size=(8, 7, 7), patch_norm=True)
+    m.inflate_weights(logging.getLogger("golden"))
+    sd = m.state_dict()
+    out = {"patch_embed.proj.weight": sd["patch_embed.proj.weight"].numpy(),
+           "layers.0.blocks.1.attn.relative_position_bias_table": sd["layers.0.blocks.1.attn.relative_position_bias_table"].numpy(),
+           "layers.1.blocks.0.attn.relative_position_bias_table": sd["layers.1.blocks.0.attn.relative_position_bias_table"].numpy(),
+           "layers.1.blocks.0.mlp.fc1.weight": sd["layers.1.blocks.0.mlp.fc1.weight"].numpy()}
+    np.savez_compressed(os.path.join(OUT, "inflate_2d.npz"), **out)
+    print({k: v.shape for k, v in out.items()})
+
+
 def gen_state_keys(ref):
     cfg = pretrain_cfg(128, [2, 2, 18, 2], [4, 8, 16, 32], 1024, 768, 30522, 12, 3, 4)
     torch.manual_seed(0)
@@ -391,7 +410,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = ref_shim.load_reference()
-    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "ft", "eval", "keys"]
+    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "ft", "eval", "inflate", "keys"]
     if "tables" in which:
         gen_tables(ref)
     if "wa" in which:
@@ -422,6 +441,8 @@ def main():
             gen_finetune(ref, tag, task, cfg, SMALL_BERT, B=3, frames=16, size=56, L=20, vocab=1000, seed=70)
     if "eval" in which:
         gen_eval(ref)
+    if "inflate" in which:
+        gen_inflate(ref)
     if "keys" in which:
         gen_state_keys(ref)
     print("golden written to", OUT)
