@@ -79,4 +79,4 @@ def acc_for_msrvtt_mc(video_embd=None, text_embd=None, label=None, use_sim=False
     own = scores.view(v.shape[0], v.shape[0], ans)[torch.arange(v.shape[0]), torch.arange(v.shape[0])]
     pred = own.argmax(dim=-1)
     lab = torch.as_tensor(np.asarray(label)).to(pred.device).view(-1)
-    return {"acc": float((pred == lab).float().mean())}
+    return {"acc": float((pred == lab).double().mean())}

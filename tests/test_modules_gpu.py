@@ -466,7 +466,7 @@ def test_retrieval_evaluation_vs_reference_golden(cb, golden_dir):
     for i, l in enumerate(lab[:5]):
         txt[i * 5 + l] = vid[i] * 3
     want = float(np.mean(np.argmax((vid @ txt.T).reshape(7, 7, 5)[np.arange(7), np.arange(7)], -1) == lab))
-    assert abs(E.acc_for_msrvtt_mc(vid, txt, lab)["acc"] - want) < 1e-9 and want >= 5 / 7
+    assert abs(E.acc_for_msrvtt_mc(vid, txt, lab)["acc"] - want) < 1e-6 and want >= 5 / 7
 
 
 def test_swin_uint8_clips_gpu_normalize_hook(cb):
