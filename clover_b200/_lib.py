@@ -24,7 +24,7 @@ class GemmEpilogue(C.Structure):
         ("out_pre", c_vp), ("ld_pre", c_ll), ("gelu_pre", c_vp), ("ld_gelu_pre", c_ll),
         ("act", C.c_int), ("scale_cols", C.c_int), ("scale", C.c_float),
         ("window", C.POINTER(WindowGeom)), ("k_splits", C.c_int), ("accumulate", C.c_int),
-        ("row_scale", c_vp), ("row_scale_rows", c_ll),
+        ("row_scale", c_vp), ("row_scale_rows", c_ll), ("rowsum", c_vp),
     ]
 
 
@@ -65,6 +65,7 @@ class LnrBwd(C.Structure):
     _fields_ = [
         ("dy", c_vp), ("dy_is_bf16", C.c_int), ("dy_mapped", C.c_int), ("dres", c_vp), ("dx", c_vp),
         ("dx_bf16", c_vp), ("dx_bf16_mapped", C.c_int), ("dgamma", c_vp), ("dbeta", c_vp), ("dxsum", c_vp),
+        ("copy_scale", c_vp), ("copy_scale_rows", c_ll),
     ]
 
 

@@ -30,8 +30,10 @@ template <int BN> struct GemmCfg {
   static constexpr int STAGES = BN == 128 ? 6 : 4;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages
+  static constexpr int ONES_BYTES = 2048;    // 16 rows x 64 bf16 of 1.0: B operand of the row-sum MMA (see GemmEpi::rowsum)
+  static constexpr int SMEM = STAGES * STAGE_BYTES + ONES_BYTES + 1024 /*align slack*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 512;      // two accumulator stages (2 * BN) + two 16-column row-sum accumulators (BN = 128)
+  static constexpr int RS_COL = 2 * BN;      // first row-sum column (only used when BN == 128)
 };
 
 struct GemmEpi {
@@ -48,6 +50,9 @@ struct GemmEpi {
   int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
   const float* row_scale;   // per row-group factor on (acc + bias) before the residual (DropPath), or nullptr
   long long row_scale_rows;
+  float* rowsum;            // [M] += sum_k A[m, k] (fp32 atomics), or nullptr.  For a weight gradient dW = dY^T X this is the
+                            // bias gradient sum_t dY[t, m]: one extra N = 16 MMA per K step against a tile of ones, issued only
+                            // by the n_idx == 0 tiles -- the column-sum pass over dY disappears.  BN == 128 only.
   WindowGeom geom;
 };
 
@@ -148,7 +153,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* sBias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
+  uint8_t* sOnes = smem + STAGES * STAGE_BYTES;                                  // 1024-byte aligned
+  float* sBias = reinterpret_cast<float*>(sOnes + Cfg::ONES_BYTES);              // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -175,6 +181,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  const bool do_rowsum = BN == 128 && ep.rowsum != nullptr;
+  if (do_rowsum) {
+    for (int x = threadIdx.x; x < Cfg::ONES_BYTES / 4; x += GEMM_THREADS) reinterpret_cast<uint32_t*>(sOnes)[x] = 0x3F803F80u;
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -220,6 +231,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
+      constexpr uint32_t idesc_rs = make_idesc_bf16(BM, 16, A_MN, 0);
+      const uint32_t ones_addr = smem_u32(sOnes);
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int split = (int)(t % k_splits);
         const int kb0 = split * kb_per_split;
@@ -228,6 +241,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        const bool rs_tile = do_rowsum && ((t / k_splits) % num_n) == 0;
+        const uint32_t tmem_rs = tmem_base + Cfg::RS_COL + acc * 16;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -243,6 +258,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024)
                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (rs_tile)      // every element of the ones tile is 1.0, so its (K-major, swizzled) layout needs no care
+              umma_bf16_ss(tmem_rs, da, make_smem_desc_sw128(ones_addr + k * 32, 16, 1024), idesc_rs, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -275,6 +292,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       long long drow = row;
       if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
       const bool row_ok = row < M && drow >= 0;
+      if (do_rowsum && n_idx == 0 && chalf == 0) {     // one column of the row-sum accumulator: sum_k A[row, k] of this split
+        uint32_t rsv[2];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(rsv[0]), "=r"(rsv[1])
+                     : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::RS_COL + acc * 16) : "memory");
+        tmem_ld_wait();
+        if (row < M) atomicAdd(ep.rowsum + row, __uint_as_float(rsv[0]));
+      }
       const float rscale = (ep.row_scale && row < M) ? __ldg(ep.row_scale + row / ep.row_scale_rows) : 1.0f;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
@@ -426,7 +450,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   CLV_REQUIRE(N % 8 == 0, "clv_gemm_bf16: N must be a multiple of 8 (got %d)", N);
   // 128x256 tiles when N fills them (less smem traffic per MAC); 128x128 otherwise
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
-  const bool bn256 = (N % 256 == 0) && tiles256 * (e->k_splits > 0 ? e->k_splits : 1) >= 2LL * num_sms();
+  const bool bn256 = (N % 256 == 0) && tiles256 * (e->k_splits > 0 ? e->k_splits : 1) >= 2LL * num_sms() && !e->rowsum;
   CUtensorMap ta, tb;
   int rc;
   if (a_mn_major) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BK);
@@ -448,6 +472,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   ep.use_row_map = e->window != nullptr;
   ep.row_scale = e->row_scale;
   ep.row_scale_rows = e->row_scale_rows > 0 ? e->row_scale_rows : 1;
+  ep.rowsum = e->rowsum;
   CLV_REQUIRE(!e->row_scale || e->row_scale_rows > 0, "clv_gemm_bf16: row_scale needs row_scale_rows > 0");
   int k_splits = e->k_splits > 0 ? e->k_splits : 1;
   const int num_kb = (K + BK - 1) / BK;

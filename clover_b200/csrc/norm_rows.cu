@@ -33,6 +33,7 @@ struct LnrArgs {
   __nv_bfloat16* dx16; int dx16_mapped;
   float* dgamma; float* dbeta;
   float* dxsum;                  // [C] column sums of the final dx (bias gradient of the nn.Linear that produced x's input)
+  const float* copy_scale; unsigned copy_scale_rows;   // per-sample DropPath factor applied to dx16 and dxsum (not dx)
 };
 
 template <bool BF>
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
     s2 = group_sum<L>(s2) * inv_c;
     if (!live || (!a.dx && !a.dx16)) continue;
     const unsigned crow = a.dx16_mapped ? m : s;
+    const float sc = a.copy_scale ? __ldg(a.copy_scale + s / a.copy_scale_rows) : 1.0f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int c = 4 * (sub + L * j);
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
       o.x = fmaf(rs, d[j].x - s2 - xh[j].x * s1, rr[j].x); o.y = fmaf(rs, d[j].y - s2 - xh[j].y * s1, rr[j].y);
       o.z = fmaf(rs, d[j].z - s2 - xh[j].z * s1, rr[j].z); o.w = fmaf(rs, d[j].w - s2 - xh[j].w * s1, rr[j].w);
       if (a.dx) *reinterpret_cast<float4*>(a.dx + (size_t)s * a.C + c) = o;
+      o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;          // the branch copy / bias gradient carry the DropPath factor
       if (a.dx16) lnr_st<true>(a.dx16, (size_t)crow * a.C + c, o);
       if (DXS) { ds[j].x += o.x; ds[j].y += o.y; ds[j].z += o.z; ds[j].w += o.w; }
     }
@@ -286,6 +289,8 @@ extern "C" int clv_lnr_bwd(const clv_lnr_desc_t* d, const clv_lnr_bwd_t* b, void
   a.dy = b->dy; a.dy_mapped = b->dy_mapped; a.dres = b->dres; a.dx = b->dx;
   a.dx16 = reinterpret_cast<__nv_bfloat16*>(b->dx_bf16); a.dx16_mapped = b->dx_bf16_mapped;
   a.dgamma = b->dgamma; a.dbeta = b->dbeta;
+  CLV_REQUIRE(!b->copy_scale || b->copy_scale_rows > 0, "lnr_bwd: copy_scale needs copy_scale_rows > 0");
+  a.copy_scale = b->copy_scale; a.copy_scale_rows = b->copy_scale ? (unsigned)b->copy_scale_rows : 1u;
   if (a.rows == 0) return 0;
   const int rows_per_block = 8 * (32 / L);
   const long long blocks = std::min<long long>(((long long)a.rows + rows_per_block - 1) / rows_per_block, (long long)num_sms() * 2);

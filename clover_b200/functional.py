@@ -87,12 +87,14 @@ def _zeros(n, device):
     return torch.zeros(n, dtype=F32, device=device)
 
 
-def _wgrad(dy16, x16, out_features, in_features):
-    """dW[out,in] = dY^T X with split-K (dY [T,out], X [T,in], both bf16 row-major)."""
+def _wgrad(dy16, x16, out_features, in_features, want_bias=False):
+    """dW[out,in] = dY^T X with split-K (dY [T,out], X [T,in], both bf16 row-major).  want_bias: also return the bias
+    gradient sum_t dY[t, :], produced by the same GEMM (row sums of its A operand on the tensor cores)."""
     T = dy16.shape[0]
     dW = torch.empty(out_features, in_features, dtype=F32, device=dy16.device)
-    ops.gemm(dy16, x16, dW, a_t=True, b_t=True, k_splits=ops.wgrad_splits(out_features, in_features, T))
-    return dW
+    db = torch.zeros(out_features, dtype=F32, device=dy16.device) if want_bias else None
+    ops.gemm(dy16, x16, dW, a_t=True, b_t=True, k_splits=ops.wgrad_splits(out_features, in_features, T), rowsum=db)
+    return (dW, db) if want_bias else dW
 
 
 # bf16 copy of the most recent fp32 residual-stream gradient: norm1's backward writes it next to d x so that the
@@ -100,22 +102,27 @@ def _wgrad(dy16, x16, out_features, in_features):
 _GRAD16 = [None]
 
 
-def _publish_grad16(t32, t16, colsum=None):
-    _GRAD16[0] = (t32, t32._version, t16, colsum)
+def _publish_grad16(t32, t16, colsum=None, scale=None):
+    """scale: the per-sample DropPath factor tensor already folded into t16 / colsum (None = plain copy)."""
+    _GRAD16[0] = (t32, t32._version, t16, colsum, scale)
 
 
-def _grad_bf16(t, want_colsum=False):
-    """bf16 copy of gradient t (fp32 [T, C]); reuses the copy (and its column sums, the bias gradient of the layer
-    that produced t's forward value) published by the producing kernel when there is one."""
-    if t.dtype == BF16:
-        return (t, None) if want_colsum else t
+def _grad_bf16(t, want_colsum=False, scale=None, rows_per_group=0):
+    """bf16 copy of gradient t (fp32 [T, C]) times the per-sample factor `scale` (DropPath, None = 1); reuses the copy
+    (and its column sums, the bias gradient of the layer that produced t's forward value) published by the producing
+    kernel when there is one carrying the same factor."""
     ent, _GRAD16[0] = _GRAD16[0], None
-    if ent is not None:
-        t32, ver, t16, cs = ent
+    if ent is not None and t.dtype != BF16:
+        t32, ver, t16, cs, sc = ent
         if (t32.data_ptr() == t.data_ptr() and t32.numel() == t.numel() and t.is_contiguous() and t._version == ver
-                and t32._version == ver):
+                and t32._version == ver and sc is scale):
             return (t16.view(t.shape), cs) if want_colsum else t16.view(t.shape)
-    t16 = ops.to_bf16(t)
+    if scale is not None:
+        t16 = ops.rows_scale(t, torch.empty(t.shape, dtype=BF16, device=t.device), scale, rows_per_group)
+    elif t.dtype == BF16:
+        t16 = t
+    else:
+        t16 = ops.to_bf16(t)
     return (t16, None) if want_colsum else t16
 
 
@@ -163,8 +170,13 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, dtype=BF16, device=x.device)
             ops.gemm(dy16, wb, dx, b_t=True)
-        dW = _wgrad(dy16, x, N, K).view_as(weight) if ctx.needs_input_grad[1] else None
-        db = _colsum(dy16, N) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dW = db = None
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            r = _wgrad(dy16, x, N, K, want_bias=want_b)
+            dW, db = (r[0].view_as(weight), r[1]) if want_b else (r.view_as(weight), None)
+        elif want_b:
+            db = _colsum(dy16, N)
         return dx, dW, db, dres, None, None, None
 
 
@@ -258,14 +270,12 @@ class MlpFn(torch.autograd.Function):
         M, Hd = pre.shape
         dpre = torch.empty(M, Hd, dtype=BF16, device=x.device)
         ops.gemm(dy16, w2b, dpre, b_t=True, gelu_pre=pre)
-        dW2 = _wgrad(dy16, act, w2.shape[0], Hd)
-        db2 = _colsum(dy16, w2.shape[0])
+        dW2, db2 = _wgrad(dy16, act, w2.shape[0], Hd, want_bias=True)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             ops.gemm(dpre, w1b, dx, b_t=True)
-        dW1 = _wgrad(dpre, x, Hd, x.shape[1])
-        db1 = _colsum(dpre, Hd)
+        dW1, db1 = _wgrad(dpre, x, Hd, x.shape[1], want_bias=True)
         return dx, dW1, db1, dW2, db2, dres, None
 
 
@@ -362,8 +372,7 @@ class QkvLinearFn(torch.autograd.Function):
         dqkv = dqkv.contiguous()
         dx = torch.empty_like(x)
         ops.gemm(dqkv, wcat, dx, b_t=True)
-        dW = _wgrad(dqkv, x, 3 * Hd, x.shape[1])
-        db = _colsum(dqkv, 3 * Hd)
+        dW, db = _wgrad(dqkv, x, 3 * Hd, x.shape[1], want_bias=True)
         return (dx, dW[:Hd], db[:Hd], dW[Hd:2 * Hd], db[Hd:2 * Hd], dW[2 * Hd:], db[2 * Hd:], None, None)
 
 
@@ -376,9 +385,11 @@ class SwinBlockFn(torch.autograd.Function):
     reference are folded into the LN gather and the proj-GEMM scatter epilogue."""
 
     @staticmethod
-    def forward(ctx, x, wg, heads, code, code_off, region, dp,
+    def forward(ctx, x, wg, heads, code, code_off, region, dp, prev_dp,
                 n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b):
-        # dp: None, or fp32 [2, B] per-sample DropPath factors keep / (1 - p) of the attention and the MLP branch
+        # prev_dp: the MLP-branch DropPath factors (fp32 [B]) of the block that produced x, or None: norm1's backward folds
+        # them into the bf16 gradient copy / bias gradient it publishes for that block
+        # dp: None, or a pair of fp32 [B] per-sample DropPath factors keep / (1 - p) of the attention and the MLP branch
         # (timm DropPath, :499 and :503); applied as a row scale in the proj / fc2 GEMM epilogues before the residual
         T, C = x.shape
         hd = C // heads
@@ -421,14 +432,14 @@ class SwinBlockFn(torch.autograd.Function):
         ctx.save_for_backward(x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region,
                               n1w, n1b, n2w, n2b, table)
         ctx.w = (wq, wp, w1, w2)
-        ctx.meta = (wg, heads, hd, code_off, scale, fc1_w.shape[0], rmap, dp, tok)
+        ctx.meta = (wg, heads, hd, code_off, scale, fc1_w.shape[0], rmap, dp, tok, prev_dp)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region, n1w, n1b, n2w, n2b, table) = ctx.saved_tensors
         wq, wp, w1, w2 = ctx.w
-        wg, heads, hd, code_off, scale, Hd, rmap, dp, tok = ctx.meta
+        wg, heads, hd, code_off, scale, Hd, rmap, dp, tok, prev_dp = ctx.meta
         T, C = x.shape
         rows = wg.rows
         dev = x.device
@@ -438,12 +449,9 @@ class SwinBlockFn(torch.autograd.Function):
         dg1, db1, dg2, db2 = small[:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
         dtable = small[6 * C:].view_as(table)
         # ---- MLP branch
-        if dp is not None:            # d(branch) = factor[sample] * dout: every consumer below reads the scaled bf16 copy
-            _GRAD16[0] = None
-            dy16 = ops.rows_scale(dout, torch.empty(T, C, dtype=BF16, device=dev), dp[1], tok)
-            dB2 = None
-        else:
-            dy16, dB2 = _grad_bf16(dout, want_colsum=True)
+        # d(branch) = factor[sample] * dout: every consumer below reads the scaled bf16 copy (published by the next block's
+        # norm1 backward when it ran; otherwise made here)
+        dy16, dB2 = _grad_bf16(dout, want_colsum=True, scale=dp[1] if dp is not None else None, rows_per_group=tok)
         dpre = torch.empty(T, Hd, dtype=BF16, device=dev)
         ops.gemm(dy16, w2, dpre, b_t=True, gelu_pre=pre)
         dW2 = _wgrad(dy16, act, C, Hd)
@@ -451,22 +459,22 @@ class SwinBlockFn(torch.autograd.Function):
             dB2 = _colsum(dy16, C)
         dh2 = dy16                                            # reuse the buffer: [T, C] bf16
         ops.gemm(dpre, w1, dh2, b_t=True)
-        dW1 = _wgrad(dpre, h2, Hd, C)
-        dB1 = _colsum(dpre, Hd)
+        dW1, dB1 = _wgrad(dpre, h2, Hd, C, want_bias=True)
         del dpre
         # ---- LN2 backward: d x_mid = dout + LN2'(dh2); bf16 copy emitted in window order for proj
         dmid = torch.empty(T, C, dtype=F32, device=dev)
         dmid_w = (torch.zeros if wg.padded else torch.empty)(rows, C, dtype=BF16, device=dev)
         dBp = None
         if rmap is not None:
-            dBp = small[4 * C:5 * C] if dp is None else None  # proj bias gradient = column sums of d x_mid
+            dBp = small[4 * C:5 * C]                          # proj bias gradient = column sums of (scaled) d x_mid
             ops.lnr_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, dx=dmid, dres=dout, dx_bf16=dmid_w, row_map=rmap,
-                        dx_bf16_mapped=True, dgamma=dg2, dbeta=db2, dxsum=dBp)
+                        dx_bf16_mapped=True, dgamma=dg2, dbeta=db2, dxsum=dBp,
+                        copy_scale=dp[0] if dp is not None else None, copy_scale_rows=tok)
         else:
             ops.layernorm_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, rows=T, dx=dmid, dres=dout, dx_copy=dmid_w,
                               copy_window=wg, dgamma=dg2, dbeta=db2)
         # ---- attention branch
-        if dp is not None:            # window-order rows of one clip are contiguous: scale the branch gradient in place
+        if dp is not None and rmap is None:   # generic LN path: window-order rows of one clip are contiguous, scale in place
             ops.rows_scale(dmid_w, dmid_w, dp[0], tok)
         dao = torch.empty(rows, C, dtype=BF16, device=dev)
         ops.gemm(dmid_w, wp, dao, b_t=True)
@@ -478,20 +486,18 @@ class SwinBlockFn(torch.autograd.Function):
                           bias_table=table, rel_code=code, code_off=code_off, region=region)
         dxw = dao                                             # reuse: [rows, C] bf16
         ops.gemm(dqkv, wq, dxw, b_t=True)
-        dWq = _wgrad(dqkv, xw, 3 * C, C)
-        dBq = _colsum(dqkv, 3 * C)
+        dWq, dBq = _wgrad(dqkv, xw, 3 * C, C, want_bias=True)
         # ---- LN1 backward through the window gather, accumulated onto d x_mid in place
         if rmap is not None:
             dmid16 = dmid_w                                   # reuse: [T, C] bf16 (rows == T when unpadded)
             dx_sum = small[5 * C:6 * C]                       # = fc2 bias gradient of the block that produced x
             ops.lnr_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, dx=dmid, dres=dmid, dx_bf16=dmid16, row_map=rmap,
-                        dy_mapped=True, dgamma=dg1, dbeta=db1, dxsum=dx_sum)
-            if dp is None:            # (with DropPath the producer of x scales its own copy; it ignores published ones)
-                _publish_grad16(dmid, dmid16, dx_sum)
+                        dy_mapped=True, dgamma=dg1, dbeta=db1, dxsum=dx_sum, copy_scale=prev_dp, copy_scale_rows=tok)
+            _publish_grad16(dmid, dmid16, dx_sum, prev_dp)
         else:
             ops.layernorm_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, rows=rows, dx=dmid, dres=dmid, dgamma=dg1, dbeta=db1,
                               window=wg)
-        return (dmid, None, None, None, None, None, None,
+        return (dmid, None, None, None, None, None, None, None,
                 dg1, db1, dWq, dBq, dtable, dWp, dBp, dg2, db2, dW1, dB1, dW2, dB2)
 
 
@@ -546,8 +552,8 @@ class PatchEmbedFn(torch.autograd.Function):
         else:
             (cols,) = ctx.saved_tensors
             dy16 = ops.to_bf16(dout)
-        dW = _wgrad(dy16, cols, C, cols.shape[1]).view(ctx.wshape)
-        dB = _colsum(dy16, C)
+        dW, dB = _wgrad(dy16, cols, C, cols.shape[1], want_bias=True)
+        dW = dW.view(ctx.wshape)
         return None, dW, dB, dgn, dbn, None, dtok, None, None
 
 

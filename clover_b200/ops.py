@@ -140,7 +140,7 @@ _ROW_MAPS = {}
 
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None, out_pre=None, gelu_pre=None,
-         scale_cols=0, scale=1.0, window=None, k_splits=1, accumulate=False, row_scale=None, row_scale_rows=0):
+         scale_cols=0, scale=1.0, window=None, k_splits=1, accumulate=False, row_scale=None, row_scale_rows=0, rowsum=None):
     """out = epilogue(A @ B^T).  a: [M,K] (or [K,M] if a_t), b: [N,K] (or [K,N] if b_t), bf16.
     See clv_gemm_bf16 in include/clover_b200.h."""
     _need_cuda(a, b, out)
@@ -178,6 +178,11 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None,
             raise ValueError("gemm: row_scale must be contiguous fp32 with numel * row_scale_rows >= M")
         _need_cuda(row_scale)
         e.row_scale, e.row_scale_rows = _ptr(row_scale), int(row_scale_rows)
+    if rowsum is not None:
+        if rowsum.dtype != F32 or not rowsum.is_contiguous() or rowsum.numel() != M:
+            raise ValueError("gemm: rowsum must be contiguous fp32 [M]")
+        _need_cuda(rowsum)
+        e.rowsum = _ptr(rowsum)
     lib = _lib.load()
     ev = _prof_open()
     _lib.check(lib.clv_gemm_bf16(_ptr(a), lda, int(a_t), _ptr(b), ldb, int(b_t), M, N, K, C.byref(e), _stream()), "clv_gemm_bf16")
@@ -303,7 +308,7 @@ def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_map
 
 @_profiled("ln_bwd", _lnr_tag)
 def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, row_map=None, dy_mapped=False,
-            dx_bf16_mapped=False, dgamma=None, dbeta=None, dxsum=None):
+            dx_bf16_mapped=False, dgamma=None, dbeta=None, dxsum=None, copy_scale=None, copy_scale_rows=0):
     _need_cuda(x, gamma, dy)
     for t, n in ((dy, "dy"), (dx, "dx"), (dres, "dres"), (dx_bf16, "dx_bf16")):
         if t is not None and (t.shape != x.shape or not t.is_contiguous()):
@@ -315,6 +320,12 @@ def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=
     b.dy, b.dy_is_bf16, b.dy_mapped = _ptr(dy), _is_bf16(dy), int(dy_mapped)
     b.dres, b.dx, b.dx_bf16, b.dx_bf16_mapped = _ptr(dres), _ptr(dx), _ptr(dx_bf16), int(dx_bf16_mapped)
     b.dgamma, b.dbeta, b.dxsum = _ptr(dgamma), _ptr(dbeta), _ptr(dxsum)
+    if copy_scale is not None:
+        if copy_scale.dtype != F32 or not copy_scale.is_contiguous() or copy_scale_rows <= 0 or \
+                copy_scale.numel() * copy_scale_rows < x.shape[0]:
+            raise ValueError("lnr_bwd: copy_scale must be contiguous fp32 with numel * copy_scale_rows >= rows")
+        _need_cuda(copy_scale)
+        b.copy_scale, b.copy_scale_rows = _ptr(copy_scale), int(copy_scale_rows)
     _lib.check(_lib.load().clv_lnr_bwd(C.byref(d), C.byref(b), _stream()), "clv_lnr_bwd")
 
 

@@ -170,22 +170,24 @@ class SwinTransformerBlock3D(nn.Module):
         if drop > 0 or attn_drop > 0:
             raise NotImplementedError("clover_b200: drop / attn_drop > 0 are not supported (0 in every Clover config)")
 
-    def forward_tokens(self, x, B, D, H, W):
-        """x fp32 [B*D*H*W, C] channels-last tokens -> same shape."""
+    def forward_tokens(self, x, B, D, H, W, prev_dp=None, return_dp=False):
+        """x fp32 [B*D*H*W, C] channels-last tokens -> same shape.  prev_dp: the MLP-branch DropPath factors of the block
+        that produced x (its gradient copy is pre-scaled in this block's backward); return_dp: also return this block's."""
         dp = None
         if self.training and self.drop_path_rate > 0:      # two independent per-sample draws: attention branch, MLP branch
             from . import rng
-            dp = torch.stack([rng.drop_path_scales(B, self.drop_path_rate, x.device),
-                              rng.drop_path_scales(B, self.drop_path_rate, x.device)])
+            dp = (rng.drop_path_scales(B, self.drop_path_rate, x.device),      # a tuple: the same tensor OBJECTS tag the
+                  rng.drop_path_scales(B, self.drop_path_rate, x.device))      # pre-scaled gradient copies in backward
         window, shift = get_window_size((D, H, W), self.window_size, self.shift_size)
         wg = ops.Window(B, D, H, W, window, shift)
         code, off, region = _device_tables((wg.Dp, wg.Hp, wg.Wp), window, shift, self.window_size, x.device)
         wg.w7 = _w7_spec((wg.Dp, wg.Hp, wg.Wp), window, shift, self.window_size, x.device)
         a, m = self.attn, self.mlp
-        return Fn.SwinBlockFn.apply(x, wg, self.num_heads, code, off, region, dp,
-                                    self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias,
-                                    a.relative_position_bias_table, a.proj.weight, a.proj.bias,
-                                    self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
+        y = Fn.SwinBlockFn.apply(x, wg, self.num_heads, code, off, region, dp, prev_dp,
+                                 self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias,
+                                 a.relative_position_bias_table, a.proj.weight, a.proj.bias,
+                                 self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
+        return (y, dp[1] if dp is not None else None) if return_dp else y
 
     def forward(self, x, mask_matrix=None):
         """reference contract: x (B, D, H, W, C) -> same."""
@@ -232,8 +234,9 @@ class BasicLayer(nn.Module):
         self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
 
     def forward_tokens(self, x, B, D, H, W):
+        prev = None                       # DropPath factors of the previous block's MLP branch (same layer only)
         for blk in self.blocks:
-            x = blk.forward_tokens(x, B, D, H, W)
+            x, prev = blk.forward_tokens(x, B, D, H, W, prev_dp=prev, return_dp=True)
         if self.downsample is not None:
             x, H, W = self.downsample.forward_tokens(x, B, D, H, W)
         return x, H, W

@@ -67,6 +67,9 @@ typedef struct {
                                  row_scale[m / row_scale_rows] before the residual add -- the per-sample keep/(1-p)
                                  factor of timm DropPath (x + drop_path(branch), swin_transformer_3d.py:499,503) */
   long long row_scale_rows;
+  float* rowsum;              /* [M] fp32 or NULL: rowsum[m] += sum_k A[m, k] (ACCUMULATED with atomics; caller zero-fills).  With
+                                 A = dY^T (a weight gradient dW = dY^T X) this is the nn.Linear bias gradient, computed by one extra
+                                 tensor-core instruction per K step instead of a separate column-sum pass over dY */
 } clv_gemm_epilogue_t;
 
 int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
@@ -134,6 +137,10 @@ typedef struct {
   float* dgamma; float* dbeta;       /* [C] fp32, ACCUMULATED (caller zero-fills); both or neither */
   float* dxsum;                      /* [C] fp32, ACCUMULATED column sums of dx, or NULL: the bias gradient of the nn.Linear
                                         whose output gradient this dx is (fc2 / proj of the Swin block); fp32 x + bf16 dy only */
+  const float* copy_scale;           /* NULL, or per-sample DropPath factors: the bf16 copy and dxsum (NOT dx) are multiplied by
+                                        copy_scale[s / copy_scale_rows] -- they are the gradient of a residual branch that the
+                                        forward pass scaled by the same factor (swin_transformer_3d.py:499,503) */
+  long long copy_scale_rows;
 } clv_lnr_bwd_t;
 
 int clv_lnr_supported(int C);

@@ -105,6 +105,28 @@ def test_gemm_splitk_wgrad(ops, splits):
     assert rel(dW, ref) < 2e-3
     ops.gemm(dY, X, dW, a_t=True, b_t=True, k_splits=splits, accumulate=True)
     assert rel(dW, 2 * ref) < 2e-3
+    # bias gradient from the same GEMM: row sums of the A operand (= column sums of dY) by one extra MMA per K step
+    db = torch.zeros(Nout, dtype=F32, device="cuda")
+    dW2 = torch.empty_like(dW)
+    ops.gemm(dY, X, dW2, a_t=True, b_t=True, k_splits=splits, rowsum=db)
+    assert rel(dW2, ref) < 2e-3 and rel(db, dY.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(2048, 512, 100352, 4), (200, 136, 333, 1), (1536, 512, 6000, 6), (96, 3 * 2 * 4 * 4, 25088, 8)])
+def test_gemm_rowsum_shapes(ops, M, N, K, splits):
+    """Row-sum (bias-gradient) epilogue on the production weight-gradient shapes, ragged M / K tails, and with a K-major A."""
+    dY, X = rnd(K, M, seed=12, dtype=BF16), rnd(K, N, seed=13, dtype=BF16)
+    dW = torch.empty(M, N, dtype=F32, device="cuda")
+    db = torch.zeros(M, dtype=F32, device="cuda")
+    ops.gemm(dY, X, dW, a_t=True, b_t=True, k_splits=splits, rowsum=db)
+    assert rel(dW, dY.float().t() @ X.float()) < 3e-3
+    assert rel(db, dY.float().sum(0)) < 1e-4
+    if K % 8 == 0:
+        A = dY.t().contiguous()                                      # K-major A: rowsum = row sums of A
+        out = torch.empty(M, N, dtype=F32, device="cuda")
+        db2 = torch.zeros(M, dtype=F32, device="cuda")
+        ops.gemm(A, X, out, b_t=True, rowsum=db2)
+        assert rel(db2, A.float().sum(1)) < 1e-4 and rel(out, A.float() @ X.float()) < 3e-3
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm

@@ -293,7 +293,7 @@ def test_swin_drop_path_vs_oracle(cb):
     R = _replay()
     torch.manual_seed(3)
     m = swin.SwinTransformer3D(pretrained=None, pretrained2d=False, patch_size=(2, 4, 4), stride=(2, 4, 4), embed_dim=32,
-                               depths=[2, 2], num_heads=[1, 2], window_size=(8, 7, 7), drop_path_rate=0.5, patch_norm=True).cuda()
+                               depths=[3, 3], num_heads=[1, 2], window_size=(8, 7, 7), drop_path_rate=0.5, patch_norm=True).cuda()
     sd = load_synth(m, 80)
     x = named_tensor("dp_imgs", (6, 3, 8, 56, 56), 81)
     m.train()
@@ -308,15 +308,19 @@ def test_swin_drop_path_vs_oracle(cb):
     pairs = rp.drop_path_pairs([blk.drop_path_rate for layer in m.layers for blk in layer.blocks])
     assert pairs[0] is None and any(float(s.min()) == 0.0 for pr in pairs[1:] for s in pr), "no path was dropped: weak test"
     st = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    y_ref = O.swin_forward(st, x, [2, 2], [1, 2], drop_paths=pairs)
+    y_ref = O.swin_forward(st, x, [3, 3], [1, 2], drop_paths=pairs)
     (y_ref * w).sum().backward()
     assert rel(y, y_ref.detach()) < TOL
     params = dict(m.named_parameters())
+    # the bias gradients below travel through the pre-scaled copies (fc2 bias of block k <- norm1 backward of block k+1,
+    # proj bias <- norm2 backward), the weights through the scaled bf16 operands
     for name in ("patch_embed.proj.weight", "layers.0.blocks.1.attn.qkv.weight", "layers.0.blocks.1.attn.proj.bias",
-                 "layers.0.blocks.0.mlp.fc2.bias", "layers.1.blocks.0.mlp.fc1.weight", "layers.1.blocks.1.attn.relative_position_bias_table"):
+                 "layers.0.blocks.0.mlp.fc2.bias", "layers.0.blocks.1.mlp.fc2.bias", "layers.0.blocks.2.mlp.fc2.bias",
+                 "layers.1.blocks.1.mlp.fc2.weight", "layers.1.blocks.1.mlp.fc2.bias", "layers.1.blocks.2.attn.proj.bias",
+                 "layers.1.blocks.0.mlp.fc1.weight", "layers.1.blocks.1.attn.relative_position_bias_table"):
         assert cos(params[name].grad, st[name].grad.numpy()) > 0.99, name
     m.eval()
-    assert rel(m(x.cuda()), O.swin_forward(st, x, [2, 2], [1, 2]).detach()) < TOL      # eval: regulariser off
+    assert rel(m(x.cuda()), O.swin_forward(st, x, [3, 3], [1, 2]).detach()) < TOL      # eval: regulariser off
 
 
 def test_bert_dropout_vs_oracle(cb):
