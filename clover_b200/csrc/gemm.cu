@@ -26,14 +26,19 @@ constexpr int BM = 128, BK = 64;
 constexpr int GEMM_EPI_WARPS = 16;    // four column quarters x four lane quarters
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
 
-template <int BN> struct GemmCfg {
-  static constexpr int STAGES = BN == 128 ? 6 : 4;
+// RS ("row sums", BN == 128 only): every stage carries 8 KB of bf16 ones right behind its B tile.  The n_idx == 0 tiles
+// issue their MMAs with N = 144 instead of 128: B columns 128..143 read the ones, so accumulator column 128 receives
+// sum_k A[m, k] -- for a weight gradient dW = dY^T X that is the bias gradient, at the price of 12.5 % more tensor work on
+// a quarter (or less) of the tiles instead of a separate HBM pass over dY.  (A separate N = 16 MMA per K step costs as much
+// as a full one: the instruction has a fixed floor.)
+template <int BN, bool RS> struct GemmCfg {
+  static constexpr int STAGES = BN == 128 ? (RS ? 5 : 6) : 4;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int ONES_BYTES = 2048;    // 16 rows x 64 bf16 of 1.0: B operand of the row-sum MMA (see GemmEpi::rowsum)
-  static constexpr int SMEM = STAGES * STAGE_BYTES + ONES_BYTES + 1024 /*align slack*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 512;      // two accumulator stages (2 * BN) + two 16-column row-sum accumulators (BN = 128)
-  static constexpr int RS_COL = 2 * BN;      // first row-sum column (only used when BN == 128)
+  static constexpr int ONES_BYTES = RS ? 8192 : 0;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + ONES_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+  static constexpr int ACC_STRIDE = RS ? 160 : BN;          // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = RS ? 512 : 2 * BN;
 };
 
 struct GemmEpi {
@@ -50,9 +55,7 @@ struct GemmEpi {
   int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
   const float* row_scale;   // per row-group factor on (acc + bias) before the residual (DropPath), or nullptr
   long long row_scale_rows;
-  float* rowsum;            // [M] += sum_k A[m, k] (fp32 atomics), or nullptr.  For a weight gradient dW = dY^T X this is the
-                            // bias gradient sum_t dY[t, m]: one extra N = 16 MMA per K step against a tile of ones, issued only
-                            // by the n_idx == 0 tiles -- the column-sum pass over dY disappears.  BN == 128 only.
+  float* rowsum;            // [M] += sum_k A[m, k] (fp32 atomics), or nullptr: see GemmCfg (RS kernels only)
   WindowGeom geom;
 };
 
@@ -144,17 +147,17 @@ CLV_DEVICE void store_row(void* base, int is_bf16, bool wide, int ncols, const f
   }
 }
 
-template <int A_MN, int B_MN, int BN>
+template <int A_MN, int B_MN, int BN, bool RS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  int M, int N, int K, int k_splits, GemmEpi ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, RS>;
+  static_assert(!RS || BN == 128, "row sums ride in the 128-column configuration");
   constexpr int STAGES = Cfg::STAGES, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sOnes = smem + STAGES * STAGE_BYTES;                                  // 1024-byte aligned
-  float* sBias = reinterpret_cast<float*>(sOnes + Cfg::ONES_BYTES);              // [2][BN]
+  float* sBias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -181,9 +184,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  const bool do_rowsum = BN == 128 && ep.rowsum != nullptr;
-  if (do_rowsum) {
-    for (int x = threadIdx.x; x < Cfg::ONES_BYTES / 4; x += GEMM_THREADS) reinterpret_cast<uint32_t*>(sOnes)[x] = 0x3F803F80u;
+  if (RS) {       // bf16 1.0 everywhere behind each stage's B tile (all elements equal: any swizzle / major-ness reads ones)
+    for (int x = threadIdx.x; x < STAGES * (Cfg::ONES_BYTES / 16); x += GEMM_THREADS) {
+      const int st = x / (Cfg::ONES_BYTES / 16), o = x % (Cfg::ONES_BYTES / 16);
+      reinterpret_cast<uint4*>(smem + st * STAGE_BYTES + A_BYTES + Cfg::B_BYTES)[o] =
+          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    }
     fence_proxy_async();
   }
   tc_fence_before();
@@ -205,7 +211,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], A_BYTES + Cfg::B_BYTES);
           if (A_MN) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], m_idx * BM, kb * BK);
             tma_load_2d(sa + A_BYTES / 2, &tma_a, &full_bar[stage], m_idx * BM + 64, kb * BK);
@@ -227,12 +233,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc_plain = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc_wide = make_idesc_bf16(BM, BN + 16, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      constexpr uint32_t idesc_rs = make_idesc_bf16(BM, 16, A_MN, 0);
-      const uint32_t ones_addr = smem_u32(sOnes);
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int split = (int)(t % k_splits);
         const int kb0 = split * kb_per_split;
@@ -240,9 +245,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        const bool rs_tile = do_rowsum && ((t / k_splits) % num_n) == 0;
-        const uint32_t tmem_rs = tmem_base + Cfg::RS_COL + acc * 16;
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
+        const uint32_t idesc = (RS && ((t / k_splits) % num_n) == 0) ? idesc_wide : idesc_plain;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -258,8 +262,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024)
                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (rs_tile)      // every element of the ones tile is 1.0, so its (K-major, swizzled) layout needs no care
-              umma_bf16_ss(tmem_rs, da, make_smem_desc_sw128(ones_addr + k * 32, 16, 1024), idesc_rs, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -292,10 +294,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       long long drow = row;
       if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
       const bool row_ok = row < M && drow >= 0;
-      if (do_rowsum && n_idx == 0 && chalf == 0) {     // one column of the row-sum accumulator: sum_k A[row, k] of this split
+      if (RS && n_idx == 0 && chalf == 0) {            // accumulator column BN: sum_k A[row, k] over this tile's K range
         uint32_t rsv[2];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(rsv[0]), "=r"(rsv[1])
-                     : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::RS_COL + acc * 16) : "memory");
+                     : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE + BN) : "memory");
         tmem_ld_wait();
         if (row < M) atomicAdd(ep.rowsum + row, __uint_as_float(rsv[0]));
       }
@@ -305,7 +307,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t r[EC];
         const int cb = chalf * CPW + c * EC;             // column offset inside the tile
         const int n0 = n_idx * BN + cb;
-        tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb, r);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE + cb, r);
         tmem_ld_wait();
         if (!row_ok || n0 >= N) continue;
         float v[EC];
@@ -413,12 +415,12 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long l
   return 0;
 }
 
-template <int A_MN, int B_MN, int BN>
+template <int A_MN, int B_MN, int BN, bool RS = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int k_splits,
                        const GemmEpi& ep, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN>;
-  constexpr int SMEM = GemmCfg<BN>::SMEM;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN, RS>;
+  constexpr int SMEM = GemmCfg<BN, RS>::SMEM;
   if (!attr_set) {
     CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
@@ -427,6 +429,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
   const int grid = (int)std::min<long long>(tiles, num_sms());
   kern<<<grid, GEMM_THREADS, SMEM, stream>>>(ta, tb, M, N, K, k_splits, ep);
   return after_launch("gemm_bf16_kernel launch");
+}
+
+static int dispatch_gemm_rowsum(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                                int k_splits, const GemmEpi& ep, cudaStream_t stream) {
+  if (a_mn && b_mn) return launch_gemm<1, 1, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
+  if (a_mn) return launch_gemm<1, 0, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
+  if (b_mn) return launch_gemm<0, 1, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
+  return launch_gemm<0, 0, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
 }
 
 template <int BN>
@@ -506,6 +516,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (e->gelu_pre) ok = ok && al32(e->gelu_pre) && (e->ld_gelu_pre * 2) % 32 == 0;
     ep.vec32 = ok ? 1 : 0;
   }
+  if (e->rowsum) return dispatch_gemm_rowsum(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
   if (bn256) return dispatch_gemm<256>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
   return dispatch_gemm<128>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
 }
