@@ -30,6 +30,7 @@ SHAPES = [
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     only = sys.argv[2] if len(sys.argv) > 2 else None
+    rowsum = len(sys.argv) > 3 and sys.argv[3] == "rowsum"      # weight-gradient shapes also produce the bias gradient
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     for (M, N, K, at, bt, ep, od, ks) in SHAPES:
         tag = f"M={M} N={N} K={K} at={at} bt={bt} ep={ep}{od} ks={ks}"
@@ -48,6 +49,9 @@ def main():
             kw["gelu_pre"] = torch.randn(M, N, device="cuda").to(BF16)
         if "r" in ep:
             kw["residual"] = torch.randn(M, N, device="cuda")
+        if rowsum and at and od == "o32":
+            kw["rowsum"] = torch.zeros(M, device="cuda")
+            tag += " +rowsum"
         ms = []
         for _ in range(reps + 1):
             flush.zero_()
