@@ -62,31 +62,35 @@ template <typename TIN>
 __global__ void patchify_kernel(const TIN* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Cin, int F,
                                 int H, int W, int pd, int ph, int pw, int D, int Hp, int Wp, const float* __restrict__ mean,
                                 const float* __restrict__ inv_std) {
-  extern __shared__ float tile[];            // [Cin*pd*ph][Wp*pw]
+  extern __shared__ float tile[];            // [Cin*pd*ph][Wp*pw + 1]  (odd pitch: phase 2 walks the rows, not the columns)
   const int hp = blockIdx.x % Hp, d = (blockIdx.x / Hp) % D, b = blockIdx.x / (Hp * D);
-  const int nrow = Cin * pd * ph, roww = Wp * pw;
-  for (int i = threadIdx.x; i < nrow * roww; i += blockDim.x) {
-    const int r = i / roww, col = i % roww;
+  const int nrow = Cin * pd * ph, roww = Wp * pw, rs = roww + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // phase 1: one input row (c, kd, kh) per warp iteration, lanes along the contiguous W axis (index math once per row)
+  for (int r = warp; r < nrow; r += nwarps) {
     const int kh = r % ph, kd = (r / ph) % pd, c = r / (ph * pd);
     const int f = d * pd + kd, h = hp * ph + kh;
-    float v = 0.f;
-    if (f < F && h < H && col < W) {
-      v = (float)x[(((long long)b * Cin + c) * F + f) * H * W + (long long)h * W + col];
-      if (mean) v = (v - __ldg(mean + c)) * __ldg(inv_std + c);
+    const bool row_ok = f < F && h < H;
+    const TIN* src = x + (((long long)b * Cin + c) * F + f) * H * W + (long long)h * W;
+    const float m = mean ? __ldg(mean + c) : 0.f, is = mean ? __ldg(inv_std + c) : 1.f;
+    for (int col = lane; col < roww; col += 32) {
+      float v = 0.f;
+      if (row_ok && col < W) v = ((float)src[col] - m) * is;
+      tile[r * rs + col] = v;
     }
-    tile[i] = v;
   }
   __syncthreads();
+  // phase 2: one token (wp) per warp iteration, lanes along the K = nrow * pw patch columns (pairs: pw is even)
   const int K = nrow * pw;
   const long long row0 = ((long long)(b * D + d) * Hp + hp) * Wp;
-  for (int i = threadIdx.x; i < Wp * K / 2; i += blockDim.x) {
-    const int e = i * 2;
-    const int wp = e / K, k = e % K;          // k even; pw even => both elements share (c,kd,kh)
-    const int r = k / pw, kw = k % pw;
-    const float v0 = tile[r * roww + wp * pw + kw];
-    const int k1 = k + 1, r1 = k1 / pw, kw1 = k1 % pw;
-    const float v1 = tile[r1 * roww + wp * pw + kw1];
-    *reinterpret_cast<uint32_t*>(out + (row0 + wp) * K + k) = pack_bf16(v0, v1);
+  for (int wp = warp; wp < Wp; wp += nwarps) {
+    __nv_bfloat16* dst = out + (row0 + wp) * K;
+    const float* srcw = tile + wp * pw;
+    for (int k = lane * 2; k < K; k += 64) {
+      const int r = k / pw, kw = k - r * pw;           // both elements of the pair share r (pw even, k even)
+      const float* p = srcw + r * rs + kw;
+      *reinterpret_cast<uint32_t*>(dst + k) = pack_bf16(p[0], p[1]);
+    }
   }
 }
 
@@ -244,7 +248,7 @@ extern "C" int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CLV_REQUIRE(x && out_bf16 && B > 0 && pw % 2 == 0, "clv_patchify: bad arguments");
   const int D = (F + pd - 1) / pd, Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
-  const size_t smem = (size_t)Cin * pd * ph * Wp * pw * sizeof(float);
+  const size_t smem = (size_t)Cin * pd * ph * (Wp * pw + 1) * sizeof(float);
   CLV_REQUIRE(smem <= 200 * 1024, "clv_patchify: row tile too large (%zu bytes)", smem);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
@@ -261,7 +265,7 @@ extern "C" int clv_patchify_u8(const unsigned char* x, const float* mean, const 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CLV_REQUIRE(x && mean && inv_std && out_bf16 && B > 0 && pw % 2 == 0, "clv_patchify_u8: bad arguments");
   const int D = (F + pd - 1) / pd, Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
-  const size_t smem = (size_t)Cin * pd * ph * Wp * pw * sizeof(float);
+  const size_t smem = (size_t)Cin * pd * ph * (Wp * pw + 1) * sizeof(float);
   CLV_REQUIRE(smem <= 200 * 1024, "clv_patchify_u8: row tile too large (%zu bytes)", smem);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {

@@ -714,3 +714,51 @@ def test_patchify_uint8_fused_normalise(ops):
         assert rel(got.float(), want.float()) < 4e-3              # (v - m) * (1/s) vs (v - m) / s before the bf16 rounding
     with pytest.raises(ValueError):
         ops.patchify(x8, (2, 4, 4))
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties (c2)
+@pytest.mark.parametrize("shifted", [False, True])
+def test_window_attention_c2_full_size_properties(ops, shifted):
+    """BASELINE config c2 at its full size (4096 windows of N = 392 tokens, 4 heads x 32): too big for the CPU oracle, so
+    the check uses size-independent properties of softmax attention.  (1) softmax rows sum to 1: with V == 1 the output
+    is 1 everywhere, whatever Q, K, bias and shift mask are; (2) dV = P^T dO, so sum_j dV_j == sum_i dO_i per (window,
+    head); (3) d(bias table) sums to 0 over each head (each softmax row's dS sums to 0); (4) the windows are
+    independent: permuting the windows of one mask class permutes outputs and gradients bit for bit."""
+    from clover_b200 import swin
+    from clover_b200.tables import rel_code, region_ids
+    dims, heads, hd, clips = (8, 56, 56), 4, 32, 64
+    win, sh = O.get_window_size(dims, (8, 7, 7), (4, 3, 3) if shifted else (0, 0, 0))
+    N, nwin = 392, 64
+    batch = clips * nwin
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(batch * N, 3 * heads * hd, generator=g, device="cuda") * 0.7).to(BF16)
+    qkv.view(batch * N, 3, heads * hd)[:, 2] = 1.0                     # V == 1
+    dout = torch.randn(batch * N, heads * hd, generator=g, device="cuda").to(BF16)
+    table = torch.randn(2535, heads, generator=g, device="cuda") * 0.5
+    code, off = rel_code(N, (8, 7, 7))
+    code = torch.from_numpy(code).cuda()
+    masked = any(s > 0 for s in sh)
+    region = torch.from_numpy(region_ids(*dims, win, sh)).cuda() if masked else None
+    kw = dict(bias_table=table, rel_code=code, code_off=off, region=region, w7=swin._w7_spec(dims, win, sh, (8, 7, 7), "cuda"))
+    out = torch.empty(batch * N, heads * hd, dtype=BF16, device="cuda")
+    lse = torch.empty(batch, heads, N, dtype=F32, device="cuda")
+    ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)
+    assert float((out.float() - 1).abs().max()) < 1e-2                                  # (1)
+    dqkv = torch.empty_like(qkv)
+    dtab = torch.zeros(2535, heads, dtype=F32, device="cuda")
+    ops.attention_bwd(qkv, out, dout, lse, batch, N, heads, hd, dqkv, hd ** -0.5, dbias_table=dtab, **kw)
+    dv = dqkv.view(batch, N, 3, heads, hd)[:, :, 2].float().sum(1)
+    want = dout.view(batch, N, heads, hd).float().sum(1)
+    assert rel(dv, want) < 1e-2                                                         # (2)
+    assert float(dtab.sum(0).abs().max()) < 2e-2 * float(dtab.abs().sum(0).max())       # (3)
+    # (4) swap clip 3 and clip 17 (same window classes, row-block permutation)
+    rows = nwin * N
+    perm = torch.arange(batch * N, device="cuda").view(clips, rows)
+    perm[[3, 17]] = perm[[17, 3]]
+    perm = perm.reshape(-1)
+    out2 = torch.empty_like(out); lse2 = torch.empty_like(lse)
+    ops.attention_fwd(qkv[perm].contiguous(), batch, N, heads, hd, out2, lse2, **kw)
+    assert torch.equal(out2, out[perm])
+    dq2 = torch.empty_like(qkv)
+    ops.attention_bwd(qkv[perm].contiguous(), out2, dout[perm].contiguous(), lse2, batch, N, heads, hd, dq2, hd ** -0.5, **kw)
+    assert torch.equal(dq2, dqkv[perm])
