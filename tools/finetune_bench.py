@@ -59,7 +59,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         print(json.dumps({"task": task, "clips_per_gpu": args.clips, "frames": 16, "query_tokens": 40, "ms_per_step": round(ms, 2),
-                          "clips_per_sec": round(args.clips / ms * 1e3, 1), "loss": float(loss),
+                          "clips_per_sec": round(args.clips / ms * 1e3, 1), "loss": float(loss.detach()),
                           "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                           "regularisers": "shipped (drop_path 0.3, BERT 0.1, QA head 0.1)"}), flush=True)
         del model, opt
