@@ -16,6 +16,7 @@
 // accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
 // Tiles 128x256x64 (4 smem stages) when N is a multiple of 256 and the grid still fills, else 128x128x64 (6 stages).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "clover_b200.h"
@@ -24,21 +25,21 @@ namespace clv {
 
 constexpr int BM = 128, BK = 64;
 constexpr int GEMM_EPI_WARPS = 16;    // four column quarters x four lane quarters
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr int GEMM_RS_WARPS = 2;       // row-sum warps (only busy in the RS kernels)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS + 32 * GEMM_RS_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue, 18-19 row sums
 
-// RS ("row sums", BN == 128 only): every stage carries 8 KB of bf16 ones right behind its B tile.  The n_idx == 0 tiles
-// issue their MMAs with N = 144 instead of 128: B columns 128..143 read the ones, so accumulator column 128 receives
-// sum_k A[m, k] -- for a weight gradient dW = dY^T X that is the bias gradient, at the price of 12.5 % more tensor work on
-// a quarter (or less) of the tiles instead of a separate HBM pass over dY.  (A separate N = 16 MMA per K step costs as much
-// as a full one: the instruction has a fixed floor.)
+// RS ("row sums"): the weight-gradient GEMMs dW = dY^T X also deliver the bias gradient sum_t dY[t, m] = the row sums of
+// their (MN-major) A operand.  Two extra warps read every A tile of the n_idx == 0 tiles out of shared memory behind the
+// TMA barrier (16-byte loads through the 128-byte swizzle), keep 8 fp32 partial sums per lane across the K loop and leave
+// with 64 atomics per warp and tile; they are a third arriver on the stage's "empty" barrier.  The tensor pipe, the operand
+// tiles and the accumulator layout are untouched (an extra N = 16 MMA per K step, or 16 extra B columns of ones, cost
+// 6-33 % of these GEMMs), and the separate column-sum pass over dY (5.5 ms per step) disappears.
 template <int BN, bool RS> struct GemmCfg {
-  static constexpr int STAGES = BN == 128 ? (RS ? 5 : 6) : 4;
+  static constexpr int STAGES = BN == 128 ? 6 : 4;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-  static constexpr int ONES_BYTES = RS ? 8192 : 0;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + ONES_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
-  static constexpr int ACC_STRIDE = RS ? 160 : BN;          // TMEM columns per accumulator stage
-  static constexpr int TMEM_COLS = RS ? 512 : 2 * BN;
+  static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages
 };
 
 struct GemmEpi {
@@ -55,7 +56,7 @@ struct GemmEpi {
   int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
   const float* row_scale;   // per row-group factor on (acc + bias) before the residual (DropPath), or nullptr
   long long row_scale_rows;
-  float* rowsum;            // [M] += sum_k A[m, k] (fp32 atomics), or nullptr: see GemmCfg (RS kernels only)
+  float* rowsum;            // [M] += sum_k A[m, k] (fp32 atomics), or nullptr: see GemmCfg (RS kernels, MN-major A only)
   WindowGeom geom;
 };
 
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  int M, int N, int K, int k_splits, GemmEpi ep) {
   using Cfg = GemmCfg<BN, RS>;
-  static_assert(!RS || BN == 128, "row sums ride in the 128-column configuration");
+  static_assert(!RS || A_MN == 1, "row sums are implemented for the MN-major A operand of the weight gradients");
   constexpr int STAGES = Cfg::STAGES, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
@@ -175,7 +176,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], RS ? 1 + GEMM_RS_WARPS : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -184,14 +185,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  if (RS) {       // bf16 1.0 everywhere behind each stage's B tile (all elements equal: any swizzle / major-ness reads ones)
-    for (int x = threadIdx.x; x < STAGES * (Cfg::ONES_BYTES / 16); x += GEMM_THREADS) {
-      const int st = x / (Cfg::ONES_BYTES / 16), o = x % (Cfg::ONES_BYTES / 16);
-      reinterpret_cast<uint4*>(smem + st * STAGE_BYTES + A_BYTES + Cfg::B_BYTES)[o] =
-          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-    }
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -211,7 +204,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], A_BYTES + Cfg::B_BYTES);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (A_MN) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], m_idx * BM, kb * BK);
             tma_load_2d(sa + A_BYTES / 2, &tma_a, &full_bar[stage], m_idx * BM + 64, kb * BK);
@@ -233,8 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_plain = make_idesc_bf16(BM, BN, A_MN, B_MN);
-      constexpr uint32_t idesc_wide = make_idesc_bf16(BM, BN + 16, A_MN, B_MN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -245,8 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
-        const uint32_t idesc = (RS && ((t / k_splits) % num_n) == 0) ? idesc_wide : idesc_plain;
+        const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -267,6 +258,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 2 + GEMM_EPI_WARPS) {
+    // ---------------- row sums of the A tiles (RS kernels): warp w owns the 64-row half w of the tile ----------------
+    if (RS) {
+      const int half = warp - (2 + GEMM_EPI_WARPS);          // which 64 x BK box of the A tile (TMA loads two of them)
+      const int unit = lane & 7, kq = lane >> 3;             // 16-byte unit (8 rows m) of the 128-byte line; k rows kq, kq+4, ...
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = (int)(t % k_splits);
+        const long long mn = t / k_splits;
+        const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(num_kb, kb0 + kb_per_split);
+        // the num_n tiles that share this A panel split its K blocks between them (kb % num_n == n_idx), so no tile's
+        // row-sum warps have more than 1 / num_n of the panel to read while its MMAs run
+        const bool mine = ep.rowsum != nullptr;
+        float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (mine && (kb % num_n) == n_idx) {
+            const uint8_t* sa = smem + stage * STAGE_BYTES + half * (A_BYTES / 2);
+#pragma unroll
+            for (int k = kq; k < BK; k += 4) {
+              const uint4 u = *reinterpret_cast<const uint4*>(sa + k * 128 + ((unit ^ (k & 7)) << 4));
+              const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+              acc8[0] += a0.x; acc8[1] += a0.y; acc8[2] += a1.x; acc8[3] += a1.y;
+              acc8[4] += a2.x; acc8[5] += a2.y; acc8[6] += a3.x; acc8[7] += a3.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 8);
+            acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 16);
+          }
+          if (kq == 0) {
+            const int row = m_idx * BM + half * 64 + unit * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (row + j < M) atomicAdd(ep.rowsum + row + j, acc8[j]);
+          }
+        }
       }
     }
   } else {
@@ -294,20 +333,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       long long drow = row;
       if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
       const bool row_ok = row < M && drow >= 0;
-      if (RS && n_idx == 0 && chalf == 0) {            // accumulator column BN: sum_k A[row, k] over this tile's K range
-        uint32_t rsv[2];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(rsv[0]), "=r"(rsv[1])
-                     : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE + BN) : "memory");
-        tmem_ld_wait();
-        if (row < M) atomicAdd(ep.rowsum + row, __uint_as_float(rsv[0]));
-      }
       const float rscale = (ep.row_scale && row < M) ? __ldg(ep.row_scale + row / ep.row_scale_rows) : 1.0f;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[EC];
         const int cb = chalf * CPW + c * EC;             // column offset inside the tile
         const int n0 = n_idx * BN + cb;
-        tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE + cb, r);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb, r);
         tmem_ld_wait();
         if (!row_ok || n0 >= N) continue;
         float v[EC];
@@ -431,12 +463,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
   return after_launch("gemm_bf16_kernel launch");
 }
 
+template <int BN>
 static int dispatch_gemm_rowsum(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                                 int k_splits, const GemmEpi& ep, cudaStream_t stream) {
-  if (a_mn && b_mn) return launch_gemm<1, 1, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
-  if (a_mn) return launch_gemm<1, 0, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
-  if (b_mn) return launch_gemm<0, 1, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
-  return launch_gemm<0, 0, 128, true>(ta, tb, M, N, K, k_splits, ep, stream);
+  CLV_REQUIRE(a_mn, "clv_gemm_bf16: rowsum needs an MN-major A operand (a weight gradient dY^T X)");
+  if (b_mn) return launch_gemm<1, 1, BN, true>(ta, tb, M, N, K, k_splits, ep, stream);
+  return launch_gemm<1, 0, BN, true>(ta, tb, M, N, K, k_splits, ep, stream);
 }
 
 template <int BN>
@@ -460,7 +492,11 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   CLV_REQUIRE(N % 8 == 0, "clv_gemm_bf16: N must be a multiple of 8 (got %d)", N);
   // 128x256 tiles when N fills them (less smem traffic per MAC); 128x128 otherwise
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
-  const bool bn256 = (N % 256 == 0) && tiles256 * (e->k_splits > 0 ? e->k_splits : 1) >= 2LL * num_sms() && !e->rowsum;
+  static long long min_units256 = -1;     // experiment knob: CLOVER_B200_GEMM_BN256_MIN_UNITS overrides the 2-waves rule
+  if (min_units256 < 0) { const char* ev = getenv("CLOVER_B200_GEMM_BN256_MIN_UNITS"); min_units256 = ev ? atoll(ev) : 2LL * num_sms(); }
+  // weight gradients (split-K, K blocks per tile in the hundreds) are L2-bound: always take the wide tile there
+  const bool long_k = (e->k_splits > 1 || e->accumulate) && K / (e->k_splits > 0 ? e->k_splits : 1) >= 4096;
+  const bool bn256 = (N % 256 == 0) && (tiles256 * (e->k_splits > 0 ? e->k_splits : 1) >= min_units256 || long_k);
   CUtensorMap ta, tb;
   int rc;
   if (a_mn_major) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BK);
@@ -516,7 +552,8 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (e->gelu_pre) ok = ok && al32(e->gelu_pre) && (e->ld_gelu_pre * 2) % 32 == 0;
     ep.vec32 = ok ? 1 : 0;
   }
-  if (e->rowsum) return dispatch_gemm_rowsum(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
+  if (e->rowsum) return bn256 ? dispatch_gemm_rowsum<256>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream)
+                              : dispatch_gemm_rowsum<128>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
   if (bn256) return dispatch_gemm<256>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
   return dispatch_gemm<128>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
 }

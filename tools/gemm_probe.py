@@ -16,6 +16,8 @@ SHAPES = [
     # tile-shape sweep for the weight gradients (tag: bn256): k_splits >= 10 makes the dispatcher pick 128x256 tiles
     (512, 2048, 100352, 1, 1, "", "o32", 10), (2048, 512, 100352, 1, 1, "", "o32", 10), (2048, 512, 100352, 1, 1, "", "o32", 4),
     (1536, 512, 100352, 1, 1, "", "o32", 6), (1536, 512, 100352, 1, 1, "", "o32", 13), (512, 512, 100352, 1, 1, "", "o32", 18),
+    (512, 2048, 100352, 1, 1, "", "o32", 5), (512, 2048, 100352, 1, 1, "", "o32", 9), (2048, 512, 100352, 1, 1, "", "o32", 5),
+    (2048, 512, 100352, 1, 1, "", "o32", 9), (1536, 512, 100352, 1, 1, "", "o32", 4), (1536, 512, 100352, 1, 1, "", "o32", 8),
     (50176, 2048, 512, 0, 0, "bg", "o16", 1), (50176, 2048, 512, 0, 1, "p", "o16", 1), (50176, 1536, 512, 0, 0, "b", "o16", 1),
     (50176, 512, 2048, 0, 0, "br", "o32", 1), (50176, 512, 2048, 0, 1, "", "o16", 1), (50176, 512, 512, 0, 0, "br", "o32", 1),
     (802816, 512, 128, 0, 0, "bg", "o16", 1), (802816, 512, 128, 0, 1, "p", "o16", 1), (802816, 384, 128, 0, 0, "b", "o16", 1),
