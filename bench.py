@@ -243,16 +243,21 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     n0 = _lib.launch_count()
-    ops.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     e0.record()
-    for _ in range(args.steps):
+    prof_raw = []
+    for i in range(args.steps):
+        if i == 0:
+            ops.profile_begin()          # per-launch CUDA events on the FIRST timed step only (they cost ~3 % of a step)
         loss = step(devb)
+        if i == 0:
+            prof_raw = ops.profile_detach()
     e1.record()
     sync()
     ms_total = e0.elapsed_time(e1)
-    prof = ops.profile_end()
+    prof = ops.profile_resolve(prof_raw)
+    prof_steps = 1
     launches = _lib.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev)
@@ -307,13 +312,13 @@ def run_ours(args):
         for f, fl, by, ms in prof:
             a = fam.setdefault(f, [0.0, 0.0, 0.0, 0])
             a[0] += fl; a[1] += by; a[2] += ms; a[3] += 1
-        fam_total = sum(v[2] for v in fam.values()) / args.steps
+        fam_total = sum(v[2] for v in fam.values()) / prof_steps
 
         def pre(prefix, i):
             return sum(v[i] for k, v in fam.items() if k.startswith(prefix))
         if os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1":
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            rows = sorted(((k, v[3] // args.steps, v[2] / args.steps, v[0] / max(v[2], 1e-9) / 1e9, v[1] / max(v[2], 1e-9) / 1e6)
+            rows = sorted(((k, v[3] // prof_steps, v[2] / prof_steps, v[0] / max(v[2], 1e-9) / 1e9, v[1] / max(v[2], 1e-9) / 1e6)
                            for k, v in fam.items()), key=lambda r: -r[2])
             with open(os.path.join(ROOT, "gpurun_out", "family_times.txt"), "w") as f:
                 f.write("family | launches/step | ms/step | TFLOP/s | GB/s\n")
@@ -330,8 +335,9 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": gemm_tflops, "peak": sus,
                     "unit": "TFLOP/s", "frac": gemm_tflops / sus, "traffic": traffic, "peak_source": f"{src} bf16_tflops_sustained",
                     "launches_timed": g[3], "avg_launch_ms": g[2] / max(1, g[3]),
-                    "share_of_step": g[2] / (ms_step * args.steps),
-                    "families_ms_per_step": {k: round(pre(k, 2) / args.steps, 3) for k in sorted({n.split(" ")[0] for n in fam})},
+                    "share_of_step": g[2] / (ms_step * prof_steps),
+                    "launch_timing": "CUDA events around every launch of the first timed step",
+                    "families_ms_per_step": {k: round(pre(k, 2) / prof_steps, 3) for k in sorted({n.split(" ")[0] for n in fam})},
                     "untracked_ms_per_step": round(ms_step - fam_total, 3),
                     "window_attn_core_tflops": (pre("attn_fwd_hd32", 0) + pre("attn_bwd_hd32", 0)) /
                                                max(1e-9, (pre("attn_fwd_hd32", 2) + pre("attn_bwd_hd32", 2)) * 1e-3) / 1e12,

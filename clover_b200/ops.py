@@ -62,8 +62,18 @@ def profile_begin():
 
 def profile_end():
     """Returns [(family, algorithmic_flops, algorithmic_bytes, milliseconds)] after synchronising."""
+    return profile_resolve(profile_detach())
+
+
+def profile_detach():
+    """Stop recording WITHOUT synchronising; hand the raw event list to profile_resolve() later (bench.py times only the
+    first step of its timed region this way, so the per-launch events do not tax the other steps)."""
     global _PROF
     rec, _PROF = _PROF or [], None
+    return rec
+
+
+def profile_resolve(rec):
     torch.cuda.synchronize()
     return [(fam, fl, by, e0.elapsed_time(e1)) for fam, fl, by, e0, e1 in rec]
 
