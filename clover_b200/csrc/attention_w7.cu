@@ -83,6 +83,12 @@ CLV_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+// shared -> global with an element-wise add performed at the destination (L2): bf16 tiles of several units accumulate
+// into one small buffer instead of being written out one by one
+CLV_DEVICE void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
 CLV_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 CLV_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 CLV_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -380,6 +386,9 @@ struct W7BwdArgs {
   int pipe;                      // issue dV / dK steps chunk by chunk while the softmax warps are still working
   __nv_bfloat16* dkv_part;       // bwd2 with 392 keys: dK | dV partial sums of the second query half, bf16 [rows, 2 C]
   long long ds_half_rows;        // bwd2 with 392 keys: row offset of the second query half in the dS^T dump
+  int ds_spans;                  // dump_ds == 2 (bwd2): dS^T tiles are ADDED (TMA reduce, bf16) into per-CTA buffers
+                                 // [gridDim.x][ds_spans heads][query halves][keys][nq] that stay in L2; ds_spans = max number of
+                                 // heads one CTA's contiguous unit range touches
 };
 
 constexpr int W7_BWD_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2-9: two column groups x four lane quarters
@@ -1005,7 +1014,13 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
           tc_fence_after();
           mma_dvk(2, 0, acc);
           umma_commit(dvk_done);
-          if (a.dump_ds) {
+          if (a.dump_ds == 2) {
+            const int hh = (int)((u / NH) / a.batch), h_first = (int)((u_begin / NH) / a.batch);
+            const int buf = ((int)blockIdx.x * a.ds_spans + (hh - h_first)) * NH + (int)(u % NH);
+            const int grow = buf * KSEQ + t * W7_TILE;
+            for (int q = 0; q < 4; ++q) tma_reduce_add_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
+            tma_store_commit();
+          } else if (a.dump_ds) {
             const long long uu = u / NH;
             const int grow = (int)((u % NH) * a.ds_half_rows + ((uu % a.batch) * a.heads + (uu / a.batch)) * KSEQ) + t * W7_TILE;
             for (int q = 0; q < 4; ++q) tma_store_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
@@ -1168,6 +1183,42 @@ __global__ void __launch_bounds__(256) attn_w7_dbias_kernel(const __nv_bfloat16*
     if (i < nqv) {
       const int ci = (i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7);
       atomicAdd(dtable + (long long)(ci - cj + code_off) * heads + h, acc[e]);
+    }
+  }
+}
+
+// Same reduction from the per-CTA accumulation buffers of the dump_ds == 2 mode: buffer (c, slot, qh) holds the sum of
+// dS^T over the units of head h_first(c) + slot that CTA c of the backward kernel processed (its contiguous unit range is
+// recomputed here from the same formula), so a thread walks the <= grid_bwd CTAs and adds the buffers of ITS head.
+__global__ void __launch_bounds__(256) attn_w7_dbias_acc_kernel(const __nv_bfloat16* ds, int grid_bwd, long long units, int batch,
+                                                                int heads, int nh, int spans, int kseq, int ld, int nqv,
+                                                                int code_off, float* dtable) {
+  const int oct = ld >> 3;
+  const int pos = blockIdx.x * 256 + threadIdx.x;
+  if (pos >= kseq * oct) return;
+  const int j = pos / oct, i0 = (pos - j * oct) * 8;
+  const int h = blockIdx.y, qh = blockIdx.z;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long base = units / grid_bwd, rem = units % grid_bwd;
+  for (int c = 0; c < grid_bwd; ++c) {
+    const long long u0 = c * base + (c < rem ? c : rem), u1 = u0 + base + (c < rem ? 1 : 0);
+    if (u1 <= u0) continue;
+    const int h0 = (int)((u0 / nh) / batch), h1 = (int)(((u1 - 1) / nh) / batch);
+    if (h < h0 || h > h1) continue;
+    const long long buf = ((long long)c * spans + (h - h0)) * nh + qh;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(ds + (buf * kseq + j) * ld + i0));
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+    acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+    acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+  }
+  const int cj = (j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7);
+  const int off = code_off + qh * 4 * W7_SH;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int i = i0 + e;
+    if (i < nqv && acc[e] != 0.f) {
+      const int ci = (i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7);
+      atomicAdd(dtable + (long long)(ci - cj + off) * heads + h, acc[e]);
     }
   }
 }
@@ -1346,13 +1397,44 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   if (int rc = make_tmap_bf16_2d(&tdo, dout, ldo, rows, ldo, W7_HD, a.nq, 64)) return rc;
   if (int rc = make_tmap_bf16_2d(&te, e, 16, rows * d->heads, 16, 16, a.nq, 32)) return rc;
   tkx = te; tds = te;
-  if (ds_out) { if (int rc = make_tmap_bf16_2d(&tds, ds_out, a.nq, rows * d->heads * (halves ? 2 : 1), a.nq, 64, W7_TILE, 128)) return rc; }
+  // bias-table gradient: either dump every unit's dS^T (batch * heads * seq * nq bf16, read back by attn_w7_dbias_kernel) or,
+  // for the chunk-ring kernels, let TMA ADD the tiles into per-CTA buffers that stay in L2 (dump_ds == 2)
+  static int gen2 = -1;
+  if (gen2 < 0) { const char* ev = getenv("CLOVER_B200_W7_BWD2"); gen2 = ev ? atoi(ev) : 1; }
+  const bool ring = halves || (a.seq == 196 && gen2);
+  const int nh = halves ? 2 : 1;
+  const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
+  long long nbuf = 0;
+  if (ds_out && ring) {
+    // acc_mode: 0 never, 1 when the dump would be large (it then costs more HBM traffic than the L2 adds), 2 always
+    static int acc_mode = -1;
+    if (acc_mode < 0) { const char* ev = getenv("CLOVER_B200_W7_DBIAS_ACC"); acc_mode = ev ? atoi(ev) : 1; }
+    static long long acc_min_bytes = -1;
+    if (acc_min_bytes < 0) { const char* ev = getenv("CLOVER_B200_W7_DBIAS_ACC_MIN_MB"); acc_min_bytes = (ev ? atoll(ev) : 512) << 20; }
+    int spans = 1;
+    const long long base = a.units / grid, rem = a.units % grid;
+    for (int c = 0; c < grid; ++c) {
+      const long long u0 = c * base + (c < rem ? c : rem), u1 = u0 + base + (c < rem ? 1 : 0);
+      if (u1 > u0) spans = std::max(spans, (int)(((u1 - 1) / nh) / d->batch - (u0 / nh) / d->batch) + 1);
+    }
+    nbuf = (long long)grid * spans * nh;
+    const long long dump_bytes = rows * d->heads * nh * a.nq * 2;
+    if (acc_mode && (acc_mode == 2 || dump_bytes >= acc_min_bytes) && nbuf * a.seq <= rows * d->heads * nh) {   // fits in the dump's space
+      a.dump_ds = 2;
+      a.ds_spans = spans;
+      CLV_CHECK_CUDA(cudaMemsetAsync(ds_out, 0, (size_t)nbuf * a.seq * a.nq * 2, stream));
+    } else {
+      nbuf = 0;
+    }
+  }
+  if (ds_out) {
+    const long long ds_rows = a.dump_ds == 2 ? nbuf * a.seq : rows * d->heads * nh;
+    if (int rc = make_tmap_bf16_2d(&tds, ds_out, a.nq, ds_rows, a.nq, 64, W7_TILE, 128)) return rc;
+  }
   if (a.has_kx) { if (int rc = make_tmap_bf16_2d(&tkx, d->k_ext, 16, (long long)a.nwin * a.seq, 16, 16, 128, 32)) return rc; }
   const size_t smem = 1024 + 2 * (2 * (size_t)a.qb_bytes + a.eb_bytes) + 2 * (2 * 8192 + 4096) + 4096 + (size_t)a.n_mq * 2 * 16384 +
                       (size_t)a.table_ld * 4 + 22 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_bwd: %zu bytes of shared memory needed", smem);
-  static int gen2 = -1;
-  if (gen2 < 0) { const char* ev = getenv("CLOVER_B200_W7_BWD2"); gen2 = ev ? atoi(ev) : 1; }
   auto kern = halves ? attn_w7_bwd2_kernel<392>
                      : (a.seq == 196 ? (gen2 ? attn_w7_bwd2_kernel<196> : attn_w7_bwd_kernel<196>) : attn_w7_bwd_kernel<98>);
   const int ki = halves ? 2 : (a.seq == 196 ? 1 : 0);
@@ -1361,7 +1443,6 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set[ki] = smem;
   }
-  const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
   kern<<<grid, W7_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, te, tkx, tds, a);
   if (int rc = after_launch("attn_w7_bwd_kernel")) return rc;
   if (halves) {
@@ -1370,7 +1451,12 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     attn_w7_dkv_combine_kernel<<<g, 256, 0, stream>>>(a.dqkv, a.dkv_part, rows, d->heads * W7_HD);
     if (int rc = after_launch("attn_w7_dkv_combine_kernel")) return rc;
   }
-  if (dbias_table) {
+  if (dbias_table && a.dump_ds == 2) {
+    dim3 g((a.seq * (a.nq / 8) + 255) / 256, d->heads, nh);
+    attn_w7_dbias_acc_kernel<<<g, 256, 0, stream>>>(ds_out, grid, a.units, d->batch, d->heads, nh, a.ds_spans, a.seq, a.nq,
+                                                    halves ? 196 : a.seq, a.code_off, dbias_table);
+    if (int rc = after_launch("attn_w7_dbias_acc_kernel")) return rc;
+  } else if (dbias_table) {
     const int pos_blocks = (a.seq * (a.nq / 8) + 255) / 256;
     const int zsplit = std::max(1, std::min(std::min(64, d->batch / 8), (8 * num_sms()) / (pos_blocks * d->heads) + 1));
     dim3 g(pos_blocks, d->heads, zsplit);

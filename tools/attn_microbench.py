@@ -32,12 +32,14 @@ def main():
     ap.add_argument("--which", default="fwd,bwd")
     ap.add_argument("--shifted", type=int, default=1)
     ap.add_argument("--dbias", type=int, default=1, help="0: backward without the bias-table gradient (no dS dump)")
+    ap.add_argument("--clips", type=int, default=0, help="override the clip count of every shape (c3 batches 128 clip-passes)")
     args = ap.parse_args()
     from clover_b200 import ops, swin, tables
     dev = torch.device("cuda")
     res = []
     for name in args.shapes.split(","):
         clips, dims, heads = SHAPES[name]
+        clips = args.clips or clips
         hd = 32
         win, sh = tables.get_window_size(dims, (8, 7, 7), (4, 3, 3) if args.shifted else (0, 0, 0))
         N = win[0] * win[1] * win[2]
