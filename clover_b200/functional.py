@@ -37,7 +37,8 @@ def w16_cat(params, key_obj):
     key = ("cat", id(key_obj))
     vers = tuple(p._version for p in params)
     ent = _W16.get(key)
-    if ent is not None and ent[0] == vers and ent[1].device == params[0].device:
+    if (ent is not None and ent[0] == vers and ent[1].device == params[0].device and ent[2] is key_obj
+            and len(ent[3]) == len(params) and all(a is b for a, b in zip(ent[3], params))):
         return ent[1]
     t = ops.to_bf16(torch.cat([p.detach() for p in params], 0).contiguous())
     _W16[key] = (vers, t, key_obj, tuple(params))
