@@ -50,6 +50,12 @@ def _worker(rank, world, port, q):
         res["emb_grads"] = [e.grad.clone() for e in embs]
         res["loss"] = float(loss["nce_loss"] + loss["rank_t_tm_loss"])
         res["x"] = x.detach()
+        # logged scalars: one packed all-reduce, every entry averaged over the ranks (recognizers/base.py:254-288); the
+        # returned loss tensor stays local (DDP averages its gradient)
+        from clover_b200.recognizers import BaseRecognizer
+        lt = torch.tensor(float(rank + 1), requires_grad=True)
+        total, log_vars = BaseRecognizer._parse_losses({"a_loss": lt * 2.0, "acc": torch.tensor(10.0 * rank), "b_loss": [lt, lt]})
+        res["parse_total"], res["parse_log"] = float(total.detach()), dict(log_vars)
         # tensors travel through the queue as shared-memory handles that die with this process: send them by value
         res = {k: ([t.numpy().copy() for t in v] if isinstance(v, list) else (v.numpy().copy() if torch.is_tensor(v) else v))
                for k, v in res.items()}
@@ -91,3 +97,7 @@ def test_gather_semantics_world2():
     for i in range(4):
         assert torch.allclose(r0["emb_grads"][i], glob[i].grad[:4], atol=1e-6)
         assert torch.allclose(r1["emb_grads"][i], glob[i].grad[4:], atol=1e-6)
+    # _parse_losses: local total = sum of the '*loss*' entries; logged values are rank means
+    assert r0["parse_total"] == 4.0 and r1["parse_total"] == 8.0
+    for r in (r0, r1):
+        assert r["parse_log"] == {"a_loss": 3.0, "acc": 5.0, "b_loss": 3.0, "loss": 6.0}
