@@ -1195,18 +1195,27 @@ __global__ void __launch_bounds__(256) attn_w7_dbias_acc_kernel(const __nv_bfloa
                                                                 int code_off, float* dtable) {
   const int oct = ld >> 3;
   const int pos = blockIdx.x * 256 + threadIdx.x;
+  const int h = blockIdx.y, qh = blockIdx.z;
+  // the buffers that hold head h: found once per block (the backward kernel's unit ranges are recomputed from its formula)
+  __shared__ int hit[256];
+  __shared__ int nhit;
+  if (threadIdx.x == 0) nhit = 0;
+  __syncthreads();
+  {
+    const long long base = units / grid_bwd, rem = units % grid_bwd;
+    for (int c = threadIdx.x; c < grid_bwd; c += 256) {
+      const long long u0 = c * base + (c < rem ? c : rem), u1 = u0 + base + (c < rem ? 1 : 0);
+      if (u1 <= u0) continue;
+      const int h0 = (int)((u0 / nh) / batch), h1 = (int)(((u1 - 1) / nh) / batch);
+      if (h >= h0 && h <= h1) hit[atomicAdd(&nhit, 1)] = (int)((((long long)c * spans + (h - h0)) * nh) + qh);
+    }
+  }
+  __syncthreads();
   if (pos >= kseq * oct) return;
   const int j = pos / oct, i0 = (pos - j * oct) * 8;
-  const int h = blockIdx.y, qh = blockIdx.z;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const long long base = units / grid_bwd, rem = units % grid_bwd;
-  for (int c = 0; c < grid_bwd; ++c) {
-    const long long u0 = c * base + (c < rem ? c : rem), u1 = u0 + base + (c < rem ? 1 : 0);
-    if (u1 <= u0) continue;
-    const int h0 = (int)((u0 / nh) / batch), h1 = (int)(((u1 - 1) / nh) / batch);
-    if (h < h0 || h > h1) continue;
-    const long long buf = ((long long)c * spans + (h - h0)) * nh + qh;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(ds + (buf * kseq + j) * ld + i0));
+  for (int k = 0; k < nhit; ++k) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(ds + ((long long)hit[k] * kseq + j) * ld + i0));
     const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
     acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
     acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
@@ -1410,7 +1419,7 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     static int acc_mode = -1;
     if (acc_mode < 0) { const char* ev = getenv("CLOVER_B200_W7_DBIAS_ACC"); acc_mode = ev ? atoi(ev) : 1; }
     static long long acc_min_bytes = -1;
-    if (acc_min_bytes < 0) { const char* ev = getenv("CLOVER_B200_W7_DBIAS_ACC_MIN_MB"); acc_min_bytes = (ev ? atoll(ev) : 512) << 20; }
+    if (acc_min_bytes < 0) { const char* ev = getenv("CLOVER_B200_W7_DBIAS_ACC_MIN_MB"); acc_min_bytes = (ev ? atoll(ev) : 128) << 20; }
     int spans = 1;
     const long long base = a.units / grid, rem = a.units % grid;
     for (int c = 0; c < grid; ++c) {
