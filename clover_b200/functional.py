@@ -84,7 +84,37 @@ def clear_weight_cache():
     _W16_CAT_OF.clear()
 
 
+# Zero-initialised fp32 scratch for the small accumulated gradients (LayerNorm gamma / beta, bias-table, bias row sums ...):
+# ~200 separate torch.zeros fills per step become ONE.  The recogniser opens a fresh arena at the start of every training
+# forward (a new buffer each time -- gradients of the previous step may still alias the old one); requests that do not
+# fit, or arrive before any arena exists, fall back to torch.zeros and enlarge the next arena.
+class _ZeroArena:
+    buf, off, cap, used, device = None, 0, 0, 0, None
+
+
+_ARENA = _ZeroArena()
+
+
+def zero_arena_begin(device):
+    a = _ARENA
+    want = max(a.used, a.off)
+    a.used, a.off = 0, 0
+    if want == 0:
+        a.buf, a.cap = None, 0
+        return
+    a.cap = int(want * 1.25) + 4096
+    a.buf = torch.zeros(a.cap, dtype=F32, device=device)
+    a.device = a.buf.device
+
+
 def _zeros(n, device):
+    a = _ARENA
+    n_al = (int(n) + 63) // 64 * 64                      # 256-byte granules keep every slice vector-aligned
+    a.used += n_al
+    if a.buf is not None and a.device == torch.device(device) and a.off + n_al <= a.cap:
+        t = a.buf[a.off:a.off + n]
+        a.off += n_al
+        return t
     return torch.zeros(n, dtype=F32, device=device)
 
 
@@ -93,7 +123,7 @@ def _wgrad(dy16, x16, out_features, in_features, want_bias=False):
     gradient sum_t dY[t, :], produced by the same GEMM (row sums of its A operand on the tensor cores)."""
     T = dy16.shape[0]
     dW = torch.empty(out_features, in_features, dtype=F32, device=dy16.device)
-    db = torch.zeros(out_features, dtype=F32, device=dy16.device) if want_bias else None
+    db = _zeros(out_features, dy16.device) if want_bias else None
     ops.gemm(dy16, x16, dW, a_t=True, b_t=True, k_splits=ops.wgrad_splits(out_features, in_features, T), rowsum=db)
     return (dW, db) if want_bias else dW
 

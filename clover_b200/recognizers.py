@@ -135,6 +135,7 @@ class CloverPretrain(BaseRecognizer):
     def forward_train(self, imgs, label, token_ids=None, segment_ids=None, input_mask=None, mlm_label=None,
                       dvae_imgs=None, v_token_mask=None, hog_features=None, img_metas=None, **kwargs):
         imgs = _flat(imgs)                                                         # :81
+        Fn.zero_arena_begin(imgs.device)
         if self.from_scratch:
             imgs = imgs / 255.0
         token_ids, text_mask = _flat(token_ids), _flat(input_mask)                 # :85-86
@@ -265,6 +266,8 @@ class CloverFinetune(BaseRecognizer):
 
     def _encode(self, imgs, token_ids, input_mask):
         imgs = _flat(imgs)
+        if self.training:
+            Fn.zero_arena_begin(imgs.device)
         if self.from_scratch:
             imgs = imgs / 255.0
         B_text = token_ids.shape[0]
