@@ -118,6 +118,13 @@ CLV_DEVICE void mma_p_r(float (&o)[HD / 8][4], const float (&p)[8][4], const __n
   }
 }
 
+// 2^x on the MUFU pipe without exp2f's denormal fix-up (the arguments here are <= 0 or differences to a row maximum / lse)
+CLV_DEVICE float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct BiasCtx {
   const float* table;   // smem [table_len] for this head, or nullptr
   const int* code;      // smem [npad]
@@ -127,8 +134,11 @@ struct BiasCtx {
 };
 
 // additive score term for (query i, key j); NEG_BIG for keys/queries outside the sequence.
+// MODE 1 = the BERT / fusion case (key mask only): no table / region tests in the element loop.
+template <int MODE>
 CLV_DEVICE float score_bias(const BiasCtx& c, int i, int j) {
   if (j >= c.seq || i >= c.seq) return NEG_BIG;
+  if (MODE == 1) return c.kmask[j];
   float b = 0.f;
   if (c.table) b += c.table[c.code[i] - c.code[j] + c.code_off];
   if (c.region) b += (c.region[i] != c.region[j]) ? -100.0f : 0.0f;
@@ -145,7 +155,7 @@ CLV_DEVICE float attn_keep(const AttnArgs& a, int bh, int i, int j) {
 // shared-memory carve-up helpers ------------------------------------------------------------
 CLV_DEVICE int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-template <int HD>
+template <int HD, int MODE>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
   constexpr int STRIDE = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -204,8 +214,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
       for (int nt = 0; nt < 8; ++nt) {
         const int j = kc + nt * 8 + q4 * 2;
         if (nt < ntv) {
-          s[nt][0] += score_bias(bc, i0, j); s[nt][1] += score_bias(bc, i0, j + 1);
-          s[nt][2] += score_bias(bc, i1, j); s[nt][3] += score_bias(bc, i1, j + 1);
+          s[nt][0] += score_bias<MODE>(bc, i0, j); s[nt][1] += score_bias<MODE>(bc, i0, j + 1);
+          s[nt][2] += score_bias<MODE>(bc, i1, j); s[nt][3] += score_bias<MODE>(bc, i1, j + 1);
         } else {
           s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = NEG_BIG;
         }
@@ -215,13 +225,13 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-      const float c0 = exp2f((m0 - mn0) * LOG2E), c1 = exp2f((m1 - mn1) * LOG2E);
+      const float c0 = fast_ex2((m0 - mn0) * LOG2E), c1 = fast_ex2((m1 - mn1) * LOG2E);
       m0 = mn0; m1 = mn1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = exp2f((s[nt][0] - mn0) * LOG2E); s[nt][1] = exp2f((s[nt][1] - mn0) * LOG2E);
-        s[nt][2] = exp2f((s[nt][2] - mn1) * LOG2E); s[nt][3] = exp2f((s[nt][3] - mn1) * LOG2E);
+        s[nt][0] = fast_ex2((s[nt][0] - mn0) * LOG2E); s[nt][1] = fast_ex2((s[nt][1] - mn0) * LOG2E);
+        s[nt][2] = fast_ex2((s[nt][2] - mn1) * LOG2E); s[nt][3] = fast_ex2((s[nt][3] - mn1) * LOG2E);
         rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
       }
       l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
@@ -283,7 +293,7 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* out, const __nv_bfloat
 }
 
 // dQ (+ d bias table).  Resident: K, V.  Per warp: Q and dO tiles of 16 rows.
-template <int HD>
+template <int HD, int MODE>
 __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnArgs a) {
   constexpr int STRIDE = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -356,12 +366,12 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnArgs a) {
         const int j = kc + nt * 8 + q4 * 2;
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
         if (nt < ntv) {
-          const float b0 = score_bias(bc, i0, j), b1 = score_bias(bc, i0, j + 1);
-          const float b2 = score_bias(bc, i1, j), b3 = score_bias(bc, i1, j + 1);
-          p0 = b0 <= NEG_BIG ? 0.f : exp2f((s[nt][0] + b0 - lse0) * LOG2E);
-          p1 = b1 <= NEG_BIG ? 0.f : exp2f((s[nt][1] + b1 - lse0) * LOG2E);
-          p2 = b2 <= NEG_BIG ? 0.f : exp2f((s[nt][2] + b2 - lse1) * LOG2E);
-          p3 = b3 <= NEG_BIG ? 0.f : exp2f((s[nt][3] + b3 - lse1) * LOG2E);
+          const float b0 = score_bias<MODE>(bc, i0, j), b1 = score_bias<MODE>(bc, i0, j + 1);
+          const float b2 = score_bias<MODE>(bc, i1, j), b3 = score_bias<MODE>(bc, i1, j + 1);
+          p0 = b0 <= NEG_BIG ? 0.f : fast_ex2((s[nt][0] + b0 - lse0) * LOG2E);
+          p1 = b1 <= NEG_BIG ? 0.f : fast_ex2((s[nt][1] + b1 - lse0) * LOG2E);
+          p2 = b2 <= NEG_BIG ? 0.f : fast_ex2((s[nt][2] + b2 - lse1) * LOG2E);
+          p3 = b3 <= NEG_BIG ? 0.f : fast_ex2((s[nt][3] + b3 - lse1) * LOG2E);
         }
         if (a.drop_thresh) {   // dP = dP_dropped * keep / (1 - p)
           dp[nt][0] *= attn_keep(a, bh, i0, j); dp[nt][1] *= attn_keep(a, bh, i0, j + 1);
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(AttnArgs a) {
 }
 
 // dK, dV.  Resident: Q, dO (+ lse, D).  Per warp: K and V tiles of 16 keys.
-template <int HD>
+template <int HD, int MODE>
 __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(AttnArgs a) {
   constexpr int STRIDE = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -479,12 +489,12 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(AttnArgs a) {
         const int i = qc + nt * 8 + q4 * 2;          // query index (column)
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
         if (nt < ntv) {
-          const float b0 = score_bias(bc, i, j0), b1 = score_bias(bc, i + 1, j0);
-          const float b2 = score_bias(bc, i, j1), b3 = score_bias(bc, i + 1, j1);
-          p0 = b0 <= NEG_BIG ? 0.f : exp2f((st[nt][0] + b0 - sLse[i]) * LOG2E);
-          p1 = b1 <= NEG_BIG ? 0.f : exp2f((st[nt][1] + b1 - sLse[i + 1]) * LOG2E);
-          p2 = b2 <= NEG_BIG ? 0.f : exp2f((st[nt][2] + b2 - sLse[i]) * LOG2E);
-          p3 = b3 <= NEG_BIG ? 0.f : exp2f((st[nt][3] + b3 - sLse[i + 1]) * LOG2E);
+          const float b0 = score_bias<MODE>(bc, i, j0), b1 = score_bias<MODE>(bc, i + 1, j0);
+          const float b2 = score_bias<MODE>(bc, i, j1), b3 = score_bias<MODE>(bc, i + 1, j1);
+          p0 = b0 <= NEG_BIG ? 0.f : fast_ex2((st[nt][0] + b0 - sLse[i]) * LOG2E);
+          p1 = b1 <= NEG_BIG ? 0.f : fast_ex2((st[nt][1] + b1 - sLse[i + 1]) * LOG2E);
+          p2 = b2 <= NEG_BIG ? 0.f : fast_ex2((st[nt][2] + b2 - sLse[i]) * LOG2E);
+          p3 = b3 <= NEG_BIG ? 0.f : fast_ex2((st[nt][3] + b3 - sLse[i + 1]) * LOG2E);
           float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
           if (a.drop_thresh) {
             k0 = attn_keep(a, bh, i, j0); k1 = attn_keep(a, bh, i + 1, j0);
@@ -570,7 +580,7 @@ __global__ void __launch_bounds__(128) attn_probs_mean_kernel(AttnArgs a) {
     float sum = 0.f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      sc[u] = (tid + u * 128 < seq) ? exp2f((sc[u] - mx) * LOG2E) : 0.f;
+      sc[u] = (tid + u * 128 < seq) ? fast_ex2((sc[u] - mx) * LOG2E) : 0.f;
       sum += sc[u];
     }
     sum = warp_sum(sum);
@@ -640,8 +650,10 @@ extern "C" int clv_attention_fwd(const clv_attn_desc_t* d, const void* qkv, void
   const size_t resident = (size_t)2 * npad * stride * 2;
   const int nw = pick_warps(resident);
   const size_t smem = resident + (size_t)nw * 16 * stride * 2 + (d->bias_table ? d->table_len * 4 : 0) + (size_t)npad * 12;
-  if (hd == 32) return launch_attn(attn_fwd_kernel<32>, a, nw, smem, stream, "attn_fwd_kernel<32>");
-  return launch_attn(attn_fwd_kernel<64>, a, nw, smem, stream, "attn_fwd_kernel<64>");
+  const bool mask_only = d->key_mask && !d->bias_table && !d->region;
+  if (hd == 32) return launch_attn(attn_fwd_kernel<32, 0>, a, nw, smem, stream, "attn_fwd_kernel<32>");
+  if (mask_only) return launch_attn(attn_fwd_kernel<64, 1>, a, nw, smem, stream, "attn_fwd_kernel<64,mask>");
+  return launch_attn(attn_fwd_kernel<64, 0>, a, nw, smem, stream, "attn_fwd_kernel<64>");
 }
 
 extern "C" int clv_attention_bwd(const clv_attn_desc_t* d, const void* qkv, const void* out, const void* dout,
@@ -669,12 +681,16 @@ extern "C" int clv_attention_bwd(const clv_attn_desc_t* d, const void* qkv, cons
   const size_t smem_dq = resident + (size_t)nw * 32 * stride * 2 + tab + (dbias_table ? tab : 0) + (size_t)npad * 12;
   const size_t smem_dkv = resident + (size_t)nw * 32 * stride * 2 + tab + (size_t)npad * 20;
   int rc;
+  const bool mask_only = d->key_mask && !d->bias_table && !d->region;
   if (hd == 32) {
-    rc = launch_attn(attn_bwd_dq_kernel<32>, a, nw, smem_dq, stream, "attn_bwd_dq_kernel<32>");
-    if (!rc) rc = launch_attn(attn_bwd_dkv_kernel<32>, a, nw, smem_dkv, stream, "attn_bwd_dkv_kernel<32>");
+    rc = launch_attn(attn_bwd_dq_kernel<32, 0>, a, nw, smem_dq, stream, "attn_bwd_dq_kernel<32>");
+    if (!rc) rc = launch_attn(attn_bwd_dkv_kernel<32, 0>, a, nw, smem_dkv, stream, "attn_bwd_dkv_kernel<32>");
+  } else if (mask_only) {
+    rc = launch_attn(attn_bwd_dq_kernel<64, 1>, a, nw, smem_dq, stream, "attn_bwd_dq_kernel<64,mask>");
+    if (!rc) rc = launch_attn(attn_bwd_dkv_kernel<64, 1>, a, nw, smem_dkv, stream, "attn_bwd_dkv_kernel<64,mask>");
   } else {
-    rc = launch_attn(attn_bwd_dq_kernel<64>, a, nw, smem_dq, stream, "attn_bwd_dq_kernel<64>");
-    if (!rc) rc = launch_attn(attn_bwd_dkv_kernel<64>, a, nw, smem_dkv, stream, "attn_bwd_dkv_kernel<64>");
+    rc = launch_attn(attn_bwd_dq_kernel<64, 0>, a, nw, smem_dq, stream, "attn_bwd_dq_kernel<64>");
+    if (!rc) rc = launch_attn(attn_bwd_dkv_kernel<64, 0>, a, nw, smem_dkv, stream, "attn_bwd_dkv_kernel<64>");
   }
   return rc;
 }
