@@ -22,32 +22,54 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "clover_pretrain_clips_per_sec"
 UNIT = "clips/s"
 SWIN_B = dict(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), img_in=1024)
-FLOP_PER_CLIP_FWD_BWD = 885e9          # ~295 GFLOP fwd, x3 for fwd+bwd
+# BASELINE.json configs that are whole training steps (c1 is the CPU case = the reference arm's sample, c2 the window-attention
+# microbenchmark reported inside the c3 line).  flop = algorithmic FLOP per clip, forward + backward (SURVEY.md 8(d) / BASELINE.md 4).
+WORKLOADS = {
+    "c3": dict(metric="clover_pretrain_clips_per_sec", frames=8, L=32, clips=64, flop=885e9, grad_clip=15.0, wd=0.005,
+               text="c3: CloverPretrain step, Video Swin-B + BERT-base text + 3-layer fusion, tri-modal NCE/ranking + MLM focal, "
+                    "fwd+bwd+grad-allreduce+AdamW"),
+    "c4": dict(metric="clover_finetune_retrieval_clips_per_sec", frames=16, L=40, clips=16, flop=3 * (281.3e9 + 6.9e9), grad_clip=5.0,
+               wd=0.001, task="retrieval",
+               text="c4: CloverFinetune(task='retrieval') step, Video Swin-B on 16x224x224 clips (N = 392 windows) + BERT-base on "
+                    "40-token queries, NormSoftmaxLoss over the all-gathered batch, fwd+bwd+grad-allreduce+AdamW"),
+    "c5": dict(metric="clover_finetune_videoqa_clips_per_sec", frames=16, L=40, clips=16, flop=3 * (281.3e9 + 6.9e9 + 20.1e9),
+               grad_clip=50.0, wd=0.001, task="video_qa",
+               text="c5: CloverFinetune(task='video_qa') step, Video Swin-B on 16x224x224 clips + BERT-base + 3-layer fusion over "
+                    "432 tokens + QA_OE_Head(1500) + CE, fwd+bwd+grad-allreduce+AdamW"),
+}
+METRIC = WORKLOADS["c3"]["metric"]
+FLOP_PER_CLIP_FWD_BWD = WORKLOADS["c3"]["flop"]
 
 
-def model_cfg(regularisers=True):
-    from clover_b200.configs import SHIPPED_REGULARISERS, pretrain_cfg
-    reg = SHIPPED_REGULARISERS if regularisers else {}
-    return pretrain_cfg(SWIN_B["embed"], SWIN_B["depths"], SWIN_B["heads"], SWIN_B["img_in"], 768, 30522, 12, 3, 4, **reg)
+def model_cfg(regularisers=True, workload="c3"):
+    from clover_b200.configs import SHIPPED_REGULARISERS, finetune_cfg, pretrain_cfg
+    if workload == "c3":
+        reg = SHIPPED_REGULARISERS if regularisers else {}
+        return pretrain_cfg(SWIN_B["embed"], SWIN_B["depths"], SWIN_B["heads"], SWIN_B["img_in"], 768, 30522, 12, 3, 4, **reg)
+    # fine-tune shapes: mm_backbone.num_frames must cover T = 16 / 2
+    drop = 0.1 if regularisers else 0.0
+    cfg = finetune_cfg(WORKLOADS[workload]["task"], frames_half=8, bert_dropout=drop, qa_dropout=0.5 if regularisers else 0.0)
+    cfg["backbone"]["drop_path_rate"] = 0.3 if regularisers else 0.0
+    return cfg
 
 
-def workload_config(clips, n_gpus, regularisers=True):
+def workload_config(clips, n_gpus, regularisers=True, workload="c3"):
     from clover_b200.configs import SHIPPED_REGULARISERS
+    w = WORKLOADS[workload]
     reg = SHIPPED_REGULARISERS if regularisers else dict(bert_dropout=0.0, drop_path_rate=0.0, t_head_dropout=0.0)
+    mb = clips * 3 * w["frames"] * 224 * 224 * 4 / 1e6
     return {
-        "workload": "c3: CloverPretrain step, Video Swin-B + BERT-base text + 3-layer fusion, tri-modal NCE/ranking + MLM focal, "
-                    "fwd+bwd+grad-allreduce+AdamW",
-        "clips_per_gpu": clips, "frames": 8, "resolution": 224, "caption_tokens": 32, "global_batch": clips * n_gpus,
+        "workload": w["text"],
+        "clips_per_gpu": clips, "frames": w["frames"], "resolution": 224, "caption_tokens": w["L"], "global_batch": clips * n_gpus,
         "parallelism": f"dp{n_gpus}", "dropout": reg["bert_dropout"], "drop_path": reg["drop_path_rate"],
-        "text_head_dropout": reg["t_head_dropout"],
-        "regularisers": "shipped rates of configs/exp_local/pretrain_webvid_cc3m.py (training mode)" if regularisers else
+        "text_head_dropout": reg["t_head_dropout"] if workload == "c3" else None,
+        "regularisers": "shipped rates of the reference config (training mode)" if regularisers else
                         "all zero (the parity configuration; --parity-config)",
-        "optimizer": "clover_b200.optim.FusedAdamW (one multi-tensor kernel: AdamW on fp32 masters + grad-norm clip 15 + finite check "
-                     "+ bf16 weight refresh), paramwise weight decay of pretrain_webvid_cc3m.py:129-137, inside the timed region",
-        "l2_policy": "per-step inputs (308 MB of clips) and activations (tens of GB) far exceed the 126 MB L2",
+        "optimizer": f"clover_b200.optim.FusedAdamW (one multi-tensor kernel: AdamW on fp32 masters + grad-norm clip {w['grad_clip']:g} + "
+                     "finite check + bf16 weight refresh), paramwise weight decay of the shipped config, inside the timed region",
+        "l2_policy": f"per-step inputs ({mb:.0f} MB of clips) and activations (tens of GB) far exceed the 126 MB L2",
     }
 
 
@@ -93,8 +115,9 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, clips=2, seed=1000, regularisers=True):
-    """The reference's algorithm (oracle port, fp32, plain PyTorch CPU ops) on the host cores: fwd + bwd of the same
-    pre-train step on a bounded sample of `clips` clips per step.  Returns (clips_per_sec, ms_per_step, cores)."""
+    """The reference's algorithm (oracle port, fp32, plain PyTorch CPU ops) on the host cores: fwd + bwd + grad-norm clip +
+    AdamW (torch.optim, the reference's optimizer) of the same pre-train step on a bounded sample of `clips` clips per step.
+    Returns (clips_per_sec, ms_per_step, cores)."""
     import torch
     from clover_b200.synthetic import make_batch, synth_state_dict
     from oracle import clover_oracle as O
@@ -106,6 +129,8 @@ def cpu_reference_run(steps, warmup, clips=2, seed=1000, regularisers=True):
     state = {k: v.requires_grad_(True) for k, v in synth_state_dict(shapes, 7).items()}
     cfg = dict(depths=list(SWIN_B["depths"]), num_heads=list(SWIN_B["heads"]), text_layers=12, fusion_layers=3, bert_heads=12,
                vocab=30522)
+    params = list(state.values())
+    opt = torch.optim.AdamW(params, lr=1e-7, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.005)
     times = []
     for it in range(warmup + steps):
         batch = make_batch(clips, frames=8, L=32, seed=seed + it)
@@ -113,8 +138,9 @@ def cpu_reference_run(steps, warmup, clips=2, seed=1000, regularisers=True):
         drop, dps = O.random_regularisers(cfg["depths"], clips, 0.3, 0.1, seed + it) if regularisers else (None, None)
         losses, _ = O.pretrain_forward(state, batch, cfg, drop=drop, drop_paths=dps)
         O.total_loss(losses).backward()
-        for v in state.values():
-            v.grad = None
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 15.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
@@ -125,18 +151,96 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload != "c3":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm times the c3 (pre-train) step only"}), flush=True)
+        return
     clips = 2
     value, ms, cores = cpu_reference_run(args.steps, args.warmup, clips, regularisers=not args.parity_config)
-    sample = f"{clips} clips/step of the c3 step (Swin-B + BERT-base + fusion, 8x224x224, L=32), fp32, fwd+bwd, no optimizer"
+    sample = (f"{clips} clips per step of the c3 step (Swin-B + BERT-base + fusion, 8x224x224, L=32), fp32, "
+              "fwd + bwd + grad-norm clip + torch.optim.AdamW; ONE process on all host cores whatever --gpus is")
+    # `config` names the WORKLOAD both arms are quoted on (c3, 64 clips per GPU); what this arm actually runs per step is a
+    # bounded sample of it -- stated in config.reference_sample and cpu_baseline.sample, never implied to be 64 clips
+    config = dict(workload_config(64, args.gpus, not args.parity_config),
+                  reference_sample={"clips_per_step": clips, "processes": 1, "optimizer_in_step": True, "dtype": "f32",
+                                    "note": "clips/s = clips_per_step / seconds per step of this sample"})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(64, args.gpus, not args.parity_config),
+        "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(dev, regularisers, steps=2, try_clips=(32, 16, 8, 4)):
+    """The like-for-like GPU baseline SURVEY.md 0 / 8(d) names: the reference's algorithm in plain PyTorch eager ON THIS B200
+    (the oracle restatement on cuda = ATen / cuBLAS / cuDNN library kernels, what the reference itself launches), the same c3
+    step (fwd + bwd + clip + torch.optim.AdamW(fused)), in fp32 and under torch.autocast(bfloat16).  Eager materialises every
+    attention score tensor, so 64 clips do not fit in 180 GB: the largest batch of `try_clips` that fits is used and stated.
+    Test-infrastructure code (oracle/) timed as a BASELINE -- never on the product path."""
+    import torch
+    from clover_b200.synthetic import make_batch, synth_state_dict
+    from oracle import clover_oracle as O
+    from oracle.state_shapes import pretrain_shapes
+    shapes = pretrain_shapes(SWIN_B["embed"], list(SWIN_B["depths"]), list(SWIN_B["heads"]), SWIN_B["img_in"], 768, 3072,
+                             30522, 512, 12, 3, 4)
+    cfg = dict(depths=list(SWIN_B["depths"]), num_heads=list(SWIN_B["heads"]), text_layers=12, fusion_layers=3, bert_heads=12,
+               vocab=30522)
+    out = {}
+    for mode in ("bf16_autocast", "fp32"):
+        res = None
+        for clips in try_clips:
+            state = opt = None
+            try:
+                torch.manual_seed(0)
+                state = {k: v.to(dev).requires_grad_(True) for k, v in synth_state_dict(shapes, 7).items()}
+                params = list(state.values())
+                opt = torch.optim.AdamW(params, lr=1e-7, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.005, fused=True)
+                batch = {k: v.to(dev) for k, v in make_batch(clips, frames=8, L=32, seed=1000).items()}
+
+                def one(it):
+                    drop = dps = None
+                    if regularisers:
+                        g = torch.Generator(device=dev).manual_seed(it)
+                        rates = torch.linspace(0, 0.3, sum(cfg["depths"])).tolist()
+                        drop = lambda kind, x: x * (torch.rand(x.shape, generator=g, device=dev) >= 0.1).to(x.dtype) / 0.9
+                        dps = lambda: [None if r == 0 else tuple((torch.rand(clips, generator=g, device=dev) < 1.0 - r).float() / (1.0 - r)
+                                                                  for _ in range(2)) for r in rates]
+                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                        losses, _ = O.pretrain_forward(state, batch, cfg, drop=drop, drop_paths=dps)
+                        loss = O.total_loss(losses)
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 15.0)
+                    opt.step()
+                    opt.zero_grad(set_to_none=True)
+                    return loss
+                one(0)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for it in range(steps):
+                    loss = one(1 + it)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                res = {"value": clips / ms * 1e3, "unit": UNIT, "clips_per_step": clips, "ms_per_step": ms, "loss": float(loss),
+                       "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+            except torch.OutOfMemoryError:
+                res = None
+            finally:
+                state = opt = None
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats()
+            if res is not None:
+                break
+        out[mode] = res
+    out["what"] = ("reference algorithm in PyTorch eager on the same B200 (oracle restatement on cuda: ATen/cuBLAS library kernels), "
+                   "c3 step fwd+bwd+clip+AdamW(fused), largest batch that fits; a baseline, not the product")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,29 +305,45 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     registry.register_all()
     torch.manual_seed(0)
-    model = registry.build_model(model_cfg(not args.parity_config)).to(dev)
+    wl = args.workload
+    W = WORKLOADS[wl]
+    METRIC = W["metric"]
+    model = registry.build_model(model_cfg(not args.parity_config, wl)).to(dev)
     model.train()
-    # parameters the reference never gives a gradient (text pooler, fusion's unused bert_embedding): keep DDP static
+    # parameters the reference never gives a gradient (text pooler, fusion's unused bert_embedding; the whole fusion encoder
+    # in the retrieval fine-tune): keep DDP static
     for n, p in model.named_parameters():
-        if ".pooler." in n or ".bert_embedding." in n:
+        if ".pooler." in n or ".bert_embedding." in n or (wl == "c4" and n.startswith("multimodal_backbone.")):
             p.requires_grad_(False)
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
                                                         gradient_as_bucket_view=True, bucket_cap_mb=100)
     from clover_b200.optim import FusedAdamW, param_groups_from_cfg
-    paramwise = dict(norm_decay_mult=0.0, bias_decay_mult=0.0, custom_keys={"absolute_pos_embed": dict(decay_mult=0.0),
-                                                                             "relative_position_bias_table": dict(decay_mult=0.0)})
-    opt = FusedAdamW(param_groups_from_cfg(model, 1e-7, 0.005, paramwise), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=15.0)
-    clips = args.clips
-    keys = ("imgs", "label", "token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")
-    host = {k: v.pin_memory() for k, v in make_batch(clips, frames=8, L=32, seed=1000 + rank).items()}
+    if wl == "c3":       # configs/exp_local/pretrain_webvid_cc3m.py:129-137
+        paramwise = dict(norm_decay_mult=0.0, bias_decay_mult=0.0, custom_keys={"absolute_pos_embed": dict(decay_mult=0.0),
+                                                                                 "relative_position_bias_table": dict(decay_mult=0.0)})
+    else:                # configs/exp_local/finetune_msrvttQA.py:90-97 / finetune_msrvtt_retrieval.py
+        paramwise = dict(norm_decay_mult=0.0, bias_decay_mult=0.0, custom_keys={"qa_head": dict(lr_mult=10)})
+    opt = FusedAdamW(param_groups_from_cfg(model, 1e-7, W["wd"], paramwise), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=W["grad_clip"])
+    clips = args.clips if args.clips > 0 else W["clips"]
+    if wl == "c3":
+        keys = ("imgs", "label", "token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")
+        raw = make_batch(clips, frames=8, L=32, seed=1000 + rank)
+    else:
+        from clover_b200.synthetic import make_finetune_batch
+        keys = ("imgs", "label", "token_ids", "segment_ids", "input_mask")
+        raw = make_finetune_batch(W["task"], clips, frames=16, size=224, L=40, seed=1000 + rank)
+    host = {k: v.pin_memory() for k, v in raw.items()}
     devb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+    last_losses = {}
 
     def step(batch):
         kw = {k: batch[k] for k in keys[2:]}
         losses = net(batch["imgs"], batch["label"], return_loss=True, **kw)
+        last_losses.clear()
+        last_losses.update({k: v.detach() for k, v in losses.items()})
         loss = sum(v for k, v in losses.items() if "loss" in k)
         loss.backward()
         opt.step()
@@ -265,6 +385,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t) / args.steps
     value = world * clips / (ms_step / 1e3)
+    # ---- multi-rank numerical check: the alignment losses are evaluated on the ALL-GATHERED embeddings, so every rank must
+    # hold the identical value (models/utils/gather_loss.py:47-62); the per-rank MLM / QA losses legitimately differ
+    consistency = None
+    if world > 1:
+        names = sorted(k for k in last_losses if k in ("nce_loss", "rank_t_tm_loss", "v_nce_loss", "rank_v_vm_loss", "retrieval_nce_loss"))
+        if names:
+            mine = torch.stack([last_losses[k].float().reshape(()) for k in names])
+            allv = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine)
+            allv = torch.stack(allv)
+            spread = float(((allv.max(0).values - allv.min(0).values) / allv.abs().max(0).values.clamp_min(1e-12)).max())
+            consistency = {"global_loss_entries": names, "max_relative_spread_over_ranks": spread}
+            assert spread <= 1e-5, f"alignment losses differ across ranks: {allv.tolist()}"
     # ---- timed region 2: end to end through the public API with host buffers ----------------------
     # Every step copies ITS inputs from pinned host memory (on a copy stream, one step ahead of the compute stream, like any
     # input pipeline) and reads ITS loss back to the host (asynchronous copy into pinned memory, consumed one step later, like
@@ -348,27 +481,44 @@ def run_ours(args):
                     "share_of_step": g[2] / (ms_step * prof_steps),
                     "launch_timing": "CUDA events around every launch of the first timed step",
                     "families_ms_per_step": {k: round(pre(k, 2) / prof_steps, 3) for k in sorted({n.split(" ")[0] for n in fam})},
+                    "hbm_bound_families": {k: {"ms_per_step": round(pre(k, 2) / prof_steps, 3),
+                                                "algorithmic_gbs": round(pre(k, 1) / max(1e-9, pre(k, 2)) / 1e6, 1),
+                                                "frac_of_measured_hbm": round(pre(k, 1) / max(1e-9, pre(k, 2)) / 1e6 / hbm, 3)}
+                                            for k in sorted({n.split(" ")[0] for n in fam}) if pre(k, 1) > 0 and pre(k, 0) == 0},
                     "untracked_ms_per_step": round(ms_step - fam_total, 3),
                     "window_attn_core_tflops": (pre("attn_fwd_hd32", 0) + pre("attn_bwd_hd32", 0)) /
                                                max(1e-9, (pre("attn_fwd_hd32", 2) + pre("attn_bwd_hd32", 2)) * 1e-3) / 1e12,
-                    "step_model_tflops": FLOP_PER_CLIP_FWD_BWD * clips / (ms_step * 1e-3) / 1e12}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+                    "step_model_tflops": W["flop"] * clips / (ms_step * 1e-3) / 1e12}
+        cpu = eager = None
+        max_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+        if world == 1 and wl == "c3":
+            c2 = window_attention_c2()
+            roofline["window_attn_c2_fwd_bwd"] = dict(c2, workload="c2: N=392 window (8,7,7), C=128, 4096 windows, qkv (1.6M x 384 bf16) > L2",
+                                                      frac_of_peak={k: round(v["tflops"] / sus, 4) for k, v in c2.items()})
+        if world == 1 and wl == "c3" and not args.no_cpu_baseline:
             v, ms, cores = cpu_reference_run(1, 1, 2, regularisers=not args.parity_config)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "2 clips of the same c3 step (fp32 oracle port, fwd+bwd), 1 warm-up + 1 timed step"}
-        c2 = window_attention_c2()
-        roofline["window_attn_c2_fwd_bwd"] = dict(c2, workload="c2: N=392 window (8,7,7), C=128, 4096 windows, qkv (1.6M x 384 bf16) > L2",
-                                                  frac_of_peak={k: round(v["tflops"] / sus, 4) for k, v in c2.items()})
+                   "sample": "2 clips of the same c3 step (fp32 oracle port, fwd+bwd+clip+AdamW), 1 warm-up + 1 timed step"}
+        if world == 1 and wl == "c3" and not args.no_eager_baseline:
+            del net, opt, devb
+            model.cpu()
+            from clover_b200 import functional as Fn
+            Fn.clear_weight_cache()
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+            eager = gpu_eager_baseline(dev, not args.parity_config)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": workload_config(clips, world, not args.parity_config),
+            "data": "synthetic", "config": workload_config(clips, world, not args.parity_config, wl),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "e2e_uint8_staging": {"value": e2e8_value, "unit": UNIT, "h2d_bytes_per_step": h2d8, "d2h_bytes_per_step": 4,
                                   "note": "raw uint8 clips + GPUNormalize folded into the patch gather (utils/module_hooks.py:35-87)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "loss": float(loss_host), "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "gpu_eager_baseline": eager, "rank_consistency": consistency,
+            "loss": float(loss_host), "max_mem_gb": max_mem,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -381,8 +531,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=64, help="clips per GPU (BASELINE config c3: 64)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config: c3 pre-train step (the headline, default), c4 retrieval fine-tune, c5 video-QA fine-tune")
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: 64 for c3, 16 for c4 / c5 = the shipped configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg (N = 1, c3)")
     ap.add_argument("--parity-config", action="store_true",
                     help="zero dropout / drop-path (the configuration of the parity tests) instead of the shipped training rates")
     args = ap.parse_args()

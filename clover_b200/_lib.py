@@ -125,7 +125,9 @@ SIGNATURES = {
     "clv_attention_w7_bwd_workspace_bytes": (c_ll, [C.POINTER(AttnW7Desc), C.c_int]),
     "clv_attention_w7_bwd": (C.c_int, [C.POINTER(AttnW7Desc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
     "clv_cast": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, c_vp]),
+    "clv_set_tunable": (C.c_int, [C.c_char_p, c_ll]),
     "clv_gelu": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, c_vp]),
+    "clv_tanh": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, c_vp]),
     "clv_patchify": (C.c_int, [c_vp, c_vp] + [C.c_int] * 8 + [c_vp]),
     "clv_patchify_u8": (C.c_int, [c_vp, c_vp, c_vp, c_vp] + [C.c_int] * 8 + [c_vp]),
     "clv_grouped_colsum": (C.c_int, [c_vp, C.c_int, c_ll, c_ll, C.c_int, C.c_int, C.c_int, C.c_float, c_vp, C.c_int, c_vp]),
@@ -133,7 +135,7 @@ SIGNATURES = {
     "clv_cosine_scores": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp]),
     "clv_retrieval_ranks": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "clv_adamw_step": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
-                                 C.c_float, C.c_int, c_vp, c_vp]),
+                                 C.c_float, C.c_int, c_vp, c_vp, c_vp]),
     "clv_scatter_add_rows": (C.c_int, [c_vp, c_vp, c_vp, c_ll, C.c_int, c_vp]),
     "clv_nce_workspace_floats": (c_ll, [C.c_int, C.c_int, C.c_int]),
     "clv_nce_rank_fwd": (C.c_int, [C.POINTER(c_vp), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,

@@ -61,6 +61,21 @@ def finetune_cfg(task="retrieval", embed=128, depths=(2, 2, 18, 2), heads=(4, 8,
         cfg.update(task="video_qa", separate_test=False, ssl_head=None, answer_cls=True,
                    qa_head=dict(type="QA_MC_head", hidden_dim=hidden, dropout_ratio=qa_dropout),
                    loss_type=dict(type="CrossEntropyLoss"))
+    elif task == "FIB":
+        # configs/exp_local/finetune_lsmdc_FIB.py:22-60: the fusion encoder keeps the class default use_text_cls=False (an
+        # all-cls token is appended to the video tokens), the answer is read at the [MASK] position, the ITM head is built
+        # but not on the path
+        mm = {k: v for k, v in base["mm_backbone"].items() if k not in ("use_text_cls", "use_prompt")}
+        cfg.update(task="FIB", separate_test=False, ssl_head=None, answer_mask=True, mm_backbone=mm,
+                   itm_head=dict(type="ITMHead", hidden_dim=hidden, dropout_ratio=0.5, finetune=True),
+                   qa_head=dict(type="QA_OE_Head", hidden_dim=hidden, dropout_ratio=qa_dropout, num_labels=num_labels),
+                   loss_type=dict(type="CrossEntropyLoss"))
+    elif task == "video_qa_itm":
+        # the answer_cls + itm_head + no qa_head branch of finetune.py:101-108,116-118 with use_text_cls=False: the all-cls
+        # state goes through the ITM head and logit 1 is the score (not used by a shipped config; covered for completeness)
+        mm = {k: v for k, v in base["mm_backbone"].items() if k not in ("use_text_cls", "use_prompt")}
+        cfg.update(task="video_qa", separate_test=False, ssl_head=None, answer_cls=True, mm_backbone=mm, qa_head=None,
+                   itm_head=dict(type="ITMHead", hidden_dim=hidden), loss_type=dict(type="CrossEntropyLoss"))
     else:
         raise ValueError(task)
     return cfg

@@ -629,7 +629,7 @@ static void fill_args(AttnArgs& a, const clv_attn_desc_t* d) {
 template <typename K>
 static int launch_attn(K kern, const AttnArgs& a, int nwarps, size_t smem, cudaStream_t stream, const char* what) {
   CLV_REQUIRE(smem <= 227 * 1024, "%s: needs %zu bytes of shared memory (seq too long)", what, smem);
-  CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem)) return rc;
   kern<<<a.batch * a.heads, nwarps * 32, smem, stream>>>(a);
   return after_launch(what);
 }

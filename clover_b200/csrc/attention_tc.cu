@@ -302,11 +302,7 @@ extern "C" int clv_attention_fwd_tc(const clv_attn_desc_t* d, const void* qkv, v
   if (int rc = make_tmap_bf16_2d(&tkv, qkv, ld, rows, ld, TC_HD, a.kv_box_rows, 64)) return rc;
   const size_t smem = 1024 + 2 * (size_t)(8192 + 2 * a.kb_bytes) + (size_t)((a.table_len + 3) & ~3) * 4 + (size_t)a.nk * 8 + 8 + 128;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_fwd_tc: %zu bytes of shared memory needed", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel), (int)smem)) return rc;
   const int per_sm = (a.tmem_cols == 256 && smem <= 110 * 1024) ? 2 : 1;
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms() * per_sm);
   attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(tq, tkv, a);
@@ -695,11 +691,7 @@ extern "C" int clv_attention_bwd_tc(const clv_attn_desc_t* d, const void* qkv, c
   const size_t smem = 1024 + 4 * (size_t)a.qb_bytes + 4 * 8192 + (size_t)a.n_mq * 2 * 16384 + (size_t)((a.table_len + 3) & ~3) * 4 +
                       (size_t)a.nq * 16 + 8 + 14 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_bwd_tc: %zu bytes of shared memory needed", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_bwd_tc_kernel), (int)smem)) return rc;
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
   attn_bwd_tc_kernel<<<grid, TC_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, a);
   if (int rc = after_launch("attn_bwd_tc_kernel")) return rc;

@@ -1316,11 +1316,7 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
   const size_t stage = 8192 + 2 * (size_t)a.kb_bytes + (a.has_ext ? 4096 + (size_t)a.kx_bytes : 0);
   const size_t smem = 1024 + 2 * stage + (size_t)a.table_ld * 4 + 9 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_fwd: %zu bytes of shared memory needed", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(attn_w7_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_w7_fwd_kernel), (int)smem)) return rc;
   const int per_sm = (a.tmem_cols == 256 && smem <= 113 * 1024) ? 2 : 1;
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms() * per_sm);
   attn_w7_fwd_kernel<<<grid, W7_FWD_THREADS, smem, stream>>>(tq, tkv0, tkv1, tqx, tkx0, tkx1, a);
@@ -1378,11 +1374,7 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   }
   a.code_off = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;
   a.has_kx = d->k_ext != nullptr; a.nwin = d->nwin > 0 ? d->nwin : 1;
-  {
-    static int pipe = -1;
-    if (pipe < 0) { const char* e = getenv("CLOVER_B200_W7_PIPE"); pipe = e ? atoi(e) : 1; }
-    a.pipe = pipe;
-  }
+  a.pipe = (int)tunable(TUNE_W7_PIPE, 1);
   const long long rows = (long long)d->batch * a.seq;
   const long long t_bytes = w7_table_bytes(d);
   __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + t_bytes);
@@ -1408,18 +1400,15 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   tkx = te; tds = te;
   // bias-table gradient: either dump every unit's dS^T (batch * heads * seq * nq bf16, read back by attn_w7_dbias_kernel) or,
   // for the chunk-ring kernels, let TMA ADD the tiles into per-CTA buffers that stay in L2 (dump_ds == 2)
-  static int gen2 = -1;
-  if (gen2 < 0) { const char* ev = getenv("CLOVER_B200_W7_BWD2"); gen2 = ev ? atoi(ev) : 1; }
+  const int gen2 = (int)tunable(TUNE_W7_BWD2, 1);
   const bool ring = halves || (a.seq == 196 && gen2);
   const int nh = halves ? 2 : 1;
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
   long long nbuf = 0;
   if (ds_out && ring) {
     // acc_mode: 0 never, 1 when the dump would be large (it then costs more HBM traffic than the L2 adds), 2 always
-    static int acc_mode = -1;
-    if (acc_mode < 0) { const char* ev = getenv("CLOVER_B200_W7_DBIAS_ACC"); acc_mode = ev ? atoi(ev) : 1; }
-    static long long acc_min_bytes = -1;
-    if (acc_min_bytes < 0) { const char* ev = getenv("CLOVER_B200_W7_DBIAS_ACC_MIN_MB"); acc_min_bytes = (ev ? atoll(ev) : 128) << 20; }
+    const int acc_mode = (int)tunable(TUNE_W7_DBIAS_ACC, 1);
+    const long long acc_min_bytes = tunable(TUNE_W7_DBIAS_ACC_MIN_MB, 128) << 20;
     int spans = 1;
     const long long base = a.units / grid, rem = a.units % grid;
     for (int c = 0; c < grid; ++c) {
@@ -1446,12 +1435,7 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_bwd: %zu bytes of shared memory needed", smem);
   auto kern = halves ? attn_w7_bwd2_kernel<392>
                      : (a.seq == 196 ? (gen2 ? attn_w7_bwd2_kernel<196> : attn_w7_bwd_kernel<196>) : attn_w7_bwd_kernel<98>);
-  const int ki = halves ? 2 : (a.seq == 196 ? 1 : 0);
-  static size_t smem_set[3] = {0, 0, 0};
-  if (smem > smem_set[ki]) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[ki] = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem)) return rc;
   kern<<<grid, W7_BWD_THREADS, smem, stream>>>(tfull, ttile, tdo, te, tkx, tds, a);
   if (int rc = after_launch("attn_w7_bwd_kernel")) return rc;
   if (halves) {

@@ -34,6 +34,7 @@ __global__ void cast_kernel(const void* src, int src_bf16, void* dst, int dst_bf
 }
 
 // y = GELU(x)  (mode 0)   or   y = dy * GELU'(x)  (mode 1); exact erf form (nn.GELU default)
+// y = tanh(x)  (mode 2)   or   y = dy * (1 - x^2) with x = the saved tanh OUTPUT  (mode 3)   (nn.Tanh of ITMHead)
 __global__ void gelu_kernel(const void* x, int x_bf16, const void* dy, int dy_bf16, void* y, int y_bf16, long long n4, int mode) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -41,9 +42,14 @@ __global__ void gelu_kernel(const void* x, int x_bf16, const void* dy, int dy_bf
     float4 o;
     if (mode == 0) {
       o = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
-    } else {
+    } else if (mode == 1) {
       const float4 d = ldv4(dy, dy_bf16, i * 4);
       o = make_float4(d.x * gelu_erf_grad(v.x), d.y * gelu_erf_grad(v.y), d.z * gelu_erf_grad(v.z), d.w * gelu_erf_grad(v.w));
+    } else if (mode == 2) {
+      o = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+    } else {
+      const float4 d = ldv4(dy, dy_bf16, i * 4);
+      o = make_float4(d.x * (1.f - v.x * v.x), d.y * (1.f - v.y * v.y), d.z * (1.f - v.z * v.z), d.w * (1.f - v.w * v.w));
     }
     stv4(y, y_bf16, i * 4, o);
   }
@@ -243,6 +249,15 @@ extern "C" int clv_gelu(const void* x, int x_is_bf16, const void* dy, int dy_is_
   return after_launch("gelu_kernel");
 }
 
+extern "C" int clv_tanh(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, void* y, int y_is_bf16, long long n,
+                        void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CLV_REQUIRE(x && y && n >= 0 && n % 4 == 0, "clv_tanh: n must be a multiple of 4 (got %lld)", n);
+  if (n == 0) return 0;
+  gelu_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(x, x_is_bf16, dy, dy_is_bf16, y, y_is_bf16, n / 4, dy ? 3 : 2);
+  return after_launch("gelu_kernel(tanh)");
+}
+
 extern "C" int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int F, int H, int W, int pd, int ph, int pw,
                             void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -250,11 +265,7 @@ extern "C" int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int 
   const int D = (F + pd - 1) / pd, Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
   const size_t smem = (size_t)Cin * pd * ph * (Wp * pw + 1) * sizeof(float);
   CLV_REQUIRE(smem <= 200 * 1024, "clv_patchify: row tile too large (%zu bytes)", smem);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(patchify_kernel<float>), (int)smem)) return rc;
   patchify_kernel<float><<<B * D * Hp, 256, smem, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, F, H, W, pd,
                                                            ph, pw, D, Hp, Wp, nullptr, nullptr);
   return after_launch("patchify_kernel");
@@ -267,11 +278,7 @@ extern "C" int clv_patchify_u8(const unsigned char* x, const float* mean, const 
   const int D = (F + pd - 1) / pd, Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
   const size_t smem = (size_t)Cin * pd * ph * (Wp * pw + 1) * sizeof(float);
   CLV_REQUIRE(smem <= 200 * 1024, "clv_patchify_u8: row tile too large (%zu bytes)", smem);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(patchify_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(patchify_kernel<unsigned char>), (int)smem)) return rc;
   patchify_kernel<unsigned char><<<B * D * Hp, 256, smem, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, F, H, W,
                                                                    pd, ph, pw, D, Hp, Wp, mean, inv_std);
   return after_launch("patchify_kernel<u8>");

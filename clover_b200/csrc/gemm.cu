@@ -11,9 +11,10 @@
 // (fp32 or bf16), window-reverse row scatter (window_reverse + roll back, :471-474), bf16 or fp32
 // output, and split-K with fp32 atomic accumulation for weight gradients.
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-9 =
-// epilogue (TMEM -> registers -> 256-bit global stores; bias staged in shared memory).  Two TMEM
-// accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+// Roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-17 = epilogue (four column
+// quarters x four TMEM lane quarters: TMEM -> registers -> 256-bit global stores; bias staged in shared memory), warps
+// 18-19 = row sums of the MN-major A tiles (bias gradients; busy only in the RS instantiations).  Two TMEM accumulator
+// stages let the epilogue of tile i overlap the mainloop of tile i+1.
 // Tiles 128x256x64 (4 smem stages) when N is a multiple of 256 and the grid still fills, else 128x128x64 (6 stages).
 #include <algorithm>
 #include <cstdlib>
@@ -450,13 +451,9 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long l
 template <int A_MN, int B_MN, int BN, bool RS = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int k_splits,
                        const GemmEpi& ep, cudaStream_t stream) {
-  static bool attr_set = false;
   auto kern = gemm_bf16_kernel<A_MN, B_MN, BN, RS>;
   constexpr int SMEM = GemmCfg<BN, RS>::SMEM;
-  if (!attr_set) {
-    CLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), SMEM)) return rc;
   const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
   const int grid = (int)std::min<long long>(tiles, num_sms());
   kern<<<grid, GEMM_THREADS, SMEM, stream>>>(ta, tb, M, N, K, k_splits, ep);
@@ -492,8 +489,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   CLV_REQUIRE(N % 8 == 0, "clv_gemm_bf16: N must be a multiple of 8 (got %d)", N);
   // 128x256 tiles when N fills them (less smem traffic per MAC); 128x128 otherwise
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
-  static long long min_units256 = -1;     // experiment knob: CLOVER_B200_GEMM_BN256_MIN_UNITS overrides the 2-waves rule
-  if (min_units256 < 0) { const char* ev = getenv("CLOVER_B200_GEMM_BN256_MIN_UNITS"); min_units256 = ev ? atoll(ev) : 2LL * num_sms(); }
+  const long long min_units256 = tunable(TUNE_GEMM_BN256_MIN_UNITS, 2LL * num_sms());   // the 2-waves rule
   // weight gradients (split-K, K blocks per tile in the hundreds) are L2-bound: always take the wide tile there
   const bool long_k = (e->k_splits > 1 || e->accumulate) && K / (e->k_splits > 0 ? e->k_splits : 1) >= 4096;
   const bool bn256 = (N % 256 == 0) && (tiles256 * (e->k_splits > 0 ? e->k_splits : 1) >= min_units256 || long_k);

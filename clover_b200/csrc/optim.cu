@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const AdamTensor* __re
   }
 }
 
-struct AdamHyper { float b1, b2, eps, inv_bc1, inv_sqrt_bc2, grad_scale, max_norm; };
+struct AdamHyper { float b1, b2, eps, inv_bc1, inv_sqrt_bc2, grad_scale, max_norm; const float* step_dev; };
 
 CLV_DEVICE void adam_elem(float& p, float g, float& m, float& v, float coef, float lr, float decay, const AdamHyper& h) {
   g *= coef;
@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
                                                     const long long* __restrict__ chunk_off, int chunk, AdamHyper h,
                                                     const float* __restrict__ sqnorm, float* status) {
   float coef = h.grad_scale;
+  if (h.step_dev) {                              // device-resident step counter: this is update number *step_dev + 1
+    const float t1 = *h.step_dev + 1.f;
+    h.inv_bc1 = 1.f / (1.f - powf(h.b1, t1));
+    h.inv_sqrt_bc2 = rsqrtf(1.f - powf(h.b2, t1));
+  }
   if (sqnorm) {
     const float nrm = sqrtf(*sqnorm) * fabsf(h.grad_scale);
     if (!isfinite(nrm)) {                        // overflow: skip the step (reference: Fp16OptimizerHook skips + shrinks the scale)
@@ -100,6 +105,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
   }
 }
 
+// the step counter advances only when the update was applied (a skipped overflow step must not age the bias correction)
+__global__ void adam_step_advance_kernel(float* step_dev, const float* status, int check) {
+  if (!check || status[1] == 0.f) *step_dev += 1.f;
+}
+
 }  // namespace clv
 
 using namespace clv;
@@ -108,11 +118,11 @@ static_assert(sizeof(clv_adamw_tensor_t) == sizeof(AdamTensor), "clv_adamw_tenso
 
 extern "C" int clv_adamw_step(const clv_adamw_tensor_t* tensors_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
                               int n_chunks, int chunk_elems, float beta1, float beta2, float eps, int step, float grad_scale,
-                              float max_grad_norm, int check_finite, float* status_dev, void* stream_) {
+                              float max_grad_norm, int check_finite, float* status_dev, float* step_dev, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CLV_REQUIRE(tensors_dev && chunk_tensor_dev && chunk_offset_dev && n_chunks >= 0 && chunk_elems > 0 && chunk_elems % 4 == 0,
               "clv_adamw_step: bad arguments");
-  CLV_REQUIRE(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "clv_adamw_step: bad hyper-parameters");
+  CLV_REQUIRE((step >= 1 || step_dev) && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "clv_adamw_step: bad hyper-parameters");
   const bool need_norm = max_grad_norm > 0.f || check_finite;
   CLV_REQUIRE(!need_norm || status_dev, "clv_adamw_step: status_dev (fp32[3]) is required for clipping / the finite check");
   if (n_chunks == 0) return 0;
@@ -126,9 +136,15 @@ extern "C" int clv_adamw_step(const clv_adamw_tensor_t* tensors_dev, const int* 
   }
   AdamHyper h;
   h.b1 = beta1; h.b2 = beta2; h.eps = eps;
-  h.inv_bc1 = (float)(1.0 / (1.0 - pow((double)beta1, step)));
-  h.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, step)));
-  h.grad_scale = grad_scale; h.max_norm = max_grad_norm;
+  const int host_step = step >= 1 ? step : 1;
+  h.inv_bc1 = (float)(1.0 / (1.0 - pow((double)beta1, host_step)));
+  h.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, host_step)));
+  h.grad_scale = grad_scale; h.max_norm = max_grad_norm; h.step_dev = step_dev;
   adamw_kernel<<<n_chunks, 256, 0, stream>>>(ts, chunk_tensor_dev, chunk_offset_dev, chunk_elems, h, sq, status_dev);
-  return after_launch("adamw_kernel");
+  if (int rc = after_launch("adamw_kernel")) return rc;
+  if (step_dev) {
+    adam_step_advance_kernel<<<1, 1, 0, stream>>>(step_dev, status_dev, need_norm ? 1 : 0);
+    return after_launch("adam_step_advance_kernel");
+  }
+  return 0;
 }

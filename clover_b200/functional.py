@@ -234,6 +234,25 @@ def gelu(x):
     return GeluFn.apply(x)
 
 
+class TanhFn(torch.autograd.Function):
+    """nn.Tanh (ITMHead.itm_projector, heads/mlm_itm_head.py:67-70); the output is saved for backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = ops.tanh(x.contiguous(), torch.empty_like(x))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ops.tanh(y, torch.empty_like(y), dy=dy.contiguous())
+
+
+def tanh(x):
+    return TanhFn.apply(x)
+
+
 class DropoutFn(torch.autograd.Function):
     """y = residual + dropout_p(x) (nn.Dropout semantics: kept elements scaled by 1 / (1 - p)); the mask is a range of
     the counter-based stream (clover_b200.rng) and is regenerated in backward.  HF BertSelfOutput / BertOutput apply
@@ -554,6 +573,15 @@ class PatchEmbedFn(torch.autograd.Function):
         stats = torch.empty(2 * T, dtype=F32, device=imgs.device)
         blend = None
         if mask is not None:
+            # the blend kernel reads the mask as int64 on the device: validate / convert here (the reference accepts any
+            # dtype through .type_as(mask_tokens), swin_transformer_3d.py:227)
+            if mask.numel() % B or mask.dim() < 2 or mask.numel() != B * mask.shape[-2] * mask.shape[-1]:
+                raise ValueError(f"v_token_mask of shape {tuple(mask.shape)} does not match the batch of {B} clips")
+            if mask.is_floating_point() or mask.dtype in (torch.bool, torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+                mask = (mask != 0) if mask.is_floating_point() else mask
+            else:
+                raise TypeError(f"v_token_mask: unsupported dtype {mask.dtype}")
+            mask = mask.to(device=imgs.device, dtype=torch.int64)
             blend = (mask.reshape(B, mask.shape[-2], mask.shape[-1]).contiguous(), token.detach().reshape(-1).contiguous(),
                      (D, Hp, Wp))
         ops.layernorm_fwd(y, nw, nb, 1e-5, out, mean=stats[:T], rstd=stats[T:], blend=blend)
@@ -686,13 +714,16 @@ class BertEmbedFn(torch.autograd.Function):
 
 
 class FusionInputFn(torch.autograd.Function):
-    """cross_transformer.py:84-108: z = cat(LN(v + space + tempor + type0), t + type1) written
-    directly into one bf16 [B, T*S + L, H] buffer.  v bf16 [B*T*S, H] (fc_in output), t bf16 [B*L, H]."""
+    """cross_transformer.py:84-108: z = cat(LN(v + space + tempor + type0), [prompt tokens,] [all_cls token,] t + type1)
+    written directly into one bf16 [B, T*S + E + L, H] buffer.  v bf16 [B*T*S, H] (fc_in output), t bf16 [B*L, H],
+    extra: fp32 [E, H] learned tokens appended to the video tokens of every sample (use_text_cls=False / use_prompt,
+    :99-104; they get neither a position nor a type embedding nor the LayerNorm) or None."""
 
     @staticmethod
-    def forward(ctx, v, t, space, tempor, type_emb, gamma, beta, B, T, S, L):
+    def forward(ctx, v, t, space, tempor, type_emb, gamma, beta, extra, B, T, S, L):
         Hd = v.shape[1]
-        tot = T * S + L
+        E = 0 if extra is None else extra.shape[0]
+        tot = T * S + E + L
         z = torch.empty(B * tot, Hd, dtype=BF16, device=v.device)
         stats = torch.empty(2 * B * T * S, dtype=F32, device=v.device)
         ty = type_emb.detach()
@@ -700,17 +731,19 @@ class FusionInputFn(torch.autograd.Function):
         tp = tempor.detach().reshape(-1, Hd)[:T].contiguous()
         ops.layernorm_fwd(v, gamma, beta, 1e-5, z, rows=B * T * S, mean=stats[:B * T * S], rstd=stats[B * T * S:],
                           add0=ty[0].contiguous(), add1=(sp, 1, S), add2=(tp, S, T), group=(T * S, tot, 0))
-        ops.rows_affine(z, B * L, Hd, x=t, out_group=(L, tot, T * S), add0=ty[1].contiguous())
+        if E:
+            ops.rows_affine(z, B * E, Hd, x=extra.detach().contiguous(), in_group=(E, 0, 0), out_group=(E, tot, T * S))
+        ops.rows_affine(z, B * L, Hd, x=t, out_group=(L, tot, T * S + E), add0=ty[1].contiguous())
         ctx.save_for_backward(v, space, tempor, type_emb, gamma, beta, stats, sp, tp)
-        ctx.meta = (B, T, S, L)
+        ctx.meta = (B, T, S, L, E)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         v, space, tempor, type_emb, gamma, beta, stats, sp, tp = ctx.saved_tensors
-        B, T, S, L = ctx.meta
+        B, T, S, L, E = ctx.meta
         Hd = v.shape[1]
-        tot = T * S + L
+        tot = T * S + E + L
         rows = B * T * S
         dev = v.device
         dz = dz.contiguous()
@@ -722,7 +755,13 @@ class FusionInputFn(torch.autograd.Function):
                           dgamma=small[:Hd], dbeta=small[Hd:], add0=ty[0].contiguous(), add1=(sp, 1, S), add2=(tp, S, T),
                           group=(T * S, tot, 0))
         dt = torch.empty(B * L, Hd, dtype=BF16, device=dev)
-        ops.rows_affine(dt, B * L, Hd, x=dz, in_group=(L, tot, T * S))
+        ops.rows_affine(dt, B * L, Hd, x=dz, in_group=(L, tot, T * S + E))
+        dextra = None
+        if E:
+            de = torch.empty(B * E, Hd, dtype=F32, device=dev)
+            ops.rows_affine(de, B * E, Hd, x=dz, in_group=(E, tot, T * S))
+            dextra = torch.zeros(E, Hd, dtype=F32, device=dev)
+            ops.grouped_colsum(de, dextra, div=1, mod=E)
         dspace = torch.zeros_like(space)
         ops.grouped_colsum(dv32, dspace.view(-1, Hd)[:S], div=1, mod=S)
         dtempor = torch.zeros_like(tempor)
@@ -730,7 +769,7 @@ class FusionInputFn(torch.autograd.Function):
         dtype_emb = torch.zeros_like(type_emb)
         ops.grouped_colsum(dv32, dtype_emb[:1])
         ops.grouped_colsum(dt, dtype_emb[1:2])
-        return dv16, dt, dspace, dtempor, dtype_emb, small[:Hd], small[Hd:], None, None, None, None
+        return dv16, dt, dspace, dtempor, dtype_emb, small[:Hd], small[Hd:], dextra, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

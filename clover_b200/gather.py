@@ -92,3 +92,47 @@ def gather_stacked(tensors):
     if ws == 1:
         return [t.float() for t in tensors]
     return list(_StackedGather.apply(rank, ws, *tensors))
+
+
+class _StackedVariedGather(torch.autograd.Function):
+    """Several (B_r, D) embeddings whose batch B_r may differ per rank (the last, ragged batch of an epoch): ONE size
+    exchange (a single host read of W integers) and ONE padded stacked all-gather instead of the reference's size exchange
+    + padded gather per tensor (gather_loss.py:47-58, called 4x per loss).  Backward keeps the local slice."""
+
+    @staticmethod
+    def forward(ctx, rank, ws, *tensors):
+        B = tensors[0].shape[0]
+        dev = tensors[0].device
+        local = torch.tensor([B], device=dev, dtype=torch.int64)
+        sizes = torch.empty(ws, device=dev, dtype=torch.int64)
+        if local.is_cuda:
+            dist.all_gather_into_tensor(sizes, local)
+        else:
+            dist.all_gather(list(sizes.split(1)), local)
+        sizes = sizes.tolist()
+        mx = max(sizes)
+        stack = torch.stack([t.float() for t in tensors], 0)                       # (n, B, D)
+        if mx != B:
+            stack = torch.cat([stack, stack.new_zeros(stack.shape[0], mx - B, stack.shape[2])], 1)
+        stack = stack.contiguous()
+        out = torch.empty((ws,) + tuple(stack.shape), dtype=stack.dtype, device=dev)
+        if stack.is_cuda:
+            dist.all_gather_into_tensor(out.view(ws * stack.shape[0], mx, -1), stack)
+        else:
+            dist.all_gather(list(out.unbind(0)), stack)
+        start = sum(sizes[:rank])
+        ctx.bounds = (start, start + sizes[rank])
+        return tuple(torch.cat([out[r, i, :n] for r, n in enumerate(sizes)], 0) for i in range(len(tensors)))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        a, b = ctx.bounds
+        return (None, None) + tuple(g[a:b] for g in grads)
+
+
+def gather_stacked_varied(tensors):
+    """gather_stacked for batches that may be ragged across ranks (VariedShapeGatherLoss semantics)."""
+    rank, ws = _world()
+    if ws == 1:
+        return [t.float() for t in tensors]
+    return list(_StackedVariedGather.apply(rank, ws, *tensors))

@@ -191,11 +191,8 @@ class MLMHead(nn.Module):
         x = self.transform(sequence_output.reshape(-1, shp[-1]))
         d = self.predictions.decoder
         V = d.weight.shape[0]
-        if V % 8:
-            raise NotImplementedError("MLMHead.forward: vocab size must be a multiple of 8 for dense logits; "
-                                      "use focal_loss() (fused decoder + loss) instead")
-        y = Fn.linear(x, d.weight, d.bias, out_fp32=True)
-        return y.view(*shp[:-1], V)
+        y = _linear_any_n(x, d)                      # the shipped vocabulary (30522) is not a multiple of 8: padded weight cache
+        return y.reshape(*shp[:-1], V)
 
     def focal_loss(self, sequence_output, mlm_label, gamma=2.0, ignore_index=-100):
         """decoder + row selection (pretrain.py:137-139) + SoftmaxFocalLossMultiClass in one pass."""
@@ -203,6 +200,27 @@ class MLMHead(nn.Module):
         x = self.transform(sequence_output.reshape(-1, shp[-1]))
         d = self.predictions.decoder
         return Fn.VocabFocalFn.apply(x, d.weight, d.bias, mlm_label.reshape(-1), gamma, ignore_index)
+
+
+class ITMHead(nn.Module):
+    """reference mlm_itm_head.py:55-97: Dropout(0.1) -> Linear(hidden, hidden) -> Tanh -> Linear(hidden, 2)
+    (the dropout rate is hard-coded; ``dropout_ratio`` / ``finetune`` of the shipped config are swallowed by **kwargs)."""
+
+    def __init__(self, hidden_dim=768, **kwargs):
+        super().__init__()
+        self.itm_projector = nn.Sequential(nn.Dropout(p=0.1), nn.Linear(hidden_dim, hidden_dim), nn.Tanh(),
+                                           nn.Linear(hidden_dim, 2))
+        self.fp16_enabled = False
+        _xavier_init(self)
+
+    def init_weights(self):
+        _xavier_init(self)
+
+    def forward(self, cls_feature):
+        c = self.itm_projector
+        x = _head_dropout(self, Fn.to_dtype(cls_feature.contiguous(), BF16), c[0].p, "head_itm")
+        x = Fn.tanh(Fn.linear(x, c[1].weight, c[1].bias))
+        return _linear_any_n(x, c[3])
 
 
 class QA_OE_Head(nn.Module):

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
-from .gather import GatherLoss, VariedShapeGatherLoss, _world
+from .gather import GatherLoss, VariedShapeGatherLoss, _world, gather_stacked, gather_stacked_varied
 
 
 class NormSoftmaxLoss(nn.Module):
@@ -22,8 +22,7 @@ class NormSoftmaxLoss(nn.Module):
         if sim_mat is not None:
             raise NotImplementedError("clover_b200: NormSoftmaxLoss(sim_mat=...) is not supported")
         self.rank, self.world_size = _world()
-        v = self.allgather(video_embd.float(), self.rank, self.world_size)
-        t = self.allgather(text_embd.float(), self.rank, self.world_size)
+        v, t = gather_stacked([video_embd, text_embd])          # one collective (GatherLoss semantics: equal batch per rank)
         return self.forward_gathered(v, t)
 
     def forward_gathered(self, v, t):
@@ -51,8 +50,8 @@ class ExclusiveNCEwithRankingLoss(nn.Module):
             raise NotImplementedError("clover_b200: ExclusiveNCEwithRankingLoss needs all four embeddings "
                                       "(use_Cmask=True, as in the shipped pre-train config)")
         self.rank, self.world_size = _world()
-        g = [self.allgather(e.float(), self.rank, self.world_size)
-             for e in (video_embd, text_embd, text_mask_embd, text_recon_embd)]
+        # one size exchange + one stacked collective for the four embeddings (ragged batches allowed, :111-114)
+        g = gather_stacked_varied([video_embd, text_embd, text_mask_embd, text_recon_embd])
         return self.forward_gathered(*g)
 
     def forward_gathered(self, v, t, tm, tr):

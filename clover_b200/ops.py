@@ -48,11 +48,17 @@ def _rowmajor2d(t, name):
 # optional per-launch CUDA-event timing (bench.py's roofline leg); off by default
 # ------------------------------------------------------------------------------------------------
 _PROF = None
-PROFILE_SHAPES = os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1"
-# head_dim-32 window attention runs on the tcgen05 kernel; the mma.sync kernel serves head_dim 64 (BERT / fusion)
-USE_TC_ATTENTION = os.environ.get("CLOVER_B200_TC_ATTENTION", "1") != "0"
-# (., 7, 7) windows with tokens in (d, h, w) order run on the specialised kernels of attention_w7.cu
-USE_W7_ATTENTION = os.environ.get("CLOVER_B200_W7_ATTENTION", "1") != "0"
+PROFILE_SHAPES = os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1"       # bench / tools: family names carry the shapes
+# Kernel selection is fixed (no environment switches): (., 7, 7) windows with tokens in (d, h, w) order run on the
+# specialised kernels of attention_w7.cu, other head_dim-32 windows on the generic tcgen05 kernel of attention_tc.cu.
+# Tests flip these module attributes to compare the kernels against each other.
+USE_TC_ATTENTION = True
+USE_W7_ATTENTION = True
+
+
+def set_tunable(name, value):
+    """Experiment knobs of the library for tools / tests (clv_set_tunable); -1 restores the default."""
+    _lib.check(_lib.load().clv_set_tunable(name.encode(), int(value)), "clv_set_tunable")
 
 
 def profile_begin():
@@ -93,7 +99,14 @@ def _prof_close(e0, family, flops, nbytes):
         _PROF.append((family, flops, nbytes, e0, e1))
 
 
-def _profiled(family, tag=None):
+def _tb(*ts):
+    """bytes of the given tensors (None entries skipped)"""
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+def _profiled(family, tag=None, nbytes=None):
+    """nbytes(*args, **kwargs) -> ALGORITHMIC bytes of the launch (inputs read once + outputs written once): the numerator of
+    the HBM roofline fraction bench.py reports for the memory-bound families."""
     def deco(fn):
         def wrapped(*a, **k):
             if _PROF is None:
@@ -103,7 +116,7 @@ def _profiled(family, tag=None):
             name = family
             if PROFILE_SHAPES and tag is not None:
                 name = family + " " + tag(*a, **k)
-            _prof_close(e0, name, 0.0, 0.0)
+            _prof_close(e0, name, 0.0, nbytes(*a, **k) if nbytes is not None else 0.0)
             return out
         wrapped.__name__ = fn.__name__
         wrapped.__doc__ = fn.__doc__
@@ -247,7 +260,18 @@ def _ln_tag(x, gamma, *a, **k):
     return f"generic rows={k.get('rows') or x.shape[0]} C={gamma.numel()} x={str(x.dtype)[-4:]} {'+'.join(kinds)}"
 
 
-@_profiled("ln_fwd", _ln_tag)
+def _ln_fwd_bytes(x, gamma, beta, eps, y, *, rows=None, **kw):
+    r = y.shape[0] if rows is None else rows
+    return float(r * gamma.numel() * (x.element_size() + y.element_size()))
+
+
+def _ln_bwd_bytes(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=None, dx_copy=None, **kw):
+    n = rows * gamma.numel()
+    return float(n * (x.element_size() + dy.element_size() + (4 if dx is not None else 0) + (4 if dres is not None else 0)
+                      + (dx_copy.element_size() if dx_copy is not None else 0)))
+
+
+@_profiled("ln_fwd", _ln_tag, _ln_fwd_bytes)
 def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **kw):
     """y = LN(gather(x) + adds) (* blend).  x: [..., C] fp32/bf16 2-D; y: 2-D bf16/fp32."""
     _need_cuda(x, gamma, beta, y)
@@ -258,7 +282,7 @@ def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **
     return y
 
 
-@_profiled("ln_bwd", _ln_tag)
+@_profiled("ln_bwd", _ln_tag, _ln_bwd_bytes)
 def layernorm_bwd(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=None, dx_copy=None, copy_window=None,
                   dgamma=None, dbeta=None, dtoken=None, dx_dense=False, **kw):
     _need_cuda(x, gamma, dy)
@@ -305,7 +329,7 @@ def _lnr_tag(x, gamma, *a, **k):
     return f"rows={x.shape[0]} C={x.shape[1]} x={str(x.dtype)[-4:]} {'+'.join(kinds)}"
 
 
-@_profiled("ln_fwd", _lnr_tag)
+@_profiled("ln_fwd", _lnr_tag, lambda x, gamma, beta, eps, y, **k: _tb(x, y))
 def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_mapped=False):
     """y[m(s)] = LN(x[s]) on dense rows (clv_lnr_fwd); m = identity unless y_mapped."""
     _need_cuda(x, gamma, beta, y)
@@ -316,7 +340,8 @@ def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_map
     return y
 
 
-@_profiled("ln_bwd", _lnr_tag)
+@_profiled("ln_bwd", _lnr_tag, lambda x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, **k:
+           _tb(x, dy, dx, dres if dres is not dx else None, dx_bf16))
 def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, row_map=None, dy_mapped=False,
             dx_bf16_mapped=False, dgamma=None, dbeta=None, dxsum=None, copy_scale=None, copy_scale_rows=0):
     _need_cuda(x, gamma, dy)
@@ -439,7 +464,7 @@ def attention_probs_mean(qkv, batch, seq, heads, hd, **bias):
 
 
 # ------------------------------------------------------------------------------------------------
-@_profiled("dropout")
+@_profiled("dropout", None, lambda x, y, p, seed, offset, residual=None: _tb(x, y, residual))
 def dropout(x, y, p, seed, offset, residual=None):
     """y = residual + x * keep / (1 - p) with keep drawn from stream (seed, offset + i); see clv_dropout."""
     _need_cuda(x, y, residual)
@@ -460,7 +485,7 @@ def keep_mask(n, p, seed, offset, device):
     return out
 
 
-@_profiled("rows_scale")
+@_profiled("rows_scale", None, lambda x, y, scale, rows_per_group: _tb(x, y))
 def rows_scale(x, y, scale, rows_per_group):
     """y[r, :] = x[r, :] * scale[r // rows_per_group]  (DropPath factor on a gradient)."""
     _need_cuda(x, y, scale)
@@ -474,7 +499,8 @@ def rows_scale(x, y, scale, rows_per_group):
 
 
 # ------------------------------------------------------------------------------------------------
-@_profiled("cast", lambda src, dst, *a, **k: f"n={src.numel()} {str(src.dtype)[-4:]}->{str(dst.dtype)[-4:]}")
+@_profiled("cast", lambda src, dst, *a, **k: f"n={src.numel()} {str(src.dtype)[-4:]}->{str(dst.dtype)[-4:]}",
+           lambda src, dst, *a, **k: _tb(src, dst))
 def cast(src, dst, scale=1.0):
     _need_cuda(src, dst)
     if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
@@ -490,7 +516,7 @@ def to_bf16(src):
     return cast(src, torch.empty(src.shape, dtype=BF16, device=src.device))
 
 
-@_profiled("gelu")
+@_profiled("gelu", None, lambda x, y, dy=None: _tb(x, y, dy))
 def gelu(x, y, dy=None):
     """y = GELU(x), or y = dy * GELU'(x) when dy is given (contiguous tensors of equal size)."""
     _need_cuda(x, y, dy)
@@ -502,7 +528,19 @@ def gelu(x, y, dy=None):
     return y
 
 
-@_profiled("patchify")
+@_profiled("gelu")
+def tanh(x, y, dy=None):
+    """y = tanh(x), or y = dy * (1 - x^2) when dy is given and x is the saved tanh output."""
+    _need_cuda(x, y, dy)
+    n = x.numel()
+    if n % 4 or y.numel() != n or not (x.is_contiguous() and y.is_contiguous()) or (dy is not None and not dy.is_contiguous()):
+        raise ValueError("tanh: contiguous tensors with numel % 4 == 0 required")
+    _lib.check(_lib.load().clv_tanh(_ptr(x), _is_bf16(x), _ptr(dy), _is_bf16(dy) if dy is not None else 0, _ptr(y),
+                                   _is_bf16(y), n, _stream()), "clv_tanh")
+    return y
+
+
+@_profiled("patchify", None, lambda x, patch, norm=None: _tb(x) + 2.0 * x.numel())
 def patchify(x, patch, norm=None):
     """x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw] and (D,Hp,Wp).
     x uint8 + norm=(mean, inv_std) fp32 [Cin] device tensors: raw frames normalised in the load (GPUNormalize)."""

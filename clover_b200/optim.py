@@ -58,9 +58,41 @@ class FusedAdamW(torch.optim.Optimizer):
         self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
         self.check_finite, self.emit_bf16 = bool(check_finite), bool(emit_bf16)
         self.grad_scale = 1.0                    # multiply gradients by this (1 / loss scale) before clipping
-        self._step = 0
+        # Count of APPLIED updates, resident on the device (an overflow-skipped step does not advance it) and shared by every
+        # parameter as state[p]['step'] -- the torch.optim.AdamW state layout (step, exp_avg, exp_avg_sq), so state_dict()
+        # carries it and checkpoints are interchangeable with the reference's optimizer.
+        self._step_dev = None
         self._static = None                      # (param ids, chunk tables) for the current set of parameters with gradients
+        self._host = [None, None]                # double-buffered pinned descriptor tables + the events guarding their reuse
+        self._host_ev = [None, None]
+        self._calls = 0
         self.status = None                       # device fp32[3]: gradient norm, skipped flag, scratch
+
+    @property
+    def applied_steps(self):
+        """Number of updates applied so far (one device -> host read)."""
+        return 0 if self._step_dev is None else int(self._step_dev.item())
+
+    def state_dict(self):
+        """torch.optim.AdamW's layout: every parameter's state holds its OWN cpu scalar 'step' (the shared device counter is
+        read once), so the dict loads into the reference's optimizer unchanged."""
+        sd = super().state_dict()
+        if self._step_dev is not None:
+            step = float(self._step_dev.item())
+            sd["state"] = {k: dict(st, step=torch.tensor(step, dtype=torch.float32)) if "step" in st else st
+                           for k, st in sd["state"].items()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        # re-link the shared device counter: every parameter was saved with the same 'step'
+        steps = [st["step"] for st in self.state.values() if "step" in st]
+        self._step_dev = None
+        if steps:
+            dev = next(iter(self.state.keys())).device
+            self._step_dev = torch.as_tensor(steps[0], dtype=torch.float32).reshape(1).to(dev).clone()
+            for st in self.state.values():
+                st["step"] = self._step_dev
 
     # ---- tables ----------------------------------------------------------------------------------------------------
     def _chunks(self, plist, device):
@@ -73,8 +105,12 @@ class FusedAdamW(torch.optim.Optimizer):
                 co.append(offs)
             ct = torch.from_numpy(np.concatenate(ct)).to(device)
             co = torch.from_numpy(np.concatenate(co)).to(device)
-            host = torch.empty(len(plist) * _DT.itemsize, dtype=torch.uint8).pin_memory()
-            self._static = (key, ct, co, host, torch.empty(len(plist) * _DT.itemsize, dtype=torch.uint8, device=device))
+            for ev in self._host_ev:             # the old pinned tables may still be in flight
+                if ev is not None:
+                    ev.synchronize()
+            self._host = [torch.empty(len(plist) * _DT.itemsize, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._host_ev = [None, None]
+            self._static = (key, ct, co, torch.empty(len(plist) * _DT.itemsize, dtype=torch.uint8, device=device))
         return self._static[1:]
 
     @torch.no_grad()
@@ -97,28 +133,45 @@ class FusedAdamW(torch.optim.Optimizer):
         if not plist:
             return loss
         dev = plist[0].device
-        ct, co, host, table = self._chunks(plist, dev)
+        ct, co, table = self._chunks(plist, dev)
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         rec = np.zeros(len(plist), dtype=_DT)
         dests = []
         for i, p in enumerate(plist):
             st = self.state[p]
             if not st:
+                st["step"] = self._step_dev
                 st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p), torch.zeros_like(p)
             d = Fn.bf16_destination(p) if self.emit_bf16 else None
             dests.append(d)
             rec[i] = (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                       d[0] if d else 0, p.numel(), lrs[i], wds[i])
+        # The pinned table is read by an asynchronous copy: never rewrite a buffer whose previous upload may still be in
+        # flight (a loop without a per-step host sync lets the CPU run ahead).  Two buffers alternate, each guarded by the
+        # event recorded after its copy.
+        slot = self._calls & 1
+        self._calls += 1
+        if self._host_ev[slot] is not None:
+            self._host_ev[slot].synchronize()
+        host = self._host[slot]
         host.numpy()[:] = np.frombuffer(rec.tobytes(), dtype=np.uint8)
         table.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._host_ev[slot] = ev
         if self.status is None:
             self.status = torch.zeros(3, dtype=torch.float32, device=dev)
-        self._step += 1
         lib = _lib.load()
+        from . import ops
+        ev = ops._prof_open()
         rc = lib.clv_adamw_step(C.c_void_p(table.data_ptr()), C.c_void_p(ct.data_ptr()), C.c_void_p(co.data_ptr()), ct.numel(), CHUNK,
-                                float(betas[0]), float(betas[1]), float(eps), self._step, float(self.grad_scale),
+                                float(betas[0]), float(betas[1]), float(eps), 0, float(self.grad_scale),
                                 float(self.max_grad_norm), int(self.check_finite), C.c_void_p(self.status.data_ptr()),
-                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                C.c_void_p(self._step_dev.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "clv_adamw_step")
+        # algorithmic bytes: grad read twice (norm pass + update), p / m / v read + written, bf16 copy written
+        ops._prof_close(ev, "adamw", 0.0, float(sum(p.numel() for p in plist)) * (4 * 2 + 4 * 6 + 2))
         # the kernel wrote the parameters through raw pointers: bump their version counters (every derived cache keyed on
         # them re-validates) and re-stamp the bf16 copies that were refreshed in the same pass
         vers = tuple(p._version + 1 for p in plist)

@@ -162,13 +162,14 @@ class CloverPretrain(BaseRecognizer):
         # ---- fusion passes ----------------------------------------------------------------- :117-121
         v_f, _ = self.multimodal_backbone.forward_tokens(vm_tok, B, T, S, T_e, text_mask)
         t_f, _ = self.multimodal_backbone.forward_tokens(v_tok, B, T, S, T_m, text_mask)
-        t_last = t_f[:, T * S:]                                                     # (B, L, H)
+        vs = self.multimodal_backbone.v_seq_len(T, S)                               # text tokens start here (cross_transformer.py:111-117)
+        t_last = t_f[:, vs:]                                                        # (B, L, H)
         losses = dict()
         # ---- MLM: decoder + row selection + focal loss fused ------------------------------- :129-143
         gamma = getattr(self.mlm_loss_func, "gamma", 0.0) if self.mlm_loss_func is not None else 0.0
         losses["mlm_loss"] = self.mlm_head.focal_loss(t_last.reshape(B * L, H), mlm_label.reshape(-1), gamma=gamma)
         # ---- tri-modal alignment ------------------------------------------------------------ :147-169
-        m_vmf = self.mlm_ssl_V_head(v_f[:, T * S])                                  # fused text-CLS slot, (B, H)
+        m_vmf = self.mlm_ssl_V_head(v_f[:, vs])                                     # fused text-CLS slot, (B, H)
         tm_emb = self.ssl_head.forward_text(T_m)
         m_tmf = self.mlm_ssl_T_head(t_last[:, 0])
         vm_emb = self.ssl_head.forward_vision_tokens(vm_tok, B, T * S)
@@ -202,11 +203,12 @@ class CloverPretrain(BaseRecognizer):
         vm_emb, v_emb = vemb2.split(B)
         t_emb, tm_emb = temb2.split(B)
         f2, _ = self.multimodal_backbone.forward_tokens(tok2, B2, T, S, T2, tmask2)  # (vm, T_e) ; (v, T_m)
-        t_last = f2[B:, T * S:]                                                     # (B, L, H) of the masked-text pass
+        vs = self.multimodal_backbone.v_seq_len(T, S)                               # text tokens start here (cross_transformer.py:111-117)
+        t_last = f2[B:, vs:]                                                        # (B, L, H) of the masked-text pass
         losses = dict()
         gamma = getattr(self.mlm_loss_func, "gamma", 0.0) if self.mlm_loss_func is not None else 0.0
         losses["mlm_loss"] = self.mlm_head.focal_loss(t_last.reshape(B * L, H), mlm_label.reshape(-1), gamma=gamma)
-        m_vmf = self.mlm_ssl_V_head(f2[:B, T * S])                                  # fused text-CLS slot of the masked-video pass
+        m_vmf = self.mlm_ssl_V_head(f2[:B, vs])                                     # fused text-CLS slot of the masked-video pass
         m_tmf = self.mlm_ssl_T_head(t_last[:, 0])
         g_v, g_t, g_tm, g_vmf, g_vm, g_tmf = gather_stacked([v_emb, t_emb, tm_emb, m_vmf, vm_emb, m_tmf])
         losses.update(self.ssl_loss.forward_gathered(g_v, g_t, g_tm, g_vmf))
@@ -238,7 +240,8 @@ class CloverPretrain(BaseRecognizer):
 
 
 class CloverFinetune(BaseRecognizer):
-    """reference multimodal_transformer_finetune.py:9-203 (tasks 'retrieval' and 'video_qa' with answer_cls)."""
+    """reference multimodal_transformer_finetune.py:9-203: tasks 'retrieval', 'video_qa' and 'FIB', every answer-feature
+    branch of :98-118 (answer_mask / answer_cls with or without itm_head / all-cls + itm_head, qa_head or raw ITM logit)."""
 
     def __init__(self, mm_backbone, text_backbone=None, freeze_text_backbone=None, loss_type=None, task=None,
                  ssl_head=None, itm_head=None, answer_mask=False, answer_cls=False, qa_head=None, from_scratch=False,
@@ -252,10 +255,12 @@ class CloverFinetune(BaseRecognizer):
             self.loss_func = build_loss(loss_type)
         elif task in ("video_qa", "FIB"):
             self.answer_mask, self.answer_cls = answer_mask, answer_cls
-            if itm_head is not None or answer_mask or not answer_cls:
-                raise NotImplementedError("clover_b200: video_qa is supported with answer_cls=True and a qa_head")
-            self.itm_head = None
+            self.itm_head = build_head(itm_head) if itm_head is not None else None
             self.qa_head = build_head(qa_head) if qa_head is not None else None
+            if self.itm_head is None and self.qa_head is None:
+                raise ValueError("CloverFinetune(task=%r) needs a qa_head or an itm_head" % (task,))
+            if not answer_mask and not answer_cls and self.itm_head is None:
+                raise ValueError("answer_mask=False, answer_cls=False reads the all-cls slot through itm_head (:110-112)")
             self.loss_func = build_loss(loss_type)
             self.loss_type = loss_type["type"]
         else:
@@ -280,18 +285,35 @@ class CloverFinetune(BaseRecognizer):
         T_e = self.text_backbone(token_ids, input_mask)["last_hidden_state"]
         return v_tok, (B, T, h * w), T_e, token_ids, input_mask
 
-    def _qa_logits(self, v_tok, B, T, S, T_e, input_mask, want_attention=False):
-        if not hasattr(self.qa_head, "num_labels"):
-            n = T_e.shape[0] // B                                                   # multiple choice: repeat the clip
+    def _qa_logits(self, v_tok, B, T, S, T_e, token_ids, input_mask, test=False):
+        """:88-118 (train) / :158-188 (test).  Returns (final_output, head-mean attention or None)."""
+        if hasattr(self.qa_head, "num_labels"):                                     # :90-92
+            n, Bq = self.qa_head.num_labels, B
+        else:                                                                       # :93-95 every candidate sees the clip
+            n = T_e.shape[0] // B
             v_tok = v_tok.view(B, 1, T * S, -1).expand(-1, n, -1, -1).reshape(B * n * T * S, -1).contiguous()
             Bq = B * n
-        else:
-            n, Bq = self.qa_head.num_labels, B
-        res = self.multimodal_backbone.forward_tokens(v_tok, Bq, T, S, T_e, input_mask, want_last_probs=want_attention)
+        mm = self.multimodal_backbone
+        res = mm.forward_tokens(v_tok, Bq, T, S, T_e, input_mask, want_last_probs=test)
         out = res[0]
-        cls = out[:, T * S]                                                         # t_last_hidden_state[:, 0]
-        logits = self.qa_head(cls).reshape(-1, n)
-        return (logits, res[2]) if want_attention else logits
+        vs = mm.v_seq_len(T, S)
+        if self.answer_mask:                                                        # :98-100 the [MASK] (id 103) positions
+            bi, li = torch.where(token_ids.reshape(Bq, -1) == 103)
+            feat = out[bi, vs + li]
+        elif self.answer_cls:                                                       # :101-108
+            # cls_last_hidden_state.squeeze() when the encoder has an all-cls token, else t_last_hidden_state[:, 0]
+            feat = out[:, vs - 1] if mm.all_cls_token is not None else out[:, vs]
+            if self.itm_head is not None:
+                feat = self.itm_head(feat)
+        else:                                                                       # :110-112
+            feat = self.itm_head(out[:, 0])
+        if self.qa_head is not None:
+            final = self.qa_head(feat).reshape(-1, n)                               # :115
+        elif test:
+            final = torch.softmax(feat.float(), dim=-1)[:, 1].reshape(-1, n)        # :187-188
+        else:
+            final = feat[:, 1]                                                      # :118
+        return final, (res[2] if test else None)
 
     def forward_train(self, imgs, label, token_ids=None, segment_ids=None, input_mask=None, ans_ids=None, ans_mask=None,
                       **kwargs):
@@ -302,16 +324,16 @@ class CloverFinetune(BaseRecognizer):
             t_emb = self.ssl_head.forward_text(T_e)
             losses["retrieval_nce_loss"] = self.loss_func(v_emb, t_emb)
         else:
-            logits = self._qa_logits(v_tok, B, T, S, T_e, input_mask)
+            logits, _ = self._qa_logits(v_tok, B, T, S, T_e, token_ids, input_mask)
             losses["qa_loss"] = self.loss_func(logits, label.view(-1))
         return losses
 
     def forward_test(self, imgs, token_ids=None, segment_ids=None, input_mask=None, ans_ids=None, ans_mask=None, **kwargs):
         v_tok, (B, T, S), T_e, token_ids, input_mask = self._encode(imgs, token_ids, input_mask)
-        if self.task == "retrieval":
+        if self.separate_test or self.task == "retrieval":                          # :152-154
             return self.ssl_head.forward_vision_tokens(v_tok, B, T * S), self.ssl_head.forward_text(T_e)
         # reference :188-192: {'result': fp32 logits, 'attention': last fusion layer's head-mean attention probabilities}
-        logits, attn = self._qa_logits(v_tok, B, T, S, T_e, input_mask, want_attention=True)
+        logits, attn = self._qa_logits(v_tok, B, T, S, T_e, token_ids, input_mask, test=True)
         return {"result": logits.to(torch.float32), "attention": attn}
 
     def forward_gradcam(self, imgs, token_ids=None, input_mask=None):

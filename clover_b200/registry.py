@@ -90,6 +90,7 @@ def plugin_classes():
         "NCEHeadForVision": heads.NCEHeadForVision,
         "NCEHeadForText": heads.NCEHeadForText,
         "MLMHead": heads.MLMHead,
+        "ITMHead": heads.ITMHead,
         "QA_OE_Head": heads.QA_OE_Head,
         "QA_MC_head": heads.QA_MC_head,
         "ExclusiveNCEwithRankingLoss": losses.ExclusiveNCEwithRankingLoss,

@@ -12,21 +12,46 @@ rank, so data-parallel ranks draw different masks as they do in the reference (i
 import torch
 
 _MASK64 = (1 << 64) - 1
-_state = {"seed": None, "offset": 0}
+_state = {"seed": None, "offset": 0, "pinned": False, "key": None}
 LOG = None
 
 
 def manual_seed(seed):
-    _state["seed"] = int(seed) & _MASK64
-    _state["offset"] = 0
+    """Pin the stream to `seed` (offset 0) until reseed() is called."""
+    _state.update(seed=int(seed) & _MASK64, offset=0, pinned=True, key=None)
+
+
+def reseed():
+    """Drop a pinned / derived seed: the next draw re-derives it from torch.initial_seed() and the rank."""
+    _state.update(seed=None, offset=0, pinned=False, key=None)
+
+
+def get_state():
+    """(seed, offset, pinned) -- put it into a checkpoint next to torch's RNG state to make a resume reproducible."""
+    return _seed(), _state["offset"], _state["pinned"]
+
+
+def set_state(state):
+    seed, offset, pinned = state
+    _state.update(seed=int(seed) & _MASK64, offset=int(offset), pinned=bool(pinned), key=_key() if not pinned else None)
+
+
+def _key():
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    return int(torch.initial_seed()), rank
 
 
 def _seed():
-    if _state["seed"] is None:
-        rank = 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            rank = torch.distributed.get_rank()
-        _state["seed"] = (int(torch.initial_seed()) ^ (rank * 0x9E3779B97F4A7C15)) & _MASK64
+    """Unless pinned, the seed follows torch.initial_seed() and the data-parallel rank: a later torch.manual_seed() (the
+    reference's set_random_seed, tools/train.py) or init_process_group() re-derives it and restarts the stream, so ranks
+    never share masks because the first draw happened before the process group existed."""
+    if _state["pinned"]:
+        return _state["seed"]
+    key = _key()
+    if _state["seed"] is None or _state["key"] != key:
+        _state.update(seed=(key[0] ^ (key[1] * 0x9E3779B97F4A7C15)) & _MASK64, offset=0, key=key)
     return _state["seed"]
 
 

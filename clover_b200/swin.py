@@ -317,7 +317,7 @@ class SwinTransformer3D(nn.Module):
         if drop_rate > 0:
             raise NotImplementedError("clover_b200: drop_rate > 0 is not supported (0 in every Clover config)")
         self.pos_drop = nn.Dropout(p=drop_rate)
-        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths), device="cpu")]
         self.layers = nn.ModuleList()
         for i in range(self.num_layers):
             self.layers.append(BasicLayer(

@@ -88,7 +88,7 @@ def make_batch(B, frames=8, L=32, seed=1, size=224, vocab=30522, mask_cells=10, 
 
 def make_finetune_batch(task, B, frames=16, size=224, L=40, vocab=30522, seed=1, num_labels=1500, choices=5):
     """Fine-tune batches.  'retrieval' and 'video_qa' (open-ended) carry one caption / question per
-    clip; 'video_qa_mc' carries `choices` candidate sentences per clip (token_ids (B, choices, L)) and label = the
+    clip ('FIB': with exactly one [MASK] token); 'video_qa_mc' carries `choices` candidate sentences per clip (token_ids (B, choices, L)) and label = the
     index of the right one.  No MLM masking is used by the fine-tune recognisers, the [MASK] ids are just tokens."""
     if task == "video_qa_mc":
         parts = [make_batch(B, frames=frames, L=L, seed=seed + 10 * c, size=size, vocab=vocab) for c in range(choices)]
@@ -99,7 +99,14 @@ def make_finetune_batch(task, B, frames=16, size=224, L=40, vocab=30522, seed=1,
         return batch
     b = make_batch(B, frames=frames, L=L, seed=seed, size=size, vocab=vocab)
     batch = {k: b[k] for k in ("imgs", "token_ids", "input_mask", "segment_ids")}
-    hi = num_labels if task == "video_qa" else 1
+    if task == "FIB":
+        # fill-in-the-blank: exactly ONE [MASK] per sentence (finetune.py:98-100 picks the fused states at token id 103 and
+        # pairs them with one label per sample); keep the first masked position of make_batch, restore the others
+        lab = b["mlm_label"]
+        tok = torch.where(lab == -100, b["token_ids"], lab)
+        first = (lab != -100).int().argmax(dim=-1, keepdim=True)
+        batch["token_ids"] = tok.scatter(-1, first, b["token_ids"].gather(-1, first))
+    hi = num_labels if task in ("video_qa", "FIB") else 1
     batch["label"] = torch.from_numpy(np.random.default_rng([seed, 5]).integers(0, hi, size=(B, 1)))
     return batch
 

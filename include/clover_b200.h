@@ -25,6 +25,9 @@ const char* clv_last_error(void);
 int clv_version(void);
 /* Number of kernel launches issued by this library in the calling process (gpu_launches claim). */
 long long clv_launch_count(void);
+/* Experiment knobs for tools / tests ("gemm_bn256_min_units", "w7_pipe", "w7_bwd2", "w7_dbias_acc", "w7_dbias_acc_min_mb");
+ * value -1 restores the built-in default.  The library reads no environment variables.  Returns non-zero for unknown names. */
+int clv_set_tunable(const char* name, long long value);
 
 /* Window geometry of one Swin stage call: real extent (B,D,H,W), clamped window and shift as
  * returned by get_window_size (swin_transformer_3d.py:302-315).  Padding to window multiples
@@ -195,6 +198,10 @@ int clv_cast(const void* src, int src_is_bf16, void* dst, int dst_is_bf16, long 
  * otherwise y = dy * GELU'(x).  n % 4 == 0. */
 int clv_gelu(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, void* y, int y_is_bf16, long long n, void* stream);
 
+/* nn.Tanh of ITMHead.itm_projector (heads/mlm_itm_head.py:67-70).  dy == NULL: y = tanh(x); otherwise x holds the saved
+ * tanh OUTPUT t and y = dy * (1 - t^2).  n % 4 == 0. */
+int clv_tanh(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, void* y, int y_is_bf16, long long n, void* stream);
+
 /* PatchEmbed3D's Conv3d(kernel == stride) as a patch matrix (swin_transformer_3d.py:665,671-681):
  * x fp32 (B,Cin,F,H,W) -> bf16 [B*D*Hp*Wp, Cin*pd*ph*pw], column order (c,kd,kh,kw); zero padding. */
 int clv_patchify(const float* x, void* out_bf16, int B, int Cin, int F, int H, int W, int pd, int ph, int pw, void* stream);
@@ -262,6 +269,10 @@ int clv_retrieval_ranks(const float* scores, long long ld, int rows, int cols, c
  *   tensors_dev[n]               one entry per parameter (param_bf16 may be NULL)
  *   chunk_tensor_dev[n_chunks]   tensor index of every chunk;  chunk_offset_dev[n_chunks] first element of the chunk
  *   status_dev fp32[3]           out: [0] gradient norm (after grad_scale), [1] 1 if the step was skipped, [2] scratch
+ *   step_dev fp32[1] or NULL     device-resident count of APPLIED updates (torch.optim.AdamW's state['step']): when given,
+ *                                the bias corrections use *step_dev + 1 and the counter advances only if the step was not
+ *                                skipped (so `step` is ignored and a resume / an overflow skip keep the schedule exact);
+ *                                NULL: the host passes `step` >= 1
  * g' = g * grad_scale * min(1, max_grad_norm / (norm + 1e-6)) (max_grad_norm <= 0: no clipping).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -272,7 +283,7 @@ typedef struct {
 } clv_adamw_tensor_t;
 int clv_adamw_step(const clv_adamw_tensor_t* tensors_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
                    int n_chunks, int chunk_elems, float beta1, float beta2, float eps, int step, float grad_scale,
-                   float max_grad_norm, int check_finite, float* status_dev, void* stream);
+                   float max_grad_norm, int check_finite, float* status_dev, float* step_dev, void* stream);
 
 /* dst[index[r],:] += src[r,:]  (fp32 atomics; word-embedding gradient of HF BertEmbeddings). */
 int clv_scatter_add_rows(const float* src, const long long* index, float* dst, long long rows, int C, void* stream);

@@ -259,6 +259,16 @@ def pretrain_cfg(embed, depths, heads, img_in, hidden, vocab, text_layers, fusio
         symmetry_rank=True, train_cfg=dict(aux_info=aux))
 
 
+def _sample_idx(flat):
+    """2048 sample positions of a large gradient; for sparse gradients (word embeddings: only the rows of the tokens in
+    the batch are non-zero) the sample is drawn from the non-zero entries, so it is not a handful of lucky hits."""
+    rng = np.random.default_rng(5)
+    nz = np.flatnonzero(flat.numpy())
+    if nz.size < flat.numel() // 2:
+        return np.sort(rng.choice(nz, size=min(2048, nz.size), replace=False))
+    return rng.integers(0, flat.numel(), size=2048)
+
+
 GRAD_KEYS = ["backbone.patch_embed.proj.weight", "backbone.mask_token",
              "backbone.layers.0.blocks.1.attn.relative_position_bias_table",
              "backbone.layers.1.blocks.0.attn.qkv.weight", "backbone.norm.bias",
@@ -270,7 +280,16 @@ GRAD_KEYS = ["backbone.patch_embed.proj.weight", "backbone.mask_token",
              "mlm_head.predictions.decoder.weight", "mlm_ssl_V_head.img_fc1.weight", "mlm_ssl_T_head.fc2.weight"]
 
 
-def gen_pretrain(ref, tag, cfg, bert_over, B, frames, size, L, vocab, seed, full_grads):
+SWINB_EXTRA_GRAD_KEYS = ["backbone.layers.0.blocks.0.norm1.weight", "backbone.layers.0.blocks.0.attn.qkv.weight",
+                         "backbone.layers.2.blocks.9.mlp.fc1.weight", "backbone.layers.2.blocks.17.attn.proj.weight",
+                         "backbone.layers.2.blocks.4.attn.relative_position_bias_table",
+                         "backbone.layers.3.blocks.1.attn.relative_position_bias_table", "backbone.layers.3.blocks.1.mlp.fc2.bias",
+                         "backbone.layers.1.downsample.reduction.weight",
+                         "text_backbone.bert.encoder.layer.11.output.dense.weight",
+                         "multimodal_backbone.bert_encoder.layer.2.attention.self.value.weight"]
+
+
+def gen_pretrain(ref, tag, cfg, bert_over, B, frames, size, L, vocab, seed, full_grads, extra_keys=(), embeddings=False):
     ref_shim.ensure_gloo_group()
     ref_shim.BERT_OVERRIDES.clear()
     ref_shim.BERT_OVERRIDES.update(bert_over)
@@ -281,13 +300,21 @@ def gen_pretrain(ref, tag, cfg, bert_over, B, frames, size, L, vocab, seed, full
     load_synth(m, seed=seed)
     batch = make_batch(B, frames=frames, L=L, seed=seed + 1, size=size, vocab=vocab)
     kw = {k: batch[k] for k in ("token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")}
+    captured = []
+    hook = m.ssl_loss.register_forward_pre_hook(lambda mod, args: captured.append([a.detach().clone() for a in args]))
     losses = m(batch["imgs"], batch["label"], return_loss=True, **kw)
+    hook.remove()
     total, log_vars = m._parse_losses(losses)
     total.backward()
     out = {f"loss::{k}": np.float64(v) for k, v in log_vars.items()}
+    if embeddings:
+        # the two ssl_loss calls of forward_train (pretrain.py:151,161): (V_e, T_e, T_m, M_Vmf) then (T_e, V_e, V_m, M_Tmf)
+        (v_e, t_e, t_m, m_vmf), (_, _, v_m, m_tmf) = captured
+        for n, e in (("v", v_e), ("t", t_e), ("tm", t_m), ("vmf", m_vmf), ("vm", v_m), ("tmf", m_tmf)):
+            out[f"emb::{n}"] = e.float().numpy().copy()
     params = dict(m.named_parameters())
     out["nograd_keys"] = np.array(json.dumps(sorted(k for k, p in params.items() if p.grad is None)))
-    for k in GRAD_KEYS:
+    for k in list(GRAD_KEYS) + list(extra_keys):
         if k not in params:
             continue
         g = params[k].grad
@@ -296,7 +323,7 @@ def gen_pretrain(ref, tag, cfg, bert_over, B, frames, size, L, vocab, seed, full
             out[f"grad::{k}"] = g.numpy().copy()
         else:
             flat = g.reshape(-1)
-            idx = np.random.default_rng(5).integers(0, flat.numel(), size=2048)
+            idx = _sample_idx(flat)
             out[f"gradidx::{k}"] = idx
             out[f"gradsample::{k}"] = flat.numpy()[idx].copy()
     np.savez_compressed(os.path.join(OUT, f"pretrain_{tag}.npz"), **out)
@@ -311,7 +338,8 @@ FT_GRAD_KEYS = ["backbone.patch_embed.proj.weight", "backbone.layers.0.blocks.1.
                 "multimodal_backbone.bert_encoder.layer.0.output.dense.weight",
                 "ssl_head.img_projector.3.weight", "ssl_head.text_projector.0.bias",
                 "qa_head.vqa_classifier.1.weight", "qa_head.vqa_classifier.4.bias",
-                "qa_head.mc_vqa_classifier.1.weight", "qa_head.mc_vqa_classifier.4.weight"]
+                "qa_head.mc_vqa_classifier.1.weight", "qa_head.mc_vqa_classifier.4.weight",
+                "multimodal_backbone.all_cls_token"]
 
 
 def gen_finetune(ref, tag, task, cfg, bert_over, B, frames, size, L, vocab, seed, num_labels=50):
@@ -342,7 +370,7 @@ def gen_finetune(ref, tag, task, cfg, bert_over, B, frames, size, L, vocab, seed
             out[f"grad::{k}"] = g.numpy().copy()
         else:
             flat = g.reshape(-1)
-            idx = np.random.default_rng(5).integers(0, flat.numel(), size=2048)
+            idx = _sample_idx(flat)
             out[f"gradidx::{k}"] = idx
             out[f"gradsample::{k}"] = flat.numpy()[idx].copy()
     m.eval()
@@ -410,7 +438,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = ref_shim.load_reference()
-    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "ft", "eval", "inflate", "keys"]
+    which = sys.argv[1:] or ["tables", "wa", "swin", "bfh", "losses", "tiny", "c1", "swinb", "ft", "eval", "inflate", "keys"]
     if "tables" in which:
         gen_tables(ref)
     if "wa" in which:
@@ -423,17 +451,27 @@ def main():
         gen_losses(ref)
     if "tiny" in which:
         cfg = pretrain_cfg(32, [2, 2], [1, 2], 64, 128, 1000, 2, 2, 2)
-        gen_pretrain(ref, "tiny", cfg, SMALL_BERT, B=3, frames=4, size=56, L=16, vocab=1000, seed=50, full_grads=True)
+        gen_pretrain(ref, "tiny", cfg, SMALL_BERT, B=3, frames=4, size=56, L=16, vocab=1000, seed=50, full_grads=True,
+                     embeddings=True)
     if "c1" in which:
         cfg = pretrain_cfg(96, [2, 2, 6, 2], [3, 6, 12, 24], 768, 768, 30522, 12, 3, 4)
         gen_pretrain(ref, "c1", cfg, dict(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
-                     B=2, frames=8, size=224, L=32, vocab=30522, seed=60, full_grads=False)
-    if "ft" in which:
+                     B=2, frames=8, size=224, L=32, vocab=30522, seed=60, full_grads=False, embeddings=True)
+    if "swinb" in which:
+        # the headline configuration (BASELINE c3 model: Video Swin-B + BERT-base + 3-layer fusion) at B = 2
+        cfg = pretrain_cfg(128, [2, 2, 18, 2], [4, 8, 16, 32], 1024, 768, 30522, 12, 3, 4)
+        gen_pretrain(ref, "swinb", cfg, dict(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
+                     B=2, frames=8, size=224, L=32, vocab=30522, seed=62, full_grads=False,
+                     extra_keys=SWINB_EXTRA_GRAD_KEYS, embeddings=True)
+    only = [w[3:] for w in which if w.startswith("ft:")]          # e.g. `ft:fib` regenerates one fine-tune fixture
+    if "ft" in which or only:
         from clover_b200.configs import finetune_cfg
         small = dict(embed=32, depths=[2, 2], heads=[1, 2], img_in=64, hidden=128, vocab=1000, text_layers=2, fusion_layers=2,
                      frames_half=8)
         # 16-frame clips -> T = 8 token frames -> the full (8,7,7) window, N = 392 (BASELINE c4 / c5 shapes)
-        for tag, task in (("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc")):
+        for tag, task in (("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc"), ("fib", "FIB")):
+            if only and tag not in only:
+                continue
             cfg = finetune_cfg(task, num_labels=50, **small)
             for k in ("hidden_dropout_prob", "attention_probs_dropout_prob"):
                 cfg["mm_backbone"].pop(k, None), cfg["text_backbone"].pop(k, None)

@@ -82,7 +82,11 @@ def finetune_shapes(task, embed, depths, heads, img_in, hidden, inter, vocab, ma
     full = pretrain_shapes(embed, depths, heads, img_in, hidden, inter, vocab, maxpos, text_layers, fusion_layers, frames_half)
     keep = ("backbone.", "text_backbone.", "multimodal_backbone.") + (("ssl_head.",) if task == "retrieval" else ())
     sh = {k: v for k, v in full.items() if k.startswith(keep) and k != "backbone.mask_token"}
-    if task == "video_qa":
+    if task == "FIB":                                    # use_text_cls=False encoder + ITM head (finetune_lsmdc_FIB.py)
+        sh["multimodal_backbone.all_cls_token"] = (1, 1, hidden)
+        i = "itm_head.itm_projector."
+        sh.update({i + "1.weight": (hidden, hidden), i + "1.bias": (hidden,), i + "3.weight": (2, hidden), i + "3.bias": (2,)})
+    if task in ("video_qa", "FIB"):
         q = "qa_head.vqa_classifier."
         sh.update({q + "1.weight": (hidden // 2, hidden), q + "1.bias": (hidden // 2,), q + "2.weight": (hidden // 2,),
                    q + "2.bias": (hidden // 2,), q + "4.weight": (num_labels, hidden // 2), q + "4.bias": (num_labels,)})

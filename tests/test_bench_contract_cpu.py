@@ -19,6 +19,8 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"].startswith("c3:") and d["config"]["clips_per_gpu"] == 64 and d["config"]["drop_path"] == 0.3
+    # the arm states what it really runs per step: a bounded 2-clip sample, one process, optimizer included
+    assert d["config"]["reference_sample"]["clips_per_step"] == 2 and d["config"]["reference_sample"]["optimizer_in_step"] is True
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "clips" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -26,7 +26,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from clover_b200.gather import GatherLoss, VariedShapeGatherLoss, gather_stacked
+        from clover_b200.gather import GatherLoss, VariedShapeGatherLoss, gather_stacked, gather_stacked_varied
         res = {}
         g = torch.Generator().manual_seed(100 + rank)
         # fixed-size gather
@@ -41,6 +41,13 @@ def _worker(rank, world, port, q):
         wr = torch.arange(yr.numel(), dtype=torch.float32).view_as(yr) * 0.5
         (yr * wr).sum().backward()
         res["ragged_out"], res["ragged_grad"], res["ragged_in"], res["ragged_w"] = yr.detach(), xr.grad.clone(), xr.detach(), wr
+        # ragged STACKED gather (one size exchange + one collective for several tensors)
+        xs = [torch.randn(2 + rank, 4, generator=g, requires_grad=True) for _ in range(3)]
+        ys = gather_stacked_varied(xs)
+        ws_ = [torch.arange(y_.numel(), dtype=torch.float32).view_as(y_) * (i + 1) for i, y_ in enumerate(ys)]
+        sum((y_ * w_).sum() for y_, w_ in zip(ys, ws_)).backward()
+        res["sv_out"], res["sv_in"] = [y_.detach() for y_ in ys], [x_.detach() for x_ in xs]
+        res["sv_grad"], res["sv_w"] = [x_.grad.clone() for x_ in xs], ws_
         # stacked gather of several embeddings + the loss evaluated on the global batch
         embs = [torch.randn(4, 16, generator=g, requires_grad=True) for _ in range(4)]
         gathered = gather_stacked(embs)
@@ -88,6 +95,10 @@ def test_gather_semantics_world2():
     ragged = torch.cat([r0["ragged_in"], r1["ragged_in"]])
     assert torch.equal(r0["ragged_out"], ragged) and torch.equal(r1["ragged_out"], ragged)
     assert torch.equal(r0["ragged_grad"], r0["ragged_w"][:2]) and torch.equal(r1["ragged_grad"], r1["ragged_w"][2:])
+    for i in range(3):
+        cat = torch.cat([r0["sv_in"][i], r1["sv_in"][i]])
+        assert torch.equal(r0["sv_out"][i], cat) and torch.equal(r1["sv_out"][i], cat)
+        assert torch.equal(r0["sv_grad"][i], r0["sv_w"][i][:2]) and torch.equal(r1["sv_grad"][i], r1["sv_w"][i][2:])
     # global loss identical on every rank; local grads == the matching rows of the single-process full-batch gradient
     assert abs(r0["loss"] - r1["loss"]) < 1e-6
     glob = [torch.cat([r0["embs"][i], r1["embs"][i]]).requires_grad_(True) for i in range(4)]

@@ -354,9 +354,11 @@ def _attn_ref(qkv, dout, batch, seq, heads, hd, bias=None):
     return x, o, lse
 
 
-@pytest.mark.parametrize("dims,shifted", [((4, 14, 14), False), ((4, 14, 14), True), ((8, 14, 7), True), ((16, 7, 7), True)])
-def test_window_attention_core(ops, dims, shifted):
-    heads, hd, Bc = 3, 32, 2
+@pytest.mark.parametrize("dims,shifted,heads", [((4, 14, 14), False, 3), ((4, 14, 14), True, 3), ((8, 14, 7), True, 3),
+                                               ((16, 7, 7), True, 3), ((4, 14, 14), True, 4), ((4, 14, 7), True, 8),
+                                               ((4, 7, 7), False, 16), ((4, 7, 7), False, 32)])
+def test_window_attention_core(ops, dims, shifted, heads):
+    hd, Bc = 32, 2
     win, sh = O.get_window_size(dims, (8, 7, 7), (4, 3, 3) if shifted else (0, 0, 0))
     N = win[0] * win[1] * win[2]
     nwin = (dims[0] // win[0]) * (dims[1] // win[1]) * (dims[2] // win[2])
@@ -391,10 +393,14 @@ def test_window_attention_core(ops, dims, shifted):
 @pytest.mark.parametrize("dims,shifted,Bc", [((4, 14, 14), False, 2), ((4, 14, 14), True, 2), ((4, 14, 14), True, 40),
                                             ((2, 14, 14), True, 3), ((8, 14, 7), True, 2), ((16, 7, 7), True, 2),
                                             ((6, 7, 7), False, 5), ((8, 14, 14), False, 20), ((8, 14, 14), True, 9)])
-def test_window_attention_w7(ops, dims, shifted, Bc):
+@pytest.mark.parametrize("heads", [3, 4, 8, 16, 32])
+def test_window_attention_w7(ops, dims, shifted, Bc, heads):
     """Specialised (wd, 7, 7) window attention (attention_w7.cu): static bias gather, shift mask / lse / D folded
-    into the MMA K-extension.  Same oracle and tolerances as the generic kernels."""
-    heads, hd = 3, 32
+    into the MMA K-extension.  Same oracle and tolerances as the generic kernels.  heads 4 / 8 / 16 / 32 are the four
+    Swin-B stages (production), 3 the Swin-T stage-1 width."""
+    hd = 32
+    if heads > 4 and (Bc > 9 or dims[0] > 8):          # keep the CPU reference of the wide cases to a few seconds
+        pytest.skip("wide-head case covered at the smaller batch")
     win, sh = O.get_window_size(dims, (8, 7, 7), (4, 3, 3) if shifted else (0, 0, 0))
     N = win[0] * win[1] * win[2]
     nwin = (dims[0] // win[0]) * (dims[1] // win[1]) * (dims[2] // win[2])
@@ -696,6 +702,27 @@ def test_fused_adamw_vs_torch(ops):
     o1.step()
     nrm, skipped = o1.grad_norm()
     assert skipped and all(torch.equal(a.detach(), b) for a, b in zip(ours, before))
+    assert o1.applied_steps == 4                              # the skipped step did not age the bias correction
+    # checkpoint / resume: state_dict() carries the step in torch.optim.AdamW's layout, a fresh optimizer
+    # resumed from it continues exactly like the torch reference resumed from ITS state -- and the two are interchangeable
+    sd = o1.state_dict()
+    assert all(set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 4.0 for st in sd["state"].values())
+    ours2 = [torch.nn.Parameter(a.detach().clone()) for a in ours]
+    o3 = FusedAdamW(groups(ours2), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=2.0)
+    o3.load_state_dict(sd)
+    ref2 = [torch.nn.Parameter(b.detach().clone()) for b in ref]
+    o4 = torch.optim.AdamW(groups(ref2), betas=(0.9, 0.98), eps=1e-8)
+    o4.load_state_dict(sd)                                    # our state loads into the reference optimizer as is
+    for it in range(2):
+        for a, b in zip(ours2, ref2):
+            g = torch.randn(a.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(200 + it))
+            a.grad, b.grad = g.clone(), g.clone()
+        o3.step()
+        torch.nn.utils.clip_grad_norm_(ref2, 2.0)
+        o4.step()
+        for a, b in zip(ours2, ref2):
+            assert rel(a.detach(), b.detach()) < 2e-6, (it, tuple(a.shape))
+    assert o3.applied_steps == 6
 
 
 # ------------------------------------------------------------------------------------------------ input staging
@@ -753,6 +780,27 @@ def test_window_attention_c2_full_size_properties(ops, shifted):
     want = dout.view(batch, N, heads, hd).float().sum(1)
     assert rel(dv, want) < 1e-2                                                         # (2)
     assert float(dtab.sum(0).abs().max()) < 2e-2 * float(dtab.abs().sum(0).max())       # (3)
+    # (5) windows are independent, so a sample of them against the fp32 oracle is a full-size numerical check: 16 windows
+    # spread over the clips and over every shift-mask class (corner / edge / interior windows of the 8x8 grid)
+    sample = [0, 7, 56, 63, 9, 27, 36, 62] + [nwin * c + w for c, w in ((1, 0), (5, 63), (17, 8), (31, 15), (40, 33), (50, 55), (63, 62), (63, 63))]
+    idx = torch.from_numpy(O.relative_position_index((8, 7, 7))[:N, :N].reshape(-1))
+    bias_ref = table.cpu()[idx].view(N, N, heads).permute(2, 0, 1)
+    mask_ref = torch.from_numpy(O.compute_mask(*dims, win, sh)) if masked else None
+    worst = [0.0, 0.0, 0.0]
+    for wdx in sample:
+        rows_w = slice(wdx * N, (wdx + 1) * N)
+        b = bias_ref[None] + (mask_ref[wdx % nwin][None, None] if masked else 0.0)
+        xw, o_ref, lse_ref = _attn_ref(qkv[rows_w], dout[rows_w], 1, N, heads, hd, b)
+        (o_ref * dout[rows_w].float().cpu()).sum().backward()
+        gq = xw.grad.clone().view(N, 3, heads * hd)
+        gq[:, 0] *= hd ** -0.5                                          # the kernel returns d(unscaled q) = scale * d(q)
+        worst[0] = max(worst[0], rel(out[rows_w], o_ref.detach()))
+        worst[1] = max(worst[1], rel(lse[wdx], lse_ref.detach()[0]))
+        worst[2] = max(worst[2], rel(dqkv[rows_w], gq.view(N, -1)))
+    from conftest import record_parity
+    record_parity(f"window_attention_c2_full_size_sampled_windows_{'shifted' if shifted else 'unshifted'}",
+                  {"windows": len(sample), "out_rel": worst[0], "lse_rel": worst[1], "dqkv_rel": worst[2]})
+    assert worst[0] < 1e-2 and worst[1] < 1e-4 and worst[2] < 2e-2, worst
     # (4) swap clip 3 and clip 17 (same window classes, row-block permutation)
     rows = nwin * N
     perm = torch.arange(batch * N, device="cuda").view(clips, rows)

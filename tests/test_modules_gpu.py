@@ -12,7 +12,11 @@ from clover_b200.synthetic import make_batch, named_tensor, synth_state_dict
 from oracle import clover_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-2
+TOL = 2e-2           # bf16 outputs / embeddings vs the fp32 reference (north-star)
+LOSS_TOL = 1e-3      # every loss entry, relative to max(1, |reference|) (north-star "loss within 1e-3")
+GRAD_TOL = 2e-2      # parameter gradients, relative L2 (north-star) -- met by the shallow fine-tune / module cases
+LOSS_ENTRY_TOL = 5e-3  # single loss entries of the pre-train step (see _check_pretrain)
+GRAD_LIMIT = 8e-2    # parameter gradients of the full-depth pre-train step (see _check_pretrain)
 
 
 @pytest.fixture(scope="module")
@@ -181,51 +185,139 @@ def _pretrain_model(cb, embed, depths, heads, img_in, hidden, vocab, text_layers
     return cb.build_model(cfg).cuda()
 
 
-def _check_pretrain(model, g, batch, loss_tol):
+LOSS_KEYS = ("mlm_loss", "nce_loss", "rank_t_tm_loss", "v_nce_loss", "rank_v_vm_loss", "loss")
+EMB_NAMES = ("v", "t", "tm", "vmf", "vm", "tmf")          # gather_stacked order: V_e, T_e, T_m, M_Vmf, V_m, M_Tmf
+
+
+def _eager_bf16_floor(sd, g, batch, ocfg):
+    """The reference's algorithm in PyTorch eager under torch.autocast(bfloat16) on the same GPU (the oracle restatement
+    on cuda: cuBLAS bf16 GEMMs, fp32 softmax / LayerNorm, fp32 master weights) measured against the same fp32 golden: the
+    error any bf16 implementation of this network carries, i.e. the yardstick for the entries below."""
+    st = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    b = {k: v.cuda() for k, v in batch.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        losses, aux = O.pretrain_forward(st, b, ocfg)
+        total = O.total_loss(losses)
+    total.backward()
+    out = {"loss": {}, "emb": {}, "grad": {}}
+    for k in LOSS_KEYS:
+        v = float(total) if k == "loss" else float(losses[k])
+        ref = float(g[f"loss::{k}"])
+        out["loss"][k] = abs(v - ref) / max(1.0, abs(ref))
+    if "emb::v" in g.files:
+        for n, a in zip(EMB_NAMES, ("v_emb", "t_emb", "tm_emb", "m_vmf", "vm_emb", "m_tmf")):
+            out["emb"][n] = rel(aux[a], g[f"emb::{n}"])
+    for k in g.files:
+        name = k.split("::")[-1]
+        if k.startswith("grad::"):
+            out["grad"][name] = rel(st[name].grad, g[k])
+        elif k.startswith("gradsample::"):
+            out["grad"][name] = rel(st[name].grad.reshape(-1).cpu()[torch.from_numpy(g["gradidx::" + name])], g[k])
+    return out
+
+
+def _check_pretrain(model, g, batch, tag, sd=None, ocfg=None):
+    """One pre-train step against the executed reference (fp32 golden).  North-star tolerances, asserted where bf16 can
+    meet them: total loss within 1e-3 (relative to max(1, |ref|)); the six alignment embeddings <= 2e-2 relative and
+    cosine >= 0.999.  The individual loss entries (cosine / 0.05 logits amplify embedding noise 20x) and the parameter
+    gradients (~100 bf16 layers deep) are bounded by fixed documented limits AND by 2x the error of the reference's own
+    algorithm run in PyTorch eager under autocast(bf16) on this GPU (`_eager_bf16_floor`), measured in the same test.
+    Identical set of grad-less parameters.  All achieved errors go to gpurun_out/parity_errors.json."""
+    import json
+    from clover_b200 import gather
+    from conftest import record_parity
     kw = {k: batch[k].cuda() for k in ("token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")}
-    losses = model(batch["imgs"].cuda(), batch["label"].cuda(), return_loss=True, **kw)
+    embs = []
+    orig = gather.gather_stacked
+
+    def spy(ts):
+        embs.extend(t.detach().float().cpu() for t in ts)
+        return orig(ts)
+    import clover_b200.recognizers as R
+    R.gather_stacked = spy
+    try:
+        losses = model(batch["imgs"].cuda(), batch["label"].cuda(), return_loss=True, **kw)
+    finally:
+        R.gather_stacked = orig
     total, log_vars = model._parse_losses(losses)
     total.backward()
-    for k in ("mlm_loss", "nce_loss", "rank_t_tm_loss", "v_nce_loss", "rank_v_vm_loss", "loss"):
+    rec = {"loss": {}, "emb": {}, "grad": {}}
+    for k in LOSS_KEYS:
         ref = float(g[f"loss::{k}"])
-        assert abs(log_vars[k] - ref) <= loss_tol * max(1.0, abs(ref)), (k, log_vars[k], ref)
+        rec["loss"][k] = {"got": log_vars[k], "ref": ref, "abs": abs(log_vars[k] - ref), "rel": abs(log_vars[k] - ref) / max(1.0, abs(ref))}
+    if "emb::v" in g.files:
+        for n, e in zip(EMB_NAMES, embs):
+            rec["emb"][n] = {"rel": rel(e, g[f"emb::{n}"]), "cos": cos(e, g[f"emb::{n}"])}
     params = dict(model.named_parameters())
-    worst = {}
     for k in g.files:
         if k.startswith("grad::"):
             name = k.split("::")[1]
-            worst[name] = (rel(params[name].grad, g[k]), cos(params[name].grad, g[k]))
+            rec["grad"][name] = {"rel": rel(params[name].grad, g[k]), "cos": cos(params[name].grad, g[k])}
         if k.startswith("gradsample::"):
             name = k.split("::")[1]
             idx = torch.from_numpy(g["gradidx::" + name])
             got = params[name].grad.reshape(-1).cpu()[idx]
-            worst[name] = (rel(got, g[k]), cos(got, g[k]))
-    bad = {n: v for n, v in worst.items() if v[1] < 0.99}
+            rec["grad"][name] = {"rel": rel(got, g[k]), "cos": cos(got, g[k])}
+    rec["worst"] = {"loss_rel": max(v["rel"] for v in rec["loss"].values()),
+                    "emb_rel": max([v["rel"] for v in rec["emb"].values()] or [0.0]),
+                    "emb_cos": min([v["cos"] for v in rec["emb"].values()] or [1.0]),
+                    "grad_rel": max(v["rel"] for v in rec["grad"].values()),
+                    "grad_cos": min(v["cos"] for v in rec["grad"].values())}
+    floor = _eager_bf16_floor(sd, g, batch, ocfg) if sd is not None else None
+    if floor is not None:
+        rec["eager_bf16_floor"] = floor
+        rec["worst"]["floor_loss_rel"] = max(floor["loss"].values())
+        rec["worst"]["floor_grad_rel"] = max(floor["grad"].values())
+        rec["worst"]["floor_emb_rel"] = max(list(floor["emb"].values()) or [0.0])
+    record_parity(tag, rec)
+    print(tag, json.dumps(rec["worst"]))
+    assert rec["loss"]["loss"]["rel"] <= LOSS_TOL, rec["loss"]["loss"]                         # north-star: loss within 1e-3
+    bad = {k: v for k, v in rec["emb"].items() if v["cos"] < 0.999 or v["rel"] > TOL}          # north-star
     assert not bad, bad
-    import json
+    bad = {k: v for k, v in rec["loss"].items() if v["rel"] > LOSS_ENTRY_TOL}
+    assert not bad, bad
+    bad = {k: v for k, v in rec["grad"].items() if v["rel"] > GRAD_LIMIT or v["cos"] < 0.997}
+    assert not bad, bad
+    if floor is not None:                          # never worse than 2x eager bf16 of the reference algorithm (+ noise slack)
+        bad = {k: (v["rel"], floor["loss"][k]) for k, v in rec["loss"].items() if v["rel"] > 2 * floor["loss"][k] + 1e-3}
+        assert not bad, bad
+        bad = {k: (v["rel"], floor["grad"][k]) for k, v in rec["grad"].items() if v["rel"] > 2 * floor["grad"][k] + 5e-3}
+        assert not bad, bad
     nograd = set(json.loads(str(g["nograd_keys"])))
     ours = {n for n, p in params.items() if p.grad is None}
     assert ours == nograd, (ours ^ nograd)
-    return worst
+    return rec
 
 
 def test_pretrain_step_tiny_vs_reference_golden(cb, golden_dir):
     g = _g(golden_dir, "pretrain_tiny.npz")
     bert = dict(num_attention_heads=2, intermediate_size=256, max_position_embeddings=64, vocab_size=1000)
     m = _pretrain_model(cb, 32, (2, 2), (1, 2), 64, 128, 1000, 2, 2, 2, bert)
-    load_synth(m, 50)
+    sd = load_synth(m, 50)
     batch = make_batch(3, frames=4, L=16, seed=51, size=56, vocab=1000)
-    _check_pretrain(m, g, batch, 2e-2)
+    _check_pretrain(m, g, batch, "pretrain_tiny", sd,
+                    dict(depths=[2, 2], num_heads=[1, 2], text_layers=2, fusion_layers=2, bert_heads=2, vocab=1000))
 
 
 def test_pretrain_step_c1_swin_t_vs_reference_golden(cb, golden_dir):
     """BASELINE config 1 shapes (Swin-T + BERT-base + 3-layer fusion, B=2, 8x224x224, L=32) on the B200."""
     g = _g(golden_dir, "pretrain_c1.npz")
     m = _pretrain_model(cb, 96, (2, 2, 6, 2), (3, 6, 12, 24), 768, 768, 30522, 12, 3, 4, {})
-    load_synth(m, 60)
+    sd = load_synth(m, 60)
     batch = make_batch(2, frames=8, L=32, seed=61, size=224, vocab=30522)
-    worst = _check_pretrain(m, g, batch, 2e-2)
-    print({k: (round(v[0], 4), round(v[1], 5)) for k, v in worst.items()})
+    _check_pretrain(m, g, batch, "pretrain_c1_swin_t", sd,
+                    dict(depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], text_layers=12, fusion_layers=3, bert_heads=12, vocab=30522))
+
+
+def test_pretrain_step_swin_b_vs_reference_golden(cb, golden_dir):
+    """The headline model (BASELINE c3: Video Swin-B 128 / 2-2-18-2 / heads 4-8-16-32 + BERT-base + 3-layer fusion) at
+    B = 2, 8x224x224, L = 32 against the executed reference."""
+    g = _g(golden_dir, "pretrain_swinb.npz")
+    m = _pretrain_model(cb, 128, (2, 2, 18, 2), (4, 8, 16, 32), 1024, 768, 30522, 12, 3, 4, {})
+    sd = load_synth(m, 62)
+    batch = make_batch(2, frames=8, L=32, seed=63, size=224, vocab=30522)
+    _check_pretrain(m, g, batch, "pretrain_swin_b", sd,
+                    dict(depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], text_layers=12, fusion_layers=3, bert_heads=12, vocab=30522))
 
 
 # ------------------------------------------------------------------------------------------------ fine-tune (a20)
@@ -239,11 +331,14 @@ def _finetune_model(cb, task, **over):
     return cb.build_model(finetune_cfg(task, num_labels=50, **dict(FT_SMALL, **over))).cuda()
 
 
-@pytest.mark.parametrize("tag,task", [("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc")])
+@pytest.mark.parametrize("tag,task", [("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc"), ("fib", "FIB")])
 def test_finetune_vs_reference_golden(cb, golden_dir, tag, task):
     """CloverFinetune (multimodal_transformer_finetune.py:59-197) on 16-frame clips (T = 8 -> the full (8,7,7) window,
-    N = 392, the BASELINE c4 / c5 shape) against the executed reference: train loss, gradients, forward_test outputs."""
+    N = 392, the BASELINE c4 / c5 shape) against the executed reference: train loss, gradients, forward_test outputs.
+    'fib' is configs/exp_local/finetune_lsmdc_FIB.py: use_text_cls=False (all-cls token), answer read at the [MASK] token."""
+    import json
     from clover_b200.synthetic import make_finetune_batch
+    from conftest import record_parity
     g = _g(golden_dir, f"finetune_{tag}.npz")
     m = _finetune_model(cb, task)
     load_synth(m, 70)
@@ -255,26 +350,35 @@ def test_finetune_vs_reference_golden(cb, golden_dir, tag, task):
     total.backward()
     key = "retrieval_nce_loss" if task == "retrieval" else "qa_loss"
     ref = float(g[f"loss::{key}"])
-    assert abs(log_vars[key] - ref) <= 2e-2 * max(1.0, abs(ref)), (log_vars[key], ref)
+    rec = {"loss": {"got": log_vars[key], "ref": ref, "rel": abs(log_vars[key] - ref) / max(1.0, abs(ref))}, "grad": {}}
     params = dict(m.named_parameters())
-    worst = {}
     for k in g.files:
         name = k.split("::")[-1]
         if k.startswith("grad::"):
-            worst[name] = cos(params[name].grad, g[k])
+            rec["grad"][name] = {"rel": rel(params[name].grad, g[k]), "cos": cos(params[name].grad, g[k])}
         elif k.startswith("gradsample::"):
-            worst[name] = cos(params[name].grad.reshape(-1).cpu()[torch.from_numpy(g["gradidx::" + name])], g[k])
-    assert len(worst) >= 8 and min(worst.values()) > 0.99, worst
+            got = params[name].grad.reshape(-1).cpu()[torch.from_numpy(g["gradidx::" + name])]
+            rec["grad"][name] = {"rel": rel(got, g[k]), "cos": cos(got, g[k])}
+    nograd = set(json.loads(str(g["nograd_keys"])))
+    assert {n for n, p in params.items() if p.grad is None} == nograd
     m.eval()
     with torch.no_grad():
         res = m(batch["imgs"].cuda(), None, return_loss=False, **kw)
     if task == "retrieval":
-        assert cos(res[0], g["test::visual_emb"]) > 0.999 and cos(res[1], g["test::text_emb"]) > 0.999
-        assert rel(res[0], g["test::visual_emb"]) < TOL and rel(res[1], g["test::text_emb"]) < TOL
+        rec["test"] = {"visual_emb": {"rel": rel(res[0], g["test::visual_emb"]), "cos": cos(res[0], g["test::visual_emb"])},
+                       "text_emb": {"rel": rel(res[1], g["test::text_emb"]), "cos": cos(res[1], g["test::text_emb"])}}
     else:
-        assert rel(res["result"], g["test::result"]) < TOL and res["result"].dtype == torch.float32
+        assert res["result"].dtype == torch.float32
         rows = torch.from_numpy(g["test::attention_rows"])
-        assert rel(res["attention"][:, rows.cuda()], g["test::attention_sample"]) < TOL
+        rec["test"] = {"result": {"rel": rel(res["result"], g["test::result"])},
+                       "attention": {"rel": rel(res["attention"][:, rows.cuda()], g["test::attention_sample"])}}
+    record_parity(f"finetune_{tag}", rec)
+    print(tag, json.dumps(rec["loss"]), {n.split(".")[-2] + "." + n.split(".")[-1]: (round(v["rel"], 4), round(v["cos"], 5)) for n, v in rec["grad"].items()})
+    assert rec["loss"]["rel"] <= LOSS_TOL, rec["loss"]
+    assert len(rec["grad"]) >= 8
+    bad = {n: v for n, v in rec["grad"].items() if v["rel"] > GRAD_TOL or v["cos"] < 0.999}
+    assert not bad, bad
+    assert all(v["rel"] < TOL and v.get("cos", 1.0) > 0.999 for v in rec["test"].values()), rec["test"]
 
 
 # ------------------------------------------------------------------------------------------------ training-mode regularisers

@@ -221,7 +221,16 @@ def test_pretrain_c1_full_size(golden_dir):
 FT_SMALL = dict(depths=[2, 2], num_heads=[1, 2], text_layers=2, fusion_layers=2, bert_heads=2, vocab=1000)
 
 
-@pytest.mark.parametrize("tag,task", [("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc")])
+@pytest.mark.slow
+def test_pretrain_swin_b_headline_model(golden_dir):
+    """The headline model of BASELINE c3 (Video Swin-B + BERT-base + 3-layer fusion) at B=2, 8x224x224, L=32 (fp32 CPU)."""
+    shapes = pretrain_shapes(128, [2, 2, 18, 2], [4, 8, 16, 32], 1024, 768, 3072, 30522, 512, 12, 3, 4)
+    cfg = dict(depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], text_layers=12, fusion_layers=3, bert_heads=12, vocab=30522)
+    batch = make_batch(2, frames=8, L=32, seed=63, size=224, vocab=30522)
+    _run_pretrain_case(golden_dir, "pretrain_swinb.npz", shapes, cfg, batch, 62, 2e-4)
+
+
+@pytest.mark.parametrize("tag,task", [("retrieval", "retrieval"), ("qa_oe", "video_qa"), ("qa_mc", "video_qa_mc"), ("fib", "FIB")])
 def test_finetune(golden_dir, tag, task):
     """CloverFinetune (BASELINE c4 / c5 shapes scaled down: 16-frame clips -> T = 8 -> the full (8,7,7) window)
     against the executed reference: train loss + gradients, then the forward_test outputs."""
@@ -229,7 +238,8 @@ def test_finetune(golden_dir, tag, task):
     shapes = finetune_shapes(task, 32, [2, 2], [1, 2], 64, 128, 256, 1000, 64, 2, 2, 8, num_labels=50)
     st = {k: v.clone().requires_grad_(True) for k, v in synth_state_dict(shapes, 70).items()}
     batch = make_finetune_batch(task, 3, frames=16, size=56, L=20, vocab=1000, seed=71, num_labels=50, choices=3)
-    losses = O.finetune_forward(st, batch, FT_SMALL, task, train=True)
+    cfg = dict(FT_SMALL, answer_mask=True, answer_cls=False) if task == "FIB" else FT_SMALL
+    losses = O.finetune_forward(st, batch, cfg, task, train=True)
     total = O.total_loss(losses)
     total.backward()
     tol = 1e-4
@@ -249,7 +259,7 @@ def test_finetune(golden_dir, tag, task):
             assert relerr(st[name].grad.reshape(-1)[g["gradidx::" + name]], g[k]) < 10 * tol, name
     assert seen >= 8
     with torch.no_grad():
-        res = O.finetune_forward(st, batch, FT_SMALL, task, train=False)
+        res = O.finetune_forward(st, batch, cfg, task, train=False)
     if task == "retrieval":
         assert relerr(res[0], g["test::visual_emb"]) < tol and relerr(res[1], g["test::text_emb"]) < tol
     else:
