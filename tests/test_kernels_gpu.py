@@ -709,10 +709,11 @@ def test_fused_adamw_vs_torch(ops):
     assert all(set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 4.0 for st in sd["state"].values())
     ours2 = [torch.nn.Parameter(a.detach().clone()) for a in ours]
     o3 = FusedAdamW(groups(ours2), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=2.0)
-    o3.load_state_dict(sd)
+    import copy
+    o3.load_state_dict(copy.deepcopy(sd))                     # (load_state_dict keeps same-device tensors by reference)
     ref2 = [torch.nn.Parameter(b.detach().clone()) for b in ref]
     o4 = torch.optim.AdamW(groups(ref2), betas=(0.9, 0.98), eps=1e-8)
-    o4.load_state_dict(sd)                                    # our state loads into the reference optimizer as is
+    o4.load_state_dict(copy.deepcopy(sd))                     # our state loads into the reference optimizer as is
     for it in range(2):
         for a, b in zip(ours2, ref2):
             g = torch.randn(a.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(200 + it))
