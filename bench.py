@@ -546,7 +546,11 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg (N = 1, c3)")
     ap.add_argument("--parity-config", action="store_true",
                     help="zero dropout / drop-path (the configuration of the parity tests) instead of the shipped training rates")
+    ap.add_argument("--lib", default=None, help="developer A/B runs: another build of libclover_b200.so to load")
     args = ap.parse_args()
+    if args.lib:
+        from clover_b200 import _lib
+        _lib.set_library(args.lib)
     if args.impl == "reference":
         run_reference(args)
     else:

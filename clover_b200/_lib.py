@@ -112,6 +112,9 @@ SIGNATURES = {
     "clv_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_fwd_tc": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
     "clv_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp, c_vp]),
+    "clv_attention_tc64_supported": (C.c_int, [C.c_int]),
+    "clv_attention_fwd_tc64": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp]),
+    "clv_attention_bwd_tc64": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp, c_vp, c_vp, C.c_float, c_vp, c_vp]),
     "clv_attention_probs_mean": (C.c_int, [C.POINTER(AttnDesc), c_vp, c_vp, c_vp]),
     "clv_dropout": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_ll, C.c_float, C.c_ulonglong, C.c_ulonglong, c_vp]),
     "clv_keep_mask": (C.c_int, [c_vp, c_ll, C.c_float, C.c_ulonglong, C.c_ulonglong, c_vp]),
@@ -147,6 +150,15 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+def set_library(path):
+    """Developer tooling (A/B runs of two builds on the same box: bench.py --lib): point the loader at another build of
+    libclover_b200.so BEFORE the first call.  Not used by the product path."""
+    global LIB_PATH, _lib
+    if _lib is not None:
+        raise RuntimeError("set_library must be called before the library is first loaded")
+    LIB_PATH = os.path.abspath(path)
 
 
 def load():

@@ -54,6 +54,7 @@ PROFILE_SHAPES = os.environ.get("CLOVER_B200_PROFILE_SHAPES", "0") == "1"       
 # Tests flip these module attributes to compare the kernels against each other.
 USE_TC_ATTENTION = True
 USE_W7_ATTENTION = True
+USE_TC64_ATTENTION = True      # head_dim-64 BERT / fusion attention on tcgen05 (attention_h64.cu); False: the mma.sync kernels
 
 
 def set_tunable(name, value):
@@ -419,6 +420,9 @@ def attention_fwd(qkv, batch, seq, heads, hd, out, lse, w7=None, **bias):
                    "clv_attention_w7_fwd")
     elif hd == 32 and bias.get("key_mask") is None and bias.get("drop") is None and 33 <= seq <= 416 and USE_TC_ATTENTION:
         _lib.check(lib.clv_attention_fwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd_tc")
+    elif hd == 64 and USE_TC64_ATTENTION and bias.get("bias_table") is None and bias.get("region") is None and \
+            lib.clv_attention_tc64_supported(seq):
+        _lib.check(lib.clv_attention_fwd_tc64(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd_tc64")
     else:
         _lib.check(lib.clv_attention_fwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(lse), _stream()), "clv_attention_fwd")
     _prof_close(ev, ("attn_fwd_hd%d" % hd) + (f" b={batch} n={seq} h={heads}" if PROFILE_SHAPES else ""), 4.0 * batch * heads * seq * seq * hd, 2.0 * batch * seq * heads * hd * 4)
@@ -444,6 +448,11 @@ def attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, q_scale, dbi
         ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
         _lib.check(lib.clv_attention_bwd_tc(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
                                             float(q_scale), _ptr(dbias_table), _ptr(ws), _stream()), "clv_attention_bwd_tc")
+    elif hd == 64 and USE_TC64_ATTENTION and bias.get("bias_table") is None and bias.get("region") is None and \
+            dbias_table is None and lib.clv_attention_tc64_supported(seq):
+        ws = torch.empty(batch * heads * seq, dtype=F32, device=qkv.device)
+        _lib.check(lib.clv_attention_bwd_tc64(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                              float(q_scale), _ptr(ws), _stream()), "clv_attention_bwd_tc64")
     else:
         ws = torch.empty(batch * heads * seq, dtype=F32, device=qkv.device)
         _lib.check(lib.clv_attention_bwd(C.byref(d), _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),

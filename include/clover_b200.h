@@ -182,6 +182,14 @@ int clv_attention_fwd_tc(const clv_attn_desc_t* desc, const void* qkv, void* out
 int clv_attention_bwd(const clv_attn_desc_t* desc, const void* qkv, const void* out, const void* dout,
                       const float* lse, void* dqkv, float q_scale, float* dbias_table,
                       float* dsum_workspace /* fp32 [batch*heads*seq] */, void* stream);
+/* The BERT / fusion attention (head_dim 64, optional key_mask, optional attention-probability dropout; no bias table / region)
+ * on tcgen05 / TMEM / TMA: HF BertSelfAttention (transformers 4.6.1) at the reference's call sites bert_from_hugface.py:30 and
+ * cross_transformer.py:109-110.  Same contract as clv_attention_fwd / clv_attention_bwd for 1 <= seq <= 448
+ * (clv_attention_tc64_supported); the backward recomputes the probabilities in a dK|dV and a dQ kernel. */
+int clv_attention_tc64_supported(int seq);
+int clv_attention_fwd_tc64(const clv_attn_desc_t* desc, const void* qkv, void* out, float* lse, void* stream);
+int clv_attention_bwd_tc64(const clv_attn_desc_t* desc, const void* qkv, const void* out, const void* dout, const float* lse,
+                           void* dqkv, float q_scale, float* dsum_workspace /* fp32 [batch*heads*seq] */, void* stream);
 /* probs_mean[b, i, j] = mean over heads of softmax_j(q_i . k_j + bias/mask terms): the `attentions[-1].mean(dim=1)`
  * that CloverFinetune.forward_test returns for video QA (multimodal_transformer_finetune.py:192; HF BertEncoder
  * output_attentions).  Evaluation only (no dropout).  out: fp32 [batch, seq, seq]. */

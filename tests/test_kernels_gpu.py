@@ -473,6 +473,51 @@ def test_bert_attention_core(ops, seq):
     assert rel(dqkv, g.view(batch * seq, -1)) < 2e-2
 
 
+@pytest.mark.parametrize("seq,batch,heads,p", [(228, 3, 2, 0.1), (40, 5, 12, 0.1), (432, 2, 3, 0.25), (1, 2, 2, 0.0),
+                                               (33, 2, 1, 0.0), (448, 1, 2, 0.0), (228, 30, 12, 0.0)])
+def test_bert_attention_tc64_mask_dropout_and_legacy_agreement(ops, seq, batch, heads, p):
+    """attention_h64.cu (tcgen05, head_dim 64): key mask + attention-probability dropout against the fp32 reference that
+    applies the SAME keep mask (clv_keep_mask stream, index (b, h, i, j)), and against the mma.sync kernels it replaces;
+    30 x 12 x two query tiles = 720 units exercises the persistent loop (more units than resident CTAs)."""
+    hd = 64
+    qkv, dout = _attn_inputs(batch, seq, heads, hd, 77)
+    keep = torch.ones(batch, seq)
+    for b in range(batch):
+        keep[b, max(1, seq - 1 - (b * 7) % max(1, seq // 2)):] = 0 if seq > 2 else 1
+    km = ((1 - keep) * -10000.0).cuda()
+    drop = (p, 1234567, 96) if p > 0 else None
+    out = torch.empty(batch * seq, heads * hd, dtype=BF16, device="cuda")
+    lse = torch.empty(batch, heads, seq, dtype=F32, device="cuda")
+    assert ops.USE_TC64_ATTENTION
+    ops.attention_fwd(qkv, batch, seq, heads, hd, out, lse, key_mask=km, drop=drop)
+    # fp32 reference with the identical keep mask
+    x = qkv.float().cpu().requires_grad_(True)
+    q, k, v = x.view(batch, seq, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    s_ = q @ k.transpose(-1, -2) + km.cpu()[:, None, None, :]
+    pr = torch.softmax(s_, -1)
+    if p > 0:
+        kmask = ops.keep_mask(batch * heads * seq * seq, p, drop[1], drop[2], "cuda").cpu().view(batch, heads, seq, seq).float()
+        pr = pr * kmask / (1.0 - p)
+    o_ref = (pr @ v).transpose(1, 2).reshape(batch * seq, heads * hd)
+    assert rel(out, o_ref.detach()) < 1e-2
+    assert rel(lse, torch.logsumexp(s_, -1).detach()) < 1e-4
+    (o_ref * dout.float().cpu()).sum().backward()
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(qkv, out, dout, lse, batch, seq, heads, hd, dqkv, 0.125, key_mask=km, drop=drop)
+    g = x.grad.clone().view(batch * seq, 3, heads * hd)
+    g[:, 0] *= 0.125
+    assert rel(dqkv, g.view(batch * seq, -1)) < 2e-2
+    # the legacy mma.sync kernels on the same inputs (same lse convention, same dropout stream)
+    ops.USE_TC64_ATTENTION = False
+    try:
+        out2 = torch.empty_like(out); lse2 = torch.empty_like(lse); dq2 = torch.empty_like(dqkv)
+        ops.attention_fwd(qkv, batch, seq, heads, hd, out2, lse2, key_mask=km, drop=drop)
+        ops.attention_bwd(qkv, out2, dout, lse2, batch, seq, heads, hd, dq2, 0.125, key_mask=km, drop=drop)
+    finally:
+        ops.USE_TC64_ATTENTION = True
+    assert rel(out, out2.float()) < 6e-3 and rel(lse, lse2) < 1e-5 and rel(dqkv, dq2.float()) < 1.5e-2
+
+
 # ------------------------------------------------------------------------------------------------ elementwise
 def test_cast_patchify_colsum_affine_scatter(ops):
     x = rnd(4096, seed=1)
