@@ -108,7 +108,7 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   const uint32_t nst = (uint32_t)a.stages;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
         const int t = (int)(u % a.n_tiles);
@@ -129,7 +129,7 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_pv = make_idesc_bf16(128, H64_HD, 0, 1);
       const uint32_t idesc_s0 = make_idesc_bf16(128, a.n0, 0, 0);
       const uint32_t idesc_s1 = make_idesc_bf16(128, a.n1 > 0 ? a.n1 : 16, 0, 0);
@@ -312,7 +312,7 @@ attn64_bwd_kernel(const __grid_constant__ CUtensorMap tm_tile, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0, cc = 0;
       for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
         const int t = (int)(u % a.n_tiles);
@@ -338,7 +338,7 @@ attn64_bwd_kernel(const __grid_constant__ CUtensorMap tm_tile, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_s = make_idesc_bf16(128, H64_CH, 0, 0);        // scores: both operands K-major
       const uint32_t idesc_acc = make_idesc_bf16(128, H64_HD, 0, 1);      // accumulators: A from TMEM, B MN-major
       uint32_t it = 0, cc = 0;

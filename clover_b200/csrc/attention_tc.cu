@@ -83,7 +83,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
         const int t = (int)(u % a.n_qt);
@@ -105,7 +105,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_pv = make_idesc_bf16(128, TC_HD, 0, 1);
       // S-MMA column chunks (N <= 256, multiple of 16)
       const int n0 = a.nk <= 256 ? a.nk : ((a.nk / 2 + 15) & ~15);
@@ -393,7 +393,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   const uint32_t col_dv = NQ - TC_HD, col_dp = NQ, col_dk = 2 * NQ - TC_HD, col_dq = 2 * NQ;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0, tt = 0;
       for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
         const int b = (int)(u % a.batch), h = (int)(u / a.batch);
@@ -416,7 +416,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_st = make_idesc_bf16(128, NQ, 0, 0);
       const uint32_t idesc_ts = make_idesc_bf16(128, TC_HD, 0, 1);
       const uint32_t idesc_dq = make_idesc_bf16(128, TC_HD, 1, 1);

@@ -185,7 +185,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   w7_unit_range(a.units, u_begin, u_end);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int t = (int)(u % a.n_qt);
@@ -216,7 +216,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_pv = make_idesc_bf16(128, W7_HD, 0, 1);
       const uint32_t idesc_s0 = make_idesc_bf16(128, a.n0, 0, 0);
       const uint32_t idesc_s1 = make_idesc_bf16(128, n1 > 0 ? n1 : 16, 0, 0);
@@ -515,7 +515,7 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
   w7_unit_range(a.units, u_begin, u_end);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0, tt = 0;
       for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int b = (int)(u % a.batch), h = (int)(u / a.batch);
@@ -541,7 +541,7 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_st = make_idesc_bf16(128, NQ, 0, 0);
       const uint32_t idesc_ts = make_idesc_bf16(128, W7_HD, 0, 1);
       const uint32_t idesc_dq = make_idesc_bf16(128, W7_HD, 1, 1);
@@ -922,7 +922,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
   w7_unit_range(a.units, u_begin, u_end);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0, tt = 0;
       for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int qh = (int)(u % NH);
@@ -950,7 +950,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_ts = make_idesc_bf16(128, W7_HD, 0, 1);
       const uint32_t idesc_dq = make_idesc_bf16(128, W7_HD, 1, 1);
       const uint32_t idesc_c96 = make_idesc_bf16(128, 96, 0, 0), idesc_c16 = make_idesc_bf16(128, 16, 0, 0);
