@@ -69,6 +69,7 @@ def workload_config(clips, n_gpus, regularisers=True, workload="c3"):
                         "all zero (the parity configuration; --parity-config)",
         "optimizer": f"clover_b200.optim.FusedAdamW (one multi-tensor kernel: AdamW on fp32 masters + grad-norm clip {w['grad_clip']:g} + "
                      "finite check + bf16 weight refresh), paramwise weight decay of the shipped config, inside the timed region",
+        "grad_allreduce": "DDP buckets, bf16-compressed (the reference all-reduces half-precision gradients)" if n_gpus > 1 else "none (1 GPU)",
         "l2_policy": f"per-step inputs ({mb:.0f} MB of clips) and activations (tens of GB) far exceed the 126 MB L2",
     }
 
@@ -319,6 +320,11 @@ def run_ours(args):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
                                                         gradient_as_bucket_view=True, bucket_cap_mb=100)
+        if not args.fp32_allreduce:
+            # the reference all-reduces HALF-precision gradients (model.half() + allreduce_grads, core/hooks/
+            # mmcv_Fp16OptimizerHook.py:120-122): 0.55 GB per step over NVLink instead of 1.1 GB; masters / Adam stay fp32
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     from clover_b200.optim import FusedAdamW, param_groups_from_cfg
     if wl == "c3":       # configs/exp_local/pretrain_webvid_cc3m.py:129-137
         paramwise = dict(norm_decay_mult=0.0, bias_decay_mult=0.0, custom_keys={"absolute_pos_embed": dict(decay_mult=0.0),
@@ -542,6 +548,7 @@ def main():
                     help="BASELINE.json config: c3 pre-train step (the headline, default), c4 retrieval fine-tune, c5 video-QA fine-tune")
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: 64 for c3, 16 for c4 / c5 = the shipped configs)")
     ap.add_argument("--kernels-only", action="store_true", help="run warm-up + timed steps and exit (short command for ncu captures)")
+    ap.add_argument("--fp32-allreduce", action="store_true", help="N > 1: all-reduce fp32 gradient buckets instead of bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg (N = 1, c3)")
     ap.add_argument("--parity-config", action="store_true",

@@ -795,6 +795,25 @@ class NceRankFn(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class GatherRowsFn(torch.autograd.Function):
+    """y = x[rows] for a 2-D x and UNIQUE int64 row indices (the `mlm_prediction_score[mlm_idx]` row selection of
+    multimodal_transformer_pretrain.py:137-139, moved in front of the MLM head); backward scatters into zeros.
+    Pure data movement -- no arithmetic."""
+
+    @staticmethod
+    def forward(ctx, x, rows):
+        ctx.save_for_backward(rows)
+        ctx.n = x.shape[0]
+        return x.index_select(0, rows)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (rows,) = ctx.saved_tensors
+        dx = torch.zeros(ctx.n, dy.shape[1], dtype=dy.dtype, device=dy.device)
+        dx.index_copy_(0, rows, dy)
+        return dx, None
+
+
 class VocabFocalFn(torch.autograd.Function):
     """decoder GEMM (hidden -> vocab) + softmax focal / CE over rows whose label != ignore_index.
     h bf16 [rows, H]; decoder weight fp32 [V, H] (padded to a multiple of 8 rows in the bf16 cache)."""

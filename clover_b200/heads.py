@@ -194,12 +194,26 @@ class MLMHead(nn.Module):
         y = _linear_any_n(x, d)                      # the shipped vocabulary (30522) is not a multiple of 8: padded weight cache
         return y.reshape(*shp[:-1], V)
 
-    def focal_loss(self, sequence_output, mlm_label, gamma=2.0, ignore_index=-100):
-        """decoder + row selection (pretrain.py:137-139) + SoftmaxFocalLossMultiClass in one pass."""
+    def focal_loss(self, sequence_output, mlm_label, gamma=2.0, ignore_index=-100, rows=None):
+        """Row selection (pretrain.py:137-139) + transform + decoder + SoftmaxFocalLossMultiClass.  The reference runs the
+        head on all B*L rows and indexes the (B*L, 30522) fp32 logits afterwards; here the masked rows are selected FIRST
+        (`rows`: their int64 indices, computed once per step by the recogniser), so the transform, the vocabulary GEMM, its two
+        backward GEMMs and the logits tensor shrink to the ~20-30 % of the tokens that carry a label -- the same arithmetic on
+        the same rows (LayerNorm / GELU / dense are row-wise).  rows=None keeps every row (labels == ignore_index are skipped
+        inside the loss kernel)."""
         shp = sequence_output.shape
-        x = self.transform(sequence_output.reshape(-1, shp[-1]))
+        h = sequence_output.reshape(-1, shp[-1])
+        lab = mlm_label.reshape(-1)
+        if rows is not None and rows.numel() > 0:
+            h = Fn.GatherRowsFn.apply(h.contiguous(), rows)
+            lab = lab.index_select(0, rows)
+            pad = (-h.shape[0]) % 8                      # the GEMM tiles want a multiple of 8 rows: pad with ignored rows
+            if pad:
+                h = torch.cat([h, h.new_zeros(pad, h.shape[1])], 0)
+                lab = torch.cat([lab, lab.new_full((pad,), ignore_index)], 0)
+        x = self.transform(h)
         d = self.predictions.decoder
-        return Fn.VocabFocalFn.apply(x, d.weight, d.bias, mlm_label.reshape(-1), gamma, ignore_index)
+        return Fn.VocabFocalFn.apply(x, d.weight, d.bias, lab, gamma, ignore_index)
 
 
 class ITMHead(nn.Module):

@@ -135,6 +135,12 @@ class CloverPretrain(BaseRecognizer):
     def forward_train(self, imgs, label, token_ids=None, segment_ids=None, input_mask=None, mlm_label=None,
                       dvae_imgs=None, v_token_mask=None, hog_features=None, img_metas=None, **kwargs):
         imgs = _flat(imgs)                                                         # :81
+        # rows that carry an MLM label (:137-139): their indices are needed to shrink the MLM head to those rows.  The one
+        # device -> host size read happens HERE, at the very start of the step (the labels are an input), not in the middle
+        # of the forward where it would drain the launch queue.
+        mlm_rows = None
+        if mlm_label is not None and self.select_mlm_rows:
+            mlm_rows = torch.nonzero(mlm_label.reshape(-1) != -100).squeeze(1)
         Fn.zero_arena_begin(imgs.device)
         if self.from_scratch:
             imgs = imgs / 255.0
@@ -148,7 +154,7 @@ class CloverPretrain(BaseRecognizer):
         Bt, L = token_ids.shape
         H = self.multimodal_backbone.hidden_size
         if self.batch_passes and v_token_mask is not None and imgs.shape[0] == Bt:
-            return self._forward_train_batched(imgs, token_ids, text_mask, mlm_label, v_token_mask, Bt, L, H)
+            return self._forward_train_batched(imgs, token_ids, text_mask, mlm_label, v_token_mask, Bt, L, H, mlm_rows)
         # ---- clean video + clean text ---------------------------------------------------- :91-102
         v_tok, (B, T, h, w) = self.backbone.forward_tokens(imgs)                    # fp32 [B*T*hw, C]
         S = h * w
@@ -167,7 +173,7 @@ class CloverPretrain(BaseRecognizer):
         losses = dict()
         # ---- MLM: decoder + row selection + focal loss fused ------------------------------- :129-143
         gamma = getattr(self.mlm_loss_func, "gamma", 0.0) if self.mlm_loss_func is not None else 0.0
-        losses["mlm_loss"] = self.mlm_head.focal_loss(t_last.reshape(B * L, H), mlm_label.reshape(-1), gamma=gamma)
+        losses["mlm_loss"] = self.mlm_head.focal_loss(t_last.reshape(B * L, H), mlm_label.reshape(-1), gamma=gamma, rows=mlm_rows)
         # ---- tri-modal alignment ------------------------------------------------------------ :147-169
         m_vmf = self.mlm_ssl_V_head(v_f[:, vs])                                     # fused text-CLS slot, (B, H)
         tm_emb = self.ssl_head.forward_text(T_m)
@@ -188,8 +194,10 @@ class CloverPretrain(BaseRecognizer):
     # fusion pairs (masked video, clean text) ; (clean video, masked text) line up without any reshuffle.  Same
     # arithmetic per sample, half the launches, and every parameter gets ONE gradient instead of two accumulated.
     batch_passes = True
+    # run the MLM head only on the rows that carry a label (False: on all B*L rows like the reference, no host read)
+    select_mlm_rows = True
 
-    def _forward_train_batched(self, imgs, token_ids, text_mask, mlm_label, v_token_mask, B, L, H):
+    def _forward_train_batched(self, imgs, token_ids, text_mask, mlm_label, v_token_mask, B, L, H, mlm_rows=None):
         imgs2 = torch.cat([imgs, imgs], 0)
         vmask2 = torch.cat([v_token_mask, torch.zeros_like(v_token_mask)], 0)
         tok2, (B2, T, h, w) = self.backbone.forward_tokens(imgs2, vmask2)           # [masked ; clean] fp32 [2B*T*hw, C]
@@ -207,7 +215,7 @@ class CloverPretrain(BaseRecognizer):
         t_last = f2[B:, vs:]                                                        # (B, L, H) of the masked-text pass
         losses = dict()
         gamma = getattr(self.mlm_loss_func, "gamma", 0.0) if self.mlm_loss_func is not None else 0.0
-        losses["mlm_loss"] = self.mlm_head.focal_loss(t_last.reshape(B * L, H), mlm_label.reshape(-1), gamma=gamma)
+        losses["mlm_loss"] = self.mlm_head.focal_loss(t_last.reshape(B * L, H), mlm_label.reshape(-1), gamma=gamma, rows=mlm_rows)
         m_vmf = self.mlm_ssl_V_head(f2[:B, vs])                                     # fused text-CLS slot of the masked-video pass
         m_tmf = self.mlm_ssl_T_head(t_last[:, 0])
         g_v, g_t, g_tm, g_vmf, g_vm, g_tmf = gather_stacked([v_emb, t_emb, tm_emb, m_vmf, vm_emb, m_tmf])
