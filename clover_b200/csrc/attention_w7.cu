@@ -98,6 +98,7 @@ CLV_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;
 // =================================================================================================================
 struct W7FwdArgs {
   int batch, heads, seq, n_qt;
+  int tile_rows;                // fwd2: rows of every query tile but the last (a multiple of 32)
   int nmma;                     // S columns issued to the tensor core: seq rounded up to 16
   int n0;                       // first N chunk of the S product (<= 256), the rest is nmma - n0
   int kb_bytes, kx_bytes;       // bytes reserved per K (or V) buffer / per key-side extension buffer (multiples of 1024)
@@ -348,6 +349,278 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                                 pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv),
                                 pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv));
           a.lse[((long long)b * a.heads + h) * a.seq + i] = (m + log2f(l)) * W7_LN2;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// =================================================================================================================
+// Forward, second generation.  Same math and operands as attn_w7_fwd_kernel; what changes is how the softmax is spread
+// over the SM (ncu r01c: 12 warps / SM, 19 % warps active, issue slots 42 % busy, MUFU 35 % -- latency-bound):
+//   * EIGHT softmax warps per CTA instead of four: warps q and q + 4 share TMEM lane quarter q and split the key columns
+//     of a query row at SPLIT (a multiple of 16): half 0 owns [0, SPLIT), half 1 owns [SPLIT, SEQ).  The halves exchange
+//     their partial row max (before the exponentials) and row sum (before the epilogue) through shared memory and a
+//     64-thread named barrier; each half packs its P in place at the START of its own column range, so no half ever writes
+//     a column the other one still reads, and the P V product takes its A operand from two TMEM segments;
+//   * query tiles are cut at multiples of 32 rows (196 = 96 + 100, 392 = 96 + 96 + 96 + 104) instead of 98-row slabs
+//     whose fourth warp carried two rows: 7 instead of 8 warp-passes per 196-token window (13 instead of 16 at 392);
+//   * 320 threads at <= 102 registers keep two CTAs (20 warps) resident per SM.
+// =================================================================================================================
+constexpr int W7_FWD2_THREADS = 320;
+
+template <int CNT>
+CLV_DEVICE void w7_tmem_ld(uint32_t taddr, uint32_t (&r)[CNT]) {
+  if constexpr (CNT == 32) tmem_ld_32x32(taddr, r);
+  else if constexpr (CNT == 16) tmem_ld_32x16(taddr, r);
+  else if constexpr (CNT == 8)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+  else if constexpr (CNT == 4) tmem_ld_32x4(taddr, r);
+  else tmem_ld_32x2(taddr, r);
+}
+template <int CNT>
+CLV_DEVICE void w7_tmem_st(uint32_t taddr, const uint32_t (&r)[CNT]) {
+  if constexpr (CNT == 32) tmem_st_32x32(taddr, r);
+  else if constexpr (CNT == 16) tmem_st_32x16(taddr, r);
+  else if constexpr (CNT == 8) tmem_st_32x8(taddr, r);
+  else if constexpr (CNT == 4)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+  else if constexpr (CNT == 2) tmem_st_32x2(taddr, r[0], r[1]);
+  else tmem_st_32x1(taddr, r[0]);
+}
+__host__ __device__ constexpr int w7_pow2_chunk(int rem) { return rem >= 32 ? 32 : (rem >= 16 ? 16 : (rem >= 8 ? 8 : (rem >= 4 ? 4 : 2))); }
+// table offset of key column c of the window (two 49-token slabs per 98 columns)
+__host__ __device__ constexpr int w7_col_code(int c) { return w7_code(c % 98) + (c / 98) * 2 * W7_SH; }
+
+// pass 1 on the static column range [C, END): x = s * log2 e + bias * log2 e written back; running row max
+template <int C, int END>
+CLV_DEVICE void w7f2_pass1(uint32_t taddr, const float* tb, float& m) {
+  if constexpr (C < END) {
+    constexpr int CNT = w7_pow2_chunk(END - C);
+    uint32_t v[CNT];
+    w7_tmem_ld<CNT>(taddr + C, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int x = 0; x < CNT; ++x) v[x] = __float_as_uint(fmaf(__uint_as_float(v[x]), W7_LOG2E, tb[-w7_col_code(C + x)]));
+#pragma unroll
+    for (int x = 0; x + 1 < CNT; x += 2) m = w7_max3(m, __uint_as_float(v[x]), __uint_as_float(v[x + 1]));
+    w7_tmem_st<CNT>(taddr + C, v);
+    w7f2_pass1<C + CNT, END>(taddr, tb, m);
+  }
+}
+// pass 2 on [C, END): p = 2^(x - m), partial row sums, packed bf16 pairs stored at column PB + (C - LO) / 2
+template <int C, int END, int LO, int PB>
+CLV_DEVICE void w7f2_pass2(uint32_t taddr, float m, float& l0, float& l1) {
+  if constexpr (C < END) {
+    constexpr int CNT = w7_pow2_chunk(END - C);
+    uint32_t v[CNT], pk[CNT / 2];
+    w7_tmem_ld<CNT>(taddr + C, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int x = 0; x < CNT; x += 2) {
+      const float p0 = w7_ex2(__uint_as_float(v[x]) - m), p1 = w7_ex2(__uint_as_float(v[x + 1]) - m);
+      l0 += p0; l1 += p1;
+      pk[x >> 1] = pack_bf16(p0, p1);
+    }
+    w7_tmem_st<CNT / 2>(taddr + PB + (C - LO) / 2, pk);
+    w7f2_pass2<C + CNT, END, LO, PB>(taddr, m, l0, l1);
+  }
+}
+
+template <int SEQ>
+__global__ void __launch_bounds__(W7_FWD2_THREADS, 2)
+attn_w7_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv0,
+                    const __grid_constant__ CUtensorMap tm_kv1, const __grid_constant__ CUtensorMap tm_qx,
+                    const __grid_constant__ CUtensorMap tm_kx0, const __grid_constant__ CUtensorMap tm_kx1, W7FwdArgs a) {
+  constexpr int NMMA = (SEQ + 15) / 16 * 16;
+  constexpr int SPLIT = (SEQ / 2) / 16 * 16;          // 48, 96, 144, 192
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = 8192 + 2 * a.kb_bytes + (a.has_ext ? 4096 + a.kx_bytes : 0);
+  float* sTable = reinterpret_cast<float*>(smem + 2 * stage_bytes);
+  float* sMax = sTable + a.table_ld;                  // [2][128] partial row max of the two column halves
+  float* sSum = sMax + 256;                           // [2][128] partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 256);
+  uint64_t* full_bar = bars;          // [2]
+  uint64_t* empty_bar = bars + 2;     // [2]
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_ready = bars + 5;
+  uint64_t* o_full = bars + 6;
+  uint64_t* s_free = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.heads * W7_HD;
+  const int n1 = a.nmma - a.n0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv0);
+    if (n1 > 0) tma_prefetch_desc(&tm_kv1);
+    if (a.has_ext) { tma_prefetch_desc(&tm_qx); tma_prefetch_desc(&tm_kx0); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, 1); mbar_init(s_free, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long u_begin, u_end;
+  w7_unit_range(a.units, u_begin, u_end);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int t = (int)(u % a.n_qt);
+        const long long bh = u / a.n_qt;
+        const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+        const int stage = it & 1;
+        mbar_wait(&empty_bar[stage], ((it >> 1) & 1) ^ 1);
+        uint8_t* sQ = smem + stage * stage_bytes;
+        uint8_t* sK = sQ + 8192;
+        uint8_t* sV = sK + a.kb_bytes;
+        uint8_t* sQx = sV + a.kb_bytes;
+        uint8_t* sKx = sQx + 4096;
+        mbar_expect_tx(&full_bar[stage], 8192 + 2 * a.nmma * W7_ROWB + (a.has_ext ? 4096 + a.nmma * W7_XROWB : 0));
+        const int row0 = b * SEQ;
+        tma_load_2d(sQ, &tm_q, &full_bar[stage], h * W7_HD, row0 + t * a.tile_rows);
+        tma_load_2d(sK, &tm_kv0, &full_bar[stage], C + h * W7_HD, row0);
+        tma_load_2d(sV, &tm_kv0, &full_bar[stage], 2 * C + h * W7_HD, row0);
+        if (n1 > 0) {
+          tma_load_2d(sK + a.n0 * W7_ROWB, &tm_kv1, &full_bar[stage], C + h * W7_HD, row0 + a.n0);
+          tma_load_2d(sV + a.n0 * W7_ROWB, &tm_kv1, &full_bar[stage], 2 * C + h * W7_HD, row0 + a.n0);
+        }
+        if (a.has_ext) {
+          const int xrow0 = (b % a.nwin) * SEQ;
+          tma_load_2d(sQx, &tm_qx, &full_bar[stage], 0, xrow0 + t * a.tile_rows);
+          tma_load_2d(sKx, &tm_kx0, &full_bar[stage], 0, xrow0);
+          if (n1 > 0) tma_load_2d(sKx + a.n0 * W7_XROWB, &tm_kx1, &full_bar[stage], 0, xrow0 + a.n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc_pv = make_idesc_bf16(128, W7_HD, 0, 1);
+      const uint32_t idesc_s0 = make_idesc_bf16(128, a.n0, 0, 0);
+      const uint32_t idesc_s1 = make_idesc_bf16(128, n1 > 0 ? n1 : 16, 0, 0);
+      uint32_t it = 0;
+      for (long long u = u_begin; u < u_end; ++u, ++it) {
+        const int stage = it & 1;
+        mbar_wait(&full_bar[stage], (it >> 1) & 1);
+        mbar_wait(s_free, (it & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
+        const uint32_t k_addr = q_addr + 8192;
+        const uint32_t v_addr = k_addr + a.kb_bytes;
+        const uint32_t qx_addr = v_addr + a.kb_bytes;
+        const uint32_t kx_addr = qx_addr + 4096;
+#pragma unroll
+        for (int k = 0; k < W7_HD / 16; ++k)
+          umma_bf16_ss(tmem_base, make_smem_desc(q_addr + k * 32, 16, 512, 4), make_smem_desc(k_addr + k * 32, 16, 512, 4), idesc_s0, k > 0);
+        if (a.has_ext)
+          umma_bf16_ss(tmem_base, make_smem_desc(qx_addr, 16, 256, 6), make_smem_desc(kx_addr, 16, 256, 6), idesc_s0, 1);
+        if (n1 > 0) {
+#pragma unroll
+          for (int k = 0; k < W7_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + a.n0, make_smem_desc(q_addr + k * 32, 16, 512, 4),
+                         make_smem_desc(k_addr + a.n0 * W7_ROWB + k * 32, 16, 512, 4), idesc_s1, k > 0);
+          if (a.has_ext)
+            umma_bf16_ss(tmem_base + a.n0, make_smem_desc(qx_addr, 16, 256, 6),
+                         make_smem_desc(kx_addr + a.n0 * W7_XROWB, 16, 256, 6), idesc_s1, 1);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        const uint32_t tmem_o = tmem_base + a.col_o;
+#pragma unroll
+        for (int kk = 0; kk < NMMA / 16; ++kk) {      // P of keys [16 kk, 16 kk + 16): first or second packed segment
+          const uint32_t pc = kk * 16 < SPLIT ? kk * 8 : SPLIT + ((kk * 16 - SPLIT) >> 1);
+          umma_bf16_ts(tmem_o, tmem_base + pc, make_smem_desc(v_addr + kk * 1024, 16, 512, 4), idesc_pv, kk > 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&empty_bar[stage]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int cur_h = -1;
+    uint32_t it = 0;
+    for (long long u = u_begin; u < u_end; ++u, ++it) {
+      const int t = (int)(u % a.n_qt);
+      const long long bh = u / a.n_qt;
+      const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+      const int rows_here = (t == a.n_qt - 1) ? SEQ - t * a.tile_rows : a.tile_rows;
+      const bool valid = r < rows_here;
+      const bool warp_active = quarter * 32 < rows_here;
+      const int i = t * a.tile_rows + (valid ? r : 0);
+      if (h != cur_h) {                       // stage this head's bias column, pre-multiplied by log2 e
+        named_bar_sync(1, 256);
+        const float4* src = reinterpret_cast<const float4*>(a.table_t + (long long)h * a.table_ld);
+        for (int x = tid; x < a.table_ld / 4; x += 256) reinterpret_cast<float4*>(sTable)[x] = __ldg(src + x);
+        cur_h = h;
+        named_bar_sync(1, 256);
+      }
+      const float* tb = sTable + ((i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7) + a.code_off);
+
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float m = -1.0e30f, l = 0.f;
+      if (warp_active) {
+        if (half == 0) w7f2_pass1<0, SPLIT>(taddr, tb, m);
+        else w7f2_pass1<SPLIT, SEQ>(taddr, tb, m);
+        tmem_st_wait();
+        sMax[half * 128 + r] = m;
+        named_bar_sync(2 + quarter, 64);
+        m = fmaxf(m, sMax[(half ^ 1) * 128 + r]);
+        float l0 = 0.f, l1 = 0.f;
+        if (half == 0) {
+          w7f2_pass2<0, SPLIT, 0, 0>(taddr, m, l0, l1);
+        } else {
+          w7f2_pass2<SPLIT, SEQ, SPLIT, SPLIT>(taddr, m, l0, l1);
+          // keys [SEQ, NMMA) of the P V product: zero probabilities (8 packed columns cover the <= 7 pad columns)
+          const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          tmem_st_32x8(taddr + SPLIT + (SEQ - SPLIT) / 2, z);
+        }
+        tmem_st_wait();
+        sSum[half * 128 + r] = l0 + l1;
+        named_bar_sync(2 + quarter, 64);
+        l = (l0 + l1) + sSum[(half ^ 1) * 128 + r];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+
+      // ---- epilogue: each half normalises and stores 16 of the 32 output columns; half 0 also writes lse (natural log)
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      if (warp_active) {
+        uint32_t o[16];
+        tmem_ld_32x16(taddr + a.col_o + half * 16, o);
+        tmem_ld_wait();
+        if (valid) {
+          const float inv = 1.0f / l;
+          uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)b * SEQ + i) * C + h * W7_HD + half * 16);
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            dst[q] = make_uint4(pack_bf16(__uint_as_float(o[q * 8]) * inv, __uint_as_float(o[q * 8 + 1]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv),
+                                pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv));
+          if (half == 0) a.lse[((long long)b * a.heads + h) * SEQ + i] = (m + log2f(l)) * W7_LN2;
         }
       }
       tc_fence_before();
@@ -1314,6 +1587,24 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
     if (n1 > 0) { if (int rc = make_tmap_bf16_2d(&tkx1, d->k_ext, 16, xrows, 16, 16, n1, 32)) return rc; }
   }
   const size_t stage = 8192 + 2 * (size_t)a.kb_bytes + (a.has_ext ? 4096 + (size_t)a.kx_bytes : 0);
+  // second-generation forward (query tiles cut at multiples of 32 rows, eight softmax warps per CTA): +9 % at 392 tokens
+  // (13 instead of 16 warp-passes per window), neutral-to-slightly-slower at 196 where the first-generation kernel stays
+  // (tools/attn_microbench.py, profiles/r02*_attn_microbench*); w7_fwd2 = 1 / 0 forces one or the other
+  const long long fwd2 = tunable(TUNE_W7_FWD2, -2);
+  if (fwd2 == 1 || (fwd2 == -2 && d->wd >= 6)) {
+    a.n_qt = (a.seq + 127) / 128;
+    a.tile_rows = a.n_qt == 1 ? a.seq : (a.seq / a.n_qt) / 32 * 32;
+    a.units = (long long)d->batch * d->heads * a.n_qt;
+    const size_t smem2 = 1024 + 2 * stage + (size_t)a.table_ld * 4 + 2048 + 9 * 8 + 16;
+    CLV_REQUIRE(smem2 <= 227 * 1024, "attention_w7_fwd: %zu bytes of shared memory needed", smem2);
+    auto kern = d->wd == 2 ? attn_w7_fwd2_kernel<98> : d->wd == 4 ? attn_w7_fwd2_kernel<196>
+              : d->wd == 6 ? attn_w7_fwd2_kernel<294> : attn_w7_fwd2_kernel<392>;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem2)) return rc;
+    const int per_sm2 = (a.tmem_cols == 256 && smem2 <= 113 * 1024) ? 2 : 1;
+    const int grid2 = (int)std::min<long long>(a.units, (long long)num_sms() * per_sm2);
+    kern<<<grid2, W7_FWD2_THREADS, smem2, stream>>>(tq, tkv0, tkv1, tqx, tkx0, tkx1, a);
+    return after_launch("attn_w7_fwd2_kernel");
+  }
   const size_t smem = 1024 + 2 * stage + (size_t)a.table_ld * 4 + 9 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_fwd: %zu bytes of shared memory needed", smem);
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_w7_fwd_kernel), (int)smem)) return rc;

@@ -314,7 +314,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // (issue-bound for K <= 512: four warps per scheduler hide the dependent-latency stalls of the element math)
     const int quarter = warp & 3;
     const int chalf = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;
     constexpr int CPW = BN / (GEMM_EPI_WARPS / 4);   // columns per warp
     constexpr int EC = 16;                           // columns per epilogue step (register budget: 576 threads)
     constexpr int CHUNKS = CPW / EC;
@@ -323,11 +322,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const long long mn = t / k_splits;
       const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const float* sb = sBias + acc * BN;
-      if (ep.bias) {
-        for (int x = et; x < BN; x += 32 * GEMM_EPI_WARPS) sBias[acc * BN + x] = (n_idx * BN + x < N) ? __ldg(ep.bias + n_idx * BN + x) : 0.f;
-        named_bar_sync(1, 32 * GEMM_EPI_WARPS);
-      }
+      // bias: every lane of a warp needs the SAME 16 values per step -> four broadcast 128-bit loads straight from L1 / L2
+      // (one wavefront each); staging the tile's bias in shared memory needed a 512-thread barrier per tile that cost 15 %
+      // of a K = 512 GEMM (tools/epi_probe.py)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const long long row = (long long)m_idx * BM + quarter * 32 + lane;
@@ -358,8 +355,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (ep.bias) {
 #pragma unroll
           for (int q = 0; q < EC / 4; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + cb + q * 4);
-            v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+            if (q * 4 < ncols) {          // N % 8 == 0 and n0 % 16 == 0: whole float4 groups are in range (bias is 16-byte aligned)
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
+              v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+            }
           }
         }
         if (ep.scale_cols > n0) {
@@ -487,6 +486,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   CLV_REQUIRE(A && B && e && e->out, "clv_gemm_bf16: null pointer");
   CLV_REQUIRE(M > 0 && N > 0 && K > 0, "clv_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   CLV_REQUIRE(N % 8 == 0, "clv_gemm_bf16: N must be a multiple of 8 (got %d)", N);
+  CLV_REQUIRE(!e->bias || (reinterpret_cast<uintptr_t>(e->bias) & 15) == 0, "clv_gemm_bf16: bias must be 16-byte aligned");
   // 128x256 tiles when N fills them (less smem traffic per MAC); 128x128 otherwise
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
   const long long min_units256 = tunable(TUNE_GEMM_BN256_MIN_UNITS, 2LL * num_sms());   // the 2-waves rule

@@ -440,6 +440,19 @@ def test_window_attention_w7(ops, dims, shifted, Bc, heads):
     out2 = torch.empty_like(out); lse2 = torch.empty_like(lse)
     ops.attention_fwd(qkv, batch, N, heads, hd, out2, lse2, **kw)
     assert rel(out, out2) < 4e-3 and rel(lse, lse2) < 1e-5
+    # ... and so do the two generations of the specialised forward (gen 1: 4 softmax warps, 98-row tiles; gen 2: 8 softmax
+    # warps, tiles cut at multiples of 32 rows -- the default from 294 tokens up)
+    outs = []
+    for gen in (0, 1):
+        ops.set_tunable("w7_fwd2", gen)
+        try:
+            o_, l_ = torch.empty_like(out), torch.empty_like(lse)
+            ops.attention_fwd(qkv, batch, N, heads, hd, o_, l_, w7=spec, **kw)
+            outs.append((o_, l_))
+        finally:
+            ops.set_tunable("w7_fwd2", -1)
+    assert rel(outs[0][0], outs[1][0]) < 2e-3 and rel(outs[0][1], outs[1][1]) < 1e-6
+    assert rel(out, outs[1][0]) < 2e-3 and rel(lse, outs[1][1]) < 1e-6
     (o_ref * dout.float().cpu()).sum().backward()
     dqkv = torch.empty_like(qkv)
     dtab = torch.zeros(2535, heads, dtype=F32, device="cuda")
