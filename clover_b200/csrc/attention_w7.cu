@@ -78,21 +78,6 @@ CLV_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
       : "memory");
 }
 
-// ---- TMA store (shared -> global), bulk-group completion ----------------------------------------------------------
-CLV_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
-}
-// shared -> global with an element-wise add performed at the destination (L2): bf16 tiles of several units accumulate
-// into one small buffer instead of being written out one by one
-CLV_DEVICE void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
-}
-CLV_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-CLV_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-CLV_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // =================================================================================================================
 // Forward.  Unit = (window b, head h, query tile t of 98 rows).
 // =================================================================================================================

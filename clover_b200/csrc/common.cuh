@@ -36,7 +36,7 @@ int after_launch(const char* what);
 
 int num_sms();                                            // of the current device (cached per device)
 int ensure_dynamic_smem(const void* kernel, int bytes);   // cudaFuncSetAttribute once per (kernel, device)
-enum Tunable { TUNE_GEMM_BN256_MIN_UNITS = 0, TUNE_W7_PIPE, TUNE_W7_BWD2, TUNE_W7_DBIAS_ACC, TUNE_W7_DBIAS_ACC_MIN_MB, TUNE_W7_FWD2, TUNE_COUNT };
+enum Tunable { TUNE_GEMM_BN256_MIN_UNITS = 0, TUNE_W7_PIPE, TUNE_W7_BWD2, TUNE_W7_DBIAS_ACC, TUNE_W7_DBIAS_ACC_MIN_MB, TUNE_W7_FWD2, TUNE_GEMM_TMA_STORE, TUNE_COUNT };
 long long tunable(int id, long long dflt);                // clv_set_tunable overrides (tools only); no getenv in the library
 // D[b,h,i] = <dO_i, O_i> (attention backward preparation), defined in attention.cu
 int launch_attn_bwd_prep(const void* out, const void* dout, float* dsum, long long rows, int heads, int hd, int seq,
@@ -44,6 +44,9 @@ int launch_attn_bwd_prep(const void* out, const void* dout, float* dsum, long lo
 // 2-D bf16 tensor map (inner contiguous dimension first).  swizzle_bytes: 128, 64, 32 or 0.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
                       int box_outer, int swizzle_bytes = 128);
+// same for 2- or 4-byte elements (elem_bytes 2 = bf16, 4 = fp32); ld in elements
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, long long inner, long long outer, long long ld, int box_inner,
+                 int box_outer, int swizzle_bytes);
 
 // ------------------------------------------------------------------------------------------
 // small math
@@ -103,15 +106,18 @@ CLV_DEVICE float gelu_fit(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, th, hx);
 }
-// d/dx GELU = Phi(x) + x phi(x): Phi from the same tanh fit, phi = exp(-x^2/2) / sqrt(2 pi) from MUFU.EX2
+// d/dx of the SAME fitted function gelu_fit(x) = 0.5 x (1 + tanh(u)), u = x P(x^2):
+//   0.5 (1 + tanh u) + 0.5 x (1 - tanh^2 u) u'(x),   u'(x) = A0 + 3 A1 x^2 + 5 A2 x^4   (0 beyond the |x| = 6 clamp, where
+// 1 - tanh^2 u underflows anyway).  One MUFU (tanh) instead of two (tanh + ex2 for the exact phi(x)): the fc2-dgrad epilogue
+// that evaluates it on 2 x 10^8 elements per launch is XU / issue-bound.  |error| vs the exact erf-GELU derivative < 4e-4
+// (tests/test_kernels_gpu.py::test_gemm_epilogues), below the bf16 rounding of the gradient it multiplies.
 CLV_DEVICE float gelu_fit_grad(float x) {
-  const float xx = x * x;
-  const float x2 = fminf(xx, 36.0f);
+  const float x2 = fminf(x * x, 36.0f);
   const float t = fmaf(x2, fmaf(x2, GELU_A2, GELU_A1), GELU_A0);
+  const float du = fmaf(x2, fmaf(x2, 5.0f * GELU_A2, 3.0f * GELU_A1), GELU_A0);
   const float th = tanh_approx(x * t);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xx * -0.72134752044448170368f));
-  return fmaf(x * 0.39894228040143267794f, e, fmaf(0.5f, th, 0.5f));
+  const float hs = fmaf(-th, th, 1.0f) * (0.5f * x);          // 0.5 x sech^2(u)
+  return fmaf(hs, du, fmaf(0.5f, th, 0.5f));
 }
 // ------------------------------------------------------------------------------------------
 // counter-based random stream of the dropout kernels: 32 bits = high word of splitmix64(seed * phi + idx).
@@ -246,6 +252,22 @@ CLV_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// ---- TMA store (shared -> global), bulk-group completion ----------------------------------------------------------
+CLV_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+// shared -> global with an element-wise add performed at the destination (L2): bf16 tiles of several units accumulate
+// into one small buffer instead of being written out one by one
+CLV_DEVICE void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+CLV_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+CLV_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+CLV_DEVICE void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group
+CLV_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 CLV_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 CLV_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

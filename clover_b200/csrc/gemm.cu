@@ -27,7 +27,9 @@ namespace clv {
 constexpr int BM = 128, BK = 64;
 constexpr int GEMM_EPI_WARPS = 16;    // four column quarters x four lane quarters
 constexpr int GEMM_RS_WARPS = 2;       // row-sum warps (only busy in the RS kernels)
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS + 32 * GEMM_RS_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue, 18-19 row sums
+// warp 0 TMA, warp 1 MMA, warps 2-17 epilogue, (RS kernels only) warps 18-19 row sums: 576 threads leave 112 registers per
+// thread to the epilogue of the ordinary kernels, 640 threads (96 registers) only where the row-sum warps exist
+template <bool RS> constexpr int gemm_threads() { return 64 + 32 * GEMM_EPI_WARPS + (RS ? 32 * GEMM_RS_WARPS : 0); }
 
 // RS ("row sums"): the weight-gradient GEMMs dW = dY^T X also deliver the bias gradient sum_t dY[t, m] = the row sums of
 // their (MN-major) A operand.  Two extra warps read every A tile of the n_idx == 0 tiles out of shared memory behind the
@@ -39,7 +41,12 @@ template <int BN, bool RS> struct GemmCfg {
   static constexpr int STAGES = BN == 128 ? 6 : 4;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 2048;     // per epilogue warp: 32 rows x 64 B staged for TMA stores
+  // shared memory of the kernels without / with the TMA-store stage: the per-lane store path wants the ~28 KB of L1 that
+  // 200 KB of shared memory leave (its 32-byte row pieces merge into full lines there; 230 KB cost it 15-25 % on the
+  // store-bound K = 128 shapes), so only the TMA-store instantiations pay for the stage
+  static constexpr int SMEM_BASE = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_TS = SMEM_BASE + STG_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages
 };
 
@@ -55,6 +62,7 @@ struct GemmEpi {
   float scale;
   int use_row_map;
   int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
+  int tma_out;              // bit 0: `out` leaves through TMA stores (tensor map tma_out), bit 1: `out_pre` too (tma_pre)
   const float* row_scale;   // per row-group factor on (acc + bias) before the residual (DropPath), or nullptr
   long long row_scale_rows;
   float* rowsum;            // [M] += sum_k A[m, k] (fp32 atomics), or nullptr: see GemmCfg (RS kernels, MN-major A only)
@@ -149,9 +157,69 @@ CLV_DEVICE void store_row(void* base, int is_bf16, bool wide, int ncols, const f
   }
 }
 
-template <int A_MN, int B_MN, int BN, bool RS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// Element math of one 16-column epilogue step: accumulator -> v (final fp32 values) and pk (packed bf16 pre-activation when
+// act == 1 && out_pre).  Returns false when the lane has nothing to do (row beyond M, columns beyond N).
+template <int EC>
+CLV_DEVICE bool gemm_chunk_math(const GemmEpi& ep, uint32_t taddr, int n0, int N, long long row, long long drow, bool row_ok,
+                          float rscale, float (&v)[EC], uint32_t (&pk)[EC / 2], int& ncols) {
+  uint32_t r[EC];
+  tmem_ld_32x16(taddr, r);
+  tmem_ld_wait();
+
+  if (!row_ok || n0 >= N) return false;
+#pragma unroll
+  for (int j = 0; j < EC; ++j) v[j] = __uint_as_float(r[j]);
+  ncols = min(EC, N - n0);            // multiple of 8 (N % 8 == 0)
+  const bool wide = ep.vec32 != 0;    // implies ncols == EC
+  if (ep.atomic_out) return true;
+  if (ep.bias) {
+#pragma unroll
+    for (int q = 0; q < EC / 4; ++q) {
+      if (q * 4 < ncols) {          // N % 8 == 0 and n0 % 16 == 0: whole float4 groups are in range (bias is 16-byte aligned)
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
+        v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+      }
+    }
+  }
+  if (ep.scale_cols > n0) {
+#pragma unroll
+    for (int j = 0; j < EC; ++j)
+      if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
+  }
+  if (ep.act == 1) {
+    if (ep.out_pre) {
+#pragma unroll
+      for (int j = 0; j < EC / 2; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < EC; ++j) v[j] = gelu_fit(v[j]);
+  }
+  if (ep.gelu_pre) {
+    float g[EC];
+    load_row<EC>(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
+#pragma unroll
+    for (int j = 0; j < EC; ++j) v[j] *= gelu_fit_grad(g[j]);
+  }
+  if (ep.row_scale) {
+#pragma unroll
+    for (int j = 0; j < EC; ++j) v[j] *= rscale;
+  }
+  if (ep.residual) {
+    float g[EC];
+    if (ep.residual_bf16)
+      load_row<EC>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + drow * ep.ld_res + n0, 1, wide, ncols, g);
+    else
+      load_row<EC>(reinterpret_cast<const float*>(ep.residual) + drow * ep.ld_res + n0, 0, wide, ncols, g);
+#pragma unroll
+    for (int j = 0; j < EC; ++j) v[j] += g[j];
+  }
+  return true;
+      }
+
+template <int A_MN, int B_MN, int BN, bool RS, bool TS>
+__global__ void __launch_bounds__(gemm_threads<RS>(), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                  int M, int N, int K, int k_splits, GemmEpi ep) {
   using Cfg = GemmCfg<BN, RS>;
   static_assert(!RS || A_MN == 1, "row sums are implemented for the MN-major A operand of the weight gradients");
@@ -159,8 +227,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* sBias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [2][BN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
+  uint8_t* sStage = smem + STAGES * STAGE_BYTES;                                 // TS: [16 warps][2 KB], 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + (TS ? Cfg::STG_BYTES : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -175,6 +243,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (TS) tma_prefetch_desc(&tma_out);
+    if (TS && (ep.tma_out & 2)) tma_prefetch_desc(&tma_pre);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], RS ? 1 + GEMM_RS_WARPS : 1);
@@ -332,73 +402,91 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
       const bool row_ok = row < M && drow >= 0;
       const float rscale = (ep.row_scale && row < M) ? __ldg(ep.row_scale + row / ep.row_scale_rows) : 1.0f;
+      const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chalf * CPW;
+      if constexpr (TS) {
+        // ---- outputs leave through TMA stores: the row-per-lane layout of a TMEM load makes every per-lane global store
+        // touch 32 different lines (32 L1 wavefronts per instruction -- the LSU data pipe was the busiest unit of the
+        // K <= 512 GEMMs, ncu r01c: 65 %); instead each lane drops its 16-byte pieces into the warp's swizzled 2 KB stage
+        // (4 wavefronts per instruction) and one lane hands the 32-row x 64-byte box to the TMA unit.
+        // Per 16-column step the warp's stage holds [32 rows][32 B] of bf16 `out` (+ [32 rows][32 B] of `out_pre` at +1 KB) or
+        // [32 rows][64 B] of fp32 `out`; 16-byte pieces are XOR-swizzled exactly like the tensor map (SWIZZLE_32B / 64B).
+        uint8_t* stg = sStage + (warp - 2) * 2048;
+        const int box_row = m_idx * BM + quarter * 32;
+        const bool dual = (ep.tma_out & 2) != 0;
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        uint32_t r[EC];
-        const int cb = chalf * CPW + c * EC;             // column offset inside the tile
-        const int n0 = n_idx * BN + cb;
-        tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cb, r);
-        tmem_ld_wait();
-        if (!row_ok || n0 >= N) continue;
-        float v[EC];
+        for (int c = 0; c < CHUNKS; ++c) {
+          float v[EC]; uint32_t pk[EC / 2]; int ncols;
+          const int n0 = n_idx * BN + chalf * CPW + c * EC;
+          const bool live = gemm_chunk_math<EC>(ep, tacc + c * EC, n0, N, row, drow, row_ok, rscale, v, pk, ncols);
+          // a single bf16 output needs 1 KB per step: the two halves of the stage alternate and only the step before the
+          // previous one must have left shared memory; dual / fp32 outputs fill the whole stage every step
+          const bool two_buf = ep.out_bf16 && !dual;
+          uint8_t* buf = stg + ((two_buf && (c & 1)) ? 1024 : 0);
+          if (lane == 0) { if (two_buf) tma_store_wait_read_1(); else tma_store_wait_read(); }
+          __syncwarp();
+          if (live) {
+            if (ep.out_bf16) {
+              uint8_t* myrow = buf + lane * 32;
+              const int sw = (lane >> 2) & 1;
+              *reinterpret_cast<uint4*>(myrow + ((0 ^ sw) << 4)) =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              *reinterpret_cast<uint4*>(myrow + ((1 ^ sw) << 4)) =
+                  make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              if (dual) {
+                *reinterpret_cast<uint4*>(myrow + 1024 + ((0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(myrow + 1024 + ((1 ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
+            } else {
+              uint8_t* myrow = stg + lane * 64;
+              const int sw = (lane >> 1) & 3;
 #pragma unroll
-        for (int j = 0; j < EC; ++j) v[j] = __uint_as_float(r[j]);
-        const int ncols = min(EC, N - n0);  // multiple of 8 (N % 8 == 0)
-        const bool wide = ep.vec32 != 0;    // implies ncols == EC
-        if (ep.atomic_out) {
-          float* o = reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0;
-#pragma unroll
-          for (int j = 0; j < EC; ++j)
-            if (j < ncols) atomicAdd(o + j, v[j]);
-          continue;
-        }
-        if (ep.bias) {
-#pragma unroll
-          for (int q = 0; q < EC / 4; ++q) {
-            if (q * 4 < ncols) {          // N % 8 == 0 and n0 % 16 == 0: whole float4 groups are in range (bias is 16-byte aligned)
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
-              v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(myrow + ((q ^ sw) << 4)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+            if (ep.act == 1 && ep.out_pre && !dual) {
+              uint4* pp = reinterpret_cast<uint4*>(ep.out_pre + row * ep.ld_pre + n0);
+              pp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              pp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && n0 < N) {
+            tma_store_2d(&tma_out, buf, n0, box_row);
+            if (dual) tma_store_2d(&tma_pre, stg + 1024, n0, box_row);
+            tma_store_commit();
+          }
         }
-        if (ep.scale_cols > n0) {
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          float v[EC]; uint32_t pk[EC / 2]; int n0, ncols;
+          n0 = n_idx * BN + chalf * CPW + c * EC;
+          if (!gemm_chunk_math<EC>(ep, tacc + c * EC, n0, N, row, drow, row_ok, rscale, v, pk, ncols)) continue;
+          const bool wide = ep.vec32 != 0;
+          if (ep.atomic_out) {
+            float* o = reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0;
 #pragma unroll
-          for (int j = 0; j < EC; ++j)
-            if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
-        }
-        if (ep.act == 1) {
-          if (ep.out_pre) store_row<EC>(ep.out_pre + row * ep.ld_pre + n0, 1, wide, ncols, v);
-#pragma unroll
-          for (int j = 0; j < EC; ++j) v[j] = gelu_fit(v[j]);
-        }
-        if (ep.gelu_pre) {
-          float g[EC];
-          load_row<EC>(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
-#pragma unroll
-          for (int j = 0; j < EC; ++j) v[j] *= gelu_fit_grad(g[j]);
-        }
-        if (ep.row_scale) {
-#pragma unroll
-          for (int j = 0; j < EC; ++j) v[j] *= rscale;
-        }
-        if (ep.residual) {
-          float g[EC];
-          if (ep.residual_bf16)
-            load_row<EC>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + drow * ep.ld_res + n0, 1, wide, ncols, g);
+            for (int j = 0; j < EC; ++j)
+              if (j < ncols) atomicAdd(o + j, v[j]);
+            continue;
+          }
+          if (ep.act == 1 && ep.out_pre) {
+            uint4* pp = reinterpret_cast<uint4*>(ep.out_pre + row * ep.ld_pre + n0);
+            pp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (ncols > 8) pp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (ep.out_bf16)
+            store_row<EC>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0, 1, wide, ncols, v);
           else
-            load_row<EC>(reinterpret_cast<const float*>(ep.residual) + drow * ep.ld_res + n0, 0, wide, ncols, g);
-#pragma unroll
-          for (int j = 0; j < EC; ++j) v[j] += g[j];
+            store_row<EC>(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0, 0, wide, ncols, v);
         }
-        if (ep.out_bf16)
-          store_row<EC>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0, 1, wide, ncols, v);
-        else
-          store_row<EC>(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0, 0, wide, ncols, v);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (TS && lane == 0) tma_store_wait_all();      // the stage must outlive the bulk reads; writes drain here
   }
 
   tc_fence_before();
@@ -425,18 +513,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: inner dimension `inner` (contiguous), outer `outer`, row pitch ld elements.
-int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
-                      int box_inner, int box_outer, int swizzle_bytes) {
+// 2-D tensor map of 2-byte (bf16) or 4-byte (fp32) elements: inner dimension `inner` (contiguous), outer `outer`, row pitch ld elements.
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, long long inner, long long outer, long long ld,
+                 int box_inner, int box_outer, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   CLV_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
-  CLV_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
+  CLV_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "make_tmap_2d: 2- or 4-byte elements only");
+  CLV_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * elem_bytes) % 16 == 0,
               "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p ld=%lld)", ptr, ld);
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                   : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -446,34 +536,44 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long l
               outer, ld);
   return 0;
 }
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld,
+                      int box_inner, int box_outer, int swizzle_bytes) {
+  return make_tmap_2d(map, ptr, 2, inner, outer, ld, box_inner, box_outer, swizzle_bytes);
+}
 
-template <int A_MN, int B_MN, int BN, bool RS = false>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int k_splits,
-                       const GemmEpi& ep, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN, RS>;
-  constexpr int SMEM = GemmCfg<BN, RS>::SMEM;
+template <int A_MN, int B_MN, int BN, bool RS = false, bool TS = false>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tp, int M, int N, int K,
+                       int k_splits, const GemmEpi& ep, cudaStream_t stream) {
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN, RS, TS>;
+  constexpr int SMEM = TS ? GemmCfg<BN, RS>::SMEM_TS : GemmCfg<BN, RS>::SMEM_BASE;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), SMEM)) return rc;
   const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
   const int grid = (int)std::min<long long>(tiles, num_sms());
-  kern<<<grid, GEMM_THREADS, SMEM, stream>>>(ta, tb, M, N, K, k_splits, ep);
+  kern<<<grid, gemm_threads<RS>(), SMEM, stream>>>(ta, tb, to, tp, M, N, K, k_splits, ep);
   return after_launch("gemm_bf16_kernel launch");
 }
 
 template <int BN>
-static int dispatch_gemm_rowsum(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                                int k_splits, const GemmEpi& ep, cudaStream_t stream) {
+static int dispatch_gemm_rowsum(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                                const CUtensorMap& tp, int M, int N, int K, int k_splits, const GemmEpi& ep, cudaStream_t stream) {
   CLV_REQUIRE(a_mn, "clv_gemm_bf16: rowsum needs an MN-major A operand (a weight gradient dY^T X)");
-  if (b_mn) return launch_gemm<1, 1, BN, true>(ta, tb, M, N, K, k_splits, ep, stream);
-  return launch_gemm<1, 0, BN, true>(ta, tb, M, N, K, k_splits, ep, stream);
+  if (b_mn) return launch_gemm<1, 1, BN, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  return launch_gemm<1, 0, BN, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
 }
 
 template <int BN>
-static int dispatch_gemm(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int k_splits,
-                         const GemmEpi& ep, cudaStream_t stream) {
-  if (a_mn && b_mn) return launch_gemm<1, 1, BN>(ta, tb, M, N, K, k_splits, ep, stream);
-  if (a_mn) return launch_gemm<1, 0, BN>(ta, tb, M, N, K, k_splits, ep, stream);
-  if (b_mn) return launch_gemm<0, 1, BN>(ta, tb, M, N, K, k_splits, ep, stream);
-  return launch_gemm<0, 0, BN>(ta, tb, M, N, K, k_splits, ep, stream);
+static int dispatch_gemm(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tp,
+                         int M, int N, int K, int k_splits, const GemmEpi& ep, cudaStream_t stream) {
+  if (ep.tma_out & 1) {
+    if (a_mn && b_mn) return launch_gemm<1, 1, BN, false, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+    if (a_mn) return launch_gemm<1, 0, BN, false, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+    if (b_mn) return launch_gemm<0, 1, BN, false, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+    return launch_gemm<0, 0, BN, false, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  }
+  if (a_mn && b_mn) return launch_gemm<1, 1, BN>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (a_mn) return launch_gemm<1, 0, BN>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (b_mn) return launch_gemm<0, 1, BN>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  return launch_gemm<0, 0, BN>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
 }
 
 }  // namespace clv
@@ -548,8 +648,24 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (e->gelu_pre) ok = ok && al32(e->gelu_pre) && (e->ld_gelu_pre * 2) % 32 == 0;
     ep.vec32 = ok ? 1 : 0;
   }
-  if (e->rowsum) return bn256 ? dispatch_gemm_rowsum<256>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream)
-                              : dispatch_gemm_rowsum<128>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
-  if (bn256) return dispatch_gemm<256>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
-  return dispatch_gemm<128>(a_mn_major, b_mn_major, ta, tb, M, N, K, k_splits, ep, stream);
+  // TMA-store epilogue: dense (unscattered) bf16 / fp32 outputs with 32-byte aligned rows and N % 32 == 0, so a 16-column
+  // box is either fully inside N or fully outside; rows beyond M are clipped by the tensor map
+  CUtensorMap to = ta, tp = ta;
+  // Measured (tools/epi_probe.py, profiles/r02f_epilogue_probe_*): -7 % for the dual-output fc1 epilogue and for fp32 outputs;
+  // a SINGLE bf16 output is as fast (K = 512) or faster (K = 128, store-bound: 32-byte-wide boxes cost the TMA unit more than
+  // 256-bit LSU stores) on the per-lane path, which therefore keeps it.  gemm_tma_store = 2 forces TMA stores everywhere, 0 off.
+  const long long ts_mode = tunable(TUNE_GEMM_TMA_STORE, 1);
+  const bool ts_want = ts_mode == 2 || (ts_mode == 1 && (!e->out_is_bf16 || (e->out_pre && e->act)));
+  if (ep.vec32 && !ep.atomic_out && !e->window && !e->rowsum && ts_want) {
+    if (int rc2 = make_tmap_2d(&to, e->out, e->out_is_bf16 ? 2 : 4, N, M, e->ld_out, 16, 32, e->out_is_bf16 ? 32 : 64)) return rc2;
+    ep.tma_out = 1;
+    if (e->out_pre && e->act && e->out_is_bf16) {
+      if (int rc2 = make_tmap_2d(&tp, e->out_pre, 2, N, M, e->ld_pre, 16, 32, 32)) return rc2;
+      ep.tma_out |= 2;
+    }
+  }
+  if (e->rowsum) return bn256 ? dispatch_gemm_rowsum<256>(a_mn_major, b_mn_major, ta, tb, to, tp, M, N, K, k_splits, ep, stream)
+                              : dispatch_gemm_rowsum<128>(a_mn_major, b_mn_major, ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (bn256) return dispatch_gemm<256>(a_mn_major, b_mn_major, ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  return dispatch_gemm<128>(a_mn_major, b_mn_major, ta, tb, to, tp, M, N, K, k_splits, ep, stream);
 }

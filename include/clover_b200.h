@@ -25,7 +25,7 @@ const char* clv_last_error(void);
 int clv_version(void);
 /* Number of kernel launches issued by this library in the calling process (gpu_launches claim). */
 long long clv_launch_count(void);
-/* Experiment knobs for tools / tests ("gemm_bn256_min_units", "w7_pipe", "w7_bwd2", "w7_dbias_acc", "w7_dbias_acc_min_mb", "w7_fwd2");
+/* Experiment knobs for tools / tests ("gemm_bn256_min_units", "w7_pipe", "w7_bwd2", "w7_dbias_acc", "w7_dbias_acc_min_mb", "w7_fwd2", "gemm_tma_store");
  * value -1 restores the built-in default.  The library reads no environment variables.  Returns non-zero for unknown names. */
 int clv_set_tunable(const char* name, long long value);
 

@@ -48,7 +48,16 @@ def test_gemm_layouts(ops, a_t, b_t, M, N, K):
     assert rel(out, ref) < 2e-3
 
 
-def test_gemm_epilogues(ops):
+@pytest.fixture(params=[1, 0, 2], ids=["ts_default", "ts_off", "ts_forced"])
+def tma_store_mode(request, ops):
+    """The GEMM epilogue's output path: 1 = default (TMA stores for dual / fp32 outputs), 0 = per-lane stores only,
+    2 = TMA stores wherever the layout allows -- every epilogue test runs under all three."""
+    ops.set_tunable("gemm_tma_store", request.param)
+    yield request.param
+    ops.set_tunable("gemm_tma_store", -1)
+
+
+def test_gemm_epilogues(ops, tma_store_mode):
     M, N, K = 392, 256, 192
     A, B = rnd(M, K, seed=3, dtype=BF16), rnd(N, K, seed=4, scale=0.1, dtype=BF16)
     bias = rnd(N, seed=5)
