@@ -331,7 +331,8 @@ def run_ours(args):
                                                                                  "relative_position_bias_table": dict(decay_mult=0.0)})
     else:                # configs/exp_local/finetune_msrvttQA.py:90-97 / finetune_msrvtt_retrieval.py
         paramwise = dict(norm_decay_mult=0.0, bias_decay_mult=0.0, custom_keys={"qa_head": dict(lr_mult=10)})
-    opt = FusedAdamW(param_groups_from_cfg(model, 1e-7, W["wd"], paramwise), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=W["grad_clip"])
+    opt = FusedAdamW(param_groups_from_cfg(model, 1e-7, W["wd"], paramwise), betas=(0.9, 0.98), eps=1e-8, max_grad_norm=W["grad_clip"],
+                     reuse_grad_buffers=not args.no_grad_sinks)
     clips = args.clips if args.clips > 0 else W["clips"]
     if wl == "c3":
         keys = ("imgs", "label", "token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")
@@ -444,6 +445,15 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return world * clips / (float(t) / args.steps / 1e3), last
 
+    if args.trace:                   # developer aid: kernel timeline of two more steps (compute + NCCL streams) per rank
+        from torch.profiler import profile, ProfilerActivity
+        sync()
+        with profile(activities=[ProfilerActivity.CUDA]) as tp:
+            for _ in range(2):
+                step(devb)
+            sync()
+        os.makedirs(args.trace, exist_ok=True)
+        tp.export_chrome_trace(os.path.join(args.trace, f"trace_rank{rank}.json.gz"))
     if args.kernels_only:            # profiler captures (ncu): only the device-timed region above matters
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": ms_step,
@@ -517,6 +527,7 @@ def run_ours(args):
             model.cpu()
             from clover_b200 import functional as Fn
             Fn.clear_weight_cache()
+            Fn.clear_grad_sinks()
             import gc
             gc.collect()
             torch.cuda.empty_cache()
@@ -549,10 +560,12 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: 64 for c3, 16 for c4 / c5 = the shipped configs)")
     ap.add_argument("--kernels-only", action="store_true", help="run warm-up + timed steps and exit (short command for ncu captures)")
     ap.add_argument("--fp32-allreduce", action="store_true", help="N > 1: all-reduce fp32 gradient buckets instead of bf16")
+    ap.add_argument("--no-grad-sinks", action="store_true", help="allocate fresh gradient tensors every step (developer A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg (N = 1, c3)")
     ap.add_argument("--parity-config", action="store_true",
                     help="zero dropout / drop-path (the configuration of the parity tests) instead of the shipped training rates")
+    ap.add_argument("--trace", default=None, help="developer aid: directory for a torch.profiler kernel timeline of two extra steps")
     ap.add_argument("--lib", default=None, help="developer A/B runs: another build of libclover_b200.so to load")
     args = ap.parse_args()
     if args.lib:

@@ -118,13 +118,75 @@ def _zeros(n, device):
     return torch.zeros(n, dtype=F32, device=device)
 
 
-def _wgrad(dy16, x16, out_features, in_features, want_bias=False):
+# Gradient sinks: destination buffers for PARAMETER gradients that outlive a step.  Under DistributedDataParallel with
+# gradient_as_bucket_view=True every `param.grad` ends up as a view into an all-reduce bucket; a gradient that backward
+# produces anywhere else is copied into that view by DDP's hook -- ~600 small device copies (1.1 GB) per step.
+# `FusedAdamW.zero_grad(keep_buffers=True)` hands the old `.grad` tensors (the bucket views) to `stash_grad_sinks`; the
+# backward functions below then write the weight / bias / LayerNorm gradients straight into them and return an alias, which
+# AccumulateGrad adopts and DDP recognises as already in place.  A sink is used at most once per stash (a second backward
+# without zero_grad, or a parameter used twice, falls back to a fresh tensor and the usual accumulation).  Sinks whose
+# producer ACCUMULATES (atomics / column sums) are cleared in bulk at stash time once the producer has asked for that.
+_SINKS = {}
+_SINK_ZERO_KEYS = set()
+
+
+def stash_grad_sinks(params_and_grads):
+    _SINKS.clear()
+    zero = []
+    for p, g in params_and_grads:
+        # DDP packs its bucket views back to back, so a view that follows an odd-sized parameter (a (2535, 4) bias table, the
+        # 30522-entry decoder bias) is not 32-byte aligned: the kernels' vector stores need that, such parameters keep the copy
+        if g is None or g.dtype != F32 or not g.is_contiguous() or g.shape != p.shape or g.data_ptr() % 32:
+            continue
+        key = p.data_ptr()
+        _SINKS[key] = g
+        if key in _SINK_ZERO_KEYS:
+            zero.append(g)
+    if zero:
+        torch._foreach_zero_(zero)
+
+
+def clear_grad_sinks():
+    _SINKS.clear()
+    _SINK_ZERO_KEYS.clear()
+
+
+def _sink(key, shape, zero=False):
+    """Alias of the stashed gradient buffer of the parameter whose storage starts at `key` (None = no sink)."""
+    if not _SINKS or key is None:
+        return None
+    g = _SINKS.pop(key, None)
+    if g is None or tuple(g.shape) != tuple(shape):
+        return None
+    g = g.detach()                                         # fresh TensorImpl: AccumulateGrad may adopt it without a copy
+    if zero:
+        if key not in _SINK_ZERO_KEYS:
+            _SINK_ZERO_KEYS.add(key)                       # from the next stash on it is cleared in the bulk fill
+            g.zero_()
+    return g
+
+
+def _pkey(p):
+    return p.data_ptr() if (p is not None and p.requires_grad) else None
+
+
+def _small(key, n, device):
+    """Zero-initialised fp32 accumulator for a small parameter gradient: its sink when there is one, else an arena slice."""
+    g = _sink(key, (n,), zero=True)
+    return g if g is not None else _zeros(n, device)
+
+
+def _wgrad(dy16, x16, out_features, in_features, want_bias=False, wkey=None, bkey=None, wshape=None):
     """dW[out,in] = dY^T X with split-K (dY [T,out], X [T,in], both bf16 row-major).  want_bias: also return the bias
-    gradient sum_t dY[t, :], produced by the same GEMM (row sums of its A operand on the tensor cores)."""
+    gradient sum_t dY[t, :], produced by the same GEMM (row sums of its A operand on the tensor cores).  wkey / bkey:
+    gradient-sink keys of the weight / bias parameter (`_pkey`)."""
     T = dy16.shape[0]
-    dW = torch.empty(out_features, in_features, dtype=F32, device=dy16.device)
-    db = _zeros(out_features, dy16.device) if want_bias else None
-    ops.gemm(dy16, x16, dW, a_t=True, b_t=True, k_splits=ops.wgrad_splits(out_features, in_features, T), rowsum=db)
+    dW = _sink(wkey, wshape if wshape is not None else (out_features, in_features))
+    if dW is None:
+        dW = torch.empty(out_features, in_features, dtype=F32, device=dy16.device)
+    db = _small(bkey, out_features, dy16.device) if want_bias else None
+    ops.gemm(dy16, x16, dW.view(out_features, in_features), a_t=True, b_t=True,
+             k_splits=ops.wgrad_splits(out_features, in_features, T), rowsum=db)
     return (dW, db) if want_bias else dW
 
 
@@ -179,6 +241,7 @@ class LinearFn(torch.autograd.Function):
         ops.gemm(x, wb, out, bias=bias, act=act, out_pre=pre, residual=residual)
         ctx.save_for_backward(x, weight, pre)
         ctx.has_bias, ctx.has_res, ctx.act, ctx.wb = bias is not None, residual is not None, act, wb
+        ctx.bkey = _pkey(bias)
         ctx.res_dtype = residual.dtype if residual is not None else None
         return out
 
@@ -204,7 +267,7 @@ class LinearFn(torch.autograd.Function):
         dW = db = None
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            r = _wgrad(dy16, x, N, K, want_bias=want_b)
+            r = _wgrad(dy16, x, N, K, want_bias=want_b, wkey=_pkey(weight), bkey=ctx.bkey, wshape=weight.shape)
             dW, db = (r[0].view_as(weight), r[1]) if want_b else (r.view_as(weight), None)
         elif want_b:
             db = _colsum(dy16, N)
@@ -305,6 +368,7 @@ class MlpFn(torch.autograd.Function):
         ops.gemm(act, w2b, out, bias=b2, residual=residual)
         ctx.save_for_backward(x, w1, w2, pre, act)
         ctx.wb = (w1b, w2b)
+        ctx.bkeys = (_pkey(b1), _pkey(b2))
         ctx.res_dtype = residual.dtype if residual is not None else None
         return out
 
@@ -320,12 +384,12 @@ class MlpFn(torch.autograd.Function):
         M, Hd = pre.shape
         dpre = torch.empty(M, Hd, dtype=BF16, device=x.device)
         ops.gemm(dy16, w2b, dpre, b_t=True, gelu_pre=pre)
-        dW2, db2 = _wgrad(dy16, act, w2.shape[0], Hd, want_bias=True)
+        dW2, db2 = _wgrad(dy16, act, w2.shape[0], Hd, want_bias=True, wkey=_pkey(w2), bkey=ctx.bkeys[1])
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             ops.gemm(dpre, w1b, dx, b_t=True)
-        dW1, db1 = _wgrad(dpre, x, Hd, x.shape[1], want_bias=True)
+        dW1, db1 = _wgrad(dpre, x, Hd, x.shape[1], want_bias=True, wkey=_pkey(w1), bkey=ctx.bkeys[0])
         return dx, dW1, db1, dW2, db2, dres, None
 
 
@@ -356,19 +420,18 @@ class LayerNormFn(torch.autograd.Function):
         x, gamma, beta, mean, rstd = ctx.saved_tensors
         rows, C = x.shape
         dy = dy.contiguous()
-        small = _zeros(2 * C, x.device)
+        dg, db = _small(_pkey(gamma), C, x.device), _small(_pkey(beta), C, x.device)
         copy = torch.empty(rows, C, dtype=BF16, device=x.device) if x.dtype == BF16 else None
         fast = x.is_contiguous() and ops.lnr_supported(C)
         dx32 = torch.empty(rows, C, dtype=F32, device=x.device) if (copy is None or not fast) else None
         if fast:
             if copy is not None:                  # bf16 activations (BERT): only the bf16 gradient is consumed
-                ops.lnr_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, dx_bf16=copy, dgamma=small[:C], dbeta=small[C:])
+                ops.lnr_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, dx_bf16=copy, dgamma=dg, dbeta=db)
             else:
-                ops.lnr_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, dx=dx32, dgamma=small[:C], dbeta=small[C:])
+                ops.lnr_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, dx=dx32, dgamma=dg, dbeta=db)
         else:
-            ops.layernorm_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, rows=rows, dx=dx32, dx_copy=copy,
-                              dgamma=small[:C], dbeta=small[C:])
-        return (copy if copy is not None else dx32), small[:C], small[C:], None, None
+            ops.layernorm_bwd(x, gamma, beta, ctx.eps, mean, rstd, dy, rows=rows, dx=dx32, dx_copy=copy, dgamma=dg, dbeta=db)
+        return (copy if copy is not None else dx32), dg, db, None, None
 
 
 def layer_norm(x, gamma, beta, eps=1e-5, out_fp32=False):
@@ -479,6 +542,7 @@ class SwinBlockFn(torch.autograd.Function):
         ops.gemm(h2, w1, act, bias=fc1_b, act="gelu", out_pre=pre)
         out = torch.empty(T, C, dtype=F32, device=dev)
         ops.gemm(act, w2, out, bias=fc2_b, residual=x_mid, row_scale=dp[1] if dp is not None else None, row_scale_rows=tok)
+        ctx.pkeys = tuple(_pkey(p) for p in (qkv_w, qkv_b, proj_w, proj_b, fc1_w, fc1_b, fc2_w))
         ctx.save_for_backward(x, xw, qkv, ao, lse, x_mid, h2, pre, act, stats, code, region,
                               n1w, n1b, n2w, n2b, table)
         ctx.w = (wq, wp, w1, w2)
@@ -495,28 +559,31 @@ class SwinBlockFn(torch.autograd.Function):
         dev = x.device
         mean1, rstd1, mean2, rstd2 = stats[:rows], stats[rows:2 * rows], stats[2 * rows:2 * rows + T], stats[2 * rows + T:]
         dout = dout.contiguous()
-        small = _zeros(6 * C + table.numel(), dev)
-        dg1, db1, dg2, db2 = small[:C], small[C:2 * C], small[2 * C:3 * C], small[3 * C:4 * C]
-        dtable = small[6 * C:].view_as(table)
+        k_qw, k_qb, k_pw, k_pb, k_1w, k_1b, k_2w = ctx.pkeys
+        dg1, db1 = _small(_pkey(n1w), C, dev), _small(_pkey(n1b), C, dev)
+        dg2, db2 = _small(_pkey(n2w), C, dev), _small(_pkey(n2b), C, dev)
+        dtable = _sink(_pkey(table), table.shape, zero=True)
+        if dtable is None:
+            dtable = _zeros(table.numel(), dev).view_as(table)
         # ---- MLP branch
         # d(branch) = factor[sample] * dout: every consumer below reads the scaled bf16 copy (published by the next block's
         # norm1 backward when it ran; otherwise made here)
         dy16, dB2 = _grad_bf16(dout, want_colsum=True, scale=dp[1] if dp is not None else None, rows_per_group=tok)
         dpre = torch.empty(T, Hd, dtype=BF16, device=dev)
         ops.gemm(dy16, w2, dpre, b_t=True, gelu_pre=pre)
-        dW2 = _wgrad(dy16, act, C, Hd)
+        dW2 = _wgrad(dy16, act, C, Hd, wkey=k_2w)
         if dB2 is None:
             dB2 = _colsum(dy16, C)
         dh2 = dy16                                            # reuse the buffer: [T, C] bf16
         ops.gemm(dpre, w1, dh2, b_t=True)
-        dW1, dB1 = _wgrad(dpre, h2, Hd, C, want_bias=True)
+        dW1, dB1 = _wgrad(dpre, h2, Hd, C, want_bias=True, wkey=k_1w, bkey=k_1b)
         del dpre
         # ---- LN2 backward: d x_mid = dout + LN2'(dh2); bf16 copy emitted in window order for proj
         dmid = torch.empty(T, C, dtype=F32, device=dev)
         dmid_w = (torch.zeros if wg.padded else torch.empty)(rows, C, dtype=BF16, device=dev)
         dBp = None
         if rmap is not None:
-            dBp = small[4 * C:5 * C]                          # proj bias gradient = column sums of (scaled) d x_mid
+            dBp = _small(k_pb, C, dev)                        # proj bias gradient = column sums of (scaled) d x_mid
             ops.lnr_bwd(x_mid, n2w, n2b, 1e-5, mean2, rstd2, dh2, dx=dmid, dres=dout, dx_bf16=dmid_w, row_map=rmap,
                         dx_bf16_mapped=True, dgamma=dg2, dbeta=db2, dxsum=dBp,
                         copy_scale=dp[0] if dp is not None else None, copy_scale_rows=tok)
@@ -528,7 +595,7 @@ class SwinBlockFn(torch.autograd.Function):
             ops.rows_scale(dmid_w, dmid_w, dp[0], tok)
         dao = torch.empty(rows, C, dtype=BF16, device=dev)
         ops.gemm(dmid_w, wp, dao, b_t=True)
-        dWp = _wgrad(dmid_w, ao, C, C)
+        dWp = _wgrad(dmid_w, ao, C, C, wkey=k_pw)
         if dBp is None:
             dBp = _colsum(dmid_w, C)
         dqkv = torch.empty(rows, 3 * C, dtype=BF16, device=dev)
@@ -536,11 +603,11 @@ class SwinBlockFn(torch.autograd.Function):
                           bias_table=table, rel_code=code, code_off=code_off, region=region)
         dxw = dao                                             # reuse: [rows, C] bf16
         ops.gemm(dqkv, wq, dxw, b_t=True)
-        dWq, dBq = _wgrad(dqkv, xw, 3 * C, C, want_bias=True)
+        dWq, dBq = _wgrad(dqkv, xw, 3 * C, C, want_bias=True, wkey=k_qw, bkey=k_qb)
         # ---- LN1 backward through the window gather, accumulated onto d x_mid in place
         if rmap is not None:
             dmid16 = dmid_w                                   # reuse: [T, C] bf16 (rows == T when unpadded)
-            dx_sum = small[5 * C:6 * C]                       # = fc2 bias gradient of the block that produced x
+            dx_sum = _zeros(C, dev)                           # = fc2 bias gradient of the block that produced x
             ops.lnr_bwd(x, n1w, n1b, 1e-5, mean1, rstd1, dxw, dx=dmid, dres=dmid, dx_bf16=dmid16, row_map=rmap,
                         dy_mapped=True, dgamma=dg1, dbeta=db1, dxsum=dx_sum, copy_scale=prev_dp, copy_scale_rows=tok)
             _publish_grad16(dmid, dmid16, dx_sum, prev_dp)
@@ -565,6 +632,7 @@ class PatchEmbedFn(torch.autograd.Function):
         ops.gemm(cols, wb, y, bias=bias)
         ctx.dims = (B, D, Hp, Wp, C)
         ctx.wshape = weight.shape
+        ctx.pkeys = (_pkey(weight), _pkey(bias))
         if nw is None:
             ctx.save_for_backward(cols)
             ctx.norm = False
@@ -611,7 +679,7 @@ class PatchEmbedFn(torch.autograd.Function):
         else:
             (cols,) = ctx.saved_tensors
             dy16 = ops.to_bf16(dout)
-        dW, dB = _wgrad(dy16, cols, C, cols.shape[1], want_bias=True)
+        dW, dB = _wgrad(dy16, cols, C, cols.shape[1], want_bias=True, wkey=ctx.pkeys[0], bkey=ctx.pkeys[1], wshape=ctx.wshape)
         dW = dW.view(ctx.wshape)
         return None, dW, dB, dgn, dbn, None, dtok, None, None
 
@@ -633,6 +701,7 @@ class PatchMergeFn(torch.autograd.Function):
         ops.gemm(h, wb, out)
         ctx.save_for_backward(x, h, stats, nw, nb)
         ctx.meta = (dims, wb, red_w.shape[0])
+        ctx.wkey = _pkey(red_w)
         return out
 
     @staticmethod
@@ -644,12 +713,12 @@ class PatchMergeFn(torch.autograd.Function):
         dy16 = _grad_bf16(dout.contiguous())
         dh = torch.empty(rows, 4 * C, dtype=BF16, device=x.device)
         ops.gemm(dy16, wb, dh, b_t=True)
-        dW = _wgrad(dy16, h, Co, 4 * C)
-        small = _zeros(8 * C, x.device)
+        dW = _wgrad(dy16, h, Co, 4 * C, wkey=ctx.wkey)
+        dg, db = _small(_pkey(nw), 4 * C, x.device), _small(_pkey(nb), 4 * C, x.device)
         dx = torch.empty_like(x)
-        ops.layernorm_bwd(x, nw, nb, 1e-5, stats[:rows], stats[rows:], dh, rows=rows, dx=dx, dgamma=small[:4 * C],
-                          dbeta=small[4 * C:], merge=(B, D, H, W, C))
-        return dx, None, small[:4 * C], small[4 * C:], dW
+        ops.layernorm_bwd(x, nw, nb, 1e-5, stats[:rows], stats[rows:], dh, rows=rows, dx=dx, dgamma=dg, dbeta=db,
+                          merge=(B, D, H, W, C))
+        return dx, None, dg, db, dW
 
 
 # ------------------------------------------------------------------------------------------------
@@ -700,17 +769,21 @@ class BertEmbedFn(torch.autograd.Function):
         rows = B * L
         dev = word.device
         dx = torch.empty(rows, Hd, dtype=F32, device=dev)
-        small = _zeros(2 * Hd, dev)
+        dg, db = _small(_pkey(gamma), Hd, dev), _small(_pkey(beta), Hd, dev)
         ops.layernorm_bwd(word.detach(), gamma, beta, eps, stats[:rows], stats[rows:], dy.contiguous(), rows=rows, dx=dx,
-                          dgamma=small[:Hd], dbeta=small[Hd:], dx_dense=True, row_index=flat,
+                          dgamma=dg, dbeta=db, dx_dense=True, row_index=flat,
                           add0=typ.detach()[0].contiguous(), add1=(pos.detach(), 1, L))
-        dword = torch.zeros_like(word)
+
+        def table_grad(t):                          # embedding tables: only a few rows are touched, the rest stays zero
+            g = _sink(_pkey(t), t.shape, zero=True)
+            return g if g is not None else torch.zeros_like(t)
+        dword = table_grad(word)
         ops.scatter_add_rows(dx, flat, dword)
-        dpos = torch.zeros_like(pos)
+        dpos = table_grad(pos)
         ops.grouped_colsum(dx, dpos[:L], div=1, mod=L)
-        dtyp = torch.zeros_like(typ)
+        dtyp = table_grad(typ)
         ops.grouped_colsum(dx, dtyp[:1])
-        return None, dword, dpos, dtyp, small[:Hd], small[Hd:], None
+        return None, dword, dpos, dtyp, dg, db, None
 
 
 class FusionInputFn(torch.autograd.Function):

@@ -53,8 +53,13 @@ def param_groups_from_cfg(model, base_lr, weight_decay, paramwise_cfg=None):
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None,
-                 check_finite=True, emit_bf16=True):
+                 check_finite=True, emit_bf16=True, reuse_grad_buffers=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # reuse_grad_buffers: zero_grad() hands the gradient tensors of the finished step to the backward functions as
+        # destinations for the next one (clover_b200.functional.stash_grad_sinks).  Under DistributedDataParallel with
+        # gradient_as_bucket_view=True those tensors are the all-reduce bucket views, so the weight gradients are produced
+        # in place and DDP's per-parameter copy into the bucket disappears.
+        self.reuse_grad_buffers = bool(reuse_grad_buffers)
         self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
         self.check_finite, self.emit_bf16 = bool(check_finite), bool(emit_bf16)
         self.grad_scale = 1.0                    # multiply gradients by this (1 / loss scale) before clipping
@@ -180,6 +185,13 @@ class FusedAdamW(torch.optim.Optimizer):
             if d:
                 Fn.bf16_restamp(p, d)
         return loss
+
+    def zero_grad(self, set_to_none=True):
+        if self.reuse_grad_buffers:
+            from . import functional as Fn
+            Fn.stash_grad_sinks([(p, p.grad) for g in self.param_groups for p in g["params"]])
+            set_to_none = True
+        super().zero_grad(set_to_none=set_to_none)
 
     def grad_norm(self):
         """Gradient norm of the last step (after grad_scale) and whether that step was skipped -- one device->host read."""

@@ -562,6 +562,48 @@ def test_pretrain_step_with_shipped_regularisers_reproducible(cb, golden_dir):
         assert abs(e[k] - ref) <= 2e-2 * max(1.0, abs(ref)), (k, e[k], ref)
 
 
+def test_gradient_sinks_reuse_buffers_and_keep_accumulation_semantics(cb):
+    """FusedAdamW(reuse_grad_buffers=True): zero_grad() hands last step's gradient tensors to backward as destinations
+    (under DDP these are the all-reduce bucket views, so the per-parameter copy into the bucket disappears).  Checks:
+    gradients equal the fresh-tensor path; from the second step on most `.grad` tensors sit at their previous address; a
+    second backward WITHOUT zero_grad still accumulates (a sink is consumed once); lr = 0 keeps the weights fixed."""
+    from clover_b200 import functional as Fn
+    from clover_b200.configs import pretrain_cfg
+    from clover_b200.optim import FusedAdamW
+    bert = dict(num_attention_heads=2, intermediate_size=256, max_position_embeddings=64, vocab_size=1000)
+    m = cb.build_model(pretrain_cfg(32, (2, 2), (1, 2), 64, 128, 1000, 2, 2, 2, **bert)).cuda()
+    load_synth(m, 50)
+    m.train()
+    batch = make_batch(3, frames=4, L=16, seed=51, size=56, vocab=1000)
+    kw = {k: batch[k].cuda() for k in ("token_ids", "segment_ids", "input_mask", "mlm_label", "v_token_mask")}
+    params = [p for p in m.parameters() if p.requires_grad]
+
+    def backward():
+        total, _ = m._parse_losses(m(batch["imgs"].cuda(), batch["label"].cuda(), return_loss=True, **kw))
+        total.backward()
+    Fn.clear_grad_sinks()
+    m.zero_grad(set_to_none=True)
+    backward()
+    ref = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    opt = FusedAdamW(params, lr=0.0, weight_decay=0.0, reuse_grad_buffers=True)
+    try:
+        for it in range(3):
+            ptrs = {n: p.grad.data_ptr() for n, p in m.named_parameters() if p.grad is not None}
+            opt.step()
+            opt.zero_grad()
+            assert all(p.grad is None for p in params)
+            backward()
+            worst = max(rel(p.grad, ref[n]) for n, p in m.named_parameters() if p.grad is not None and float(ref[n].norm()) > 0)
+            assert worst <= 1e-4, (it, worst)
+            same = sum(p.grad.data_ptr() == ptrs[n] for n, p in m.named_parameters() if p.grad is not None)
+            assert same >= 0.5 * len(ptrs), (it, same, len(ptrs))
+        backward()                                   # no zero_grad in between: gradients add up
+        worst = max(rel(p.grad, 2 * ref[n]) for n, p in m.named_parameters() if p.grad is not None and float(ref[n].norm()) > 0)
+        assert worst <= 1e-4, worst
+    finally:
+        Fn.clear_grad_sinks()
+
+
 # ------------------------------------------------------------------------------------------------ evaluation (SURVEY 8 f2)
 def test_retrieval_evaluation_vs_reference_golden(cb, golden_dir):
     """Device-side R@k / MedR (clover_b200.evaluation) against the executed reference function and, rank by rank
