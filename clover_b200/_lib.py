@@ -51,6 +51,7 @@ class LnBwd(C.Structure):
         ("dx_copy", c_vp), ("dx_copy_is_bf16", C.c_int), ("ld_copy", c_ll),
         ("copy_window", C.POINTER(WindowGeom)),
         ("dgamma", c_vp), ("dbeta", c_vp), ("dtoken", c_vp), ("dx_dense", C.c_int),
+        ("dxsum", c_vp), ("copy_scale", c_vp), ("copy_scale_rows", c_ll),
     ]
 
 
@@ -58,6 +59,7 @@ class LnrDesc(C.Structure):
     _fields_ = [
         ("x", c_vp), ("x_is_bf16", C.c_int), ("gamma", c_vp), ("beta", c_vp), ("eps", C.c_float),
         ("mean", c_vp), ("rstd", c_vp), ("rows", c_ll), ("C", C.c_int), ("row_map", c_vp), ("map_period", C.c_int),
+        ("row_blend", c_vp), ("blend_token", c_vp),
     ]
 
 
@@ -65,7 +67,7 @@ class LnrBwd(C.Structure):
     _fields_ = [
         ("dy", c_vp), ("dy_is_bf16", C.c_int), ("dy_mapped", C.c_int), ("dres", c_vp), ("dx", c_vp),
         ("dx_bf16", c_vp), ("dx_bf16_mapped", C.c_int), ("dgamma", c_vp), ("dbeta", c_vp), ("dxsum", c_vp),
-        ("copy_scale", c_vp), ("copy_scale_rows", c_ll),
+        ("copy_scale", c_vp), ("copy_scale_rows", c_ll), ("dtoken", c_vp),
     ]
 
 

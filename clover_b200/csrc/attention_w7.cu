@@ -644,6 +644,7 @@ struct W7BwdArgs {
   int pipe;                      // issue dV / dK steps chunk by chunk while the softmax warps are still working
   __nv_bfloat16* dkv_part;       // bwd2 with 392 keys: dK | dV partial sums of the second query half, bf16 [rows, 2 C]
   long long ds_half_rows;        // bwd2 with 392 keys: row offset of the second query half in the dS^T dump
+  int l2_hint;                   // bwd2, dump_ds == 2: streamed operands evict-first, the accumulation buffers evict-last
   int ds_spans;                  // dump_ds == 2 (bwd2): dS^T tiles are ADDED (TMA reduce, bf16) into per-CTA buffers
                                  // [gridDim.x][ds_spans heads][query halves][keys][nq] that stay in L2; ds_spans = max number of
                                  // heads one CTA's contiguous unit range touches
@@ -1182,6 +1183,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
   if (warp == 0) {
     if (elect_one()) {
       uint32_t it = 0, tt = 0;
+      const uint64_t pol_stream = l2_policy_evict_first();
       for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int qh = (int)(u % NH);
         const long long uu = u / NH;
@@ -1193,16 +1195,26 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         uint8_t* sE = sDO + a.qb_bytes;
         mbar_expect_tx(&qdo_full[us], 2 * NQ * W7_ROWB + NQ * W7_XROWB);
         const int row0 = b * KSEQ;
-        tma_load_2d(sQ, &tm_q_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ);
-        tma_load_2d(sDO, &tm_do_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ);
+        if (a.l2_hint) {
+          tma_load_2d_hint(sQ, &tm_q_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ, pol_stream);
+          tma_load_2d_hint(sDO, &tm_do_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ, pol_stream);
+        } else {
+          tma_load_2d(sQ, &tm_q_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ);
+          tma_load_2d(sDO, &tm_do_full, &qdo_full[us], h * W7_HD, row0 + qh * SEQ);
+        }
         tma_load_2d(sE, &tm_e, &qdo_full[us], 0, (int)(((long long)b * a.heads + h) * KSEQ + qh * SEQ));
         for (int t = 0; t < NKT; ++t, ++tt) {
           const int ts = tt & 1;
           mbar_wait(&kv_empty[ts], ((tt >> 1) & 1) ^ 1);
           uint8_t* sK = sKV + ts * tile_bytes;
           mbar_expect_tx(&kv_full[ts], 2 * 8192 + (a.has_kx ? 4096 : 0));
-          tma_load_2d(sK, &tm_kv_tile, &kv_full[ts], C + h * W7_HD, row0 + t * W7_TILE);
-          tma_load_2d(sK + 8192, &tm_kv_tile, &kv_full[ts], 2 * C + h * W7_HD, row0 + t * W7_TILE);
+          if (a.l2_hint) {
+            tma_load_2d_hint(sK, &tm_kv_tile, &kv_full[ts], C + h * W7_HD, row0 + t * W7_TILE, pol_stream);
+            tma_load_2d_hint(sK + 8192, &tm_kv_tile, &kv_full[ts], 2 * C + h * W7_HD, row0 + t * W7_TILE, pol_stream);
+          } else {
+            tma_load_2d(sK, &tm_kv_tile, &kv_full[ts], C + h * W7_HD, row0 + t * W7_TILE);
+            tma_load_2d(sK + 8192, &tm_kv_tile, &kv_full[ts], 2 * C + h * W7_HD, row0 + t * W7_TILE);
+          }
           if (a.has_kx) tma_load_2d(sK + 2 * 8192, &tm_kx, &kv_full[ts], 0, (b % a.nwin) * KSEQ + t * W7_TILE);
         }
       }
@@ -1276,7 +1288,12 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
             const int hh = (int)((u / NH) / a.batch), h_first = (int)((u_begin / NH) / a.batch);
             const int buf = ((int)blockIdx.x * a.ds_spans + (hh - h_first)) * NH + (int)(u % NH);
             const int grow = buf * KSEQ + t * W7_TILE;
-            for (int q = 0; q < 4; ++q) tma_reduce_add_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
+            if (a.l2_hint) {
+              const uint64_t pol_keep = l2_policy_evict_last();
+              for (int q = 0; q < 4; ++q) tma_reduce_add_2d_hint(&tm_ds, sDS + q * 16384, q * 64, grow, pol_keep);
+            } else {
+              for (int q = 0; q < 4; ++q) tma_reduce_add_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
+            }
             tma_store_commit();
           } else if (a.dump_ds) {
             const long long uu = u / NH;
@@ -1696,6 +1713,7 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     if (acc_mode && (acc_mode == 2 || dump_bytes >= acc_min_bytes) && nbuf * a.seq <= rows * d->heads * nh) {   // fits in the dump's space
       a.dump_ds = 2;
       a.ds_spans = spans;
+      a.l2_hint = (int)tunable(TUNE_W7_L2_HINT, 1);
       CLV_CHECK_CUDA(cudaMemsetAsync(ds_out, 0, (size_t)nbuf * a.seq * a.nq * 2, stream));
     } else {
       nbuf = 0;

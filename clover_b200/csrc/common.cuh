@@ -36,7 +36,7 @@ int after_launch(const char* what);
 
 int num_sms();                                            // of the current device (cached per device)
 int ensure_dynamic_smem(const void* kernel, int bytes);   // cudaFuncSetAttribute once per (kernel, device)
-enum Tunable { TUNE_GEMM_BN256_MIN_UNITS = 0, TUNE_W7_PIPE, TUNE_W7_BWD2, TUNE_W7_DBIAS_ACC, TUNE_W7_DBIAS_ACC_MIN_MB, TUNE_W7_FWD2, TUNE_GEMM_TMA_STORE, TUNE_COUNT };
+enum Tunable { TUNE_GEMM_BN256_MIN_UNITS = 0, TUNE_W7_PIPE, TUNE_W7_BWD2, TUNE_W7_DBIAS_ACC, TUNE_W7_DBIAS_ACC_MIN_MB, TUNE_W7_FWD2, TUNE_GEMM_TMA_STORE, TUNE_W7_L2_HINT, TUNE_COUNT };
 long long tunable(int id, long long dflt);                // clv_set_tunable overrides (tools only); no getenv in the library
 // D[b,h,i] = <dO_i, O_i> (attention backward preparation), defined in attention.cu
 int launch_attn_bwd_prep(const void* out, const void* dout, float* dsum, long long rows, int heads, int hd, int seq,
@@ -263,6 +263,27 @@ CLV_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c
 CLV_DEVICE void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+// L2 eviction-priority policies for the bulk copies: streamed operands leave first, accumulation buffers stay
+CLV_DEVICE uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+CLV_DEVICE uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+CLV_DEVICE void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+CLV_DEVICE void tma_reduce_add_2d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 CLV_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 CLV_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -11,6 +11,8 @@
 //   * mask-token blend after the patch-embed LN  (:222-230)
 // Backward mirrors them (scatter instead of gather) and can add the residual-stream gradient and
 // emit a bf16 copy (optionally in window order) for the next GEMM's operand.
+#include <algorithm>
+
 #include "common.cuh"
 #include "clover_b200.h"
 
@@ -309,6 +311,223 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(LnBwdArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// PatchMerging LayerNorm (swin_transformer_3d.py:535-542) for the Swin widths 4C = 512 / 1024 / 2048.
+// The generic kernels above give a whole 4C-wide row to one warp (16 float4 per lane at 4C = 2048, plus as many
+// accumulators in the backward: > 255 registers, local-memory spills, 0.5-1.5 TB/s).  Here a merged row belongs to
+// T = C/4 threads (1, 2 or 4 warps) and every thread holds ONE float4 of each of the four 2x2 neighbours:
+// vector j of thread t is column j*C + 4t of the merged row = column 4t of source row (2*h2 + (j & 1), 2*w2 + (j >> 1)),
+// so all loads / stores are contiguous C-wide rows of x / dx.  Row statistics cross the warps of a row through shared memory.
+// ------------------------------------------------------------------------------------------
+struct LnmArgs {
+  const float* x; const float* gamma; const float* beta; float eps;
+  float* mean; float* rstd;
+  unsigned rows; int C;                 // merged rows, source width (merged width 4C)
+  int D, H, W;                          // source token grid per clip
+  __nv_bfloat16* y;                     // forward: [rows, 4C]
+  const __nv_bfloat16* dy; float* dx;   // backward: dy [rows, 4C]; dx at the source rows [B*D*H*W, C]
+  float* dgamma; float* dbeta;
+  __nv_bfloat16* dx16; float* dxsum;    // optional bf16 copy of dx and its column sums [C], both times copy_scale[clip]
+  const float* copy_scale; unsigned copy_scale_rows;
+};
+
+// source rows of the four channel blocks of merged row r: [(even h, even w), (odd h, even w), (even h, odd w), (odd h, odd w)];
+// -1 = zero padding (odd H / W)
+CLV_DEVICE void lnm_sources(const LnmArgs& a, unsigned r, long long (&src)[4]) {
+  const unsigned W2 = (a.W + 1) / 2, H2 = (a.H + 1) / 2;
+  const unsigned w2 = r % W2; unsigned t = r / W2;
+  const unsigned h2 = t % H2; t /= H2;             // t = b * D + d
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int h = 2 * (int)h2 + (j & 1), w = 2 * (int)w2 + (j >> 1);
+    src[j] = (h < a.H && w < a.W) ? ((long long)t * a.H + h) * a.W + w : -1;
+  }
+}
+
+CLV_DEVICE void lnm_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// ask L2 for the lines of the merged row this thread's row group handles NEXT iteration (one thread per 128-byte line): the
+// kernels are latency-bound on their loads, this doubles the bytes in flight without a live register
+template <bool WITH_DY>
+CLV_DEVICE void lnm_prefetch_next(const LnmArgs& a, unsigned rn, int t) {
+  if (rn >= a.rows) return;
+  if ((t & 7) == 0) {
+    long long sn[4];
+    lnm_sources(a, rn, sn);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (sn[j] >= 0) lnm_prefetch_l2(a.x + sn[j] * a.C + 4 * t);
+  }
+  if (WITH_DY && (t & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lnm_prefetch_l2(a.dy + (size_t)rn * 4 * a.C + j * a.C + 4 * t);
+  }
+}
+
+template <int T>
+CLV_DEVICE float lnm_row_sum(float v, float* slot, int warp_in_row) {
+  v = warp_sum(v);
+  if constexpr (T == 32) return v;
+  if ((threadIdx.x & 31) == 0) slot[warp_in_row] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < T / 32; ++w) s += slot[w];
+  return s;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) lnm_fwd_kernel(LnmArgs a) {
+  constexpr int R = 256 / T;                       // merged rows per CTA iteration
+  __shared__ float part[2][R][4];
+  const int g = threadIdx.x / T, t = threadIdx.x % T, wir = t >> 5;
+  const float inv_c = 1.0f / (float)(4 * a.C);
+  float4 gam[4], bet[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    gam[j] = __ldg(reinterpret_cast<const float4*>(a.gamma + j * a.C + 4 * t));
+    bet[j] = __ldg(reinterpret_cast<const float4*>(a.beta + j * a.C + 4 * t));
+  }
+  for (unsigned base = blockIdx.x * R; base < a.rows; base += gridDim.x * R) {
+    const unsigned r = base + g;
+    const bool live = r < a.rows;
+    long long src[4] = {-1, -1, -1, -1};
+    if (live) lnm_sources(a, r, src);
+    lnm_prefetch_next<false>(a, r + gridDim.x * R, t);
+    float4 v[4];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = src[j] >= 0 ? *reinterpret_cast<const float4*>(a.x + src[j] * a.C + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mu = lnm_row_sum<T>(sum, part[0][g], wir) * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
+      sq = fmaf(v[j].x, v[j].x, sq); sq = fmaf(v[j].y, v[j].y, sq); sq = fmaf(v[j].z, v[j].z, sq); sq = fmaf(v[j].w, v[j].w, sq);
+    }
+    const float rs = rsqrtf(lnm_row_sum<T>(sq, part[1][g], wir) * inv_c + a.eps);
+    if (!live) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 o;
+      o.x = fmaf(v[j].x * rs, gam[j].x, bet[j].x); o.y = fmaf(v[j].y * rs, gam[j].y, bet[j].y);
+      o.z = fmaf(v[j].z * rs, gam[j].z, bet[j].z); o.w = fmaf(v[j].w * rs, gam[j].w, bet[j].w);
+      *reinterpret_cast<uint2*>(a.y + (size_t)r * 4 * a.C + j * a.C + 4 * t) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+    if (t == 0) { a.mean[r] = mu; a.rstd[r] = rs; }
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(256, 2) lnm_bwd_kernel(LnmArgs a) {
+  constexpr int R = 256 / T;
+  extern __shared__ float red[];                   // [2][4C]: dgamma | dbeta of this CTA
+  __shared__ float part[2][2][R][4];               // [iteration parity][s1 | s2][row][warp of the row]
+  const int g = threadIdx.x / T, t = threadIdx.x % T, wir = t >> 5;
+  const int C4 = 4 * a.C;
+  const float inv_c = 1.0f / (float)C4;
+  for (int c = threadIdx.x; c < 2 * C4; c += blockDim.x) red[c] = 0.f;
+  float4 gam[4], dg[4], db[4];
+  float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);       // column sums of the scaled dx: the four neighbours share their columns
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    gam[j] = __ldg(reinterpret_cast<const float4*>(a.gamma + j * a.C + 4 * t));
+    dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int par = 0;
+  for (unsigned base = blockIdx.x * R; base < a.rows; base += gridDim.x * R, par ^= 1) {
+    const unsigned r = base + g;
+    const bool live = r < a.rows;
+    long long src[4] = {-1, -1, -1, -1};
+    float mu = 0.f, rs = 0.f;
+    if (live) { lnm_sources(a, r, src); mu = a.mean[r]; rs = a.rstd[r]; }
+    lnm_prefetch_next<true>(a, r + gridDim.x * R, t);
+    float4 xh[4], d[4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      xh[j] = d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        if (src[j] >= 0) xh[j] = *reinterpret_cast<const float4*>(a.x + src[j] * a.C + 4 * t);
+        const uint2 u = *reinterpret_cast<const uint2*>(a.dy + (size_t)r * C4 + j * a.C + 4 * t);
+        const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+        d[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        // a padded neighbour is a real (zero) element of the normalised row: it takes part in the statistics and in dgamma
+        xh[j].x = (xh[j].x - mu) * rs; xh[j].y = (xh[j].y - mu) * rs; xh[j].z = (xh[j].z - mu) * rs; xh[j].w = (xh[j].w - mu) * rs;
+      }
+      dg[j].x = fmaf(d[j].x, xh[j].x, dg[j].x); dg[j].y = fmaf(d[j].y, xh[j].y, dg[j].y);
+      dg[j].z = fmaf(d[j].z, xh[j].z, dg[j].z); dg[j].w = fmaf(d[j].w, xh[j].w, dg[j].w);
+      db[j].x += d[j].x; db[j].y += d[j].y; db[j].z += d[j].z; db[j].w += d[j].w;
+      d[j].x *= gam[j].x; d[j].y *= gam[j].y; d[j].z *= gam[j].z; d[j].w *= gam[j].w;       // d <- dy * gamma
+      s1 = fmaf(d[j].x, xh[j].x, s1); s1 = fmaf(d[j].y, xh[j].y, s1); s1 = fmaf(d[j].z, xh[j].z, s1); s1 = fmaf(d[j].w, xh[j].w, s1);
+      s2 += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if constexpr (T > 32) {
+      if ((threadIdx.x & 31) == 0) { part[par][0][g][wir] = s1; part[par][1][g][wir] = s2; }
+      __syncthreads();
+      s1 = s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < T / 32; ++w) { s1 += part[par][0][g][w]; s2 += part[par][1][g][w]; }
+    }
+    s1 *= inv_c; s2 *= inv_c;
+    if (!live) continue;
+    float sc = 1.0f;
+    if (a.copy_scale) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (src[j] >= 0) { sc = __ldg(a.copy_scale + (unsigned)src[j] / a.copy_scale_rows); break; }   // one clip per merged row
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (src[j] < 0) continue;
+      float4 o;
+      o.x = rs * (d[j].x - s2 - xh[j].x * s1); o.y = rs * (d[j].y - s2 - xh[j].y * s1);
+      o.z = rs * (d[j].z - s2 - xh[j].z * s1); o.w = rs * (d[j].w - s2 - xh[j].w * s1);
+      *reinterpret_cast<float4*>(a.dx + src[j] * a.C + 4 * t) = o;
+      if (a.dx16) {
+        o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
+        *reinterpret_cast<uint2*>(a.dx16 + src[j] * a.C + 4 * t) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        ds.x += o.x; ds.y += o.y; ds.z += o.z; ds.w += o.w;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = j * a.C + 4 * t;
+    atomicAdd(red + c, dg[j].x); atomicAdd(red + c + 1, dg[j].y); atomicAdd(red + c + 2, dg[j].z); atomicAdd(red + c + 3, dg[j].w);
+    atomicAdd(red + C4 + c, db[j].x); atomicAdd(red + C4 + c + 1, db[j].y);
+    atomicAdd(red + C4 + c + 2, db[j].z); atomicAdd(red + C4 + c + 3, db[j].w);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+    atomicAdd(a.dgamma + c, red[c]);
+    atomicAdd(a.dbeta + c, red[C4 + c]);
+  }
+  if (a.dxsum) {                                   // fold the row groups' column sums through the (now free) staging area
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) red[c] = 0.f;
+    __syncthreads();
+    atomicAdd(red + 4 * t, ds.x); atomicAdd(red + 4 * t + 1, ds.y); atomicAdd(red + 4 * t + 2, ds.z); atomicAdd(red + 4 * t + 3, ds.w);
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) atomicAdd(a.dxsum + c, red[c]);
+  }
+}
+
+static bool lnm_eligible(const LnArgs& f) {
+  return f.mode == 2 && !f.x_bf16 && f.ld_x == f.mC && (f.mC == 128 || f.mC == 256 || f.mC == 512) && !f.add0 && !f.add1 &&
+         !f.add2 && f.group_rows == 0 && !f.blend_mask && !f.row_index && f.mean && f.rstd;
+}
+static LnmArgs lnm_args(const LnArgs& f) {
+  LnmArgs m{};
+  m.x = reinterpret_cast<const float*>(f.x); m.gamma = f.gamma; m.beta = f.beta; m.eps = f.eps; m.mean = f.mean; m.rstd = f.rstd;
+  m.rows = (unsigned)f.rows; m.C = f.mC; m.D = f.mD; m.H = f.mH; m.W = f.mW;
+  return m;
+}
+
 static void fill_geom(WindowGeom& g, const clv_window_geom_t* w) {
   g.B = w->B; g.D = w->D; g.H = w->H; g.W = w->W; g.wd = w->wd; g.wh = w->wh; g.ww = w->ww;
   g.sd = w->sd; g.sh = w->sh; g.sw = w->sw;
@@ -370,6 +589,16 @@ extern "C" int clv_layernorm_fwd(const clv_ln_desc_t* d, void* y, int y_is_bf16,
   CLV_REQUIRE(y != nullptr, "layernorm_fwd: null output");
   a.y = y; a.y_bf16 = y_is_bf16; a.ld_y = ld_y;
   if (a.rows == 0) return 0;
+  if (lnm_eligible(a) && y_is_bf16 && ld_y == a.C) {
+    LnmArgs m = lnm_args(a);
+    m.y = reinterpret_cast<__nv_bfloat16*>(y);
+    const int T = a.mC / 4, R = 256 / T;
+    const int blocks = (int)std::min<long long>((a.rows + R - 1) / R, (long long)num_sms() * 8);
+    if (T == 32) lnm_fwd_kernel<32><<<blocks, 256, 0, stream>>>(m);
+    else if (T == 64) lnm_fwd_kernel<64><<<blocks, 256, 0, stream>>>(m);
+    else lnm_fwd_kernel<128><<<blocks, 256, 0, stream>>>(m);
+    return after_launch("lnm_fwd_kernel launch");
+  }
   const int vpl = (a.C / 4 + 31) / 32;
   const int warps_per_block = 8;
   const long long rows_per_block = (long long)warps_per_block * ln_rows_per_warp(vpl);
@@ -391,8 +620,26 @@ extern "C" int clv_layernorm_bwd(const clv_ln_desc_t* d, const clv_ln_bwd_t* b, 
   a.copy_window_map = b->copy_window != nullptr;
   if (b->copy_window) fill_geom(a.copy_geom, b->copy_window);
   a.dgamma = b->dgamma; a.dbeta = b->dbeta; a.dtoken = b->dtoken; a.dx_dense = b->dx_dense;
+  const bool lnm_copy_ok = !a.dx_copy || (a.dx_copy_bf16 && a.ld_copy == a.f.mC && !b->copy_window);
+  CLV_REQUIRE(!b->dxsum || a.dx_copy, "layernorm_bwd: dxsum comes with the bf16 dx_copy");
+  CLV_REQUIRE(!b->copy_scale || b->copy_scale_rows > 0, "layernorm_bwd: copy_scale needs copy_scale_rows > 0");
   CLV_REQUIRE(a.f.C <= 2048, "layernorm_bwd: C must be <= 2048 (got %d)", a.f.C);
   if (a.f.rows == 0) return 0;
+  if (lnm_eligible(a.f) && a.dy_bf16 && a.ld_dy == a.f.C && a.dx && a.ld_dx == a.f.mC && !a.dres && lnm_copy_ok && !a.dtoken &&
+      !a.dx_dense && a.dgamma && a.dbeta) {
+    LnmArgs m = lnm_args(a.f);
+    m.dy = reinterpret_cast<const __nv_bfloat16*>(a.dy); m.dx = a.dx; m.dgamma = a.dgamma; m.dbeta = a.dbeta;
+    m.dx16 = reinterpret_cast<__nv_bfloat16*>(a.dx_copy); m.dxsum = b->dxsum;
+    m.copy_scale = b->copy_scale; m.copy_scale_rows = b->copy_scale ? (unsigned)b->copy_scale_rows : 1u;
+    const int T = a.f.mC / 4, R = 256 / T;
+    const int blocks = (int)std::min<long long>((a.f.rows + R - 1) / R, (long long)num_sms() * 2);
+    const size_t smem = 2 * (size_t)a.f.C * sizeof(float);
+    if (T == 32) lnm_bwd_kernel<32><<<blocks, 256, smem, stream>>>(m);
+    else if (T == 64) lnm_bwd_kernel<64><<<blocks, 256, smem, stream>>>(m);
+    else lnm_bwd_kernel<128><<<blocks, 256, smem, stream>>>(m);
+    return after_launch("lnm_bwd_kernel launch");
+  }
+  CLV_REQUIRE(!b->dxsum && !b->copy_scale, "layernorm_bwd: dxsum / copy_scale only with the merge gather at the Swin widths");
   const int vpl = (a.f.C / 4 + 31) / 32;
   const int warps_per_block = 4;
   const long long rows_per_block = (long long)warps_per_block * ln_rows_per_warp(vpl);

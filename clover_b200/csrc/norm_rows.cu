@@ -34,6 +34,9 @@ struct LnrArgs {
   float* dgamma; float* dbeta;
   float* dxsum;                  // [C] column sums of the final dx (bias gradient of the nn.Linear that produced x's input)
   const float* copy_scale; unsigned copy_scale_rows;   // per-sample DropPath factor applied to dx16 and dxsum (not dx)
+  // mask-token blend after the patch-embed LN: y = LN(x) (1 - w[s]) + token w[s]; the backward accumulates dtoken in the
+  // dxsum accumulators (the two never occur together)
+  const float* row_w; const float* token;
 };
 
 template <bool BF>
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) lnr_fwd_kernel(LnrArgs a) {
     const float rs = rsqrtf(group_sum<L>(sq) * inv_c + a.eps);
     if (!live) continue;
     const unsigned orow = a.y_mapped ? lnr_mapped(a, s) : s;
+    const float bw = a.row_w ? __ldg(a.row_w + s) : 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int c = 4 * (sub + L * j);
@@ -113,6 +117,11 @@ __global__ void __launch_bounds__(256) lnr_fwd_kernel(LnrArgs a) {
       float4 o;
       o.x = fmaf(v[j].x * rs, g.x, b.x); o.y = fmaf(v[j].y * rs, g.y, b.y);
       o.z = fmaf(v[j].z * rs, g.z, b.z); o.w = fmaf(v[j].w * rs, g.w, b.w);
+      if (bw != 0.f) {
+        const float4 tk = __ldg(reinterpret_cast<const float4*>(a.token + c));
+        o.x = o.x * (1.f - bw) + tk.x * bw; o.y = o.y * (1.f - bw) + tk.y * bw;
+        o.z = o.z * (1.f - bw) + tk.z * bw; o.w = o.w * (1.f - bw) + tk.w * bw;
+      }
       lnr_st<YB>(a.y, (size_t)orow * a.C + c, o);
     }
     if (sub == 0 && a.mean) { a.mean[s] = mu; a.rstd[s] = rs; }
@@ -161,6 +170,15 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
         if (a.dres) rr[j] = *reinterpret_cast<const float4*>(a.dres + (size_t)s * a.C + c);
       }
     }
+    if (DXS && a.row_w) {            // d(LN out) = dy (1 - w); the token takes dy w
+      const float bw = live ? __ldg(a.row_w + s) : 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        ds[j].x = fmaf(d[j].x, bw, ds[j].x); ds[j].y = fmaf(d[j].y, bw, ds[j].y);
+        ds[j].z = fmaf(d[j].z, bw, ds[j].z); ds[j].w = fmaf(d[j].w, bw, ds[j].w);
+        d[j].x *= (1.f - bw); d[j].y *= (1.f - bw); d[j].z *= (1.f - bw); d[j].w *= (1.f - bw);
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
       if (a.dx) *reinterpret_cast<float4*>(a.dx + (size_t)s * a.C + c) = o;
       o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;          // the branch copy / bias gradient carry the DropPath factor
       if (a.dx16) lnr_st<true>(a.dx16, (size_t)crow * a.C + c, o);
-      if (DXS) { ds[j].x += o.x; ds[j].y += o.y; ds[j].z += o.z; ds[j].w += o.w; }
+      if (DXS && !a.row_w) { ds[j].x += o.x; ds[j].y += o.y; ds[j].z += o.z; ds[j].w += o.w; }
     }
   }
 
@@ -275,6 +293,8 @@ static int lnr_fill(LnrArgs& a, const clv_lnr_desc_t* d, int& V, int& L) {
   a = LnrArgs{};
   a.x = d->x; a.gamma = d->gamma; a.beta = d->beta; a.eps = d->eps; a.mean = d->mean; a.rstd = d->rstd;
   a.rows = (unsigned)d->rows; a.C = d->C; a.row_map = d->row_map; a.period = d->row_map ? (unsigned)d->map_period : 1u;
+  CLV_REQUIRE(!d->row_blend || d->blend_token, "lnr: row_blend needs blend_token");
+  a.row_w = d->row_blend; a.token = d->blend_token;
   return 0;
 }
 
@@ -320,7 +340,12 @@ extern "C" int clv_lnr_bwd(const clv_lnr_desc_t* d, const clv_lnr_bwd_t* b, void
   const size_t smem = 3 * (size_t)a.C * sizeof(float);
   const bool xb = d->x_is_bf16 != 0, dyb = b->dy_is_bf16 != 0;
   a.dxsum = b->dxsum;
-  if (a.dxsum) {
+  if (a.row_w) {
+    // patch-embed LN with the mask-token blend: fp32 x and dy, dtoken rides in the column-sum accumulators
+    CLV_REQUIRE(b->dtoken && !b->dxsum && !xb && !dyb && !b->copy_scale, "lnr_bwd: the blend needs dtoken, fp32 x / dy, no dxsum / copy_scale");
+    a.dxsum = b->dtoken;
+    LNR_SHAPES_B(false, false, true, <<<(int)blocks, 256, smem, stream>>>(a))
+  } else if (a.dxsum) {
     // fp32 residual stream, bf16 dy: the Swin block configuration (the only producer of a fused bias gradient)
     CLV_REQUIRE(!xb && dyb && (b->dx || b->dx_bf16), "lnr_bwd: dxsum needs fp32 x, bf16 dy and a dx output");
     LNR_SHAPES_B(false, true, true, <<<(int)blocks, 256, smem, stream>>>(a))

@@ -652,7 +652,15 @@ class PatchEmbedFn(torch.autograd.Function):
             mask = mask.to(device=imgs.device, dtype=torch.int64)
             blend = (mask.reshape(B, mask.shape[-2], mask.shape[-1]).contiguous(), token.detach().reshape(-1).contiguous(),
                      (D, Hp, Wp))
-        ops.layernorm_fwd(y, nw, nb, 1e-5, out, mean=stats[:T], rstd=stats[T:], blend=blend)
+        ctx.fast = ops.lnr_supported(C) and (blend is None or (Hp % mask.shape[-2] == 0 and Wp % mask.shape[-1] == 0))
+        if ctx.fast:
+            # lean row kernels (norm_rows.cu): the mask arrives as one fp32 weight per token row
+            if blend is not None:
+                w = blend[0].to(F32).repeat_interleave(Hp // mask.shape[-2], 1).repeat_interleave(Wp // mask.shape[-1], 2)
+                blend = (w[:, None].expand(B, D, Hp, Wp).reshape(-1).contiguous(), blend[1])
+            ops.lnr_fwd(y, nw, nb, 1e-5, out, mean=stats[:T], rstd=stats[T:], blend=blend)
+        else:
+            ops.layernorm_fwd(y, nw, nb, 1e-5, out, mean=stats[:T], rstd=stats[T:], blend=blend)
         ctx.save_for_backward(cols, y, nw, nb, stats, blend[0] if blend else None, blend[1] if blend else None)
         ctx.norm = True
         return out
@@ -671,9 +679,14 @@ class PatchEmbedFn(torch.autograd.Function):
             dgn, dbn = small[:C], small[C:2 * C]
             dy = torch.empty(T, C, dtype=F32, device=dev)
             dy16 = torch.empty(T, C, dtype=BF16, device=dev)
-            blend = (mask, token, (D, Hp, Wp)) if mask is not None else None
-            ops.layernorm_bwd(y, nw, nb, 1e-5, stats[:T], stats[T:], dout, rows=T, dx=dy, dx_copy=dy16, dgamma=dgn,
-                              dbeta=dbn, dtoken=small[2 * C:] if blend else None, blend=blend)
+            if ctx.fast:
+                blend = (mask, token) if mask is not None else None
+                ops.lnr_bwd(y, nw, nb, 1e-5, stats[:T], stats[T:], dout, dx=dy, dx_bf16=dy16, dgamma=dgn, dbeta=dbn,
+                            blend=blend, dtoken=small[2 * C:] if blend else None)
+            else:
+                blend = (mask, token, (D, Hp, Wp)) if mask is not None else None
+                ops.layernorm_bwd(y, nw, nb, 1e-5, stats[:T], stats[T:], dout, rows=T, dx=dy, dx_copy=dy16, dgamma=dgn,
+                                  dbeta=dbn, dtoken=small[2 * C:] if blend else None, blend=blend)
             if blend:
                 dtok = small[2 * C:].view(1, C, 1, 1, 1)
         else:
@@ -688,7 +701,8 @@ class PatchMergeFn(torch.autograd.Function):
     """PatchMerging (:521-544): 2x2 gather + LN(4C) in one kernel, then the bias-free reduction GEMM."""
 
     @staticmethod
-    def forward(ctx, x, dims, nw, nb, red_w):
+    def forward(ctx, x, dims, nw, nb, red_w, prev_dp=None):
+        # prev_dp: MLP-branch DropPath factors (fp32 [B]) of the block that produced x, or None (see SwinBlockFn)
         B, D, H, W = dims
         C = x.shape[1]
         H2, W2 = (H + 1) // 2, (W + 1) // 2
@@ -702,6 +716,7 @@ class PatchMergeFn(torch.autograd.Function):
         ctx.save_for_backward(x, h, stats, nw, nb)
         ctx.meta = (dims, wb, red_w.shape[0])
         ctx.wkey = _pkey(red_w)
+        ctx.prev_dp = prev_dp
         return out
 
     @staticmethod
@@ -716,9 +731,19 @@ class PatchMergeFn(torch.autograd.Function):
         dW = _wgrad(dy16, h, Co, 4 * C, wkey=ctx.wkey)
         dg, db = _small(_pkey(nw), 4 * C, x.device), _small(_pkey(nb), 4 * C, x.device)
         dx = torch.empty_like(x)
-        ops.layernorm_bwd(x, nw, nb, 1e-5, stats[:rows], stats[rows:], dh, rows=rows, dx=dx, dgamma=dg, dbeta=db,
-                          merge=(B, D, H, W, C))
-        return dx, None, dg, db, dW
+        if ops.ln_merge_fast(C) and x.is_contiguous():
+            # the last block of the stage consumes a bf16 copy of dx times its DropPath factor and the column sums of that
+            # copy (its fc2 bias gradient): both leave this kernel (no cast / row-scale / column-sum pass over dx)
+            dx16 = torch.empty(x.shape, dtype=BF16, device=x.device)
+            dx_sum = _zeros(C, x.device)
+            sc = ctx.prev_dp
+            ops.layernorm_bwd(x, nw, nb, 1e-5, stats[:rows], stats[rows:], dh, rows=rows, dx=dx, dgamma=dg, dbeta=db,
+                              merge=(B, D, H, W, C), dx_copy=dx16, dxsum=dx_sum, copy_scale=sc, copy_scale_rows=D * H * W)
+            _publish_grad16(dx, dx16, dx_sum, sc)
+        else:
+            ops.layernorm_bwd(x, nw, nb, 1e-5, stats[:rows], stats[rows:], dh, rows=rows, dx=dx, dgamma=dg, dbeta=db,
+                              merge=(B, D, H, W, C))
+        return dx, None, dg, db, dW, None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -285,7 +285,7 @@ def layernorm_fwd(x, gamma, beta, eps, y, *, rows=None, mean=None, rstd=None, **
 
 @_profiled("ln_bwd", _ln_tag, _ln_bwd_bytes)
 def layernorm_bwd(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=None, dx_copy=None, copy_window=None,
-                  dgamma=None, dbeta=None, dtoken=None, dx_dense=False, **kw):
+                  dgamma=None, dbeta=None, dtoken=None, dx_dense=False, dxsum=None, copy_scale=None, copy_scale_rows=0, **kw):
     _need_cuda(x, gamma, dy)
     Cn = gamma.numel()
     d = _ln_desc(x, gamma, beta, eps, rows, Cn, mean, rstd, **kw)
@@ -303,7 +303,22 @@ def layernorm_bwd(x, gamma, beta, eps, mean, rstd, dy, *, rows, dx=None, dres=No
         b.copy_window = copy_window.ref()
     b.dgamma, b.dbeta, b.dtoken = _ptr(dgamma), _ptr(dbeta), _ptr(dtoken)
     b.dx_dense = int(dx_dense)
+    if dxsum is not None:
+        if dxsum.dtype != F32 or not dxsum.is_contiguous():
+            raise TypeError("layernorm_bwd: dxsum must be contiguous fp32")
+        _need_cuda(dxsum)
+        b.dxsum = _ptr(dxsum)
+    if copy_scale is not None:
+        if copy_scale.dtype != F32 or not copy_scale.is_contiguous() or copy_scale_rows <= 0:
+            raise ValueError("layernorm_bwd: copy_scale must be contiguous fp32 with copy_scale_rows > 0")
+        _need_cuda(copy_scale)
+        b.copy_scale, b.copy_scale_rows = _ptr(copy_scale), int(copy_scale_rows)
     _lib.check(_lib.load().clv_layernorm_bwd(C.byref(d), C.byref(b), _stream()), "clv_layernorm_bwd")
+
+
+def ln_merge_fast(Cn):
+    """Source widths with a dedicated PatchMerging LayerNorm kernel (bf16 copy / column sums of dx supported)."""
+    return int(Cn) in (128, 256, 512)
 
 
 def lnr_supported(Cn):
@@ -326,17 +341,30 @@ def _lnr_desc(x, gamma, beta, eps, mean, rstd, row_map):
 
 
 def _lnr_tag(x, gamma, *a, **k):
-    kinds = [n for n in ("dres", "dx", "dx_bf16", "row_map") if k.get(n) is not None]
+    kinds = [n for n in ("dres", "dx", "dx_bf16", "row_map", "blend") if k.get(n) is not None]
     return f"rows={x.shape[0]} C={x.shape[1]} x={str(x.dtype)[-4:]} {'+'.join(kinds)}"
 
 
+def _lnr_blend(d, x, blend):
+    if blend is None:
+        return
+    w, token = blend                        # fp32 [rows] weights, fp32 [C] token
+    if w.dtype != F32 or token.dtype != F32 or w.numel() != x.shape[0] or token.numel() != x.shape[1] or \
+            not w.is_contiguous() or not token.is_contiguous():
+        raise ValueError("lnr: blend = (fp32 [rows] weights, fp32 [C] token), both contiguous")
+    _need_cuda(w, token)
+    d.row_blend, d.blend_token = _ptr(w), _ptr(token)
+
+
 @_profiled("ln_fwd", _lnr_tag, lambda x, gamma, beta, eps, y, **k: _tb(x, y))
-def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_mapped=False):
-    """y[m(s)] = LN(x[s]) on dense rows (clv_lnr_fwd); m = identity unless y_mapped."""
+def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_mapped=False, blend=None):
+    """y[m(s)] = LN(x[s]) on dense rows (clv_lnr_fwd); m = identity unless y_mapped.  blend = (w [rows], token [C]):
+    y = LN(x) (1 - w) + token w (mask-token blend after the patch-embed LN)."""
     _need_cuda(x, gamma, beta, y)
     if y.shape != x.shape or not y.is_contiguous():
         raise ValueError("lnr_fwd: y must be contiguous with x's shape")
     d = _lnr_desc(x, gamma, beta, eps, mean, rstd, row_map)
+    _lnr_blend(d, x, blend)
     _lib.check(_lib.load().clv_lnr_fwd(C.byref(d), _ptr(y), _is_bf16(y), int(y_mapped), _stream()), "clv_lnr_fwd")
     return y
 
@@ -344,7 +372,8 @@ def lnr_fwd(x, gamma, beta, eps, y, *, mean=None, rstd=None, row_map=None, y_map
 @_profiled("ln_bwd", _lnr_tag, lambda x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, **k:
            _tb(x, dy, dx, dres if dres is not dx else None, dx_bf16))
 def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=None, row_map=None, dy_mapped=False,
-            dx_bf16_mapped=False, dgamma=None, dbeta=None, dxsum=None, copy_scale=None, copy_scale_rows=0):
+            dx_bf16_mapped=False, dgamma=None, dbeta=None, dxsum=None, copy_scale=None, copy_scale_rows=0, blend=None,
+            dtoken=None):
     _need_cuda(x, gamma, dy)
     for t, n in ((dy, "dy"), (dx, "dx"), (dres, "dres"), (dx_bf16, "dx_bf16")):
         if t is not None and (t.shape != x.shape or not t.is_contiguous()):
@@ -352,7 +381,13 @@ def lnr_bwd(x, gamma, beta, eps, mean, rstd, dy, *, dx=None, dres=None, dx_bf16=
     if (dx is not None and dx.dtype != F32) or (dres is not None and dres.dtype != F32) or (dx_bf16 is not None and dx_bf16.dtype != BF16):
         raise TypeError("lnr_bwd: dx / dres fp32 and dx_bf16 bf16 required")
     d = _lnr_desc(x, gamma, beta, eps, mean, rstd, row_map)
+    _lnr_blend(d, x, blend)
     b = LnrBwd()
+    if blend is not None:
+        if dtoken is None or dtoken.dtype != F32 or not dtoken.is_contiguous() or dtoken.numel() != x.shape[1]:
+            raise ValueError("lnr_bwd: the blend needs a contiguous fp32 [C] dtoken accumulator")
+        _need_cuda(dtoken)
+        b.dtoken = _ptr(dtoken)
     b.dy, b.dy_is_bf16, b.dy_mapped = _ptr(dy), _is_bf16(dy), int(dy_mapped)
     b.dres, b.dx, b.dx_bf16, b.dx_bf16_mapped = _ptr(dres), _ptr(dx), _ptr(dx_bf16), int(dx_bf16_mapped)
     b.dgamma, b.dbeta, b.dxsum = _ptr(dgamma), _ptr(dbeta), _ptr(dxsum)

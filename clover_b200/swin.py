@@ -205,8 +205,8 @@ class PatchMerging(nn.Module):
         self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
         self.norm = norm_layer(4 * dim)
 
-    def forward_tokens(self, x, B, D, H, W):
-        y = Fn.PatchMergeFn.apply(x, (B, D, H, W), self.norm.weight, self.norm.bias, self.reduction.weight)
+    def forward_tokens(self, x, B, D, H, W, prev_dp=None):
+        y = Fn.PatchMergeFn.apply(x, (B, D, H, W), self.norm.weight, self.norm.bias, self.reduction.weight, prev_dp)
         return y, (H + 1) // 2, (W + 1) // 2
 
     def forward(self, x):
@@ -238,7 +238,7 @@ class BasicLayer(nn.Module):
         for blk in self.blocks:
             x, prev = blk.forward_tokens(x, B, D, H, W, prev_dp=prev, return_dp=True)
         if self.downsample is not None:
-            x, H, W = self.downsample.forward_tokens(x, B, D, H, W)
+            x, H, W = self.downsample.forward_tokens(x, B, D, H, W, prev_dp=prev)
         return x, H, W
 
     def forward(self, x):

@@ -112,6 +112,10 @@ typedef struct {
   float* dgamma; float* dbeta;                 /* [C] fp32, ACCUMULATED (caller zero-fills) */
   float* dtoken;                               /* [C] d(mask_token), blend only */
   int dx_dense;                                /* write dx at row r, not at the (gathered) source row */
+  /* merge gather at the Swin widths (merge_C = 128 / 256 / 512, fp32 x, bf16 dy) only: the bf16 dx_copy and dxsum carry the
+   * per-sample DropPath factor copy_scale[source row / copy_scale_rows] of the block that produced x (like clv_lnr_bwd_t);
+   * dxsum [merge_C] fp32 ACCUMULATES the column sums of that scaled dx = the bias gradient of the block's fc2 */
+  float* dxsum; const float* copy_scale; long long copy_scale_rows;
 } clv_ln_bwd_t;
 
 int clv_layernorm_bwd(const clv_ln_desc_t* desc, const clv_ln_bwd_t* bwd, void* stream);
@@ -129,6 +133,10 @@ typedef struct {
   float* mean; float* rstd;          /* [rows] fp32 by source row; written by fwd (may be NULL), read by bwd */
   long long rows; int C;
   const int* row_map; int map_period;
+  /* optional SimMIM mask-token blend after the patch-embed LayerNorm (swin_transformer_3d.py:222-230):
+   * y[s] = LN(x[s]) * (1 - w[s]) + token * w[s]; backward: d(LN out) = dy * (1 - w), dtoken += sum_s dy[s] * w[s] */
+  const float* row_blend;            /* [rows] fp32 weights w (0 / 1 from v_token_mask), or NULL */
+  const float* blend_token;          /* [C] fp32 */
 } clv_lnr_desc_t;
 
 typedef struct {
@@ -144,6 +152,7 @@ typedef struct {
                                         copy_scale[s / copy_scale_rows] -- they are the gradient of a residual branch that the
                                         forward pass scaled by the same factor (swin_transformer_3d.py:499,503) */
   long long copy_scale_rows;
+  float* dtoken;                     /* [C] fp32, ACCUMULATED gradient of blend_token (row_blend set; excludes dxsum) */
 } clv_lnr_bwd_t;
 
 int clv_lnr_supported(int C);

@@ -307,6 +307,94 @@ def test_layernorm_merge(ops, H, W):
     assert rel(dx, xr.grad) < 1e-4
 
 
+@pytest.mark.parametrize("C,H,W", [(128, 8, 6), (128, 7, 5), (256, 6, 6), (256, 5, 7), (512, 4, 6), (512, 3, 5)])
+def test_layernorm_merge_swin_widths(ops, C, H, W):
+    """PatchMerging LN at the Swin widths (4C = 512 / 1024 / 2048, fp32 tokens in, bf16 out): the dedicated kernels
+    (T = C/4 threads per merged row) against the fp32 reference incl. odd H / W padding, dgamma / dbeta and several
+    grid-stride iterations (rows > rows per wave is forced by the small clip count only at C = 512; larger below)."""
+    Bc, D = 3, 5
+    x = rnd(Bc * D * H * W, C, seed=1, scale=2)
+    g, b = 1 + 0.1 * rnd(4 * C, seed=2), 0.1 * rnd(4 * C, seed=3)
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    rows = Bc * D * H2 * W2
+    y = torch.empty(rows, 4 * C, dtype=BF16, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd, merge=(Bc, D, H, W, C))
+    xr = x.cpu().requires_grad_(True)
+    gr, br = g.cpu().requires_grad_(True), b.cpu().requires_grad_(True)
+    xx = torch.nn.functional.pad(xr.view(Bc, D, H, W, C), (0, 0, 0, W % 2, 0, H % 2))
+    cat = torch.cat([xx[:, :, i::2, j::2] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))], -1).reshape(rows, 4 * C)
+    yr = _ln_ref(cat, gr, br, 1e-5)
+    assert rel(y, yr.detach()) < 4e-3                                           # bf16 rounding of the output only
+    assert rel(mean, cat.detach().mean(-1)) < 1e-5
+    dy = rnd(rows, 4 * C, seed=4, dtype=BF16)
+    (yr * dy.float().cpu()).sum().backward()
+    dx = torch.full((Bc * D * H * W, C), float("nan"), dtype=F32, device="cuda")  # every source row must be written
+    dg, db = torch.zeros(4 * C, device="cuda"), torch.zeros(4 * C, device="cuda")
+    ops.layernorm_bwd(x, g, b, 1e-5, mean, rstd, dy, rows=rows, dx=dx, dgamma=dg, dbeta=db, merge=(Bc, D, H, W, C))
+    assert rel(dx, xr.grad) < 1e-4
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    # the same call also emitting the bf16 copy of dx times a per-clip factor and the column sums of that copy
+    scale = (0.5 + torch.arange(Bc, dtype=F32)).cuda()
+    dx2 = torch.empty_like(dx)
+    dx16 = torch.full((Bc * D * H * W, C), float("nan"), dtype=BF16, device="cuda")
+    dsum = torch.zeros(C, device="cuda")
+    dg2, db2 = torch.zeros(4 * C, device="cuda"), torch.zeros(4 * C, device="cuda")
+    ops.layernorm_bwd(x, g, b, 1e-5, mean, rstd, dy, rows=rows, dx=dx2, dgamma=dg2, dbeta=db2, merge=(Bc, D, H, W, C),
+                      dx_copy=dx16, dxsum=dsum, copy_scale=scale, copy_scale_rows=D * H * W)
+    want = xr.grad.view(Bc, -1, C) * scale.cpu()[:, None, None]
+    assert torch.equal(dx2, dx) and rel(dx16, want.reshape(-1, C)) < 4e-3
+    assert rel(dsum, want.reshape(-1, C).sum(0)) < 1e-4
+
+
+def test_layernorm_merge_many_rows(ops):
+    """More merged rows than one wave of CTAs covers (grid-stride loop, shared-memory parity buffers)."""
+    Bc, D, H, W, C = 8, 4, 28, 28, 256
+    x = rnd(Bc * D * H * W, C, seed=1, scale=2)
+    g, b = 1 + 0.1 * rnd(4 * C, seed=2), 0.1 * rnd(4 * C, seed=3)
+    rows = Bc * D * (H // 2) * (W // 2)
+    y = torch.empty(rows, 4 * C, dtype=BF16, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd, merge=(Bc, D, H, W, C))
+    xr = x.requires_grad_(True)
+    cat = torch.cat([xr.view(Bc, D, H, W, C)[:, :, i::2, j::2] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))], -1).reshape(rows, 4 * C)
+    yr = torch.nn.functional.layer_norm(cat, (4 * C,), g, b, 1e-5)
+    assert rel(y, yr.detach()) < 4e-3
+    dy = rnd(rows, 4 * C, seed=4, dtype=BF16)
+    (yr * dy.float()).sum().backward()
+    dx = torch.full((Bc * D * H * W, C), float("nan"), dtype=F32, device="cuda")
+    dg, db = torch.zeros(4 * C, device="cuda"), torch.zeros(4 * C, device="cuda")
+    ops.layernorm_bwd(x.detach(), g, b, 1e-5, mean, rstd, dy, rows=rows, dx=dx, dgamma=dg, dbeta=db, merge=(Bc, D, H, W, C))
+    assert rel(dx, xr.grad) < 1e-4
+    gg, gb = torch.autograd.grad((torch.nn.functional.layer_norm(cat.detach(), (4 * C,), g.requires_grad_(True), b.requires_grad_(True), 1e-5)
+                                  * dy.float()).sum(), (g, b))
+    assert rel(dg, gg) < 2e-4 and rel(db, gb) < 2e-4
+
+
+def test_lnr_mask_token_blend(ops):
+    """Patch-embed LayerNorm + SimMIM mask-token blend on the lean row kernels (C = 128, fp32 in / out, per-row weights):
+    y = LN(x) (1 - w) + token w; backward returns d x (+ bf16 copy), dgamma / dbeta and d token."""
+    rows, C = 5000, 128
+    x = rnd(rows, C, seed=1, scale=2)
+    g, b, tok = 1 + 0.1 * rnd(C, seed=2), 0.1 * rnd(C, seed=3), rnd(C, seed=4)
+    w = (torch.rand(rows, generator=torch.Generator().manual_seed(5)) < 0.4).float().cuda()
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.lnr_fwd(x, g, b, 1e-5, y, mean=mean, rstd=rstd, blend=(w, tok))
+    xr, gr, br, tr = (t.detach().clone().requires_grad_(True) for t in (x, g, b, tok))
+    yr = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-5) * (1 - w[:, None]) + tr[None] * w[:, None]
+    assert rel(y, yr.detach()) < 1e-5
+    dy = rnd(rows, C, seed=6)
+    (yr * dy).sum().backward()
+    dx = torch.empty_like(x)
+    dx16 = torch.empty(rows, C, dtype=BF16, device="cuda")
+    small = torch.zeros(3 * C, device="cuda")
+    ops.lnr_bwd(x, g, b, 1e-5, mean, rstd, dy, dx=dx, dx_bf16=dx16, dgamma=small[:C], dbeta=small[C:2 * C], blend=(w, tok),
+                dtoken=small[2 * C:])
+    assert rel(dx, xr.grad) < 1e-4 and rel(dx16, xr.grad) < 4e-3
+    assert rel(small[:C], gr.grad) < 1e-4 and rel(small[C:2 * C], br.grad) < 1e-4 and rel(small[2 * C:], tr.grad) < 1e-4
+
+
 def test_layernorm_fusion_adds_and_blend_and_lookup(ops):
     # fusion: LN(v + space[s] + tempor[t] + type0) written into rows of the concat buffer
     Bc, T, S, C, L = 3, 2, 49, 128, 16
