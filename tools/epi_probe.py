@@ -1,6 +1,10 @@
+"""GEMM epilogue probe: times one launch of the Swin-B hot shapes per epilogue variant (b bias, g GELU + pre-activation copy,
+G GELU only, p x GELU'(pre), r residual, 16 / 32 output width).   python tools/epi_probe.py [other libclover_b200.so]"""
 import sys, torch
 sys.path.insert(0, ".")
-from clover_b200 import ops
+from clover_b200 import _lib, ops
+if len(sys.argv) > 1:
+    _lib.set_library(sys.argv[1])
 BF16, F32 = torch.bfloat16, torch.float32
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 def run(M,N,K,bt,variant):
@@ -24,6 +28,8 @@ def run(M,N,K,bt,variant):
     print(f"M={M} N={N} K={K} bt={bt} {variant:6s} {t:7.3f} ms {2*M*N*K/t/1e9:7.1f} TFLOP/s", flush=True)
 for v in ("16", "b16", "bG16", "bg16", "p16", "32", "br32"):
     run(100352, 2048, 512, 0, v)
+run(100352, 1536, 512, 0, "b16")
+run(100352, 2048, 512, 1, "p16")
 for v in ("16", "bg16", "32"):
     run(1605632, 512, 128, 0, v)
 for v in ("16","32","br32"):
