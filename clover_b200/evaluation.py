@@ -23,6 +23,30 @@ def _dev(x):
     return t.float().contiguous()
 
 
+def gather_embeddings(*tensors, group=None):
+    """Cross-rank gather of per-rank `forward_test` outputs (rows may differ per rank: the last batches of a sharded test
+    set) as TENSORS: one size exchange + one padded all-gather per tensor, no pickling and no host hop (the reference
+    pickles every result list through a byte tensor, core/hooks/my_eval_hook.py:317-401 -> mmcv collect_results_gpu).
+    Returns the row-wise concatenation over ranks, in rank order, on every rank (a tuple when several tensors are given)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return tensors[0] if len(tensors) == 1 else tuple(tensors)
+    world = dist.get_world_size(group)
+    sizes = torch.tensor([t.shape[0] for t in tensors], dtype=torch.int64, device=tensors[0].device)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = torch.stack(all_sizes).cpu()                      # [world, len(tensors)]: the one host read
+    out = []
+    for k, t in enumerate(tensors):
+        n_max = int(all_sizes[:, k].max())
+        pad = t.new_zeros((n_max,) + tuple(t.shape[1:]))
+        pad[:t.shape[0]] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad.contiguous(), group=group)
+        out.append(torch.cat([p[:int(all_sizes[r, k])] for r, p in enumerate(parts)], 0))
+    return out[0] if len(out) == 1 else tuple(out)
+
+
 def cosine_scores(a, b):
     """scores[i, j] = <a_i / |a_i|, b_j / |b_j|> fp32 (rows of zero norm are left unscaled, numpy_norm.py:5-8)."""
     a, b = _dev(a), _dev(b)

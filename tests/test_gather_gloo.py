@@ -63,6 +63,11 @@ def _worker(rank, world, port, q):
         lt = torch.tensor(float(rank + 1), requires_grad=True)
         total, log_vars = BaseRecognizer._parse_losses({"a_loss": lt * 2.0, "acc": torch.tensor(10.0 * rank), "b_loss": [lt, lt]})
         res["parse_total"], res["parse_log"] = float(total.detach()), dict(log_vars)
+        # evaluation: ragged forward_test outputs gathered as tensors (no pickling)
+        from clover_b200.evaluation import gather_embeddings
+        ev_v, ev_t = torch.randn(3 + rank, 6, generator=g), torch.randn(3 + rank, 5, generator=g)
+        gv, gt_ = gather_embeddings(ev_v, ev_t)
+        res["ev_in"], res["ev_out"] = [ev_v, ev_t], [gv, gt_]
         # tensors travel through the queue as shared-memory handles that die with this process: send them by value
         res = {k: ([t.numpy().copy() for t in v] if isinstance(v, list) else (v.numpy().copy() if torch.is_tensor(v) else v))
                for k, v in res.items()}
@@ -108,6 +113,9 @@ def test_gather_semantics_world2():
     for i in range(4):
         assert torch.allclose(r0["emb_grads"][i], glob[i].grad[:4], atol=1e-6)
         assert torch.allclose(r1["emb_grads"][i], glob[i].grad[4:], atol=1e-6)
+    for i in range(2):
+        cat = torch.cat([r0["ev_in"][i], r1["ev_in"][i]])
+        assert torch.equal(r0["ev_out"][i], cat) and torch.equal(r1["ev_out"][i], cat)
     # _parse_losses: local total = sum of the '*loss*' entries; logged values are rank means
     assert r0["parse_total"] == 4.0 and r1["parse_total"] == 8.0
     for r in (r0, r1):
