@@ -62,6 +62,7 @@ struct GemmEpi {
   float scale;
   int use_row_map;
   int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
+  int spec;                 // host: EpiSpec specialisation this epilogue matches exactly (0 = none)
   int tma_out;              // bit 0: `out` leaves through TMA stores (tensor map tma_out), bit 1: `out_pre` too (tma_pre)
   const float* row_scale;   // per row-group factor on (acc + bias) before the residual (DropPath), or nullptr
   long long row_scale_rows;
@@ -157,54 +158,132 @@ CLV_DEVICE void store_row(void* base, int is_bf16, bool wide, int ncols, const f
   }
 }
 
+// Compile-time knowledge about the epilogue of the two hottest GEMM families.  The generic kernel decides every option at run
+// time (a dozen uniform branches, parameter loads and predicated tails per 16-column step: ncu r02m counts 24 executed
+// instructions per output element on fc1, 10 on a bias-only GEMM); the specialisations fold those decisions away.
+//   SPEC 0  generic (all flags read from GemmEpi)
+//   SPEC 1  fc1 of the Swin / BERT MLP: + bias, tanh-fit GELU, bf16 `out` and bf16 pre-activation copy, both through TMA stores
+//   SPEC 2  fc2 dgrad: x GELU'(pre) with a bf16 `pre` row, bf16 out, per-lane 256-bit stores
+//   SPEC 3 / 5 / 6  qkv, fc2 forward, proj (see below)
+// value -1: decided at run time
+template <int SPEC> struct EpiSpec {
+  static constexpr int bias = -1, act = -1, out_pre = -1, gelu_pre = -1, residual = -1, row_scale = -1, scale = -1, atomic = -1,
+                       row_map = -1, wide = -1, out_bf16 = -1, dual = -1;
+};
+template <> struct EpiSpec<1> {
+  static constexpr int bias = 1, act = 1, out_pre = 1, gelu_pre = 0, residual = 0, row_scale = 0, scale = 0, atomic = 0,
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 1;
+};
+template <> struct EpiSpec<2> {
+  static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 1, residual = 0, row_scale = 0, scale = 0, atomic = 0,
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0;
+};
+template <> struct EpiSpec<3> {      // qkv: + bias, q columns scaled (run-time column count), bf16 out, per-lane stores
+  static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = -1, atomic = 0,
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0;
+};
+template <> struct EpiSpec<5> {      // fc2 forward: + bias, (DropPath row scale), + residual, fp32 out through TMA stores
+  static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 1, row_scale = -1, scale = 0, atomic = 0,
+                       row_map = 0, wide = 1, out_bf16 = 0, dual = 0;
+};
+template <> struct EpiSpec<6> {      // proj: + bias, (DropPath row scale), + residual, fp32 out scattered through window_reverse
+  static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 1, row_scale = -1, scale = 0, atomic = 0,
+                       row_map = 1, wide = 1, out_bf16 = 0, dual = 0;
+};
+#define EPI_IS(field, runtime) (S::field < 0 ? (runtime) : (S::field != 0))
+
 // Element math of one 16-column epilogue step: accumulator -> v (final fp32 values) and pk (packed bf16 pre-activation when
 // act == 1 && out_pre).  Returns false when the lane has nothing to do (row beyond M, columns beyond N).
-template <int EC>
+template <int EC, int SPEC>
 CLV_DEVICE bool gemm_chunk_math(const GemmEpi& ep, uint32_t taddr, int n0, int N, long long row, long long drow, bool row_ok,
                           float rscale, float (&v)[EC], uint32_t (&pk)[EC / 2], int& ncols) {
+  using S = EpiSpec<SPEC>;
+  static_assert(EC == 16, "one 16-column step");
   uint32_t r[EC];
   tmem_ld_32x16(taddr, r);
+  // Specialised epilogues have registers to spare (64-80 of 96): what the step reads from global memory does not depend on
+  // the accumulator, so it is requested BEFORE waiting for the tensor-memory load and the two latencies overlap.  (The
+  // generic kernel sits at the 96-register cap; hoisting there spills and costs 30 %.)
+  constexpr bool HOIST = SPEC != 0;
+  [[maybe_unused]] float4 hb[EC / 4];
+  [[maybe_unused]] uint32_t ha[8], ha2[8];
+  if constexpr (HOIST) {
+    if (row_ok && n0 < N) {
+      if constexpr (S::bias == 1) {
+#pragma unroll
+        for (int q = 0; q < EC / 4; ++q) hb[q] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
+      }
+      if constexpr (S::gelu_pre == 1) ld256(ep.gelu_pre + row * ep.ld_gpre + n0, ha);
+      if constexpr (S::residual == 1) {
+        if (ep.residual_bf16) {
+          ld256(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + drow * ep.ld_res + n0, ha);
+        } else {
+          const float* p = reinterpret_cast<const float*>(ep.residual) + drow * ep.ld_res + n0;
+          ld256(p, ha);
+          ld256(p + 8, ha2);
+        }
+      }
+    }
+  }
   tmem_ld_wait();
 
   if (!row_ok || n0 >= N) return false;
 #pragma unroll
   for (int j = 0; j < EC; ++j) v[j] = __uint_as_float(r[j]);
-  ncols = min(EC, N - n0);            // multiple of 8 (N % 8 == 0)
-  const bool wide = ep.vec32 != 0;    // implies ncols == EC
-  if (ep.atomic_out) return true;
-  if (ep.bias) {
+  const bool wide = EPI_IS(wide, ep.vec32 != 0);    // implies ncols == EC
+  ncols = wide ? EC : min(EC, N - n0);               // multiple of 8 (N % 8 == 0)
+  if (EPI_IS(atomic, ep.atomic_out)) return true;
+  if (EPI_IS(bias, ep.bias != nullptr)) {
 #pragma unroll
     for (int q = 0; q < EC / 4; ++q) {
-      if (q * 4 < ncols) {          // N % 8 == 0 and n0 % 16 == 0: whole float4 groups are in range (bias is 16-byte aligned)
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
+      if (wide || q * 4 < ncols) {    // N % 8 == 0 and n0 % 16 == 0: whole float4 groups are in range (bias is 16-byte aligned)
+        float4 b4;
+        if constexpr (HOIST && S::bias == 1) b4 = hb[q];
+        else b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
         v[q * 4] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
       }
     }
   }
-  if (ep.scale_cols > n0) {
+  if (EPI_IS(scale, ep.scale_cols > n0)) {
 #pragma unroll
     for (int j = 0; j < EC; ++j)
       if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
   }
-  if (ep.act == 1) {
-    if (ep.out_pre) {
+  if (EPI_IS(act, ep.act == 1)) {
+    if (EPI_IS(out_pre, ep.out_pre != nullptr)) {
 #pragma unroll
       for (int j = 0; j < EC / 2; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
     }
 #pragma unroll
     for (int j = 0; j < EC; ++j) v[j] = gelu_fit(v[j]);
   }
-  if (ep.gelu_pre) {
-    float g[EC];
-    load_row<EC>(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
+  if (EPI_IS(gelu_pre, ep.gelu_pre != nullptr)) {
+    if constexpr (HOIST && S::gelu_pre == 1) {
 #pragma unroll
-    for (int j = 0; j < EC; ++j) v[j] *= gelu_fit_grad(g[j]);
+      for (int j = 0; j < EC / 2; ++j) {
+        const float2 t = unpack_bf16(ha[j]);
+        v[2 * j] *= gelu_fit_grad(t.x); v[2 * j + 1] *= gelu_fit_grad(t.y);
+      }
+    } else {
+      float g[EC];
+      load_row<EC>(ep.gelu_pre + row * ep.ld_gpre + n0, 1, wide, ncols, g);
+#pragma unroll
+      for (int j = 0; j < EC; ++j) v[j] *= gelu_fit_grad(g[j]);
+    }
   }
-  if (ep.row_scale) {
+  if (EPI_IS(row_scale, ep.row_scale != nullptr)) {
 #pragma unroll
     for (int j = 0; j < EC; ++j) v[j] *= rscale;
   }
-  if (ep.residual) {
+  if constexpr (HOIST && S::residual == 1) {
+    if (ep.residual_bf16) {
+#pragma unroll
+      for (int j = 0; j < EC / 2; ++j) { const float2 t = unpack_bf16(ha[j]); v[2 * j] += t.x; v[2 * j + 1] += t.y; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[j] += __uint_as_float(ha[j]); v[8 + j] += __uint_as_float(ha2[j]); }
+    }
+  } else if (EPI_IS(residual, ep.residual != nullptr)) {
     float g[EC];
     if (ep.residual_bf16)
       load_row<EC>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + drow * ep.ld_res + n0, 1, wide, ncols, g);
@@ -214,14 +293,15 @@ CLV_DEVICE bool gemm_chunk_math(const GemmEpi& ep, uint32_t taddr, int n0, int N
     for (int j = 0; j < EC; ++j) v[j] += g[j];
   }
   return true;
-      }
+}
 
-template <int A_MN, int B_MN, int BN, bool RS, bool TS>
+template <int A_MN, int B_MN, int BN, bool RS, bool TS, int SPEC>
 __global__ void __launch_bounds__(gemm_threads<RS>(), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                  int M, int N, int K, int k_splits, GemmEpi ep) {
   using Cfg = GemmCfg<BN, RS>;
+  using S = EpiSpec<SPEC>;
   static_assert(!RS || A_MN == 1, "row sums are implemented for the MN-major A operand of the weight gradients");
   constexpr int STAGES = Cfg::STAGES, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -399,9 +479,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_after();
       const long long row = (long long)m_idx * BM + quarter * 32 + lane;
       long long drow = row;
-      if (ep.use_row_map && row < M) drow = window_row_to_src(ep.geom, row);
+      if (EPI_IS(row_map, ep.use_row_map) && row < M) drow = window_row_to_src(ep.geom, row);
       const bool row_ok = row < M && drow >= 0;
-      const float rscale = (ep.row_scale && row < M) ? __ldg(ep.row_scale + row / ep.row_scale_rows) : 1.0f;
+      const float rscale = (EPI_IS(row_scale, ep.row_scale != nullptr) && row < M) ? __ldg(ep.row_scale + row / ep.row_scale_rows) : 1.0f;
       const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chalf * CPW;
       if constexpr (TS) {
         // ---- outputs leave through TMA stores: the row-per-lane layout of a TMEM load makes every per-lane global store
@@ -412,20 +492,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         // [32 rows][64 B] of fp32 `out`; 16-byte pieces are XOR-swizzled exactly like the tensor map (SWIZZLE_32B / 64B).
         uint8_t* stg = sStage + (warp - 2) * 2048;
         const int box_row = m_idx * BM + quarter * 32;
-        const bool dual = (ep.tma_out & 2) != 0;
+        const bool dual = EPI_IS(dual, (ep.tma_out & 2) != 0);
+        const bool out_bf16 = EPI_IS(out_bf16, ep.out_bf16 != 0);
 #pragma unroll 1
         for (int c = 0; c < CHUNKS; ++c) {
           float v[EC]; uint32_t pk[EC / 2]; int ncols;
           const int n0 = n_idx * BN + chalf * CPW + c * EC;
-          const bool live = gemm_chunk_math<EC>(ep, tacc + c * EC, n0, N, row, drow, row_ok, rscale, v, pk, ncols);
+          const bool live = gemm_chunk_math<EC, SPEC>(ep, tacc + c * EC, n0, N, row, drow, row_ok, rscale, v, pk, ncols);
           // a single bf16 output needs 1 KB per step: the two halves of the stage alternate and only the step before the
           // previous one must have left shared memory; dual / fp32 outputs fill the whole stage every step
-          const bool two_buf = ep.out_bf16 && !dual;
+          const bool two_buf = out_bf16 && !dual;
           uint8_t* buf = stg + ((two_buf && (c & 1)) ? 1024 : 0);
           if (lane == 0) { if (two_buf) tma_store_wait_read_1(); else tma_store_wait_read(); }
           __syncwarp();
           if (live) {
-            if (ep.out_bf16) {
+            if (out_bf16) {
               uint8_t* myrow = buf + lane * 32;
               const int sw = (lane >> 2) & 1;
               *reinterpret_cast<uint4*>(myrow + ((0 ^ sw) << 4)) =
@@ -443,7 +524,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(myrow + ((q ^ sw) << 4)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
             }
-            if (ep.act == 1 && ep.out_pre && !dual) {
+            if (EPI_IS(act, ep.act == 1) && EPI_IS(out_pre, ep.out_pre != nullptr) && !dual) {
               uint4* pp = reinterpret_cast<uint4*>(ep.out_pre + row * ep.ld_pre + n0);
               pp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               pp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -462,21 +543,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int c = 0; c < CHUNKS; ++c) {
           float v[EC]; uint32_t pk[EC / 2]; int n0, ncols;
           n0 = n_idx * BN + chalf * CPW + c * EC;
-          if (!gemm_chunk_math<EC>(ep, tacc + c * EC, n0, N, row, drow, row_ok, rscale, v, pk, ncols)) continue;
-          const bool wide = ep.vec32 != 0;
-          if (ep.atomic_out) {
+          if (!gemm_chunk_math<EC, SPEC>(ep, tacc + c * EC, n0, N, row, drow, row_ok, rscale, v, pk, ncols)) continue;
+          const bool wide = EPI_IS(wide, ep.vec32 != 0);
+          if (EPI_IS(atomic, ep.atomic_out)) {
             float* o = reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0;
 #pragma unroll
             for (int j = 0; j < EC; ++j)
               if (j < ncols) atomicAdd(o + j, v[j]);
             continue;
           }
-          if (ep.act == 1 && ep.out_pre) {
+          if (EPI_IS(act, ep.act == 1) && EPI_IS(out_pre, ep.out_pre != nullptr)) {
             uint4* pp = reinterpret_cast<uint4*>(ep.out_pre + row * ep.ld_pre + n0);
             pp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             if (ncols > 8) pp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          if (ep.out_bf16)
+          if (EPI_IS(out_bf16, ep.out_bf16 != 0))
             store_row<EC>(reinterpret_cast<__nv_bfloat16*>(ep.out) + drow * ep.ld_out + n0, 1, wide, ncols, v);
           else
             store_row<EC>(reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0, 0, wide, ncols, v);
@@ -541,10 +622,10 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long inner, long l
   return make_tmap_2d(map, ptr, 2, inner, outer, ld, box_inner, box_outer, swizzle_bytes);
 }
 
-template <int A_MN, int B_MN, int BN, bool RS = false, bool TS = false>
+template <int A_MN, int B_MN, int BN, bool RS = false, bool TS = false, int SPEC = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tp, int M, int N, int K,
                        int k_splits, const GemmEpi& ep, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN, RS, TS>;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, BN, RS, TS, SPEC>;
   constexpr int SMEM = TS ? GemmCfg<BN, RS>::SMEM_TS : GemmCfg<BN, RS>::SMEM_BASE;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), SMEM)) return rc;
   const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
@@ -564,6 +645,12 @@ static int dispatch_gemm_rowsum(int a_mn, int b_mn, const CUtensorMap& ta, const
 template <int BN>
 static int dispatch_gemm(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tp,
                          int M, int N, int K, int k_splits, const GemmEpi& ep, cudaStream_t stream) {
+  // compile-time epilogues of the two hottest families (EpiSpec); anything else takes the generic kernel
+  if (ep.spec == 1 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, true, 1>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (ep.spec == 2 && !a_mn && b_mn) return launch_gemm<0, 1, BN, false, false, 2>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (ep.spec == 3 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, false, 3>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (ep.spec == 5 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, true, 5>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (ep.spec == 6 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, false, 6>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.tma_out & 1) {
     if (a_mn && b_mn) return launch_gemm<1, 1, BN, false, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
     if (a_mn) return launch_gemm<1, 0, BN, false, true>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
@@ -662,6 +749,16 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (e->out_pre && e->act && e->out_is_bf16) {
       if (int rc2 = make_tmap_2d(&tp, e->out_pre, 2, N, M, e->ld_pre, 16, 32, 32)) return rc2;
       ep.tma_out |= 2;
+    }
+  }
+  if (tunable(TUNE_GEMM_SPEC, 1) && ep.vec32 && !ep.atomic_out && !e->rowsum) {
+    const bool plain = !e->window && !e->residual && !e->row_scale;
+    if (plain && e->out_is_bf16 && e->scale_cols <= 0 && ep.tma_out == 3 && e->bias && e->act == 1 && e->out_pre && !e->gelu_pre) ep.spec = 1;
+    else if (plain && e->out_is_bf16 && e->scale_cols <= 0 && ep.tma_out == 0 && !e->bias && !e->act && !e->out_pre && e->gelu_pre) ep.spec = 2;
+    else if (plain && e->out_is_bf16 && ep.tma_out == 0 && e->bias && !e->act && !e->out_pre && !e->gelu_pre) ep.spec = 3;
+    else if (!e->out_is_bf16 && e->bias && e->residual && !e->act && !e->out_pre && !e->gelu_pre && e->scale_cols <= 0) {
+      if (!e->window && ep.tma_out == 1) ep.spec = 5;
+      else if (e->window && ep.tma_out == 0) ep.spec = 6;
     }
   }
   if (e->rowsum) return bn256 ? dispatch_gemm_rowsum<256>(a_mn_major, b_mn_major, ta, tb, to, tp, M, N, K, k_splits, ep, stream)
