@@ -64,13 +64,40 @@ def next_stream(n, kind="dropout", shape=None, p=0.0):
     return seed, off
 
 
+_PREDRAWN = []          # FIFO of (batch, p, tensor) filled by predraw_drop_path and consumed by drop_path_scales
+
+
+def predraw_drop_path(batch, ps, device):
+    """Draws the DropPath factors of a whole backbone pass (one entry of `ps` per later drop_path_scales call, in call order)
+    with ONE uniform draw instead of two tiny kernels per residual branch (48 branches in Swin-B).  Same distribution as
+    bernoulli_(keep) / keep; the following drop_path_scales(batch, p, device) calls return rows of the batch draw."""
+    _PREDRAWN.clear()
+    ps = [float(p) for p in ps]
+    if not ps:
+        return
+    keep = 1.0 - torch.tensor(ps, dtype=torch.float32).clamp_(0.0, 1.0)
+    keep_d = keep.to(device)[:, None]
+    u = torch.rand(len(ps), batch, dtype=torch.float32, device=device)
+    s = (u < keep_d).to(torch.float32) / keep_d.clamp_min(1e-30)
+    for p, row in zip(ps, s.unbind(0)):
+        _PREDRAWN.append((batch, p, row))
+
+
 def drop_path_scales(batch, p, device):
     """timm DropPath factors (drop.py: x.new_empty(B,1,..).bernoulli_(keep) / keep): fp32 [batch] on `device`, drawn
     from torch's generator of that device (torch.manual_seed controls it, as in the reference)."""
     keep = 1.0 - float(p)
-    s = torch.empty(batch, dtype=torch.float32, device=device).bernoulli_(keep)
-    if keep > 0.0:
-        s.div_(keep)
+    s = None
+    if _PREDRAWN:
+        b0, p0, row = _PREDRAWN.pop(0)
+        if b0 == batch and p0 == float(p) and row.device == torch.device(device):
+            s = row
+        else:
+            _PREDRAWN.clear()               # out of step with the pre-drawn sequence: fall back to individual draws
+    if s is None:
+        s = torch.empty(batch, dtype=torch.float32, device=device).bernoulli_(keep)
+        if keep > 0.0:
+            s.div_(keep)
     if LOG is not None:
         LOG.append(dict(kind="drop_path", shape=(batch,), p=float(p), scale=s.detach().cpu().clone()))
     return s

@@ -404,6 +404,10 @@ class SwinTransformer3D(nn.Module):
         if mask is not None and tok is None:
             raise ValueError("SwinTransformer3D: mask given but the backbone was built with mask_token=False")
         t, (B, D, H, W) = self.patch_embed.forward_tokens(x, mask, tok)
+        if self.training:                  # all DropPath factors of this pass in one draw (two per block, in block order)
+            from . import rng
+            ps = [blk.drop_path_rate for layer in self.layers for blk in layer.blocks for _ in range(2) if blk.drop_path_rate > 0]
+            rng.predraw_drop_path(B, ps, t.device)
         for layer in self.layers:
             t, H, W = layer.forward_tokens(t, B, D, H, W)
         t = Fn.layer_norm(t, self.norm.weight, self.norm.bias, 1e-5, out_fp32=True)
