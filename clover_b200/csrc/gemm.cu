@@ -164,7 +164,7 @@ CLV_DEVICE void store_row(void* base, int is_bf16, bool wide, int ncols, const f
 //   SPEC 0  generic (all flags read from GemmEpi)
 //   SPEC 1  fc1 of the Swin / BERT MLP: + bias, tanh-fit GELU, bf16 `out` and bf16 pre-activation copy, both through TMA stores
 //   SPEC 2  fc2 dgrad: x GELU'(pre) with a bf16 `pre` row, bf16 out, per-lane 256-bit stores
-//   SPEC 3 / 5 / 6  qkv, fc2 forward, proj (see below)
+//   SPEC 3 / 4 / 5 / 6  qkv, plain dgrad, fc2 forward, proj (see below)
 // value -1: decided at run time
 template <int SPEC> struct EpiSpec {
   static constexpr int bias = -1, act = -1, out_pre = -1, gelu_pre = -1, residual = -1, row_scale = -1, scale = -1, atomic = -1,
@@ -180,6 +180,10 @@ template <> struct EpiSpec<2> {
 };
 template <> struct EpiSpec<3> {      // qkv: + bias, q columns scaled (run-time column count), bf16 out, per-lane stores
   static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = -1, atomic = 0,
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0;
+};
+template <> struct EpiSpec<4> {      // activation gradients (dgrad): accumulator -> bf16, nothing else
+  static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = 0, atomic = 0,
                        row_map = 0, wide = 1, out_bf16 = 1, dual = 0;
 };
 template <> struct EpiSpec<5> {      // fc2 forward: + bias, (DropPath row scale), + residual, fp32 out through TMA stores
@@ -649,6 +653,7 @@ static int dispatch_gemm(int a_mn, int b_mn, const CUtensorMap& ta, const CUtens
   if (ep.spec == 1 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, true, 1>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.spec == 2 && !a_mn && b_mn) return launch_gemm<0, 1, BN, false, false, 2>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.spec == 3 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, false, 3>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (ep.spec == 4 && !a_mn && b_mn) return launch_gemm<0, 1, BN, false, false, 4>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.spec == 5 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, true, 5>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.spec == 6 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, false, 6>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.tma_out & 1) {
@@ -756,6 +761,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if (plain && e->out_is_bf16 && e->scale_cols <= 0 && ep.tma_out == 3 && e->bias && e->act == 1 && e->out_pre && !e->gelu_pre) ep.spec = 1;
     else if (plain && e->out_is_bf16 && e->scale_cols <= 0 && ep.tma_out == 0 && !e->bias && !e->act && !e->out_pre && e->gelu_pre) ep.spec = 2;
     else if (plain && e->out_is_bf16 && ep.tma_out == 0 && e->bias && !e->act && !e->out_pre && !e->gelu_pre) ep.spec = 3;
+    else if (plain && e->out_is_bf16 && e->scale_cols <= 0 && ep.tma_out == 0 && !e->bias && !e->act && !e->out_pre && !e->gelu_pre) ep.spec = 4;
     else if (!e->out_is_bf16 && e->bias && e->residual && !e->act && !e->out_pre && !e->gelu_pre && e->scale_cols <= 0) {
       if (!e->window && ep.tma_out == 1) ep.spec = 5;
       else if (e->window && ep.tma_out == 0) ep.spec = 6;
