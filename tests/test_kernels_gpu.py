@@ -87,6 +87,47 @@ def test_gemm_epilogues(ops, tma_store_mode):
     assert rel(out, base + resb.float()) < 1e-2
 
 
+def test_gemm_specialised_epilogues_match_generic(ops):
+    """The compile-time epilogue specialisations (fc1, fc2 dgrad, qkv, plain dgrad, fc2 forward, proj scatter) against the
+    generic kernel on the same inputs: same arithmetic in the same order, so the outputs agree to the last bit."""
+    M, N, K = 1000, 512, 256
+    A, B = rnd(M, K, seed=3, dtype=BF16), rnd(N, K, seed=4, scale=0.1, dtype=BF16)
+    Bt = B.t().contiguous()
+    bias, res, rs = rnd(N, seed=5), rnd(M, N, seed=6), (0.5 + torch.rand(4, generator=torch.Generator().manual_seed(1))).cuda()
+    gder = rnd(M, N, seed=7, dtype=BF16)
+    B_, D, H, W = 2, 4, 7, 14
+    wg = ops.Window(B_, D, H, W, (4, 7, 7), (2, 3, 3))
+    Aw = rnd(wg.rows, K, seed=8, dtype=BF16)
+    xw = rnd(wg.tokens, N, seed=9)
+
+    def run_all():
+        outs = []
+        o1, p1 = torch.empty(M, N, dtype=BF16, device="cuda"), torch.empty(M, N, dtype=BF16, device="cuda")
+        ops.gemm(A, B, o1, bias=bias, act="gelu", out_pre=p1); outs += [o1, p1]                  # SPEC 1
+        o2 = torch.empty(M, N, dtype=BF16, device="cuda")
+        ops.gemm(A, Bt, o2, b_t=True, gelu_pre=gder); outs.append(o2)                           # SPEC 2
+        o3 = torch.empty(M, N, dtype=BF16, device="cuda")
+        ops.gemm(A, B, o3, bias=bias, scale_cols=128, scale=0.125); outs.append(o3)                                # SPEC 3
+        o4 = torch.empty(M, N, dtype=BF16, device="cuda")
+        ops.gemm(A, Bt, o4, b_t=True); outs.append(o4)                                                            # SPEC 4
+        o5 = torch.empty(M, N, dtype=F32, device="cuda")
+        ops.gemm(A, B, o5, bias=bias, residual=res, row_scale=rs, row_scale_rows=250); outs.append(o5)             # SPEC 5
+        o6 = torch.empty(wg.tokens, N, dtype=F32, device="cuda")
+        ops.gemm(Aw, B, o6, bias=bias, residual=xw, window=wg, row_scale=rs[:2].contiguous(), row_scale_rows=wg.rows // 2)
+        outs.append(o6)                                                                                            # SPEC 6
+        return outs
+    try:
+        ops.set_tunable("gemm_spec", 0)
+        ref = run_all()
+        ops.set_tunable("gemm_spec", 1)
+        got = run_all()
+    finally:
+        ops.set_tunable("gemm_spec", -1)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert torch.equal(g, r), (i, rel(g, r))
+    assert rel(got[5], (A.float() @ B.float().t() + bias) * rs.repeat_interleave(250)[:, None] + res) < 2e-3
+
+
 def test_gemm_window_scatter(ops):
     # proj GEMM + window_reverse + roll back + residual, with spatial padding
     B_, D, H, W, Cc = 2, 4, 10, 9, 64
