@@ -168,31 +168,31 @@ CLV_DEVICE void store_row(void* base, int is_bf16, bool wide, int ncols, const f
 // value -1: decided at run time
 template <int SPEC> struct EpiSpec {
   static constexpr int bias = -1, act = -1, out_pre = -1, gelu_pre = -1, residual = -1, row_scale = -1, scale = -1, atomic = -1,
-                       row_map = -1, wide = -1, out_bf16 = -1, dual = -1;
+                       row_map = -1, wide = -1, out_bf16 = -1, dual = -1, pipe = 0;
 };
 template <> struct EpiSpec<1> {
   static constexpr int bias = 1, act = 1, out_pre = 1, gelu_pre = 0, residual = 0, row_scale = 0, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 1;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 1, pipe = 0;
 };
 template <> struct EpiSpec<2> {
   static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 1, residual = 0, row_scale = 0, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 0;
 };
 template <> struct EpiSpec<3> {      // qkv: + bias, q columns scaled (run-time column count), bf16 out, per-lane stores
   static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = -1, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 1;
 };
 template <> struct EpiSpec<4> {      // activation gradients (dgrad): accumulator -> bf16, nothing else
   static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 1;
 };
 template <> struct EpiSpec<5> {      // fc2 forward: + bias, (DropPath row scale), + residual, fp32 out through TMA stores
   static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 1, row_scale = -1, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 0, dual = 0;
+                       row_map = 0, wide = 1, out_bf16 = 0, dual = 0, pipe = 0;
 };
 template <> struct EpiSpec<6> {      // proj: + bias, (DropPath row scale), + residual, fp32 out scattered through window_reverse
   static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 1, row_scale = -1, scale = 0, atomic = 0,
-                       row_map = 1, wide = 1, out_bf16 = 0, dual = 0;
+                       row_map = 1, wide = 1, out_bf16 = 0, dual = 0, pipe = 0;
 };
 #define EPI_IS(field, runtime) (S::field < 0 ? (runtime) : (S::field != 0))
 
@@ -541,6 +541,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (dual) tma_store_2d(&tma_pre, stg + 1024, n0, box_row);
             tma_store_commit();
           }
+        }
+      } else if constexpr (S::pipe == 1) {
+        // bias (+ q-scale) / plain bf16 epilogues need so few registers that the NEXT step's accumulator load can be in flight
+        // while the current step is converted and stored: tcgen05.wait::ld waits for every outstanding load, so the next load
+        // is issued right after the wait and overlaps the math / stores of the current step
+        uint32_t rb[2][EC];
+        tmem_ld_32x16(tacc, rb[0]);
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int n0 = n_idx * BN + chalf * CPW + c * EC;
+          const bool live = row_ok && n0 < N;
+          [[maybe_unused]] float4 hb[EC / 4];
+          if constexpr (S::bias == 1) {
+            if (live) {
+#pragma unroll
+              for (int q = 0; q < EC / 4; ++q) hb[q] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
+            }
+          }
+          tmem_ld_wait();
+          if (c + 1 < CHUNKS) tmem_ld_32x16(tacc + (c + 1) * EC, rb[(c + 1) & 1]);
+          if (!live) continue;
+          float v[EC];
+#pragma unroll
+          for (int j = 0; j < EC; ++j) v[j] = __uint_as_float(rb[c & 1][j]);
+          if constexpr (S::bias == 1) {
+#pragma unroll
+            for (int q = 0; q < EC / 4; ++q) {
+              v[q * 4] += hb[q].x; v[q * 4 + 1] += hb[q].y; v[q * 4 + 2] += hb[q].z; v[q * 4 + 3] += hb[q].w;
+            }
+          }
+          if (EPI_IS(scale, ep.scale_cols > n0)) {
+#pragma unroll
+            for (int j = 0; j < EC; ++j)
+              if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
+          }
+          store_row<EC>(reinterpret_cast<__nv_bfloat16*>(ep.out) + row * ep.ld_out + n0, 1, true, EC, v);
         }
       } else {
 #pragma unroll 1
