@@ -63,6 +63,7 @@ struct GemmEpi {
   int use_row_map;
   int vec32;                // every pointer / pitch 32-byte aligned and N % 32 == 0: 256-bit global accesses
   int spec;                 // host: EpiSpec specialisation this epilogue matches exactly (0 = none)
+  int atomic_vec;           // split-K / accumulate output rows are 16-byte aligned: 4-wide fp32 reductions
   int tma_out;              // bit 0: `out` leaves through TMA stores (tensor map tma_out), bit 1: `out_pre` too (tma_pre)
   const float* row_scale;   // per row-group factor on (acc + bias) before the residual (DropPath), or nullptr
   long long row_scale_rows;
@@ -73,6 +74,9 @@ struct GemmEpi {
 CLV_DEVICE void ld256(const void* p, uint32_t (&r)[8]) {
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+CLV_DEVICE void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 CLV_DEVICE void st256(void* p, const uint32_t (&r)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -587,9 +591,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const bool wide = EPI_IS(wide, ep.vec32 != 0);
           if (EPI_IS(atomic, ep.atomic_out)) {
             float* o = reinterpret_cast<float*>(ep.out) + drow * ep.ld_out + n0;
+            if (ep.atomic_vec) {          // 16-byte aligned rows: one 4-wide reduction per four columns (a quarter of the L2 atomics)
 #pragma unroll
-            for (int j = 0; j < EC; ++j)
-              if (j < ncols) atomicAdd(o + j, v[j]);
+              for (int q = 0; q < EC / 4; ++q)
+                if (q * 4 < ncols) red_add_v4(o + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < EC; ++j)
+                if (j < ncols) atomicAdd(o + j, v[j]);
+            }
             continue;
           }
           if (EPI_IS(act, ep.act == 1) && EPI_IS(out_pre, ep.out_pre != nullptr)) {
@@ -752,6 +762,7 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     k_splits = (num_kb + per - 1) / per;
   }
   ep.atomic_out = k_splits > 1 || e->accumulate;
+  ep.atomic_vec = ep.atomic_out && (reinterpret_cast<uintptr_t>(e->out) & 15) == 0 && e->ld_out % 4 == 0;
   if (ep.atomic_out) {
     CLV_REQUIRE(!e->out_is_bf16 && !e->bias && !e->residual && !e->act && !e->gelu_pre && !e->window && !e->row_scale,
                 "clv_gemm_bf16: split-K / accumulate supports plain fp32 output only");

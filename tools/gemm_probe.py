@@ -29,6 +29,13 @@ SHAPES = [
     (2048, 512, 50176, 1, 1, "", "o32", 9), (2048, 512, 50176, 1, 1, "", "o32", 18),
     (1536, 512, 50176, 1, 1, "", "o32", 6), (1536, 512, 50176, 1, 1, "", "o32", 12), (1536, 512, 50176, 1, 1, "", "o32", 24),
     (512, 512, 50176, 1, 1, "", "o32", 9), (512, 512, 50176, 1, 1, "", "o32", 37),
+    # BERT-base text encoder weight gradients at the c3 batch (4096 caption tokens; tag: K=4096) and the fusion encoder's (K=29184)
+    (3072, 768, 4096, 1, 1, "", "o32", 1), (3072, 768, 4096, 1, 1, "", "o32", 2), (3072, 768, 4096, 1, 1, "", "o32", 4),
+    (768, 3072, 4096, 1, 1, "", "o32", 1), (768, 3072, 4096, 1, 1, "", "o32", 2), (768, 3072, 4096, 1, 1, "", "o32", 4),
+    (2304, 768, 4096, 1, 1, "", "o32", 1), (2304, 768, 4096, 1, 1, "", "o32", 2), (2304, 768, 4096, 1, 1, "", "o32", 4),
+    (768, 768, 4096, 1, 1, "", "o32", 2), (768, 768, 4096, 1, 1, "", "o32", 4), (768, 768, 4096, 1, 1, "", "o32", 8),
+    (768, 768, 4096, 1, 1, "", "o32", 16),
+    (4096, 3072, 768, 0, 0, "bg", "o16", 1), (4096, 768, 3072, 0, 0, "b", "o16", 1), (4096, 2304, 768, 0, 0, "b", "o16", 1),
 ]
 
 
