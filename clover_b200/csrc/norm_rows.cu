@@ -128,8 +128,11 @@ __global__ void __launch_bounds__(256) lnr_fwd_kernel(LnrArgs a) {
   }
 }
 
-template <int V, int L, bool XB, bool DYB, bool DXS>
-__global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs a) {
+// DRES: a residual-stream gradient is added (Swin blocks).  Without it (BERT / fusion / final norms) the V float4 that would hold
+// it are not allocated, which lets the V = 6 (C = 768) instantiation fit two CTAs per SM: these kernels are latency-bound on
+// their row loads and 8 warps per SM left the 29184 x 768 fusion LayerNorm at 1.4 TB/s.
+template <int V, int L, bool XB, bool DYB, bool DXS, bool DRES>
+__global__ void __launch_bounds__(256, ((V <= 4 || (V <= 6 && !DRES && !DXS)) ? 2 : 1)) lnr_bwd_kernel(LnrArgs a) {
   constexpr int G = 32 / L;
   extern __shared__ float red[];          // [3][C]: dgamma | dbeta | dx column sums of this CTA
   const int lane = threadIdx.x & 31, sub = lane % L, grp = lane / L;
@@ -154,20 +157,21 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
         lnr_prefetch_row<L>(a.x, (size_t)sn * a.C * (XB ? 2 : 4), a.C * (XB ? 2 : 4), sub);
         const unsigned dn = a.dy_mapped ? lnr_mapped(a, sn) : sn;
         lnr_prefetch_row<L>(a.dy, (size_t)dn * a.C * (DYB ? 2 : 4), a.C * (DYB ? 2 : 4), sub);
-        if (a.dres) lnr_prefetch_row<L>(a.dres, (size_t)sn * a.C * 4, a.C * 4, sub);
+        if (DRES) lnr_prefetch_row<L>(a.dres, (size_t)sn * a.C * 4, a.C * 4, sub);
       }
     }
-    float4 xh[V], d[V], rr[V];
+    float4 xh[V], d[V], rr[DRES ? V : 1];
     float mu = 0.f, rs = 0.f;
     if (live) { mu = a.mean[s]; rs = a.rstd[s]; }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int c = 4 * (sub + L * j);
-      xh[j] = d[j] = rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[j] = d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (DRES) rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) {
         xh[j] = lnr_ld<XB>(a.x, (size_t)s * a.C + c);
         d[j] = lnr_ld<DYB>(a.dy, (size_t)dyrow * a.C + c);
-        if (a.dres) rr[j] = *reinterpret_cast<const float4*>(a.dres + (size_t)s * a.C + c);
+        if (DRES) rr[j] = *reinterpret_cast<const float4*>(a.dres + (size_t)s * a.C + c);
       }
     }
     if (DXS && a.row_w) {            // d(LN out) = dy (1 - w); the token takes dy w
@@ -201,8 +205,9 @@ __global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1)) lnr_bwd_kernel(LnrArgs 
     for (int j = 0; j < V; ++j) {
       const int c = 4 * (sub + L * j);
       float4 o;
-      o.x = fmaf(rs, d[j].x - s2 - xh[j].x * s1, rr[j].x); o.y = fmaf(rs, d[j].y - s2 - xh[j].y * s1, rr[j].y);
-      o.z = fmaf(rs, d[j].z - s2 - xh[j].z * s1, rr[j].z); o.w = fmaf(rs, d[j].w - s2 - xh[j].w * s1, rr[j].w);
+      const float4 r4 = DRES ? rr[DRES ? j : 0] : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = fmaf(rs, d[j].x - s2 - xh[j].x * s1, r4.x); o.y = fmaf(rs, d[j].y - s2 - xh[j].y * s1, r4.y);
+      o.z = fmaf(rs, d[j].z - s2 - xh[j].z * s1, r4.z); o.w = fmaf(rs, d[j].w - s2 - xh[j].w * s1, r4.w);
       if (a.dx) *reinterpret_cast<float4*>(a.dx + (size_t)s * a.C + c) = o;
       o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;          // the branch copy / bias gradient carry the DropPath factor
       if (a.dx16) lnr_st<true>(a.dx16, (size_t)crow * a.C + c, o);
@@ -271,15 +276,17 @@ static bool lnr_shape(int C, int& V, int& L) {
   else if (L == 32 && V == 6) KERNEL<6, 32, XB, OB> __VA_ARGS__;              \
   else KERNEL<8, 32, XB, OB> __VA_ARGS__;
 
+#define LNR_SHAPES_B2(XB, OB, S, R, ...)                                      \
+  if (L == 8 && V == 3) lnr_bwd_kernel<3, 8, XB, OB, S, R> __VA_ARGS__;       \
+  else if (L == 8 && V == 4) lnr_bwd_kernel<4, 8, XB, OB, S, R> __VA_ARGS__;  \
+  else if (L == 16 && V == 3) lnr_bwd_kernel<3, 16, XB, OB, S, R> __VA_ARGS__; \
+  else if (L == 16 && V == 4) lnr_bwd_kernel<4, 16, XB, OB, S, R> __VA_ARGS__; \
+  else if (L == 32 && V == 3) lnr_bwd_kernel<3, 32, XB, OB, S, R> __VA_ARGS__; \
+  else if (L == 32 && V == 4) lnr_bwd_kernel<4, 32, XB, OB, S, R> __VA_ARGS__; \
+  else if (L == 32 && V == 6) lnr_bwd_kernel<6, 32, XB, OB, S, R> __VA_ARGS__; \
+  else lnr_bwd_kernel<8, 32, XB, OB, S, R> __VA_ARGS__;
 #define LNR_SHAPES_B(XB, OB, S, ...)                                          \
-  if (L == 8 && V == 3) lnr_bwd_kernel<3, 8, XB, OB, S> __VA_ARGS__;          \
-  else if (L == 8 && V == 4) lnr_bwd_kernel<4, 8, XB, OB, S> __VA_ARGS__;     \
-  else if (L == 16 && V == 3) lnr_bwd_kernel<3, 16, XB, OB, S> __VA_ARGS__;   \
-  else if (L == 16 && V == 4) lnr_bwd_kernel<4, 16, XB, OB, S> __VA_ARGS__;   \
-  else if (L == 32 && V == 3) lnr_bwd_kernel<3, 32, XB, OB, S> __VA_ARGS__;   \
-  else if (L == 32 && V == 4) lnr_bwd_kernel<4, 32, XB, OB, S> __VA_ARGS__;   \
-  else if (L == 32 && V == 6) lnr_bwd_kernel<6, 32, XB, OB, S> __VA_ARGS__;   \
-  else lnr_bwd_kernel<8, 32, XB, OB, S> __VA_ARGS__;
+  if (has_dres) { LNR_SHAPES_B2(XB, OB, S, true, __VA_ARGS__) } else { LNR_SHAPES_B2(XB, OB, S, false, __VA_ARGS__) }
 
 #define LNR_DISPATCH(KERNEL, xb, ob, ...)                                     \
   if (xb) { if (ob) { LNR_SHAPES(KERNEL, true, true, __VA_ARGS__) } else { LNR_SHAPES(KERNEL, true, false, __VA_ARGS__) } } \
@@ -339,6 +346,7 @@ extern "C" int clv_lnr_bwd(const clv_lnr_desc_t* d, const clv_lnr_bwd_t* b, void
   const long long blocks = std::min<long long>(((long long)a.rows + rows_per_block - 1) / rows_per_block, (long long)num_sms() * 2);
   const size_t smem = 3 * (size_t)a.C * sizeof(float);
   const bool xb = d->x_is_bf16 != 0, dyb = b->dy_is_bf16 != 0;
+  const bool has_dres = b->dres != nullptr;
   a.dxsum = b->dxsum;
   if (a.row_w) {
     // patch-embed LN with the mask-token blend: fp32 x and dy, dtoken rides in the column-sum accumulators
