@@ -644,6 +644,7 @@ struct W7BwdArgs {
   int pipe;                      // issue dV / dK steps chunk by chunk while the softmax warps are still working
   __nv_bfloat16* dkv_part;       // bwd2 with 392 keys: dK | dV partial sums of the second query half, bf16 [rows, 2 C]
   long long ds_half_rows;        // bwd2 with 392 keys: row offset of the second query half in the dS^T dump
+  int early;                     // bwd2: score MMAs of tile g + 1 are issued before the dQ products of tile g
   int l2_hint;                   // bwd2, dump_ds == 2: streamed operands evict-first, the accumulation buffers evict-last
   int ds_spans;                  // dump_ds == 2 (bwd2): dS^T tiles are ADDED (TMA reduce, bf16) into per-CTA buffers
                                  // [gridDim.x][ds_spans heads][query halves][keys][nq] that stay in L2; ds_spans = max number of
@@ -1080,28 +1081,34 @@ CLV_DEVICE void w7_ds_store(uint8_t* ds_row, int rsw, uint32_t a, uint32_t b, ui
   *reinterpret_cast<uint4*>(ds_row + (I8 >> 6) * 16384 + ((((I8 >> 3) & 7) ^ rsw) * 16)) = make_uint4(a, b, c, d);
 }
 
-// 48 query columns [I0, I0 + 48) of one key row: TMEM (S^T at ts, dP^T at td, column 0 = query I0) -> packed in place
+// 48 query columns [I0, I0 + 48) of one key row: TMEM (S^T at ts, dP^T at td, column 0 = query I0) -> P^T / dS^T packed in place
+// (operands of the dV / dK steps); the dS^T values are returned in dk / dk2 for the shared tile the dQ products read.
 template <int I0>
-CLV_DEVICE void w7_bwd2_body(uint32_t ts, uint32_t td, const float* tbj, uint8_t* ds_row, int rsw, bool valid) {
-  uint32_t v[32], w[32], v2[16], w2[16], pk[16], dk[16];
+CLV_DEVICE void w7_bwd2_compute(uint32_t ts, uint32_t td, const float* tbj, uint32_t (&dk)[16], uint32_t (&dk2)[8]) {
+  uint32_t v[32], w[32], v2[16], w2[16], pk[16];
   tmem_ld_32x32(ts, v); tmem_ld_32x32(td, w); tmem_ld_wait();
   tmem_ld_32x16(ts + 32, v2); tmem_ld_32x16(td + 32, w2);
   w7_bwd_chunk<I0, 32>(v, w, tbj, pk, dk);
   tmem_st_32x16(ts, pk); tmem_st_32x16(td, dk);
-  if (valid) {
-    w7_ds_store<I0>(ds_row, rsw, dk[0], dk[1], dk[2], dk[3]);
-    w7_ds_store<I0 + 8>(ds_row, rsw, dk[4], dk[5], dk[6], dk[7]);
-    w7_ds_store<I0 + 16>(ds_row, rsw, dk[8], dk[9], dk[10], dk[11]);
-    w7_ds_store<I0 + 24>(ds_row, rsw, dk[12], dk[13], dk[14], dk[15]);
-  }
   tmem_ld_wait();
-  uint32_t pk2[8], dk2[8];
+  uint32_t pk2[8];
   w7_bwd_chunk<I0 + 32, 16>(v2, w2, tbj, pk2, dk2);
   tmem_st_32x8(ts + 16, pk2); tmem_st_32x8(td + 16, dk2);
-  if (valid) {
-    w7_ds_store<I0 + 32>(ds_row, rsw, dk2[0], dk2[1], dk2[2], dk2[3]);
-    w7_ds_store<I0 + 40>(ds_row, rsw, dk2[4], dk2[5], dk2[6], dk2[7]);
-  }
+}
+template <int I0>
+CLV_DEVICE void w7_bwd2_store(uint8_t* ds_row, int rsw, const uint32_t (&dk)[16], const uint32_t (&dk2)[8]) {
+  w7_ds_store<I0>(ds_row, rsw, dk[0], dk[1], dk[2], dk[3]);
+  w7_ds_store<I0 + 8>(ds_row, rsw, dk[4], dk[5], dk[6], dk[7]);
+  w7_ds_store<I0 + 16>(ds_row, rsw, dk[8], dk[9], dk[10], dk[11]);
+  w7_ds_store<I0 + 24>(ds_row, rsw, dk[12], dk[13], dk[14], dk[15]);
+  w7_ds_store<I0 + 32>(ds_row, rsw, dk2[0], dk2[1], dk2[2], dk2[3]);
+  w7_ds_store<I0 + 40>(ds_row, rsw, dk2[4], dk2[5], dk2[6], dk2[7]);
+}
+template <int I0>
+CLV_DEVICE void w7_bwd2_body(uint32_t ts, uint32_t td, const float* tbj, uint8_t* ds_row, int rsw, bool valid) {
+  uint32_t dk[16], dk2[8];
+  w7_bwd2_compute<I0>(ts, td, tbj, dk, dk2);
+  if (valid) w7_bwd2_store<I0>(ds_row, rsw, dk, dk2);
 }
 
 // KSEQ = 196: unit = (window, head).  KSEQ = 392 (the full (8,7,7) window of 16-frame clips and of BASELINE config c2):
@@ -1225,92 +1232,103 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
       const uint32_t idesc_dq = make_idesc_bf16(128, W7_HD, 1, 1);
       const uint32_t idesc_c96 = make_idesc_bf16(128, 96, 0, 0), idesc_c16 = make_idesc_bf16(128, 16, 0, 0);
       const uint64_t desc_vx = make_smem_desc(smem_u32(sVx), 16, 256, 6);
-      uint32_t it = 0, tt = 0;
       uint32_t nuse0 = 0, nuse1 = 0;          // completed uses of buffer 0 / 1 (barrier phases)
-      for (long long u = u_begin; u < u_end; ++u, ++it) {
-        const int us = it & 1;
-        mbar_wait(&qdo_full[us], (it >> 1) & 1);
-        mbar_wait(dq_free, (it & 1) ^ 1);
+      const long long G = (u_end - u_begin) * NKT;      // key tiles this CTA walks (NKT per unit)
+      // scores of one chunk of tile g: S^T = [K_t | kx] [Q_c | e_c]^T and dP^T = [V_t | vx] [dO_c | e_c]^T into buffer `buf`
+      auto mma1 = [&](long long g, int c, int buf) {
+        const uint32_t q_addr = smem_u32(sQdO + ((g / NKT) & 1) * unit_bytes);
+        const uint32_t do_addr = q_addr + a.qb_bytes, e_addr = do_addr + a.qb_bytes;
+        const uint32_t k_addr = smem_u32(sKV + (g & 1) * tile_bytes), v_addr = k_addr + 8192;
+        const uint64_t desc_kx = make_smem_desc(v_addr + 8192, 16, 256, 6);
+        const uint32_t idesc = c < 2 ? idesc_c96 : idesc_c16;
+        const uint32_t ds_ = tmem_base + buf * W7B2_BUF, dp_ = ds_ + W7B2_CH;
+        const uint32_t qo = c * W7B2_CH * W7_ROWB, eo = c * W7B2_CH * W7_XROWB;
+        const uint64_t desc_e = make_smem_desc(e_addr + eo, 16, 256, 6);
+#pragma unroll
+        for (int k = 0; k < W7_HD / 16; ++k)
+          umma_bf16_ss(ds_, make_smem_desc(k_addr + k * 32, 16, 512, 4), make_smem_desc(q_addr + qo + k * 32, 16, 512, 4), idesc, k > 0);
+        umma_bf16_ss(ds_, desc_kx, desc_e, idesc, 1);
+#pragma unroll
+        for (int k = 0; k < W7_HD / 16; ++k)
+          umma_bf16_ss(dp_, make_smem_desc(v_addr + k * 32, 16, 512, 4), make_smem_desc(do_addr + qo + k * 32, 16, 512, 4), idesc, k > 0);
+        umma_bf16_ss(dp_, desc_vx, desc_e, idesc, 1);
+        umma_commit(&s_ready[buf]);
+      };
+      // operands of tile g have landed -> score MMAs of its first two chunks
+      auto scores01 = [&](long long g) {
+        const uint32_t it = (uint32_t)(g / NKT);
+        if (g % NKT == 0) mbar_wait(&qdo_full[it & 1], (it >> 1) & 1);
+        mbar_wait(&kv_full[g & 1], (uint32_t)(g >> 1) & 1);
+        tc_fence_after();
+        mma1(g, 0, 0);
+        mma1(g, 1, 1);
+      };
+      // Tile order.  early == 0: scores(g), dV/dK(g), dQ(g).  early == 1: the score MMAs of tile g + 1 are issued BEFORE the dQ
+      // products of tile g, so the softmax warps exponentiate the first chunk of the next tile while the tensor pipe works
+      // through the 16 dQ instructions (they used to idle there, and the pipe idled at the start of every tile).
+      if (a.early && G > 0) scores01(0);
+      for (long long g = 0; g < G; ++g) {
+        const uint32_t it = (uint32_t)(g / NKT);
+        const int t = (int)(g % NKT);
+        const long long u = u_begin + it;
+        const int us = it & 1, ts = (int)(g & 1);
         const uint32_t q_addr = smem_u32(sQdO + us * unit_bytes);
         const uint32_t do_addr = q_addr + a.qb_bytes;
-        const uint32_t e_addr = do_addr + a.qb_bytes;
-        for (int t = 0; t < NKT; ++t, ++tt) {
-          const int ts = tt & 1;
-          mbar_wait(&kv_full[ts], (tt >> 1) & 1);
-          tc_fence_after();
-          const uint32_t k_addr = smem_u32(sKV + ts * tile_bytes);
-          const uint32_t v_addr = k_addr + 8192;
-          const uint64_t desc_kx = make_smem_desc(v_addr + 8192, 16, 256, 6);
-          // scores of one chunk: S^T = [K_t | kx] [Q_c | e_c]^T and dP^T = [V_t | vx] [dO_c | e_c]^T into buffer `buf`
-          auto mma1 = [&](int c, int buf) {
-            const uint32_t idesc = c < 2 ? idesc_c96 : idesc_c16;
-            const uint32_t ds_ = tmem_base + buf * W7B2_BUF, dp_ = ds_ + W7B2_CH;
-            const uint32_t qo = c * W7B2_CH * W7_ROWB, eo = c * W7B2_CH * W7_XROWB;
-            const uint64_t desc_e = make_smem_desc(e_addr + eo, 16, 256, 6);
-#pragma unroll
-            for (int k = 0; k < W7_HD / 16; ++k)
-              umma_bf16_ss(ds_, make_smem_desc(k_addr + k * 32, 16, 512, 4), make_smem_desc(q_addr + qo + k * 32, 16, 512, 4), idesc, k > 0);
-            umma_bf16_ss(ds_, desc_kx, desc_e, idesc, 1);
-#pragma unroll
-            for (int k = 0; k < W7_HD / 16; ++k)
-              umma_bf16_ss(dp_, make_smem_desc(v_addr + k * 32, 16, 512, 4), make_smem_desc(do_addr + qo + k * 32, 16, 512, 4), idesc, k > 0);
-            umma_bf16_ss(dp_, desc_vx, desc_e, idesc, 1);
-            umma_commit(&s_ready[buf]);
-          };
-          // dV_t += P^T_c dO_c ; dK_t += dS^T_c Q_c : K-steps of 16 queries; packed operands of warp group g at [48 g, 48 g + 24)
-          auto mma_dvk = [&](int c, int buf, uint32_t& acc) {
-            const uint32_t ps = tmem_base + buf * W7B2_BUF, pd = ps + W7B2_CH;
-            const int nsteps = c < 2 ? 6 : 1;
-            for (int s = 0; s < nsteps; ++s) {
-              const uint32_t pc = (s < 3 ? 0 : 48) + (s % 3) * 8;
-              const uint32_t ro = (c * W7B2_CH + s * 16) * W7_ROWB;     // 16 query rows = 1024 bytes
-              umma_bf16_ts(tmem_base + W7B2_DV, ps + pc, make_smem_desc(do_addr + ro, 16, 512, 4), idesc_ts, acc);
-              umma_bf16_ts(tmem_base + W7B2_DK, pd + pc, make_smem_desc(q_addr + ro, 16, 512, 4), idesc_ts, acc);
-              acc = 1;
-            }
-          };
-          uint32_t acc = 0;
-          mma1(0, 0);
-          mma1(1, 1);
-          mbar_wait(&p_ready[0], nuse0 & 1); ++nuse0;
-          mbar_wait(acc_free, (tt & 1) ^ 1);            // previous tile's dV / dK have been read
-          tc_fence_after();
-          mma_dvk(0, 0, acc);
-          mma1(2, 0);                                   // executes after the dV/dK steps that read buffer 0
-          mbar_wait(&p_ready[1], nuse1 & 1); ++nuse1;
-          tc_fence_after();
-          mma_dvk(1, 1, acc);
-          mbar_wait(&p_ready[0], nuse0 & 1); ++nuse0;
-          tc_fence_after();
-          mma_dvk(2, 0, acc);
-          umma_commit(dvk_done);
-          if (a.dump_ds == 2) {
-            const int hh = (int)((u / NH) / a.batch), h_first = (int)((u_begin / NH) / a.batch);
-            const int buf = ((int)blockIdx.x * a.ds_spans + (hh - h_first)) * NH + (int)(u % NH);
-            const int grow = buf * KSEQ + t * W7_TILE;
-            if (a.l2_hint) {
-              const uint64_t pol_keep = l2_policy_evict_last();
-              for (int q = 0; q < 4; ++q) tma_reduce_add_2d_hint(&tm_ds, sDS + q * 16384, q * 64, grow, pol_keep);
-            } else {
-              for (int q = 0; q < 4; ++q) tma_reduce_add_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
-            }
-            tma_store_commit();
-          } else if (a.dump_ds) {
-            const long long uu = u / NH;
-            const int grow = (int)((u % NH) * a.ds_half_rows + ((uu % a.batch) * a.heads + (uu / a.batch)) * KSEQ) + t * W7_TILE;
-            for (int q = 0; q < 4; ++q) tma_store_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
-            tma_store_commit();
+        const uint32_t k_addr = smem_u32(sKV + ts * tile_bytes);
+        if (!a.early) scores01(g);
+        // dV_t += P^T_c dO_c ; dK_t += dS^T_c Q_c : K-steps of 16 queries; packed operands of warp group g at [48 g, 48 g + 24)
+        auto mma_dvk = [&](int c, int buf, uint32_t& acc) {
+          const uint32_t ps = tmem_base + buf * W7B2_BUF, pd = ps + W7B2_CH;
+          const int nsteps = c < 2 ? 6 : 1;
+          for (int s = 0; s < nsteps; ++s) {
+            const uint32_t pc = (s < 3 ? 0 : 48) + (s % 3) * 8;
+            const uint32_t ro = (c * W7B2_CH + s * 16) * W7_ROWB;     // 16 query rows = 1024 bytes
+            umma_bf16_ts(tmem_base + W7B2_DV, ps + pc, make_smem_desc(do_addr + ro, 16, 512, 4), idesc_ts, acc);
+            umma_bf16_ts(tmem_base + W7B2_DK, pd + pc, make_smem_desc(q_addr + ro, 16, 512, 4), idesc_ts, acc);
+            acc = 1;
           }
-          const uint32_t ds_addr = smem_u32(sDS);
-          for (int mq = 0; mq < 2; ++mq)           // dQ[mq] += dS K_t   (K = 128 keys of this tile; rows >= 98 of dS^T are zero)
-            for (int ks = 0; ks < 8; ++ks)
-              umma_bf16_ss(tmem_base + W7B2_DQ + mq * W7_HD, make_smem_desc(ds_addr + mq * 2 * 16384 + ks * 2048, 16384, 1024, 2),
-                           make_smem_desc(k_addr + ks * 1024, 16, 512, 4), idesc_dq, (t > 0 || ks > 0) ? 1u : 0u);
-          if (a.dump_ds) tma_store_wait_read();     // (the dQ products above were only issued; the stores finish reading first)
-          umma_commit(mma2_done);
-          umma_commit(&kv_empty[ts]);
-          if (t == NKT - 1) umma_commit(&qdo_empty[us]);
+        };
+        uint32_t acc = 0;
+        mbar_wait(&p_ready[0], nuse0 & 1); ++nuse0;
+        mbar_wait(acc_free, (uint32_t)(g & 1) ^ 1);   // previous tile's dV / dK have been read
+        tc_fence_after();
+        mma_dvk(0, 0, acc);
+        mma1(g, 2, 0);                                // executes after the dV/dK steps that read buffer 0
+        mbar_wait(&p_ready[1], nuse1 & 1); ++nuse1;
+        tc_fence_after();
+        mma_dvk(1, 1, acc);
+        mbar_wait(&p_ready[0], nuse0 & 1); ++nuse0;
+        tc_fence_after();
+        mma_dvk(2, 0, acc);
+        umma_commit(dvk_done);
+        if (a.early && g + 1 < G) scores01(g + 1);
+        if (a.dump_ds == 2) {
+          const int hh = (int)((u / NH) / a.batch), h_first = (int)((u_begin / NH) / a.batch);
+          const int buf = ((int)blockIdx.x * a.ds_spans + (hh - h_first)) * NH + (int)(u % NH);
+          const int grow = buf * KSEQ + t * W7_TILE;
+          if (a.l2_hint) {
+            const uint64_t pol_keep = l2_policy_evict_last();
+            for (int q = 0; q < 4; ++q) tma_reduce_add_2d_hint(&tm_ds, sDS + q * 16384, q * 64, grow, pol_keep);
+          } else {
+            for (int q = 0; q < 4; ++q) tma_reduce_add_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
+          }
+          tma_store_commit();
+        } else if (a.dump_ds) {
+          const long long uu = u / NH;
+          const int grow = (int)((u % NH) * a.ds_half_rows + ((uu % a.batch) * a.heads + (uu / a.batch)) * KSEQ) + t * W7_TILE;
+          for (int q = 0; q < 4; ++q) tma_store_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
+          tma_store_commit();
         }
+        if (t == 0) mbar_wait(dq_free, (it & 1) ^ 1);     // the previous unit's dQ accumulators have been read out
+        const uint32_t ds_addr = smem_u32(sDS);
+        for (int mq = 0; mq < 2; ++mq)           // dQ[mq] += dS K_t   (98 keys of this tile: K steps of 16 up to 112; rows >= 98 of
+          for (int ks = 0; ks < 7; ++ks)         //  dS^T are zero, so the step over keys [112, 128) would add nothing)
+            umma_bf16_ss(tmem_base + W7B2_DQ + mq * W7_HD, make_smem_desc(ds_addr + mq * 2 * 16384 + ks * 2048, 16384, 1024, 2),
+                         make_smem_desc(k_addr + ks * 1024, 16, 512, 4), idesc_dq, (t > 0 || ks > 0) ? 1u : 0u);
+        if (a.dump_ds) tma_store_wait_read();     // (the dQ products above were only issued; the stores finish reading first)
+        umma_commit(mma2_done);
+        umma_commit(&kv_empty[ts]);
+        if (t == NKT - 1) umma_commit(&qdo_empty[us]);
       }
       if (a.dump_ds) tma_store_wait_all();
     }
@@ -1326,6 +1344,9 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
     int cur_h = -1;
     uint32_t it = 0, tt = 0;
     uint32_t nuse0 = 0, nuse1 = 0;
+    const uint32_t total_tiles = (uint32_t)((u_end - u_begin) * NKT);
+    bool pend_dq = false;                      // early mode: dQ of the unit that ended with the previous tile still to be read out
+    int pend_b = 0, pend_qh = 0, pend_h = 0;
     for (long long u = u_begin; u < u_end; ++u, ++it) {
       const int qh = (int)(u % NH);
       const long long uu = u / NH;
@@ -1346,14 +1367,53 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         tc_fence_before();                                                         \
         __syncwarp();                                                              \
         if (lane == 0) mbar_arrive(&p_ready[BUF]);
-        // the previous tile's dQ products (which read the shared dS^T tile) are ordered before this tile's first
-        // score MMA, so s_ready also says the tile may be overwritten
+        // dQ of a whole unit (all key tiles accumulated) -> dqkv; query row i = grp*128 + r
+        auto dq_readout = [&](int b_, int qh_, int h_) {
+          tc_fence_after();
+          const int i = grp * 128 + r;
+          if (grp * 128 + quarter * 32 < SEQ) {
+            uint32_t oq[32];
+            tmem_ld_32x32(taddr + W7B2_DQ + grp * W7_HD, oq);
+            tmem_ld_wait();
+            if (i < SEQ) {
+              uint4* gq = reinterpret_cast<uint4*>(a.dqkv + ((long long)b_ * KSEQ + qh_ * SEQ + i) * (3 * C) + h_ * W7_HD);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                gq[q] = make_uint4(pack_bf16(__uint_as_float(oq[q * 8]) * a.q_scale, __uint_as_float(oq[q * 8 + 1]) * a.q_scale),
+                                   pack_bf16(__uint_as_float(oq[q * 8 + 2]) * a.q_scale, __uint_as_float(oq[q * 8 + 3]) * a.q_scale),
+                                   pack_bf16(__uint_as_float(oq[q * 8 + 4]) * a.q_scale, __uint_as_float(oq[q * 8 + 5]) * a.q_scale),
+                                   pack_bf16(__uint_as_float(oq[q * 8 + 6]) * a.q_scale, __uint_as_float(oq[q * 8 + 7]) * a.q_scale));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
+        };
         // ---- chunk 0: queries [0, 96) in buffer 0
         mbar_wait(&s_ready[0], nuse0 & 1); ++nuse0;
         tc_fence_after();
-        if (grp == 0) w7_bwd2_body<0>(taddr, taddr + W7B2_CH, tbj, ds_row, rsw, valid);
-        else w7_bwd2_body<48>(taddr + 48, taddr + W7B2_CH + 48, tbj, ds_row, rsw, valid);
-        W7B2_PUBLISH(0)
+        if (!a.early) {
+          // the previous tile's dQ products (which read the shared dS^T tile) are ordered before this tile's first
+          // score MMA, so s_ready also says the tile may be overwritten
+          if (grp == 0) w7_bwd2_body<0>(taddr, taddr + W7B2_CH, tbj, ds_row, rsw, valid);
+          else w7_bwd2_body<48>(taddr + 48, taddr + W7B2_CH + 48, tbj, ds_row, rsw, valid);
+          W7B2_PUBLISH(0)
+        } else {
+          // early mode: these scores were issued BEFORE the previous tile's dQ products.  Exponentiate and publish the packed
+          // operands first (that is what the dV / dK steps wait for), then wait until the dQ products -- and the dS^T dump --
+          // of the previous tile have finished reading the shared dS^T tile before overwriting it; the dQ read-out of a unit
+          // that ended with the previous tile happens here too.
+          uint32_t dk[16], dk2[8];
+          if (grp == 0) w7_bwd2_compute<0>(taddr, taddr + W7B2_CH, tbj, dk, dk2);
+          else w7_bwd2_compute<48>(taddr + 48, taddr + W7B2_CH + 48, tbj, dk, dk2);
+          W7B2_PUBLISH(0)
+          if (tt > 0) mbar_wait(mma2_done, (tt - 1) & 1);
+          if (pend_dq) { dq_readout(pend_b, pend_qh, pend_h); pend_dq = false; }
+          if (valid) {
+            if (grp == 0) w7_bwd2_store<0>(ds_row, rsw, dk, dk2);
+            else w7_bwd2_store<48>(ds_row, rsw, dk, dk2);
+          }
+        }
         // ---- chunk 1: queries [96, 192) in buffer 1
         mbar_wait(&s_ready[1], nuse1 & 1); ++nuse1;
         tc_fence_after();
@@ -1396,27 +1456,12 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
         if (t == NKT - 1) {
-          // dQ of the whole unit (all key tiles accumulated); query row i = grp*128 + r
-          mbar_wait(mma2_done, tt & 1);
-          tc_fence_after();
-          const int i = grp * 128 + r;
-          if (grp * 128 + quarter * 32 < SEQ) {
-            uint32_t oq[32];
-            tmem_ld_32x32(taddr + W7B2_DQ + grp * W7_HD, oq);
-            tmem_ld_wait();
-            if (i < SEQ) {
-              uint4* gq = reinterpret_cast<uint4*>(a.dqkv + ((long long)b * KSEQ + qh * SEQ + i) * (3 * C) + h * W7_HD);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                gq[q] = make_uint4(pack_bf16(__uint_as_float(oq[q * 8]) * a.q_scale, __uint_as_float(oq[q * 8 + 1]) * a.q_scale),
-                                   pack_bf16(__uint_as_float(oq[q * 8 + 2]) * a.q_scale, __uint_as_float(oq[q * 8 + 3]) * a.q_scale),
-                                   pack_bf16(__uint_as_float(oq[q * 8 + 4]) * a.q_scale, __uint_as_float(oq[q * 8 + 5]) * a.q_scale),
-                                   pack_bf16(__uint_as_float(oq[q * 8 + 6]) * a.q_scale, __uint_as_float(oq[q * 8 + 7]) * a.q_scale));
-            }
+          if (a.early && tt + 1 < total_tiles) {       // read out behind the next tile's first chunk (see chunk 0 above)
+            pend_dq = true; pend_b = b; pend_qh = qh; pend_h = h;
+          } else {
+            mbar_wait(mma2_done, tt & 1);
+            dq_readout(b, qh, h);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dq_free);
         }
       }
     }
@@ -1694,6 +1739,7 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   // bias-table gradient: either dump every unit's dS^T (batch * heads * seq * nq bf16, read back by attn_w7_dbias_kernel) or,
   // for the chunk-ring kernels, let TMA ADD the tiles into per-CTA buffers that stay in L2 (dump_ds == 2)
   const int gen2 = (int)tunable(TUNE_W7_BWD2, 1);
+  a.early = (int)tunable(TUNE_W7_BWD_EARLY, 1);
   const bool ring = halves || (a.seq == 196 && gen2);
   const int nh = halves ? 2 : 1;
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms());
