@@ -1634,11 +1634,13 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
     if (n1 > 0) { if (int rc = make_tmap_bf16_2d(&tkx1, d->k_ext, 16, xrows, 16, 16, n1, 32)) return rc; }
   }
   const size_t stage = 8192 + 2 * (size_t)a.kb_bytes + (a.has_ext ? 4096 + (size_t)a.kx_bytes : 0);
-  // second-generation forward (query tiles cut at multiples of 32 rows, eight softmax warps per CTA): +9 % at 392 tokens
-  // (13 instead of 16 warp-passes per window), neutral-to-slightly-slower at 196 where the first-generation kernel stays
-  // (tools/attn_microbench.py, profiles/r02*_attn_microbench*); w7_fwd2 = 1 / 0 forces one or the other
-  const long long fwd2 = tunable(TUNE_W7_FWD2, -2);
-  if (fwd2 == 1 || (fwd2 == -2 && d->wd >= 6)) {
+  // second-generation forward (query tiles cut at multiples of 32 rows, eight softmax warps per CTA, rows split between two
+  // threads with a max / sum exchange): it was +9 % at 392 tokens when written, but the first-generation kernel has since
+  // gained more from the elect.sync role entry and the barrier wait hints and is now 3-10 % faster at every size
+  // (tools/ab_w7_fwd2.py, profiles/r02x_attn_microbench_fwd_generations.jsonl), so it is the default again; w7_fwd2 = 1
+  // selects the second generation
+  const long long fwd2 = tunable(TUNE_W7_FWD2, 0);
+  if (fwd2 == 1) {
     a.n_qt = (a.seq + 127) / 128;
     a.tile_rows = a.n_qt == 1 ? a.seq : (a.seq / a.n_qt) / 32 * 32;
     a.units = (long long)d->batch * d->heads * a.n_qt;
