@@ -622,7 +622,10 @@ class PatchEmbedFn(torch.autograd.Function):
     """PatchEmbed3D (:671-688) + SimMIM mask-token blend (:222-230): patchify -> GEMM -> LN(+blend)."""
 
     @staticmethod
-    def forward(ctx, imgs, weight, bias, nw, nb, mask, token, patch, in_norm=None):
+    def forward(ctx, imgs, weight, bias, nw, nb, mask, token, patch, in_norm=None, pair=False):
+        # pair: the masked and the clean pass of CloverPretrain.forward_train see the SAME clips (pretrain.py:91-121), so the
+        # patch gather and the projection GEMM run once and only the LayerNorm (+ mask-token blend) is evaluated twice; the
+        # output holds [masked pass ; clean pass] token rows (2T rows), `mask` belongs to the first half.
         B = imgs.shape[0]
         cols, (D, Hp, Wp) = ops.patchify(imgs.contiguous(), patch, norm=in_norm)
         C = weight.shape[0]
@@ -653,7 +656,16 @@ class PatchEmbedFn(torch.autograd.Function):
             blend = (mask.reshape(B, mask.shape[-2], mask.shape[-1]).contiguous(), token.detach().reshape(-1).contiguous(),
                      (D, Hp, Wp))
         ctx.fast = ops.lnr_supported(C) and (blend is None or (Hp % mask.shape[-2] == 0 and Wp % mask.shape[-1] == 0))
-        if ctx.fast:
+        ctx.pair = bool(pair)
+        if pair:
+            if not ctx.fast or blend is None:
+                raise RuntimeError("PatchEmbedFn(pair=True) needs the row-kernel LayerNorm path and a mask")
+            w = blend[0].to(F32).repeat_interleave(Hp // mask.shape[-2], 1).repeat_interleave(Wp // mask.shape[-1], 2)
+            blend = (w[:, None].expand(B, D, Hp, Wp).reshape(-1).contiguous(), blend[1])
+            out = torch.empty(2 * T, C, dtype=F32, device=imgs.device)
+            ops.lnr_fwd(y, nw, nb, 1e-5, out[:T], mean=stats[:T], rstd=stats[T:], blend=blend)
+            ops.lnr_fwd(y, nw, nb, 1e-5, out[T:], mean=stats[:T], rstd=stats[T:])
+        elif ctx.fast:
             # lean row kernels (norm_rows.cu): the mask arrives as one fp32 weight per token row
             if blend is not None:
                 w = blend[0].to(F32).repeat_interleave(Hp // mask.shape[-2], 1).repeat_interleave(Wp // mask.shape[-1], 2)
@@ -670,7 +682,7 @@ class PatchEmbedFn(torch.autograd.Function):
         B, D, Hp, Wp, C = ctx.dims
         dout = dout.contiguous()
         _GRAD16[0] = None                 # the published bf16 copy of d(tokens) has no consumer here
-        T = dout.shape[0]
+        T = dout.shape[0] // (2 if ctx.pair else 1)
         dev = dout.device
         dgn = dbn = dtok = None
         if ctx.norm:
@@ -679,7 +691,13 @@ class PatchEmbedFn(torch.autograd.Function):
             dgn, dbn = small[:C], small[C:2 * C]
             dy = torch.empty(T, C, dtype=F32, device=dev)
             dy16 = torch.empty(T, C, dtype=BF16, device=dev)
-            if ctx.fast:
+            if ctx.pair:
+                # d y = LN'(clean half) + LN'(masked half with the blend): the second call adds the first through dres
+                ops.lnr_bwd(y, nw, nb, 1e-5, stats[:T], stats[T:], dout[T:], dx=dy, dgamma=dgn, dbeta=dbn)
+                ops.lnr_bwd(y, nw, nb, 1e-5, stats[:T], stats[T:], dout[:T], dx=dy, dres=dy, dx_bf16=dy16, dgamma=dgn, dbeta=dbn,
+                            blend=(mask, token), dtoken=small[2 * C:])
+                blend = True
+            elif ctx.fast:
                 blend = (mask, token) if mask is not None else None
                 ops.lnr_bwd(y, nw, nb, 1e-5, stats[:T], stats[T:], dout, dx=dy, dx_bf16=dy16, dgamma=dgn, dbeta=dbn,
                             blend=blend, dtoken=small[2 * C:] if blend else None)
@@ -694,7 +712,7 @@ class PatchEmbedFn(torch.autograd.Function):
             dy16 = ops.to_bf16(dout)
         dW, dB = _wgrad(dy16, cols, C, cols.shape[1], want_bias=True, wkey=ctx.pkeys[0], bkey=ctx.pkeys[1], wshape=ctx.wshape)
         dW = dW.view(ctx.wshape)
-        return None, dW, dB, dgn, dbn, None, dtok, None, None
+        return None, dW, dB, dgn, dbn, None, dtok, None, None, None
 
 
 class PatchMergeFn(torch.autograd.Function):

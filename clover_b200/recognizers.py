@@ -198,9 +198,14 @@ class CloverPretrain(BaseRecognizer):
     select_mlm_rows = True
 
     def _forward_train_batched(self, imgs, token_ids, text_mask, mlm_label, v_token_mask, B, L, H, mlm_rows=None):
-        imgs2 = torch.cat([imgs, imgs], 0)
-        vmask2 = torch.cat([v_token_mask, torch.zeros_like(v_token_mask)], 0)
-        tok2, (B2, T, h, w) = self.backbone.forward_tokens(imgs2, vmask2)           # [masked ; clean] fp32 [2B*T*hw, C]
+        pe = getattr(self.backbone, "patch_embed", None)
+        if pe is not None and hasattr(pe, "pair_supported") and pe.pair_supported(imgs, v_token_mask):
+            # both passes see the same clips: one patch gather + projection, two LayerNorm / blend evaluations
+            tok2, (B2, T, h, w) = self.backbone.forward_tokens(imgs, v_token_mask, pair=True)
+        else:
+            imgs2 = torch.cat([imgs, imgs], 0)
+            vmask2 = torch.cat([v_token_mask, torch.zeros_like(v_token_mask)], 0)
+            tok2, (B2, T, h, w) = self.backbone.forward_tokens(imgs2, vmask2)       # [masked ; clean] fp32 [2B*T*hw, C]
         S = h * w
         ids_clean = torch.where(mlm_label == -100, token_ids, mlm_label)
         ids2 = torch.cat([ids_clean, token_ids], 0)                                 # [clean ; masked]

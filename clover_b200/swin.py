@@ -274,8 +274,16 @@ class PatchEmbed3D(nn.Module):
             raise ValueError(f"set_input_normalization: need {self.in_chans} means and stds")
         self.input_norm = (m, 1.0 / s)
 
-    def forward_tokens(self, x, mask=None, mask_token=None):
-        """x fp32 (or uint8 after set_input_normalization) (B, Cin, F, H, W) -> (tokens fp32 [B*D*Hp*Wp, C], (B, D, Hp, Wp))."""
+    def pair_supported(self, x, mask):
+        """Whether forward_tokens(..., pair=True) can share the patch gather / projection between a masked and a clean pass."""
+        if mask is None or self.norm is None or not ops.lnr_supported(self.embed_dim):
+            return False
+        Hp, Wp = -(-x.shape[-2] // self.patch_size[1]), -(-x.shape[-1] // self.patch_size[2])
+        return Hp % mask.shape[-2] == 0 and Wp % mask.shape[-1] == 0
+
+    def forward_tokens(self, x, mask=None, mask_token=None, pair=False):
+        """x fp32 (or uint8 after set_input_normalization) (B, Cin, F, H, W) -> (tokens fp32 [B*D*Hp*Wp, C], (B, D, Hp, Wp)).
+        pair=True: tokens of [masked pass ; clean pass] of the same clips, (2B, D, Hp, Wp)."""
         if mask is not None and self.norm is None:
             raise NotImplementedError("clover_b200: mask-token blend requires patch_norm=True")
         B, _, Fr, H, W = x.shape
@@ -291,8 +299,8 @@ class PatchEmbed3D(nn.Module):
             norm = self.input_norm
         else:
             x = x.float()
-        y = Fn.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, nw, nb, mask, mask_token, self.patch_size, norm)
-        return y, (B, D, Hp, Wp)
+        y = Fn.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, nw, nb, mask, mask_token, self.patch_size, norm, pair)
+        return y, ((2 * B if pair else B), D, Hp, Wp)
 
     def forward(self, x):
         y, (B, D, Hp, Wp) = self.forward_tokens(x)
@@ -398,12 +406,13 @@ class SwinTransformer3D(nn.Module):
         self.load_state_dict(sd, strict=False)
 
     # ---- forward ---------------------------------------------------------------------------------
-    def forward_tokens(self, x, mask=None):
-        """x (B, 3, F, H, W) -> (tokens fp32 [B*D*h*w, C_out] channels-last, (B, D, h, w))."""
+    def forward_tokens(self, x, mask=None, pair=False):
+        """x (B, 3, F, H, W) -> (tokens fp32 [B*D*h*w, C_out] channels-last, (B, D, h, w)).  pair=True (with a mask): the masked
+        and the clean pass of the same clips in one doubled batch [masked ; clean], sharing the patch embedding."""
         tok = getattr(self, "mask_token", None) if mask is not None else None
         if mask is not None and tok is None:
             raise ValueError("SwinTransformer3D: mask given but the backbone was built with mask_token=False")
-        t, (B, D, H, W) = self.patch_embed.forward_tokens(x, mask, tok)
+        t, (B, D, H, W) = self.patch_embed.forward_tokens(x, mask, tok, pair=pair)
         if self.training:                  # all DropPath factors of this pass in one draw (two per block, in block order)
             from . import rng
             ps = [blk.drop_path_rate for layer in self.layers for blk in layer.blocks for _ in range(2) if blk.drop_path_rate > 0]
