@@ -37,8 +37,8 @@ template <bool RS> constexpr int gemm_threads() { return 64 + 32 * GEMM_EPI_WARP
 // with 64 atomics per warp and tile; they are a third arriver on the stage's "empty" barrier.  The tensor pipe, the operand
 // tiles and the accumulator layout are untouched (an extra N = 16 MMA per K step, or 16 extra B columns of ones, cost
 // 6-33 % of these GEMMs), and the separate column-sum pass over dY (5.5 ms per step) disappears.
-template <int BN, bool RS> struct GemmCfg {
-  static constexpr int STAGES = BN == 128 ? 6 : 4;
+template <int BN, bool RS, bool BOX = false> struct GemmCfg {
+  static constexpr int STAGES = BOX ? 3 : (BN == 128 ? 6 : 4);   // BOX: one pipeline stage makes room for the epilogue's row boxes
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = GEMM_EPI_WARPS * 2048;     // per epilogue warp: 32 rows x 64 B staged for TMA stores
@@ -47,6 +47,8 @@ template <int BN, bool RS> struct GemmCfg {
   // store-bound K = 128 shapes), so only the TMA-store instantiations pay for the stage
   static constexpr int SMEM_BASE = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int SMEM_TS = SMEM_BASE + STG_BYTES;
+  static constexpr int BOX_BYTES = GEMM_EPI_WARPS * 4096;     // per epilogue warp: 32 rows x 128 B (64 bf16 columns)
+  static constexpr int SMEM_BOX = SMEM_BASE + BOX_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages
 };
 
@@ -172,31 +174,43 @@ CLV_DEVICE void store_row(void* base, int is_bf16, bool wide, int ncols, const f
 // value -1: decided at run time
 template <int SPEC> struct EpiSpec {
   static constexpr int bias = -1, act = -1, out_pre = -1, gelu_pre = -1, residual = -1, row_scale = -1, scale = -1, atomic = -1,
-                       row_map = -1, wide = -1, out_bf16 = -1, dual = -1, pipe = 0;
+                       row_map = -1, wide = -1, out_bf16 = -1, dual = -1, pipe = 0, box = 0;
 };
 template <> struct EpiSpec<1> {
   static constexpr int bias = 1, act = 1, out_pre = 1, gelu_pre = 0, residual = 0, row_scale = 0, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 1, pipe = 0;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 1, pipe = 0, box = 0;
 };
 template <> struct EpiSpec<2> {
   static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 1, residual = 0, row_scale = 0, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 0;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 0, box = 0;
 };
 template <> struct EpiSpec<3> {      // qkv: + bias, q columns scaled (run-time column count), bf16 out, per-lane stores
   static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = -1, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 1;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 1, box = 0;
 };
 template <> struct EpiSpec<4> {      // activation gradients (dgrad): accumulator -> bf16, nothing else
   static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 1;
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 1, box = 0;
 };
 template <> struct EpiSpec<5> {      // fc2 forward: + bias, (DropPath row scale), + residual, fp32 out through TMA stores
   static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 1, row_scale = -1, scale = 0, atomic = 0,
-                       row_map = 0, wide = 1, out_bf16 = 0, dual = 0, pipe = 0;
+                       row_map = 0, wide = 1, out_bf16 = 0, dual = 0, pipe = 0, box = 0;
 };
 template <> struct EpiSpec<6> {      // proj: + bias, (DropPath row scale), + residual, fp32 out scattered through window_reverse
   static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 1, row_scale = -1, scale = 0, atomic = 0,
-                       row_map = 1, wide = 1, out_bf16 = 0, dual = 0, pipe = 0;
+                       row_map = 1, wide = 1, out_bf16 = 0, dual = 0, pipe = 0, box = 0;
+};
+template <> struct EpiSpec<7> {      // fc2 dgrad with 256-column tiles: the pre-activation rows arrive, and the results leave, as
+  static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 1, residual = 0, row_scale = 0, scale = 0, atomic = 0,   // TMA boxes
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 0, box = 1;
+};
+template <> struct EpiSpec<8> {      // qkv (bias, q-scale) with 256-column tiles, results leave as TMA boxes
+  static constexpr int bias = 1, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = -1, atomic = 0,
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 0, box = 1;
+};
+template <> struct EpiSpec<9> {      // plain dgrad with 256-column tiles, results leave as TMA boxes
+  static constexpr int bias = 0, act = 0, out_pre = 0, gelu_pre = 0, residual = 0, row_scale = 0, scale = 0, atomic = 0,
+                       row_map = 0, wide = 1, out_bf16 = 1, dual = 0, pipe = 0, box = 1;
 };
 #define EPI_IS(field, runtime) (S::field < 0 ? (runtime) : (S::field != 0))
 
@@ -308,19 +322,22 @@ __global__ void __launch_bounds__(gemm_threads<RS>(), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_pre,
                  int M, int N, int K, int k_splits, GemmEpi ep) {
-  using Cfg = GemmCfg<BN, RS>;
   using S = EpiSpec<SPEC>;
+  constexpr bool BOX = S::box == 1;
+  using Cfg = GemmCfg<BN, RS, BOX>;
+  static_assert(!BOX || (BN == 256 && !TS && !RS), "the box epilogue is written for 128 x 256 tiles");
   static_assert(!RS || A_MN == 1, "row sums are implemented for the MN-major A operand of the weight gradients");
   constexpr int STAGES = Cfg::STAGES, A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from the __shared__ array (an integer round-trip would demote every access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sStage = smem + STAGES * STAGE_BYTES;                                 // TS: [16 warps][2 KB], 1024-byte aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + (TS ? Cfg::STG_BYTES : 0));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + (TS ? Cfg::STG_BYTES : (BOX ? Cfg::BOX_BYTES : 0)));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* box_bar = tempty_bar + 3;                                            // BOX: one per epilogue warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
@@ -333,6 +350,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     tma_prefetch_desc(&tma_b);
     if (TS) tma_prefetch_desc(&tma_out);
     if (TS && (ep.tma_out & 2)) tma_prefetch_desc(&tma_pre);
+    if (BOX) {
+      tma_prefetch_desc(&tma_out);
+      if (S::gelu_pre == 1) tma_prefetch_desc(&tma_pre);
+      for (int w = 0; w < GEMM_EPI_WARPS; ++w) mbar_init(&box_bar[w], 1);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], RS ? 1 + GEMM_RS_WARPS : 1);
@@ -476,6 +498,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     constexpr int EC = 16;                           // columns per epilogue step (register budget: 576 threads)
     constexpr int CHUNKS = CPW / EC;
     uint32_t it = 0;
+    [[maybe_unused]] uint32_t box_phase = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const long long mn = t / k_splits;
       const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
@@ -483,6 +506,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       // bias: every lane of a warp needs the SAME 16 values per step -> four broadcast 128-bit loads straight from L1 / L2
       // (one wavefront each); staging the tile's bias in shared memory needed a 512-thread barrier per tile that cost 15 %
       // of a K = 512 GEMM (tools/epi_probe.py)
+      // BOX: this warp's 32 rows x 64 columns of the pre-activation tensor are requested as ONE swizzled TMA box while the tile's
+      // MMAs are still running (the per-lane path reads them as 32-byte row pieces: 32 L1 wavefronts per instruction, the busiest
+      // unit of this epilogue in ncu r02m); the results overwrite the box in place and leave as one TMA store.
+      [[maybe_unused]] uint8_t* box = nullptr;
+      [[maybe_unused]] bool box_live = false;
+      if constexpr (BOX) {
+        box = sStage + (warp - 2) * 4096;
+        const int bcol = n_idx * BN + chalf * CPW, brow = m_idx * BM + quarter * 32;
+        box_live = bcol < N;
+        if (lane == 0 && box_live) {
+          tma_store_wait_read();                       // the previous tile's store has finished reading the box
+          if constexpr (S::gelu_pre == 1) {
+            mbar_expect_tx(&box_bar[warp - 2], 4096);
+            tma_load_2d(box, &tma_pre, &box_bar[warp - 2], bcol, brow);
+          }
+        }
+        if constexpr (S::gelu_pre != 1) __syncwarp();  // every lane may overwrite the box after lane 0's wait
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const long long row = (long long)m_idx * BM + quarter * 32 + lane;
@@ -543,6 +584,66 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (lane == 0 && n0 < N) {
             tma_store_2d(&tma_out, buf, n0, box_row);
             if (dual) tma_store_2d(&tma_pre, stg + 1024, n0, box_row);
+            tma_store_commit();
+          }
+        }
+      } else if constexpr (BOX) {
+        if (box_live) {
+          if constexpr (S::gelu_pre == 1) {
+            mbar_wait(&box_bar[warp - 2], box_phase);
+            box_phase ^= 1;
+          }
+          uint8_t* myrow = box + lane * 128;
+          const int sw = lane & 7;
+          const int nb = n_idx * BN + chalf * CPW;
+#pragma unroll 1
+          for (int c = 0; c < CHUNKS; ++c) {
+            uint32_t r[EC];
+            tmem_ld_32x16(tacc + c * EC, r);
+            uint4* q0 = reinterpret_cast<uint4*>(myrow + (((2 * c) ^ sw) << 4));
+            uint4* q1 = reinterpret_cast<uint4*>(myrow + (((2 * c + 1) ^ sw) << 4));
+            uint32_t o[8];
+            if constexpr (S::gelu_pre == 1) {
+              const uint4 p0 = *q0, p1 = *q1;
+              tmem_ld_wait();
+              const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 t = unpack_bf16(pw[j]);
+                o[j] = pack_bf16(__uint_as_float(r[2 * j]) * gelu_fit_grad(t.x), __uint_as_float(r[2 * j + 1]) * gelu_fit_grad(t.y));
+              }
+            } else {
+              const int n0 = nb + c * EC;
+              [[maybe_unused]] float4 hb[EC / 4];
+              if constexpr (S::bias == 1) {
+#pragma unroll
+                for (int q = 0; q < EC / 4; ++q) hb[q] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + q);
+              }
+              tmem_ld_wait();
+              float v[EC];
+#pragma unroll
+              for (int j = 0; j < EC; ++j) v[j] = __uint_as_float(r[j]);
+              if constexpr (S::bias == 1) {
+#pragma unroll
+                for (int q = 0; q < EC / 4; ++q) {
+                  v[q * 4] += hb[q].x; v[q * 4 + 1] += hb[q].y; v[q * 4 + 2] += hb[q].z; v[q * 4 + 3] += hb[q].w;
+                }
+              }
+              if (EPI_IS(scale, ep.scale_cols > n0)) {
+#pragma unroll
+                for (int j = 0; j < EC; ++j)
+                  if (n0 + j < ep.scale_cols) v[j] *= ep.scale;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            }
+            *q0 = make_uint4(o[0], o[1], o[2], o[3]);
+            *q1 = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_out, box, nb, m_idx * BM + quarter * 32);
             tma_store_commit();
           }
         }
@@ -617,7 +718,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (TS && lane == 0) tma_store_wait_all();      // the stage must outlive the bulk reads; writes drain here
+    if ((TS || BOX) && lane == 0) tma_store_wait_all();      // the stage must outlive the bulk reads; writes drain here
   }
 
   tc_fence_before();
@@ -676,7 +777,8 @@ template <int A_MN, int B_MN, int BN, bool RS = false, bool TS = false, int SPEC
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tp, int M, int N, int K,
                        int k_splits, const GemmEpi& ep, cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<A_MN, B_MN, BN, RS, TS, SPEC>;
-  constexpr int SMEM = TS ? GemmCfg<BN, RS>::SMEM_TS : GemmCfg<BN, RS>::SMEM_BASE;
+  constexpr bool BOX = EpiSpec<SPEC>::box == 1;
+  constexpr int SMEM = BOX ? GemmCfg<BN, RS, true>::SMEM_BOX : (TS ? GemmCfg<BN, RS>::SMEM_TS : GemmCfg<BN, RS>::SMEM_BASE);
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), SMEM)) return rc;
   const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
   const int grid = (int)std::min<long long>(tiles, num_sms());
@@ -697,7 +799,14 @@ static int dispatch_gemm(int a_mn, int b_mn, const CUtensorMap& ta, const CUtens
                          int M, int N, int K, int k_splits, const GemmEpi& ep, cudaStream_t stream) {
   // compile-time epilogues of the two hottest families (EpiSpec); anything else takes the generic kernel
   if (ep.spec == 1 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, true, 1>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
-  if (ep.spec == 2 && !a_mn && b_mn) return launch_gemm<0, 1, BN, false, false, 2>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if constexpr (BN == 256) {
+    if (ep.spec == 7 && !a_mn && b_mn) return launch_gemm<0, 1, 256, false, false, 7>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+    if (ep.spec == 8 && !a_mn && !b_mn) return launch_gemm<0, 0, 256, false, false, 8>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+    if (ep.spec == 9 && !a_mn && b_mn) return launch_gemm<0, 1, 256, false, false, 9>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  }
+  if (ep.spec == 8) return launch_gemm<0, 0, BN, false, false, 3>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if (ep.spec == 9) return launch_gemm<0, 1, BN, false, false, 4>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
+  if ((ep.spec == 2 || ep.spec == 7) && !a_mn && b_mn) return launch_gemm<0, 1, BN, false, false, 2>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.spec == 3 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, false, 3>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.spec == 4 && !a_mn && b_mn) return launch_gemm<0, 1, BN, false, false, 4>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
   if (ep.spec == 5 && !a_mn && !b_mn) return launch_gemm<0, 0, BN, false, true, 5>(ta, tb, to, tp, M, N, K, k_splits, ep, stream);
@@ -813,6 +922,17 @@ extern "C" int clv_gemm_bf16(const void* A, long long lda, int a_mn_major, const
       if (!e->window && ep.tma_out == 1) ep.spec = 5;
       else if (e->window && ep.tma_out == 0) ep.spec = 6;
     }
+  }
+  if (ep.spec == 2 && bn256 && !a_mn_major && b_mn_major && tunable(TUNE_GEMM_BOX, 1)) {
+    // fc2 dgrad on 128 x 256 tiles: pre-activation rows in / results out as 32-row x 64-column TMA boxes (SWIZZLE_128B)
+    if (int rc2 = make_tmap_2d(&to, e->out, 2, N, M, e->ld_out, 64, 32, 128)) return rc2;
+    if (int rc2 = make_tmap_2d(&tp, e->gelu_pre, 2, N, M, e->ld_gelu_pre, 64, 32, 128)) return rc2;
+    ep.spec = 7;
+  } else if ((ep.spec == 3 || ep.spec == 4) && bn256 && !a_mn_major && (ep.spec == 3 ? !b_mn_major : b_mn_major) &&
+             tunable(TUNE_GEMM_BOX, 1) >= 2) {
+    // bias-only (qkv) / plain (dgrad) epilogues on 128 x 256 tiles: results leave as 32-row x 64-column TMA boxes
+    if (int rc2 = make_tmap_2d(&to, e->out, 2, N, M, e->ld_out, 64, 32, 128)) return rc2;
+    ep.spec = ep.spec == 3 ? 8 : 9;
   }
   if (e->rowsum) return bn256 ? dispatch_gemm_rowsum<256>(a_mn_major, b_mn_major, ta, tb, to, tp, M, N, K, k_splits, ep, stream)
                               : dispatch_gemm_rowsum<128>(a_mn_major, b_mn_major, ta, tb, to, tp, M, N, K, k_splits, ep, stream);

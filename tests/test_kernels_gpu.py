@@ -128,6 +128,42 @@ def test_gemm_specialised_epilogues_match_generic(ops):
     assert rel(got[5], (A.float() @ B.float().t() + bias) * rs.repeat_interleave(250)[:, None] + res) < 2e-3
 
 
+def test_gemm_fc2_dgrad_tma_box_epilogue(ops):
+    """fc2 dgrad on 128 x 256 tiles: the epilogue that moves the pre-activation rows in and the results out as swizzled TMA boxes
+    against the per-lane epilogue (bit-identical), incl. a ragged last row tile, and against the fp32 reference."""
+    for M in (40000, 40000 + 77):
+        N, K = 512, 128
+        A, Bt = rnd(M, K, seed=3, dtype=BF16), rnd(K, N, seed=4, scale=0.1, dtype=BF16)
+        pre = rnd(M, N, seed=7, dtype=BF16)
+        outs = []
+        try:
+            for mode in (0, 1):
+                ops.set_tunable("gemm_box", mode)
+                o = torch.full((M, N), float("nan"), dtype=BF16, device="cuda")
+                ops.gemm(A, Bt, o, b_t=True, gelu_pre=pre)
+                outs.append(o)
+        finally:
+            ops.set_tunable("gemm_box", -1)
+        assert torch.equal(outs[0], outs[1]), rel(outs[1], outs[0])
+        p = pre.float().cpu().requires_grad_(True)
+        O.gelu(p).sum().backward()
+        assert rel(outs[1], (A.float() @ Bt.float()).cpu() * p.grad) < 1e-2
+        # bias + q-scale (qkv) and plain dgrad epilogues through the same boxes (gemm_box = 2) vs the per-lane stores
+        Bk, bias = rnd(N, K, seed=5, scale=0.1, dtype=BF16), rnd(N, seed=6)
+        res = []
+        try:
+            for mode in (0, 2):
+                ops.set_tunable("gemm_box", mode)
+                o1 = torch.full((M, N), float("nan"), dtype=BF16, device="cuda")
+                ops.gemm(A, Bk, o1, bias=bias, scale_cols=128, scale=0.125)
+                o2 = torch.full((M, N), float("nan"), dtype=BF16, device="cuda")
+                ops.gemm(A, Bt, o2, b_t=True)
+                res.append((o1, o2))
+        finally:
+            ops.set_tunable("gemm_box", -1)
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 def test_gemm_window_scatter(ops):
     # proj GEMM + window_reverse + roll back + residual, with spatial padding
     B_, D, H, W, Cc = 2, 4, 10, 9, 64

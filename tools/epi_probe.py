@@ -28,6 +28,22 @@ def run(M,N,K,bt,variant):
     print(f"M={M} N={N} K={K} bt={bt} {variant:6s} {t:7.3f} ms {2*M*N*K/t/1e9:7.1f} TFLOP/s", flush=True)
 for v in ("16", "b16", "bG16", "bg16", "p16", "32", "br32"):
     run(100352, 2048, 512, 0, v)
+for box in (1, 0):
+    ops.set_tunable("gemm_box", box)
+    print(f"# gemm_box = {box}")
+    run(100352, 2048, 512, 1, "p16")
+    run(1605632, 512, 128, 1, "p16")
+    run(401408, 1024, 256, 1, "p16")
+for box in (2, 1):
+    ops.set_tunable("gemm_box", box)
+    print(f"# gemm_box = {box} (2: bias-only / plain bf16 epilogues through TMA boxes too)")
+    run(100352, 1536, 512, 0, "b16")
+    run(100352, 2048, 512, 0, "b16")
+    run(100352, 512, 512, 1, "16")
+    run(100352, 512, 2048, 1, "16")
+    run(401408, 768, 256, 0, "b16")
+    run(401408, 256, 1024, 1, "16")
+ops.set_tunable("gemm_box", -1)
 run(100352, 1536, 512, 0, "b16")
 run(100352, 2048, 512, 1, "p16")
 for v in ("16", "bg16", "32"):
