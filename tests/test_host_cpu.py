@@ -121,3 +121,49 @@ def test_param_groups_follow_the_shipped_paramwise_cfg():
     assert abs(g["qa_head.vqa_classifier.1.weight"]["lr"] - 1e-3) < 1e-12 and g["qa_head.vqa_classifier.1.weight"]["weight_decay"] == 0.05
     assert g["text_backbone.bert.embeddings.LayerNorm.weight"]["weight_decay"] == 0.0
     assert len(g) == sum(1 for p in m.parameters() if p.requires_grad)
+
+
+def test_gradient_sink_bookkeeping_cpu():
+    """Host logic of the gradient sinks (clover_b200.functional): a stashed buffer is handed out once as a fresh alias, shapes and
+    32-byte alignment are checked, accumulating sinks are cleared at stash time once their producer asked for zeros."""
+    import torch
+    from clover_b200 import functional as Fn
+    Fn.clear_grad_sinks()
+    p = torch.nn.Parameter(torch.zeros(8, 16))
+    q = torch.nn.Parameter(torch.zeros(16))
+    gp, gq = torch.ones(8, 16), torch.full((16,), 3.0)
+    Fn.stash_grad_sinks([(p, gp), (q, gq)])
+    a = Fn._sink(Fn._pkey(p), p.shape)
+    assert a is not gp and a.data_ptr() == gp.data_ptr() and torch.equal(a, gp)          # alias, not the stashed object
+    assert Fn._sink(Fn._pkey(p), p.shape) is None                                        # consumed: a second use allocates
+    z = Fn._sink(Fn._pkey(q), q.shape, zero=True)
+    assert z.data_ptr() == gq.data_ptr() and float(z.abs().sum()) == 0.0                 # first zero request clears in place
+    gq.fill_(5.0)
+    Fn.stash_grad_sinks([(p, gp), (q, gq)])                                              # ... later stashes clear it in bulk
+    assert float(gq.abs().sum()) == 0.0 and float(gp.sum()) == 128.0
+    assert Fn._sink(Fn._pkey(p), (4, 32)) is None                                        # shape mismatch -> no sink
+    frozen = torch.nn.Parameter(torch.zeros(4), requires_grad=False)
+    assert Fn._pkey(frozen) is None and Fn._sink(None, (4,)) is None
+    Fn.stash_grad_sinks([(q, torch.zeros(17)[1:])])                                      # 4-byte-offset view: not 32-byte aligned
+    assert Fn._sink(Fn._pkey(q), q.shape) is None
+    Fn.clear_grad_sinks()
+
+
+def test_drop_path_predraw_cpu():
+    """rng.predraw_drop_path: one uniform draw serves the following drop_path_scales calls in order; values are 0 or 1 / keep;
+    a call that does not match the pre-drawn sequence falls back to an individual draw."""
+    import torch
+    from clover_b200 import rng
+    torch.manual_seed(3)
+    ps = [0.0, 0.1, 0.1, 0.3, 0.3]
+    rng.predraw_drop_path(64, ps, "cpu")
+    outs = [rng.drop_path_scales(64, p, "cpu") for p in ps]
+    for p, s in zip(ps, outs):
+        keep = 1.0 - p
+        assert s.shape == (64,) and s.is_contiguous()
+        assert bool(((s == 0) | ((s - 1.0 / keep).abs() < 1e-6)).all())
+    assert bool((outs[0] == 1).all())
+    assert 0.4 < float((outs[3] > 0).float().mean()) <= 1.0
+    rng.predraw_drop_path(64, [0.2, 0.2], "cpu")
+    s = rng.drop_path_scales(32, 0.2, "cpu")                                             # other batch size: individual draw
+    assert s.shape == (32,) and not rng._PREDRAWN
