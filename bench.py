@@ -319,7 +319,8 @@ def run_ours(args):
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
-                                                        gradient_as_bucket_view=True, bucket_cap_mb=100)
+                                                        gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb,
+                                                        static_graph=args.static_graph)
         if not args.fp32_allreduce:
             # the reference all-reduces HALF-precision gradients (model.half() + allreduce_grads, core/hooks/
             # mmcv_Fp16OptimizerHook.py:120-122): 0.55 GB per step over NVLink instead of 1.1 GB; masters / Adam stay fp32
@@ -560,6 +561,8 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: 64 for c3, 16 for c4 / c5 = the shipped configs)")
     ap.add_argument("--kernels-only", action="store_true", help="run warm-up + timed steps and exit (short command for ncu captures)")
     ap.add_argument("--fp32-allreduce", action="store_true", help="N > 1: all-reduce fp32 gradient buckets instead of bf16")
+    ap.add_argument("--bucket-mb", type=int, default=100, help="N > 1: DDP gradient bucket size (developer sweep)")
+    ap.add_argument("--static-graph", action="store_true", help="N > 1: DistributedDataParallel(static_graph=True) (developer sweep)")
     ap.add_argument("--no-grad-sinks", action="store_true", help="allocate fresh gradient tensors every step (developer A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg (N = 1, c3)")
