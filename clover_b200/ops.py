@@ -218,12 +218,16 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=None,
 
 
 def wgrad_splits(M, N, K):
-    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K).  Splitting costs a clear of the output and
-    fp32 reductions in L2 instead of plain stores: measured on the BERT gradients (K = 4096 caption tokens,
-    tools/gemm_probe.py) one pass is 2x faster than two halves, so every split keeps at least 4096 of K."""
-    tiles = -(-M // 128) * -(-N // 128)
-    want = max(1, (148 * 2) // tiles)
-    return max(1, min(want, K // 4096))
+    """Split-K factor for a weight-gradient GEMM (few output tiles, very long K): one wave of CTAs (148 SMs, one resident CTA
+    each) over the 128 x 256 tiles the kernel takes when N fills them, 128 x 128 otherwise -- two waves were 18 % slower on
+    the N = 128 stage-1 gradients (tools/gemm_probe.py).  Splitting costs a clear of the output and fp32 reductions in L2
+    instead of plain stores: on the BERT gradients (K = 4096 caption tokens, >= 54 tiles) one pass is faster than two halves,
+    so every split keeps at least 4096 of K (2048 when the tiles fill a quarter of the SMs or less)."""
+    bn = 256 if N % 256 == 0 else 128
+    tiles = -(-M // 128) * -(-N // bn)
+    want = max(1, 148 // tiles)
+    kmin = 2048 if tiles <= 36 else 4096          # a quarter wave or less: two halves of K = 4096 still beat one pass
+    return max(1, min(want, K // kmin))
 
 
 # ------------------------------------------------------------------------------------------------

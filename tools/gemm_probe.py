@@ -35,6 +35,10 @@ SHAPES = [
     (2304, 768, 4096, 1, 1, "", "o32", 1), (2304, 768, 4096, 1, 1, "", "o32", 2), (2304, 768, 4096, 1, 1, "", "o32", 4),
     (768, 768, 4096, 1, 1, "", "o32", 2), (768, 768, 4096, 1, 1, "", "o32", 4), (768, 768, 4096, 1, 1, "", "o32", 8),
     (768, 768, 4096, 1, 1, "", "o32", 16),
+    # stage-1 weight gradients (K = 1.6 M token rows, tiny outputs; tag: K=1605632)
+    (512, 128, 1605632, 1, 1, "", "o32", 74), (512, 128, 1605632, 1, 1, "", "o32", 37), (512, 128, 1605632, 1, 1, "", "o32", 148),
+    (128, 512, 1605632, 1, 1, "", "o32", 74), (128, 512, 1605632, 1, 1, "", "o32", 148), (384, 128, 1605632, 1, 1, "", "o32", 98),
+    (128, 128, 1605632, 1, 1, "", "o32", 296), (128, 128, 1605632, 1, 1, "", "o32", 148),
     (4096, 3072, 768, 0, 0, "bg", "o16", 1), (4096, 768, 3072, 0, 0, "b", "o16", 1), (4096, 2304, 768, 0, 0, "b", "o16", 1),
 ]
 
