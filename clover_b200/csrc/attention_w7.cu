@@ -92,6 +92,7 @@ struct W7FwdArgs {
   __nv_bfloat16* out; float* lse;
   const float* table_t; int table_len, table_ld; int code_off;   // [heads, table_ld] fp32, pre-multiplied by log2 e
   int has_ext, nwin;
+  int early;                    // score MMAs of tile i+1 issued before the O read-out of tile i has been acknowledged
 };
 
 constexpr int W7_FWD_THREADS = 192;
@@ -210,7 +211,10 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (long long u = u_begin; u < u_end; ++u, ++it) {
         const int stage = it & 1;
         mbar_wait(&full_bar[stage], (it >> 1) & 1);
-        mbar_wait(s_free, (it & 1) ^ 1);
+        // early: the score MMAs of this tile are issued straight behind the P V products of the previous one (the tensor pipe runs
+        // them in order, so P has been consumed before S overwrites it): the softmax warps find the scores ready when they return
+        // from the previous tile's O read-out.  Only the P V products below, which overwrite O, wait for that read-out (s_free).
+        if (!a.early) mbar_wait(s_free, (it & 1) ^ 1);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
         const uint32_t k_addr = q_addr + 8192;
@@ -233,6 +237,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         umma_commit(s_full);
         mbar_wait(p_ready, it & 1);
+        if (a.early) mbar_wait(s_free, (it & 1) ^ 1);      // the previous tile's O has been read out of tensor memory
         tc_fence_after();
         const uint32_t tmem_o = tmem_base + a.col_o;
         for (int kk = 0; kk < a.nmma / 16; ++kk)
@@ -1640,6 +1645,9 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
   // (tools/ab_w7_fwd2.py, profiles/r02x_attn_microbench_fwd_generations.jsonl), so it is the default again; w7_fwd2 = 1
   // selects the second generation
   const long long fwd2 = tunable(TUNE_W7_FWD2, 0);
+  // early issue of the next tile's score MMAs: +2.4 % at 392 tokens (one CTA per SM, nothing else hides the MMA latency), neutral to
+  // -1 % at 196 where the second resident CTA already fills the gap (tools/ab_w7_fwd_early.py, profiles/r04a_*)
+  a.early = (int)tunable(TUNE_W7_FWD_EARLY, a.seq >= 392 ? 1 : 0);
   if (fwd2 == 1) {
     a.n_qt = (a.seq + 127) / 128;
     a.tile_rows = a.n_qt == 1 ? a.seq : (a.seq / a.n_qt) / 32 * 32;

@@ -627,6 +627,17 @@ def test_window_attention_w7(ops, dims, shifted, Bc, heads):
             ops.set_tunable("w7_fwd2", -1)
     assert rel(outs[0][0], outs[1][0]) < 2e-3 and rel(outs[0][1], outs[1][1]) < 1e-6
     assert rel(out, outs[1][0]) < 2e-3 and rel(lse, outs[1][1]) < 1e-6
+    # the two issue orders of the forward (w7_fwd_early: score MMAs of the next tile before the O read-out of the current one is
+    # acknowledged) run the same arithmetic: bit-identical results, repeated to shake out ordering hazards
+    for mode in (0, 1):
+        ops.set_tunable("w7_fwd_early", mode)
+        try:
+            for _ in range(3):
+                o_, l_ = torch.full_like(out, float("nan")), torch.empty_like(lse)
+                ops.attention_fwd(qkv, batch, N, heads, hd, o_, l_, w7=spec, **kw)
+                assert torch.equal(o_, outs[0][0]) and torch.equal(l_, outs[0][1])
+        finally:
+            ops.set_tunable("w7_fwd_early", -1)
     (o_ref * dout.float().cpu()).sum().backward()
     dqkv = torch.empty_like(qkv)
     dtab = torch.zeros(2535, heads, dtype=F32, device="cuda")
