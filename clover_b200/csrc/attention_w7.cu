@@ -30,12 +30,19 @@ constexpr int W7_HD = 32;
 constexpr int W7_ROWB = 64;            // bytes per Q/K/V row of one head
 constexpr int W7_XROWB = 32;           // bytes per K-extension row (16 bf16)
 constexpr int W7_TILE = 98;            // rows per tile = two 49-token slabs
-constexpr int W7_SH = 169, W7_SW = 13; // code strides of the configured (., 7, 7) window: (2*7-1)^2 and 2*7-1
+constexpr int W7_SH = 169, W7_SW = 13; // code strides of the reference's bias table for a (., 7, 7) window: (2*7-1)^2 and 2*7-1
+// Strides of the STAGED table the kernels look up (attn_w7_table_kernel re-lays the used depth range out with them): both are
+// unique decodes (PW >= 13, PH >= 12 * PW + 13) and PW = 7, PH = 49 (mod 32), so the staged address of token t = 49 d + 7 h + w
+// is t (mod 32) plus a warp-uniform constant -- the 32 lanes of a warp (32 consecutive query rows forward, key rows backward)
+// hit 32 different banks.  With the reference strides 20-40 % of the lanes collided pairwise and every bias load took two
+// shared-memory wavefronts (ncu: 22.5 M wavefronts for 12.8 M loads, the busiest unit of both kernels).
+constexpr int W7_PH = 497, W7_PW = 39;
+static_assert(W7_PW % 32 == 7 && W7_PH % 32 == 49 % 32 && W7_PW >= 13 && W7_PH >= 12 * W7_PW + 13, "staged-table strides");
 constexpr float W7_LOG2E = 1.4426950408889634f;
 constexpr float W7_LN2 = 0.6931471805599453f;
 
 // code of body column c (two slabs of 49 tokens) relative to the body's first slab
-__host__ __device__ constexpr int w7_code(int c) { return (c / 49) * W7_SH + ((c % 49) / 7) * W7_SW + (c % 7); }
+__host__ __device__ constexpr int w7_code(int c) { return (c / 49) * W7_PH + ((c % 49) / 7) * W7_PW + (c % 7); }
 
 CLV_DEVICE float w7_ex2(float x) {
   float y;
@@ -93,16 +100,23 @@ struct W7FwdArgs {
   const float* table_t; int table_len, table_ld; int code_off;   // [heads, table_ld] fp32, pre-multiplied by log2 e
   int has_ext, nwin;
   int early;                    // score MMAs of tile i+1 issued before the O read-out of tile i has been acknowledged
+  long long* dbg;               // phase-cycle sums (DBG instantiation only)
+  int split_body;               // > 0: the P V products of key bodies [0, split_body) are issued while the softmax still packs the rest
 };
 
 constexpr int W7_FWD_THREADS = 192;
 
-// bias table -> [heads][ld] (ld = len rounded up to 4), times log2 e: one coalesced 10 KB copy per head change
-__global__ void attn_w7_table_kernel(const float* table, float* table_t, int len, int ld, int heads) {
+// bias table -> staged layout [heads][ld], times log2 e: entry (dz + wd - 1) * PH + (dy + 6) * PW + (dx + 6) of head h holds
+// table[(dz + cfg_wd - 1) * 169 + (dy + 6) * 13 + (dx + 6), h] for the 2 wd - 1 depth offsets a wd-deep window can produce
+// (one coalesced 6-30 KB copy per head change in the kernels); padding entries are zero and never read
+__global__ void attn_w7_table_kernel(const float* table, float* table_t, int ld, int heads, int wd, int cfg_wd) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ld * heads) return;
   const int h = idx / ld, x = idx - h * ld;
-  table_t[idx] = x < len ? table[(long long)x * heads + h] * W7_LOG2E : 0.f;
+  const int zz = x / W7_PH, rem = x - zz * W7_PH, yy = rem / W7_PW, xx = rem - yy * W7_PW;
+  const bool used = zz <= 2 * (wd - 1) && yy <= 12 && xx <= 12;
+  const int src = (zz - (wd - 1) + cfg_wd - 1) * W7_SH + yy * W7_SW + xx;
+  table_t[idx] = used ? table[(long long)src * heads + h] * W7_LOG2E : 0.f;
 }
 
 // contiguous unit range of CTA c: consecutive units share the head (slowest index), so the staged table is reloaded
@@ -114,14 +128,29 @@ CLV_DEVICE void w7_unit_range(long long units, long long& u0, long long& u1) {
   u1 = u0 + base + (c < rem ? 1 : 0);
 }
 
+// (tile t, window b, head h) of unit u = (h * batch + b) * n_t + t, advanced incrementally: the 64-bit divisions by run-time
+// values cost several hundred cycles per unit when they sit between two tiles of the softmax warps
+struct W7Idx {
+  int t, b, h;
+  CLV_DEVICE void init(long long u, int n_t, int batch) {
+    t = (int)(u % n_t);
+    const long long bh = u / n_t;
+    b = (int)(bh % batch); h = (int)(bh / batch);
+  }
+  CLV_DEVICE void next(int n_t, int batch) {
+    if (++t == n_t) { t = 0; if (++b == batch) { b = 0; ++h; } }
+  }
+};
+
 // pass 1 on CNT (<= 32) consecutive body columns starting at static column C0: x = s*log2e + bias*log2e; running max
+// (four independent running maxima: a single one is a chain of 98 dependent FMNMX3 per row that the in-order issue cannot hide)
 template <int C0, int CNT, int NREG>
-CLV_DEVICE void w7_fwd_p1(uint32_t (&v)[NREG], const float* tb, float& m) {
+CLV_DEVICE void w7_fwd_p1(uint32_t (&v)[NREG], const float* tb, float (&m)[4]) {
 #pragma unroll
   for (int x = 0; x < CNT; ++x) v[x] = __float_as_uint(fmaf(__uint_as_float(v[x]), W7_LOG2E, tb[-w7_code(C0 + x)]));
 #pragma unroll
-  for (int x = 0; x + 1 < CNT; x += 2) m = w7_max3(m, __uint_as_float(v[x]), __uint_as_float(v[x + 1]));
-  if (CNT & 1) m = fmaxf(m, __uint_as_float(v[CNT - 1]));
+  for (int x = 0; x + 1 < CNT; x += 2) m[(x >> 1) & 3] = w7_max3(m[(x >> 1) & 3], __uint_as_float(v[x]), __uint_as_float(v[x + 1]));
+  if (CNT & 1) m[0] = fmaxf(m[0], __uint_as_float(v[CNT - 1]));
 }
 // pass 2: p = 2^(x - m), partial row sums, packed bf16 pairs
 template <int CNT, int NREG>
@@ -134,6 +163,9 @@ CLV_DEVICE void w7_fwd_p2(const uint32_t (&v)[NREG], float m, float& l0, float& 
   }
 }
 
+// DBG: tools/w7_fwd_phases.py only -- softmax warp 0 of every CTA sums the cycles it spends in each phase of a tile
+// (wait for S, pass 1, pass 2, wait for O, epilogue) into a.dbg[blockIdx.x * 8 ..]
+template <bool DBG>
 __global__ void __launch_bounds__(W7_FWD_THREADS, 2)
 attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv0,
                    const __grid_constant__ CUtensorMap tm_kv1, const __grid_constant__ CUtensorMap tm_qx,
@@ -149,7 +181,8 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* p_ready = bars + 5;
   uint64_t* o_full = bars + 6;
   uint64_t* s_free = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* p_half = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = a.heads * W7_HD;
@@ -160,7 +193,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     if (n1 > 0) tma_prefetch_desc(&tm_kv1);
     if (a.has_ext) { tma_prefetch_desc(&tm_qx); tma_prefetch_desc(&tm_kx0); }
     for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(s_free, 4);
+    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(s_free, 4); mbar_init(p_half, 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, a.tmem_cols);
@@ -174,10 +207,9 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) {
     if (elect_one()) {
       uint32_t it = 0;
-      for (long long u = u_begin; u < u_end; ++u, ++it) {
-        const int t = (int)(u % a.n_qt);
-        const long long bh = u / a.n_qt;
-        const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+      W7Idx ix; ix.init(u_begin, a.n_qt, a.batch);
+      for (long long u = u_begin; u < u_end; ++u, ++it, ix.next(a.n_qt, a.batch)) {
+        const int t = ix.t, b = ix.b, h = ix.h;
         const int stage = it & 1;
         mbar_wait(&empty_bar[stage], ((it >> 1) & 1) ^ 1);
         uint8_t* sQ = smem + stage * stage_bytes;
@@ -236,11 +268,24 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                          make_smem_desc(kx_addr + a.n0 * W7_XROWB, 16, 256, 6), idesc_s1, 1);
         }
         umma_commit(s_full);
-        mbar_wait(p_ready, it & 1);
-        if (a.early) mbar_wait(s_free, (it & 1) ^ 1);      // the previous tile's O has been read out of tensor memory
-        tc_fence_after();
         const uint32_t tmem_o = tmem_base + a.col_o;
-        for (int kk = 0; kk < a.nmma / 16; ++kk)
+        int kk = 0;
+        if (a.split_body > 0) {
+          // the packed probabilities of the first key bodies are complete: their P V products run on the tensor pipe while the
+          // softmax warps exponentiate the remaining bodies (whole 16-key steps only; the straddling step waits for p_ready)
+          mbar_wait(p_half, it & 1);
+          if (a.early) mbar_wait(s_free, (it & 1) ^ 1);
+          tc_fence_after();
+          const int k_half = a.split_body * W7_TILE / 16;
+          for (; kk < k_half; ++kk)
+            umma_bf16_ts(tmem_o, tmem_base + kk * 8, make_smem_desc(v_addr + kk * 1024, 16, 512, 4), idesc_pv, kk > 0);
+          mbar_wait(p_ready, it & 1);
+        } else {
+          mbar_wait(p_ready, it & 1);
+          if (a.early) mbar_wait(s_free, (it & 1) ^ 1);    // the previous tile's O has been read out of tensor memory
+        }
+        tc_fence_after();
+        for (; kk < a.nmma / 16; ++kk)
           umma_bf16_ts(tmem_o, tmem_base + kk * 8, make_smem_desc(v_addr + kk * 1024, 16, 512, 4), idesc_pv, kk > 0);
         umma_commit(o_full);
         umma_commit(&empty_bar[stage]);
@@ -256,10 +301,11 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int n_body = a.seq / W7_TILE;
     int cur_h = -1;
     uint32_t it = 0;
-    for (long long u = u_begin; u < u_end; ++u, ++it) {
-      const int t = (int)(u % a.n_qt);
-      const long long bh = u / a.n_qt;
-      const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+    long long ph[5] = {0, 0, 0, 0, 0};
+    long long tk = 0;
+    W7Idx ix; ix.init(u_begin, a.n_qt, a.batch);
+    for (long long u = u_begin; u < u_end; ++u, ++it, ix.next(a.n_qt, a.batch)) {
+      const int t = ix.t, b = ix.b, h = ix.h;
       const int i = t * W7_TILE + (valid ? r : 0);
       if (h != cur_h) {                       // stage this head's bias column, pre-multiplied by log2 e
         named_bar_sync(1, 128);
@@ -269,31 +315,36 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         named_bar_sync(1, 128);
       }
       // sTable[(code_i + off) - code_j]: per-thread base, static column offsets
-      const float* tb0 = sTable + ((i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7) + a.code_off);
+      const float* tb0 = sTable + ((i / 49) * W7_PH + ((i % 49) / 7) * W7_PW + (i % 7) + a.code_off);
 
+      if constexpr (DBG) tk = clock64();
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      if constexpr (DBG) { const long long c = clock64(); ph[0] += c - tk; tk = c; }
       float m = -1.0e30f, l = 0.f;
       if (warp_active) {
         // ---- pass 1: x = (s + bias) * log2 e written back; row max
         const float* tb = tb0;
+        float m4[4] = {-1.0e30f, -1.0e30f, -1.0e30f, -1.0e30f};
 #pragma unroll 1
-        for (int body = 0; body < n_body; ++body, tb -= 2 * W7_SH) {
+        for (int body = 0; body < n_body; ++body, tb -= 2 * W7_PH) {
           const uint32_t tc = taddr + body * W7_TILE;
           uint32_t va[32], vb[32], vd[2];
           tmem_ld_32x32(tc, va); tmem_ld_wait();
           tmem_ld_32x32(tc + 32, vb);
-          w7_fwd_p1<0, 32>(va, tb, m); tmem_st_32x32(tc, va);
+          w7_fwd_p1<0, 32>(va, tb, m4); tmem_st_32x32(tc, va);
           tmem_ld_wait();
           tmem_ld_32x32(tc + 64, va);
-          w7_fwd_p1<32, 32>(vb, tb, m); tmem_st_32x32(tc + 32, vb);
+          w7_fwd_p1<32, 32>(vb, tb, m4); tmem_st_32x32(tc + 32, vb);
           tmem_ld_wait();
           tmem_ld_32x2(tc + 96, vd);
-          w7_fwd_p1<64, 32>(va, tb, m); tmem_st_32x32(tc + 64, va);
+          w7_fwd_p1<64, 32>(va, tb, m4); tmem_st_32x32(tc + 64, va);
           tmem_ld_wait();
-          w7_fwd_p1<96, 2>(vd, tb, m); tmem_st_32x2(tc + 96, vd[0], vd[1]);
+          w7_fwd_p1<96, 2>(vd, tb, m4); tmem_st_32x2(tc + 96, vd[0], vd[1]);
         }
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         tmem_st_wait();
+        if constexpr (DBG) { const long long c = clock64(); ph[1] += c - tk; tk = c; }
         // ---- pass 2: p = 2^(x - m); packed bf16 P written in place (columns [0, seq/2))
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
@@ -311,6 +362,12 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           w7_fwd_p2<32>(va, m, l0, l1, pk); tmem_st_32x16(tp + 32, pk);
           tmem_ld_wait();
           w7_fwd_p2<2>(vd, m, l0, l1, pk); tmem_st_32x1(tp + 48, pk[0]);
+          if (body + 1 == a.split_body) {       // first key bodies packed: release their P V products
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_half);
+          }
         }
         l = l0 + l1;
         // keys [seq, nmma) of the P V product: zero probabilities
@@ -318,13 +375,16 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_st_32x8(taddr + a.seq / 2, z);
         tmem_st_wait();
       }
+      if (!warp_active && a.split_body > 0 && lane == 0) mbar_arrive(p_half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
+      if constexpr (DBG) { const long long c = clock64(); ph[2] += c - tk; tk = c; }
 
       // ---- epilogue: O / l -> bf16 -> global; lse (natural log)
       mbar_wait(o_full, it & 1);
       tc_fence_after();
+      if constexpr (DBG) { const long long c = clock64(); ph[3] += c - tk; tk = c; }
       if (warp_active) {
         uint32_t o[32];
         tmem_ld_32x32(taddr + a.col_o, o);
@@ -344,6 +404,13 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
+      if constexpr (DBG) { const long long c = clock64(); ph[4] += c - tk; tk = c; }
+    }
+    if constexpr (DBG) {
+      if (quarter == 0 && lane == 0 && a.dbg) {
+        for (int k = 0; k < 5; ++k) a.dbg[(long long)blockIdx.x * 8 + k] = ph[k];
+        a.dbg[(long long)blockIdx.x * 8 + 5] = (long long)it;
+      }
     }
   }
 
@@ -388,7 +455,7 @@ CLV_DEVICE void w7_tmem_st(uint32_t taddr, const uint32_t (&r)[CNT]) {
 }
 __host__ __device__ constexpr int w7_pow2_chunk(int rem) { return rem >= 32 ? 32 : (rem >= 16 ? 16 : (rem >= 8 ? 8 : (rem >= 4 ? 4 : 2))); }
 // table offset of key column c of the window (two 49-token slabs per 98 columns)
-__host__ __device__ constexpr int w7_col_code(int c) { return w7_code(c % 98) + (c / 98) * 2 * W7_SH; }
+__host__ __device__ constexpr int w7_col_code(int c) { return w7_code(c % 98) + (c / 98) * 2 * W7_PH; }
 
 // pass 1 on the static column range [C, END): x = s * log2 e + bias * log2 e written back; running row max
 template <int C, int END>
@@ -470,10 +537,9 @@ attn_w7_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 0) {
     if (elect_one()) {
       uint32_t it = 0;
-      for (long long u = u_begin; u < u_end; ++u, ++it) {
-        const int t = (int)(u % a.n_qt);
-        const long long bh = u / a.n_qt;
-        const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+      W7Idx ix; ix.init(u_begin, a.n_qt, a.batch);
+      for (long long u = u_begin; u < u_end; ++u, ++it, ix.next(a.n_qt, a.batch)) {
+        const int t = ix.t, b = ix.b, h = ix.h;
         const int stage = it & 1;
         mbar_wait(&empty_bar[stage], ((it >> 1) & 1) ^ 1);
         uint8_t* sQ = smem + stage * stage_bytes;
@@ -564,7 +630,7 @@ attn_w7_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         cur_h = h;
         named_bar_sync(1, 256);
       }
-      const float* tb = sTable + ((i / 49) * W7_SH + ((i % 49) / 7) * W7_SW + (i % 7) + a.code_off);
+      const float* tb = sTable + ((i / 49) * W7_PH + ((i % 49) / 7) * W7_PW + (i % 7) + a.code_off);
 
       mbar_wait(s_full, it & 1);
       tc_fence_after();
@@ -699,8 +765,8 @@ template <int C0, int CNT, int NREG>
 CLV_DEVICE void w7_bwd_chunk(const uint32_t (&v)[NREG], const uint32_t (&w)[NREG], const float* tbj, uint32_t* pk, uint32_t* dk) {
 #pragma unroll
   for (int x = 0; x < CNT; x += 2) {
-    const float p0 = w7_ex2(fmaf(__uint_as_float(v[x]), W7_LOG2E, tbj[w7_code((C0 + x) % 98) + ((C0 + x) / 98) * 2 * W7_SH]));
-    const float p1 = w7_ex2(fmaf(__uint_as_float(v[x + 1]), W7_LOG2E, tbj[w7_code((C0 + x + 1) % 98) + ((C0 + x + 1) / 98) * 2 * W7_SH]));
+    const float p0 = w7_ex2(fmaf(__uint_as_float(v[x]), W7_LOG2E, tbj[w7_code((C0 + x) % 98) + ((C0 + x) / 98) * 2 * W7_PH]));
+    const float p1 = w7_ex2(fmaf(__uint_as_float(v[x + 1]), W7_LOG2E, tbj[w7_code((C0 + x + 1) % 98) + ((C0 + x + 1) / 98) * 2 * W7_PH]));
     pk[x >> 1] = pack_bf16(p0, p1);
     dk[x >> 1] = pack_bf16(p0 * __uint_as_float(w[x]), p1 * __uint_as_float(w[x + 1]));
   }
@@ -924,7 +990,7 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
       for (int t = 0; t < a.n_kt; ++t, ++tt) {
         const int j = t * W7_TILE + (valid ? r : 0);
         // sTable[code_i + (off - code_j)]: per-thread base, static query offsets
-        const float* tbj = sTable + (a.code_off - ((j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7)));
+        const float* tbj = sTable + (a.code_off - ((j / 49) * W7_PH + ((j % 49) / 7) * W7_PW + (j % 7)));
         mbar_wait(st_full, tt & 1);
         tc_fence_after();
         if (warp_active) {
@@ -1196,10 +1262,9 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
     if (elect_one()) {
       uint32_t it = 0, tt = 0;
       const uint64_t pol_stream = l2_policy_evict_first();
-      for (long long u = u_begin; u < u_end; ++u, ++it) {
-        const int qh = (int)(u % NH);
-        const long long uu = u / NH;
-        const int b = (int)(uu % a.batch), h = (int)(uu / a.batch);
+      W7Idx ix; ix.init(u_begin, NH, a.batch);
+      for (long long u = u_begin; u < u_end; ++u, ++it, ix.next(NH, a.batch)) {
+        const int qh = ix.t, b = ix.b, h = ix.h;
         const int us = it & 1;
         mbar_wait(&qdo_empty[us], ((it >> 1) & 1) ^ 1);
         uint8_t* sQ = sQdO + us * unit_bytes;
@@ -1272,10 +1337,11 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
       // products of tile g, so the softmax warps exponentiate the first chunk of the next tile while the tensor pipe works
       // through the 16 dQ instructions (they used to idle there, and the pipe idled at the start of every tile).
       if (a.early && G > 0) scores01(0);
+      W7Idx mx; mx.init(u_begin, NH, a.batch);        // (query half, window, head) of the unit of tile g
+      const int h_first = mx.h;
       for (long long g = 0; g < G; ++g) {
         const uint32_t it = (uint32_t)(g / NKT);
         const int t = (int)(g % NKT);
-        const long long u = u_begin + it;
         const int us = it & 1, ts = (int)(g & 1);
         const uint32_t q_addr = smem_u32(sQdO + us * unit_bytes);
         const uint32_t do_addr = q_addr + a.qb_bytes;
@@ -1308,8 +1374,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         umma_commit(dvk_done);
         if (a.early && g + 1 < G) scores01(g + 1);
         if (a.dump_ds == 2) {
-          const int hh = (int)((u / NH) / a.batch), h_first = (int)((u_begin / NH) / a.batch);
-          const int buf = ((int)blockIdx.x * a.ds_spans + (hh - h_first)) * NH + (int)(u % NH);
+          const int buf = ((int)blockIdx.x * a.ds_spans + (mx.h - h_first)) * NH + mx.t;
           const int grow = buf * KSEQ + t * W7_TILE;
           if (a.l2_hint) {
             const uint64_t pol_keep = l2_policy_evict_last();
@@ -1319,8 +1384,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
           }
           tma_store_commit();
         } else if (a.dump_ds) {
-          const long long uu = u / NH;
-          const int grow = (int)((u % NH) * a.ds_half_rows + ((uu % a.batch) * a.heads + (uu / a.batch)) * KSEQ) + t * W7_TILE;
+          const int grow = (int)(mx.t * a.ds_half_rows + ((long long)mx.b * a.heads + mx.h) * KSEQ) + t * W7_TILE;
           for (int q = 0; q < 4; ++q) tma_store_2d(&tm_ds, sDS + q * 16384, q * 64, grow);
           tma_store_commit();
         }
@@ -1333,7 +1397,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         if (a.dump_ds) tma_store_wait_read();     // (the dQ products above were only issued; the stores finish reading first)
         umma_commit(mma2_done);
         umma_commit(&kv_empty[ts]);
-        if (t == NKT - 1) umma_commit(&qdo_empty[us]);
+        if (t == NKT - 1) { umma_commit(&qdo_empty[us]); mx.next(NH, a.batch); }
       }
       if (a.dump_ds) tma_store_wait_all();
     }
@@ -1352,10 +1416,9 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
     const uint32_t total_tiles = (uint32_t)((u_end - u_begin) * NKT);
     bool pend_dq = false;                      // early mode: dQ of the unit that ended with the previous tile still to be read out
     int pend_b = 0, pend_qh = 0, pend_h = 0;
-    for (long long u = u_begin; u < u_end; ++u, ++it) {
-      const int qh = (int)(u % NH);
-      const long long uu = u / NH;
-      const int b = (int)(uu % a.batch), h = (int)(uu / a.batch);
+    W7Idx ix; ix.init(u_begin, NH, a.batch);
+    for (long long u = u_begin; u < u_end; ++u, ++it, ix.next(NH, a.batch)) {
+      const int qh = ix.t, b = ix.b, h = ix.h;
       if (h != cur_h) {
         named_bar_sync(1, 256);
         const float4* src = reinterpret_cast<const float4*>(a.table_t + (long long)h * a.table_ld);
@@ -1365,7 +1428,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
       }
       for (int t = 0; t < NKT; ++t, ++tt) {
         const int j = t * W7_TILE + (valid ? r : 0);
-        const float* tbj = sTable + (a.code_off + qh * 4 * W7_SH - ((j / 49) * W7_SH + ((j % 49) / 7) * W7_SW + (j % 7)));
+        const float* tbj = sTable + (a.code_off + qh * 4 * W7_PH - ((j / 49) * W7_PH + ((j % 49) / 7) * W7_PW + (j % 7)));
 #define W7B2_PUBLISH(BUF)                                                          \
         tmem_st_wait();                                                            \
         fence_proxy_async();                                                       \
@@ -1591,8 +1654,10 @@ static int w7_check(const clv_attn_w7_desc_t* d, const char* who, int max_wd) {
 
 using namespace clv;
 
+// staged table: 2 wd - 1 depth offsets at stride PH, the last one cut after its 13 x 13 block; floats per head, multiple of 4
+static int w7_table_ld(const clv_attn_w7_desc_t* d) { return (2 * (d->wd - 1) * W7_PH + 12 * W7_PW + 13 + 3) & ~3; }
 static long long w7_table_bytes(const clv_attn_w7_desc_t* d) {
-  return ((long long)((d->table_len + 3) & ~3) * d->heads * 4 + 255) / 256 * 256;
+  return ((long long)w7_table_ld(d) * d->heads * 4 + 255) / 256 * 256;
 }
 
 extern "C" long long clv_attention_w7_fwd_workspace_bytes(const clv_attn_w7_desc_t* d) { return d ? w7_table_bytes(d) : 0; }
@@ -1613,15 +1678,15 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
   a.col_o = a.nmma;
   a.units = (long long)d->batch * d->heads * a.n_qt;
   a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse;
-  a.table_len = d->table_len; a.table_ld = (d->table_len + 3) & ~3;
+  a.table_len = d->table_len; a.table_ld = w7_table_ld(d);
   {
     float* tt = reinterpret_cast<float*>(workspace);
     const int n = a.table_ld * d->heads;
-    attn_w7_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d->bias_table, tt, a.table_len, a.table_ld, d->heads);
+    attn_w7_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d->bias_table, tt, a.table_ld, d->heads, d->wd, d->cfg_wd);
     if (int rc = after_launch("attn_w7_table_kernel")) return rc;
     a.table_t = tt;
   }
-  a.code_off = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;
+  a.code_off = (d->wd - 1) * W7_PH + 6 * W7_PW + 6;            // staged-table offset of (dz, dy, dx) = 0
   a.has_ext = d->q_ext != nullptr; a.nwin = d->nwin > 0 ? d->nwin : 1;
   const long long rows = (long long)d->batch * a.seq;
   const long long ld = 3LL * d->heads * W7_HD;
@@ -1645,9 +1710,9 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
   // (tools/ab_w7_fwd2.py, profiles/r02x_attn_microbench_fwd_generations.jsonl), so it is the default again; w7_fwd2 = 1
   // selects the second generation
   const long long fwd2 = tunable(TUNE_W7_FWD2, 0);
-  // early issue of the next tile's score MMAs: +2.4 % at 392 tokens (one CTA per SM, nothing else hides the MMA latency), neutral to
-  // -1 % at 196 where the second resident CTA already fills the gap (tools/ab_w7_fwd_early.py, profiles/r04a_*)
-  a.early = (int)tunable(TUNE_W7_FWD_EARLY, a.seq >= 392 ? 1 : 0);
+  // early issue of the next tile's score MMAs + split P V products: together -2 % at 196 tokens, -3.6 % at 392 (one CTA per SM,
+  // nothing else hides the MMA latency); each alone is neutral at 196 (tools/ab_w7_fwd_early.py, profiles/r04b_*)
+  a.early = (int)tunable(TUNE_W7_FWD_EARLY, 1);
   if (fwd2 == 1) {
     a.n_qt = (a.seq + 127) / 128;
     a.tile_rows = a.n_qt == 1 ? a.seq : (a.seq / a.n_qt) / 32 * 32;
@@ -1662,12 +1727,22 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
     kern<<<grid2, W7_FWD2_THREADS, smem2, stream>>>(tq, tkv0, tkv1, tqx, tkx0, tkx1, a);
     return after_launch("attn_w7_fwd2_kernel");
   }
-  const size_t smem = 1024 + 2 * stage + (size_t)a.table_ld * 4 + 9 * 8 + 16;
+  const size_t smem = 1024 + 2 * stage + (size_t)a.table_ld * 4 + 10 * 8 + 16;
   CLV_REQUIRE(smem <= 227 * 1024, "attention_w7_fwd: %zu bytes of shared memory needed", smem);
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_w7_fwd_kernel), (int)smem)) return rc;
   const int per_sm = (a.tmem_cols == 256 && smem <= 113 * 1024) ? 2 : 1;
   const int grid = (int)std::min<long long>(a.units, (long long)num_sms() * per_sm);
-  attn_w7_fwd_kernel<<<grid, W7_FWD_THREADS, smem, stream>>>(tq, tkv0, tkv1, tqx, tkx0, tkx1, a);
+  {   // w7_fwd_pvsplit: 0 off, 1 (default) split after half of the key bodies (never for a single body)
+    const int n_body = a.seq / W7_TILE;
+    a.split_body = (tunable(TUNE_W7_FWD_PVSPLIT, 1) == 1 && n_body >= 2) ? n_body / 2 : 0;
+  }
+  a.dbg = reinterpret_cast<long long*>(tunable(TUNE_W7_FWD_DBG, 0));        // device buffer of grid * 8 int64 (tools only)
+  if (a.dbg) {
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_w7_fwd_kernel<true>), (int)smem)) return rc;
+    attn_w7_fwd_kernel<true><<<grid, W7_FWD_THREADS, smem, stream>>>(tq, tkv0, tkv1, tqx, tkx0, tkx1, a);
+    return after_launch("attn_w7_fwd_kernel<dbg>");
+  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_w7_fwd_kernel<false>), (int)smem)) return rc;
+  attn_w7_fwd_kernel<false><<<grid, W7_FWD_THREADS, smem, stream>>>(tq, tkv0, tkv1, tqx, tkx0, tkx1, a);
   return after_launch("attn_w7_fwd_kernel");
 }
 
@@ -1712,15 +1787,15 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
   }
   a.units = (long long)d->batch * d->heads * (halves ? 2 : 1);
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.q_scale = q_scale;
-  a.table_len = d->table_len; a.table_ld = (d->table_len + 3) & ~3;
+  a.table_len = d->table_len; a.table_ld = w7_table_ld(d);
   {
     float* tt = reinterpret_cast<float*>(workspace);
     const int n = a.table_ld * d->heads;
-    attn_w7_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d->bias_table, tt, a.table_len, a.table_ld, d->heads);
+    attn_w7_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d->bias_table, tt, a.table_ld, d->heads, d->wd, d->cfg_wd);
     if (int rc = after_launch("attn_w7_table_kernel")) return rc;
     a.table_t = tt;
   }
-  a.code_off = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;
+  a.code_off = (d->wd - 1) * W7_PH + 6 * W7_PW + 6;            // staged-table offset of (dz, dy, dx) = 0
   a.has_kx = d->k_ext != nullptr; a.nwin = d->nwin > 0 ? d->nwin : 1;
   a.pipe = (int)tunable(TUNE_W7_PIPE, 1);
   const long long rows = (long long)d->batch * a.seq;
@@ -1794,10 +1869,11 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     attn_w7_dkv_combine_kernel<<<g, 256, 0, stream>>>(a.dqkv, a.dkv_part, rows, d->heads * W7_HD);
     if (int rc = after_launch("attn_w7_dkv_combine_kernel")) return rc;
   }
+  const int code_off_ref = (d->cfg_wd - 1) * W7_SH + 6 * W7_SW + 6;     // the gradient is scattered in the reference's table layout
   if (dbias_table && a.dump_ds == 2) {
     dim3 g((a.seq * (a.nq / 8) + 255) / 256, d->heads, nh);
     attn_w7_dbias_acc_kernel<<<g, 256, 0, stream>>>(ds_out, grid, a.units, d->batch, d->heads, nh, a.ds_spans, a.seq, a.nq,
-                                                    halves ? 196 : a.seq, a.code_off, dbias_table);
+                                                    halves ? 196 : a.seq, code_off_ref, dbias_table);
     if (int rc = after_launch("attn_w7_dbias_acc_kernel")) return rc;
   } else if (dbias_table) {
     const int pos_blocks = (a.seq * (a.nq / 8) + 255) / 256;
@@ -1805,7 +1881,7 @@ extern "C" int clv_attention_w7_bwd(const clv_attn_w7_desc_t* d, const void* qkv
     dim3 g(pos_blocks, d->heads, zsplit);
     for (int qh = 0; qh < (halves ? 2 : 1); ++qh) {
       attn_w7_dbias_kernel<<<g, 256, 0, stream>>>(ds_out + (long long)qh * a.ds_half_rows * a.nq, d->batch, d->heads, a.seq, a.nq,
-                                                 halves ? 196 : a.seq, a.code_off + qh * 4 * W7_SH, dbias_table);
+                                                 halves ? 196 : a.seq, code_off_ref + qh * 4 * W7_SH, dbias_table);
       if (int rc = after_launch("attn_w7_dbias_kernel")) return rc;
     }
   }

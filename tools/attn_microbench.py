@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--which", default="fwd,bwd")
     ap.add_argument("--shifted", type=int, default=1)
     ap.add_argument("--dbias", type=int, default=1, help="0: backward without the bias-table gradient (no dS dump)")
+    ap.add_argument("--phases", type=int, default=0, help="1: per-phase cycle sums of the forward's softmax warp (w7_fwd_dbg instantiation)")
     ap.add_argument("--clips", type=int, default=0, help="override the clip count of every shape (c3 batches 128 clip-passes)")
     args = ap.parse_args()
     from clover_b200 import ops, swin, tables
@@ -78,6 +79,19 @@ def main():
             fl = flops_f if which == "fwd" else 2 * flops_f
             row[which + "_ms"] = round(ms, 4)
             row[which + "_tflops"] = round(fl / ms / 1e9, 1)
+        if args.phases:
+            dbg = torch.zeros(296 * 8, dtype=torch.int64, device=dev)
+            ops.set_tunable("w7_fwd_dbg", dbg.data_ptr())
+            try:
+                ops.attention_fwd(qkv, batch, N, heads, hd, out, lse, **kw)
+                torch.cuda.synchronize()
+            finally:
+                ops.set_tunable("w7_fwd_dbg", -1)
+            d = dbg.view(296, 8).cpu().double()
+            d = d[d[:, 5] > 0]
+            per_tile = (d[:, :5].sum(0) / d[:, 5].sum()).tolist()
+            row["fwd_phase_cycles_per_tile"] = dict(zip(["wait_s", "pass1", "pass2", "wait_o", "epilogue"], [round(x) for x in per_tile]))
+            row["fwd_tiles_per_cta"] = round(float(d[:, 5].mean()), 1)
         res.append(row)
         print(json.dumps(row), flush=True)
     return res
