@@ -317,6 +317,18 @@ CLV_DEVICE bool gemm_chunk_math(const GemmEpi& ep, uint32_t taddr, int n0, int N
   return true;
 }
 
+// tile t -> (K split, n tile, m tile), t = (m * num_n + n) * k_splits + split.  32-bit unsigned divisions (the launcher checks
+// the tile count): the 64-bit forms cost two ~300-cycle subroutine calls per tile in every role, on the critical path of the
+// epilogue warps of the K <= 512 GEMMs.
+CLV_DEVICE void gemm_tile_coords(uint32_t t, int k_splits, int num_n, int& split, int& n_idx, int& m_idx) {
+  uint32_t mn = t;
+  split = 0;
+  if (k_splits != 1) { mn = t / (uint32_t)k_splits; split = (int)(t - mn * (uint32_t)k_splits); }
+  const uint32_t m = mn / (uint32_t)num_n;
+  m_idx = (int)m;
+  n_idx = (int)(mn - m * (uint32_t)num_n);
+}
+
 template <int A_MN, int B_MN, int BN, bool RS, bool TS, int SPEC>
 __global__ void __launch_bounds__(gemm_threads<RS>(), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -376,9 +388,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int split = (int)(t % k_splits);
-        const long long mn = t / k_splits;
-        const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
+        int split, n_idx, m_idx;
+        gemm_tile_coords((uint32_t)t, k_splits, num_n, split, n_idx, m_idx);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(num_kb, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -412,7 +423,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       uint32_t it = 0;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int split = (int)(t % k_splits);
+        const int split = k_splits == 1 ? 0 : (int)((uint32_t)t % (uint32_t)k_splits);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(num_kb, kb0 + kb_per_split);
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -449,9 +460,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int split = (int)(t % k_splits);
-        const long long mn = t / k_splits;
-        const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
+        int split, n_idx, m_idx;
+        gemm_tile_coords((uint32_t)t, k_splits, num_n, split, n_idx, m_idx);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(num_kb, kb0 + kb_per_split);
         // the num_n tiles that share this A panel split its K blocks between them (kb % num_n == n_idx), so no tile's
@@ -500,8 +510,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t it = 0;
     [[maybe_unused]] uint32_t box_phase = 0;
     for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const long long mn = t / k_splits;
-      const int n_idx = (int)(mn % num_n), m_idx = (int)(mn / num_n);
+      int split_unused, n_idx, m_idx;
+      gemm_tile_coords((uint32_t)t, k_splits, num_n, split_unused, n_idx, m_idx);
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       // bias: every lane of a warp needs the SAME 16 values per step -> four broadcast 128-bit loads straight from L1 / L2
       // (one wavefront each); staging the tile's bias in shared memory needed a 512-thread barrier per tile that cost 15 %
@@ -781,6 +791,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   constexpr int SMEM = BOX ? GemmCfg<BN, RS, true>::SMEM_BOX : (TS ? GemmCfg<BN, RS>::SMEM_TS : GemmCfg<BN, RS>::SMEM_BASE);
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), SMEM)) return rc;
   const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
+  CLV_REQUIRE(tiles < (1LL << 31), "clv_gemm_bf16: %lld tiles exceed the 32-bit tile index of the kernel", tiles);
   const int grid = (int)std::min<long long>(tiles, num_sms());
   kern<<<grid, gemm_threads<RS>(), SMEM, stream>>>(ta, tb, to, tp, M, N, K, k_splits, ep);
   return after_launch("gemm_bf16_kernel launch");

@@ -34,7 +34,11 @@ def main():
     ap.add_argument("--dbias", type=int, default=1, help="0: backward without the bias-table gradient (no dS dump)")
     ap.add_argument("--phases", type=int, default=0, help="1: per-phase cycle sums of the forward's softmax warp (w7_fwd_dbg instantiation)")
     ap.add_argument("--clips", type=int, default=0, help="override the clip count of every shape (c3 batches 128 clip-passes)")
+    ap.add_argument("--lib", default=None, help="another build of libclover_b200.so (same-box A/B)")
     args = ap.parse_args()
+    if args.lib:
+        from clover_b200 import _lib
+        _lib.set_library(args.lib)
     from clover_b200 import ops, swin, tables
     dev = torch.device("cuda")
     res = []
