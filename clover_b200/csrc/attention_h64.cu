@@ -35,6 +35,16 @@ CLV_DEVICE float h64_ex2(float x) {
   return y;
 }
 
+// unit u = (h * batch + b) * n_tiles + t with 32-bit divisions (the launchers check the unit count; the 64-bit forms are
+// ~300-cycle subroutine calls between two tiles of every role)
+CLV_DEVICE void h64_unit(uint32_t u, int n_tiles, int batch, int& t, int& b, int& h) {
+  const uint32_t bh = u / (uint32_t)n_tiles;
+  t = (int)(u - bh * (uint32_t)n_tiles);
+  const uint32_t hh = bh / (uint32_t)batch;
+  h = (int)hh;
+  b = (int)(bh - hh * (uint32_t)batch);
+}
+
 struct H64Args {
   int batch, seq, heads;
   int nk;                        // forward: keys padded to a multiple of 32
@@ -111,9 +121,8 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     if (elect_one()) {
       uint32_t it = 0;
       for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
-        const int t = (int)(u % a.n_tiles);
-        const long long bh = u / a.n_tiles;
-        const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+        int t, b, h;
+        h64_unit((uint32_t)u, a.n_tiles, a.batch, t, b, h);
         const uint32_t stage = it % nst, phase = (it / nst) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sQ = smem + stage * stage_bytes;
@@ -168,9 +177,8 @@ attn64_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     int cur_b = -1;
     uint32_t it = 0;
     for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
-      const int t = (int)(u % a.n_tiles);
-      const long long bh = u / a.n_tiles;
-      const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+      int t, b, h;
+      h64_unit((uint32_t)u, a.n_tiles, a.batch, t, b, h);
       const int i = t * 128 + r;
       const bool valid = i < a.seq;
       const bool warp_active = (t * 128 + quarter * 32) < a.seq;
@@ -315,9 +323,8 @@ attn64_bwd_kernel(const __grid_constant__ CUtensorMap tm_tile, const __grid_cons
     if (elect_one()) {
       uint32_t it = 0, cc = 0;
       for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
-        const int t = (int)(u % a.n_tiles);
-        const long long bh = u / a.n_tiles;
-        const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+        int t, b, h;
+        h64_unit((uint32_t)u, a.n_tiles, a.batch, t, b, h);
         const int row0 = b * a.seq;
         const uint32_t us = it & 1;
         mbar_wait(&tile_empty[us], ((it >> 1) & 1) ^ 1);
@@ -389,12 +396,12 @@ attn64_bwd_kernel(const __grid_constant__ CUtensorMap tm_tile, const __grid_cons
     long long cur_bh = -1;
     uint32_t it = 0, cc = 0, nvec = 0;
     for (long long u = blockIdx.x; u < a.units; u += gridDim.x, ++it) {
-      const int t = (int)(u % a.n_tiles);
-      const long long bh = u / a.n_tiles;
-      const int b = (int)(bh % a.batch), h = (int)(bh / a.batch);
+      int t, b, h;
+      h64_unit((uint32_t)u, a.n_tiles, a.batch, t, b, h);
       const int row = t * 128 + r;                          // key index j (dK|dV kernel) or query index i (dQ kernel)
       const bool valid = row < a.seq;
       const long long stat = ((long long)b * a.heads + h) * a.seq;
+      const long long bh = (long long)h * a.batch + b;
       // ---- per-(b,h) column vectors, double-buffered so that a unit never waits for the previous one's readers
       if (bh != cur_bh) {
         nvec ^= 1;
@@ -541,6 +548,7 @@ extern "C" int clv_attention_fwd_tc64(const clv_attn_desc_t* d, const void* qkv,
   if (int rc = h64_checks(d, "attention_fwd_tc64")) return rc;
   CLV_REQUIRE(qkv && out && lse, "attention_fwd_tc64: null pointer");
   H64Args a; h64_fill(a, d);
+  CLV_REQUIRE(a.units < (1LL << 31), "attention_tc64: %lld units exceed the 32-bit unit index", a.units);
   a.nk = (d->seq + 31) / 32 * 32;
   a.n0 = a.nk <= 256 ? a.nk : ((a.nk / 2 + 15) & ~15);
   a.n1 = a.nk - a.n0;
@@ -577,6 +585,7 @@ extern "C" int clv_attention_bwd_tc64(const clv_attn_desc_t* d, const void* qkv,
   if (int rc = h64_checks(d, "attention_bwd_tc64")) return rc;
   CLV_REQUIRE(qkv && out && dout && lse && dqkv && dsum_ws, "attention_bwd_tc64: null pointer");
   H64Args a; h64_fill(a, d);
+  CLV_REQUIRE(a.units < (1LL << 31), "attention_tc64: %lld units exceed the 32-bit unit index", a.units);
   a.lse_in = lse; a.dsum = dsum_ws; a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.q_scale = q_scale;
   const long long rows = (long long)d->batch * d->seq;
   if (int rc = launch_attn_bwd_prep(out, dout, dsum_ws, rows, d->heads, H64_HD, d->seq, stream)) return rc;

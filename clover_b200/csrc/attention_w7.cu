@@ -101,6 +101,7 @@ struct W7FwdArgs {
   int has_ext, nwin;
   int early;                    // score MMAs of tile i+1 issued before the O read-out of tile i has been acknowledged
   long long* dbg;               // phase-cycle sums (DBG instantiation only)
+  int q_rows;                   // query rows per tile: 98 (two slabs) or 128 (every TMEM lane used; the last tile is ragged)
   int split_body;               // > 0: the P V products of key bodies [0, split_body) are issued while the softmax still packs the rest
 };
 
@@ -219,7 +220,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         uint8_t* sKx = sQx + 4096;
         mbar_expect_tx(&full_bar[stage], 8192 + 2 * a.nmma * W7_ROWB + (a.has_ext ? 4096 + a.nmma * W7_XROWB : 0));
         const int row0 = b * a.seq;
-        tma_load_2d(sQ, &tm_q, &full_bar[stage], h * W7_HD, row0 + t * W7_TILE);
+        tma_load_2d(sQ, &tm_q, &full_bar[stage], h * W7_HD, row0 + t * a.q_rows);
         tma_load_2d(sK, &tm_kv0, &full_bar[stage], C + h * W7_HD, row0);
         tma_load_2d(sV, &tm_kv0, &full_bar[stage], 2 * C + h * W7_HD, row0);
         if (n1 > 0) {
@@ -228,7 +229,7 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         if (a.has_ext) {
           const int xrow0 = (b % a.nwin) * a.seq;
-          tma_load_2d(sQx, &tm_qx, &full_bar[stage], 0, xrow0 + t * W7_TILE);
+          tma_load_2d(sQx, &tm_qx, &full_bar[stage], 0, xrow0 + t * a.q_rows);
           tma_load_2d(sKx, &tm_kx0, &full_bar[stage], 0, xrow0);
           if (n1 > 0) tma_load_2d(sKx + a.n0 * W7_XROWB, &tm_kx1, &full_bar[stage], 0, xrow0 + a.n0);
         }
@@ -296,8 +297,6 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int r = quarter * 32 + lane;
     const int tid = threadIdx.x - 64;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const bool valid = r < W7_TILE;
-    const bool warp_active = quarter * 32 < W7_TILE;
     const int n_body = a.seq / W7_TILE;
     int cur_h = -1;
     uint32_t it = 0;
@@ -306,7 +305,13 @@ attn_w7_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     W7Idx ix; ix.init(u_begin, a.n_qt, a.batch);
     for (long long u = u_begin; u < u_end; ++u, ++it, ix.next(a.n_qt, a.batch)) {
       const int t = ix.t, b = ix.b, h = ix.h;
-      const int i = t * W7_TILE + (valid ? r : 0);
+      // rows of this query tile (the last one may be ragged); a warp whose 32 lanes are all beyond it skips the tile.  Lanes
+      // beyond the tile inside an active warp mirror the warp's first row: same address as lane 0 in every bias load (a
+      // broadcast, no second wavefront -- mirroring row 0 of the tile put them on lane 0's bank with another address)
+      const int rows_t = min(a.q_rows, a.seq - t * a.q_rows);
+      const bool valid = r < rows_t;
+      const bool warp_active = quarter * 32 < rows_t;
+      const int i = t * a.q_rows + (valid ? r : (warp_active ? quarter * 32 : 0));
       if (h != cur_h) {                       // stage this head's bias column, pre-multiplied by log2 e
         named_bar_sync(1, 128);
         const float4* src = reinterpret_cast<const float4*>(a.table_t + (long long)h * a.table_ld);
@@ -1669,7 +1674,12 @@ extern "C" int clv_attention_w7_fwd(const clv_attn_w7_desc_t* d, const void* qkv
   CLV_REQUIRE(qkv && out && lse && workspace, "attention_w7_fwd: null pointer");
   CLV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "attention_w7_fwd: workspace must be 16-byte aligned");
   W7FwdArgs a{};
-  a.batch = d->batch; a.heads = d->heads; a.seq = 49 * d->wd; a.n_qt = d->wd / 2;
+  a.batch = d->batch; a.heads = d->heads; a.seq = 49 * d->wd;
+  // query tiles of 128 rows use every TMEM lane: 7 instead of 8 warp-passes per 196-token window (-4 % where two CTAs share an
+  // SM and the softmax is partly throughput-bound; at 392 tokens -- one CTA per SM, latency-bound -- the ragged fourth tile
+  // costs 0.8 %, so the 98-row tiles stay there; w7_fwd_qtile = 0 / 1 forces 98 / 128; tools/ab_w7_fwd_qtile.py)
+  a.q_rows = tunable(TUNE_W7_FWD_QTILE, a.seq <= 196 ? 1 : 0) == 1 ? 128 : W7_TILE;
+  a.n_qt = (a.seq + a.q_rows - 1) / a.q_rows;
   a.nmma = (a.seq + 15) / 16 * 16;
   a.n0 = a.nmma <= 256 ? a.nmma : 208;
   a.kb_bytes = (a.nmma * W7_ROWB + 1023) / 1024 * 1024;

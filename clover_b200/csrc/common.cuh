@@ -36,7 +36,7 @@ int after_launch(const char* what);
 
 int num_sms();                                            // of the current device (cached per device)
 int ensure_dynamic_smem(const void* kernel, int bytes);   // cudaFuncSetAttribute once per (kernel, device)
-enum Tunable { TUNE_GEMM_BN256_MIN_UNITS = 0, TUNE_W7_PIPE, TUNE_W7_BWD2, TUNE_W7_DBIAS_ACC, TUNE_W7_DBIAS_ACC_MIN_MB, TUNE_W7_FWD2, TUNE_GEMM_TMA_STORE, TUNE_W7_L2_HINT, TUNE_GEMM_SPEC, TUNE_W7_BWD_EARLY, TUNE_GEMM_BOX, TUNE_W7_FWD_EARLY, TUNE_W7_FWD_DBG, TUNE_W7_FWD_PVSPLIT, TUNE_COUNT };
+enum Tunable { TUNE_GEMM_BN256_MIN_UNITS = 0, TUNE_W7_PIPE, TUNE_W7_BWD2, TUNE_W7_DBIAS_ACC, TUNE_W7_DBIAS_ACC_MIN_MB, TUNE_W7_FWD2, TUNE_GEMM_TMA_STORE, TUNE_W7_L2_HINT, TUNE_GEMM_SPEC, TUNE_W7_BWD_EARLY, TUNE_GEMM_BOX, TUNE_W7_FWD_EARLY, TUNE_W7_FWD_DBG, TUNE_W7_FWD_PVSPLIT, TUNE_W7_FWD_QTILE, TUNE_COUNT };
 long long tunable(int id, long long dflt);                // clv_set_tunable overrides (tools only); no getenv in the library
 // D[b,h,i] = <dO_i, O_i> (attention backward preparation), defined in attention.cu
 int launch_attn_bwd_prep(const void* out, const void* dout, float* dsum, long long rows, int heads, int hd, int seq,

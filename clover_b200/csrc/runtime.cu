@@ -68,7 +68,7 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
 // No environment variable is read anywhere in the library.
 static std::atomic<long long> g_tunables[TUNE_COUNT] = {};
 static std::atomic<bool> g_tunable_set[TUNE_COUNT] = {};
-static const char* const TUNE_NAMES[TUNE_COUNT] = {"gemm_bn256_min_units", "w7_pipe", "w7_bwd2", "w7_dbias_acc", "w7_dbias_acc_min_mb", "w7_fwd2", "gemm_tma_store", "w7_l2_hint", "gemm_spec", "w7_bwd_early", "gemm_box", "w7_fwd_early", "w7_fwd_dbg", "w7_fwd_pvsplit"};
+static const char* const TUNE_NAMES[TUNE_COUNT] = {"gemm_bn256_min_units", "w7_pipe", "w7_bwd2", "w7_dbias_acc", "w7_dbias_acc_min_mb", "w7_fwd2", "gemm_tma_store", "w7_l2_hint", "gemm_spec", "w7_bwd_early", "gemm_box", "w7_fwd_early", "w7_fwd_dbg", "w7_fwd_pvsplit", "w7_fwd_qtile"};
 
 long long tunable(int id, long long dflt) {
   return g_tunable_set[id].load(std::memory_order_relaxed) ? g_tunables[id].load(std::memory_order_relaxed) : dflt;

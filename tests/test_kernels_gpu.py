@@ -629,9 +629,11 @@ def test_window_attention_w7(ops, dims, shifted, Bc, heads):
     assert rel(out, outs[1][0]) < 2e-3 and rel(lse, outs[1][1]) < 1e-6
     # the two issue orders of the forward (w7_fwd_early: score MMAs of the next tile before the O read-out of the current one is
     # acknowledged) run the same arithmetic: bit-identical results, repeated to shake out ordering hazards
-    for early, split in ((0, 0), (1, 0), (0, 1), (1, 1)):       # w7_fwd_pvsplit: P V products of the first key bodies issued early
+    # w7_fwd_pvsplit: P V products of the first key bodies issued early; w7_fwd_qtile: 98- or 128-row query tiles
+    for early, split, qtile in ((0, 0, 0), (1, 0, 0), (0, 1, 1), (1, 1, 0), (1, 1, 1), (0, 0, 1)):
         ops.set_tunable("w7_fwd_early", early)
         ops.set_tunable("w7_fwd_pvsplit", split)
+        ops.set_tunable("w7_fwd_qtile", qtile)
         try:
             for _ in range(3):
                 o_, l_ = torch.full_like(out, float("nan")), torch.empty_like(lse)
@@ -640,6 +642,7 @@ def test_window_attention_w7(ops, dims, shifted, Bc, heads):
         finally:
             ops.set_tunable("w7_fwd_early", -1)
             ops.set_tunable("w7_fwd_pvsplit", -1)
+            ops.set_tunable("w7_fwd_qtile", -1)
     (o_ref * dout.float().cpu()).sum().backward()
     dqkv = torch.empty_like(qkv)
     dtab = torch.zeros(2535, heads, dtype=F32, device="cuda")
