@@ -993,7 +993,7 @@ attn_w7_bwd_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_c
         named_bar_sync(1, 256);
       }
       for (int t = 0; t < a.n_kt; ++t, ++tt) {
-        const int j = t * W7_TILE + (valid ? r : 0);
+        const int j = t * W7_TILE + (valid ? r : quarter * 32);     // lanes beyond the tile mirror their warp's first row (broadcast bias loads)
         // sTable[code_i + (off - code_j)]: per-thread base, static query offsets
         const float* tbj = sTable + (a.code_off - ((j / 49) * W7_PH + ((j % 49) / 7) * W7_PW + (j % 7)));
         mbar_wait(st_full, tt & 1);
@@ -1432,7 +1432,7 @@ attn_w7_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q_full, const __grid_
         named_bar_sync(1, 256);
       }
       for (int t = 0; t < NKT; ++t, ++tt) {
-        const int j = t * W7_TILE + (valid ? r : 0);
+        const int j = t * W7_TILE + (valid ? r : quarter * 32);     // lanes beyond the tile mirror their warp's first row (broadcast bias loads)
         const float* tbj = sTable + (a.code_off + qh * 4 * W7_PH - ((j / 49) * W7_PH + ((j % 49) / 7) * W7_PW + (j % 7)));
 #define W7B2_PUBLISH(BUF)                                                          \
         tmem_st_wait();                                                            \
