@@ -40,6 +40,39 @@ def test_product_tables_bit_exact(golden_dir):
             assert np.array_equal(rmap[clip0], np.arange(D * H * W))
 
 
+def _kernel_constants():
+    src = open(os.path.join(ROOT, "clover_b200", "csrc", "attention_w7.cu")).read()
+    m = re.search(r"constexpr int W7_PH = (\d+), W7_PW = (\d+);", src)
+    assert m, "staged-table strides not found in attention_w7.cu"
+    return int(m.group(1)), int(m.group(2))
+
+
+@pytest.mark.parametrize("wd", [2, 4, 6, 8])
+def test_w7_staged_bias_table_layout(golden_dir, wd):
+    """The (wd,7,7) window-attention kernels look the relative-position bias up in a re-laid-out copy of the table
+    (attn_w7_table_kernel / w7_code in csrc/attention_w7.cu: strides W7_PH / W7_PW instead of the reference's 169 / 13).
+    Restated here from the kernel's formulas with the constants read from the source: every (i, j) lookup must land on the
+    entry the reference's relative_position_index names (swin_transformer_3d.py:345-359), inside the staged buffer, and the 32
+    lanes of any warp (32 consecutive rows) must hit 32 different shared-memory banks."""
+    PH, PW = _kernel_constants()
+    cfg_wd, SH, SW = 8, 169, 13
+    N = 49 * wd
+    ref = np.load(os.path.join(golden_dir, "tables.npz"))["rel_index_877"].astype(np.int64)[:N, :N]
+    ld = (2 * (wd - 1) * PH + 12 * PW + 13 + 3) & ~3                    # w7_table_ld
+    x = np.arange(ld)
+    zz, rem = x // PH, x % PH
+    yy, xx = rem // PW, rem % PW
+    used = (zz <= 2 * (wd - 1)) & (yy <= 12) & (xx <= 12)
+    staged = np.where(used, (zz - (wd - 1) + cfg_wd - 1) * SH + yy * SW + xx, -1)   # attn_w7_table_kernel
+    t = np.arange(N)
+    pcode = (t // 49) * PH + ((t % 49) // 7) * PW + t % 7              # w7_code / per-thread base
+    addr = pcode[:, None] - pcode[None, :] + (wd - 1) * PH + 6 * PW + 6  # a.code_off
+    assert addr.min() >= 0 and addr.max() < ld
+    assert np.array_equal(staged[addr], ref)
+    for r0 in range(N - 31):
+        assert len(set((pcode[r0:r0 + 32] % 32).tolist())) == 32
+
+
 def test_library_exports_every_declared_symbol():
     from clover_b200 import _lib
     header = open(os.path.join(ROOT, "include", "clover_b200.h")).read()
