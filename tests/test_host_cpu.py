@@ -73,6 +73,23 @@ def test_w7_staged_bias_table_layout(golden_dir, wd):
         assert len(set((pcode[r0:r0 + 32] % 32).tolist())) == 32
 
 
+def test_tunable_names_match_enum():
+    """clv_set_tunable resolves names by position: the name table in runtime.cu must list exactly the enumerators of
+    common.cuh's Tunable enum, in order, and every name must be accepted by the built library."""
+    csrc = os.path.join(ROOT, "clover_b200", "csrc")
+    enum = re.search(r"enum Tunable \{([^}]*)\}", open(os.path.join(csrc, "common.cuh")).read()).group(1)
+    ids = [e.split("=")[0].strip() for e in enum.split(",") if e.strip()]
+    assert ids[-1] == "TUNE_COUNT"
+    names = re.search(r"TUNE_NAMES\[TUNE_COUNT\] = \{([^}]*)\}", open(os.path.join(csrc, "runtime.cu")).read()).group(1)
+    names = re.findall(r'"([a-z0-9_]+)"', names)
+    assert [i[len("TUNE_"):].lower() for i in ids[:-1]] == names
+    from clover_b200 import _lib
+    lib = _lib.load()
+    for n in names:
+        assert lib.clv_set_tunable(n.encode(), -1) == 0
+    assert lib.clv_set_tunable(b"no_such_knob", 1) != 0
+
+
 def test_library_exports_every_declared_symbol():
     from clover_b200 import _lib
     header = open(os.path.join(ROOT, "include", "clover_b200.h")).read()
