@@ -164,7 +164,7 @@ CLV_DEVICE void w7_fwd_p2(const uint32_t (&v)[NREG], float m, float& l0, float& 
   }
 }
 
-// DBG: tools/w7_fwd_phases.py only -- softmax warp 0 of every CTA sums the cycles it spends in each phase of a tile
+// DBG: tools/attn_microbench.py --phases 1 only (tunable w7_fwd_dbg = device buffer) -- softmax warp 0 of every CTA sums the cycles it spends in each phase of a tile
 // (wait for S, pass 1, pass 2, wait for O, epilogue) into a.dbg[blockIdx.x * 8 ..]
 template <bool DBG>
 __global__ void __launch_bounds__(W7_FWD_THREADS, 2)
