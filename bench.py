@@ -500,7 +500,9 @@ def run_ours(args):
         if os.path.isfile(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": gemm_tflops, "peak": sus,
-                    "unit": "TFLOP/s", "frac": gemm_tflops / sus, "traffic": traffic, "peak_source": f"{src} bf16_tflops_sustained",
+                    "unit": "TFLOP/s", "frac": gemm_tflops / sus, "traffic": traffic,
+                    "traffic_source": "profiles/gemm_traffic.json: ncu dram__bytes_read + write per GEMM launch of this command (r02z launch list), not re-measured in this run",
+                    "peak_source": f"{src} bf16_tflops_sustained",
                     "launches_timed": g[3], "avg_launch_ms": g[2] / max(1, g[3]),
                     "share_of_step": g[2] / (ms_step * prof_steps),
                     "launch_timing": "CUDA events around every launch of the first timed step",
